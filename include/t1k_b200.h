@@ -1,0 +1,149 @@
+/* t1k_b200 — C ABI of the B200-native T1K genotyping hot path (align + EM).
+ *
+ * The reference (mourisl/T1K) has no plugin/FFI layer: the seam is the set of C++ member calls that
+ * Genotyper.cpp / Analyzer.cpp make into SeqSet and Genotyper.  Each entry point
+ * below replaces one of those call sites; the citation names the reference interface it stands for
+ * (paths relative to the reference checkout).  Plain pointers and sizes only; every function returns
+ * an int status (0 = ok) and never aborts the process.  All device work is hand-written sm_100a CUDA;
+ * there is no CPU fallback: without a CUDA device every compute entry point returns T1K_ERR_NO_DEVICE.
+ */
+#ifndef T1K_B200_H
+#define T1K_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  T1K_OK = 0,
+  T1K_ERR_NO_DEVICE = 1,    /* no usable CUDA device */
+  T1K_ERR_CUDA = 2,         /* a CUDA runtime call failed; t1k_last_error() has the text */
+  T1K_ERR_ARG = 3,          /* bad argument (NULL, read longer than T1K_MAX_READ_LEN, non-ACGTN base, ...) */
+  T1K_ERR_UNSUPPORTED = 4,  /* input outside the supported envelope (band wider than T1K_MAX_BAND, scratch overflow) */
+  T1K_ERR_NCCL = 5
+};
+
+#define T1K_MAX_READ_LEN 255
+#define T1K_KMER 11
+
+typedef struct T1KRef T1KRef;               /* allele reference + k-mer index + coverage, resident in HBM */
+typedef struct T1KAssignment T1KAssignment; /* per-read-end overlap lists, resident in HBM */
+
+/* One (read-end, allele) alignment: the result fields of `struct _overlap` (SeqSet.hpp:89-101).
+ * similarity = matchCnt / (readEnd-readStart+1 + seqEnd-seqStart+1 + 2*leftClip + 2*rightClip)
+ * exactly as SeqSet.hpp:2066-2067,2085-2086 compute it (recompute in double on the host). */
+typedef struct {
+  int32_t seqIdx, readStart, readEnd, seqStart, seqEnd, strand, matchCnt, relaxedMatchCnt, leftClip, rightClip;
+} T1KOverlap;
+
+/* One (fragment, allele) entry of the sparse read x allele matrix: `struct _readAssignment`
+ * (Genotyper.hpp:44-56). */
+typedef struct {
+  int32_t alleleIdx, start, end;
+  float weight, qual, adjustWeight;
+} T1KReadAssignment;
+
+/* Reference description.  Replaces Genotyper::InitRefSet -> SeqSet::InputRefSeq (Genotyper.hpp:707-730,
+ * SeqSet.hpp:906-982) for an already de-duplicated allele list (identical sequences collapsed by the
+ * caller, weight++ — Genotyper.hpp:717-725). */
+typedef struct {
+  int32_t n_alleles;
+  const char *bases;        /* concatenated upper-case ACGTN */
+  const int64_t *offset;    /* [n_alleles+1] */
+  const int32_t *exon_ptr;  /* [n_alleles+1] into exon_se pairs */
+  const int32_t *exon_se;   /* (start,end) inclusive, SeqSet.hpp:933-976 */
+  double similarity;        /* -s, SeqSet::SetRefSeqSimilarity (Genotyper.cpp:350) */
+  int32_t relax_intron;     /* --relaxIntronAlign, SeqSet::SetRelaxIntronAlign (Genotyper.cpp:351) */
+  int32_t device;           /* CUDA device ordinal, -1 = current */
+} T1KRefDesc;
+
+const char *t1k_last_error(void);
+int t1k_device_count(int *count);
+
+int t1k_ref_create(const T1KRefDesc *desc, T1KRef **out);
+void t1k_ref_destroy(T1KRef *ref);
+int t1k_ref_n_alleles(const T1KRef *ref);
+
+/* SeqSet::AssignRead for a batch of UNIQUE read-ends (Genotyper.cpp:149,472; Analyzer.cpp:142,476).
+ * bases/off/len: concatenated reads (host memory, pinned or not); weight[i] = number of duplicates
+ * (>=1 adds base coverage, 0 = analyzer mode, SeqSet.hpp:2253).  The result stays on the device. */
+int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const uint32_t *len,
+                     const int32_t *weight, uint32_t n_reads, T1KAssignment **out);
+void t1k_assignment_destroy(T1KAssignment *a);
+/* Host copy, per read in the reference's output order (`assign` of SeqSet.hpp:2300):
+ * row_ptr[n_reads+1] (caller-allocated), ret[n_reads] = AssignRead's return value (count or -1),
+ * records: call once with records==NULL to get *total, then with a buffer of *total entries. */
+int t1k_assignment_fetch(T1KAssignment *a, uint64_t *row_ptr, int32_t *ret, T1KOverlap *records, uint64_t *total);
+
+/* posWeight[].count[consensus base] per base of every allele, concatenated by `offset` (Q11:
+ * the only counter GetSeqMissingBaseCoverage reads, SeqSet.hpp:2727-2731). */
+int t1k_coverage_fetch(T1KRef *ref, int32_t *out /* [offset[n_alleles]] */);
+int t1k_coverage_reset(T1KRef *ref);
+/* SeqSet::GetSeqMissingBaseCoverage(i, 0.01) for every allele (SeqSet.hpp:2717-2755). */
+int t1k_missing_coverage(T1KRef *ref, int32_t *out /* [n_alleles] */);
+
+/* SeqSet::ReadAssignmentToFragmentAssignment + Genotyper::SetReadAssignments for a batch of fragments
+ * (Genotyper.cpp:183-187,542-554; SeqSet.hpp:2310-2655; Genotyper.hpp:778-832).
+ * end1[i]/end2[i] index read-ends of `a` (end2 == NULL: single-end); has_n[i] = either mate holds an N.
+ * Output CSR (library-allocated host memory, free with t1k_free): row_ptr[n_frag+1], entries in the
+ * reference's order. */
+int t1k_pair_batch(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const uint32_t *end2,
+                   const uint8_t *has_n, uint32_t n_frag, int32_t max_assign,
+                   uint64_t **row_ptr, T1KReadAssignment **entries);
+void t1k_free(void *p);
+
+/* Genotyper::QuantifyAlleleEquivalentClass main loop (Genotyper.hpp:1234-1316) on the device.
+ * Rows = read groups, columns = allele equivalence classes. */
+typedef struct {
+  int32_t n_groups, n_ec;
+  const int64_t *row_ptr;      /* [n_groups+1] */
+  const int32_t *col;          /* EC ids, per group in first-appearance order (Genotyper.hpp:1165-1189) */
+  const double *count;         /* readGroupInfo[].count */
+  const int32_t *ec_len;       /* ecInfo[].length */
+  const double *x0;            /* initial ecAbundance0 (sum of member seqWeight) */
+  double min_squarem_alpha;    /* --squaremMinAlpha, 0 = unset */
+  double filter_frac;          /* --frac */
+  /* every-10-iterations mask (Genotyper.hpp:1292-1313); n_alleles = 0 disables it */
+  int32_t n_alleles, n_major, n_gene;
+  const int32_t *ec_allele_ptr, *ec_alleles;   /* members per EC (first = representative) */
+  const int32_t *allele_major, *allele_gene;   /* [n_alleles] */
+} T1KEmProblem;
+
+typedef struct {
+  double *x;              /* [n_ec] final ecAbundance0 */
+  double *ec_read_count;  /* [n_ec] */
+  int32_t iterations;
+} T1KEmResult;
+
+int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device);
+
+/* The whole hot path for one sample: de-duplicate read-ends, align, pair, coalesce read groups,
+ * build equivalence classes, EM (Genotyper.cpp:450-646).  reads are fixed-stride host buffers
+ * (stride bytes per read, '\0'-padded); reads2 == NULL for single-end. */
+typedef struct {
+  int32_t max_assign;          /* -n (2000) */
+  double min_squarem_alpha, filter_frac;
+  const int32_t *seq_weight;   /* [n_alleles] SeqSet::GetSeqWeight */
+  const int32_t *effective_len;/* [n_alleles] SeqSet::GetSeqEffectiveLen (after InitAlleleInfo's adjustment) */
+  const int32_t *allele_major, *allele_gene; int32_t n_major, n_gene;
+} T1KGenotypeParams;
+
+typedef struct {
+  int32_t n_alleles;
+  double *abundance, *ec_abundance;   /* [n_alleles] alleleInfo[].abundance / .ecAbundance */
+  int32_t *equivalent_class;          /* [n_alleles] (-1: no reads) */
+  int32_t *missing_coverage;          /* [n_alleles] */
+  uint8_t *fragment_assigned;         /* [n_frag] */
+  int32_t em_iterations, n_groups, n_ec, assigned_fragments;
+  uint64_t n_unique_ends, n_overlaps, n_assignments;
+  double avg_alleles_per_read;
+  float ms_dedup, ms_align, ms_pair, ms_coalesce, ms_em;   /* device/host phase times of this call */
+} T1KGenotypeResult;
+
+int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t stride, uint32_t n_frag,
+                 const T1KGenotypeParams *params, T1KGenotypeResult *res /* caller-allocated arrays */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,598 @@
+// Lane-level building blocks of the B200 alignment path.  Everything here is per-(read-end, allele)
+// work that one CUDA lane executes; the warp orchestration (tile gather, ordered emission, reductions)
+// lives in t1k_kernels.cuh.  The functions are __host__ __device__ so that tests/host_emu.cpp can run
+// the very same code sequentially on the CPU box (test harness only — the product never calls it).
+//
+// Data layout (HBM):
+//   sequences are 2 bits/base, 32 bases per uint64 word, base i at bits [2i,2i+1] of word i>>5;
+//   A0 C1 G2 T3, N stored as 3 (what nucToNum&3 gives, KmerCode.hpp:99) with a parallel "n2" plane
+//   that holds 01 at N bases (so masks combine with the XOR plane without bit spreading) and, for
+//   alleles, an "ex2" plane with 01 at exonic bases (isValidDiff[].exon, SeqSet.hpp:651-671).
+//   Every allele starts on a word boundary and is followed by >= 1 zero pad word.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define T1K_HD __host__ __device__ __forceinline__
+#define T1K_HDN __host__ __device__
+#else
+#define T1K_HD inline
+#define T1K_HDN
+#endif
+
+namespace t1k {
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef uint16_t u16;
+typedef uint8_t u8;
+
+constexpr int KMER = 11;
+constexpr int RADIUS = 10;          // SeqSet.hpp:763
+constexpr int HIT_LEN_REQ = 31;     // SeqSet.hpp:764
+constexpr int BAND = 5;             // AlignAlgo.hpp:215
+constexpr int RWORDS = 9;           // packed words per read strand plane (255 bases + fetch slack)
+constexpr int MAX_BAND_W = 64;      // widest DP band kept (band = 11 + |lent-lenp| + 2 sentinels)
+constexpr int MAX_EMIT = 48;        // seed overlaps one (strand, allele) group may emit
+constexpr u64 M55 = 0x5555555555555555ull;
+
+struct Posting { u32 idx, off; };
+
+struct RefView {
+  const u64 *seq2, *n2, *ex2;
+  const u64 *wordOff;    // [nAlleles] first word of allele
+  const int32_t *len;    // [nAlleles]
+  const u32 *kstart;     // [4^K + 1]
+  const Posting *post;
+  int32_t *covDiff;      // range-add difference array, indexed by padded base (wordOff*32 + pos)
+  int32_t *covPoint;     // point corrections
+  int32_t nAlleles;
+  double sim;
+  int32_t relax;
+};
+
+struct ReadView {        // one strand of one read-end
+  const u64 *seq2, *n2;  // RWORDS words each
+  int len;
+};
+
+// candidate = seed overlap that passed the similarity filter of GetOverlapsFromRead (SeqSet.hpp:1893-1908)
+struct Cand {
+  int32_t seqIdx, seqStart, seqEnd;
+  u8 readStart, readEnd, strand01, flags;   // strand01: 1 = same strand (+1), 0 = reverse (-1)
+  u16 matchCnt, pad;
+  // filled by the extension stage (SeqSet::ExtendOverlap, SeqSet.hpp:1994-2100)
+  int32_t eSeqStart, eSeqEnd;
+  u8 eReadStart, eReadEnd, leftClip, rightClip;
+  int32_t eMatchCnt, relaxed;
+};
+enum { CF_SEP = 1, CF_NEEDCLIP = 2, CF_RET = 4, CF_INCLUDE = 8 };
+
+// final record kept resident in HBM for pairing: 32 B
+struct Rec {
+  int32_t seqIdx, seqStart, seqEnd;
+  u32 packed;            // readStart | readEnd<<8 | leftClip<<16 | rightClip<<24
+  u32 mcStrand;          // matchCnt | strand01<<31
+  int32_t relaxed;
+  u64 key;               // list-order key (ascending = the reference's output order)
+};
+
+// per-lane scratch in global memory
+constexpr int SCR_OPS = 1024;
+constexpr int SCR_ROWS = 4 * (MAX_BAND_W + 2) * 4;
+constexpr int SCR_DIR = 258 * MAX_BAND_W;
+constexpr int SCR_EMIT = MAX_EMIT * (int)sizeof(Cand);
+constexpr int SCR_CHAIN = 256 * 4;   // a LIS chain has strictly increasing read offsets: <= 245 entries
+constexpr int SCR_BYTES = ((SCR_OPS + SCR_ROWS + SCR_DIR + SCR_EMIT + SCR_CHAIN + 255) / 256) * 256;
+
+struct LaneScratch {
+  u8 *base;
+  T1K_HD u8 *ops() const { return base; }
+  T1K_HD int *rows() const { return (int *)(base + SCR_OPS); }
+  T1K_HD u8 *dir() const { return base + SCR_OPS + SCR_ROWS; }
+  T1K_HD Cand *emit() const { return (Cand *)(base + SCR_OPS + SCR_ROWS + SCR_DIR); }
+  T1K_HD u32 *chain() const { return (u32 *)(base + SCR_OPS + SCR_ROWS + SCR_DIR + SCR_EMIT); }
+};
+
+enum { ERR_BAND = 1, ERR_SCRATCH = 2, ERR_EMIT = 4, ERR_CAND = 8, ERR_STORE = 16, ERR_HITS = 32 };
+
+T1K_HD int popc64(u64 x) {
+#ifdef __CUDA_ARCH__
+  return __popcll(x);
+#else
+  return __builtin_popcountll(x);
+#endif
+}
+T1K_HD int ctz64(u64 x) {
+#ifdef __CUDA_ARCH__
+  return __ffsll((long long)x) - 1;
+#else
+  return __builtin_ctzll(x);
+#endif
+}
+T1K_HD int imin(int a, int b) { return a < b ? a : b; }
+T1K_HD int imax(int a, int b) { return a > b ? a : b; }
+T1K_HD int iabs(int a) { return a < 0 ? -a : a; }
+
+// 32 bases starting at base `pos` (>= 0) of a plane that begins at word w0
+T1K_HD u64 fetch32(const u64 *plane, u64 w0, int pos) {
+  const u64 *p = plane + w0 + (pos >> 5);
+  int sh = (pos & 31) * 2;
+  u64 lo = p[0];
+  if (sh == 0) return lo;
+  return (lo >> sh) | (p[1] << (64 - sh));
+}
+T1K_HD int base2(const u64 *plane, u64 w0, int pos) { return (int)((plane[w0 + (pos >> 5)] >> ((pos & 31) * 2)) & 3); }
+T1K_HD u64 lowmask2(int nBases) { return nBases >= 32 ? ~0ull : ((1ull << (2 * nBases)) - 1); }
+
+// AlignAlgo.hpp:304-305: equal, or either side N
+T1K_HD bool base_eq(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos) {
+  if (base2(R.n2, w0, tpos) | base2(Q.n2, 0, ppos)) return true;
+  return base2(R.seq2, w0, tpos) == base2(Q.seq2, 0, ppos);
+}
+
+// mismatch plane (01 per mismatching column) of 32 columns starting at (tpos+k, ppos+k)
+T1K_HD u64 mm_chunk(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos, int nLeft) {
+  u64 x = fetch32(R.seq2, w0, tpos) ^ fetch32(Q.seq2, 0, ppos);
+  u64 d = (x | (x >> 1)) & M55;
+  d &= ~(fetch32(R.n2, w0, tpos) | fetch32(Q.n2, 0, ppos));
+  return d & lowmask2(nLeft);
+}
+
+// Equal-length global alignment without the DP.  For lent == lenp == n the diagonal is the alignment the
+// reference's traceback returns whenever no gapped path scores strictly higher at any prefix.  A gapped
+// excursion pays >= 4 per gap event plus the lost rows, and can only gain 4 per diagonal mismatch that a
+// shift d (|d| <= BAND) turns into a match; with F_d = number of diagonal mismatches fixed by shift d,
+// sum_d max(0, F_d - 1) <= 1 (always true for <= 3 mismatches) leaves every excursion <= 0
+// (DESIGN.md "Diagonal certificate").  Returns true and the mismatch count if certified.
+T1K_HDN inline bool diag_certified(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos, int n, int &mmOut) {
+  int mm = 0;
+  for (int k = 0; k < n; k += 32) mm += popc64(mm_chunk(R, w0, tpos + k, Q, ppos + k, n - k));
+  mmOut = mm;
+  if (mm <= 3) return true;
+  if (mm > 24) return false;
+  int F[2 * BAND + 1];
+#pragma unroll
+  for (int d = 0; d <= 2 * BAND; ++d) F[d] = 0;
+  for (int k = 0; k < n; k += 32) {
+    u64 m = mm_chunk(R, w0, tpos + k, Q, ppos + k, n - k);
+    while (m) {
+      int p = k + (ctz64(m) >> 1);
+      m &= m - 1;
+#pragma unroll
+      for (int d = -BAND; d <= BAND; ++d) {
+        if (d == 0) continue;
+        int q = p + d;
+        if (q < 0 || q >= n) continue;
+        if (base_eq(R, w0, tpos + q, Q, ppos + p)) ++F[d + BAND];
+      }
+    }
+  }
+  int excess = 0;
+#pragma unroll
+  for (int d = 0; d <= 2 * BAND; ++d) excess += F[d] > 1 ? F[d] - 1 : 0;
+  return excess <= 1;
+}
+
+// AlignAlgo::GlobalAlignment (AlignAlgo.hpp:215-421), one lane, band-only storage:
+// two rolling rows of (m,e) and one direction nibble per band cell
+//   bit0 diagonal predecessor reproduces m, bit1 f >= e, bit2 e opened from m, bit3 f opened from m.
+// Writes the edit ops in forward order to S.ops() (0 M,1 X,2 I,3 D) and returns their count (<0: error).
+T1K_HDN inline int dp_align(const RefView &R, u64 w0, int tpos, int lent, const ReadView &Q, int ppos, int lenp,
+                            const LaneScratch &S, int &err) {
+  u8 *ops = S.ops();
+  if (lent == 0 || lenp == 0) return 0;
+  if (lent == 1 && lenp == 1) { ops[0] = base_eq(R, w0, tpos, Q, ppos) ? 0 : 1; return 1; }
+  int lb = BAND, rb = BAND;
+  if (lent > lenp) rb += lent - lenp; else if (lent < lenp) lb += lenp - lent;
+  const int W = lb + rb + 3;          // columns i-lb-1 .. i+rb+1
+  if (W > MAX_BAND_W || lenp > 256 || lent + lenp + 8 > SCR_OPS) { err |= ERR_BAND; return -1; }
+  const int negInf = (lent + 1) * (lenp + 1) * -4;
+  const int stale = -4 + (lenp + 1) * -4;   // e[0][j], AlignAlgo.hpp:268 (Q5)
+  int *mP = S.rows(), *eP = mP + (MAX_BAND_W + 2), *mC = eP + (MAX_BAND_W + 2), *eC = mC + (MAX_BAND_W + 2);
+  u8 *dir = S.dir();
+  // row 0 window: columns -lb-1 .. rb+1
+  for (int jj = 0; jj < W; ++jj) {
+    int j = jj - lb - 1;
+    if (j < 0 || j > lent) { mP[jj] = negInf; eP[jj] = negInf; }
+    else if (j == 0) { mP[jj] = 0; eP[jj] = 0; }
+    else { mP[jj] = -4 - 4 * j; eP[jj] = stale; }
+  }
+  for (int i = 1; i <= lenp; ++i) {
+    int start = i - lb < 1 ? 1 : i - lb;
+    int end = i + rb > lent ? lent : i + rb;
+    int pb = base2(Q.seq2, 0, ppos + i - 1), pn = base2(Q.n2, 0, ppos + i - 1);
+    int fPrev = negInf, mLeft = negInf;        // f and m of column j-1 in this row
+    u8 *drow = dir + (size_t)i * W;
+    for (int jj = 0; jj < W; ++jj) {
+      int j = i - lb - 1 + jj;
+      int mv, ev, fv;
+      u8 bits = 0;
+      if (j < 0 || j > lent) { mv = ev = fv = negInf; }
+      else if (j == 0) { mv = -4 - 4 * i; ev = -4 - i; fv = -4 - 4 * i; }
+      else if (j < start || j > end) { mv = ev = fv = negInf; }
+      else {
+        // previous row window starts one column earlier: column j is at jj+1, column j-1 at jj
+        int mUp = mP[jj + 1], eUp = eP[jj + 1], mDiag = mP[jj];
+        int e1 = eUp - 1, e2 = mUp - 5;
+        ev = e1 > e2 ? e1 : e2;
+        int f1 = fPrev - 1, f2 = mLeft - 5;
+        fv = f1 > f2 ? f1 : f2;
+        bool eq = pn || base2(R.n2, w0, tpos + j - 1) || base2(R.seq2, w0, tpos + j - 1) == pb;
+        int dv = mDiag + (eq ? 2 : -2);
+        mv = dv;
+        if (ev > mv) mv = ev;
+        if (fv > mv) mv = fv;
+        bits = (u8)((dv == mv ? 1 : 0) | (fv >= ev ? 2 : 0) | (e2 == ev ? 4 : 0) | (f2 == fv ? 8 : 0));
+      }
+      mC[jj] = mv; eC[jj] = ev;
+      drow[jj] = bits;
+      fPrev = fv; mLeft = mv;
+    }
+    // the window of row i must be readable at jj+1 by row i+1
+    mC[W] = negInf; eC[W] = negInf;
+    int *t = mP; mP = mC; mC = t;
+    t = eP; eP = eC; eC = t;
+  }
+  // traceback (AlignAlgo.hpp:323-408); boundary rows/columns by their closed forms
+  int ti = lenp, tj = lent, mat = 0, n = 0;
+  while (ti > 0 || tj > 0) {
+    if (n >= SCR_OPS - 2) { err |= ERR_BAND; return -1; }
+    if (mat == 0) {
+      int a;
+      if (ti > 0 && tj > 0) {
+        u8 b = dir[(size_t)ti * W + (tj - (ti - lb - 1))];
+        if (b & 1) a = base_eq(R, w0, tpos + tj - 1, Q, ppos + ti - 1) ? 0 : 1;
+        else a = (b & 2) ? 3 : 2;
+      } else if (ti == 0) a = (-4 - tj >= stale) ? 3 : 2;
+      else a = 2;                      // tj == 0, ti > 0: f = -4-4ti < e = -4-ti
+      if (a <= 1) { ops[n++] = (u8)a; --ti; --tj; }
+      else mat = a == 2 ? 1 : 2;
+    } else if (mat == 1) {
+      ops[n++] = 2;
+      if (ti > 0) {
+        bool fromM;
+        if (tj == 0) fromM = ti == 1;
+        else fromM = (dir[(size_t)ti * W + (tj - (ti - lb - 1))] & 4) != 0;
+        --ti; mat = fromM ? 0 : 1;
+      } else mat = 2;
+    } else {
+      ops[n++] = 3;
+      if (tj > 0) {
+        bool fromM;
+        if (ti == 0) fromM = tj == 1;
+        else fromM = (dir[(size_t)ti * W + (tj - (ti - lb - 1))] & 8) != 0;
+        --tj; mat = fromM ? 0 : 2;
+      } else mat = 1;
+    }
+  }
+  for (int a = 0, b = n - 1; a < b; ++a, --b) { u8 t = ops[a]; ops[a] = ops[b]; ops[b] = t; }
+  return n;
+}
+
+// number of EDIT_MATCH columns of GlobalAlignment(t, lent, p, lenp)  (GetAlignStats, SeqSet.hpp:438-455)
+T1K_HDN inline int align_matches(const RefView &R, u64 w0, int tpos, int lent, const ReadView &Q, int ppos, int lenp,
+                                 const LaneScratch &S, int &err) {
+  if (lent == 0 || lenp == 0) return 0;
+  if (lent == lenp) {
+    int mm;
+    if (diag_certified(R, w0, tpos, Q, ppos, lent, mm)) return lent - mm;
+  }
+  int n = dp_align(R, w0, tpos, lent, Q, ppos, lenp, S, err);
+  int c = 0;
+  const u8 *ops = S.ops();
+  for (int i = 0; i < n; ++i) c += ops[i] == 0;
+  return c;
+}
+
+// any N of the allele inside [s, e] (clamped to the allele)
+T1K_HD bool n_in_range(const RefView &R, u64 w0, int s, int e) {
+  for (int k = s; k <= e; k += 32)
+    if (fetch32(R.n2, w0, k) & lowmask2(e - k + 1)) return true;
+  return false;
+}
+// IsSeparatorInRange (SeqSet.hpp:487-498): separators are -1, every N, and len
+T1K_HD bool sep_in_range(const RefView &R, u64 w0, int len, int s, int e) {
+  if (s > e) return false;
+  if (s <= -1 || e >= len) return true;
+  return n_in_range(R, w0, s, e);
+}
+
+// IsOverlapLowComplex (SeqSet.hpp:458-485)
+T1K_HD bool low_complex(const ReadView &Q, int s, int e) {
+  int cnt[4] = {0, 0, 0, 0};
+  int n = e - s + 1;
+  for (int k = 0; k < n; k += 32) {
+    u64 w = fetch32(Q.seq2, 0, s + k), nm = fetch32(Q.n2, 0, s + k);
+    u64 keep = ~nm & M55 & lowmask2(n - k);
+    u64 lo = w & M55, hi = (w >> 1) & M55;
+    cnt[0] += popc64(~lo & ~hi & keep);
+    cnt[1] += popc64(lo & ~hi & keep);
+    cnt[2] += popc64(~lo & hi & keep);
+    cnt[3] += popc64(lo & hi & keep);
+  }
+  int low = 0, lowTotal = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) if (cnt[i] <= 2) { ++low; lowTotal += cnt[i]; }
+  if (lowTotal * 7 >= n) return false;
+  return low >= 2;
+}
+
+// hit encoding: readOffset | seqOffset << 8
+T1K_HD int hit_a(u32 h) { return (int)(h & 255); }
+T1K_HD int hit_b(u32 h) { return (int)(h >> 8); }
+T1K_HD bool hit_diag_less(u32 x, u32 y) {   // CompSortHitCoordDiff (SeqSet.hpp:266-274): (a-b, b, a)
+  int cx = hit_a(x) - hit_b(x), cy = hit_a(y) - hit_b(y);
+  if (cx != cy) return cx < cy;
+  return x < y;                              // numeric order of the encoding is (b, a)
+}
+
+// strand-selection key (maximise): the seed overlap that is smallest under _overlap::operator< with
+// similarity 0 (SeqSet.hpp:1619-1627) decides the strand.
+T1K_HD u64 strand_key(int matchCnt, int span, int seqIdx, int strand01) {
+  return ((u64)matchCnt << 40) | ((u64)span << 32) | ((u64)(0xFFFFFFu - (u32)seqIdx) << 1) | (u64)(strand01 ? 0 : 1);
+}
+
+// list-order key, ascending = _overlap::operator< order (matchCnt desc, similarity desc == denominator asc
+// for equal matchCnt, read span desc, seqIdx asc, readStart asc)
+T1K_HD u64 order_key(int matchCnt, int denom, int span, int seqIdx, int readStart) {
+  return ((u64)(2047 - matchCnt) << 53) | ((u64)denom << 41) | ((u64)(255 - span) << 33) | ((u64)seqIdx << 9) |
+         ((u64)readStart << 1);
+}
+
+// ---- chain consumer: GetOverlapsFromHits tail (SeqSet.hpp:1500-1550) + the matchCnt recomputation of
+// GetOverlapsFromRead (SeqSet.hpp:1697-1845).  `C` yields the LIS chain as encoded hits.
+template <class Chain>
+T1K_HDN inline void consume_chain(const RefView &R, const ReadView &Q, int strand01, int seqIdx, const Chain &C, int sz,
+                                  const LaneScratch &S, int &nEmit, u64 &bestStrandKey, int &err) {
+  if (sz * KMER < HIT_LEN_REQ) return;
+  int hitLen = 0, seqLenCov = 0;
+  {
+    int i = 0;
+    while (i < sz) {
+      int j = i + 1;
+      while (j < sz && hit_a(C(j)) <= hit_a(C(j - 1)) + KMER - 1) ++j;
+      hitLen += hit_a(C(j - 1)) - hit_a(C(i)) + KMER;
+      i = j;
+    }
+    if (hitLen < HIT_LEN_REQ) return;
+    i = 0;
+    while (i < sz) {
+      int j = i + 1;
+      while (j < sz && hit_b(C(j)) <= hit_b(C(j - 1)) + KMER - 1) ++j;
+      seqLenCov += hit_b(C(j - 1)) - hit_b(C(i)) + KMER;
+      i = j;
+    }
+    if (seqLenCov < HIT_LEN_REQ) return;
+  }
+  const u64 w0 = R.wordOff[seqIdx];
+  int rs = hit_a(C(0)), re = hit_a(C(sz - 1)) + KMER - 1;
+  int ss = hit_b(C(0)), se = hit_b(C(sz - 1)) + KMER - 1;
+  u64 sk = strand_key(2 * hitLen, re - rs, seqIdx, strand01);
+  if (sk > bestStrandKey) bestStrandKey = sk;
+  int mc = 2 * KMER;
+  for (int j = 1; j < sz; ++j) {
+    int pa = hit_a(C(j - 1)), pb = hit_b(C(j - 1)), a = hit_a(C(j)), b = hit_b(C(j));
+    bool aOv = pa + KMER - 1 >= a, bOv = pb + KMER - 1 >= b;
+    if (pb - pa == b - a) {
+      if (aOv) mc += 2 * (a - pa);
+      else mc += 2 * KMER + 2 * align_matches(R, w0, pb + KMER, b - (pb + KMER), Q, pa + KMER, a - (pa + KMER), S, err);
+    } else if (aOv && !bOv) mc += 2 * (a - pa);
+    else if (!aOv && bOv) mc += 2 * (b - pb);
+    else if (aOv && bOv) mc += 2 * imin(a - pa, b - pb);
+    else mc += 2 * KMER + 2 * align_matches(R, w0, pb + KMER, b - (pb + KMER), Q, pa + KMER, a - (pa + KMER), S, err);
+  }
+  double sim = (double)mc / (double)(se - ss + 1 + re - rs + 1);
+  if (low_complex(Q, rs, re)) sim = 0;
+  if (sim < R.sim) return;
+  if (nEmit >= MAX_EMIT) { err |= ERR_EMIT; return; }
+  Cand &c = S.emit()[nEmit++];
+  c.seqIdx = seqIdx; c.seqStart = ss; c.seqEnd = se;
+  c.readStart = (u8)rs; c.readEnd = (u8)re; c.strand01 = (u8)strand01; c.flags = 0;
+  c.matchCnt = (u16)mc; c.pad = 0;
+}
+
+struct ChainDirect {   // contiguous run of a hit store
+  const u32 *p; int stride;
+  T1K_HD u32 operator()(int i) const { return p[(size_t)i * stride]; }
+};
+
+// ---- SeqSet::GetOverlapsFromHits for one (strand, allele) group (SeqSet.hpp:1303-1553; filter=0, isRef).
+// hits: n encoded hits at h[i*stride]; on entry sorted by (readOffset, seqOffset); sorted in place by diagonal.
+// Scratch use of the general (multi-diagonal) path: conc/chain/top/link live in S.dir().
+T1K_HDN inline void chain_allele(const RefView &R, const ReadView &Q, int strand01, int seqIdx, u32 *h, int stride, int n,
+                                 const LaneScratch &S, int &nEmit, u64 &bestStrandKey, int &err) {
+  if (n < 3) return;
+  // insertion sort by (diag, b, a); a single-diagonal group is already in order
+  for (int i = 1; i < n; ++i) {
+    u32 v = h[(size_t)i * stride];
+    if (!hit_diag_less(v, h[(size_t)(i - 1) * stride])) continue;
+    int j = i - 1;
+    while (j >= 0 && hit_diag_less(v, h[(size_t)j * stride])) { h[(size_t)(j + 1) * stride] = h[(size_t)j * stride]; --j; }
+    h[(size_t)(j + 1) * stride] = v;
+  }
+  int dom = 0;
+  for (int s = 0; s < n;) {
+    int e, cur, curCnt = 1, domCnt = 0, prevC;
+    { u32 v = h[(size_t)s * stride]; cur = hit_a(v) - hit_b(v); prevC = cur; }
+    for (e = s + 1; e < n; ++e) {
+      u32 v = h[(size_t)e * stride];
+      int c = hit_a(v) - hit_b(v);
+      int diff = c - prevC;               // sorted ascending: diff >= 0
+      if (diff > RADIUS) break;
+      if (diff == 0) ++curCnt;
+      else {
+        if (curCnt > domCnt) { dom = cur; domCnt = curCnt; }
+        cur = c; curCnt = 1;
+      }
+      prevC = c;
+    }
+    if (curCnt > domCnt) dom = cur;
+    int m = e - s;
+    if (m < 3 || m * KMER < HIT_LEN_REQ) { s = e; continue; }
+    u32 first = h[(size_t)s * stride], last = h[(size_t)(e - 1) * stride];
+    if (hit_a(first) - hit_b(first) == hit_a(last) - hit_b(last)) {
+      // one diagonal: every read offset occurs once, (b,a) order == current order, LIS keeps everything
+      ChainDirect cd; cd.p = h + (size_t)s * stride; cd.stride = stride;
+      consume_chain(R, Q, strand01, seqIdx, cd, m, S, nEmit, bestStrandKey, err);
+      s = e; continue;
+    }
+    // general path (SeqSet.hpp:1437-1456 + LIS :352-436)
+    if ((size_t)m * 12 + 512 > (size_t)SCR_DIR) { err |= ERR_SCRATCH; s = e; continue; }
+    u16 *used = (u16 *)S.dir();                 // min |diag - dom| per read offset
+    u32 *conc = (u32 *)(S.dir() + 512);
+    u32 *chain = conc + m;
+    u16 *top = (u16 *)(chain + m);
+    u16 *link = top + m;
+    for (int k = s; k < e; ++k) used[hit_a(h[(size_t)k * stride])] = 0xFFFF;
+    for (int k = s; k < e; ++k) {
+      u32 v = h[(size_t)k * stride];
+      int d = iabs(hit_a(v) - hit_b(v) - dom);
+      if (d > 0xFFFE) d = 0xFFFE;
+      if (used[hit_a(v)] > d) used[hit_a(v)] = (u16)d;
+    }
+    int cn = 0;
+    for (int k = s; k < e; ++k) {
+      u32 v = h[(size_t)k * stride];
+      int d = iabs(hit_a(v) - hit_b(v) - dom);
+      if (d > 0xFFFE) d = 0xFFFE;
+      if (d == used[hit_a(v)]) {             // insertion into (b,a) order == numeric order
+        int j = cn - 1;
+        while (j >= 0 && conc[j] > v) { conc[j + 1] = conc[j]; --j; }
+        conc[j + 1] = v; ++cn;
+      }
+    }
+    // LIS over read offsets (non-strict probe, strict extend; Q4)
+    int ret = 1;
+    top[0] = 0; link[0] = 0xFFFF;
+    for (int i = 1; i < cn; ++i) {
+      int ai = hit_a(conc[i]);
+      int tag;
+      if (hit_a(conc[top[ret - 1]]) <= ai) tag = ret - 1;
+      else {
+        int l = 0, r = ret - 1; tag = -2;
+        while (l <= r) {
+          int mid = (l + r) / 2, am = hit_a(conc[top[mid]]);
+          if (ai == am) { tag = mid; break; }
+          if (ai < am) r = mid - 1; else l = mid + 1;
+        }
+        if (tag == -2) tag = l - 1;
+      }
+      if (tag == -1) { top[0] = (u16)i; link[i] = 0xFFFF; }
+      else if (ai > hit_a(conc[top[tag]])) {
+        if (tag == ret - 1) { top[ret] = (u16)i; ++ret; link[i] = top[tag]; }
+        else if (ai < hit_a(conc[top[tag + 1]])) { top[tag + 1] = (u16)i; link[i] = top[tag]; }
+      }
+    }
+    {
+      int k = top[ret - 1];
+      for (int i = ret - 1; i >= 0; --i) { chain[i] = conc[k]; k = link[k]; }
+    }
+    int sz = 0;
+    for (int i = 0; i < ret; ++i)
+      if (i == 0 || hit_b(chain[i]) != hit_b(chain[sz - 1])) chain[sz++] = chain[i];
+    // the chain was built in S.dir(), which consume_chain's gap DPs overwrite: park it in its own region
+    u32 *park = S.chain();
+    if (sz > SCR_CHAIN / 4) { err |= ERR_SCRATCH; s = e; continue; }
+    for (int i = 0; i < sz; ++i) park[i] = chain[i];
+    ChainDirect cd; cd.p = park; cd.stride = 1;
+    consume_chain(R, Q, strand01, seqIdx, cd, sz, S, nEmit, bestStrandKey, err);
+    s = e;
+  }
+}
+
+// ---- SeqSet::ExtendOverlap (SeqSet.hpp:1994-2100) + the separator tests of AssignRead (SeqSet.hpp:2163-2169)
+T1K_HDN inline void extend_cand(const RefView &R, const ReadView &Q, Cand &c, const LaneScratch &S, int &err) {
+  const u64 w0 = R.wordOff[c.seqIdx];
+  const int clen = R.len[c.seqIdx], len = Q.len;
+  int rs = c.readStart, re = c.readEnd, ss = c.seqStart, se = c.seqEnd;
+  u8 flags = 0;
+  if (sep_in_range(R, w0, clen, ss, se)) { c.flags = CF_SEP; return; }
+  if (sep_in_range(R, w0, clen, ss - rs, se + (len - re - 1))) flags |= CF_NEEDCLIP;
+  int lo = imin(rs, ss), leftClip = 0, rightClip = 0;
+  if (rs > ss) leftClip = rs - ss;
+  for (int i = 0; i < lo; ++i)
+    if (base2(R.n2, w0, ss - i - 1)) { leftClip = lo - i; lo = i; break; }
+  int m = align_matches(R, w0, ss - lo, lo, Q, rs - lo, lo, S, err);
+  int ro = imin(len - 1 - re, clen - 1 - se);
+  if (len - 1 - re > clen - 1 - se) rightClip = len - 1 - re - (clen - 1 - se);
+  for (int i = 0; i < ro; ++i)
+    if (base2(R.n2, w0, se + 1 + i)) { rightClip = ro - i; ro = i; break; }
+  m += align_matches(R, w0, se + 1, ro, Q, re + 1, ro, S, err);
+  c.eReadStart = (u8)(rs - lo); c.eReadEnd = (u8)(re + ro);
+  c.eSeqStart = ss - lo; c.eSeqEnd = se + ro;
+  int mc = 2 * m + c.matchCnt;
+  double sim = (double)mc / (double)((re + ro) - (rs - lo) + 1 + (se + ro) - (ss - lo) + 1);
+  if (!(sim < R.sim)) flags |= CF_RET;
+  c.leftClip = (u8)leftClip; c.rightClip = (u8)rightClip;
+  c.relaxed = mc;                                  // SeqSet.hpp:2068 (before the clip bonus)
+  c.eMatchCnt = mc + 2 * leftClip + 2 * rightClip;
+  c.flags = flags;
+}
+
+T1K_HD void cov_add(int32_t *p, int v) {
+#ifdef __CUDA_ARCH__
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+}
+
+// ---- full-read alignment of an extended overlap (SeqSet.hpp:2203-2274): exon-relaxed match count and
+// base coverage.  Coverage is kept as a range-add difference array plus point corrections, so a
+// certified-diagonal record costs 2 + (#uncredited columns) atomics instead of one per base.
+T1K_HDN inline void full_align(const RefView &R, const ReadView &Q, Cand &c, int weight, const LaneScratch &S, int &err) {
+  const u64 w0 = R.wordOff[c.seqIdx];
+  const int tpos = c.eSeqStart, ppos = c.eReadStart;
+  const int lent = c.eSeqEnd - c.eSeqStart + 1, lenp = c.eReadEnd - c.eReadStart + 1;
+  const size_t cb = (size_t)w0 * 32;
+  int mm;
+  if (lent == lenp && diag_certified(R, w0, tpos, Q, ppos, lent, mm)) {
+    int exMm = 0;
+    if (weight > 0) { cov_add(R.covDiff + cb + tpos, weight); cov_add(R.covDiff + cb + tpos + lent, -weight); }
+    for (int k = 0; k < lent; k += 32) {
+      u64 d = mm_chunk(R, w0, tpos + k, Q, ppos + k, lent - k);
+      if (R.relax) exMm += popc64(d & fetch32(R.ex2, w0, tpos + k));
+      if (weight > 0) {
+        u64 un = (d | fetch32(R.n2, w0, tpos + k) | fetch32(Q.n2, 0, ppos + k)) & lowmask2(lent - k);
+        while (un) {
+          int p = k + (ctz64(un) >> 1);
+          un &= un - 1;
+          cov_add(R.covPoint + cb + tpos + p, -weight);
+        }
+      }
+    }
+    c.relaxed = R.relax ? 2 * (lent - exMm) : c.eMatchCnt;
+    return;
+  }
+  int n = dp_align(R, w0, tpos, lent, Q, ppos, lenp, S, err);
+  if (n < 0) { c.relaxed = c.eMatchCnt; return; }
+  const u8 *ops = S.ops();
+  int refPos = tpos, readPos = ppos, m = 0;
+  for (int k = 0; k < n; ++k) {
+    int op = ops[k];
+    if (R.relax) {
+      if (base2(R.ex2, w0, refPos)) { if (op == 0) ++m; } else ++m;
+    }
+    if (weight > 0 && op == 0 && readPos < Q.len && refPos < R.len[c.seqIdx] && !base2(Q.n2, 0, readPos) &&
+        !base2(R.n2, w0, refPos) && base2(R.seq2, w0, refPos) == base2(Q.seq2, 0, readPos))
+      cov_add(R.covPoint + cb + refPos, weight);
+    if (op != 2) ++refPos;
+    if (op != 3) ++readPos;
+  }
+  c.relaxed = R.relax ? 2 * m : c.eMatchCnt;
+}
+
+// post-extension denominators / keys
+T1K_HD int cand_denom_pre(const Cand &c) { return c.seqEnd - c.seqStart + 1 + c.readEnd - c.readStart + 1; }
+T1K_HD int cand_denom_post(const Cand &c) {
+  return c.eSeqEnd - c.eSeqStart + 1 + c.eReadEnd - c.eReadStart + 1 + 2 * c.leftClip + 2 * c.rightClip;
+}
+T1K_HD u64 cand_key_pre(const Cand &c) {
+  return order_key(c.matchCnt, cand_denom_pre(c), c.readEnd - c.readStart, c.seqIdx, c.readStart);
+}
+T1K_HD u64 cand_key_post(const Cand &c) {
+  return order_key(c.eMatchCnt, cand_denom_post(c), c.eReadEnd - c.eReadStart, c.seqIdx, c.eReadStart);
+}
+
+}  // namespace t1k

@@ -1,0 +1,108 @@
+// Host-side packing of alleles / reads into the 2-bit planes described in t1k_core.cuh and the
+// direct-address k-mer table.  Plain C++ (no CUDA), shared by the ABI implementation and the test emulator.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+
+#include "t1k_core.cuh"
+
+namespace t1k {
+
+inline int code_of(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3; }   // nucToNum & 3
+inline bool valid_base(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N'; }
+
+struct PackedRef {
+  int32_t nAlleles = 0;
+  std::vector<u64> seq2, n2, ex2;
+  std::vector<u64> wordOff;
+  std::vector<int32_t> len;
+  std::vector<u32> kstart;
+  std::vector<Posting> post;
+  size_t totalWords = 0;
+};
+
+inline void set2(std::vector<u64> &plane, u64 w0, int pos, u64 v) { plane[w0 + (pos >> 5)] |= v << ((pos & 31) * 2); }
+
+// returns false on a character outside ACGTN
+inline bool pack_reference(int32_t n, const char *bases, const int64_t *off, const int32_t *exonPtr, const int32_t *exonSE,
+                           PackedRef &P) {
+  P.nAlleles = n;
+  P.wordOff.resize(n); P.len.resize(n);
+  size_t words = 0;
+  for (int i = 0; i < n; ++i) {
+    int len = (int)(off[i + 1] - off[i]);
+    P.wordOff[i] = words; P.len[i] = len;
+    words += (size_t)(len + 31) / 32 + 2;     // >= 1 pad word after every allele (coverage diff writes at len)
+  }
+  words += 2;
+  P.totalWords = words;
+  P.seq2.assign(words, 0); P.n2.assign(words, 0); P.ex2.assign(words, 0);
+  const size_t nK = (size_t)1 << (2 * KMER);
+  std::vector<u32> cnt(nK + 1, 0);
+  // two passes over the k-mers (count, fill) in allele order => postings sorted by (k-mer, allele, offset),
+  // the insertion order of KmerIndex::BuildIndexFromRead (KmerIndex.hpp:107-130) including its i==kl quirk.
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int i = 0; i < n; ++i) {
+      const char *s = bases + off[i];
+      int len = P.len[i];
+      u64 w0 = P.wordOff[i];
+      if (pass == 0) {
+        for (int j = 0; j < len; ++j) {
+          if (!valid_base(s[j])) return false;
+          set2(P.seq2, w0, j, (u64)code_of(s[j]));
+          if (s[j] == 'N') set2(P.n2, w0, j, 1);
+        }
+        for (int e = exonPtr[i]; e < exonPtr[i + 1]; ++e)
+          for (int j = exonSE[2 * e]; j <= exonSE[2 * e + 1] && j < len; ++j)
+            if (j >= 0) P.ex2[w0 + (j >> 5)] |= 1ull << ((j & 31) * 2);
+      }
+      if (len < KMER) continue;
+      u32 code = 0, prev = 0; int bad = -1;
+      const u32 mask = (u32)(nK - 1);
+      for (int j = 0; j < len; ++j) {
+        if (bad != -1) ++bad;
+        // same code layout as the device: base j of the window at bits 2*(position in window)
+        code = (code >> 2) | ((u32)code_of(s[j]) << (2 * (KMER - 1)));
+        if (s[j] == 'N') bad = 0;
+        if (bad >= KMER) bad = -1;
+        if (j < KMER - 1) continue;
+        code &= mask;
+        if (bad == -1 && (j == KMER || code != prev)) {
+          if (pass == 0) ++cnt[code + 1];
+          else { Posting p; p.idx = (u32)i; p.off = (u32)(j - KMER + 1); P.post[cnt[code]++] = p; }
+        }
+        prev = code;
+      }
+    }
+    if (pass == 0) {
+      for (size_t c = 0; c < nK; ++c) cnt[c + 1] += cnt[c];
+      P.kstart = cnt;
+      P.post.resize(cnt[nK]);
+      // cnt[c] now = start of bucket c; fill pass advances it
+    }
+  }
+  return true;
+}
+
+// pack one read (both strands) into planes of RWORDS words each; returns false on invalid characters
+inline bool pack_read(const char *s, int len, u64 *fseq, u64 *fn, u64 *rseq, u64 *rn) {
+  for (int w = 0; w < RWORDS; ++w) fseq[w] = fn[w] = rseq[w] = rn[w] = 0;
+  for (int j = 0; j < len; ++j) {
+    char c = s[j];
+    if (!valid_base(c)) return false;
+    int sh = (j & 31) * 2, w = j >> 5;
+    int rj = len - 1 - j, rsh = (rj & 31) * 2, rw = rj >> 5;
+    if (c == 'N') {
+      fseq[w] |= 3ull << sh; fn[w] |= 1ull << sh;
+      rseq[rw] |= 3ull << rsh; rn[rw] |= 1ull << rsh;
+    } else {
+      u64 v = (u64)code_of(c);
+      fseq[w] |= v << sh;
+      rseq[rw] |= (3 - v) << rsh;
+    }
+  }
+  return true;
+}
+
+}  // namespace t1k

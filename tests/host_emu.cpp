@@ -1,0 +1,196 @@
+// TEST HARNESS ONLY.  Runs the lane-level product code of t1k_b200/csrc/t1k_core.cuh sequentially on the
+// CPU (compiled by g++ with the CUDA qualifiers defined away) so that its logic can be checked against the
+// oracle on the GPU-less build box.  The warp orchestration of the real kernels is re-stated here with plain
+// loops; nothing in the product links against this file.
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../t1k_b200/csrc/t1k_core.cuh"
+#include "../t1k_b200/csrc/t1k_host.hpp"
+
+using namespace t1k;
+
+struct Emu {
+  PackedRef P;
+  std::vector<int32_t> covDiff, covPoint;
+  RefView R;
+  std::vector<u8> scratch;
+};
+
+struct EmuOverlap { int32_t seqIdx, readStart, readEnd, seqStart, seqEnd, strand, matchCnt, relaxedMatchCnt, leftClip, rightClip; };
+
+extern "C" {
+
+Emu *emu_create(int32_t n, const char *bases, const int64_t *off, const int32_t *exonPtr, const int32_t *exonSE,
+                double sim, int32_t relax) {
+  Emu *e = new Emu;
+  if (!pack_reference(n, bases, off, exonPtr, exonSE, e->P)) { delete e; return NULL; }
+  e->covDiff.assign(e->P.totalWords * 32, 0);
+  e->covPoint.assign(e->P.totalWords * 32, 0);
+  RefView &R = e->R;
+  R.seq2 = e->P.seq2.data(); R.n2 = e->P.n2.data(); R.ex2 = e->P.ex2.data();
+  R.wordOff = e->P.wordOff.data(); R.len = e->P.len.data();
+  R.kstart = e->P.kstart.data(); R.post = e->P.post.data();
+  R.covDiff = e->covDiff.data(); R.covPoint = e->covPoint.data();
+  R.nAlleles = n; R.sim = sim; R.relax = relax;
+  e->scratch.assign(SCR_BYTES, 0);
+  return e;
+}
+void emu_destroy(Emu *e) { delete e; }
+
+// dp_align / diag_certified on a single pair of strings; returns number of ops, fills ops, *certified
+int32_t emu_align(const char *t, int32_t lent, const char *p, int32_t lenp, int8_t *opsOut, int32_t *certified,
+                  int32_t *matches) {
+  // build a one-allele reference holding t and a read holding p
+  std::vector<u64> seq2((lent + 31) / 32 + 3, 0), n2(seq2.size(), 0), ex2(seq2.size(), 0);
+  for (int j = 0; j < lent; ++j) {
+    seq2[j >> 5] |= (u64)code_of(t[j]) << ((j & 31) * 2);
+    if (t[j] == 'N') n2[j >> 5] |= 1ull << ((j & 31) * 2);
+  }
+  u64 w0 = 0; int32_t len = lent;
+  RefView R; memset(&R, 0, sizeof(R));
+  R.seq2 = seq2.data(); R.n2 = n2.data(); R.ex2 = ex2.data(); R.wordOff = &w0; R.len = &len; R.nAlleles = 1;
+  u64 fs[RWORDS], fn[RWORDS], rs[RWORDS], rn[RWORDS];
+  if (lenp > 255) return -2;
+  pack_read(p, lenp, fs, fn, rs, rn);
+  ReadView Q; Q.seq2 = fs; Q.n2 = fn; Q.len = lenp;
+  std::vector<u8> scr(SCR_BYTES, 0);
+  LaneScratch S; S.base = scr.data();
+  int err = 0, mm = 0;
+  *certified = (lent == lenp && lent > 0) ? (int)diag_certified(R, 0, 0, Q, 0, lent, mm) : 0;
+  *matches = align_matches(R, 0, 0, lent, Q, 0, lenp, S, err);
+  int n = dp_align(R, 0, 0, lent, Q, 0, lenp, S, err);
+  if (err) return -1;
+  for (int i = 0; i < n; ++i) opsOut[i] = (int8_t)S.ops()[i];
+  return n;
+}
+
+// SeqSet::AssignRead through the product's lane code
+int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, int32_t cap, int32_t *errOut) {
+  const RefView &R = E->R;
+  int len = (int)strlen(read);
+  *errOut = 0;
+  if (len < KMER || len > 255) return -1;
+  u64 planes[4][RWORDS];
+  if (!pack_read(read, len, planes[0], planes[1], planes[2], planes[3])) { *errOut = -1; return -1; }
+  LaneScratch S; S.base = E->scratch.data();
+  int err = 0;
+  std::vector<Cand> cands;
+  u64 bestKey = 0;
+  int nFwd = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    int strand01 = pass == 0 ? 1 : 0;
+    ReadView Q; Q.seq2 = planes[pass * 2]; Q.n2 = planes[pass * 2 + 1]; Q.len = len;
+    // seed selection (GetHitsFromRead skip rule), then group hits per allele
+    std::map<u32, std::vector<u32> > groups;
+    u32 prev = 0; int skip = 0;
+    const int P = len - KMER + 1;
+    for (int a = 0; a < P; ++a) {
+      u32 code = (u32)(fetch32(Q.seq2, 0, a) & 0x3FFFFF);
+      bool valid = (fetch32(Q.n2, 0, a) & 0x155555) == 0;
+      if (a == 0 || prev != code) {
+        u32 lo = 0, hi = 0;
+        if (valid) { lo = R.kstart[code]; hi = R.kstart[code + 1]; }
+        int size = (int)(hi - lo);
+        if (size >= 100 && a != 0 && a != P - 1 && skip < KMER / 2) { ++skip; continue; }
+        skip = 0;
+        for (u32 j = lo; j < hi; ++j) groups[R.post[j].idx].push_back((u32)a | (R.post[j].off << 8));
+      }
+      prev = code;
+    }
+    for (std::map<u32, std::vector<u32> >::iterator it = groups.begin(); it != groups.end(); ++it) {
+      int nEmit = 0;
+      std::vector<u32> &h = it->second;
+      chain_allele(R, Q, strand01, (int)it->first, h.data(), 1, (int)h.size(), S, nEmit, bestKey, err);
+      for (int k = 0; k < nEmit; ++k) cands.push_back(S.emit()[k]);
+    }
+    if (pass == 0) nFwd = (int)cands.size();
+  }
+  int best01 = (bestKey & 1) ? 0 : 1;
+  int c0 = best01 ? 0 : nFwd, c1 = best01 ? nFwd : (int)cands.size();
+  if (c1 - c0 <= 0) { *errOut = err; return -1; }
+  ReadView Q; Q.seq2 = planes[best01 ? 0 : 2]; Q.n2 = planes[best01 ? 1 : 3]; Q.len = len;
+  // pass 1: extension + first failing key
+  u64 fKey = ~0ull; int fIdx = 0x7fffffff;
+  for (int i = c0; i < c1; ++i) {
+    extend_cand(R, Q, cands[i], S, err);
+    Cand &c = cands[i];
+    if (!(c.flags & CF_SEP) && !(c.flags & CF_RET)) {
+      u64 k = cand_key_pre(c);
+      if (k < fKey || (k == fKey && i < fIdx)) { fKey = k; fIdx = i; }
+    }
+  }
+  int good = -1;
+  for (int i = c0; i < c1; ++i) {
+    Cand &c = cands[i];
+    if ((c.flags & CF_SEP) || !(c.flags & CF_RET)) continue;
+    u64 k = cand_key_pre(c);
+    if (k < fKey || (k == fKey && i < fIdx)) good = std::max(good, (int)c.matchCnt);
+  }
+  int bestMc = -1, nInc = 0;
+  for (int i = c0; i < c1; ++i) {
+    Cand &c = cands[i];
+    if ((c.flags & CF_SEP) || !(c.flags & CF_RET)) continue;
+    u64 k = cand_key_pre(c);
+    bool before = k < fKey || (k == fKey && i < fIdx);
+    double sim = (double)c.matchCnt / (double)cand_denom_pre(c);
+    if (!before && (int)c.matchCnt < good && (!(c.flags & CF_NEEDCLIP) || sim < 0.95)) continue;
+    c.flags |= CF_INCLUDE;
+    bestMc = std::max(bestMc, c.eMatchCnt);
+    ++nInc;
+  }
+  for (int i = c0; i < c1; ++i) {
+    Cand &c = cands[i];
+    if (!(c.flags & CF_INCLUDE)) continue;
+    if (weight >= 0) {
+      if (c.eMatchCnt >= bestMc - 10) full_align(R, Q, c, weight, S, err);
+      else c.relaxed = 0;
+    }
+  }
+  bool usePost = nInc > 1000;
+  if (usePost) {
+    u64 bKey = ~0ull; int bIdx = 0x7fffffff;
+    for (int i = c0; i < c1; ++i) if (cands[i].flags & CF_INCLUDE) {
+      u64 k = cand_key_post(cands[i]);
+      if (k < bKey || (k == bKey && i < bIdx)) { bKey = k; bIdx = i; }
+    }
+    double bestSim = (double)cands[bIdx].eMatchCnt / (double)cand_denom_post(cands[bIdx]);
+    u64 cKey = ~0ull; int cIdx = 0x7fffffff;
+    for (int i = c0; i < c1; ++i) if ((cands[i].flags & CF_INCLUDE) && i != bIdx) {
+      double sim = (double)cands[i].eMatchCnt / (double)cand_denom_post(cands[i]);
+      if (sim < bestSim - 0.1) {
+        u64 k = cand_key_post(cands[i]);
+        if (k < cKey || (k == cKey && i < cIdx)) { cKey = k; cIdx = i; }
+      }
+    }
+    for (int i = c0; i < c1; ++i) if (cands[i].flags & CF_INCLUDE) {
+      u64 k = cand_key_post(cands[i]);
+      if (k > cKey || (k == cKey && i >= cIdx)) cands[i].flags &= ~CF_INCLUDE;
+    }
+  }
+  std::vector<std::pair<u64, int> > order;
+  for (int i = c0; i < c1; ++i) if (cands[i].flags & CF_INCLUDE)
+    order.push_back(std::make_pair(usePost ? cand_key_post(cands[i]) : cand_key_pre(cands[i]), i));
+  std::sort(order.begin(), order.end());
+  int w = 0;
+  for (size_t k = 0; k < order.size() && w < cap; ++k, ++w) {
+    const Cand &c = cands[order[k].second];
+    EmuOverlap &o = out[w];
+    o.seqIdx = c.seqIdx; o.readStart = c.eReadStart; o.readEnd = c.eReadEnd; o.seqStart = c.eSeqStart; o.seqEnd = c.eSeqEnd;
+    o.strand = c.strand01 ? 1 : -1; o.matchCnt = c.eMatchCnt; o.relaxedMatchCnt = c.relaxed;
+    o.leftClip = c.leftClip; o.rightClip = c.rightClip;
+  }
+  *errOut = err;
+  return (int)order.size();
+}
+
+// coverage of one allele = prefix(covDiff) + covPoint
+void emu_coverage(Emu *E, int32_t allele, int32_t *out) {
+  size_t cb = (size_t)E->P.wordOff[allele] * 32;
+  int run = 0;
+  for (int j = 0; j < E->P.len[allele]; ++j) { run += E->covDiff[cb + j]; out[j] = run + E->covPoint[cb + j]; }
+}
+
+}  // extern "C"
