@@ -15,9 +15,11 @@
 #ifdef __CUDACC__
 #define T1K_HD __host__ __device__ __forceinline__
 #define T1K_HDN __host__ __device__
+#define T1K_NOINLINE __noinline__
 #else
 #define T1K_HD inline
 #define T1K_HDN
+#define T1K_NOINLINE
 #endif
 
 namespace t1k {
@@ -178,7 +180,7 @@ T1K_HDN inline bool diag_certified(const RefView &R, u64 w0, int tpos, const Rea
 // two rolling rows of (m,e) and one direction nibble per band cell
 //   bit0 diagonal predecessor reproduces m, bit1 f >= e, bit2 e opened from m, bit3 f opened from m.
 // Writes the edit ops in forward order to S.ops() (0 M,1 X,2 I,3 D) and returns their count (<0: error).
-T1K_HDN inline int dp_align(const RefView &R, u64 w0, int tpos, int lent, const ReadView &Q, int ppos, int lenp,
+T1K_HDN T1K_NOINLINE inline int dp_align(const RefView &R, u64 w0, int tpos, int lent, const ReadView &Q, int ppos, int lenp,
                             const LaneScratch &S, int &err) {
   u8 *ops = S.ops();
   if (lent == 0 || lenp == 0) return 0;

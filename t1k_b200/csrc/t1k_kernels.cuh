@@ -1,0 +1,409 @@
+// sm_100a kernels of the alignment path: read packing, the persistent warp-per-read-end assignment kernel
+// (seed selection -> allele-tile gather -> lane-per-allele chaining/rescoring -> extension -> full-read
+// alignment + coverage -> ordered compaction into the HBM-resident overlap store) and coverage finalisation.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "t1k_core.cuh"
+
+namespace t1k {
+
+constexpr int WARPS_PER_BLOCK = 4;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct ReadsDev {
+  const u64 *planes;       // [(r*4 + plane) * RWORDS]; planes: fwd seq2, fwd n2, rc seq2, rc n2
+  const u16 *len;
+  const int32_t *weight;
+  const u32 *workList;     // optional indirection (deferred re-runs); NULL = identity
+  u32 nWork;
+};
+
+struct AssignOut {
+  Rec *store;
+  unsigned long long *storeCtr;
+  u64 storeCap;
+  u64 *readOff;            // per read-end: first record
+  u32 *readCnt;
+  int32_t *readRet;        // AssignRead's return value; -2 = deferred (store full)
+  int *err;
+  unsigned long long *stats;   // [0] postings visited, [1] candidates, [2] tiles, [3] dp calls (debug/roofline)
+};
+
+struct AssignParams {
+  RefView R;
+  ReadsDev Q;
+  AssignOut O;
+  Cand *candBuf;           // per warp
+  u32 candCap;
+  u8 *laneScratch;         // per lane SCR_BYTES
+  unsigned int *workCtr;
+  int hitCap;              // hits per allele kept in shared memory
+};
+
+__device__ __forceinline__ u32 warp_min_u32(u32 v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_max_i32(int v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i32(int v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ u64 warp_max_u64(u64 v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { u64 t = __shfl_xor_sync(FULL, v, o); v = t > v ? t : v; }
+  return v;
+}
+__device__ __forceinline__ u64 warp_min_u64(u64 v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { u64 t = __shfl_xor_sync(FULL, v, o); v = t < v ? t : v; }
+  return v;
+}
+// lexicographic min of (key, idx) over the warp
+__device__ __forceinline__ void warp_min_pair(u64 &key, int &idx) {
+  u64 k = warp_min_u64(key);
+  int i = key == k ? idx : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) i = min(i, __shfl_xor_sync(FULL, i, o));
+  key = k; idx = i;
+}
+__device__ __forceinline__ bool pair_less(u64 k, int i, u64 fk, int fi) { return k < fk || (k == fk && i < fi); }
+
+// ---------------------------------------------------------------------------------------------------
+// ASCII reads -> 2-bit planes of both strands (rc: SeqSet::ReverseComplement, SeqSet.hpp:2103-2114)
+__global__ void k_pack_reads(const char *bases, const u64 *off, const u32 *len, u32 n, u64 *planes, u16 *lenOut, int *err) {
+  u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const char *s = bases + off[r];
+  int L = (int)len[r];
+  u64 *out = planes + (size_t)r * 4 * RWORDS;
+  if (L > 255) { atomicOr(err, 1); L = 0; }
+  lenOut[r] = (u16)L;
+  u64 fs = 0, fn = 0;
+  for (int w = 0; w < RWORDS; ++w) { out[w] = 0; out[RWORDS + w] = 0; out[2 * RWORDS + w] = 0; out[3 * RWORDS + w] = 0; }
+  for (int j = 0; j < L; ++j) {
+    char c = s[j];
+    int v = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : c == 'N' ? 4 : 5;
+    if (v == 5) { atomicOr(err, 2); v = 4; }
+    int sh = (j & 31) * 2;
+    fs |= (u64)(v == 4 ? 3 : v) << sh;
+    fn |= (u64)(v == 4) << sh;
+    if ((j & 31) == 31 || j == L - 1) { out[j >> 5] = fs; out[RWORDS + (j >> 5)] = fn; fs = fn = 0; }
+  }
+  u64 rs = 0, rn = 0;
+  for (int j = 0; j < L; ++j) {
+    char c = s[L - 1 - j];
+    int v = c == 'A' ? 3 : c == 'C' ? 2 : c == 'G' ? 1 : c == 'T' ? 0 : 4;
+    int sh = (j & 31) * 2;
+    rs |= (u64)(v == 4 ? 3 : v) << sh;
+    rn |= (u64)(v == 4) << sh;
+    if ((j & 31) == 31 || j == L - 1) { out[2 * RWORDS + (j >> 5)] = rs; out[3 * RWORDS + (j >> 5)] = rn; rs = rn = 0; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One warp = one read-end at a time (dynamic work queue).  Shared memory per warp:
+//   H[hitCap][32]  encoded hits of the current allele tile, lane-interleaved (bank = lane)
+//   cnt[32], seedA[256], cur[256], end[256], nxt[256], read planes (2 x RWORDS words)
+struct WarpSmem {
+  u32 *H, *cnt, *cur, *end, *nxt;
+  u8 *seedA;
+  u64 *seq, *nn;
+};
+__host__ __device__ inline size_t warp_smem_bytes(int hitCap) {
+  return (size_t)hitCap * 32 * 4 + 32 * 4 + 3 * 256 * 4 + 256 + 2 * RWORDS * 8;
+}
+
+__device__ __forceinline__ void load_planes(const AssignParams &P, u32 r, int strand01, const WarpSmem &W, int lane) {
+  const u64 *src = P.Q.planes + ((size_t)r * 4 + (strand01 ? 0 : 2)) * RWORDS;
+  if (lane < RWORDS) W.seq[lane] = src[lane];
+  else if (lane < 2 * RWORDS) W.nn[lane - RWORDS] = src[lane];   // n2 plane follows the seq plane
+  __syncwarp();
+}
+
+__device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W, Cand *cands, const LaneScratch &S, int lane) {
+  const RefView &R = P.R;
+  const int len = P.Q.len[r];
+  const int weight = P.Q.weight[r];
+  const int CAP = P.hitCap;
+  int err = 0;
+  u32 nCand = 0, nFwd = 0;
+  u64 bestKey = 0;
+  unsigned long long stPost = 0, stTiles = 0;
+  ReadView Qv; Qv.seq2 = W.seq; Qv.n2 = W.nn; Qv.len = len;
+
+  if (len >= KMER) {
+    const int NP = len - KMER + 1;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int strand01 = pass == 0 ? 1 : 0;
+      load_planes(P, r, strand01, W, lane);
+      // ---- k-mer codes and posting ranges of every window (GetHitsFromRead, SeqSet.hpp:1093-1153)
+      for (int a = lane; a < NP; a += 32) {
+        u32 code = (u32)(fetch32(W.seq, 0, a) & 0x3FFFFFull);
+        bool valid = (fetch32(W.nn, 0, a) & 0x155555ull) == 0;
+        u32 lo = R.kstart[code], hi = R.kstart[code + 1];
+        W.nxt[a] = code; W.cur[a] = lo; W.end[a] = valid ? hi : lo;
+      }
+      __syncwarp();
+      // ---- the sequential skip rule (list >= 100, not first/last, <= K/2 in a row; Q2)
+      int nS = 0;
+      if (lane == 0) {
+        u32 prev = 0; int skip = 0;
+        for (int a = 0; a < NP; ++a) {
+          u32 code = W.nxt[a];
+          if (a == 0 || prev != code) {
+            u32 lo = W.cur[a], hi = W.end[a];
+            int size = (int)(hi - lo);
+            if (size >= 100 && a != 0 && a != NP - 1 && skip < KMER / 2) { ++skip; continue; }
+            skip = 0;
+            if (size > 0) { W.seedA[nS] = (u8)a; W.cur[nS] = lo; W.end[nS] = hi; ++nS; }
+          }
+          prev = code;
+        }
+      }
+      nS = __shfl_sync(FULL, nS, 0);
+      __syncwarp();
+      for (int k = lane; k < nS; k += 32) { W.nxt[k] = R.post[W.cur[k]].idx; stPost += W.end[k] - W.cur[k]; }
+      __syncwarp();
+      u64 laneKey = 0;
+      // ---- allele tiles: 32 consecutive allele ids starting at the smallest pending one
+      for (;;) {
+        u32 mn = 0xffffffffu;
+        for (int k = lane; k < nS; k += 32) mn = min(mn, W.nxt[k]);
+        mn = warp_min_u32(mn);
+        if (mn == 0xffffffffu) break;
+        const u32 base = mn;
+        ++stTiles;
+        W.cnt[lane] = 0;
+        __syncwarp();
+        for (int k = 0; k < nS; ++k) {           // seeds in read-offset order => per-allele hits sorted by (a, b)
+          if (W.nxt[k] >= base + 32) continue;   // warp-uniform (shared-memory broadcast)
+          const u32 a = W.seedA[k];
+          for (;;) {
+            const u32 c = W.cur[k], e = W.end[k];
+            Posting p; p.idx = 0xffffffffu; p.off = 0;
+            if (c + lane < e) p = R.post[c + lane];
+            const bool in = p.idx < base + 32;
+            const unsigned bal = __ballot_sync(FULL, in);
+            const int consumed = __popc(bal);
+            const u32 prevIdx = __shfl_up_sync(FULL, p.idx, 1);
+            const bool startRun = lane == 0 || p.idx != prevIdx;
+            const unsigned sm = __ballot_sync(FULL, startRun);
+            const int runStart = 31 - __clz(sm & (0xffffffffu >> (31 - lane)));
+            const int rank = lane - runStart;
+            const bool lastOfRun = lane == 31 || ((sm >> (lane + 1)) & 1u);
+            const u32 local = p.idx - base;
+            u32 slot = 0;
+            if (in) {
+              slot = W.cnt[local] + rank;
+              if ((int)slot < CAP) W.H[slot * 32 + local] = a | (p.off << 8);
+            }
+            __syncwarp();
+            if (in && lastOfRun) W.cnt[local] = slot + 1;
+            __syncwarp();
+            const u32 nc = c + consumed;
+            if (consumed == 32 && nc < e) { if (lane == 0) W.cur[k] = nc; __syncwarp(); continue; }
+            const u32 nextIdx = consumed < 32 ? __shfl_sync(FULL, p.idx, consumed) : 0xffffffffu;
+            if (lane == 0) { W.cur[k] = nc; W.nxt[k] = nextIdx; }
+            __syncwarp();
+            break;
+          }
+        }
+        __syncwarp();
+        // ---- lane-per-allele chaining + rescoring
+        const int n = (int)W.cnt[lane];
+        int nEmit = 0;
+        if (n >= 3) {
+          if (n <= CAP) chain_allele(R, Qv, strand01, (int)(base + lane), W.H + lane, 32, n, S, nEmit, laneKey, err);
+          else err |= ERR_HITS;
+        }
+        // ---- ordered emission (allele order == lane order)
+        int incl = nEmit;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+        const int tot = __shfl_sync(FULL, incl, 31);
+        if (tot > 0) {
+          if (nCand + tot > P.candCap) err |= ERR_CAND;
+          else {
+            const Cand *em = S.emit();
+            for (int j = 0; j < nEmit; ++j) cands[nCand + incl - nEmit + j] = em[j];
+            nCand += tot;
+          }
+        }
+        __syncwarp();
+      }
+      bestKey = max(bestKey, warp_max_u64(laneKey));
+      if (pass == 0) nFwd = nCand;
+    }
+  }
+  // ---- AssignRead proper (SeqSet.hpp:2132-2300) on the best strand's candidates
+  const int best01 = (bestKey & 1) ? 0 : 1;
+  const int c0 = best01 ? 0 : (int)nFwd, c1 = best01 ? (int)nFwd : (int)nCand;
+  int ret = -1, nFinal = 0;
+  unsigned long long pos = 0;
+  bool deferred = false;
+  if (c1 - c0 > 0) {
+    if (best01 == 1) load_planes(P, r, 1, W, lane);
+    __threadfence_block();
+    __syncwarp();
+    // pass 1: extension; first candidate (list order) whose extension fails
+    u64 fKey = ~0ull; int fIdx = 0x7fffffff;
+    for (int i = c0 + lane; i < c1; i += 32) {
+      Cand c = cands[i];
+      extend_cand(R, Qv, c, S, err);
+      cands[i] = c;
+      if (!(c.flags & CF_SEP) && !(c.flags & CF_RET)) {
+        u64 k = cand_key_pre(c);
+        if (pair_less(k, i, fKey, fIdx)) { fKey = k; fIdx = i; }
+      }
+    }
+    warp_min_pair(fKey, fIdx);
+    __syncwarp();
+    // pass 2: goodMatchCnt
+    int good = -1;
+    for (int i = c0 + lane; i < c1; i += 32) {
+      const Cand &c = cands[i];
+      if ((c.flags & CF_SEP) || !(c.flags & CF_RET)) continue;
+      if (pair_less(cand_key_pre(c), i, fKey, fIdx)) good = max(good, (int)c.matchCnt);
+    }
+    good = warp_max_i32(good);
+    // pass 3: inclusion
+    int bestMc = -1, nInc = 0;
+    for (int i = c0 + lane; i < c1; i += 32) {
+      Cand &c = cands[i];
+      if ((c.flags & CF_SEP) || !(c.flags & CF_RET)) continue;
+      bool before = pair_less(cand_key_pre(c), i, fKey, fIdx);
+      double sim = (double)c.matchCnt / (double)cand_denom_pre(c);
+      if (!before && (int)c.matchCnt < good && (!(c.flags & CF_NEEDCLIP) || sim < 0.95)) continue;
+      c.flags |= CF_INCLUDE;
+      bestMc = max(bestMc, c.eMatchCnt);
+      ++nInc;
+    }
+    bestMc = warp_max_i32(bestMc);
+    nInc = warp_sum_i32(nInc);
+    __syncwarp();
+    // reserve the store before touching coverage, so that a full store can be retried without double counting
+    if (lane == 0 && nInc > 0) pos = atomicAdd(P.O.storeCtr, (unsigned long long)nInc);
+    pos = __shfl_sync(FULL, pos, 0);
+    if (nInc > 0 && pos + nInc > P.O.storeCap) deferred = true;
+    if (!deferred) {
+      // pass 4: full-read alignment of everything within 10 of the best (Q8)
+      if (weight >= 0) {
+        for (int i = c0 + lane; i < c1; i += 32) {
+          Cand c = cands[i];
+          if (!(c.flags & CF_INCLUDE)) continue;
+          if (c.eMatchCnt >= bestMc - 10) full_align(R, Qv, c, weight, S, err);
+          else c.relaxed = 0;
+          cands[i].relaxed = c.relaxed;
+        }
+      }
+      __syncwarp();
+      const bool usePost = nInc > 1000;      // SeqSet.hpp:2290-2298
+      if (usePost) {
+        u64 bKey = ~0ull; int bIdx = 0x7fffffff;
+        for (int i = c0 + lane; i < c1; i += 32) if (cands[i].flags & CF_INCLUDE) {
+          u64 k = cand_key_post(cands[i]);
+          if (pair_less(k, i, bKey, bIdx)) { bKey = k; bIdx = i; }
+        }
+        warp_min_pair(bKey, bIdx);
+        const double bestSim = (double)cands[bIdx].eMatchCnt / (double)cand_denom_post(cands[bIdx]);
+        u64 cKey = ~0ull; int cIdx = 0x7fffffff;
+        for (int i = c0 + lane; i < c1; i += 32) if ((cands[i].flags & CF_INCLUDE) && i != bIdx) {
+          double sim = (double)cands[i].eMatchCnt / (double)cand_denom_post(cands[i]);
+          if (sim < bestSim - 0.1) {
+            u64 k = cand_key_post(cands[i]);
+            if (pair_less(k, i, cKey, cIdx)) { cKey = k; cIdx = i; }
+          }
+        }
+        warp_min_pair(cKey, cIdx);
+        for (int i = c0 + lane; i < c1; i += 32) if (cands[i].flags & CF_INCLUDE) {
+          u64 k = cand_key_post(cands[i]);
+          if (!pair_less(k, i, cKey, cIdx)) cands[i].flags &= ~CF_INCLUDE;
+        }
+        __syncwarp();
+      }
+      // pass 5: ordered compaction into the store (allele order is kept: pairing binary-searches it)
+      int running = 0;
+      for (int b = c0; b < c1; b += 32) {
+        const int i = b + lane;
+        bool inc = false;
+        Cand c;
+        if (i < c1) { c = cands[i]; inc = (c.flags & CF_INCLUDE) != 0; }
+        const unsigned bal = __ballot_sync(FULL, inc);
+        if (inc) {
+          Rec o;
+          o.seqIdx = c.seqIdx; o.seqStart = c.eSeqStart; o.seqEnd = c.eSeqEnd;
+          o.packed = (u32)c.eReadStart | ((u32)c.eReadEnd << 8) | ((u32)c.leftClip << 16) | ((u32)c.rightClip << 24);
+          o.mcStrand = (u32)c.eMatchCnt | ((u32)c.strand01 << 31);
+          o.relaxed = c.relaxed;
+          o.key = usePost ? cand_key_post(c) : cand_key_pre(c);
+          P.O.store[pos + running + __popc(bal & ((1u << lane) - 1))] = o;
+        }
+        running += __popc(bal);
+      }
+      nFinal = running;
+      ret = nFinal;
+    }
+  }
+  if (lane == 0) {
+    P.O.readOff[r] = pos;
+    P.O.readCnt[r] = deferred ? 0 : (u32)nFinal;
+    P.O.readRet[r] = deferred ? -2 : ret;
+    if (deferred) atomicOr(P.O.err, ERR_STORE);
+  }
+  err = __reduce_or_sync(FULL, (unsigned)err);
+  if (lane == 0 && err) atomicOr(P.O.err, err);
+  if (P.O.stats) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) stPost += __shfl_xor_sync(FULL, stPost, o);
+  }
+  if (lane == 0 && P.O.stats) {
+    atomicAdd(P.O.stats + 0, stPost);
+    atomicAdd(P.O.stats + 1, (unsigned long long)nCand);
+    atomicAdd(P.O.stats + 2, stTiles);
+  }
+}
+
+extern __shared__ u64 t1k_smem[];
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_assign(AssignParams P) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t gwarp = (size_t)blockIdx.x * WARPS_PER_BLOCK + warp;
+  u8 *sm = (u8 *)t1k_smem + (size_t)warp * ((warp_smem_bytes(P.hitCap) + 15) & ~(size_t)15);
+  WarpSmem W;
+  W.seq = (u64 *)sm; W.nn = W.seq + RWORDS;
+  W.H = (u32 *)(W.nn + RWORDS);
+  W.cnt = W.H + (size_t)P.hitCap * 32;
+  W.cur = W.cnt + 32; W.end = W.cur + 256; W.nxt = W.end + 256;
+  W.seedA = (u8 *)(W.nxt + 256);
+  LaneScratch S; S.base = P.laneScratch + (gwarp * 32 + lane) * (size_t)SCR_BYTES;
+  Cand *cands = P.candBuf + gwarp * (size_t)P.candCap;
+  for (;;) {
+    u32 w = 0;
+    if (lane == 0) w = atomicAdd(P.workCtr, 1u);
+    w = __shfl_sync(FULL, w, 0);
+    if (w >= P.Q.nWork) break;
+    const u32 r = P.Q.workList ? P.Q.workList[w] : w;
+    assign_one_read(P, r, W, cands, S, lane);
+    __syncwarp();
+  }
+}
+
+// coverage = prefix(covDiff) + covPoint, written in the caller's concatenated allele layout
+__global__ void k_cov_finalize(RefView R, const int64_t *offset, int32_t *out) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= R.nAlleles) return;
+  size_t cb = (size_t)R.wordOff[a] * 32;
+  int32_t *o = out + offset[a];
+  int run = 0;
+  for (int j = 0; j < R.len[a]; ++j) { run += R.covDiff[cb + j]; o[j] = run + R.covPoint[cb + j]; }
+}
+
+}  // namespace t1k

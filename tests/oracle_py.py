@@ -227,3 +227,230 @@ def parse_harness(path):
             else:
                 cur["ov"].append(tuple(int(x) for x in t[:10]) + (float.fromhex(t[10]),))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Host-side model steps of the reference, restated for the checker (small inputs only).
+
+def parse_allele_name(allele: str, digit_units=-1, delimiter=""):
+    """Genotyper::ParseAlleleName, Genotyper.hpp:63-131 (fieldsType 0).  Returns (gene, majorAllele)."""
+    parse_type = 1
+    fields = digit_units
+    delim = ""
+    if fields == -1:
+        fields = 3
+        if ":" in allele:
+            delim = ":"
+            parse_type = 2
+    if delimiter:
+        delim = delimiter
+        parse_type = 2
+    i = allele.find("*")
+    if i < 0:
+        i = len(allele)
+    gene = allele[:i]
+    if parse_type == 1:
+        j = 0
+        while j <= fields and i + j < len(allele):
+            j += 1
+        return gene, allele[:i + j]
+    k = 0
+    j = i
+    while j < len(allele):
+        if allele[j] == delim:
+            k += 1
+            if k >= fields:
+                break
+        j += 1
+    return gene, allele[:j]
+
+
+def allele_info(names, eff_len, digit_units=-1, delimiter=""):
+    """Genotyper::InitAlleleInfo, Genotyper.hpp:559-682: gene / major-allele ids in first-appearance order and
+    the large-deletion effective-length adjustment (:641-681).  Returns (gene_idx, major_idx, eff_len')."""
+    genes, majors = {}, {}
+    gi, mi = [], []
+    for n in names:
+        g, m = parse_allele_name(n, digit_units, delimiter)
+        gi.append(genes.setdefault(g, len(genes)))
+        mi.append(majors.setdefault(m, len(majors)))
+    eff = list(eff_len)
+    for g in range(len(genes)):
+        ids = [i for i in range(len(names)) if gi[i] == g]
+        lens = sorted(eff_len[i] for i in ids)
+        mode, best, j = 0, 0, 0
+        while j < len(lens):
+            k = j
+            while k < len(lens) and lens[k] == lens[j]:
+                k += 1
+            if k - j > best:
+                best, mode = k - j, lens[j]
+            j = k
+        for i in ids:
+            if eff_len[i] < mode - 500:
+                eff[i] = mode
+    return np.asarray(gi, dtype=np.int32), np.asarray(mi, dtype=np.int32), np.asarray(eff, dtype=np.int32)
+
+
+def coalesce(frag_assignments):
+    """Genotyper::CoalesceReadAssignments (Genotyper.hpp:841-908) over all fragments in order.
+    frag_assignments: list of ASSIGN_DT arrays.  Returns (groups: list of ASSIGN_DT arrays, assigned count)."""
+    groups, index = [], {}
+    assigned = 0
+    for a in frag_assignments:
+        if len(a) == 0:
+            continue
+        assigned += 1
+        a = a[np.argsort(a["alleleIdx"], kind="stable")].copy()
+        key = (a["alleleIdx"].tobytes(), a["qual"].tobytes())
+        g = index.get(key)
+        if g is None:
+            index[key] = len(groups)
+            groups.append(a)
+        else:
+            t = groups[g]
+            q1 = a["qual"] == 1
+            lower = q1 & (a["start"] < t["start"])
+            t["start"][lower] = a["start"][lower]
+            lowere = q1 & (a["end"] < t["end"])          # Q10: end is overwritten with start
+            t["end"][lowere] = a["start"][lowere]
+            t["weight"] += a["weight"]                     # float32 adds, fragment order
+            t["adjustWeight"] += a["adjustWeight"]
+    return groups, assigned
+
+
+def build_ecs(groups, n_alleles):
+    """Genotyper::FinalizeReadAssignments + BuildAlleleEquivalentClass (Genotyper.hpp:912-939,1072-1139).
+    Returns (ecs: list of allele lists, allele_ec[n_alleles])."""
+    G = len(groups)
+    reads_in = [[] for _ in range(n_alleles)]
+    for g, a in enumerate(groups):
+        for al in a["alleleIdx"]:
+            reads_in[int(al)].append(g)
+    fp = []
+    for i in range(n_alleles):
+        b = -1
+        if reads_in[i]:
+            b = 0
+            for g in reads_in[i]:
+                b = ((((b & 0xFFFFFFFF) * (G & 0xFFFFFFFF)) & 0xFFFFFFFF) + g) & 0xFFFFFFFF
+                b %= 1000003
+        fp.append((i, b))
+    fp.sort(key=lambda p: (-p[1], p[0]))
+    ecs = []
+    allele_ec = np.full(n_alleles, -1, dtype=np.int32)
+    for i, (a, b) in enumerate(fp):
+        if b == -1:
+            break
+        found = -1
+        j = i - 1
+        while j >= 0 and fp[j][1] == b:
+            if reads_in[fp[j][0]] == reads_in[a]:
+                found = fp[j][0]
+                break
+            j -= 1
+        if found < 0:
+            allele_ec[a] = len(ecs)
+            ecs.append([a])
+        else:
+            allele_ec[a] = allele_ec[found]
+            ecs[allele_ec[found]].append(a)
+    return ecs, allele_ec
+
+
+def em_problem(groups, ecs, allele_ec, eff_len, seq_weight):
+    """EM inputs as Genotyper::QuantifyAlleleEquivalentClass builds them (Genotyper.hpp:1155-1232)."""
+    rowptr = [0]
+    col = []
+    count = []
+    for a in groups:
+        count.append(float(a["weight"].max()))
+        seen = []
+        for al in a["alleleIdx"]:
+            e = int(allele_ec[int(al)])
+            if e not in seen:
+                seen.append(e)
+        col.extend(seen)
+        rowptr.append(len(col))
+    eclen = [min(int(eff_len[a]) for a in ec) for ec in ecs]
+    x0 = [float(sum(int(seq_weight[a]) for a in ec)) for ec in ecs]
+    ptr = [0]
+    flat = []
+    for ec in ecs:
+        flat.extend(ec)
+        ptr.append(len(flat))
+    return dict(rowptr=np.asarray(rowptr, dtype=np.int64), col=np.asarray(col, dtype=np.int32),
+                count=np.asarray(count, dtype=np.float64), eclen=np.asarray(eclen, dtype=np.int32),
+                x0=np.asarray(x0, dtype=np.float64), ec_allele_ptr=np.asarray(ptr, dtype=np.int32),
+                ec_alleles=np.asarray(flat, dtype=np.int32))
+
+
+def set_allele_abundance(rc, eclen, ecs, n_alleles):
+    """Genotyper::SetAlleleAbundance (Genotyper.hpp:957-987): per allele abundance / ecAbundance."""
+    ab = np.zeros(n_alleles)
+    ecab = np.zeros(n_alleles)
+    for e, ec in enumerate(ecs):
+        a = rc[e] / eclen[e] * 1000.0
+        for k in ec:
+            ab[k] = a / len(ec)
+            ecab[k] = a
+    return ab, ecab
+
+
+def genotype_pipeline(orc: "Oracle", reads1, reads2, names, seq_weight, max_assign=2000, min_alpha=0.0,
+                      filter_frac=0.15, digit_units=-1, delimiter=""):
+    """The Genotyper.cpp:450-646 flow on the oracle: dedup read-ends, AssignRead per unique sequence,
+    fragment pairing, coalescing, equivalence classes, EM.  reads: uint8 arrays [n, L] or lists of bytes."""
+    def as_list(r):
+        return [bytes(x) if isinstance(x, (bytes, bytearray)) else x.tobytes() for x in r]
+    s1 = as_list(reads1)
+    s2 = as_list(reads2) if reads2 is not None else None
+    all_seq = s1 + (s2 if s2 is not None else [])
+    uniq = {}
+    for s in all_seq:
+        uniq[s] = uniq.get(s, 0) + 1
+    orc.coverage_reset()
+    ov = {}
+    for s in sorted(uniq):
+        ret, o = orc.assign(s, uniq[s])
+        ov[s] = o
+    frags = []
+    for i in range(len(s1)):
+        has_n = b"N" in s1[i] or (s2 is not None and b"N" in s2[i])
+        frags.append(orc.fragment_assign(ov[s1[i]], ov[s2[i]] if s2 is not None else None, has_n, max_assign))
+    groups, assigned = coalesce(frags)
+    n = orc.n
+    ecs, allele_ec = build_ecs(groups, n)
+    eff = [orc.effective_len(a) for a in range(n)]
+    gi, mi, eff = allele_info(names, eff, digit_units, delimiter)
+    missing = np.asarray([orc.missing_coverage(a) for a in range(n)], dtype=np.int32)
+    res = dict(uniq=ov, frags=frags, groups=groups, assigned=assigned, ecs=ecs, allele_ec=allele_ec, missing=missing,
+               eff_len=eff, gene=gi, major=mi)
+    if ecs:
+        P = em_problem(groups, ecs, allele_ec, eff, seq_weight)
+        it, x, rc = em(P["rowptr"], P["col"], P["count"], P["eclen"], P["x0"], min_alpha, filter_frac,
+                       P["ec_allele_ptr"], P["ec_alleles"], mi, gi)
+        ab, ecab = set_allele_abundance(rc, P["eclen"], ecs, n)
+        res.update(problem=P, iters=it, x=x, rc=rc, abundance=ab, ec_abundance=ecab)
+    else:
+        res.update(problem=None, iters=0, abundance=np.zeros(n), ec_abundance=np.zeros(n))
+    return res
+
+
+def seq_weights(records, weights):
+    """SeqSet::UpdateDnaSeqWeight (SeqSet.hpp:1008-1029): when any allele has non-adjacent exons (rnaData false,
+    SeqSet.hpp:705-713) every allele's weight becomes the summed weight of all alleles with its exon sequence."""
+    exons = [parse_exons(c, len(s)) for _, c, s in records]
+    dna = any(ex[i][0] > ex[i - 1][1] + 1 for ex in exons for i in range(1, len(ex)))
+    if not dna:
+        return list(weights)
+    keys = []
+    for (_, _, s), ex in zip(records, exons):
+        mask = np.zeros(len(s), dtype=bool)
+        for a, b in ex:
+            mask[a:min(b, len(s) - 1) + 1] = True
+        keys.append(np.frombuffer(s, dtype=np.uint8)[mask].tobytes())
+    tot = {}
+    for k, w in zip(keys, weights):
+        tot[k] = tot.get(k, 0) + w
+    return [tot[k] for k in keys]
