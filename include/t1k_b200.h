@@ -75,6 +75,14 @@ void t1k_assignment_destroy(T1KAssignment *a);
  * records: call once with records==NULL to get *total, then with a buffer of *total entries. */
 int t1k_assignment_fetch(T1KAssignment *a, uint64_t *row_ptr, int32_t *ret, T1KOverlap *records, uint64_t *total);
 
+/* Work counters of one t1k_assign_batch call, for roofline accounting (no reference counterpart). */
+typedef struct {
+  uint64_t postings, candidates, tiles, records;   /* postings read, seed overlaps chained, allele tiles, records kept */
+  float ms_kernel;                                 /* device time of k_assign (CUDA events) */
+  int32_t grid_blocks, hit_cap, n_sm;              /* launch geometry */
+} T1KAssignStats;
+int t1k_assignment_stats(const T1KAssignment *a, T1KAssignStats *out);
+
 /* posWeight[].count[consensus base] per base of every allele, concatenated by `offset` (Q11:
  * the only counter GetSeqMissingBaseCoverage reads, SeqSet.hpp:2727-2731). */
 int t1k_coverage_fetch(T1KRef *ref, int32_t *out /* [offset[n_alleles]] */);
@@ -113,6 +121,8 @@ typedef struct {
   double *x;              /* [n_ec] final ecAbundance0 */
   double *ec_read_count;  /* [n_ec] */
   int32_t iterations;
+  float ms_kernel;        /* device time of the whole EM loop (CUDA events) */
+  uint64_t n_launches;    /* kernels launched */
 } T1KEmResult;
 
 int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device);
@@ -137,7 +147,10 @@ typedef struct {
   int32_t em_iterations, n_groups, n_ec, assigned_fragments;
   uint64_t n_unique_ends, n_overlaps, n_assignments;
   double avg_alleles_per_read;
-  float ms_dedup, ms_align, ms_pair, ms_coalesce, ms_em;   /* device/host phase times of this call */
+  float ms_dedup, ms_align, ms_pair, ms_coalesce, ms_em;   /* wall time of the phases of this call (host clock) */
+  float ms_align_kernel, ms_pair_kernel, ms_em_kernel;      /* device time (CUDA events) inside k_assign / k_pair / the EM kernels */
+  uint64_t n_postings, n_candidates;                        /* k-mer postings read and seed overlaps chained (roofline accounting) */
+  uint64_t n_launches;                                      /* kernels launched by this call */
 } T1KGenotypeResult;
 
 int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t stride, uint32_t n_frag,

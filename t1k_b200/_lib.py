@@ -1,0 +1,117 @@
+"""ctypes binding of the C ABI declared in include/t1k_b200.h (t1k_b200/libt1k_b200.so).
+
+There is no CPU fallback: if the CUDA library has not been built, loading fails loudly
+(build it with `python -c "import __graft_entry__ as g; g.build()"` or `make -C t1k_b200/csrc`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libt1k_b200.so")
+
+OVERLAP_DT = np.dtype([(n, "<i4") for n in ("seqIdx", "readStart", "readEnd", "seqStart", "seqEnd", "strand",
+                                             "matchCnt", "relaxedMatchCnt", "leftClip", "rightClip")])
+ASSIGN_DT = np.dtype([("alleleIdx", "<i4"), ("start", "<i4"), ("end", "<i4"),
+                      ("weight", "<f4"), ("qual", "<f4"), ("adjustWeight", "<f4")])
+
+T1K_OK, T1K_ERR_NO_DEVICE, T1K_ERR_CUDA, T1K_ERR_ARG, T1K_ERR_UNSUPPORTED, T1K_ERR_NCCL = range(6)
+
+# every symbol include/t1k_b200.h declares
+EXPORTS = ["t1k_last_error", "t1k_device_count", "t1k_ref_create", "t1k_ref_destroy", "t1k_ref_n_alleles",
+           "t1k_assign_batch", "t1k_assignment_destroy", "t1k_assignment_fetch", "t1k_assignment_stats",
+           "t1k_coverage_fetch", "t1k_coverage_reset", "t1k_missing_coverage", "t1k_pair_batch", "t1k_free",
+           "t1k_em_run", "t1k_genotype"]
+
+
+class RefDesc(C.Structure):
+    _fields_ = [("n_alleles", C.c_int32), ("bases", C.c_char_p), ("offset", C.c_void_p), ("exon_ptr", C.c_void_p),
+                ("exon_se", C.c_void_p), ("similarity", C.c_double), ("relax_intron", C.c_int32), ("device", C.c_int32)]
+
+
+class EmProblem(C.Structure):
+    _fields_ = [("n_groups", C.c_int32), ("n_ec", C.c_int32), ("row_ptr", C.c_void_p), ("col", C.c_void_p),
+                ("count", C.c_void_p), ("ec_len", C.c_void_p), ("x0", C.c_void_p), ("min_squarem_alpha", C.c_double),
+                ("filter_frac", C.c_double), ("n_alleles", C.c_int32), ("n_major", C.c_int32), ("n_gene", C.c_int32),
+                ("ec_allele_ptr", C.c_void_p), ("ec_alleles", C.c_void_p), ("allele_major", C.c_void_p),
+                ("allele_gene", C.c_void_p)]
+
+
+class EmResult(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("ec_read_count", C.c_void_p), ("iterations", C.c_int32), ("ms_kernel", C.c_float),
+                ("n_launches", C.c_uint64)]
+
+
+class GenotypeParams(C.Structure):
+    _fields_ = [("max_assign", C.c_int32), ("min_squarem_alpha", C.c_double), ("filter_frac", C.c_double),
+                ("seq_weight", C.c_void_p), ("effective_len", C.c_void_p), ("allele_major", C.c_void_p),
+                ("allele_gene", C.c_void_p), ("n_major", C.c_int32), ("n_gene", C.c_int32)]
+
+
+class GenotypeResult(C.Structure):
+    _fields_ = [("n_alleles", C.c_int32), ("abundance", C.c_void_p), ("ec_abundance", C.c_void_p),
+                ("equivalent_class", C.c_void_p), ("missing_coverage", C.c_void_p), ("fragment_assigned", C.c_void_p),
+                ("em_iterations", C.c_int32), ("n_groups", C.c_int32), ("n_ec", C.c_int32),
+                ("assigned_fragments", C.c_int32), ("n_unique_ends", C.c_uint64), ("n_overlaps", C.c_uint64),
+                ("n_assignments", C.c_uint64), ("avg_alleles_per_read", C.c_double), ("ms_dedup", C.c_float),
+                ("ms_align", C.c_float), ("ms_pair", C.c_float), ("ms_coalesce", C.c_float), ("ms_em", C.c_float),
+                ("ms_align_kernel", C.c_float), ("ms_pair_kernel", C.c_float), ("ms_em_kernel", C.c_float),
+                ("n_postings", C.c_uint64), ("n_candidates", C.c_uint64), ("n_launches", C.c_uint64)]
+
+
+class AssignStats(C.Structure):
+    _fields_ = [("postings", C.c_uint64), ("candidates", C.c_uint64), ("tiles", C.c_uint64), ("records", C.c_uint64),
+                ("ms_kernel", C.c_float), ("grid_blocks", C.c_int32), ("hit_cap", C.c_int32), ("n_sm", C.c_int32)]
+
+
+class T1KError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("t1k_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError("t1k_b200: %s is missing — the CUDA library must be built (there is no CPU path)" % SO_PATH)
+        L = C.CDLL(SO_PATH)
+        L.t1k_last_error.restype = C.c_char_p
+        L.t1k_device_count.argtypes = [C.POINTER(C.c_int)]
+        L.t1k_ref_create.argtypes = [C.POINTER(RefDesc), C.POINTER(C.c_void_p)]
+        L.t1k_ref_destroy.argtypes = [C.c_void_p]
+        L.t1k_ref_destroy.restype = None
+        L.t1k_ref_n_alleles.argtypes = [C.c_void_p]
+        L.t1k_assign_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                       C.POINTER(C.c_void_p)]
+        L.t1k_assignment_destroy.argtypes = [C.c_void_p]
+        L.t1k_assignment_destroy.restype = None
+        L.t1k_assignment_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.t1k_assignment_stats.argtypes = [C.c_void_p, C.POINTER(AssignStats)]
+        L.t1k_coverage_fetch.argtypes = [C.c_void_p, C.c_void_p]
+        L.t1k_coverage_reset.argtypes = [C.c_void_p]
+        L.t1k_missing_coverage.argtypes = [C.c_void_p, C.c_void_p]
+        L.t1k_pair_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32,
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.t1k_free.argtypes = [C.c_void_p]
+        L.t1k_free.restype = None
+        L.t1k_em_run.argtypes = [C.POINTER(EmProblem), C.POINTER(EmResult), C.c_int32]
+        L.t1k_genotype.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                   C.POINTER(GenotypeParams), C.POINTER(GenotypeResult)]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != T1K_OK:
+        raise T1KError(rc, lib().t1k_last_error().decode(errors="replace"))
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None

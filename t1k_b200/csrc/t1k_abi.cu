@@ -1,0 +1,829 @@
+// C ABI of the B200 genotyping hot path (include/t1k_b200.h).  Host orchestration in C++, all compute in the
+// sm_100a kernels of t1k_kernels.cuh / t1k_pair.cuh / t1k_em.cuh.  There is no CPU fallback: without a CUDA
+// device every compute entry point fails with T1K_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <chrono>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/t1k_b200.h"
+#include "t1k_em.cuh"
+#include "t1k_host.hpp"
+#include "t1k_kernels.cuh"
+#include "t1k_model.hpp"
+#include "t1k_pair.cuh"
+
+using namespace t1k;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) {                                                                         \
+      char b_[512];                                                                                  \
+      snprintf(b_, sizeof(b_), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));   \
+      g_err = b_;                                                                                    \
+      return T1K_ERR_CUDA;                                                                           \
+    }                                                                                                \
+  } while (0)
+
+struct DevMem {   // owning device allocation
+  void *p = nullptr; size_t bytes = 0;
+  DevMem() {}
+  DevMem(const DevMem &) = delete;
+  DevMem &operator=(const DevMem &) = delete;
+  ~DevMem() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  cudaError_t alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n; else p = nullptr;
+    return e;
+  }
+  template <class T> T *as() const { return (T *)p; }
+  void swap(DevMem &o) { std::swap(p, o.p); std::swap(bytes, o.bytes); }
+};
+
+struct PinnedMem {
+  void *p = nullptr; size_t bytes = 0;
+  ~PinnedMem() { if (p) cudaFreeHost(p); }
+  cudaError_t ensure(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMallocHost(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  template <class T> T *as() const { return (T *)p; }
+};
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int pick_device(int want, int *out) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(T1K_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)"); }
+  int dev = want;
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+  if (dev >= n) return fail(T1K_ERR_ARG, "device ordinal out of range");
+  *out = dev;
+  return T1K_OK;
+}
+
+}  // namespace
+
+struct T1KRef {
+  int device = 0, nSM = 0;
+  int32_t nAlleles = 0;
+  std::vector<int64_t> offset;       // caller's concatenated layout
+  std::vector<u64> wordOff;
+  std::vector<int32_t> len;
+  size_t paddedBases = 0;
+  DevMem seq2, n2, ex2, dWordOff, dLen, kstart, post, covDiff, covPoint, covFinal;
+  RefView R;
+  cudaStream_t stream = nullptr;
+  // launch state of k_assign, sized on first use
+  DevMem candBuf, laneScratch, workCtr, errFlag, stats;
+  u32 candCap = 0;
+  int gridBlocks = 0, hitCap = 0;
+  u64 nPostings = 0;
+  bool covDirty = true;
+  ~T1KRef() { if (stream) cudaStreamDestroy(stream); }
+};
+
+struct T1KAssignment {
+  T1KRef *ref = nullptr;
+  u32 nReads = 0;
+  DevMem store, storeCtr, readOff, readCnt, readRet;
+  u64 storeCap = 0, storeUsed = 0;
+  u32 maxCnt = 0;
+  unsigned long long stats[4] = {0, 0, 0, 0};
+  float msKernel = 0;
+  u32 launches = 0;
+};
+
+extern "C" {
+
+const char *t1k_last_error(void) { return g_err.c_str(); }
+
+int t1k_device_count(int *count) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  if (count) *count = n;
+  return T1K_OK;
+}
+
+int t1k_ref_create(const T1KRefDesc *d, T1KRef **out) {
+  if (!d || !out || d->n_alleles <= 0 || !d->bases || !d->offset || !d->exon_ptr || !d->exon_se) return fail(T1K_ERR_ARG, "t1k_ref_create: bad argument");
+  *out = nullptr;
+  int dev;
+  if (int rc = pick_device(d->device, &dev)) return rc;
+  CK(cudaSetDevice(dev));
+  if (d->n_alleles >= (1 << 24)) return fail(T1K_ERR_UNSUPPORTED, "more than 2^24 alleles");
+  PackedRef P;
+  if (!pack_reference(d->n_alleles, d->bases, d->offset, d->exon_ptr, d->exon_se, P))
+    return fail(T1K_ERR_ARG, "reference contains a character outside ACGTN");
+  for (int i = 0; i < d->n_alleles; ++i)
+    if (P.len[i] >= (1 << 24)) return fail(T1K_ERR_UNSUPPORTED, "allele longer than 2^24 bases");
+  T1KRef *r = new T1KRef;
+  r->device = dev;
+  r->nAlleles = d->n_alleles;
+  r->offset.assign(d->offset, d->offset + d->n_alleles + 1);
+  r->wordOff = P.wordOff; r->len = P.len;
+  r->paddedBases = P.totalWords * 32;
+  r->nPostings = P.post.size();
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) { delete r; return fail(T1K_ERR_CUDA, cudaGetErrorString(e)); }
+  r->nSM = prop.multiProcessorCount;
+#define UP(dst, vec)                                                                                        \
+  do {                                                                                                      \
+    e = r->dst.alloc((vec).size() * sizeof((vec)[0]));                                                      \
+    if (e == cudaSuccess) e = cudaMemcpy(r->dst.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice); \
+    if (e != cudaSuccess) { delete r; return fail(T1K_ERR_CUDA, std::string("t1k_ref_create upload: ") + cudaGetErrorString(e)); } \
+  } while (0)
+  UP(seq2, P.seq2); UP(n2, P.n2); UP(ex2, P.ex2); UP(dWordOff, P.wordOff); UP(dLen, P.len); UP(kstart, P.kstart);
+  if (P.post.empty()) P.post.resize(1);
+  UP(post, P.post);
+#undef UP
+  const size_t covBytes = r->paddedBases * sizeof(int32_t);
+  e = r->covDiff.alloc(covBytes);
+  if (e == cudaSuccess) e = r->covPoint.alloc(covBytes);
+  if (e == cudaSuccess) e = r->covFinal.alloc(covBytes);
+  if (e == cudaSuccess) e = cudaMemset(r->covDiff.p, 0, covBytes);
+  if (e == cudaSuccess) e = cudaMemset(r->covPoint.p, 0, covBytes);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete r; return fail(T1K_ERR_CUDA, std::string("t1k_ref_create: ") + cudaGetErrorString(e)); }
+  RefView &R = r->R;
+  R.seq2 = r->seq2.as<u64>(); R.n2 = r->n2.as<u64>(); R.ex2 = r->ex2.as<u64>();
+  R.wordOff = r->dWordOff.as<u64>(); R.len = r->dLen.as<int32_t>();
+  R.kstart = r->kstart.as<u32>(); R.post = r->post.as<Posting>();
+  R.covDiff = r->covDiff.as<int32_t>(); R.covPoint = r->covPoint.as<int32_t>();
+  R.nAlleles = d->n_alleles; R.sim = d->similarity; R.relax = d->relax_intron;
+  *out = r;
+  return T1K_OK;
+}
+
+void t1k_ref_destroy(T1KRef *ref) {
+  if (!ref) return;
+  cudaSetDevice(ref->device);
+  delete ref;
+}
+
+int t1k_ref_n_alleles(const T1KRef *ref) { return ref ? ref->nAlleles : 0; }
+
+}  // extern "C"
+
+namespace {
+
+// persistent launch geometry of k_assign for reads up to maxLen bases
+int setup_assign_launch(T1KRef *r, int maxLen) {
+  int hitCap = maxLen - KMER + 1 + 24;
+  if (hitCap < 64) hitCap = 64;
+  hitCap = (hitCap + 7) & ~7;
+  if (r->gridBlocks && hitCap <= r->hitCap) return T1K_OK;
+  const size_t perWarp = (warp_smem_bytes(hitCap) + 15) & ~(size_t)15;
+  const size_t smem = perWarp * WARPS_PER_BLOCK;
+  CK(cudaFuncSetAttribute(k_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int perSM = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_assign, WARPS_PER_BLOCK * 32, smem));
+  if (perSM < 1) return fail(T1K_ERR_UNSUPPORTED, "k_assign does not fit on an SM");
+  r->hitCap = hitCap;
+  r->gridBlocks = perSM * r->nSM;
+  const size_t warps = (size_t)r->gridBlocks * WARPS_PER_BLOCK;
+  u64 cap = 2ull * (u64)r->nAlleles + 2048;
+  if (cap > (1u << 20)) cap = 1u << 20;
+  r->candCap = (u32)cap;
+  CK(r->candBuf.alloc(warps * r->candCap * sizeof(Cand)));
+  CK(r->laneScratch.alloc(warps * 32 * (size_t)SCR_BYTES));
+  CK(r->workCtr.alloc(sizeof(unsigned int)));
+  CK(r->errFlag.alloc(sizeof(int)));
+  CK(r->stats.alloc(4 * sizeof(unsigned long long)));
+  return T1K_OK;
+}
+
+std::string decode_err(int err) {
+  std::string s;
+  if (err & ERR_BAND) s += " alignment band wider than the supported envelope;";
+  if (err & ERR_SCRATCH) s += " chaining scratch overflow;";
+  if (err & ERR_EMIT) s += " more than MAX_EMIT seed overlaps for one (read, allele);";
+  if (err & ERR_CAND) s += " candidate buffer overflow;";
+  if (err & ERR_HITS) s += " more k-mer hits on one allele than the shared-memory tile holds;";
+  return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const uint32_t *len, const int32_t *weight,
+                     uint32_t n, T1KAssignment **out) {
+  if (!ref || !out || (n > 0 && (!bases || !off || !len || !weight))) return fail(T1K_ERR_ARG, "t1k_assign_batch: bad argument");
+  *out = nullptr;
+  CK(cudaSetDevice(ref->device));
+  cudaStream_t st = ref->stream;
+  size_t total = 0; int maxLen = KMER;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (len[i] > T1K_MAX_READ_LEN) return fail(T1K_ERR_ARG, "read longer than T1K_MAX_READ_LEN");
+    total = std::max(total, (size_t)(off[i] + len[i]));
+    maxLen = std::max(maxLen, (int)len[i]);
+  }
+  if (int rc = setup_assign_launch(ref, maxLen)) return rc;
+  T1KAssignment *a = new T1KAssignment;
+  struct Guard { T1KAssignment *a; ~Guard() { delete a; } } guard{a};
+  a->ref = ref; a->nReads = n;
+  DevMem dBases, dOff, dLen, dW, planes, len16;
+  CK(dBases.alloc(total)); CK(dOff.alloc((size_t)n * 8)); CK(dLen.alloc((size_t)n * 4)); CK(dW.alloc((size_t)n * 4));
+  CK(planes.alloc((size_t)n * 4 * RWORDS * 8)); CK(len16.alloc((size_t)n * 2));
+  CK(a->readOff.alloc((size_t)n * 8)); CK(a->readCnt.alloc((size_t)n * 4)); CK(a->readRet.alloc((size_t)n * 4));
+  CK(a->storeCtr.alloc(8));
+  if (n == 0) { guard.a = nullptr; *out = a; return T1K_OK; }
+  CK(cudaMemcpyAsync(dBases.p, bases, total, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dOff.p, off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dLen.p, len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dW.p, weight, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(ref->errFlag.p, 0, sizeof(int), st));
+  CK(cudaMemsetAsync(ref->stats.p, 0, 4 * sizeof(unsigned long long), st));
+  CK(cudaMemsetAsync(a->storeCtr.p, 0, 8, st));
+  k_pack_reads<<<(n + 127) / 128, 128, 0, st>>>(dBases.as<char>(), dOff.as<u64>(), dLen.as<u32>(), n, planes.as<u64>(), len16.as<u16>(),
+                                                  ref->errFlag.as<int>());
+  CK(cudaGetLastError());
+  // record store: sized from free memory, grown (and only the deferred read-ends re-run) if it fills up
+  size_t freeB = 0, totB = 0;
+  CK(cudaMemGetInfo(&freeB, &totB));
+  u64 cap = std::max<u64>((u64)n * 512, 1u << 20);
+  const u64 capMax = (u64)(freeB * 0.80) / sizeof(Rec);
+  if (cap > capMax) cap = capMax;
+  if (const char *envCap = getenv("T1K_STORE_RECORDS")) cap = std::max<u64>(1024, strtoull(envCap, nullptr, 10));
+  CK(a->store.alloc(cap * sizeof(Rec)));
+  a->storeCap = cap;
+  AssignParams P;
+  P.R = ref->R;
+  P.Q.planes = planes.as<u64>(); P.Q.len = len16.as<u16>(); P.Q.weight = dW.as<int32_t>(); P.Q.workList = nullptr; P.Q.nWork = n;
+  P.O.store = a->store.as<Rec>(); P.O.storeCtr = a->storeCtr.as<unsigned long long>(); P.O.storeCap = cap;
+  P.O.readOff = a->readOff.as<u64>(); P.O.readCnt = a->readCnt.as<u32>(); P.O.readRet = a->readRet.as<int32_t>();
+  P.O.err = ref->errFlag.as<int>(); P.O.stats = ref->stats.as<unsigned long long>();
+  P.candBuf = ref->candBuf.as<Cand>(); P.candCap = ref->candCap; P.laneScratch = ref->laneScratch.as<u8>();
+  P.workCtr = ref->workCtr.as<unsigned int>(); P.hitCap = ref->hitCap;
+  const size_t smem = ((warp_smem_bytes(ref->hitCap) + 15) & ~(size_t)15) * WARPS_PER_BLOCK;
+  DevMem workList;
+  std::vector<int32_t> hRet;
+  cudaEvent_t ev0, ev1;
+  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+  struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
+  for (int round = 0;; ++round) {
+    CK(cudaMemsetAsync(ref->workCtr.p, 0, sizeof(unsigned int), st));
+    CK(cudaEventRecord(ev0, st));
+    k_assign<<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ev1, st));
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, ref->errFlag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    a->msKernel += ms; ++a->launches;
+    ref->covDirty = true;
+    if (err & (ERR_READ_LEN | ERR_READ_CHAR)) return fail(T1K_ERR_ARG, "read contains a character outside ACGTN or is too long");
+    if (err & ~ERR_STORE) return fail(T1K_ERR_UNSUPPORTED, "t1k_assign_batch:" + decode_err(err));
+    if (!(err & ERR_STORE)) break;
+    // some read-ends did not fit: grow the store and re-run exactly those (they added no coverage)
+    hRet.resize(n);
+    CK(cudaMemcpy(hRet.data(), a->readRet.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    std::vector<u32> todo;
+    for (u32 i = 0; i < n; ++i) if (hRet[i] == -2) todo.push_back(i);
+    CK(cudaMemGetInfo(&freeB, &totB));
+    u64 newCap = cap * 2;
+    if ((newCap - 0) * sizeof(Rec) > (u64)(freeB * 0.9)) newCap = (u64)(freeB * 0.9) / sizeof(Rec);
+    if (newCap <= cap + 1024 || round > 12) return fail(T1K_ERR_UNSUPPORTED, "overlap record store does not fit in device memory; use smaller batches");
+    DevMem bigger;
+    CK(bigger.alloc(newCap * sizeof(Rec)));
+    CK(cudaMemcpyAsync(bigger.p, a->store.p, cap * sizeof(Rec), cudaMemcpyDeviceToDevice, st));
+    unsigned long long ctr = cap;   // holes left by failed reservations stay unused
+    CK(cudaMemcpyAsync(a->storeCtr.p, &ctr, 8, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    a->store.swap(bigger);
+    cap = newCap; a->storeCap = cap;
+    CK(workList.alloc(todo.size() * 4));
+    CK(cudaMemcpyAsync(workList.p, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ref->errFlag.p, 0, sizeof(int), st));
+    P.O.store = a->store.as<Rec>(); P.O.storeCap = cap;
+    P.Q.workList = workList.as<u32>(); P.Q.nWork = (u32)todo.size();
+  }
+  unsigned long long used = 0;
+  CK(cudaMemcpy(&used, a->storeCtr.p, 8, cudaMemcpyDeviceToHost));
+  a->storeUsed = used;
+  CK(cudaMemcpy(a->stats, ref->stats.p, sizeof(a->stats), cudaMemcpyDeviceToHost));
+  guard.a = nullptr;
+  *out = a;
+  return T1K_OK;
+}
+
+int t1k_assignment_stats(const T1KAssignment *a, T1KAssignStats *out) {
+  if (!a || !out) return fail(T1K_ERR_ARG, "t1k_assignment_stats: bad argument");
+  out->postings = a->stats[0]; out->candidates = a->stats[1]; out->tiles = a->stats[2]; out->records = a->storeUsed;
+  out->ms_kernel = a->msKernel; out->grid_blocks = a->ref->gridBlocks; out->hit_cap = a->ref->hitCap; out->n_sm = a->ref->nSM;
+  return T1K_OK;
+}
+
+void t1k_assignment_destroy(T1KAssignment *a) {
+  if (!a) return;
+  if (a->ref) cudaSetDevice(a->ref->device);
+  delete a;
+}
+
+int t1k_assignment_fetch(T1KAssignment *a, uint64_t *row_ptr, int32_t *ret, T1KOverlap *records, uint64_t *total) {
+  if (!a || !total) return fail(T1K_ERR_ARG, "t1k_assignment_fetch: bad argument");
+  CK(cudaSetDevice(a->ref->device));
+  const u32 n = a->nReads;
+  std::vector<u64> off(n); std::vector<u32> cnt(n);
+  if (n) {
+    CK(cudaMemcpy(off.data(), a->readOff.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cnt.data(), a->readCnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  }
+  u64 tot = 0;
+  for (u32 i = 0; i < n; ++i) tot += cnt[i];
+  *total = tot;
+  if (row_ptr) { row_ptr[0] = 0; for (u32 i = 0; i < n; ++i) row_ptr[i + 1] = row_ptr[i] + cnt[i]; }
+  if (ret && n) CK(cudaMemcpy(ret, a->readRet.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (!records || tot == 0) return T1K_OK;
+  const u64 used = std::min(a->storeUsed, a->storeCap);
+  std::vector<Rec> st(used);
+  CK(cudaMemcpy(st.data(), a->store.p, used * sizeof(Rec), cudaMemcpyDeviceToHost));
+  // unpack into the reference's output order: list-order key, then candidate order (== store order)
+  std::vector<u32> idx;
+  u64 w = 0;
+  for (u32 i = 0; i < n; ++i) {
+    idx.resize(cnt[i]);
+    std::iota(idx.begin(), idx.end(), 0u);
+    const Rec *L = st.data() + off[i];
+    std::stable_sort(idx.begin(), idx.end(), [L](u32 x, u32 y) { return L[x].key < L[y].key; });
+    for (u32 k = 0; k < cnt[i]; ++k, ++w) {
+      const Rec &r = L[idx[k]];
+      T1KOverlap &o = records[w];
+      o.seqIdx = r.seqIdx; o.seqStart = r.seqStart; o.seqEnd = r.seqEnd;
+      o.readStart = (int32_t)(r.packed & 255); o.readEnd = (int32_t)((r.packed >> 8) & 255);
+      o.leftClip = (int32_t)((r.packed >> 16) & 255); o.rightClip = (int32_t)(r.packed >> 24);
+      o.matchCnt = (int32_t)(r.mcStrand & 0x7fffffffu); o.strand = (r.mcStrand >> 31) ? 1 : -1;
+      o.relaxedMatchCnt = r.relaxed;
+    }
+  }
+  return T1K_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+__global__ void k_cov_prefix(RefView R, int32_t *covFinal) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= R.nAlleles) return;
+  const size_t cb = (size_t)R.wordOff[a] * 32;
+  int run = 0;
+  const int n = R.len[a];
+  for (int j = 0; j < n; ++j) { run += R.covDiff[cb + j]; covFinal[cb + j] = run + R.covPoint[cb + j]; }
+}
+
+// SeqSet::GetSeqMissingBaseCoverage(a, 0.01) (SeqSet.hpp:2717-2755), one warp per allele: the median of the
+// exonic coverages by bisection on the value, then the count below max(1, 1 % of the median).
+__global__ void k_missing_coverage(RefView R, const int32_t *covFinal, int32_t *out) {
+  const int a = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (a >= R.nAlleles) return;
+  const u64 w0 = R.wordOff[a];
+  const size_t cb = (size_t)w0 * 32;
+  const int n = R.len[a];
+  int nEx = 0, mx = 0;
+  for (int j = lane; j < n; j += 32)
+    if (base2(R.ex2, w0, j)) { ++nEx; const int c = base2(R.n2, w0, j) ? 0 : covFinal[cb + j]; mx = max(mx, c); }
+  nEx = warp_sum_i32(nEx); mx = warp_max_i32(mx);
+  if (nEx == 0) { if (lane == 0) out[a] = 0; return; }
+  const int k = nEx / 2;            // median = element k of the sorted list
+  int lo = 0, hi = mx;              // smallest v with count(c <= v) >= k + 1
+  while (lo < hi) {
+    const int mid = lo + (hi - lo) / 2;
+    int c = 0;
+    for (int j = lane; j < n; j += 32)
+      if (base2(R.ex2, w0, j)) { const int v = base2(R.n2, w0, j) ? 0 : covFinal[cb + j]; c += v <= mid; }
+    c = warp_sum_i32(c);
+    if (c >= k + 1) hi = mid; else lo = mid + 1;
+  }
+  double cutoff = lo * 0.01;
+  if (cutoff < 1) cutoff = 1;
+  int miss = 0;
+  for (int j = lane; j < n; j += 32)
+    if (base2(R.ex2, w0, j)) { const int v = base2(R.n2, w0, j) ? 0 : covFinal[cb + j]; miss += (double)v < cutoff; }
+  miss = warp_sum_i32(miss);
+  if (lane == 0) out[a] = miss;
+}
+
+int finalize_coverage(T1KRef *ref) {
+  if (!ref->covDirty) return T1K_OK;
+  k_cov_prefix<<<(ref->nAlleles + 127) / 128, 128, 0, ref->stream>>>(ref->R, ref->covFinal.as<int32_t>());
+  CK(cudaGetLastError());
+  ref->covDirty = false;
+  return T1K_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int t1k_coverage_fetch(T1KRef *ref, int32_t *out) {
+  if (!ref || !out) return fail(T1K_ERR_ARG, "t1k_coverage_fetch: bad argument");
+  CK(cudaSetDevice(ref->device));
+  if (int rc = finalize_coverage(ref)) return rc;
+  std::vector<int32_t> h(ref->paddedBases);
+  CK(cudaMemcpyAsync(h.data(), ref->covFinal.p, ref->paddedBases * 4, cudaMemcpyDeviceToHost, ref->stream));
+  CK(cudaStreamSynchronize(ref->stream));
+  for (int32_t a = 0; a < ref->nAlleles; ++a)
+    memcpy(out + ref->offset[a], h.data() + (size_t)ref->wordOff[a] * 32, (size_t)ref->len[a] * 4);
+  return T1K_OK;
+}
+
+int t1k_coverage_reset(T1KRef *ref) {
+  if (!ref) return fail(T1K_ERR_ARG, "t1k_coverage_reset: bad argument");
+  CK(cudaSetDevice(ref->device));
+  CK(cudaMemsetAsync(ref->covDiff.p, 0, ref->paddedBases * 4, ref->stream));
+  CK(cudaMemsetAsync(ref->covPoint.p, 0, ref->paddedBases * 4, ref->stream));
+  CK(cudaStreamSynchronize(ref->stream));
+  ref->covDirty = true;
+  return T1K_OK;
+}
+
+int t1k_missing_coverage(T1KRef *ref, int32_t *out) {
+  if (!ref || !out) return fail(T1K_ERR_ARG, "t1k_missing_coverage: bad argument");
+  CK(cudaSetDevice(ref->device));
+  if (int rc = finalize_coverage(ref)) return rc;
+  DevMem d;
+  CK(d.alloc((size_t)ref->nAlleles * 4));
+  const size_t threads = (size_t)ref->nAlleles * 32;
+  k_missing_coverage<<<(unsigned)((threads + 127) / 128), 128, 0, ref->stream>>>(ref->R, ref->covFinal.as<int32_t>(), d.as<int32_t>());
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, d.p, (size_t)ref->nAlleles * 4, cudaMemcpyDeviceToHost, ref->stream));
+  CK(cudaStreamSynchronize(ref->stream));
+  return T1K_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// Pairing of fragments [0, nFrag) against the resident lists of `a`.  Rows come back in allele order;
+// `wantOrder` additionally returns the keys that give the reference's own row order.
+struct PairHost {
+  std::vector<u64> rowPtr;            // [nFrag + 1]
+  std::vector<HostEntry> entries;
+  std::vector<u64> ordKey; std::vector<u32> ordIdx;
+  float msKernel = 0;
+  u32 launches = 1;
+};
+
+int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const uint32_t *end2, const uint8_t *hasN, uint32_t nFrag,
+                   int maxAssign, bool wantOrder, PairHost &H) {
+  cudaStream_t st = ref->stream;
+  H.rowPtr.assign((size_t)nFrag + 1, 0);
+  H.entries.clear(); H.ordKey.clear(); H.ordIdx.clear();
+  if (nFrag == 0) return T1K_OK;
+  for (uint32_t i = 0; i < nFrag; ++i)
+    if (end1[i] >= a->nReads || (end2 && end2[i] >= a->nReads)) return fail(T1K_ERR_ARG, "t1k_pair_batch: read-end index out of range");
+  DevMem dE1, dE2, dN, dUb, dRowOff, dRowCnt, dDstOff, dOut, dKey, dIdx, dCompact, dCKey, dCIdx, dCtr;
+  CK(dE1.alloc((size_t)nFrag * 4));
+  CK(cudaMemcpyAsync(dE1.p, end1, (size_t)nFrag * 4, cudaMemcpyHostToDevice, st));
+  if (end2) { CK(dE2.alloc((size_t)nFrag * 4)); CK(cudaMemcpyAsync(dE2.p, end2, (size_t)nFrag * 4, cudaMemcpyHostToDevice, st)); }
+  if (hasN) { CK(dN.alloc(nFrag)); CK(cudaMemcpyAsync(dN.p, hasN, nFrag, cudaMemcpyHostToDevice, st)); }
+  CK(dUb.alloc((size_t)nFrag * 4)); CK(dCtr.alloc(4));
+  k_pair_bound<<<(nFrag + 255) / 256, 256, 0, st>>>(a->readCnt.as<u32>(), dE1.as<u32>(), end2 ? dE2.as<u32>() : nullptr, 0, nFrag, maxAssign, dUb.as<u32>());
+  CK(cudaGetLastError());
+  std::vector<u32> ub(nFrag);
+  CK(cudaMemcpyAsync(ub.data(), dUb.p, (size_t)nFrag * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  // sub-batches bounded by the upper-bound row space
+  size_t freeB = 0, totB = 0;
+  CK(cudaMemGetInfo(&freeB, &totB));
+  const size_t perSlot = sizeof(PairEntry) * 2 + (wantOrder ? 24 : 0);
+  u64 slotCap = std::max<u64>(1u << 20, std::min<u64>((u64)(freeB * 0.5) / perSlot, 1ull << 28));
+  cudaEvent_t ev0, ev1;
+  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+  struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
+  std::vector<u64> rowOff, dstOff; std::vector<u32> rowCnt;
+  u64 allocSlots = 0, allocDense = 0;
+  for (u32 f0 = 0; f0 < nFrag;) {
+    u32 f1 = f0; u64 slots = 0;
+    while (f1 < nFrag && (f1 == f0 || slots + ub[f1] <= slotCap)) { slots += ub[f1]; ++f1; }
+    const u32 m = f1 - f0;
+    rowOff.resize(m);
+    { u64 s = 0; for (u32 i = 0; i < m; ++i) { rowOff[i] = s; s += ub[f0 + i]; } }
+    if (slots > allocSlots) {
+      allocSlots = slots;
+      CK(dOut.alloc(slots * sizeof(PairEntry)));
+      if (wantOrder) { CK(dKey.alloc(slots * 8)); CK(dIdx.alloc(slots * 4)); }
+    }
+    CK(dRowOff.alloc((size_t)m * 8)); CK(dRowCnt.alloc((size_t)m * 4)); CK(dDstOff.alloc((size_t)m * 8));
+    CK(cudaMemcpyAsync(dRowOff.p, rowOff.data(), (size_t)m * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(dCtr.p, 0, 4, st));
+    PairParams P;
+    P.R = ref->R; P.store = a->store.as<Rec>(); P.readOff = a->readOff.as<u64>(); P.readCnt = a->readCnt.as<u32>();
+    P.end1 = dE1.as<u32>(); P.end2 = end2 ? dE2.as<u32>() : nullptr; P.hasN = hasN ? dN.as<u8>() : nullptr;
+    P.fragBase = f0; P.nFrag = m; P.maxAssign = maxAssign;
+    P.rowOff = dRowOff.as<u64>(); P.out = dOut.as<PairEntry>();
+    P.ordKey = wantOrder ? dKey.as<u64>() : nullptr; P.ordIdx = wantOrder ? dIdx.as<u32>() : nullptr;
+    P.rowCnt = dRowCnt.as<u32>(); P.rowHash = nullptr; P.workCtr = dCtr.as<unsigned int>();
+    const int blocks = std::max(1, std::min<int>((int)((m + 3) / 4), ref->nSM * 8));
+    CK(cudaEventRecord(ev0, st));
+    k_pair<<<blocks, 128, 0, st>>>(P);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ev1, st));
+    rowCnt.resize(m);
+    CK(cudaMemcpyAsync(rowCnt.data(), dRowCnt.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, ev0, ev1)); H.msKernel += ms; H.launches += 2;
+    dstOff.resize(m);
+    u64 dense = 0;
+    for (u32 i = 0; i < m; ++i) { dstOff[i] = dense; dense += rowCnt[i]; H.rowPtr[(size_t)f0 + i + 1] = rowCnt[i]; }
+    if (dense > 0) {
+      if (dense > allocDense) {
+        allocDense = dense;
+        CK(dCompact.alloc(dense * sizeof(PairEntry)));
+        if (wantOrder) { CK(dCKey.alloc(dense * 8)); CK(dCIdx.alloc(dense * 4)); }
+      }
+      CK(cudaMemcpyAsync(dDstOff.p, dstOff.data(), (size_t)m * 8, cudaMemcpyHostToDevice, st));
+      const size_t threads = (size_t)m * 32;
+      k_pair_compact<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(dOut.as<PairEntry>(), dRowOff.as<u64>(), dDstOff.as<u64>(), dRowCnt.as<u32>(), m,
+                                                                        dCompact.as<PairEntry>(), wantOrder ? dKey.as<u64>() : nullptr,
+                                                                        wantOrder ? dIdx.as<u32>() : nullptr, wantOrder ? dCKey.as<u64>() : nullptr,
+                                                                        wantOrder ? dCIdx.as<u32>() : nullptr);
+      CK(cudaGetLastError());
+      const size_t base = H.entries.size();
+      H.entries.resize(base + dense);
+      CK(cudaMemcpyAsync(H.entries.data() + base, dCompact.p, dense * sizeof(PairEntry), cudaMemcpyDeviceToHost, st));
+      if (wantOrder) {
+        H.ordKey.resize(base + dense); H.ordIdx.resize(base + dense);
+        CK(cudaMemcpyAsync(H.ordKey.data() + base, dCKey.p, dense * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(H.ordIdx.data() + base, dCIdx.p, dense * 4, cudaMemcpyDeviceToHost, st));
+      }
+      CK(cudaStreamSynchronize(st));
+    }
+    f0 = f1;
+  }
+  for (u32 i = 0; i < nFrag; ++i) H.rowPtr[i + 1] += H.rowPtr[i];
+  return T1K_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int t1k_pair_batch(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const uint32_t *end2, const uint8_t *has_n,
+                   uint32_t n_frag, int32_t max_assign, uint64_t **row_ptr, T1KReadAssignment **entries) {
+  if (!ref || !a || !row_ptr || !entries || (n_frag > 0 && !end1)) return fail(T1K_ERR_ARG, "t1k_pair_batch: bad argument");
+  static_assert(sizeof(T1KReadAssignment) == sizeof(HostEntry) && sizeof(HostEntry) == sizeof(PairEntry), "layout");
+  CK(cudaSetDevice(ref->device));
+  PairHost H;
+  if (int rc = pair_fragments(ref, a, end1, end2, has_n, n_frag, max_assign, true, H)) return rc;
+  uint64_t *rp = (uint64_t *)malloc(((size_t)n_frag + 1) * 8);
+  T1KReadAssignment *en = (T1KReadAssignment *)malloc(std::max<size_t>(1, H.entries.size()) * sizeof(T1KReadAssignment));
+  if (!rp || !en) { free(rp); free(en); return fail(T1K_ERR_ARG, "out of host memory"); }
+  memcpy(rp, H.rowPtr.data(), ((size_t)n_frag + 1) * 8);
+  // the reference's row order: by the list position of each allele's first candidate (SeqSet.hpp:2440-2455)
+  std::vector<u32> idx;
+  for (uint32_t f = 0; f < n_frag; ++f) {
+    const u64 b = H.rowPtr[f], e = H.rowPtr[f + 1];
+    idx.resize(e - b);
+    std::iota(idx.begin(), idx.end(), 0u);
+    const u64 *k = H.ordKey.data() + b; const u32 *ki = H.ordIdx.data() + b;
+    std::sort(idx.begin(), idx.end(), [k, ki](u32 x, u32 y) { return k[x] != k[y] ? k[x] < k[y] : ki[x] < ki[y]; });
+    for (u64 j = 0; j < e - b; ++j) memcpy(&en[b + j], &H.entries[b + idx[j]], sizeof(HostEntry));
+  }
+  *row_ptr = rp; *entries = en;
+  return T1K_OK;
+}
+
+void t1k_free(void *p) { free(p); }
+
+int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
+  if (!p || !r || !r->x || !r->ec_read_count || p->n_ec <= 0 || p->n_groups < 0 || !p->row_ptr || !p->ec_len || !p->x0)
+    return fail(T1K_ERR_ARG, "t1k_em_run: bad argument");
+  int dev;
+  if (int rc = pick_device(device, &dev)) return rc;
+  CK(cudaSetDevice(dev));
+  const int G = p->n_groups, E = p->n_ec;
+  const int64_t nnz = p->row_ptr[G];
+  for (int64_t k = 0; k < nnz; ++k) if (p->col[k] < 0 || p->col[k] >= E) return fail(T1K_ERR_ARG, "t1k_em_run: column index out of range");
+  // CSC with ascending group order inside every column => fixed summation order
+  std::vector<int64_t> colPtr((size_t)E + 1, 0);
+  for (int64_t k = 0; k < nnz; ++k) ++colPtr[p->col[k] + 1];
+  for (int e = 0; e < E; ++e) colPtr[e + 1] += colPtr[e];
+  std::vector<int32_t> rowIdx((size_t)std::max<int64_t>(nnz, 1));
+  {
+    std::vector<int64_t> cur(colPtr.begin(), colPtr.end() - 1);
+    for (int g = 0; g < G; ++g) for (int64_t k = p->row_ptr[g]; k < p->row_ptr[g + 1]; ++k) rowIdx[cur[p->col[k]]++] = g;
+  }
+  cudaStream_t st;
+  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  struct StGuard { cudaStream_t s; ~StGuard() { cudaStreamDestroy(s); } } sg{st};
+  DevMem dRowPtr, dCol, dColPtr, dRowIdx, dCount, dLen, dPsum, dRc, dX0, dX1, dX2, dX3, dDiff;
+  CK(dRowPtr.alloc(((size_t)G + 1) * 8)); CK(dCol.alloc((size_t)nnz * 4)); CK(dColPtr.alloc(((size_t)E + 1) * 8)); CK(dRowIdx.alloc((size_t)nnz * 4));
+  CK(dCount.alloc((size_t)G * 8)); CK(dLen.alloc((size_t)E * 4)); CK(dPsum.alloc((size_t)G * 8)); CK(dRc.alloc((size_t)E * 8));
+  CK(dX0.alloc((size_t)E * 8)); CK(dX1.alloc((size_t)E * 8)); CK(dX2.alloc((size_t)E * 8)); CK(dX3.alloc((size_t)E * 8)); CK(dDiff.alloc(8));
+  CK(cudaMemcpyAsync(dRowPtr.p, p->row_ptr, ((size_t)G + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (nnz) CK(cudaMemcpyAsync(dCol.p, p->col, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dColPtr.p, colPtr.data(), ((size_t)E + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (nnz) CK(cudaMemcpyAsync(dRowIdx.p, rowIdx.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+  if (G) CK(cudaMemcpyAsync(dCount.p, p->count, (size_t)G * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dLen.p, p->ec_len, (size_t)E * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dX0.p, p->x0, (size_t)E * 8, cudaMemcpyHostToDevice, st));
+  const unsigned gRow = (unsigned)(((size_t)G * 32 + 255) / 256), gCol = (unsigned)(((size_t)E * 32 + 255) / 256);
+  cudaEvent_t ev0, ev1;
+  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+  struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
+  CK(cudaEventRecord(ev0, st));
+  uint64_t launches = 0;
+  auto em_update = [&](const double *xin, double *xout) -> int {   // Genotyper::EMupdate
+    if (G) k_em_rowsum<<<gRow, 256, 0, st>>>(G, dRowPtr.as<int64_t>(), dCol.as<int32_t>(), xin, dPsum.as<double>());
+    k_em_colsum<<<gCol, 256, 0, st>>>(E, dColPtr.as<int64_t>(), dRowIdx.as<int32_t>(), dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
+    k_em_mstep<<<1, 1024, 0, st>>>(E, dRc.as<double>(), dLen.as<int32_t>(), xout);
+    CK(cudaGetLastError());
+    launches += G ? 3 : 2;
+    return T1K_OK;
+  };
+  const int maxIter = 1000;
+  int ret = 0;
+  std::vector<double> hRc(E), hX(E);
+  const bool mask = p->n_alleles > 0 && p->ec_allele_ptr && p->ec_alleles && p->allele_major && p->allele_gene;
+  for (int t = 0; t < maxIter; ++t) {     // Genotyper.hpp:1234-1314
+    ++ret;
+    if (int rc = em_update(dX0.as<double>(), dX1.as<double>())) return rc;
+    if (int rc = em_update(dX1.as<double>(), dX2.as<double>())) return rc;
+    k_em_squarem<<<1, 1024, 0, st>>>(E, dX0.as<double>(), dX1.as<double>(), dX2.as<double>(), p->min_squarem_alpha, dX3.as<double>());
+    if (int rc = em_update(dX3.as<double>(), dX1.as<double>())) return rc;
+    k_em_advance<<<1, 1024, 0, st>>>(E, dX0.as<double>(), dX1.as<double>(), dDiff.as<double>());
+    CK(cudaGetLastError());
+    launches += 2;
+    double diff = 0;
+    CK(cudaMemcpyAsync(&diff, dDiff.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (diff < 1e-5 && t < maxIter - 2) t = maxIter - 2;
+    if (t > 0 && t % 10 == 0 && mask) {
+      CK(cudaMemcpyAsync(hRc.data(), dRc.p, (size_t)E * 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      em_mask(hRc.data(), p->ec_len, p->ec_allele_ptr, p->ec_alleles, E, p->n_alleles, p->allele_major, p->allele_gene, p->n_major,
+              p->n_gene, p->filter_frac, hX.data());
+      CK(cudaMemcpyAsync(dX0.p, hX.data(), (size_t)E * 8, cudaMemcpyHostToDevice, st));
+    }
+  }
+  CK(cudaMemcpyAsync(r->x, dX0.p, (size_t)E * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(r->ec_read_count, dRc.p, (size_t)E * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(ev1, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&r->ms_kernel, ev0, ev1));
+  r->n_launches = launches;
+  r->iterations = ret;
+  return T1K_OK;
+}
+
+// Genotyper.cpp:450-646 for one sample.
+int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t stride, uint32_t n_frag,
+                 const T1KGenotypeParams *prm, T1KGenotypeResult *res) {
+  if (!ref || !reads1 || !prm || !res || stride == 0 || !prm->effective_len) return fail(T1K_ERR_ARG, "t1k_genotype: bad argument");
+  CK(cudaSetDevice(ref->device));
+  const int32_t nA = ref->nAlleles;
+  double t0 = now_ms();
+  // ---- unique read-ends (Genotyper.cpp:450-454: the reference sorts; only the grouping matters)
+  const size_t nEnds = (size_t)n_frag * (reads2 ? 2 : 1);
+  auto end_ptr = [&](size_t i) { return i < n_frag ? reads1 + i * stride : reads2 + (i - n_frag) * stride; };
+  std::vector<u32> endLen(nEnds), uniqOf(nEnds);
+  std::vector<u8> fragHasN(n_frag, 0);
+  std::vector<size_t> uniqRep;   // representative end of each unique sequence
+  {
+    size_t tabSize = 16; while (tabSize < nEnds * 2) tabSize <<= 1;
+    std::vector<u32> table(tabSize, 0xffffffffu);
+    for (size_t i = 0; i < nEnds; ++i) {
+      const char *s = end_ptr(i);
+      u32 L = 0; u64 h = 1469598103934665603ull; bool hasN = false;
+      while (L < stride && s[L]) { h = (h ^ (u8)s[L]) * 1099511628211ull; hasN |= s[L] == 'N'; ++L; }
+      if (L > T1K_MAX_READ_LEN) return fail(T1K_ERR_ARG, "read longer than T1K_MAX_READ_LEN");
+      endLen[i] = L;
+      if (hasN) fragHasN[i < n_frag ? i : i - n_frag] = 1;
+      size_t slot = (size_t)(h ^ (h >> 29)) & (tabSize - 1);
+      for (;;) {
+        const u32 u = table[slot];
+        if (u == 0xffffffffu) { table[slot] = (u32)uniqRep.size(); uniqOf[i] = (u32)uniqRep.size(); uniqRep.push_back(i); break; }
+        const size_t rep = uniqRep[u];
+        if (endLen[rep] == L && memcmp(end_ptr(rep), s, L) == 0) { uniqOf[i] = u; break; }
+        slot = (slot + 1) & (tabSize - 1);
+      }
+    }
+  }
+  const size_t nUniq = uniqRep.size();
+  res->n_unique_ends = nUniq;
+  res->ms_dedup = (float)(now_ms() - t0);
+  CK(cudaMemsetAsync(ref->covDiff.p, 0, ref->paddedBases * 4, ref->stream));
+  CK(cudaMemsetAsync(ref->covPoint.p, 0, ref->paddedBases * 4, ref->stream));
+  ref->covDirty = true;
+  // ---- fragments in chunks: align the chunk's unique read-ends, pair on the device, coalesce on the host
+  u32 chunk = 1u << 18;
+  if (const char *env = getenv("T1K_CHUNK_FRAGMENTS")) chunk = (u32)std::max(1l, atol(env));
+  ReadGroups groups;
+  std::vector<u32> localId(nUniq, 0xffffffffu), chunkUniq, e1, e2;
+  std::vector<int32_t> w;
+  std::vector<uint64_t> off; std::vector<uint32_t> len; std::vector<char> bases;
+  res->n_overlaps = 0; res->n_assignments = 0;
+  res->ms_align = res->ms_pair = res->ms_coalesce = res->ms_em = 0;
+  res->ms_align_kernel = res->ms_pair_kernel = res->ms_em_kernel = 0;
+  res->n_postings = res->n_candidates = 0; res->n_launches = 0;
+  if (res->fragment_assigned) memset(res->fragment_assigned, 0, n_frag);
+  for (u32 f0 = 0; f0 < n_frag; f0 += chunk) {
+    const u32 m = std::min(chunk, n_frag - f0);
+    chunkUniq.clear(); w.clear(); e1.resize(m); if (reads2) e2.resize(m);
+    for (u32 i = 0; i < m; ++i) {
+      for (int mate = 0; mate < (reads2 ? 2 : 1); ++mate) {
+        const u32 u = uniqOf[(size_t)f0 + i + (mate ? n_frag : 0)];
+        if (localId[u] == 0xffffffffu) { localId[u] = (u32)chunkUniq.size(); chunkUniq.push_back(u); w.push_back(0); }
+        ++w[localId[u]];
+        (mate ? e2 : e1)[i] = localId[u];
+      }
+    }
+    off.resize(chunkUniq.size()); len.resize(chunkUniq.size());
+    size_t tot = 0;
+    for (size_t k = 0; k < chunkUniq.size(); ++k) { off[k] = tot; len[k] = endLen[uniqRep[chunkUniq[k]]]; tot += len[k]; }
+    bases.resize(tot + 1);
+    for (size_t k = 0; k < chunkUniq.size(); ++k) memcpy(bases.data() + off[k], end_ptr(uniqRep[chunkUniq[k]]), len[k]);
+    for (size_t k = 0; k < chunkUniq.size(); ++k) localId[chunkUniq[k]] = 0xffffffffu;
+    double ta = now_ms();
+    T1KAssignment *a = nullptr;
+    if (int rc = t1k_assign_batch(ref, bases.data(), off.data(), len.data(), w.data(), (uint32_t)chunkUniq.size(), &a)) return rc;
+    struct AG { T1KAssignment *a; ~AG() { t1k_assignment_destroy(a); } } ag{a};
+    res->ms_align += (float)(now_ms() - ta);
+    res->n_overlaps += a->storeUsed;
+    res->ms_align_kernel += a->msKernel; res->n_postings += a->stats[0]; res->n_candidates += a->stats[1];
+    res->n_launches += 2 + a->launches;
+    double tp = now_ms();
+    PairHost H;
+    if (int rc = pair_fragments(ref, a, e1.data(), reads2 ? e2.data() : nullptr, fragHasN.data() + f0, m, prm->max_assign, false, H)) return rc;
+    res->ms_pair += (float)(now_ms() - tp);
+    res->ms_pair_kernel += H.msKernel; res->n_launches += H.launches;
+    double tc = now_ms();
+    for (u32 i = 0; i < m; ++i) {
+      const u64 b = H.rowPtr[i], e = H.rowPtr[i + 1];
+      if (e > b) {
+        groups.add(H.entries.data() + b, (uint32_t)(e - b));
+        if (res->fragment_assigned) res->fragment_assigned[f0 + i] = 1;
+      }
+    }
+    res->n_assignments += H.entries.size();
+    res->ms_coalesce += (float)(now_ms() - tc);
+  }
+  res->assigned_fragments = (int32_t)groups.assignedFragments;
+  res->avg_alleles_per_read = groups.assignedFragments ? (double)res->n_assignments / (double)groups.assignedFragments : 0.0;
+  // ---- FinalizeReadAssignments: equivalence classes + missing coverage
+  double tc = now_ms();
+  EquivalenceClasses EC;
+  EC.build(groups, nA);
+  res->n_groups = groups.size(); res->n_ec = EC.size(); res->n_alleles = nA;
+  if (res->missing_coverage) { if (int rc = t1k_missing_coverage(ref, res->missing_coverage)) return rc; }
+  if (res->equivalent_class) memcpy(res->equivalent_class, EC.alleleEc.data(), (size_t)nA * 4);
+  res->ms_coalesce += (float)(now_ms() - tc);
+  // ---- EM
+  double te = now_ms();
+  res->em_iterations = 0;
+  if (res->abundance) memset(res->abundance, 0, (size_t)nA * 8);
+  if (res->ec_abundance) memset(res->ec_abundance, 0, (size_t)nA * 8);
+  if (EC.size() > 0) {
+    EmInputs in;
+    in.build(groups, EC, prm->effective_len, prm->seq_weight);
+    T1KEmProblem ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.n_groups = groups.size(); ep.n_ec = EC.size();
+    ep.row_ptr = in.rowPtr.data(); ep.col = in.col.data(); ep.count = in.count.data(); ep.ec_len = in.ecLen.data(); ep.x0 = in.x0.data();
+    ep.min_squarem_alpha = prm->min_squarem_alpha; ep.filter_frac = prm->filter_frac;
+    if (prm->allele_major && prm->allele_gene) {
+      ep.n_alleles = nA; ep.n_major = prm->n_major; ep.n_gene = prm->n_gene;
+      ep.ec_allele_ptr = EC.ecPtr.data(); ep.ec_alleles = EC.ecAlleles.data();
+      ep.allele_major = prm->allele_major; ep.allele_gene = prm->allele_gene;
+    }
+    std::vector<double> x(EC.size()), rc(EC.size());
+    T1KEmResult er; er.x = x.data(); er.ec_read_count = rc.data(); er.iterations = 0;
+    if (int rcode = t1k_em_run(&ep, &er, ref->device)) return rcode;
+    res->em_iterations = er.iterations;
+    res->ms_em_kernel = er.ms_kernel; res->n_launches += er.n_launches;
+    if (res->abundance && res->ec_abundance)
+      set_allele_abundance(rc.data(), in.ecLen.data(), EC.ecPtr.data(), EC.ecAlleles.data(), EC.size(), nA, res->abundance, res->ec_abundance);
+  }
+  res->ms_em = (float)(now_ms() - te);
+  return T1K_OK;
+}
+
+}  // extern "C"

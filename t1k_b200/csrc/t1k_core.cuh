@@ -96,7 +96,7 @@ struct LaneScratch {
   T1K_HD u32 *chain() const { return (u32 *)(base + SCR_OPS + SCR_ROWS + SCR_DIR + SCR_EMIT); }
 };
 
-enum { ERR_BAND = 1, ERR_SCRATCH = 2, ERR_EMIT = 4, ERR_CAND = 8, ERR_STORE = 16, ERR_HITS = 32 };
+enum { ERR_BAND = 1, ERR_SCRATCH = 2, ERR_EMIT = 4, ERR_CAND = 8, ERR_STORE = 16, ERR_HITS = 32, ERR_READ_LEN = 64, ERR_READ_CHAR = 128 };
 
 T1K_HD int popc64(u64 x) {
 #ifdef __CUDA_ARCH__

@@ -84,14 +84,14 @@ __global__ void k_pack_reads(const char *bases, const u64 *off, const u32 *len, 
   const char *s = bases + off[r];
   int L = (int)len[r];
   u64 *out = planes + (size_t)r * 4 * RWORDS;
-  if (L > 255) { atomicOr(err, 1); L = 0; }
+  if (L > 255) { atomicOr(err, ERR_READ_LEN); L = 0; }
   lenOut[r] = (u16)L;
   u64 fs = 0, fn = 0;
   for (int w = 0; w < RWORDS; ++w) { out[w] = 0; out[RWORDS + w] = 0; out[2 * RWORDS + w] = 0; out[3 * RWORDS + w] = 0; }
   for (int j = 0; j < L; ++j) {
     char c = s[j];
     int v = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : c == 'N' ? 4 : 5;
-    if (v == 5) { atomicOr(err, 2); v = 4; }
+    if (v == 5) { atomicOr(err, ERR_READ_CHAR); v = 4; }
     int sh = (j & 31) * 2;
     fs |= (u64)(v == 4 ? 3 : v) << sh;
     fn |= (u64)(v == 4) << sh;
@@ -394,16 +394,6 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_assign(AssignParams P)
     assign_one_read(P, r, W, cands, S, lane);
     __syncwarp();
   }
-}
-
-// coverage = prefix(covDiff) + covPoint, written in the caller's concatenated allele layout
-__global__ void k_cov_finalize(RefView R, const int64_t *offset, int32_t *out) {
-  int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= R.nAlleles) return;
-  size_t cb = (size_t)R.wordOff[a] * 32;
-  int32_t *o = out + offset[a];
-  int run = 0;
-  for (int j = 0; j < R.len[a]; ++j) { run += R.covDiff[cb + j]; o[j] = run + R.covPoint[cb + j]; }
 }
 
 }  // namespace t1k

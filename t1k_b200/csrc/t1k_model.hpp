@@ -1,0 +1,181 @@
+// Host side of the genotyping model between the alignment kernels and the EM kernels: the order-sensitive,
+// serial bookkeeping of Genotyper.hpp that SURVEY.md §8b keeps on the host (read-group coalescing, allele
+// equivalence classes, EM problem assembly, allele abundances).  Plain C++, no CUDA.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <unordered_map>
+#include <vector>
+
+namespace t1k {
+
+struct HostEntry {   // == PairEntry / T1KReadAssignment
+  int32_t alleleIdx, start, end;
+  float weight, qual, adjustWeight;
+};
+
+// Genotyper::CoalesceReadAssignments (Genotyper.hpp:841-908): fragments with the same allele set (and qual, which
+// is always 1 on this path, SeqSet.hpp:2507,2514) merge into one read group; float32 weights accumulate in
+// fragment order; start/end follow the reference's update rule verbatim (including end <- start, :893-894).
+struct ReadGroups {
+  std::vector<int64_t> ptr{0};
+  std::vector<HostEntry> ent;
+  std::unordered_map<uint64_t, std::vector<int32_t> > byHash;
+  int64_t assignedFragments = 0;
+
+  int32_t size() const { return (int32_t)ptr.size() - 1; }
+
+  static uint64_t hash_row(const HostEntry *row, uint32_t n) {
+    uint64_t h = 0x9e3779b97f4a7c15ull ^ n;
+    for (uint32_t i = 0; i < n; ++i) {
+      h ^= (uint64_t)(uint32_t)row[i].alleleIdx + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+      h *= 0xff51afd7ed558ccdull;
+    }
+    return h;
+  }
+
+  // row must be sorted by alleleIdx (the pairing kernel emits it that way)
+  void add(const HostEntry *row, uint32_t n) {
+    if (n == 0) return;
+    ++assignedFragments;
+    const uint64_t h = hash_row(row, n);
+    std::vector<int32_t> &cand = byHash[h];
+    for (size_t c = 0; c < cand.size(); ++c) {
+      const int32_t g = cand[c];
+      if (ptr[g + 1] - ptr[g] != (int64_t)n) continue;
+      HostEntry *t = &ent[ptr[g]];
+      bool same = true;
+      for (uint32_t j = 0; j < n && same; ++j) same = t[j].alleleIdx == row[j].alleleIdx && t[j].qual == row[j].qual;
+      if (!same) continue;
+      for (uint32_t j = 0; j < n; ++j) {
+        if (row[j].qual == 1) {
+          if (row[j].start < t[j].start) t[j].start = row[j].start;
+          if (row[j].end < t[j].end) t[j].end = row[j].start;
+        }
+        t[j].weight += row[j].weight;
+        t[j].adjustWeight += row[j].adjustWeight;
+      }
+      return;
+    }
+    cand.push_back(size());
+    ent.insert(ent.end(), row, row + n);
+    ptr.push_back((int64_t)ent.size());
+  }
+};
+
+// Genotyper::FinalizeReadAssignments + BuildAlleleEquivalentClass (Genotyper.hpp:912-939, 1072-1139).
+// RemoveLowMAPQAlleleInEquivalentClass (:1330-1368) keeps the members whose summed qual is maximal; every
+// assignment has qual 1 and EC members share their read groups, so it keeps all of them.
+struct EquivalenceClasses {
+  std::vector<int32_t> ecPtr{0}, ecAlleles, alleleEc;
+
+  void build(const ReadGroups &G, int32_t nAlleles) {
+    const int32_t readCnt = G.size();
+    std::vector<int64_t> inPtr(nAlleles + 1, 0);
+    for (size_t k = 0; k < G.ent.size(); ++k) ++inPtr[G.ent[k].alleleIdx + 1];
+    for (int32_t a = 0; a < nAlleles; ++a) inPtr[a + 1] += inPtr[a];
+    std::vector<int32_t> in(G.ent.size());
+    {
+      std::vector<int64_t> cur(inPtr.begin(), inPtr.end() - 1);
+      for (int32_t g = 0; g < readCnt; ++g)
+        for (int64_t k = G.ptr[g]; k < G.ptr[g + 1]; ++k) in[cur[G.ent[k].alleleIdx]++] = g;
+    }
+    struct FP { int32_t a, b; };
+    std::vector<FP> fp(nAlleles);
+    for (int32_t a = 0; a < nAlleles; ++a) {
+      int32_t b = -1;
+      if (inPtr[a + 1] > inPtr[a]) {
+        b = 0;
+        for (int64_t k = inPtr[a]; k < inPtr[a + 1]; ++k)
+          b = (int32_t)(((uint32_t)b * (uint32_t)readCnt + (uint32_t)in[k]) % 1000003u);   // Genotyper.hpp:1089
+      }
+      fp[a].a = a; fp[a].b = b;
+    }
+    std::sort(fp.begin(), fp.end(), [](const FP &x, const FP &y) { return x.b != y.b ? y.b < x.b : x.a < y.a; });
+    alleleEc.assign(nAlleles, -1);
+    std::vector<std::vector<int32_t> > ecs;
+    for (int32_t i = 0; i < nAlleles; ++i) {
+      if (fp[i].b == -1) break;
+      const int32_t a = fp[i].a;
+      int32_t found = -1;
+      for (int32_t j = i - 1; j >= 0 && fp[j].b == fp[i].b; --j) {
+        const int32_t o = fp[j].a;
+        const int64_t n = inPtr[a + 1] - inPtr[a];
+        if (inPtr[o + 1] - inPtr[o] == n && std::equal(in.begin() + inPtr[a], in.begin() + inPtr[a + 1], in.begin() + inPtr[o])) {
+          found = o;
+          break;
+        }
+      }
+      if (found < 0) { alleleEc[a] = (int32_t)ecs.size(); ecs.push_back(std::vector<int32_t>(1, a)); }
+      else { alleleEc[a] = alleleEc[found]; ecs[alleleEc[found]].push_back(a); }
+    }
+    ecPtr.assign(1, 0); ecAlleles.clear();
+    for (size_t e = 0; e < ecs.size(); ++e) {
+      ecAlleles.insert(ecAlleles.end(), ecs[e].begin(), ecs[e].end());
+      ecPtr.push_back((int32_t)ecAlleles.size());
+    }
+  }
+  int32_t size() const { return (int32_t)ecPtr.size() - 1; }
+};
+
+// EM inputs as QuantifyAlleleEquivalentClass assembles them (Genotyper.hpp:1155-1232)
+struct EmInputs {
+  std::vector<int64_t> rowPtr;
+  std::vector<int32_t> col, ecLen;
+  std::vector<double> count, x0;
+
+  void build(const ReadGroups &G, const EquivalenceClasses &EC, const int32_t *effectiveLen, const int32_t *seqWeight) {
+    const int32_t n = G.size(), E = EC.size();
+    rowPtr.assign(1, 0); col.clear(); count.resize(n);
+    std::vector<int32_t> stamp(E, -1);
+    for (int32_t g = 0; g < n; ++g) {
+      float c = G.ent[G.ptr[g]].weight;
+      for (int64_t k = G.ptr[g] + 1; k < G.ptr[g + 1]; ++k) if (G.ent[k].weight > c) c = G.ent[k].weight;
+      count[g] = c;
+      for (int64_t k = G.ptr[g]; k < G.ptr[g + 1]; ++k) {
+        const int32_t e = EC.alleleEc[G.ent[k].alleleIdx];
+        if (stamp[e] != g) { stamp[e] = g; col.push_back(e); }
+      }
+      rowPtr.push_back((int64_t)col.size());
+    }
+    ecLen.resize(E); x0.resize(E);
+    for (int32_t e = 0; e < E; ++e) {
+      int32_t len = effectiveLen[EC.ecAlleles[EC.ecPtr[e]]];
+      double w = 0;
+      for (int32_t k = EC.ecPtr[e]; k < EC.ecPtr[e + 1]; ++k) {
+        len = std::min(len, effectiveLen[EC.ecAlleles[k]]);
+        w += seqWeight ? seqWeight[EC.ecAlleles[k]] : 1;
+      }
+      ecLen[e] = len; x0[e] = w;
+    }
+  }
+};
+
+// Genotyper::SetAlleleAbundance, per-allele part (Genotyper.hpp:957-987)
+inline void set_allele_abundance(const double *rc, const int32_t *ecLen, const int32_t *ecPtr, const int32_t *ecAlleles, int32_t nEc,
+                                 int32_t nAlleles, double *abundance, double *ecAbundance) {
+  for (int32_t i = 0; i < nAlleles; ++i) abundance[i] = ecAbundance[i] = 0;
+  for (int32_t e = 0; e < nEc; ++e) {
+    const int32_t size = ecPtr[e + 1] - ecPtr[e];
+    const double abund = rc[e] / ecLen[e] * 1000.0;
+    for (int32_t k = ecPtr[e]; k < ecPtr[e + 1]; ++k) { abundance[ecAlleles[k]] = abund / size; ecAbundance[ecAlleles[k]] = abund; }
+  }
+}
+
+// The every-10-iterations low-abundance mask (Genotyper.hpp:1292-1313 with SetAlleleAbundance :989-1013):
+// returns the new ecAbundance0 in x0.
+inline void em_mask(const double *rc, const int32_t *ecLen, const int32_t *ecPtr, const int32_t *ecAlleles, int32_t nEc,
+                    int32_t nAlleles, const int32_t *alleleMajor, const int32_t *alleleGene, int32_t nMajor, int32_t nGene,
+                    double filterFrac, double *x0) {
+  std::vector<double> ab(nAlleles), ecAb(nAlleles), major(nMajor, 0.0), gmax(nGene, 0.0);
+  set_allele_abundance(rc, ecLen, ecPtr, ecAlleles, nEc, nAlleles, ab.data(), ecAb.data());
+  for (int32_t i = 0; i < nAlleles; ++i) major[alleleMajor[i]] += ab[i];
+  for (int32_t i = 0; i < nAlleles; ++i) gmax[alleleGene[i]] = std::max(gmax[alleleGene[i]], major[alleleMajor[i]]);
+  for (int32_t i = 0; i < nAlleles; ++i)
+    if (major[alleleMajor[i]] < filterFrac * 0.5 * gmax[alleleGene[i]]) ecAb[i] = 0;
+  for (int32_t e = 0; e < nEc; ++e) x0[e] = ecAb[ecAlleles[ecPtr[e]]];
+}
+
+}  // namespace t1k

@@ -1,0 +1,156 @@
+"""CPU-only checks of the product's host logic and of the lane-level device code compiled for the host
+(tests/host_emu.cpp runs t1k_core.cuh sequentially — test harness only) against the oracle."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_io as G
+import oracle_py as O
+import workloads as W
+from t1k_b200 import _lib as L
+from t1k_b200.refset import RefSet, parse_allele_name, parse_exons
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = os.path.join(ROOT, "tests", "host_emu.cpp")
+    so = os.path.join(ROOT, "tests", "_build", "libhostemu.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    deps = [src] + [os.path.join(ROOT, "t1k_b200", "csrc", f) for f in ("t1k_core.cuh", "t1k_host.hpp")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-w", "-std=c++14", "-shared", "-fPIC", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.emu_create.restype = C.c_void_p
+    lib.emu_create.argtypes = [C.c_int32, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32]
+    lib.emu_destroy.argtypes = [C.c_void_p]
+    lib.emu_assign.restype = C.c_int32
+    lib.emu_assign.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.emu_coverage.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.emu_align.restype = C.c_int32
+    lib.emu_align.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    return lib
+
+
+@pytest.mark.parametrize("name", G.names())
+def test_lane_code_matches_reference_golden(emu, name):
+    """chaining, diagonal certificate, banded DP, extension and full-read alignment of t1k_core.cuh reproduce the
+    reference's AssignRead records and base coverage"""
+    g = G.load(name)
+    ref = RefSet(g["records"])
+    bases, off, ptr, se = ref.packed()
+    E = emu.emu_create(ref.n, bases, O._p(off), O._p(ptr), O._p(se), g["similarity"], int(g["relax"]))
+    assert E
+    buf = np.zeros(1 << 14, dtype=O.OVERLAP_DT)
+    for i, s in enumerate(g["uniq_seq"]):
+        err = C.c_int32(0)
+        n = emu.emu_assign(E, s, int(g["uniq_weight"][i]), O._p(buf), len(buf), C.byref(err))
+        assert err.value == 0
+        want = G.uniq_overlaps(g, i)
+        got = np.stack([buf[k][:max(n, 0)] for k in O.OVERLAP_DT.names], axis=1) if n > 0 else np.zeros((0, 10), np.int32)
+        assert np.array_equal(got, want), i
+    cov = []
+    for a in range(ref.n):
+        out = np.zeros(len(ref.seqs[a]), dtype=np.int32)
+        emu.emu_coverage(E, a, O._p(out))
+        cov.append(out)
+    assert np.array_equal(np.concatenate(cov), g["cov"])
+    emu.emu_destroy(E)
+
+
+def test_banded_dp_and_diagonal_certificate(emu):
+    """dp_align == AlignAlgo::GlobalAlignment op for op (oracle) on random pairs incl. N, indels and band edges;
+    whenever the diagonal certificate fires, the reference alignment is the pure diagonal."""
+    rng = np.random.default_rng(12)
+    alpha = np.frombuffer(b"ACGT", dtype=np.uint8)
+    certified = 0
+    for it in range(1500):
+        n = int(rng.integers(1, 150))
+        t = alpha[rng.integers(0, 4, size=n)].copy()
+        if it % 3 == 0:                       # repetitive sequence stresses tie-breaking
+            unit = alpha[rng.integers(0, 4, size=int(rng.integers(1, 5)))]
+            t = np.resize(unit, n).copy()
+        p = t.copy()
+        for _ in range(int(rng.integers(0, 7))):
+            p[rng.integers(0, len(p))] = alpha[rng.integers(0, 4)]
+        if it % 4 == 1 and len(p) > 12:
+            k = int(rng.integers(1, len(p) - 1))
+            d = int(rng.integers(1, 5))
+            p = np.delete(p, slice(k, k + d)) if rng.integers(0, 2) else np.insert(p, k, alpha[rng.integers(0, 4, size=d)])
+        if it % 5 == 2:
+            p[rng.integers(0, len(p))] = ord("N")
+            t[rng.integers(0, len(t))] = ord("N")
+        if len(p) == 0 or len(p) > 250:
+            continue
+        tb, pb = t.tobytes(), p.tobytes()
+        score, ops = O.global_alignment(tb, pb)
+        out = np.zeros(len(tb) + len(pb) + 16, dtype=np.int8)
+        cert, matches = C.c_int32(0), C.c_int32(0)
+        k = emu.emu_align(tb, len(tb), pb, len(pb), O._p(out), C.byref(cert), C.byref(matches))
+        assert k == len(ops) and np.array_equal(out[:k], ops), (tb, pb)
+        assert matches.value == int((ops == 0).sum())
+        if cert.value:
+            certified += 1
+            assert len(tb) == len(pb) and set(ops.tolist()) <= {0, 1}
+    assert certified > 300
+
+
+def test_parse_helpers():
+    assert parse_exons("7 50 221 623 783", 3000) == [(50, 221), (623, 783)]
+    assert parse_exons("", 100) == [(0, 99)]
+    assert parse_exons("1 0 1099", 1100) == [(0, 1099)]
+    assert parse_allele_name("HLA-A*01:02:03:04") == ("HLA-A", "HLA-A*01:02:03")
+    assert parse_allele_name("HLA-A*01:02") == ("HLA-A", "HLA-A*01:02")
+    assert parse_allele_name("KIR2DL1*0010101") == ("KIR2DL1", "KIR2DL1*001")
+    assert parse_allele_name("CYP2D6*4.001", 1, ".") == ("CYP2D6", "CYP2D6*4")
+    for name in ("HLA-B*07:02:01", "KIR3DL2*00701", "X", "CYP2D6*10.002"):
+        for du, dl in ((-1, ""), (1, "."), (2, ":")):
+            assert parse_allele_name(name, du, dl) == O.parse_allele_name(name, du, dl)
+
+
+@pytest.mark.parametrize("name", G.names())
+def test_refset_matches_reference_golden(name):
+    g = G.load(name)
+    ref = RefSet(g["records"])
+    q = g["q"]
+    assert ref.n == len(q)
+    assert np.array_equal(ref.effective_len, q[:, 3].astype(np.int32))
+    assert np.array_equal(ref.seq_weight, q[:, 4].astype(np.int32))
+
+
+def test_abi_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "t1k_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(t1k_[a-z_0-9]+)\s*\(", hdr)))
+    assert sorted(L.EXPORTS) == declared
+    lib = L.lib()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+
+
+def test_no_cpu_fallback_without_a_device():
+    """Without a CUDA device the compute entry points fail loudly (T1K_ERR_NO_DEVICE); nothing runs on the CPU."""
+    n = C.c_int(0)
+    L.lib().t1k_device_count(C.byref(n))
+    if n.value > 0:
+        pytest.skip("a CUDA device is present")
+    from t1k_b200.genotyper import QuantifyAlleleEquivalentClass, SeqSet
+    ref = RefSet(W.small_rna_ref())
+    with pytest.raises(L.T1KError) as e:
+        SeqSet(ref, 0.8, False)
+    assert e.value.code == L.T1K_ERR_NO_DEVICE
+    with pytest.raises(L.T1KError) as e:
+        QuantifyAlleleEquivalentClass([0, 1], [0], [1.0], [100], [1.0])
+    assert e.value.code == L.T1K_ERR_NO_DEVICE
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "t1k_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in txt.lower() or f == "_never_.py", os.path.join(dirpath, f)
