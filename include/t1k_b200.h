@@ -115,6 +115,10 @@ typedef struct {
   int32_t n_alleles, n_major, n_gene;
   const int32_t *ec_allele_ptr, *ec_alleles;   /* members per EC (first = representative) */
   const int32_t *allele_major, *allele_gene;   /* [n_alleles] */
+  /* 0: every sum in the reference's sequential order, separately rounded (abundances bit-identical to the
+   *    reference's x86 result; the dependent add chains are serial);
+   * 1: warp/block tree reductions (fixed order, run-to-run reproducible, ~1e-16 relative from the reference). */
+  int32_t fast_sums;
 } T1KEmProblem;
 
 typedef struct {
@@ -136,6 +140,7 @@ typedef struct {
   const int32_t *seq_weight;   /* [n_alleles] SeqSet::GetSeqWeight */
   const int32_t *effective_len;/* [n_alleles] SeqSet::GetSeqEffectiveLen (after InitAlleleInfo's adjustment) */
   const int32_t *allele_major, *allele_gene; int32_t n_major, n_gene;
+  int32_t em_fast_sums;        /* T1KEmProblem.fast_sums */
 } T1KGenotypeParams;
 
 typedef struct {

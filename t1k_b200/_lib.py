@@ -37,7 +37,7 @@ class EmProblem(C.Structure):
                 ("count", C.c_void_p), ("ec_len", C.c_void_p), ("x0", C.c_void_p), ("min_squarem_alpha", C.c_double),
                 ("filter_frac", C.c_double), ("n_alleles", C.c_int32), ("n_major", C.c_int32), ("n_gene", C.c_int32),
                 ("ec_allele_ptr", C.c_void_p), ("ec_alleles", C.c_void_p), ("allele_major", C.c_void_p),
-                ("allele_gene", C.c_void_p)]
+                ("allele_gene", C.c_void_p), ("fast_sums", C.c_int32)]
 
 
 class EmResult(C.Structure):
@@ -48,7 +48,7 @@ class EmResult(C.Structure):
 class GenotypeParams(C.Structure):
     _fields_ = [("max_assign", C.c_int32), ("min_squarem_alpha", C.c_double), ("filter_frac", C.c_double),
                 ("seq_weight", C.c_void_p), ("effective_len", C.c_void_p), ("allele_major", C.c_void_p),
-                ("allele_gene", C.c_void_p), ("n_major", C.c_int32), ("n_gene", C.c_int32)]
+                ("allele_gene", C.c_void_p), ("n_major", C.c_int32), ("n_gene", C.c_int32), ("em_fast_sums", C.c_int32)]
 
 
 class GenotypeResult(C.Structure):

@@ -634,7 +634,9 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   cudaStream_t st;
   CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   struct StGuard { cudaStream_t s; ~StGuard() { cudaStreamDestroy(s); } } sg{st};
-  DevMem dRowPtr, dCol, dColPtr, dRowIdx, dCount, dLen, dPsum, dRc, dX0, dX1, dX2, dX3, dDiff;
+  DevMem dRowPtr, dCol, dColPtr, dRowIdx, dCount, dLen, dPsum, dRc, dX0, dX1, dX2, dX3, dDiff, dTmpA, dTmpB;
+  const bool fast = p->fast_sums != 0;
+  CK(dTmpA.alloc((size_t)E * 8)); CK(dTmpB.alloc((size_t)E * 8));
   CK(dRowPtr.alloc(((size_t)G + 1) * 8)); CK(dCol.alloc((size_t)nnz * 4)); CK(dColPtr.alloc(((size_t)E + 1) * 8)); CK(dRowIdx.alloc((size_t)nnz * 4));
   CK(dCount.alloc((size_t)G * 8)); CK(dLen.alloc((size_t)E * 4)); CK(dPsum.alloc((size_t)G * 8)); CK(dRc.alloc((size_t)E * 8));
   CK(dX0.alloc((size_t)E * 8)); CK(dX1.alloc((size_t)E * 8)); CK(dX2.alloc((size_t)E * 8)); CK(dX3.alloc((size_t)E * 8)); CK(dDiff.alloc(8));
@@ -652,9 +654,15 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   CK(cudaEventRecord(ev0, st));
   uint64_t launches = 0;
   auto em_update = [&](const double *xin, double *xout) -> int {   // Genotyper::EMupdate
-    if (G) k_em_rowsum<<<gRow, 256, 0, st>>>(G, dRowPtr.as<int64_t>(), dCol.as<int32_t>(), xin, dPsum.as<double>());
-    k_em_colsum<<<gCol, 256, 0, st>>>(E, dColPtr.as<int64_t>(), dRowIdx.as<int32_t>(), dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
-    k_em_mstep<<<1, 1024, 0, st>>>(E, dRc.as<double>(), dLen.as<int32_t>(), xout);
+    if (fast) {
+      if (G) k_em_rowsum<<<gRow, 256, 0, st>>>(G, dRowPtr.as<int64_t>(), dCol.as<int32_t>(), xin, dPsum.as<double>());
+      k_em_colsum<<<gCol, 256, 0, st>>>(E, dColPtr.as<int64_t>(), dRowIdx.as<int32_t>(), dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
+      k_em_mstep<<<1, 1024, 0, st>>>(E, dRc.as<double>(), dLen.as<int32_t>(), xout);
+    } else {
+      if (G) k_em_rowsum_seq<<<(G + 127) / 128, 128, 0, st>>>(G, dRowPtr.as<int64_t>(), dCol.as<int32_t>(), xin, dPsum.as<double>());
+      k_em_colsum_seq<<<(E + 63) / 64, 64, 0, st>>>(E, dColPtr.as<int64_t>(), dRowIdx.as<int32_t>(), dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
+      k_em_mstep_seq<<<1, 1024, 0, st>>>(E, dRc.as<double>(), dLen.as<int32_t>(), dTmpA.as<double>(), xout);
+    }
     CK(cudaGetLastError());
     launches += G ? 3 : 2;
     return T1K_OK;
@@ -667,9 +675,11 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
     ++ret;
     if (int rc = em_update(dX0.as<double>(), dX1.as<double>())) return rc;
     if (int rc = em_update(dX1.as<double>(), dX2.as<double>())) return rc;
-    k_em_squarem<<<1, 1024, 0, st>>>(E, dX0.as<double>(), dX1.as<double>(), dX2.as<double>(), p->min_squarem_alpha, dX3.as<double>());
+    if (fast) k_em_squarem<<<1, 1024, 0, st>>>(E, dX0.as<double>(), dX1.as<double>(), dX2.as<double>(), p->min_squarem_alpha, dX3.as<double>());
+    else k_em_squarem_seq<<<1, 1024, 0, st>>>(E, dX0.as<double>(), dX1.as<double>(), dX2.as<double>(), p->min_squarem_alpha, dTmpA.as<double>(), dTmpB.as<double>(), dX3.as<double>());
     if (int rc = em_update(dX3.as<double>(), dX1.as<double>())) return rc;
-    k_em_advance<<<1, 1024, 0, st>>>(E, dX0.as<double>(), dX1.as<double>(), dDiff.as<double>());
+    if (fast) k_em_advance<<<1, 1024, 0, st>>>(E, dX0.as<double>(), dX1.as<double>(), dDiff.as<double>());
+    else k_em_advance_seq<<<1, 1024, 0, st>>>(E, dX0.as<double>(), dX1.as<double>(), dTmpA.as<double>(), dDiff.as<double>());
     CK(cudaGetLastError());
     launches += 2;
     double diff = 0;
@@ -808,7 +818,7 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     memset(&ep, 0, sizeof(ep));
     ep.n_groups = groups.size(); ep.n_ec = EC.size();
     ep.row_ptr = in.rowPtr.data(); ep.col = in.col.data(); ep.count = in.count.data(); ep.ec_len = in.ecLen.data(); ep.x0 = in.x0.data();
-    ep.min_squarem_alpha = prm->min_squarem_alpha; ep.filter_frac = prm->filter_frac;
+    ep.min_squarem_alpha = prm->min_squarem_alpha; ep.filter_frac = prm->filter_frac; ep.fast_sums = prm->em_fast_sums;
     if (prm->allele_major && prm->allele_gene) {
       ep.n_alleles = nA; ep.n_major = prm->n_major; ep.n_gene = prm->n_gene;
       ep.ec_allele_ptr = EC.ecPtr.data(); ep.ec_alleles = EC.ecAlleles.data();

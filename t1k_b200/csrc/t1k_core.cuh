@@ -22,6 +22,14 @@
 #define T1K_NOINLINE
 #endif
 
+// host-emulation-only call-site counters (tests/host_emu.cpp); compiled out of the device build
+#if !defined(__CUDACC__) && defined(T1K_EMU_COUNTERS)
+extern long long t1k_emu_counters[16];
+#define T1K_COUNT(i, v) (t1k_emu_counters[i] += (v))
+#else
+#define T1K_COUNT(i, v) ((void)0)
+#endif
+
 namespace t1k {
 
 typedef uint64_t u64;
@@ -141,17 +149,69 @@ T1K_HD u64 mm_chunk(const RefView &R, u64 w0, int tpos, const ReadView &Q, int p
   return d & lowmask2(nLeft);
 }
 
-// Equal-length global alignment without the DP.  For lent == lenp == n the diagonal is the alignment the
-// reference's traceback returns whenever no gapped path scores strictly higher at any prefix.  A gapped
-// excursion pays >= 4 per gap event plus the lost rows, and can only gain 4 per diagonal mismatch that a
-// shift d (|d| <= BAND) turns into a match; with F_d = number of diagonal mismatches fixed by shift d,
-// sum_d max(0, F_d - 1) <= 1 (always true for <= 3 mismatches) leaves every excursion <= 0
-// (DESIGN.md "Diagonal certificate").  Returns true and the mismatch count if certified.
+// mismatching columns among rows [lo, hi] of the window when row r of the read is paired with allele column r + d
+T1K_HDN inline int shifted_mm(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos, int n, int d, int lo, int hi) {
+  if (lo < 0) lo = 0;
+  if (lo < -d) lo = -d;
+  if (hi > n - 1) hi = n - 1;
+  if (hi > n - 1 - d) hi = n - 1 - d;
+  int c = 0;
+  for (int k = lo; k <= hi; k += 32) c += popc64(mm_chunk(R, w0, tpos + k + d, Q, ppos + k, hi - k + 1));
+  return c;
+}
+
+// Equal-length global alignment without the DP (DESIGN.md "Diagonal certificate").  For lent == lenp == n the
+// reference's traceback returns the pure diagonal iff no gapped path reaches a diagonal cell (b,b) with a strictly
+// higher score than the diagonal prefix (ties go to the diagonal, AlignAlgo.hpp:332-345).  An excursion that leaves
+// the diagonal at row A and returns after row B with m gap events of lengths L_g gains
+//     4*(mm0[A..B] - mmShifted) - 4*m - 2*sum(L_g)
+// over the diagonal (mm0 = diagonal mismatches in the segment, mmShifted = mismatches of its shifted pairs).
+//   * m = 2 (one shift d): gain = 4*delta - 8 - 4|d|, positive only if delta >= 3 + |d|;
+//   * m >= 3 needs sum(L_g) >= 4: gain <= 4*delta - 20, positive only if delta >= 6.
+// So <= 3 mismatches are always diagonal; with 4 or 5 only single-shift excursions with |d| <= mm - 3 can win, and
+// those are enumerated exactly: the best segment starts at a mismatch (or up to |d| rows before one when the leading
+// rows are the unpaired ones) and ends at a mismatch (or up to |d| rows after one).  More mismatches fall back to
+// a shift histogram bound, and failing that to the DP.
 T1K_HDN inline bool diag_certified(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos, int n, int &mmOut) {
   int mm = 0;
   for (int k = 0; k < n; k += 32) mm += popc64(mm_chunk(R, w0, tpos + k, Q, ppos + k, n - k));
   mmOut = mm;
   if (mm <= 3) return true;
+  if (mm <= 5) {
+    int pos[5];
+    {
+      int c = 0;
+      for (int k = 0; k < n; k += 32) {
+        u64 m = mm_chunk(R, w0, tpos + k, Q, ppos + k, n - k);
+        while (m) { pos[c < 5 ? c : 4] = k + (ctz64(m) >> 1); ++c; m &= m - 1; }
+      }
+    }
+    for (int d = 1; d <= mm - 3; ++d) {
+      for (int i = 0; i + 2 + d < mm; ++i)            // at least 3 + d diagonal mismatches inside the segment
+        for (int j = i + 2 + d; j < mm; ++j)
+          for (int t = 0; t <= d; ++t) {
+            // deletion first (allele ahead by d): rows [A, B - d] paired with columns r + d, last d rows unpaired
+            {
+              const int A = pos[i], B = pos[j] + t;
+              if (B <= n - 1 && B - d >= A - 1) {
+                int in = 0;
+                for (int q = 0; q < mm; ++q) in += pos[q] >= A && pos[q] <= B;
+                if (in - shifted_mm(R, w0, tpos, Q, ppos, n, d, A, B - d) > 2 + d) return false;
+              }
+            }
+            // insertion first (allele behind by d): first d rows unpaired, rows [A + d, B] paired with columns r - d
+            {
+              const int A = pos[i] - t, B = pos[j];
+              if (A >= 0 && B >= A + d - 1) {
+                int in = 0;
+                for (int q = 0; q < mm; ++q) in += pos[q] >= A && pos[q] <= B;
+                if (in - shifted_mm(R, w0, tpos, Q, ppos, n, -d, A + d, B) > 2 + d) return false;
+              }
+            }
+          }
+    }
+    return true;
+  }
   if (mm > 24) return false;
   int F[2 * BAND + 1];
 #pragma unroll
@@ -188,6 +248,7 @@ T1K_HDN T1K_NOINLINE inline int dp_align(const RefView &R, u64 w0, int tpos, int
   int lb = BAND, rb = BAND;
   if (lent > lenp) rb += lent - lenp; else if (lent < lenp) lb += lenp - lent;
   const int W = lb + rb + 3;          // columns i-lb-1 .. i+rb+1
+  T1K_COUNT(0, 1); T1K_COUNT(1, (long long)lenp * W); T1K_COUNT(lent == lenp ? 2 : 3, 1);
   if (W > MAX_BAND_W || lenp > 256 || lent + lenp + 8 > SCR_OPS) { err |= ERR_BAND; return -1; }
   const int negInf = (lent + 1) * (lenp + 1) * -4;
   const int stale = -4 + (lenp + 1) * -4;   // e[0][j], AlignAlgo.hpp:268 (Q5)
@@ -276,10 +337,12 @@ T1K_HDN T1K_NOINLINE inline int dp_align(const RefView &R, u64 w0, int tpos, int
 T1K_HDN inline int align_matches(const RefView &R, u64 w0, int tpos, int lent, const ReadView &Q, int ppos, int lenp,
                                  const LaneScratch &S, int &err) {
   if (lent == 0 || lenp == 0) return 0;
+  T1K_COUNT(4, 1);
   if (lent == lenp) {
     int mm;
     if (diag_certified(R, w0, tpos, Q, ppos, lent, mm)) return lent - mm;
   }
+  T1K_COUNT(5, 1);
   int n = dp_align(R, w0, tpos, lent, Q, ppos, lenp, S, err);
   int c = 0;
   const u8 *ops = S.ops();
@@ -549,6 +612,7 @@ T1K_HDN inline void full_align(const RefView &R, const ReadView &Q, Cand &c, int
   const int lent = c.eSeqEnd - c.eSeqStart + 1, lenp = c.eReadEnd - c.eReadStart + 1;
   const size_t cb = (size_t)w0 * 32;
   int mm;
+  T1K_COUNT(6, 1);
   if (lent == lenp && diag_certified(R, w0, tpos, Q, ppos, lent, mm)) {
     int exMm = 0;
     if (weight > 0) { cov_add(R.covDiff + cb + tpos, weight); cov_add(R.covDiff + cb + tpos + lent, -weight); }
@@ -567,6 +631,7 @@ T1K_HDN inline void full_align(const RefView &R, const ReadView &Q, Cand &c, int
     c.relaxed = R.relax ? 2 * (lent - exMm) : c.eMatchCnt;
     return;
   }
+  T1K_COUNT(7, 1); T1K_COUNT(8 + (mm > 8 ? 8 : mm) - 1 < 16 ? (mm >= 4 && mm <= 10 ? 8 + mm - 4 : 15) : 15, 1);
   int n = dp_align(R, w0, tpos, lent, Q, ppos, lenp, S, err);
   if (n < 0) { c.relaxed = c.eMatchCnt; return; }
   const u8 *ops = S.ops();

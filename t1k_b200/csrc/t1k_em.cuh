@@ -95,4 +95,93 @@ __global__ void __launch_bounds__(1024) k_em_advance(int nEc, double *__restrict
   if (threadIdx.x == 0) *diffOut = d;
 }
 
+// ---- reference-order variants: every sum runs in the reference's own (sequential) order with separately rounded
+// multiplies and adds (no FMA contraction), so the abundances equal the reference's x86 results bit for bit and the
+// convergence test `diffSum < 1e-5` (Genotyper.hpp:1289) sees the very same number.  Elementwise work stays parallel;
+// only the dependent add chains are serial (one thread per row / per column / per vector sum).
+__global__ void k_em_rowsum_seq(int nGroups, const int64_t *__restrict__ rowPtr, const int32_t *__restrict__ col,
+                                const double *__restrict__ x, double *__restrict__ psum) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nGroups) return;
+  double s = 0;
+  for (int64_t k = rowPtr[g]; k < rowPtr[g + 1]; ++k) s = __dadd_rn(s, x[col[k]]);
+  psum[g] = s == 0 ? 1.0 : s;
+}
+
+__global__ void k_em_colsum_seq(int nEc, const int64_t *__restrict__ colPtr, const int32_t *__restrict__ rowIdx,
+                                const double *__restrict__ count, const double *__restrict__ psum,
+                                const double *__restrict__ x, double *__restrict__ rc) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nEc) return;
+  const double xe = x[e];
+  double s = 0;
+#pragma unroll 4
+  for (int64_t k = colPtr[e]; k < colPtr[e + 1]; ++k) {
+    const int g = rowIdx[k];
+    s = __dadd_rn(s, __dmul_rn(count[g], __ddiv_rn(xe, psum[g])));
+  }
+  rc[e] = s;
+}
+
+// tmp[e] = f(e) elementwise, then one thread adds tmp[0..n) in index order
+__device__ __forceinline__ double seq_sum(const double *tmp, int n) {
+  double s = 0;
+#pragma unroll 8
+  for (int e = 0; e < n; ++e) s = __dadd_rn(s, tmp[e]);
+  return s;
+}
+
+__global__ void __launch_bounds__(1024) k_em_mstep_seq(int nEc, const double *__restrict__ rc, const int32_t *__restrict__ len,
+                                                        double *__restrict__ tmp, double *__restrict__ xNext) {
+  __shared__ double norm;
+  for (int e = threadIdx.x; e < nEc; e += blockDim.x) tmp[e] = __ddiv_rn(rc[e], (double)len[e]);
+  __syncthreads();
+  if (threadIdx.x == 0) norm = seq_sum(tmp, nEc);
+  __syncthreads();
+  const double nrm = norm;
+  for (int e = threadIdx.x; e < nEc; e += blockDim.x) xNext[e] = __ddiv_rn(tmp[e], nrm);
+}
+
+__global__ void __launch_bounds__(1024) k_em_squarem_seq(int nEc, const double *__restrict__ x0, const double *__restrict__ x1,
+                                                          const double *__restrict__ x2, double minAlpha, double *__restrict__ tmpR,
+                                                          double *__restrict__ tmpV, double *__restrict__ x3) {
+  __shared__ double sAlpha;
+  for (int e = threadIdx.x; e < nEc; e += blockDim.x) {
+    const double r = __dsub_rn(x1[e], x0[e]);
+    const double v = __dadd_rn(__dsub_rn(x2[e], __dmul_rn(2.0, x1[e])), x0[e]);
+    tmpR[e] = __dmul_rn(r, r); tmpV[e] = __dmul_rn(v, v);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double sr = seq_sum(tmpR, nEc);
+    sAlpha = sr;
+  }
+  if (threadIdx.x == 32) {
+    const double sv = seq_sum(tmpV, nEc);
+    tmpV[0] = sv;              // tmpV is dead after this sum
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double sr = sAlpha, sv = tmpV[0];
+    double alpha = sv == 0 ? -1.0 : __ddiv_rn(-sqrt(sr), sqrt(sv));
+    if (minAlpha < 0 && alpha < minAlpha) alpha = minAlpha;
+    sAlpha = alpha;
+  }
+  __syncthreads();
+  const double alpha = sAlpha;
+  const double a2 = __dmul_rn(2.0, alpha), aa = __dmul_rn(alpha, alpha);
+  for (int e = threadIdx.x; e < nEc; e += blockDim.x) {
+    const double r = __dsub_rn(x1[e], x0[e]);
+    const double v = __dadd_rn(__dsub_rn(x2[e], __dmul_rn(2.0, x1[e])), x0[e]);
+    x3[e] = __dadd_rn(__dsub_rn(x0[e], __dmul_rn(a2, r)), __dmul_rn(aa, v));
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_em_advance_seq(int nEc, double *__restrict__ x0, const double *__restrict__ x1,
+                                                          double *__restrict__ tmp, double *__restrict__ diffOut) {
+  for (int e = threadIdx.x; e < nEc; e += blockDim.x) { tmp[e] = fabs(__dsub_rn(x1[e], x0[e])); x0[e] = x1[e]; }
+  __syncthreads();
+  if (threadIdx.x == 0) *diffOut = seq_sum(tmp, nEc);
+}
+
 }  // namespace t1k

@@ -136,7 +136,8 @@ class SeqSet:
 
 
 def QuantifyAlleleEquivalentClass(row_ptr, col, count, ec_len, x0, min_squarem_alpha=0.0, filter_frac=0.15,
-                                  ec_allele_ptr=None, ec_alleles=None, allele_major=None, allele_gene=None, device=-1):
+                                  ec_allele_ptr=None, ec_alleles=None, allele_major=None, allele_gene=None, device=-1,
+                                  fast_sums=False):
     """The EM loop of Genotyper::QuantifyAlleleEquivalentClass on the device -> (iterations, x, ecReadCount)."""
     row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
     col = np.ascontiguousarray(col, dtype=np.int32)
@@ -147,6 +148,7 @@ def QuantifyAlleleEquivalentClass(row_ptr, col, count, ec_len, x0, min_squarem_a
     p.n_groups, p.n_ec = len(row_ptr) - 1, len(ec_len)
     p.row_ptr, p.col, p.count, p.ec_len, p.x0 = L.ptr(row_ptr), L.ptr(col), L.ptr(count), L.ptr(ec_len), L.ptr(x0)
     p.min_squarem_alpha, p.filter_frac = float(min_squarem_alpha), float(filter_frac)
+    p.fast_sums = int(bool(fast_sums))
     keep = []
     if allele_major is not None:
         am = np.ascontiguousarray(allele_major, dtype=np.int32)
@@ -168,8 +170,9 @@ class Genotyper:
     """Genotyper.cpp:450-646 in one call: de-duplicate read-ends, align, pair, coalesce, equivalence classes, EM."""
 
     def __init__(self, refset: RefSet, similarity=0.8, relax_intron=False, max_assign=2000, filter_frac=0.15,
-                 min_squarem_alpha=0.0, device=-1):
+                 min_squarem_alpha=0.0, device=-1, em_fast_sums=False):
         self.ref = refset
+        self.em_fast_sums = em_fast_sums
         self.refSet = SeqSet(refset, similarity, relax_intron, device)
         self.max_assign = max_assign
         self.filter_frac = filter_frac
@@ -183,7 +186,7 @@ class Genotyper:
         ref = self.ref
         prm = L.GenotypeParams(self.max_assign, self.min_squarem_alpha, self.filter_frac, L.ptr(ref.seq_weight),
                                L.ptr(ref.effective_len), L.ptr(ref.allele_major), L.ptr(ref.allele_gene),
-                               len(ref.major_names), len(ref.gene_names))
+                               len(ref.major_names), len(ref.gene_names), int(bool(self.em_fast_sums)))
         out = dict(abundance=np.zeros(ref.n), ec_abundance=np.zeros(ref.n),
                    equivalent_class=np.zeros(ref.n, dtype=np.int32), missing_coverage=np.zeros(ref.n, dtype=np.int32),
                    fragment_assigned=np.zeros(n, dtype=np.uint8))

@@ -7,9 +7,11 @@
 #include <string>
 #include <vector>
 
+#define T1K_EMU_COUNTERS 1
 #include "../t1k_b200/csrc/t1k_core.cuh"
 #include "../t1k_b200/csrc/t1k_host.hpp"
 
+long long t1k_emu_counters[16];
 using namespace t1k;
 
 struct Emu {
@@ -22,6 +24,8 @@ struct Emu {
 struct EmuOverlap { int32_t seqIdx, readStart, readEnd, seqStart, seqEnd, strand, matchCnt, relaxedMatchCnt, leftClip, rightClip; };
 
 extern "C" {
+
+long long *emu_counters() { return t1k_emu_counters; }
 
 Emu *emu_create(int32_t n, const char *bases, const int64_t *off, const int32_t *exonPtr, const int32_t *exonSE,
                 double sim, int32_t relax) {
