@@ -230,7 +230,8 @@ def main():
                    "parallelism": "read-shard x%d" % world},
         "e2e": {"value": total_frag / wall_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": wall_max * 1e3 / args.steps,
-                "phases_ms": {k: float(out[k]) for k in ("ms_dedup", "ms_align", "ms_pair", "ms_coalesce", "ms_em")}},
+                "phases_ms": {k: float(out[k]) for k in ("ms_dedup", "ms_align", "ms_pair", "ms_coalesce", "ms_em", "ms_align_kernel",
+                                                            "ms_pair_kernel", "ms_em_kernel")}},
         "gpu_launches": launches,
         "roofline": {"kernel": "k_assign", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": k_ms,

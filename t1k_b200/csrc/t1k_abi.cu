@@ -98,7 +98,9 @@ struct T1KRef {
   // launch state of k_assign, sized on first use
   DevMem candBuf, laneScratch, workCtr, errFlag, stats;
   u32 candCap = 0;
-  int gridBlocks = 0, hitCap = 0;
+  // two launch geometries of k_assign: [0] small hit tile (more resident warps), [1] tile for the worst case
+  int gridBlocks[2] = {0, 0}, hitCap[2] = {0, 0};
+  size_t scratchWarps = 0;
   u64 nPostings = 0;
   bool covDirty = true;
   ~T1KRef() { if (stream) cudaStreamDestroy(stream); }
@@ -189,24 +191,33 @@ int t1k_ref_n_alleles(const T1KRef *ref) { return ref ? ref->nAlleles : 0; }
 
 namespace {
 
-// persistent launch geometry of k_assign for reads up to maxLen bases
+// persistent launch geometries of k_assign for reads up to maxLen bases
 int setup_assign_launch(T1KRef *r, int maxLen) {
-  int hitCap = maxLen - KMER + 1 + 24;
-  if (hitCap < 64) hitCap = 64;
-  hitCap = (hitCap + 7) & ~7;
-  if (r->gridBlocks && hitCap <= r->hitCap) return T1K_OK;
-  const size_t perWarp = (warp_smem_bytes(hitCap) + 15) & ~(size_t)15;
-  const size_t smem = perWarp * WARPS_PER_BLOCK;
-  CK(cudaFuncSetAttribute(k_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int perSM = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_assign, WARPS_PER_BLOCK * 32, smem));
-  if (perSM < 1) return fail(T1K_ERR_UNSUPPORTED, "k_assign does not fit on an SM");
-  r->hitCap = hitCap;
-  r->gridBlocks = perSM * r->nSM;
-  const size_t warps = (size_t)r->gridBlocks * WARPS_PER_BLOCK;
+  int big = maxLen - KMER + 1 + 24;
+  if (big < 64) big = 64;
+  big = (big + 7) & ~7;
+  int small = 72;
+  if (const char *env = getenv("T1K_HIT_TILE")) small = std::max(8, atoi(env));
+  if (small > big) small = big;
+  if (r->gridBlocks[0] && big <= r->hitCap[1]) return T1K_OK;
+  const int caps[2] = {small, big};
+  size_t maxSmem = 0;
+  for (int c = 0; c < 2; ++c) maxSmem = std::max(maxSmem, ((warp_smem_bytes(caps[c]) + 15) & ~(size_t)15) * WARPS_PER_BLOCK);
+  CK(cudaFuncSetAttribute(k_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem));
+  size_t warps = 0;
+  for (int c = 0; c < 2; ++c) {
+    const size_t smem = ((warp_smem_bytes(caps[c]) + 15) & ~(size_t)15) * WARPS_PER_BLOCK;
+    int perSM = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_assign, WARPS_PER_BLOCK * 32, smem));
+    if (perSM < 1) return fail(T1K_ERR_UNSUPPORTED, "k_assign does not fit on an SM");
+    r->hitCap[c] = caps[c];
+    r->gridBlocks[c] = perSM * r->nSM;
+    warps = std::max(warps, (size_t)r->gridBlocks[c] * WARPS_PER_BLOCK);
+  }
   u64 cap = 2ull * (u64)r->nAlleles + 2048;
   if (cap > (1u << 20)) cap = 1u << 20;
   r->candCap = (u32)cap;
+  r->scratchWarps = warps;
   CK(r->candBuf.alloc(warps * r->candCap * sizeof(Cand)));
   CK(r->laneScratch.alloc(warps * 32 * (size_t)SCR_BYTES));
   CK(r->workCtr.alloc(sizeof(unsigned int)));
@@ -221,7 +232,7 @@ std::string decode_err(int err) {
   if (err & ERR_SCRATCH) s += " chaining scratch overflow;";
   if (err & ERR_EMIT) s += " more than MAX_EMIT seed overlaps for one (read, allele);";
   if (err & ERR_CAND) s += " candidate buffer overflow;";
-  if (err & ERR_HITS) s += " more k-mer hits on one allele than the shared-memory tile holds;";
+  if (err & ERR_HITS) s += " more k-mer hits on one allele than the largest shared-memory tile holds;";
   return s;
 }
 
@@ -264,8 +275,8 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   // record store: sized from free memory, grown (and only the deferred read-ends re-run) if it fills up
   size_t freeB = 0, totB = 0;
   CK(cudaMemGetInfo(&freeB, &totB));
-  u64 cap = std::max<u64>((u64)n * 512, 1u << 20);
-  const u64 capMax = (u64)(freeB * 0.80) / sizeof(Rec);
+  u64 cap = std::max<u64>((u64)n * 6144, 1u << 20);
+  const u64 capMax = (u64)(freeB * 0.70) / sizeof(Rec);
   if (cap > capMax) cap = capMax;
   if (const char *envCap = getenv("T1K_STORE_RECORDS")) cap = std::max<u64>(1024, strtoull(envCap, nullptr, 10));
   CK(a->store.alloc(cap * sizeof(Rec)));
@@ -277,50 +288,73 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   P.O.readOff = a->readOff.as<u64>(); P.O.readCnt = a->readCnt.as<u32>(); P.O.readRet = a->readRet.as<int32_t>();
   P.O.err = ref->errFlag.as<int>(); P.O.stats = ref->stats.as<unsigned long long>();
   P.candBuf = ref->candBuf.as<Cand>(); P.candCap = ref->candCap; P.laneScratch = ref->laneScratch.as<u8>();
-  P.workCtr = ref->workCtr.as<unsigned int>(); P.hitCap = ref->hitCap;
-  const size_t smem = ((warp_smem_bytes(ref->hitCap) + 15) & ~(size_t)15) * WARPS_PER_BLOCK;
-  DevMem workList;
+  P.workCtr = ref->workCtr.as<unsigned int>();
+  DevMem workList[2];
   std::vector<int32_t> hRet;
+  std::vector<u32> todo[2];          // pending read-ends per launch geometry; empty + first == everything
+  bool first = true;
   cudaEvent_t ev0, ev1;
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
   struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
   for (int round = 0;; ++round) {
-    CK(cudaMemsetAsync(ref->workCtr.p, 0, sizeof(unsigned int), st));
+    if (round > 0) CK(cudaMemsetAsync(ref->errFlag.p, 0, sizeof(int), st));   // round 0 keeps k_pack_reads' flags
     CK(cudaEventRecord(ev0, st));
-    k_assign<<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P);
-    CK(cudaGetLastError());
+    for (int c = 0; c < 2; ++c) {
+      if (!(first && c == 0) && todo[c].empty()) continue;
+      if (first && c == 0) { P.Q.workList = nullptr; P.Q.nWork = n; }
+      else {
+        CK(workList[c].alloc(todo[c].size() * 4));
+        CK(cudaMemcpyAsync(workList[c].p, todo[c].data(), todo[c].size() * 4, cudaMemcpyHostToDevice, st));
+        P.Q.workList = workList[c].as<u32>(); P.Q.nWork = (u32)todo[c].size();
+      }
+      P.hitCap = ref->hitCap[c];
+      const size_t smem = ((warp_smem_bytes(ref->hitCap[c]) + 15) & ~(size_t)15) * WARPS_PER_BLOCK;
+      CK(cudaMemsetAsync(ref->workCtr.p, 0, sizeof(unsigned int), st));
+      k_assign<<<ref->gridBlocks[c], WARPS_PER_BLOCK * 32, smem, st>>>(P);
+      CK(cudaGetLastError());
+      ++a->launches;
+    }
     CK(cudaEventRecord(ev1, st));
     int err = 0;
     CK(cudaMemcpyAsync(&err, ref->errFlag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     float ms = 0; CK(cudaEventElapsedTime(&ms, ev0, ev1));
-    a->msKernel += ms; ++a->launches;
+    a->msKernel += ms;
     ref->covDirty = true;
     if (err & (ERR_READ_LEN | ERR_READ_CHAR)) return fail(T1K_ERR_ARG, "read contains a character outside ACGTN or is too long");
-    if (err & ~ERR_STORE) return fail(T1K_ERR_UNSUPPORTED, "t1k_assign_batch:" + decode_err(err));
-    if (!(err & ERR_STORE)) break;
-    // some read-ends did not fit: grow the store and re-run exactly those (they added no coverage)
+    if (err & ~(ERR_STORE | ERR_HITS)) return fail(T1K_ERR_UNSUPPORTED, "t1k_assign_batch:" + decode_err(err));
+    if (!(err & (ERR_STORE | ERR_HITS))) break;
+    // deferred read-ends (they added no coverage): -3 moves to the big-tile geometry, -2 waits for a larger store
     hRet.resize(n);
     CK(cudaMemcpy(hRet.data(), a->readRet.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
-    std::vector<u32> todo;
-    for (u32 i = 0; i < n; ++i) if (hRet[i] == -2) todo.push_back(i);
-    CK(cudaMemGetInfo(&freeB, &totB));
-    u64 newCap = cap * 2;
-    if ((newCap - 0) * sizeof(Rec) > (u64)(freeB * 0.9)) newCap = (u64)(freeB * 0.9) / sizeof(Rec);
-    if (newCap <= cap + 1024 || round > 12) return fail(T1K_ERR_UNSUPPORTED, "overlap record store does not fit in device memory; use smaller batches");
-    DevMem bigger;
-    CK(bigger.alloc(newCap * sizeof(Rec)));
-    CK(cudaMemcpyAsync(bigger.p, a->store.p, cap * sizeof(Rec), cudaMemcpyDeviceToDevice, st));
-    unsigned long long ctr = cap;   // holes left by failed reservations stay unused
-    CK(cudaMemcpyAsync(a->storeCtr.p, &ctr, 8, cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
-    a->store.swap(bigger);
-    cap = newCap; a->storeCap = cap;
-    CK(workList.alloc(todo.size() * 4));
-    CK(cudaMemcpyAsync(workList.p, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(ref->errFlag.p, 0, sizeof(int), st));
-    P.O.store = a->store.as<Rec>(); P.O.storeCap = cap;
-    P.Q.workList = workList.as<u32>(); P.Q.nWork = (u32)todo.size();
+    std::vector<u32> next[2];
+    auto scan = [&](u32 i, int c) {
+      if (hRet[i] == -2) next[c].push_back(i);
+      else if (hRet[i] == -3) { if (c == 1) return false; next[1].push_back(i); }
+      return true;
+    };
+    bool ok = true;
+    if (first) { for (u32 i = 0; i < n; ++i) ok &= scan(i, 0); }
+    else for (int c = 0; c < 2; ++c) for (size_t k = 0; k < todo[c].size(); ++k) ok &= scan(todo[c][k], c);
+    if (!ok) return fail(T1K_ERR_UNSUPPORTED, "t1k_assign_batch:" + decode_err(ERR_HITS));
+    first = false;
+    todo[0].swap(next[0]); todo[1].swap(next[1]);
+    if (err & ERR_STORE) {
+      CK(cudaMemGetInfo(&freeB, &totB));
+      u64 newCap = cap * 2;
+      if (newCap * sizeof(Rec) > (u64)(freeB * 0.9)) newCap = (u64)(freeB * 0.9) / sizeof(Rec);
+      if (newCap <= cap + 1024 || round > 16) return fail(T1K_ERR_UNSUPPORTED, "overlap record store does not fit in device memory; use smaller batches");
+      DevMem bigger;
+      CK(bigger.alloc(newCap * sizeof(Rec)));
+      CK(cudaMemcpyAsync(bigger.p, a->store.p, cap * sizeof(Rec), cudaMemcpyDeviceToDevice, st));
+      unsigned long long ctr = cap;   // holes left by failed reservations stay unused
+      CK(cudaMemcpyAsync(a->storeCtr.p, &ctr, 8, cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+      a->store.swap(bigger);
+      cap = newCap; a->storeCap = cap;
+      P.O.store = a->store.as<Rec>(); P.O.storeCap = cap;
+    }
+    if (todo[0].empty() && todo[1].empty()) break;
   }
   unsigned long long used = 0;
   CK(cudaMemcpy(&used, a->storeCtr.p, 8, cudaMemcpyDeviceToHost));
@@ -334,7 +368,7 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
 int t1k_assignment_stats(const T1KAssignment *a, T1KAssignStats *out) {
   if (!a || !out) return fail(T1K_ERR_ARG, "t1k_assignment_stats: bad argument");
   out->postings = a->stats[0]; out->candidates = a->stats[1]; out->tiles = a->stats[2]; out->records = a->storeUsed;
-  out->ms_kernel = a->msKernel; out->grid_blocks = a->ref->gridBlocks; out->hit_cap = a->ref->hitCap; out->n_sm = a->ref->nSM;
+  out->ms_kernel = a->msKernel; out->grid_blocks = a->ref->gridBlocks[0]; out->hit_cap = a->ref->hitCap[0]; out->n_sm = a->ref->nSM;
   return T1K_OK;
 }
 

@@ -16,10 +16,12 @@
 #define T1K_HD __host__ __device__ __forceinline__
 #define T1K_HDN __host__ __device__
 #define T1K_NOINLINE __noinline__
+#define T1K_NOUNROLL _Pragma("unroll 1")
 #else
 #define T1K_HD inline
 #define T1K_HDN
 #define T1K_NOINLINE
+#define T1K_NOUNROLL
 #endif
 
 // host-emulation-only call-site counters (tests/host_emu.cpp); compiled out of the device build
@@ -128,9 +130,7 @@ T1K_HD int iabs(int a) { return a < 0 ? -a : a; }
 T1K_HD u64 fetch32(const u64 *plane, u64 w0, int pos) {
   const u64 *p = plane + w0 + (pos >> 5);
   int sh = (pos & 31) * 2;
-  u64 lo = p[0];
-  if (sh == 0) return lo;
-  return (lo >> sh) | (p[1] << (64 - sh));
+  return (p[0] >> sh) | ((p[1] << 1) << (63 - sh));      // branch-free funnel shift (sh in 0..62)
 }
 T1K_HD int base2(const u64 *plane, u64 w0, int pos) { return (int)((plane[w0 + (pos >> 5)] >> ((pos & 31) * 2)) & 3); }
 T1K_HD u64 lowmask2(int nBases) { return nBases >= 32 ? ~0ull : ((1ull << (2 * nBases)) - 1); }
@@ -150,12 +150,13 @@ T1K_HD u64 mm_chunk(const RefView &R, u64 w0, int tpos, const ReadView &Q, int p
 }
 
 // mismatching columns among rows [lo, hi] of the window when row r of the read is paired with allele column r + d
-T1K_HDN inline int shifted_mm(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos, int n, int d, int lo, int hi) {
+T1K_HDN T1K_NOINLINE inline int shifted_mm(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos, int n, int d, int lo, int hi) {
   if (lo < 0) lo = 0;
   if (lo < -d) lo = -d;
   if (hi > n - 1) hi = n - 1;
   if (hi > n - 1 - d) hi = n - 1 - d;
   int c = 0;
+  T1K_NOUNROLL
   for (int k = lo; k <= hi; k += 32) c += popc64(mm_chunk(R, w0, tpos + k + d, Q, ppos + k, hi - k + 1));
   return c;
 }
@@ -172,56 +173,65 @@ T1K_HDN inline int shifted_mm(const RefView &R, u64 w0, int tpos, const ReadView
 // those are enumerated exactly: the best segment starts at a mismatch (or up to |d| rows before one when the leading
 // rows are the unpaired ones) and ends at a mismatch (or up to |d| rows after one).  More mismatches fall back to
 // a shift histogram bound, and failing that to the DP.
-T1K_HDN inline bool diag_certified(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos, int n, int &mmOut) {
-  int mm = 0;
-  for (int k = 0; k < n; k += 32) mm += popc64(mm_chunk(R, w0, tpos + k, Q, ppos + k, n - k));
-  mmOut = mm;
-  if (mm <= 3) return true;
-  if (mm <= 5) {
-    int pos[5];
-    {
-      int c = 0;
-      for (int k = 0; k < n; k += 32) {
-        u64 m = mm_chunk(R, w0, tpos + k, Q, ppos + k, n - k);
-        while (m) { pos[c < 5 ? c : 4] = k + (ctz64(m) >> 1); ++c; m &= m - 1; }
-      }
+// 4 or 5 diagonal mismatches: exact enumeration of the single-shift excursions (see above)
+T1K_HDN T1K_NOINLINE inline bool diag_certified_45(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos, int n, int mm) {
+  int pos[5];
+  {
+    int c = 0;
+    T1K_NOUNROLL
+    for (int k = 0; k < n; k += 32) {
+      u64 m = mm_chunk(R, w0, tpos + k, Q, ppos + k, n - k);
+      T1K_NOUNROLL
+      while (m) { pos[c < 5 ? c : 4] = k + (ctz64(m) >> 1); ++c; m &= m - 1; }
     }
-    for (int d = 1; d <= mm - 3; ++d) {
-      for (int i = 0; i + 2 + d < mm; ++i)            // at least 3 + d diagonal mismatches inside the segment
-        for (int j = i + 2 + d; j < mm; ++j)
-          for (int t = 0; t <= d; ++t) {
-            // deletion first (allele ahead by d): rows [A, B - d] paired with columns r + d, last d rows unpaired
-            {
-              const int A = pos[i], B = pos[j] + t;
-              if (B <= n - 1 && B - d >= A - 1) {
-                int in = 0;
-                for (int q = 0; q < mm; ++q) in += pos[q] >= A && pos[q] <= B;
-                if (in - shifted_mm(R, w0, tpos, Q, ppos, n, d, A, B - d) > 2 + d) return false;
-              }
-            }
-            // insertion first (allele behind by d): first d rows unpaired, rows [A + d, B] paired with columns r - d
-            {
-              const int A = pos[i] - t, B = pos[j];
-              if (A >= 0 && B >= A + d - 1) {
-                int in = 0;
-                for (int q = 0; q < mm; ++q) in += pos[q] >= A && pos[q] <= B;
-                if (in - shifted_mm(R, w0, tpos, Q, ppos, n, -d, A + d, B) > 2 + d) return false;
-              }
+  }
+  T1K_NOUNROLL
+  for (int d = 1; d <= mm - 3; ++d) {
+    T1K_NOUNROLL
+    for (int i = 0; i + 2 + d < mm; ++i)            // at least 3 + d diagonal mismatches inside the segment
+      T1K_NOUNROLL
+      for (int j = i + 2 + d; j < mm; ++j)
+        T1K_NOUNROLL
+        for (int t = 0; t <= d; ++t) {
+          // deletion first (allele ahead by d): rows [A, B - d] paired with columns r + d, last d rows unpaired
+          {
+            const int A = pos[i], B = pos[j] + t;
+            if (B <= n - 1 && B - d >= A - 1) {
+              int in = 0;
+              T1K_NOUNROLL
+              for (int q = 0; q < mm; ++q) in += pos[q] >= A && pos[q] <= B;
+              if (in - shifted_mm(R, w0, tpos, Q, ppos, n, d, A, B - d) > 2 + d) return false;
             }
           }
-    }
-    return true;
+          // insertion first (allele behind by d): first d rows unpaired, rows [A + d, B] paired with columns r - d
+          {
+            const int A = pos[i] - t, B = pos[j];
+            if (A >= 0 && B >= A + d - 1) {
+              int in = 0;
+              T1K_NOUNROLL
+              for (int q = 0; q < mm; ++q) in += pos[q] >= A && pos[q] <= B;
+              if (in - shifted_mm(R, w0, tpos, Q, ppos, n, -d, A + d, B) > 2 + d) return false;
+            }
+          }
+        }
   }
-  if (mm > 24) return false;
+  return true;
+}
+
+// 6..24 diagonal mismatches: shift-histogram bound (F_d = diagonal mismatches that shift d turns into matches;
+// sum_d max(0, F_d - 1) <= 1 leaves every excursion <= 0)
+T1K_HDN T1K_NOINLINE inline bool diag_certified_hist(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos, int n) {
   int F[2 * BAND + 1];
-#pragma unroll
+  T1K_NOUNROLL
   for (int d = 0; d <= 2 * BAND; ++d) F[d] = 0;
+  T1K_NOUNROLL
   for (int k = 0; k < n; k += 32) {
     u64 m = mm_chunk(R, w0, tpos + k, Q, ppos + k, n - k);
+    T1K_NOUNROLL
     while (m) {
       int p = k + (ctz64(m) >> 1);
       m &= m - 1;
-#pragma unroll
+      T1K_NOUNROLL
       for (int d = -BAND; d <= BAND; ++d) {
         if (d == 0) continue;
         int q = p + d;
@@ -231,9 +241,20 @@ T1K_HDN inline bool diag_certified(const RefView &R, u64 w0, int tpos, const Rea
     }
   }
   int excess = 0;
-#pragma unroll
+  T1K_NOUNROLL
   for (int d = 0; d <= 2 * BAND; ++d) excess += F[d] > 1 ? F[d] - 1 : 0;
   return excess <= 1;
+}
+
+T1K_HD bool diag_certified(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos, int n, int &mmOut) {
+  int mm = 0;
+  T1K_NOUNROLL
+  for (int k = 0; k < n; k += 32) mm += popc64(mm_chunk(R, w0, tpos + k, Q, ppos + k, n - k));
+  mmOut = mm;
+  if (mm <= 3) return true;
+  if (mm <= 5) return diag_certified_45(R, w0, tpos, Q, ppos, n, mm);
+  if (mm > 24) return false;
+  return diag_certified_hist(R, w0, tpos, Q, ppos, n);
 }
 
 // AlignAlgo::GlobalAlignment (AlignAlgo.hpp:215-421), one lane, band-only storage:
@@ -255,18 +276,21 @@ T1K_HDN T1K_NOINLINE inline int dp_align(const RefView &R, u64 w0, int tpos, int
   int *mP = S.rows(), *eP = mP + (MAX_BAND_W + 2), *mC = eP + (MAX_BAND_W + 2), *eC = mC + (MAX_BAND_W + 2);
   u8 *dir = S.dir();
   // row 0 window: columns -lb-1 .. rb+1
+  T1K_NOUNROLL
   for (int jj = 0; jj < W; ++jj) {
     int j = jj - lb - 1;
     if (j < 0 || j > lent) { mP[jj] = negInf; eP[jj] = negInf; }
     else if (j == 0) { mP[jj] = 0; eP[jj] = 0; }
     else { mP[jj] = -4 - 4 * j; eP[jj] = stale; }
   }
+  T1K_NOUNROLL
   for (int i = 1; i <= lenp; ++i) {
     int start = i - lb < 1 ? 1 : i - lb;
     int end = i + rb > lent ? lent : i + rb;
     int pb = base2(Q.seq2, 0, ppos + i - 1), pn = base2(Q.n2, 0, ppos + i - 1);
     int fPrev = negInf, mLeft = negInf;        // f and m of column j-1 in this row
     u8 *drow = dir + (size_t)i * W;
+    T1K_NOUNROLL
     for (int jj = 0; jj < W; ++jj) {
       int j = i - lb - 1 + jj;
       int mv, ev, fv;
@@ -299,6 +323,7 @@ T1K_HDN T1K_NOINLINE inline int dp_align(const RefView &R, u64 w0, int tpos, int
   }
   // traceback (AlignAlgo.hpp:323-408); boundary rows/columns by their closed forms
   int ti = lenp, tj = lent, mat = 0, n = 0;
+  T1K_NOUNROLL
   while (ti > 0 || tj > 0) {
     if (n >= SCR_OPS - 2) { err |= ERR_BAND; return -1; }
     if (mat == 0) {
@@ -329,12 +354,13 @@ T1K_HDN T1K_NOINLINE inline int dp_align(const RefView &R, u64 w0, int tpos, int
       } else mat = 1;
     }
   }
+  T1K_NOUNROLL
   for (int a = 0, b = n - 1; a < b; ++a, --b) { u8 t = ops[a]; ops[a] = ops[b]; ops[b] = t; }
   return n;
 }
 
 // number of EDIT_MATCH columns of GlobalAlignment(t, lent, p, lenp)  (GetAlignStats, SeqSet.hpp:438-455)
-T1K_HDN inline int align_matches(const RefView &R, u64 w0, int tpos, int lent, const ReadView &Q, int ppos, int lenp,
+T1K_HDN T1K_NOINLINE inline int align_matches(const RefView &R, u64 w0, int tpos, int lent, const ReadView &Q, int ppos, int lenp,
                                  const LaneScratch &S, int &err) {
   if (lent == 0 || lenp == 0) return 0;
   T1K_COUNT(4, 1);
@@ -346,12 +372,14 @@ T1K_HDN inline int align_matches(const RefView &R, u64 w0, int tpos, int lent, c
   int n = dp_align(R, w0, tpos, lent, Q, ppos, lenp, S, err);
   int c = 0;
   const u8 *ops = S.ops();
+  T1K_NOUNROLL
   for (int i = 0; i < n; ++i) c += ops[i] == 0;
   return c;
 }
 
 // any N of the allele inside [s, e] (clamped to the allele)
 T1K_HD bool n_in_range(const RefView &R, u64 w0, int s, int e) {
+  T1K_NOUNROLL
   for (int k = s; k <= e; k += 32)
     if (fetch32(R.n2, w0, k) & lowmask2(e - k + 1)) return true;
   return false;
@@ -367,6 +395,7 @@ T1K_HD bool sep_in_range(const RefView &R, u64 w0, int len, int s, int e) {
 T1K_HD bool low_complex(const ReadView &Q, int s, int e) {
   int cnt[4] = {0, 0, 0, 0};
   int n = e - s + 1;
+  T1K_NOUNROLL
   for (int k = 0; k < n; k += 32) {
     u64 w = fetch32(Q.seq2, 0, s + k), nm = fetch32(Q.n2, 0, s + k);
     u64 keep = ~nm & M55 & lowmask2(n - k);
@@ -408,22 +437,26 @@ T1K_HD u64 order_key(int matchCnt, int denom, int span, int seqIdx, int readStar
 // ---- chain consumer: GetOverlapsFromHits tail (SeqSet.hpp:1500-1550) + the matchCnt recomputation of
 // GetOverlapsFromRead (SeqSet.hpp:1697-1845).  `C` yields the LIS chain as encoded hits.
 template <class Chain>
-T1K_HDN inline void consume_chain(const RefView &R, const ReadView &Q, int strand01, int seqIdx, const Chain &C, int sz,
+T1K_HDN T1K_NOINLINE inline void consume_chain(const RefView &R, const ReadView &Q, int strand01, int seqIdx, const Chain &C, int sz,
                                   const LaneScratch &S, int &nEmit, u64 &bestStrandKey, int &err) {
   if (sz * KMER < HIT_LEN_REQ) return;
   int hitLen = 0, seqLenCov = 0;
   {
     int i = 0;
+    T1K_NOUNROLL
     while (i < sz) {
       int j = i + 1;
+      T1K_NOUNROLL
       while (j < sz && hit_a(C(j)) <= hit_a(C(j - 1)) + KMER - 1) ++j;
       hitLen += hit_a(C(j - 1)) - hit_a(C(i)) + KMER;
       i = j;
     }
     if (hitLen < HIT_LEN_REQ) return;
     i = 0;
+    T1K_NOUNROLL
     while (i < sz) {
       int j = i + 1;
+      T1K_NOUNROLL
       while (j < sz && hit_b(C(j)) <= hit_b(C(j - 1)) + KMER - 1) ++j;
       seqLenCov += hit_b(C(j - 1)) - hit_b(C(i)) + KMER;
       i = j;
@@ -436,6 +469,7 @@ T1K_HDN inline void consume_chain(const RefView &R, const ReadView &Q, int stran
   u64 sk = strand_key(2 * hitLen, re - rs, seqIdx, strand01);
   if (sk > bestStrandKey) bestStrandKey = sk;
   int mc = 2 * KMER;
+  T1K_NOUNROLL
   for (int j = 1; j < sz; ++j) {
     int pa = hit_a(C(j - 1)), pb = hit_b(C(j - 1)), a = hit_a(C(j)), b = hit_b(C(j));
     bool aOv = pa + KMER - 1 >= a, bOv = pb + KMER - 1 >= b;
@@ -465,21 +499,25 @@ struct ChainDirect {   // contiguous run of a hit store
 // ---- SeqSet::GetOverlapsFromHits for one (strand, allele) group (SeqSet.hpp:1303-1553; filter=0, isRef).
 // hits: n encoded hits at h[i*stride]; on entry sorted by (readOffset, seqOffset); sorted in place by diagonal.
 // Scratch use of the general (multi-diagonal) path: conc/chain/top/link live in S.dir().
-T1K_HDN inline void chain_allele(const RefView &R, const ReadView &Q, int strand01, int seqIdx, u32 *h, int stride, int n,
+T1K_HDN T1K_NOINLINE inline void chain_allele(const RefView &R, const ReadView &Q, int strand01, int seqIdx, u32 *h, int stride, int n,
                                  const LaneScratch &S, int &nEmit, u64 &bestStrandKey, int &err) {
   if (n < 3) return;
   // insertion sort by (diag, b, a); a single-diagonal group is already in order
+  T1K_NOUNROLL
   for (int i = 1; i < n; ++i) {
     u32 v = h[(size_t)i * stride];
     if (!hit_diag_less(v, h[(size_t)(i - 1) * stride])) continue;
     int j = i - 1;
+    T1K_NOUNROLL
     while (j >= 0 && hit_diag_less(v, h[(size_t)j * stride])) { h[(size_t)(j + 1) * stride] = h[(size_t)j * stride]; --j; }
     h[(size_t)(j + 1) * stride] = v;
   }
   int dom = 0;
+  T1K_NOUNROLL
   for (int s = 0; s < n;) {
     int e, cur, curCnt = 1, domCnt = 0, prevC;
     { u32 v = h[(size_t)s * stride]; cur = hit_a(v) - hit_b(v); prevC = cur; }
+    T1K_NOUNROLL
     for (e = s + 1; e < n; ++e) {
       u32 v = h[(size_t)e * stride];
       int c = hit_a(v) - hit_b(v);
@@ -509,7 +547,9 @@ T1K_HDN inline void chain_allele(const RefView &R, const ReadView &Q, int strand
     u32 *chain = conc + m;
     u16 *top = (u16 *)(chain + m);
     u16 *link = top + m;
+    T1K_NOUNROLL
     for (int k = s; k < e; ++k) used[hit_a(h[(size_t)k * stride])] = 0xFFFF;
+    T1K_NOUNROLL
     for (int k = s; k < e; ++k) {
       u32 v = h[(size_t)k * stride];
       int d = iabs(hit_a(v) - hit_b(v) - dom);
@@ -517,12 +557,14 @@ T1K_HDN inline void chain_allele(const RefView &R, const ReadView &Q, int strand
       if (used[hit_a(v)] > d) used[hit_a(v)] = (u16)d;
     }
     int cn = 0;
+    T1K_NOUNROLL
     for (int k = s; k < e; ++k) {
       u32 v = h[(size_t)k * stride];
       int d = iabs(hit_a(v) - hit_b(v) - dom);
       if (d > 0xFFFE) d = 0xFFFE;
       if (d == used[hit_a(v)]) {             // insertion into (b,a) order == numeric order
         int j = cn - 1;
+        T1K_NOUNROLL
         while (j >= 0 && conc[j] > v) { conc[j + 1] = conc[j]; --j; }
         conc[j + 1] = v; ++cn;
       }
@@ -530,12 +572,14 @@ T1K_HDN inline void chain_allele(const RefView &R, const ReadView &Q, int strand
     // LIS over read offsets (non-strict probe, strict extend; Q4)
     int ret = 1;
     top[0] = 0; link[0] = 0xFFFF;
+    T1K_NOUNROLL
     for (int i = 1; i < cn; ++i) {
       int ai = hit_a(conc[i]);
       int tag;
       if (hit_a(conc[top[ret - 1]]) <= ai) tag = ret - 1;
       else {
         int l = 0, r = ret - 1; tag = -2;
+        T1K_NOUNROLL
         while (l <= r) {
           int mid = (l + r) / 2, am = hit_a(conc[top[mid]]);
           if (ai == am) { tag = mid; break; }
@@ -551,14 +595,17 @@ T1K_HDN inline void chain_allele(const RefView &R, const ReadView &Q, int strand
     }
     {
       int k = top[ret - 1];
+      T1K_NOUNROLL
       for (int i = ret - 1; i >= 0; --i) { chain[i] = conc[k]; k = link[k]; }
     }
     int sz = 0;
+    T1K_NOUNROLL
     for (int i = 0; i < ret; ++i)
       if (i == 0 || hit_b(chain[i]) != hit_b(chain[sz - 1])) chain[sz++] = chain[i];
     // the chain was built in S.dir(), which consume_chain's gap DPs overwrite: park it in its own region
     u32 *park = S.chain();
     if (sz > SCR_CHAIN / 4) { err |= ERR_SCRATCH; s = e; continue; }
+    T1K_NOUNROLL
     for (int i = 0; i < sz; ++i) park[i] = chain[i];
     ChainDirect cd; cd.p = park; cd.stride = 1;
     consume_chain(R, Q, strand01, seqIdx, cd, sz, S, nEmit, bestStrandKey, err);
@@ -567,7 +614,7 @@ T1K_HDN inline void chain_allele(const RefView &R, const ReadView &Q, int strand
 }
 
 // ---- SeqSet::ExtendOverlap (SeqSet.hpp:1994-2100) + the separator tests of AssignRead (SeqSet.hpp:2163-2169)
-T1K_HDN inline void extend_cand(const RefView &R, const ReadView &Q, Cand &c, const LaneScratch &S, int &err) {
+T1K_HDN T1K_NOINLINE inline void extend_cand(const RefView &R, const ReadView &Q, Cand &c, const LaneScratch &S, int &err) {
   const u64 w0 = R.wordOff[c.seqIdx];
   const int clen = R.len[c.seqIdx], len = Q.len;
   int rs = c.readStart, re = c.readEnd, ss = c.seqStart, se = c.seqEnd;
@@ -576,11 +623,13 @@ T1K_HDN inline void extend_cand(const RefView &R, const ReadView &Q, Cand &c, co
   if (sep_in_range(R, w0, clen, ss - rs, se + (len - re - 1))) flags |= CF_NEEDCLIP;
   int lo = imin(rs, ss), leftClip = 0, rightClip = 0;
   if (rs > ss) leftClip = rs - ss;
+  T1K_NOUNROLL
   for (int i = 0; i < lo; ++i)
     if (base2(R.n2, w0, ss - i - 1)) { leftClip = lo - i; lo = i; break; }
   int m = align_matches(R, w0, ss - lo, lo, Q, rs - lo, lo, S, err);
   int ro = imin(len - 1 - re, clen - 1 - se);
   if (len - 1 - re > clen - 1 - se) rightClip = len - 1 - re - (clen - 1 - se);
+  T1K_NOUNROLL
   for (int i = 0; i < ro; ++i)
     if (base2(R.n2, w0, se + 1 + i)) { rightClip = ro - i; ro = i; break; }
   m += align_matches(R, w0, se + 1, ro, Q, re + 1, ro, S, err);
@@ -606,7 +655,7 @@ T1K_HD void cov_add(int32_t *p, int v) {
 // ---- full-read alignment of an extended overlap (SeqSet.hpp:2203-2274): exon-relaxed match count and
 // base coverage.  Coverage is kept as a range-add difference array plus point corrections, so a
 // certified-diagonal record costs 2 + (#uncredited columns) atomics instead of one per base.
-T1K_HDN inline void full_align(const RefView &R, const ReadView &Q, Cand &c, int weight, const LaneScratch &S, int &err) {
+T1K_HDN T1K_NOINLINE inline void full_align(const RefView &R, const ReadView &Q, Cand &c, int weight, const LaneScratch &S, int &err) {
   const u64 w0 = R.wordOff[c.seqIdx];
   const int tpos = c.eSeqStart, ppos = c.eReadStart;
   const int lent = c.eSeqEnd - c.eSeqStart + 1, lenp = c.eReadEnd - c.eReadStart + 1;
@@ -616,11 +665,13 @@ T1K_HDN inline void full_align(const RefView &R, const ReadView &Q, Cand &c, int
   if (lent == lenp && diag_certified(R, w0, tpos, Q, ppos, lent, mm)) {
     int exMm = 0;
     if (weight > 0) { cov_add(R.covDiff + cb + tpos, weight); cov_add(R.covDiff + cb + tpos + lent, -weight); }
+    T1K_NOUNROLL
     for (int k = 0; k < lent; k += 32) {
       u64 d = mm_chunk(R, w0, tpos + k, Q, ppos + k, lent - k);
       if (R.relax) exMm += popc64(d & fetch32(R.ex2, w0, tpos + k));
       if (weight > 0) {
         u64 un = (d | fetch32(R.n2, w0, tpos + k) | fetch32(Q.n2, 0, ppos + k)) & lowmask2(lent - k);
+        T1K_NOUNROLL
         while (un) {
           int p = k + (ctz64(un) >> 1);
           un &= un - 1;
@@ -636,6 +687,7 @@ T1K_HDN inline void full_align(const RefView &R, const ReadView &Q, Cand &c, int
   if (n < 0) { c.relaxed = c.eMatchCnt; return; }
   const u8 *ops = S.ops();
   int refPos = tpos, readPos = ppos, m = 0;
+  T1K_NOUNROLL
   for (int k = 0; k < n; ++k) {
     int op = ops[k];
     if (R.relax) {

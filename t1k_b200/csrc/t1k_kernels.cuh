@@ -25,7 +25,7 @@ struct AssignOut {
   u64 storeCap;
   u64 *readOff;            // per read-end: first record
   u32 *readCnt;
-  int32_t *readRet;        // AssignRead's return value; -2 = deferred (store full)
+  int32_t *readRet;        // AssignRead's return value; -2 = deferred (store full), -3 = deferred (hit tile too small)
   int *err;
   unsigned long long *stats;   // [0] postings visited, [1] candidates, [2] tiles, [3] dp calls (debug/roofline)
 };
@@ -137,14 +137,17 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
   u32 nCand = 0, nFwd = 0;
   u64 bestKey = 0;
   unsigned long long stPost = 0, stTiles = 0;
+  bool overflow = false;   // some allele has more hits than the shared-memory tile holds: re-run with the big tile
   ReadView Qv; Qv.seq2 = W.seq; Qv.n2 = W.nn; Qv.len = len;
 
   if (len >= KMER) {
     const int NP = len - KMER + 1;
-    for (int pass = 0; pass < 2; ++pass) {
+    T1K_NOUNROLL
+    for (int pass = 0; pass < 2 && !overflow; ++pass) {
       const int strand01 = pass == 0 ? 1 : 0;
       load_planes(P, r, strand01, W, lane);
       // ---- k-mer codes and posting ranges of every window (GetHitsFromRead, SeqSet.hpp:1093-1153)
+      T1K_NOUNROLL
       for (int a = lane; a < NP; a += 32) {
         u32 code = (u32)(fetch32(W.seq, 0, a) & 0x3FFFFFull);
         bool valid = (fetch32(W.nn, 0, a) & 0x155555ull) == 0;
@@ -156,6 +159,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
       int nS = 0;
       if (lane == 0) {
         u32 prev = 0; int skip = 0;
+        T1K_NOUNROLL
         for (int a = 0; a < NP; ++a) {
           u32 code = W.nxt[a];
           if (a == 0 || prev != code) {
@@ -170,12 +174,15 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
       }
       nS = __shfl_sync(FULL, nS, 0);
       __syncwarp();
+      T1K_NOUNROLL
       for (int k = lane; k < nS; k += 32) { W.nxt[k] = R.post[W.cur[k]].idx; stPost += W.end[k] - W.cur[k]; }
       __syncwarp();
       u64 laneKey = 0;
       // ---- allele tiles: 32 consecutive allele ids starting at the smallest pending one
+      T1K_NOUNROLL
       for (;;) {
         u32 mn = 0xffffffffu;
+        T1K_NOUNROLL
         for (int k = lane; k < nS; k += 32) mn = min(mn, W.nxt[k]);
         mn = warp_min_u32(mn);
         if (mn == 0xffffffffu) break;
@@ -183,9 +190,11 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
         ++stTiles;
         W.cnt[lane] = 0;
         __syncwarp();
+        T1K_NOUNROLL
         for (int k = 0; k < nS; ++k) {           // seeds in read-offset order => per-allele hits sorted by (a, b)
           if (W.nxt[k] >= base + 32) continue;   // warp-uniform (shared-memory broadcast)
           const u32 a = W.seedA[k];
+          T1K_NOUNROLL
           for (;;) {
             const u32 c = W.cur[k], e = W.end[k];
             Posting p; p.idx = 0xffffffffu; p.off = 0;
@@ -220,10 +229,8 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
         // ---- lane-per-allele chaining + rescoring
         const int n = (int)W.cnt[lane];
         int nEmit = 0;
-        if (n >= 3) {
-          if (n <= CAP) chain_allele(R, Qv, strand01, (int)(base + lane), W.H + lane, 32, n, S, nEmit, laneKey, err);
-          else err |= ERR_HITS;
-        }
+        if (__any_sync(FULL, n > CAP)) { overflow = true; break; }
+        if (n >= 3) chain_allele(R, Qv, strand01, (int)(base + lane), W.H + lane, 32, n, S, nEmit, laneKey, err);
         // ---- ordered emission (allele order == lane order)
         int incl = nEmit;
 #pragma unroll
@@ -233,6 +240,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
           if (nCand + tot > P.candCap) err |= ERR_CAND;
           else {
             const Cand *em = S.emit();
+            T1K_NOUNROLL
             for (int j = 0; j < nEmit; ++j) cands[nCand + incl - nEmit + j] = em[j];
             nCand += tot;
           }
@@ -249,12 +257,13 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
   int ret = -1, nFinal = 0;
   unsigned long long pos = 0;
   bool deferred = false;
-  if (c1 - c0 > 0) {
+  if (c1 - c0 > 0 && !overflow) {
     if (best01 == 1) load_planes(P, r, 1, W, lane);
     __threadfence_block();
     __syncwarp();
     // pass 1: extension; first candidate (list order) whose extension fails
     u64 fKey = ~0ull; int fIdx = 0x7fffffff;
+    T1K_NOUNROLL
     for (int i = c0 + lane; i < c1; i += 32) {
       Cand c = cands[i];
       extend_cand(R, Qv, c, S, err);
@@ -268,6 +277,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
     __syncwarp();
     // pass 2: goodMatchCnt
     int good = -1;
+    T1K_NOUNROLL
     for (int i = c0 + lane; i < c1; i += 32) {
       const Cand &c = cands[i];
       if ((c.flags & CF_SEP) || !(c.flags & CF_RET)) continue;
@@ -276,6 +286,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
     good = warp_max_i32(good);
     // pass 3: inclusion
     int bestMc = -1, nInc = 0;
+    T1K_NOUNROLL
     for (int i = c0 + lane; i < c1; i += 32) {
       Cand &c = cands[i];
       if ((c.flags & CF_SEP) || !(c.flags & CF_RET)) continue;
@@ -296,6 +307,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
     if (!deferred) {
       // pass 4: full-read alignment of everything within 10 of the best (Q8)
       if (weight >= 0) {
+        T1K_NOUNROLL
         for (int i = c0 + lane; i < c1; i += 32) {
           Cand c = cands[i];
           if (!(c.flags & CF_INCLUDE)) continue;
@@ -308,6 +320,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
       const bool usePost = nInc > 1000;      // SeqSet.hpp:2290-2298
       if (usePost) {
         u64 bKey = ~0ull; int bIdx = 0x7fffffff;
+        T1K_NOUNROLL
         for (int i = c0 + lane; i < c1; i += 32) if (cands[i].flags & CF_INCLUDE) {
           u64 k = cand_key_post(cands[i]);
           if (pair_less(k, i, bKey, bIdx)) { bKey = k; bIdx = i; }
@@ -315,6 +328,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
         warp_min_pair(bKey, bIdx);
         const double bestSim = (double)cands[bIdx].eMatchCnt / (double)cand_denom_post(cands[bIdx]);
         u64 cKey = ~0ull; int cIdx = 0x7fffffff;
+        T1K_NOUNROLL
         for (int i = c0 + lane; i < c1; i += 32) if ((cands[i].flags & CF_INCLUDE) && i != bIdx) {
           double sim = (double)cands[i].eMatchCnt / (double)cand_denom_post(cands[i]);
           if (sim < bestSim - 0.1) {
@@ -323,6 +337,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
           }
         }
         warp_min_pair(cKey, cIdx);
+        T1K_NOUNROLL
         for (int i = c0 + lane; i < c1; i += 32) if (cands[i].flags & CF_INCLUDE) {
           u64 k = cand_key_post(cands[i]);
           if (!pair_less(k, i, cKey, cIdx)) cands[i].flags &= ~CF_INCLUDE;
@@ -331,6 +346,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
       }
       // pass 5: ordered compaction into the store (allele order is kept: pairing binary-searches it)
       int running = 0;
+      T1K_NOUNROLL
       for (int b = c0; b < c1; b += 32) {
         const int i = b + lane;
         bool inc = false;
@@ -354,9 +370,10 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
   }
   if (lane == 0) {
     P.O.readOff[r] = pos;
-    P.O.readCnt[r] = deferred ? 0 : (u32)nFinal;
-    P.O.readRet[r] = deferred ? -2 : ret;
+    P.O.readCnt[r] = (deferred || overflow) ? 0 : (u32)nFinal;
+    P.O.readRet[r] = overflow ? -3 : deferred ? -2 : ret;
     if (deferred) atomicOr(P.O.err, ERR_STORE);
+    if (overflow) atomicOr(P.O.err, ERR_HITS);
   }
   err = __reduce_or_sync(FULL, (unsigned)err);
   if (lane == 0 && err) atomicOr(P.O.err, err);
@@ -373,7 +390,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
 
 extern __shared__ u64 t1k_smem[];
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_assign(AssignParams P) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_assign(AssignParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t gwarp = (size_t)blockIdx.x * WARPS_PER_BLOCK + warp;
   u8 *sm = (u8 *)t1k_smem + (size_t)warp * ((warp_smem_bytes(P.hitCap) + 15) & ~(size_t)15);
