@@ -39,7 +39,7 @@ def make_workload(n_pairs, seed, ref_records=None):
     recs = ref_records if ref_records is not None else synth.make_hla_rna_ref(seed=11)
     ref = RefSet(recs)
     kept = list(zip(ref.names, ref.comments, ref.seqs))
-    r1, r2, _ = synth.simulate_pairs(kept, n_pairs, read_len=150, insert=(300, 450), err=0.002, alleles_per_gene=2, seed=seed)
+    r1, r2, _ = synth.simulate_pairs(kept, n_pairs, read_len=150, insert=(300, 450), err=0.002, alleles_per_gene=2, seed=seed, src_seed=7)
     return recs, ref, r1, r2
 
 
@@ -172,15 +172,17 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from t1k_b200.genotyper import Genotyper
+    comm = None
     if world > 1:
         from t1k_b200 import dist_em
+        comm = dist_em.Comm.from_torch_distributed(local)       # NCCL communicator of the C library (id via torch.distributed)
 
     recs, ref, r1, r2 = make_workload(args.pairs, seed=100 + rank)          # weak scaling: every rank its own shard
     gt = Genotyper(ref, 0.97, False, device=local)
     h2d = int(r1.nbytes + r2.nbytes)
 
     def step():
-        return dist_em.genotype_sharded(gt, r1, r2, world, rank) if world > 1 else gt.Genotype(r1, r2)
+        return dist_em.genotype_sharded(gt, r1, r2, comm) if world > 1 else gt.Genotype(r1, r2)
 
     def barrier():
         if world > 1:

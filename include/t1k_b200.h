@@ -28,6 +28,8 @@ enum {
 
 typedef struct T1KRef T1KRef;               /* allele reference + k-mer index + coverage, resident in HBM */
 typedef struct T1KAssignment T1KAssignment; /* per-read-end overlap lists, resident in HBM */
+typedef struct T1KComm T1KComm;             /* NCCL communicator of the read-sharded path: one rank per process/GPU */
+typedef struct T1KGroups T1KGroups;         /* coalesced read groups (host): the rows of the EM's incidence matrix */
 
 /* One (read-end, allele) alignment: the result fields of `struct _overlap` (SeqSet.hpp:89-101).
  * similarity = matchCnt / (readEnd-readStart+1 + seqEnd-seqStart+1 + 2*leftClip + 2*rightClip)
@@ -119,6 +121,11 @@ typedef struct {
    *    reference's x86 result; the dependent add chains are serial);
    * 1: warp/block tree reductions (fixed order, run-to-run reproducible, ~1e-16 relative from the reference). */
   int32_t fast_sums;
+  /* read-sharded EM: every rank passes the SAME problem; rank r runs the E-step over its contiguous
+   * row range (t1k_em_partition) and one ncclAllReduce(sum, f64, n_ec) per EMupdate combines ecReadCount; the
+   * M-step / SQUAREM vector steps are replicated.  NULL = single GPU.  With more than one rank the sums no longer
+   * run in the reference's order (results within 1e-5 relative, deterministic for a given world size). */
+  T1KComm *comm;
 } T1KEmProblem;
 
 typedef struct {
@@ -141,6 +148,11 @@ typedef struct {
   const int32_t *effective_len;/* [n_alleles] SeqSet::GetSeqEffectiveLen (after InitAlleleInfo's adjustment) */
   const int32_t *allele_major, *allele_gene; int32_t n_major, n_gene;
   int32_t em_fast_sums;        /* T1KEmProblem.fast_sums */
+  /* read-sharded run: reads1/reads2 are THIS rank's fragments.  Alignment + pairing + coalescing run per rank with no
+   * data-path collective; then one int32 all-reduce of the base coverage, one all-gather of the per-rank read-group
+   * tables (merged in rank order on every rank) and the sharded EM.  Per-allele outputs are identical on all ranks;
+   * fragment_assigned / n_unique_ends / n_overlaps / timings are this rank's.  NULL = single GPU. */
+  T1KComm *comm;
 } T1KGenotypeParams;
 
 typedef struct {
@@ -160,6 +172,30 @@ typedef struct {
 
 int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t stride, uint32_t n_frag,
                  const T1KGenotypeParams *params, T1KGenotypeResult *res /* caller-allocated arrays */);
+
+/* ---- multi-GPU plumbing.  The launcher (torchrun + torch.distributed, MPI, a shared file ...) moves the 128-byte
+ * unique id from rank 0 to the other ranks; everything on the data path is NCCL over NVLink. */
+#define T1K_UNIQUE_ID_BYTES 128
+int t1k_comm_unique_id(uint8_t *id /* [T1K_UNIQUE_ID_BYTES] */);
+int t1k_comm_create(const uint8_t *id, int32_t rank, int32_t world, int32_t device, T1KComm **out);
+void t1k_comm_destroy(T1KComm *comm);
+/* sums the base coverage of `ref` over the ranks (in place; every rank ends with the total) */
+int t1k_coverage_allreduce(T1KRef *ref, T1KComm *comm);
+
+/* ---- host-side model steps kept in the reference's order (no device needed).
+ * Genotyper::CoalesceReadAssignments (Genotyper.hpp:841-908): fragments with the same allele set merge into one
+ * read group, float32 weights accumulate in fragment order.  Rows may be in any allele order. */
+int t1k_groups_create(T1KGroups **out);
+void t1k_groups_destroy(T1KGroups *g);
+int t1k_groups_add_fragments(T1KGroups *g, const uint64_t *row_ptr, const T1KReadAssignment *entries, uint32_t n_frag);
+/* the table as one relocatable blob (free with t1k_free) and the merge of another rank's blob into `g` */
+int t1k_groups_serialize(const T1KGroups *g, void **blob, uint64_t *bytes);
+int t1k_groups_merge(T1KGroups *g, const void *blob, uint64_t bytes);
+/* n_groups / total entries / assigned fragments; then ptr[n_groups+1] and entries (caller-allocated, may be NULL) */
+int t1k_groups_fetch(const T1KGroups *g, int32_t *n_groups, uint64_t *n_entries, uint64_t *assigned_fragments,
+                     int64_t *ptr, T1KReadAssignment *entries);
+/* contiguous row ranges of the EM problem balanced by non-zeros: bounds[world+1] */
+int t1k_em_partition(const int64_t *row_ptr, int32_t n_groups, int32_t world, int32_t *bounds);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,11 @@ T1K_OK, T1K_ERR_NO_DEVICE, T1K_ERR_CUDA, T1K_ERR_ARG, T1K_ERR_UNSUPPORTED, T1K_E
 EXPORTS = ["t1k_last_error", "t1k_device_count", "t1k_ref_create", "t1k_ref_destroy", "t1k_ref_n_alleles",
            "t1k_assign_batch", "t1k_assignment_destroy", "t1k_assignment_fetch", "t1k_assignment_stats",
            "t1k_coverage_fetch", "t1k_coverage_reset", "t1k_missing_coverage", "t1k_pair_batch", "t1k_free",
-           "t1k_em_run", "t1k_genotype"]
+           "t1k_em_run", "t1k_genotype", "t1k_comm_unique_id", "t1k_comm_create", "t1k_comm_destroy",
+           "t1k_coverage_allreduce", "t1k_groups_create", "t1k_groups_destroy", "t1k_groups_add_fragments",
+           "t1k_groups_serialize", "t1k_groups_merge", "t1k_groups_fetch", "t1k_em_partition"]
+
+UNIQUE_ID_BYTES = 128
 
 
 class RefDesc(C.Structure):
@@ -37,7 +41,7 @@ class EmProblem(C.Structure):
                 ("count", C.c_void_p), ("ec_len", C.c_void_p), ("x0", C.c_void_p), ("min_squarem_alpha", C.c_double),
                 ("filter_frac", C.c_double), ("n_alleles", C.c_int32), ("n_major", C.c_int32), ("n_gene", C.c_int32),
                 ("ec_allele_ptr", C.c_void_p), ("ec_alleles", C.c_void_p), ("allele_major", C.c_void_p),
-                ("allele_gene", C.c_void_p), ("fast_sums", C.c_int32)]
+                ("allele_gene", C.c_void_p), ("fast_sums", C.c_int32), ("comm", C.c_void_p)]
 
 
 class EmResult(C.Structure):
@@ -48,7 +52,8 @@ class EmResult(C.Structure):
 class GenotypeParams(C.Structure):
     _fields_ = [("max_assign", C.c_int32), ("min_squarem_alpha", C.c_double), ("filter_frac", C.c_double),
                 ("seq_weight", C.c_void_p), ("effective_len", C.c_void_p), ("allele_major", C.c_void_p),
-                ("allele_gene", C.c_void_p), ("n_major", C.c_int32), ("n_gene", C.c_int32), ("em_fast_sums", C.c_int32)]
+                ("allele_gene", C.c_void_p), ("n_major", C.c_int32), ("n_gene", C.c_int32), ("em_fast_sums", C.c_int32),
+                ("comm", C.c_void_p)]
 
 
 class GenotypeResult(C.Structure):
@@ -104,6 +109,20 @@ def lib():
         L.t1k_em_run.argtypes = [C.POINTER(EmProblem), C.POINTER(EmResult), C.c_int32]
         L.t1k_genotype.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                    C.POINTER(GenotypeParams), C.POINTER(GenotypeResult)]
+        L.t1k_comm_unique_id.argtypes = [C.c_void_p]
+        L.t1k_comm_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.t1k_comm_destroy.argtypes = [C.c_void_p]
+        L.t1k_comm_destroy.restype = None
+        L.t1k_coverage_allreduce.argtypes = [C.c_void_p, C.c_void_p]
+        L.t1k_groups_create.argtypes = [C.POINTER(C.c_void_p)]
+        L.t1k_groups_destroy.argtypes = [C.c_void_p]
+        L.t1k_groups_destroy.restype = None
+        L.t1k_groups_add_fragments.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.t1k_groups_serialize.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.t1k_groups_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.t1k_groups_fetch.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                       C.c_void_p, C.c_void_p]
+        L.t1k_em_partition.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         _lib = L
     return _lib
 

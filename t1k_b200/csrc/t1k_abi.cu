@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/t1k_b200.h"
+#include "t1k_comm.hpp"
 #include "t1k_em.cuh"
 #include "t1k_host.hpp"
 #include "t1k_kernels.cuh"
@@ -33,6 +34,17 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
       snprintf(b_, sizeof(b_), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));   \
       g_err = b_;                                                                                    \
       return T1K_ERR_CUDA;                                                                           \
+    }                                                                                                \
+  } while (0)
+
+#define NK(call)                                                                                     \
+  do {                                                                                               \
+    int e_ = (call);                                                                                 \
+    if (e_ != NCCL_SUCCESS) {                                                                        \
+      char b_[512];                                                                                  \
+      snprintf(b_, sizeof(b_), "%s:%d %s: %s", __FILE__, __LINE__, #call, nccl().GetErrorString(e_)); \
+      g_err = b_;                                                                                    \
+      return T1K_ERR_NCCL;                                                                           \
     }                                                                                                \
   } while (0)
 
@@ -656,14 +668,27 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   const int G = p->n_groups, E = p->n_ec;
   const int64_t nnz = p->row_ptr[G];
   for (int64_t k = 0; k < nnz; ++k) if (p->col[k] < 0 || p->col[k] >= E) return fail(T1K_ERR_ARG, "t1k_em_run: column index out of range");
-  // CSC with ascending group order inside every column => fixed summation order
+  // read-sharded E-step: this rank's contiguous row range [g0, g1)
+  T1KComm *comm = (p->comm && p->comm->world > 1) ? p->comm : nullptr;
+  int g0 = 0, g1 = G;
+  if (comm) {
+    if (!nccl().load()) return fail(T1K_ERR_NCCL, nccl().error);
+    std::vector<int32_t> bounds((size_t)comm->world + 1);
+    partition_rows(p->row_ptr, G, comm->world, bounds.data());
+    g0 = bounds[comm->rank]; g1 = bounds[comm->rank + 1];
+  }
+  const int Gl = g1 - g0;
+  const int64_t k0 = p->row_ptr[g0], nnzL = p->row_ptr[g1] - k0;
+  std::vector<int64_t> rowPtrL((size_t)Gl + 1);
+  for (int g = 0; g <= Gl; ++g) rowPtrL[g] = p->row_ptr[g0 + g] - k0;
+  // CSC of the local rows with ascending group order inside every column => fixed summation order
   std::vector<int64_t> colPtr((size_t)E + 1, 0);
-  for (int64_t k = 0; k < nnz; ++k) ++colPtr[p->col[k] + 1];
+  for (int64_t k = 0; k < nnzL; ++k) ++colPtr[p->col[k0 + k] + 1];
   for (int e = 0; e < E; ++e) colPtr[e + 1] += colPtr[e];
-  std::vector<int32_t> rowIdx((size_t)std::max<int64_t>(nnz, 1));
+  std::vector<int32_t> rowIdx((size_t)std::max<int64_t>(nnzL, 1));
   {
     std::vector<int64_t> cur(colPtr.begin(), colPtr.end() - 1);
-    for (int g = 0; g < G; ++g) for (int64_t k = p->row_ptr[g]; k < p->row_ptr[g + 1]; ++k) rowIdx[cur[p->col[k]]++] = g;
+    for (int g = g0; g < g1; ++g) for (int64_t k = p->row_ptr[g]; k < p->row_ptr[g + 1]; ++k) rowIdx[cur[p->col[k]]++] = g;
   }
   cudaStream_t st;
   CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -671,34 +696,38 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   DevMem dRowPtr, dCol, dColPtr, dRowIdx, dCount, dLen, dPsum, dRc, dX0, dX1, dX2, dX3, dDiff, dTmpA, dTmpB;
   const bool fast = p->fast_sums != 0;
   CK(dTmpA.alloc((size_t)E * 8)); CK(dTmpB.alloc((size_t)E * 8));
-  CK(dRowPtr.alloc(((size_t)G + 1) * 8)); CK(dCol.alloc((size_t)nnz * 4)); CK(dColPtr.alloc(((size_t)E + 1) * 8)); CK(dRowIdx.alloc((size_t)nnz * 4));
+  CK(dRowPtr.alloc(((size_t)Gl + 1) * 8)); CK(dCol.alloc((size_t)nnzL * 4)); CK(dColPtr.alloc(((size_t)E + 1) * 8)); CK(dRowIdx.alloc((size_t)nnzL * 4));
   CK(dCount.alloc((size_t)G * 8)); CK(dLen.alloc((size_t)E * 4)); CK(dPsum.alloc((size_t)G * 8)); CK(dRc.alloc((size_t)E * 8));
   CK(dX0.alloc((size_t)E * 8)); CK(dX1.alloc((size_t)E * 8)); CK(dX2.alloc((size_t)E * 8)); CK(dX3.alloc((size_t)E * 8)); CK(dDiff.alloc(8));
-  CK(cudaMemcpyAsync(dRowPtr.p, p->row_ptr, ((size_t)G + 1) * 8, cudaMemcpyHostToDevice, st));
-  if (nnz) CK(cudaMemcpyAsync(dCol.p, p->col, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dRowPtr.p, rowPtrL.data(), ((size_t)Gl + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (nnzL) CK(cudaMemcpyAsync(dCol.p, p->col + k0, (size_t)nnzL * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dColPtr.p, colPtr.data(), ((size_t)E + 1) * 8, cudaMemcpyHostToDevice, st));
-  if (nnz) CK(cudaMemcpyAsync(dRowIdx.p, rowIdx.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+  if (nnzL) CK(cudaMemcpyAsync(dRowIdx.p, rowIdx.data(), (size_t)nnzL * 4, cudaMemcpyHostToDevice, st));
   if (G) CK(cudaMemcpyAsync(dCount.p, p->count, (size_t)G * 8, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dLen.p, p->ec_len, (size_t)E * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dX0.p, p->x0, (size_t)E * 8, cudaMemcpyHostToDevice, st));
-  const unsigned gRow = (unsigned)(((size_t)G * 32 + 255) / 256), gCol = (unsigned)(((size_t)E * 32 + 255) / 256);
+  const unsigned gRow = (unsigned)(((size_t)Gl * 32 + 255) / 256), gCol = (unsigned)(((size_t)E * 32 + 255) / 256);
   cudaEvent_t ev0, ev1;
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
   struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
   CK(cudaEventRecord(ev0, st));
   uint64_t launches = 0;
   auto em_update = [&](const double *xin, double *xout) -> int {   // Genotyper::EMupdate
+    double *psumL = dPsum.as<double>() + g0;    // psum / count stay indexed by the global group id
     if (fast) {
-      if (G) k_em_rowsum<<<gRow, 256, 0, st>>>(G, dRowPtr.as<int64_t>(), dCol.as<int32_t>(), xin, dPsum.as<double>());
+      if (Gl) k_em_rowsum<<<gRow, 256, 0, st>>>(Gl, dRowPtr.as<int64_t>(), dCol.as<int32_t>(), xin, psumL);
       k_em_colsum<<<gCol, 256, 0, st>>>(E, dColPtr.as<int64_t>(), dRowIdx.as<int32_t>(), dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
-      k_em_mstep<<<1, 1024, 0, st>>>(E, dRc.as<double>(), dLen.as<int32_t>(), xout);
     } else {
-      if (G) k_em_rowsum_seq<<<(G + 127) / 128, 128, 0, st>>>(G, dRowPtr.as<int64_t>(), dCol.as<int32_t>(), xin, dPsum.as<double>());
+      if (Gl) k_em_rowsum_seq<<<(Gl + 127) / 128, 128, 0, st>>>(Gl, dRowPtr.as<int64_t>(), dCol.as<int32_t>(), xin, psumL);
       k_em_colsum_seq<<<(E + 63) / 64, 64, 0, st>>>(E, dColPtr.as<int64_t>(), dRowIdx.as<int32_t>(), dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
-      k_em_mstep_seq<<<1, 1024, 0, st>>>(E, dRc.as<double>(), dLen.as<int32_t>(), dTmpA.as<double>(), xout);
     }
     CK(cudaGetLastError());
-    launches += G ? 3 : 2;
+    // the one exchange of the EM: per-EC expected read counts summed over the row shards (NVLink all-reduce)
+    if (comm) NK(nccl().AllReduce(dRc.p, dRc.p, (size_t)E, NCCL_FLOAT64, NCCL_SUM, comm->comm, st));
+    if (fast) k_em_mstep<<<1, 1024, 0, st>>>(E, dRc.as<double>(), dLen.as<int32_t>(), xout);
+    else k_em_mstep_seq<<<1, 1024, 0, st>>>(E, dRc.as<double>(), dLen.as<int32_t>(), dTmpA.as<double>(), xout);
+    CK(cudaGetLastError());
+    launches += Gl ? 3 : 2;
     return T1K_OK;
   };
   const int maxIter = 1000;
@@ -737,6 +766,146 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   r->iterations = ret;
   return T1K_OK;
 }
+
+struct T1KGroups { ReadGroups G; };
+
+int t1k_comm_unique_id(uint8_t *id) {
+  if (!id) return fail(T1K_ERR_ARG, "t1k_comm_unique_id: bad argument");
+  if (!nccl().load()) return fail(T1K_ERR_NCCL, nccl().error);
+  ncclUniqueId u;
+  NK(nccl().GetUniqueId(&u));
+  static_assert(sizeof(u) == T1K_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  memcpy(id, &u, sizeof(u));
+  return T1K_OK;
+}
+
+int t1k_comm_create(const uint8_t *id, int32_t rank, int32_t world, int32_t device, T1KComm **out) {
+  if (!id || !out || world < 1 || rank < 0 || rank >= world) return fail(T1K_ERR_ARG, "t1k_comm_create: bad argument");
+  *out = nullptr;
+  int dev;
+  if (int rc = pick_device(device, &dev)) return rc;
+  if (!nccl().load()) return fail(T1K_ERR_NCCL, nccl().error);
+  CK(cudaSetDevice(dev));
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof(u));
+  T1KComm *c = new T1KComm;
+  c->rank = rank; c->world = world; c->device = dev;
+  int e = nccl().CommInitRank(&c->comm, world, u, rank);
+  if (e != NCCL_SUCCESS) { delete c; return fail(T1K_ERR_NCCL, std::string("ncclCommInitRank: ") + nccl().GetErrorString(e)); }
+  *out = c;
+  return T1K_OK;
+}
+
+void t1k_comm_destroy(T1KComm *c) {
+  if (!c) return;
+  if (c->comm) { cudaSetDevice(c->device); nccl().CommDestroy(c->comm); }
+  delete c;
+}
+
+int t1k_coverage_allreduce(T1KRef *ref, T1KComm *comm) {
+  if (!ref || !comm) return fail(T1K_ERR_ARG, "t1k_coverage_allreduce: bad argument");
+  if (comm->world == 1) return T1K_OK;
+  CK(cudaSetDevice(ref->device));
+  // coverage = prefix(covDiff) + covPoint is linear in both arrays: sum them where they lie
+  NK(nccl().AllReduce(ref->covDiff.p, ref->covDiff.p, ref->paddedBases, NCCL_INT32, NCCL_SUM, comm->comm, ref->stream));
+  NK(nccl().AllReduce(ref->covPoint.p, ref->covPoint.p, ref->paddedBases, NCCL_INT32, NCCL_SUM, comm->comm, ref->stream));
+  CK(cudaStreamSynchronize(ref->stream));
+  ref->covDirty = true;
+  return T1K_OK;
+}
+
+int t1k_groups_create(T1KGroups **out) {
+  if (!out) return fail(T1K_ERR_ARG, "t1k_groups_create: bad argument");
+  *out = new T1KGroups;
+  return T1K_OK;
+}
+
+void t1k_groups_destroy(T1KGroups *g) { delete g; }
+
+int t1k_groups_add_fragments(T1KGroups *g, const uint64_t *row_ptr, const T1KReadAssignment *entries, uint32_t n_frag) {
+  if (!g || (n_frag > 0 && (!row_ptr || !entries))) return fail(T1K_ERR_ARG, "t1k_groups_add_fragments: bad argument");
+  std::vector<HostEntry> row;
+  for (uint32_t f = 0; f < n_frag; ++f) {
+    const uint64_t b = row_ptr[f], e = row_ptr[f + 1];
+    if (e <= b) continue;
+    row.resize(e - b);
+    memcpy(row.data(), entries + b, (e - b) * sizeof(HostEntry));
+    // Genotyper.hpp:851: the fragment's assignments are sorted by allele before they are compared
+    std::stable_sort(row.begin(), row.end(), [](const HostEntry &x, const HostEntry &y) { return x.alleleIdx < y.alleleIdx; });
+    g->G.add(row.data(), (uint32_t)(e - b));
+  }
+  return T1K_OK;
+}
+
+int t1k_groups_serialize(const T1KGroups *g, void **blob, uint64_t *bytes) {
+  if (!g || !blob || !bytes) return fail(T1K_ERR_ARG, "t1k_groups_serialize: bad argument");
+  std::vector<uint8_t> b;
+  serialize_groups(g->G, b);
+  void *p = malloc(b.size());
+  if (!p) return fail(T1K_ERR_ARG, "out of host memory");
+  memcpy(p, b.data(), b.size());
+  *blob = p; *bytes = b.size();
+  return T1K_OK;
+}
+
+int t1k_groups_merge(T1KGroups *g, const void *blob, uint64_t bytes) {
+  if (!g || !blob) return fail(T1K_ERR_ARG, "t1k_groups_merge: bad argument");
+  if (!merge_groups(g->G, (const uint8_t *)blob, bytes)) return fail(T1K_ERR_ARG, "t1k_groups_merge: malformed group table");
+  return T1K_OK;
+}
+
+int t1k_groups_fetch(const T1KGroups *g, int32_t *n_groups, uint64_t *n_entries, uint64_t *assigned_fragments, int64_t *ptr,
+                     T1KReadAssignment *entries) {
+  if (!g) return fail(T1K_ERR_ARG, "t1k_groups_fetch: bad argument");
+  if (n_groups) *n_groups = g->G.size();
+  if (n_entries) *n_entries = g->G.ent.size();
+  if (assigned_fragments) *assigned_fragments = (uint64_t)g->G.assignedFragments;
+  if (ptr) memcpy(ptr, g->G.ptr.data(), g->G.ptr.size() * 8);
+  if (entries && !g->G.ent.empty()) memcpy(entries, g->G.ent.data(), g->G.ent.size() * sizeof(HostEntry));
+  return T1K_OK;
+}
+
+int t1k_em_partition(const int64_t *row_ptr, int32_t n_groups, int32_t world, int32_t *bounds) {
+  if (!row_ptr || !bounds || n_groups < 0 || world < 1) return fail(T1K_ERR_ARG, "t1k_em_partition: bad argument");
+  partition_rows(row_ptr, n_groups, world, bounds);
+  return T1K_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// all-gather of one host blob per rank through device staging (padded to the largest); out[r] = rank r's blob
+int allgather_blobs(T1KRef *ref, T1KComm *comm, const std::vector<uint8_t> &mine, std::vector<std::vector<uint8_t> > &out) {
+  cudaStream_t st = ref->stream;
+  const int W = comm->world;
+  DevMem dSizes, dBuf;
+  CK(dSizes.alloc((size_t)W * 8));
+  const uint64_t myBytes = mine.size();
+  CK(cudaMemcpyAsync(dSizes.as<uint64_t>() + comm->rank, &myBytes, 8, cudaMemcpyHostToDevice, st));
+  NK(nccl().AllGather(dSizes.as<uint64_t>() + comm->rank, dSizes.p, 1, NCCL_UINT64, comm->comm, st));
+  std::vector<uint64_t> sizes(W);
+  CK(cudaMemcpyAsync(sizes.data(), dSizes.p, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  uint64_t mx = 16;
+  for (int r = 0; r < W; ++r) mx = std::max(mx, sizes[r]);
+  mx = (mx + 15) & ~15ull;
+  CK(dBuf.alloc((size_t)W * mx));
+  uint8_t *slot = dBuf.as<uint8_t>() + (size_t)comm->rank * mx;
+  if (myBytes) CK(cudaMemcpyAsync(slot, mine.data(), myBytes, cudaMemcpyHostToDevice, st));
+  NK(nccl().AllGather(slot, dBuf.p, mx, NCCL_UINT8, comm->comm, st));
+  out.resize(W);
+  for (int r = 0; r < W; ++r) {
+    out[r].resize(sizes[r]);
+    if (sizes[r]) CK(cudaMemcpyAsync(out[r].data(), dBuf.as<uint8_t>() + (size_t)r * mx, sizes[r], cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return T1K_OK;
+}
+
+}  // namespace
+
+extern "C" {
 
 // Genotyper.cpp:450-646 for one sample.
 int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t stride, uint32_t n_frag,
@@ -830,8 +999,31 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     res->n_assignments += H.entries.size();
     res->ms_coalesce += (float)(now_ms() - tc);
   }
+  // ---- read-sharded run: total coverage, every rank's read groups merged in rank order
+  T1KComm *comm = (prm->comm && prm->comm->world > 1) ? prm->comm : nullptr;
+  uint64_t nAssignAll = res->n_assignments;
+  if (comm) {
+    double tx = now_ms();
+    if (int rc = t1k_coverage_allreduce(ref, comm)) return rc;
+    std::vector<uint8_t> mine;
+    serialize_groups(groups, mine);
+    mine.resize(mine.size() + 8);
+    memcpy(mine.data() + mine.size() - 8, &nAssignAll, 8);      // trailer: this rank's assignment count
+    std::vector<std::vector<uint8_t> > all;
+    if (int rc = allgather_blobs(ref, comm, mine, all)) return rc;
+    ReadGroups merged;
+    nAssignAll = 0;
+    for (int r = 0; r < comm->world; ++r) {
+      if (all[r].size() < 8 || !merge_groups(merged, all[r].data(), all[r].size() - 8)) return fail(T1K_ERR_NCCL, "malformed read-group table from a peer");
+      uint64_t na; memcpy(&na, all[r].data() + all[r].size() - 8, 8);
+      nAssignAll += na;
+    }
+    groups.ptr.swap(merged.ptr); groups.ent.swap(merged.ent); groups.byHash.swap(merged.byHash);
+    groups.assignedFragments = merged.assignedFragments;
+    res->ms_coalesce += (float)(now_ms() - tx);
+  }
   res->assigned_fragments = (int32_t)groups.assignedFragments;
-  res->avg_alleles_per_read = groups.assignedFragments ? (double)res->n_assignments / (double)groups.assignedFragments : 0.0;
+  res->avg_alleles_per_read = groups.assignedFragments ? (double)nAssignAll / (double)groups.assignedFragments : 0.0;
   // ---- FinalizeReadAssignments: equivalence classes + missing coverage
   double tc = now_ms();
   EquivalenceClasses EC;
@@ -853,6 +1045,7 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     ep.n_groups = groups.size(); ep.n_ec = EC.size();
     ep.row_ptr = in.rowPtr.data(); ep.col = in.col.data(); ep.count = in.count.data(); ep.ec_len = in.ecLen.data(); ep.x0 = in.x0.data();
     ep.min_squarem_alpha = prm->min_squarem_alpha; ep.filter_frac = prm->filter_frac; ep.fast_sums = prm->em_fast_sums;
+    ep.comm = comm;
     if (prm->allele_major && prm->allele_gene) {
       ep.n_alleles = nA; ep.n_major = prm->n_major; ep.n_gene = prm->n_gene;
       ep.ec_allele_ptr = EC.ecPtr.data(); ep.ec_alleles = EC.ecAlleles.data();

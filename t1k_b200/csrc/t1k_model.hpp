@@ -36,10 +36,11 @@ struct ReadGroups {
     return h;
   }
 
-  // row must be sorted by alleleIdx (the pairing kernel emits it that way)
-  void add(const HostEntry *row, uint32_t n) {
+  // row must be sorted by alleleIdx (the pairing kernel emits it that way).  `fragments` = how many fragments the
+  // row stands for: 1 for a fragment, the group's own count when another rank's table is merged in.
+  void add(const HostEntry *row, uint32_t n, int64_t fragments = 1) {
     if (n == 0) return;
-    ++assignedFragments;
+    assignedFragments += fragments;
     const uint64_t h = hash_row(row, n);
     std::vector<int32_t> &cand = byHash[h];
     for (size_t c = 0; c < cand.size(); ++c) {
@@ -64,6 +65,52 @@ struct ReadGroups {
     ptr.push_back((int64_t)ent.size());
   }
 };
+
+// Relocatable image of a group table: [nGroups, nEntries, assignedFragments] then ptr[nGroups+1] then entries.
+inline void serialize_groups(const ReadGroups &G, std::vector<uint8_t> &blob) {
+  const uint64_t hdr[3] = {(uint64_t)G.size(), (uint64_t)G.ent.size(), (uint64_t)G.assignedFragments};
+  blob.resize(sizeof(hdr) + G.ptr.size() * 8 + G.ent.size() * sizeof(HostEntry));
+  uint8_t *p = blob.data();
+  memcpy(p, hdr, sizeof(hdr)); p += sizeof(hdr);
+  memcpy(p, G.ptr.data(), G.ptr.size() * 8); p += G.ptr.size() * 8;
+  if (!G.ent.empty()) memcpy(p, G.ent.data(), G.ent.size() * sizeof(HostEntry));
+}
+
+// Merge of another rank's table (read-sharded path): its groups are added in their own order, so merging the ranks'
+// tables in rank order visits the allele sets in the order a single process would first see them shard by shard.
+// float32 weights of equal allele sets add as (sum of rank 0) + (sum of rank 1) + ...
+inline bool merge_groups(ReadGroups &G, const uint8_t *blob, uint64_t bytes) {
+  uint64_t hdr[3];
+  if (bytes < sizeof(hdr)) return false;
+  memcpy(hdr, blob, sizeof(hdr));
+  const uint64_t nG = hdr[0], nE = hdr[1];
+  if (bytes < sizeof(hdr) + (nG + 1) * 8 + nE * sizeof(HostEntry)) return false;
+  const uint8_t *pp = blob + sizeof(hdr), *pe = pp + (nG + 1) * 8;
+  std::vector<HostEntry> row;
+  for (uint64_t g = 0; g < nG; ++g) {
+    int64_t b, e;
+    memcpy(&b, pp + g * 8, 8); memcpy(&e, pp + (g + 1) * 8, 8);
+    if (b < 0 || e < b || (uint64_t)e > nE) return false;
+    row.resize((size_t)(e - b));
+    if (e > b) memcpy(row.data(), pe + (size_t)b * sizeof(HostEntry), (size_t)(e - b) * sizeof(HostEntry));
+    G.add(row.data(), (uint32_t)(e - b), 0);
+  }
+  G.assignedFragments += (int64_t)hdr[2];
+  return true;
+}
+
+// contiguous row ranges balanced by non-zeros (rank r takes rows [bounds[r], bounds[r+1]))
+inline void partition_rows(const int64_t *rowPtr, int32_t nGroups, int32_t world, int32_t *bounds) {
+  const int64_t nnz = rowPtr[nGroups];
+  bounds[0] = 0;
+  int32_t g = 0;
+  for (int32_t r = 1; r < world; ++r) {
+    const int64_t target = nnz * r / world;
+    while (g < nGroups && rowPtr[g] < target) ++g;
+    bounds[r] = g;
+  }
+  bounds[world] = nGroups;
+}
 
 // Genotyper::FinalizeReadAssignments + BuildAlleleEquivalentClass (Genotyper.hpp:912-939, 1072-1139).
 // RemoveLowMAPQAlleleInEquivalentClass (:1330-1368) keeps the members whose summed qual is maximal; every

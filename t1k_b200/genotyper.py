@@ -137,8 +137,9 @@ class SeqSet:
 
 def QuantifyAlleleEquivalentClass(row_ptr, col, count, ec_len, x0, min_squarem_alpha=0.0, filter_frac=0.15,
                                   ec_allele_ptr=None, ec_alleles=None, allele_major=None, allele_gene=None, device=-1,
-                                  fast_sums=False):
-    """The EM loop of Genotyper::QuantifyAlleleEquivalentClass on the device -> (iterations, x, ecReadCount)."""
+                                  fast_sums=False, comm=None):
+    """The EM loop of Genotyper::QuantifyAlleleEquivalentClass on the device -> (iterations, x, ecReadCount).
+    comm: a dist_em.Comm — every rank passes the same problem and runs the E-step over its own row range."""
     row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
     col = np.ascontiguousarray(col, dtype=np.int32)
     count = np.ascontiguousarray(count, dtype=np.float64)
@@ -149,6 +150,7 @@ def QuantifyAlleleEquivalentClass(row_ptr, col, count, ec_len, x0, min_squarem_a
     p.row_ptr, p.col, p.count, p.ec_len, p.x0 = L.ptr(row_ptr), L.ptr(col), L.ptr(count), L.ptr(ec_len), L.ptr(x0)
     p.min_squarem_alpha, p.filter_frac = float(min_squarem_alpha), float(filter_frac)
     p.fast_sums = int(bool(fast_sums))
+    p.comm = comm.h if comm is not None else None
     keep = []
     if allele_major is not None:
         am = np.ascontiguousarray(allele_major, dtype=np.int32)
@@ -178,15 +180,17 @@ class Genotyper:
         self.filter_frac = filter_frac
         self.min_squarem_alpha = min_squarem_alpha
 
-    def Genotype(self, reads1, reads2=None):
-        """reads: uint8 arrays [n, stride] (NUL padded for shorter reads).  Returns a dict of per-allele results."""
+    def Genotype(self, reads1, reads2=None, comm=None):
+        """reads: uint8 arrays [n, stride] (NUL padded for shorter reads).  Returns a dict of per-allele results.
+        comm: a dist_em.Comm — reads are THIS rank's shard; per-allele results are the whole job's on every rank."""
         r1 = np.ascontiguousarray(reads1, dtype=np.uint8)
         r2 = None if reads2 is None else np.ascontiguousarray(reads2, dtype=np.uint8)
         n, stride = r1.shape
         ref = self.ref
         prm = L.GenotypeParams(self.max_assign, self.min_squarem_alpha, self.filter_frac, L.ptr(ref.seq_weight),
                                L.ptr(ref.effective_len), L.ptr(ref.allele_major), L.ptr(ref.allele_gene),
-                               len(ref.major_names), len(ref.gene_names), int(bool(self.em_fast_sums)))
+                               len(ref.major_names), len(ref.gene_names), int(bool(self.em_fast_sums)),
+                               comm.h if comm is not None else None)
         out = dict(abundance=np.zeros(ref.n), ec_abundance=np.zeros(ref.n),
                    equivalent_class=np.zeros(ref.n, dtype=np.int32), missing_coverage=np.zeros(ref.n, dtype=np.int32),
                    fragment_assigned=np.zeros(n, dtype=np.uint8))

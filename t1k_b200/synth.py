@@ -129,12 +129,14 @@ def revcomp(a: np.ndarray) -> np.ndarray:
 
 
 def simulate_pairs(records, n_pairs, read_len=150, insert=(300, 450), err=0.002, n_rate=0.0,
-                   alleles_per_gene=2, seed=1, gene_of=None, single_end=False, indel_rate=0.0):
+                   alleles_per_gene=2, seed=1, gene_of=None, single_end=False, indel_rate=0.0, src_seed=None):
     """Draw n_pairs FR fragments uniformly from `alleles_per_gene` alleles of every gene.
     Returns (reads1, reads2) as uint8 arrays [n, read_len] (reads2 None if single_end),
     plus the list of source allele indices.  Substitution errors at rate `err`, 'N' at
-    `n_rate`, single-base indels (read-level) at `indel_rate` per read."""
+    `n_rate`, single-base indels (read-level) at `indel_rate` per read.  `src_seed` draws the source alleles from
+    their own stream, so that shards of one sample (different `seed`) come from the same alleles."""
     rng = np.random.default_rng(seed)
+    src_rng = rng if src_seed is None else np.random.default_rng(src_seed)
     if gene_of is None:
         gene_of = [r[0].split("*")[0] for r in records]
     genes = {}
@@ -144,7 +146,7 @@ def simulate_pairs(records, n_pairs, read_len=150, insert=(300, 450), err=0.002,
     for g in sorted(genes):
         idx = genes[g]
         k = min(alleles_per_gene, len(idx))
-        src.extend(int(x) for x in rng.choice(idx, size=k, replace=False))
+        src.extend(int(x) for x in src_rng.choice(idx, size=k, replace=False))
     seqs = [np.frombuffer(records[i][2], dtype=np.uint8) for i in src]
     which = rng.integers(0, len(src), size=n_pairs)
     ins = rng.integers(insert[0], insert[1] + 1, size=n_pairs)
