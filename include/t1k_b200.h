@@ -99,7 +99,8 @@ int t1k_missing_coverage(T1KRef *ref, int32_t *out /* [n_alleles] */);
  * reference's order. */
 int t1k_pair_batch(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const uint32_t *end2,
                    const uint8_t *has_n, uint32_t n_frag, int32_t max_assign,
-                   uint64_t **row_ptr, T1KReadAssignment **entries);
+                   uint64_t **row_ptr, T1KReadAssignment **entries,
+                   uint8_t *fragment_assigned /* [n_frag] or NULL: fragmentAssignment.size() > 0, Genotyper.cpp:564 */);
 void t1k_free(void *p);
 
 /* Genotyper::QuantifyAlleleEquivalentClass main loop (Genotyper.hpp:1234-1316) on the device.
@@ -163,7 +164,7 @@ typedef struct {
   uint8_t *fragment_assigned;         /* [n_frag] */
   int32_t em_iterations, n_groups, n_ec, assigned_fragments;
   uint64_t n_unique_ends, n_overlaps, n_assignments;
-  double avg_alleles_per_read;
+  double avg_alleles_per_read;        /* Genotyper::GetAverageReadAssignmentCnt: over read groups */
   float ms_dedup, ms_align, ms_pair, ms_coalesce, ms_em;   /* wall time of the phases of this call (host clock) */
   float ms_align_kernel, ms_pair_kernel, ms_em_kernel;      /* device time (CUDA events) inside k_assign / k_pair / the EM kernels */
   uint64_t n_postings, n_candidates;                        /* k-mer postings read and seed overlaps chained (roofline accounting) */

@@ -103,7 +103,7 @@ def lib():
         L.t1k_coverage_reset.argtypes = [C.c_void_p]
         L.t1k_missing_coverage.argtypes = [C.c_void_p, C.c_void_p]
         L.t1k_pair_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32,
-                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
         L.t1k_free.argtypes = [C.c_void_p]
         L.t1k_free.restype = None
         L.t1k_em_run.argtypes = [C.POINTER(EmProblem), C.POINTER(EmResult), C.c_int32]

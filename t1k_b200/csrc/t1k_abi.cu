@@ -533,6 +533,7 @@ struct PairHost {
   std::vector<u64> rowPtr;            // [nFrag + 1]
   std::vector<HostEntry> entries;
   std::vector<u64> ordKey; std::vector<u32> ordIdx;
+  std::vector<u8> assigned;           // [nFrag] fragmentAssignment.size() > 0 (before the SetReadAssignments cuts)
   float msKernel = 0;
   u32 launches = 1;
 };
@@ -541,6 +542,7 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
                    int maxAssign, bool wantOrder, PairHost &H) {
   cudaStream_t st = ref->stream;
   H.rowPtr.assign((size_t)nFrag + 1, 0);
+  H.assigned.assign(nFrag, 0);
   H.entries.clear(); H.ordKey.clear(); H.ordIdx.clear();
   if (nFrag == 0) return T1K_OK;
   for (uint32_t i = 0; i < nFrag; ++i)
@@ -598,7 +600,11 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
     float ms = 0; CK(cudaEventElapsedTime(&ms, ev0, ev1)); H.msKernel += ms; H.launches += 2;
     dstOff.resize(m);
     u64 dense = 0;
-    for (u32 i = 0; i < m; ++i) { dstOff[i] = dense; dense += rowCnt[i]; H.rowPtr[(size_t)f0 + i + 1] = rowCnt[i]; }
+    for (u32 i = 0; i < m; ++i) {
+      const u32 c = rowCnt[i] & 0x7fffffffu;
+      H.assigned[(size_t)f0 + i] = (u8)(rowCnt[i] >> 31);
+      dstOff[i] = dense; dense += c; H.rowPtr[(size_t)f0 + i + 1] = c;
+    }
     if (dense > 0) {
       if (dense > allocDense) {
         allocDense = dense;
@@ -633,7 +639,8 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
 extern "C" {
 
 int t1k_pair_batch(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const uint32_t *end2, const uint8_t *has_n,
-                   uint32_t n_frag, int32_t max_assign, uint64_t **row_ptr, T1KReadAssignment **entries) {
+                   uint32_t n_frag, int32_t max_assign, uint64_t **row_ptr, T1KReadAssignment **entries,
+                   uint8_t *fragment_assigned) {
   if (!ref || !a || !row_ptr || !entries || (n_frag > 0 && !end1)) return fail(T1K_ERR_ARG, "t1k_pair_batch: bad argument");
   static_assert(sizeof(T1KReadAssignment) == sizeof(HostEntry) && sizeof(HostEntry) == sizeof(PairEntry), "layout");
   CK(cudaSetDevice(ref->device));
@@ -653,6 +660,7 @@ int t1k_pair_batch(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
     std::sort(idx.begin(), idx.end(), [k, ki](u32 x, u32 y) { return k[x] != k[y] ? k[x] < k[y] : ki[x] < ki[y]; });
     for (u64 j = 0; j < e - b; ++j) memcpy(&en[b + j], &H.entries[b + idx[j]], sizeof(HostEntry));
   }
+  if (fragment_assigned && n_frag) memcpy(fragment_assigned, H.assigned.data(), n_frag);
   *row_ptr = rp; *entries = en;
   return T1K_OK;
 }
@@ -991,10 +999,8 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     double tc = now_ms();
     for (u32 i = 0; i < m; ++i) {
       const u64 b = H.rowPtr[i], e = H.rowPtr[i + 1];
-      if (e > b) {
-        groups.add(H.entries.data() + b, (uint32_t)(e - b));
-        if (res->fragment_assigned) res->fragment_assigned[f0 + i] = 1;
-      }
+      if (e > b) groups.add(H.entries.data() + b, (uint32_t)(e - b));
+      if (res->fragment_assigned) res->fragment_assigned[f0 + i] = H.assigned[i];
     }
     res->n_assignments += H.entries.size();
     res->ms_coalesce += (float)(now_ms() - tc);
@@ -1023,7 +1029,9 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     res->ms_coalesce += (float)(now_ms() - tx);
   }
   res->assigned_fragments = (int32_t)groups.assignedFragments;
-  res->avg_alleles_per_read = groups.assignedFragments ? (double)nAssignAll / (double)groups.assignedFragments : 0.0;
+  // Genotyper::GetAverageReadAssignmentCnt (Genotyper.hpp:941-955) averages over the coalesced read groups
+  res->avg_alleles_per_read = groups.size() ? (double)groups.ent.size() / (double)groups.size() : 0.0;
+  res->n_assignments = nAssignAll;
   // ---- FinalizeReadAssignments: equivalence classes + missing coverage
   double tc = now_ms();
   EquivalenceClasses EC;

@@ -30,7 +30,8 @@ struct PairParams {
   PairEntry *out;
   u64 *ordKey;              // optional: list position of the allele's first candidate (reference order)
   u32 *ordIdx;
-  u32 *rowCnt;              // per fragment of this launch
+  u32 *rowCnt;              // per fragment of this launch; bit 31 = the fragment had assignments before the
+                            // SetReadAssignments cuts (Genotyper.cpp:564 `fragmentAssigned`)
   u64 *rowHash;             // optional, 2 per fragment: order-free hash of the allele set
   unsigned int *workCtr;
 };
@@ -203,6 +204,7 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
   if (pe && n1 == 0) { A = L2; nA = n2; }
   const Rec *B = paired ? L2 : NULL; const int nB = paired ? n2 : 0;
   u32 cnt = 0;
+  bool assigned = false;
   u64 h0 = 0, h1 = 0;
   if (nA > 0) {
     // pass 1: best (matchCnt, similarity) over the alleles (SeqSet.hpp:2477-2487)
@@ -298,6 +300,7 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
         }
         drop = __any_sync(FULL, filter);
       }
+      assigned = !drop;
       // SetReadAssignments (Genotyper.hpp:778-832)
       if (!drop && P.maxAssign > 0 && nKeep > P.maxAssign) drop = true;
       if (!drop && anySep) drop = true;
@@ -347,7 +350,7 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
     for (int o = 16; o; o >>= 1) { h0 += __shfl_xor_sync(FULL, h0, o); h1 += __shfl_xor_sync(FULL, h1, o); }
   }
   if (lane == 0) {
-    P.rowCnt[fLocal] = cnt;
+    P.rowCnt[fLocal] = cnt | (assigned ? 0x80000000u : 0u);
     if (P.rowHash) { P.rowHash[2 * (size_t)fLocal] = h0 ^ ((u64)cnt << 40); P.rowHash[2 * (size_t)fLocal + 1] = h1; }
   }
 }
@@ -383,7 +386,7 @@ __global__ void k_pair_compact(const PairEntry *src, const u64 *srcOff, const u6
   const int lane = threadIdx.x & 31;
   if (w >= nFrag) return;
   const u64 s = srcOff[w], d = dstOff[w];
-  const u32 n = rowCnt[w];
+  const u32 n = rowCnt[w] & 0x7fffffffu;
   for (u32 k = lane; k < n; k += 32) {
     dst[d + k] = src[s + k];
     if (ordKeyDst) { ordKeyDst[d + k] = ordKeySrc[s + k]; ordIdxDst[d + k] = ordIdxSrc[s + k]; }

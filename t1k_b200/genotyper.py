@@ -101,14 +101,17 @@ class SeqSet:
         L.check(L.lib().t1k_assign_batch(self.h, L.ptr(bases), L.ptr(off), L.ptr(lens), L.ptr(w), n, C.byref(h)))
         return Assignment(h, n)
 
-    def ReadAssignmentToFragmentAssignment(self, assignment: Assignment, end1, end2=None, has_n=None, max_assign=2000):
-        """Fragment pairing + Genotyper::SetReadAssignments -> (row_ptr[n_frag+1], entries) in the reference's order."""
+    def ReadAssignmentToFragmentAssignment(self, assignment: Assignment, end1, end2=None, has_n=None, max_assign=2000,
+                                           with_assigned=False):
+        """Fragment pairing + Genotyper::SetReadAssignments -> (row_ptr[n_frag+1], entries) in the reference's order
+        (+ the `fragmentAssigned` flags of Genotyper.cpp:564 when with_assigned)."""
         e1 = np.ascontiguousarray(end1, dtype=np.uint32)
         e2 = None if end2 is None else np.ascontiguousarray(end2, dtype=np.uint32)
         hn = None if has_n is None else np.ascontiguousarray(has_n, dtype=np.uint8)
         rp, en = C.c_void_p(), C.c_void_p()
+        fa = np.zeros(len(e1), dtype=np.uint8)
         L.check(L.lib().t1k_pair_batch(self.h, assignment.h, L.ptr(e1), L.ptr(e2), L.ptr(hn), len(e1), int(max_assign),
-                                       C.byref(rp), C.byref(en)))
+                                       C.byref(rp), C.byref(en), L.ptr(fa)))
         try:
             row = np.ctypeslib.as_array(C.cast(rp, C.POINTER(C.c_uint64)), shape=(len(e1) + 1,)).copy()
             tot = int(row[-1])
@@ -118,7 +121,7 @@ class SeqSet:
         finally:
             L.lib().t1k_free(rp)
             L.lib().t1k_free(en)
-        return row, ent
+        return (row, ent, fa) if with_assigned else (row, ent)
 
     def GetBaseCoverage(self):
         """posWeight[].count[consensus base] of every allele, concatenated (Q11)."""

@@ -9,7 +9,7 @@ import sys
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers",
         "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps", "launch__grid_size", "launch__block_size",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed_pipe_lsu.sum", "smsp__inst_executed_pipe_alu.sum"]
@@ -30,13 +30,13 @@ def main():
                         break
             stalls = []
             for hk in h:
-                if "warp_issue_stalled" in hk and hk.endswith("_per_warp_active.pct") and "not_issued" not in hk:
+                if "average_warps_issue_stalled_" in hk and hk.endswith("_per_issue_active.ratio"):
                     try:
-                        stalls.append((float(d[hk].replace(",", "")), hk.split("warp_issue_stalled_")[1].replace("_per_warp_active.pct", "")))
+                        stalls.append((float(d[hk].replace(",", "")), hk.split("issue_stalled_")[1].replace("_per_issue_active.ratio", "")))
                     except ValueError:
                         pass
             stalls.sort(reverse=True)
-            print("   stalls (% of active warps): " + ", ".join("%s %.1f" % (n, v) for v, n in stalls[:8]))
+            print("   stalls (warps stalled per issue-active cycle): " + ", ".join("%s %.2f" % (n, v) for v, n in stalls[:8]))
 
 
 if __name__ == "__main__":
