@@ -104,7 +104,7 @@ struct T1KRef {
   std::vector<u64> wordOff;
   std::vector<int32_t> len;
   size_t paddedBases = 0;
-  DevMem seq2, n2, ex2, dWordOff, dLen, kstart, post, covDiff, covPoint, covFinal;
+  DevMem seq2, n2, ex2, dWordOff, dLen, dHasN, kstart, post, covDiff, covPoint, covFinal;
   RefView R;
   cudaStream_t stream = nullptr;
   // launch state of k_assign, sized on first use
@@ -169,7 +169,7 @@ int t1k_ref_create(const T1KRefDesc *d, T1KRef **out) {
     if (e == cudaSuccess) e = cudaMemcpy(r->dst.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice); \
     if (e != cudaSuccess) { delete r; return fail(T1K_ERR_CUDA, std::string("t1k_ref_create upload: ") + cudaGetErrorString(e)); } \
   } while (0)
-  UP(seq2, P.seq2); UP(n2, P.n2); UP(ex2, P.ex2); UP(dWordOff, P.wordOff); UP(dLen, P.len); UP(kstart, P.kstart);
+  UP(seq2, P.seq2); UP(n2, P.n2); UP(ex2, P.ex2); UP(dWordOff, P.wordOff); UP(dLen, P.len); UP(dHasN, P.hasN); UP(kstart, P.kstart);
   if (P.post.empty()) P.post.resize(1);
   UP(post, P.post);
 #undef UP
@@ -183,7 +183,7 @@ int t1k_ref_create(const T1KRefDesc *d, T1KRef **out) {
   if (e != cudaSuccess) { delete r; return fail(T1K_ERR_CUDA, std::string("t1k_ref_create: ") + cudaGetErrorString(e)); }
   RefView &R = r->R;
   R.seq2 = r->seq2.as<u64>(); R.n2 = r->n2.as<u64>(); R.ex2 = r->ex2.as<u64>();
-  R.wordOff = r->dWordOff.as<u64>(); R.len = r->dLen.as<int32_t>();
+  R.wordOff = r->dWordOff.as<u64>(); R.len = r->dLen.as<int32_t>(); R.hasN = r->dHasN.as<u8>();
   R.kstart = r->kstart.as<u32>(); R.post = r->post.as<Posting>();
   R.covDiff = r->covDiff.as<int32_t>(); R.covPoint = r->covPoint.as<int32_t>();
   R.nAlleles = d->n_alleles; R.sim = d->similarity; R.relax = d->relax_intron;

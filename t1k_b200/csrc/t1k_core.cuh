@@ -54,6 +54,7 @@ struct RefView {
   const u64 *seq2, *n2, *ex2;
   const u64 *wordOff;    // [nAlleles] first word of allele
   const int32_t *len;    // [nAlleles]
+  const u8 *hasN;        // [nAlleles] the allele holds at least one N (separator)
   const u32 *kstart;     // [4^K + 1]
   const Posting *post;
   int32_t *covDiff;      // range-add difference array, indexed by padded base (wordOff*32 + pos)
@@ -66,6 +67,16 @@ struct RefView {
 struct ReadView {        // one strand of one read-end
   const u64 *seq2, *n2;  // RWORDS words each
   int len;
+  bool anyN;             // the read holds at least one N
+};
+
+// one allele as the lane code sees it: plane pointers at the allele's first word.  Most alleles (every RNA allele)
+// and most reads hold no N, and then the two N-plane fetches of every 32-column comparison are skipped.
+struct AlleleView {
+  const u64 *seq, *n2, *ex2;
+  int len;
+  bool hasN;             // allele holds an N
+  bool useN;             // allele or read holds an N: the N planes take part in base comparisons
 };
 
 // candidate = seed overlap that passed the similarity filter of GetOverlapsFromRead (SeqSet.hpp:1893-1908)
@@ -126,38 +137,50 @@ T1K_HD int imin(int a, int b) { return a < b ? a : b; }
 T1K_HD int imax(int a, int b) { return a > b ? a : b; }
 T1K_HD int iabs(int a) { return a < 0 ? -a : a; }
 
-// 32 bases starting at base `pos` (>= 0) of a plane that begins at word w0
-T1K_HD u64 fetch32(const u64 *plane, u64 w0, int pos) {
-  const u64 *p = plane + w0 + (pos >> 5);
+// 32 bases starting at base `pos` (>= 0) of a plane
+T1K_HD u64 fetch32(const u64 *plane, int pos) {
+  const u64 *p = plane + (pos >> 5);
   int sh = (pos & 31) * 2;
   return (p[0] >> sh) | ((p[1] << 1) << (63 - sh));      // branch-free funnel shift (sh in 0..62)
 }
-T1K_HD int base2(const u64 *plane, u64 w0, int pos) { return (int)((plane[w0 + (pos >> 5)] >> ((pos & 31) * 2)) & 3); }
+T1K_HD u64 fetch32(const u64 *plane, u64 w0, int pos) { return fetch32(plane + w0, pos); }
+T1K_HD int base2(const u64 *plane, int pos) { return (int)((plane[pos >> 5] >> ((pos & 31) * 2)) & 3); }
+T1K_HD int base2(const u64 *plane, u64 w0, int pos) { return base2(plane + w0, pos); }
 T1K_HD u64 lowmask2(int nBases) { return nBases >= 32 ? ~0ull : ((1ull << (2 * nBases)) - 1); }
 
+T1K_HD AlleleView allele_view(const RefView &R, int seqIdx, const ReadView &Q) {
+  AlleleView T;
+  const u64 w0 = R.wordOff[seqIdx];
+  T.seq = R.seq2 + w0; T.n2 = R.n2 + w0; T.ex2 = R.ex2 + w0;
+  T.len = R.len[seqIdx];
+  T.hasN = R.hasN[seqIdx] != 0;
+  T.useN = T.hasN || Q.anyN;
+  return T;
+}
+
 // AlignAlgo.hpp:304-305: equal, or either side N
-T1K_HD bool base_eq(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos) {
-  if (base2(R.n2, w0, tpos) | base2(Q.n2, 0, ppos)) return true;
-  return base2(R.seq2, w0, tpos) == base2(Q.seq2, 0, ppos);
+T1K_HD bool base_eq(const AlleleView &T, int tpos, const ReadView &Q, int ppos) {
+  if (T.useN && (base2(T.n2, tpos) | base2(Q.n2, ppos))) return true;
+  return base2(T.seq, tpos) == base2(Q.seq2, ppos);
 }
 
 // mismatch plane (01 per mismatching column) of 32 columns starting at (tpos+k, ppos+k)
-T1K_HD u64 mm_chunk(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos, int nLeft) {
-  u64 x = fetch32(R.seq2, w0, tpos) ^ fetch32(Q.seq2, 0, ppos);
+T1K_HD u64 mm_chunk(const AlleleView &T, int tpos, const ReadView &Q, int ppos, int nLeft) {
+  u64 x = fetch32(T.seq, tpos) ^ fetch32(Q.seq2, ppos);
   u64 d = (x | (x >> 1)) & M55;
-  d &= ~(fetch32(R.n2, w0, tpos) | fetch32(Q.n2, 0, ppos));
+  if (T.useN) d &= ~(fetch32(T.n2, tpos) | fetch32(Q.n2, ppos));
   return d & lowmask2(nLeft);
 }
 
 // mismatching columns among rows [lo, hi] of the window when row r of the read is paired with allele column r + d
-T1K_HDN T1K_NOINLINE inline int shifted_mm(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos, int n, int d, int lo, int hi) {
+T1K_HDN T1K_NOINLINE inline int shifted_mm(const AlleleView &T, int tpos, const ReadView &Q, int ppos, int n, int d, int lo, int hi) {
   if (lo < 0) lo = 0;
   if (lo < -d) lo = -d;
   if (hi > n - 1) hi = n - 1;
   if (hi > n - 1 - d) hi = n - 1 - d;
   int c = 0;
   T1K_NOUNROLL
-  for (int k = lo; k <= hi; k += 32) c += popc64(mm_chunk(R, w0, tpos + k + d, Q, ppos + k, hi - k + 1));
+  for (int k = lo; k <= hi; k += 32) c += popc64(mm_chunk(T, tpos + k + d, Q, ppos + k, hi - k + 1));
   return c;
 }
 
@@ -174,13 +197,13 @@ T1K_HDN T1K_NOINLINE inline int shifted_mm(const RefView &R, u64 w0, int tpos, c
 // rows are the unpaired ones) and ends at a mismatch (or up to |d| rows after one).  More mismatches fall back to
 // a shift histogram bound, and failing that to the DP.
 // 4 or 5 diagonal mismatches: exact enumeration of the single-shift excursions (see above)
-T1K_HDN T1K_NOINLINE inline bool diag_certified_45(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos, int n, int mm) {
+T1K_HDN T1K_NOINLINE inline bool diag_certified_45(const AlleleView &T, int tpos, const ReadView &Q, int ppos, int n, int mm) {
   int pos[5];
   {
     int c = 0;
     T1K_NOUNROLL
     for (int k = 0; k < n; k += 32) {
-      u64 m = mm_chunk(R, w0, tpos + k, Q, ppos + k, n - k);
+      u64 m = mm_chunk(T, tpos + k, Q, ppos + k, n - k);
       T1K_NOUNROLL
       while (m) { pos[c < 5 ? c : 4] = k + (ctz64(m) >> 1); ++c; m &= m - 1; }
     }
@@ -200,7 +223,7 @@ T1K_HDN T1K_NOINLINE inline bool diag_certified_45(const RefView &R, u64 w0, int
               int in = 0;
               T1K_NOUNROLL
               for (int q = 0; q < mm; ++q) in += pos[q] >= A && pos[q] <= B;
-              if (in - shifted_mm(R, w0, tpos, Q, ppos, n, d, A, B - d) > 2 + d) return false;
+              if (in - shifted_mm(T, tpos, Q, ppos, n, d, A, B - d) > 2 + d) return false;
             }
           }
           // insertion first (allele behind by d): first d rows unpaired, rows [A + d, B] paired with columns r - d
@@ -210,7 +233,7 @@ T1K_HDN T1K_NOINLINE inline bool diag_certified_45(const RefView &R, u64 w0, int
               int in = 0;
               T1K_NOUNROLL
               for (int q = 0; q < mm; ++q) in += pos[q] >= A && pos[q] <= B;
-              if (in - shifted_mm(R, w0, tpos, Q, ppos, n, -d, A + d, B) > 2 + d) return false;
+              if (in - shifted_mm(T, tpos, Q, ppos, n, -d, A + d, B) > 2 + d) return false;
             }
           }
         }
@@ -220,13 +243,13 @@ T1K_HDN T1K_NOINLINE inline bool diag_certified_45(const RefView &R, u64 w0, int
 
 // 6..24 diagonal mismatches: shift-histogram bound (F_d = diagonal mismatches that shift d turns into matches;
 // sum_d max(0, F_d - 1) <= 1 leaves every excursion <= 0)
-T1K_HDN T1K_NOINLINE inline bool diag_certified_hist(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos, int n) {
+T1K_HDN T1K_NOINLINE inline bool diag_certified_hist(const AlleleView &T, int tpos, const ReadView &Q, int ppos, int n) {
   int F[2 * BAND + 1];
   T1K_NOUNROLL
   for (int d = 0; d <= 2 * BAND; ++d) F[d] = 0;
   T1K_NOUNROLL
   for (int k = 0; k < n; k += 32) {
-    u64 m = mm_chunk(R, w0, tpos + k, Q, ppos + k, n - k);
+    u64 m = mm_chunk(T, tpos + k, Q, ppos + k, n - k);
     T1K_NOUNROLL
     while (m) {
       int p = k + (ctz64(m) >> 1);
@@ -236,7 +259,7 @@ T1K_HDN T1K_NOINLINE inline bool diag_certified_hist(const RefView &R, u64 w0, i
         if (d == 0) continue;
         int q = p + d;
         if (q < 0 || q >= n) continue;
-        if (base_eq(R, w0, tpos + q, Q, ppos + p)) ++F[d + BAND];
+        if (base_eq(T, tpos + q, Q, ppos + p)) ++F[d + BAND];
       }
     }
   }
@@ -246,26 +269,29 @@ T1K_HDN T1K_NOINLINE inline bool diag_certified_hist(const RefView &R, u64 w0, i
   return excess <= 1;
 }
 
-T1K_HD bool diag_certified(const RefView &R, u64 w0, int tpos, const ReadView &Q, int ppos, int n, int &mmOut) {
+T1K_HD bool diag_certified(const AlleleView &T, int tpos, const ReadView &Q, int ppos, int n, int &mmOut) {
   int mm = 0;
-  T1K_NOUNROLL
-  for (int k = 0; k < n; k += 32) mm += popc64(mm_chunk(R, w0, tpos + k, Q, ppos + k, n - k));
+  if (n <= 32) mm = popc64(mm_chunk(T, tpos, Q, ppos, n));     // the gap between two seed hits: one word
+  else {
+    T1K_NOUNROLL
+    for (int k = 0; k < n; k += 32) mm += popc64(mm_chunk(T, tpos + k, Q, ppos + k, n - k));
+  }
   mmOut = mm;
   if (mm <= 3) return true;
-  if (mm <= 5) return diag_certified_45(R, w0, tpos, Q, ppos, n, mm);
+  if (mm <= 5) return diag_certified_45(T, tpos, Q, ppos, n, mm);
   if (mm > 24) return false;
-  return diag_certified_hist(R, w0, tpos, Q, ppos, n);
+  return diag_certified_hist(T, tpos, Q, ppos, n);
 }
 
 // AlignAlgo::GlobalAlignment (AlignAlgo.hpp:215-421), one lane, band-only storage:
 // two rolling rows of (m,e) and one direction nibble per band cell
 //   bit0 diagonal predecessor reproduces m, bit1 f >= e, bit2 e opened from m, bit3 f opened from m.
 // Writes the edit ops in forward order to S.ops() (0 M,1 X,2 I,3 D) and returns their count (<0: error).
-T1K_HDN T1K_NOINLINE inline int dp_align(const RefView &R, u64 w0, int tpos, int lent, const ReadView &Q, int ppos, int lenp,
+T1K_HDN T1K_NOINLINE inline int dp_align(const AlleleView &T, int tpos, int lent, const ReadView &Q, int ppos, int lenp,
                             const LaneScratch &S, int &err) {
   u8 *ops = S.ops();
   if (lent == 0 || lenp == 0) return 0;
-  if (lent == 1 && lenp == 1) { ops[0] = base_eq(R, w0, tpos, Q, ppos) ? 0 : 1; return 1; }
+  if (lent == 1 && lenp == 1) { ops[0] = base_eq(T, tpos, Q, ppos) ? 0 : 1; return 1; }
   int lb = BAND, rb = BAND;
   if (lent > lenp) rb += lent - lenp; else if (lent < lenp) lb += lenp - lent;
   const int W = lb + rb + 3;          // columns i-lb-1 .. i+rb+1
@@ -287,7 +313,7 @@ T1K_HDN T1K_NOINLINE inline int dp_align(const RefView &R, u64 w0, int tpos, int
   for (int i = 1; i <= lenp; ++i) {
     int start = i - lb < 1 ? 1 : i - lb;
     int end = i + rb > lent ? lent : i + rb;
-    int pb = base2(Q.seq2, 0, ppos + i - 1), pn = base2(Q.n2, 0, ppos + i - 1);
+    int pb = base2(Q.seq2, ppos + i - 1), pn = T.useN ? base2(Q.n2, ppos + i - 1) : 0;
     int fPrev = negInf, mLeft = negInf;        // f and m of column j-1 in this row
     u8 *drow = dir + (size_t)i * W;
     T1K_NOUNROLL
@@ -305,7 +331,7 @@ T1K_HDN T1K_NOINLINE inline int dp_align(const RefView &R, u64 w0, int tpos, int
         ev = e1 > e2 ? e1 : e2;
         int f1 = fPrev - 1, f2 = mLeft - 5;
         fv = f1 > f2 ? f1 : f2;
-        bool eq = pn || base2(R.n2, w0, tpos + j - 1) || base2(R.seq2, w0, tpos + j - 1) == pb;
+        bool eq = pn || (T.useN && base2(T.n2, tpos + j - 1)) || base2(T.seq, tpos + j - 1) == pb;
         int dv = mDiag + (eq ? 2 : -2);
         mv = dv;
         if (ev > mv) mv = ev;
@@ -330,7 +356,7 @@ T1K_HDN T1K_NOINLINE inline int dp_align(const RefView &R, u64 w0, int tpos, int
       int a;
       if (ti > 0 && tj > 0) {
         u8 b = dir[(size_t)ti * W + (tj - (ti - lb - 1))];
-        if (b & 1) a = base_eq(R, w0, tpos + tj - 1, Q, ppos + ti - 1) ? 0 : 1;
+        if (b & 1) a = base_eq(T, tpos + tj - 1, Q, ppos + ti - 1) ? 0 : 1;
         else a = (b & 2) ? 3 : 2;
       } else if (ti == 0) a = (-4 - tj >= stale) ? 3 : 2;
       else a = 2;                      // tj == 0, ti > 0: f = -4-4ti < e = -4-ti
@@ -360,16 +386,16 @@ T1K_HDN T1K_NOINLINE inline int dp_align(const RefView &R, u64 w0, int tpos, int
 }
 
 // number of EDIT_MATCH columns of GlobalAlignment(t, lent, p, lenp)  (GetAlignStats, SeqSet.hpp:438-455)
-T1K_HDN T1K_NOINLINE inline int align_matches(const RefView &R, u64 w0, int tpos, int lent, const ReadView &Q, int ppos, int lenp,
+T1K_HDN T1K_NOINLINE inline int align_matches(const AlleleView &T, int tpos, int lent, const ReadView &Q, int ppos, int lenp,
                                  const LaneScratch &S, int &err) {
   if (lent == 0 || lenp == 0) return 0;
   T1K_COUNT(4, 1);
   if (lent == lenp) {
     int mm;
-    if (diag_certified(R, w0, tpos, Q, ppos, lent, mm)) return lent - mm;
+    if (diag_certified(T, tpos, Q, ppos, lent, mm)) return lent - mm;
   }
   T1K_COUNT(5, 1);
-  int n = dp_align(R, w0, tpos, lent, Q, ppos, lenp, S, err);
+  int n = dp_align(T, tpos, lent, Q, ppos, lenp, S, err);
   int c = 0;
   const u8 *ops = S.ops();
   T1K_NOUNROLL
@@ -377,18 +403,19 @@ T1K_HDN T1K_NOINLINE inline int align_matches(const RefView &R, u64 w0, int tpos
   return c;
 }
 
-// any N of the allele inside [s, e] (clamped to the allele)
-T1K_HD bool n_in_range(const RefView &R, u64 w0, int s, int e) {
+// any N inside [s, e] of an N plane that starts at the allele's first word
+T1K_HD bool n_in_range(const u64 *n2, int s, int e) {
   T1K_NOUNROLL
   for (int k = s; k <= e; k += 32)
-    if (fetch32(R.n2, w0, k) & lowmask2(e - k + 1)) return true;
+    if (fetch32(n2, k) & lowmask2(e - k + 1)) return true;
   return false;
 }
+T1K_HD bool n_in_range(const RefView &R, u64 w0, int s, int e) { return n_in_range(R.n2 + w0, s, e); }
 // IsSeparatorInRange (SeqSet.hpp:487-498): separators are -1, every N, and len
-T1K_HD bool sep_in_range(const RefView &R, u64 w0, int len, int s, int e) {
+T1K_HD bool sep_in_range(const AlleleView &T, int s, int e) {
   if (s > e) return false;
-  if (s <= -1 || e >= len) return true;
-  return n_in_range(R, w0, s, e);
+  if (s <= -1 || e >= T.len) return true;
+  return T.hasN && n_in_range(T.n2, s, e);
 }
 
 // IsOverlapLowComplex (SeqSet.hpp:458-485)
@@ -397,7 +424,7 @@ T1K_HD bool low_complex(const ReadView &Q, int s, int e) {
   int n = e - s + 1;
   T1K_NOUNROLL
   for (int k = 0; k < n; k += 32) {
-    u64 w = fetch32(Q.seq2, 0, s + k), nm = fetch32(Q.n2, 0, s + k);
+    u64 w = fetch32(Q.seq2, s + k), nm = Q.anyN ? fetch32(Q.n2, s + k) : 0;
     u64 keep = ~nm & M55 & lowmask2(n - k);
     u64 lo = w & M55, hi = (w >> 1) & M55;
     cnt[0] += popc64(~lo & ~hi & keep);
@@ -435,51 +462,52 @@ T1K_HD u64 order_key(int matchCnt, int denom, int span, int seqIdx, int readStar
 }
 
 // ---- chain consumer: GetOverlapsFromHits tail (SeqSet.hpp:1500-1550) + the matchCnt recomputation of
-// GetOverlapsFromRead (SeqSet.hpp:1697-1845).  `C` yields the LIS chain as encoded hits.
-template <class Chain>
+// GetOverlapsFromRead (SeqSet.hpp:1697-1845).  `C` yields the LIS chain as encoded hits; read and allele offsets
+// both increase strictly along it.  OneDiag: every hit lies on one diagonal (the common case).
+//   GetTotalHitLengthOnRead/Seq (SeqSet.hpp:1032-1069): runs of hits whose k-mers touch contribute last - first + k,
+//   i.e. k for the first hit and min(step, k-or-step) for every later one -> one pass, one load per hit.
+template <bool OneDiag, class Chain>
 T1K_HDN T1K_NOINLINE inline void consume_chain(const RefView &R, const ReadView &Q, int strand01, int seqIdx, const Chain &C, int sz,
                                   const LaneScratch &S, int &nEmit, u64 &bestStrandKey, int &err) {
   if (sz * KMER < HIT_LEN_REQ) return;
-  int hitLen = 0, seqLenCov = 0;
-  {
-    int i = 0;
-    T1K_NOUNROLL
-    while (i < sz) {
-      int j = i + 1;
-      T1K_NOUNROLL
-      while (j < sz && hit_a(C(j)) <= hit_a(C(j - 1)) + KMER - 1) ++j;
-      hitLen += hit_a(C(j - 1)) - hit_a(C(i)) + KMER;
-      i = j;
-    }
-    if (hitLen < HIT_LEN_REQ) return;
-    i = 0;
-    T1K_NOUNROLL
-    while (i < sz) {
-      int j = i + 1;
-      T1K_NOUNROLL
-      while (j < sz && hit_b(C(j)) <= hit_b(C(j - 1)) + KMER - 1) ++j;
-      seqLenCov += hit_b(C(j - 1)) - hit_b(C(i)) + KMER;
-      i = j;
-    }
-    if (seqLenCov < HIT_LEN_REQ) return;
-  }
-  const u64 w0 = R.wordOff[seqIdx];
-  int rs = hit_a(C(0)), re = hit_a(C(sz - 1)) + KMER - 1;
-  int ss = hit_b(C(0)), se = hit_b(C(sz - 1)) + KMER - 1;
-  u64 sk = strand_key(2 * hitLen, re - rs, seqIdx, strand01);
-  if (sk > bestStrandKey) bestStrandKey = sk;
-  int mc = 2 * KMER;
+  const u32 h0 = C(0);
+  const int rs = hit_a(h0), ss = hit_b(h0);
+  int pa = rs, pb = ss, hitLen = KMER, seqLenCov = KMER, nGap = 0;
   T1K_NOUNROLL
   for (int j = 1; j < sz; ++j) {
-    int pa = hit_a(C(j - 1)), pb = hit_b(C(j - 1)), a = hit_a(C(j)), b = hit_b(C(j));
-    bool aOv = pa + KMER - 1 >= a, bOv = pb + KMER - 1 >= b;
-    if (pb - pa == b - a) {
-      if (aOv) mc += 2 * (a - pa);
-      else mc += 2 * KMER + 2 * align_matches(R, w0, pb + KMER, b - (pb + KMER), Q, pa + KMER, a - (pa + KMER), S, err);
-    } else if (aOv && !bOv) mc += 2 * (a - pa);
-    else if (!aOv && bOv) mc += 2 * (b - pb);
-    else if (aOv && bOv) mc += 2 * imin(a - pa, b - pb);
-    else mc += 2 * KMER + 2 * align_matches(R, w0, pb + KMER, b - (pb + KMER), Q, pa + KMER, a - (pa + KMER), S, err);
+    const u32 h = C(j);
+    const int a = hit_a(h), b = hit_b(h);
+    const bool aOv = a <= pa + KMER - 1;
+    hitLen += aOv ? a - pa : KMER;
+    if (!OneDiag) { const bool bOv = b <= pb + KMER - 1; seqLenCov += bOv ? b - pb : KMER; nGap += !(aOv && bOv); }
+    else nGap += !aOv;
+    pa = a; pb = b;
+  }
+  if (OneDiag) seqLenCov = hitLen;
+  if (hitLen < HIT_LEN_REQ || seqLenCov < HIT_LEN_REQ) return;
+  const int re = pa + KMER - 1, se = pb + KMER - 1;
+  u64 sk = strand_key(2 * hitLen, re - rs, seqIdx, strand01);
+  if (sk > bestStrandKey) bestStrandKey = sk;
+  int mc;
+  if (OneDiag && nGap == 0) mc = 2 * hitLen;       // every step overlaps: 2k + sum of 2*(a - pa)
+  else {
+    const AlleleView T = allele_view(R, seqIdx, Q);
+    mc = 2 * KMER;
+    pa = rs; pb = ss;
+    T1K_NOUNROLL
+    for (int j = 1; j < sz; ++j) {
+      const u32 h = C(j);
+      const int a = hit_a(h), b = hit_b(h);
+      const bool aOv = pa + KMER - 1 >= a, bOv = pb + KMER - 1 >= b;
+      if (OneDiag || pb - pa == b - a) {
+        if (aOv) mc += 2 * (a - pa);
+        else mc += 2 * KMER + 2 * align_matches(T, pb + KMER, b - (pb + KMER), Q, pa + KMER, a - (pa + KMER), S, err);
+      } else if (aOv && !bOv) mc += 2 * (a - pa);
+      else if (!aOv && bOv) mc += 2 * (b - pb);
+      else if (aOv && bOv) mc += 2 * imin(a - pa, b - pb);
+      else mc += 2 * KMER + 2 * align_matches(T, pb + KMER, b - (pb + KMER), Q, pa + KMER, a - (pa + KMER), S, err);
+      pa = a; pb = b;
+    }
   }
   double sim = (double)mc / (double)(se - ss + 1 + re - rs + 1);
   if (low_complex(Q, rs, re)) sim = 0;
@@ -537,7 +565,7 @@ T1K_HDN T1K_NOINLINE inline void chain_allele(const RefView &R, const ReadView &
     if (hit_a(first) - hit_b(first) == hit_a(last) - hit_b(last)) {
       // one diagonal: every read offset occurs once, (b,a) order == current order, LIS keeps everything
       ChainDirect cd; cd.p = h + (size_t)s * stride; cd.stride = stride;
-      consume_chain(R, Q, strand01, seqIdx, cd, m, S, nEmit, bestStrandKey, err);
+      consume_chain<true>(R, Q, strand01, seqIdx, cd, m, S, nEmit, bestStrandKey, err);
       s = e; continue;
     }
     // general path (SeqSet.hpp:1437-1456 + LIS :352-436)
@@ -608,31 +636,35 @@ T1K_HDN T1K_NOINLINE inline void chain_allele(const RefView &R, const ReadView &
     T1K_NOUNROLL
     for (int i = 0; i < sz; ++i) park[i] = chain[i];
     ChainDirect cd; cd.p = park; cd.stride = 1;
-    consume_chain(R, Q, strand01, seqIdx, cd, sz, S, nEmit, bestStrandKey, err);
+    consume_chain<false>(R, Q, strand01, seqIdx, cd, sz, S, nEmit, bestStrandKey, err);
     s = e;
   }
 }
 
 // ---- SeqSet::ExtendOverlap (SeqSet.hpp:1994-2100) + the separator tests of AssignRead (SeqSet.hpp:2163-2169)
 T1K_HDN T1K_NOINLINE inline void extend_cand(const RefView &R, const ReadView &Q, Cand &c, const LaneScratch &S, int &err) {
-  const u64 w0 = R.wordOff[c.seqIdx];
-  const int clen = R.len[c.seqIdx], len = Q.len;
+  const AlleleView T = allele_view(R, c.seqIdx, Q);
+  const int clen = T.len, len = Q.len;
   int rs = c.readStart, re = c.readEnd, ss = c.seqStart, se = c.seqEnd;
   u8 flags = 0;
-  if (sep_in_range(R, w0, clen, ss, se)) { c.flags = CF_SEP; return; }
-  if (sep_in_range(R, w0, clen, ss - rs, se + (len - re - 1))) flags |= CF_NEEDCLIP;
+  if (sep_in_range(T, ss, se)) { c.flags = CF_SEP; return; }
+  if (sep_in_range(T, ss - rs, se + (len - re - 1))) flags |= CF_NEEDCLIP;
   int lo = imin(rs, ss), leftClip = 0, rightClip = 0;
   if (rs > ss) leftClip = rs - ss;
-  T1K_NOUNROLL
-  for (int i = 0; i < lo; ++i)
-    if (base2(R.n2, w0, ss - i - 1)) { leftClip = lo - i; lo = i; break; }
-  int m = align_matches(R, w0, ss - lo, lo, Q, rs - lo, lo, S, err);
+  if (T.hasN) {
+    T1K_NOUNROLL
+    for (int i = 0; i < lo; ++i)
+      if (base2(T.n2, ss - i - 1)) { leftClip = lo - i; lo = i; break; }
+  }
+  int m = align_matches(T, ss - lo, lo, Q, rs - lo, lo, S, err);
   int ro = imin(len - 1 - re, clen - 1 - se);
   if (len - 1 - re > clen - 1 - se) rightClip = len - 1 - re - (clen - 1 - se);
-  T1K_NOUNROLL
-  for (int i = 0; i < ro; ++i)
-    if (base2(R.n2, w0, se + 1 + i)) { rightClip = ro - i; ro = i; break; }
-  m += align_matches(R, w0, se + 1, ro, Q, re + 1, ro, S, err);
+  if (T.hasN) {
+    T1K_NOUNROLL
+    for (int i = 0; i < ro; ++i)
+      if (base2(T.n2, se + 1 + i)) { rightClip = ro - i; ro = i; break; }
+  }
+  m += align_matches(T, se + 1, ro, Q, re + 1, ro, S, err);
   c.eReadStart = (u8)(rs - lo); c.eReadEnd = (u8)(re + ro);
   c.eSeqStart = ss - lo; c.eSeqEnd = se + ro;
   int mc = 2 * m + c.matchCnt;
@@ -655,35 +687,64 @@ T1K_HD void cov_add(int32_t *p, int v) {
 // ---- full-read alignment of an extended overlap (SeqSet.hpp:2203-2274): exon-relaxed match count and
 // base coverage.  Coverage is kept as a range-add difference array plus point corrections, so a
 // certified-diagonal record costs 2 + (#uncredited columns) atomics instead of one per base.
+// One pass over the window: mismatch count, exonic mismatch count and (while <= 3, which certifies the diagonal)
+// the mismatch positions themselves; only 4+ mismatches or N columns need a second look at the window.
 T1K_HDN T1K_NOINLINE inline void full_align(const RefView &R, const ReadView &Q, Cand &c, int weight, const LaneScratch &S, int &err) {
-  const u64 w0 = R.wordOff[c.seqIdx];
+  const AlleleView T = allele_view(R, c.seqIdx, Q);
   const int tpos = c.eSeqStart, ppos = c.eReadStart;
   const int lent = c.eSeqEnd - c.eSeqStart + 1, lenp = c.eReadEnd - c.eReadStart + 1;
-  const size_t cb = (size_t)w0 * 32;
-  int mm;
+  int32_t *covDiff = R.covDiff + (size_t)R.wordOff[c.seqIdx] * 32, *covPoint = R.covPoint + (size_t)R.wordOff[c.seqIdx] * 32;
   T1K_COUNT(6, 1);
-  if (lent == lenp && diag_certified(R, w0, tpos, Q, ppos, lent, mm)) {
-    int exMm = 0;
-    if (weight > 0) { cov_add(R.covDiff + cb + tpos, weight); cov_add(R.covDiff + cb + tpos + lent, -weight); }
+  if (lent == lenp) {
+    int mm = 0, exMm = 0, p0 = 0, p1 = 0, p2 = 0;
     T1K_NOUNROLL
     for (int k = 0; k < lent; k += 32) {
-      u64 d = mm_chunk(R, w0, tpos + k, Q, ppos + k, lent - k);
-      if (R.relax) exMm += popc64(d & fetch32(R.ex2, w0, tpos + k));
-      if (weight > 0) {
-        u64 un = (d | fetch32(R.n2, w0, tpos + k) | fetch32(Q.n2, 0, ppos + k)) & lowmask2(lent - k);
+      u64 d = mm_chunk(T, tpos + k, Q, ppos + k, lent - k);
+      if (d) {
+        if (R.relax) exMm += popc64(d & fetch32(T.ex2, tpos + k));
         T1K_NOUNROLL
-        while (un) {
-          int p = k + (ctz64(un) >> 1);
-          un &= un - 1;
-          cov_add(R.covPoint + cb + tpos + p, -weight);
+        while (d && mm < 3) {
+          const int p = k + (ctz64(d) >> 1);
+          d &= d - 1;
+          if (mm == 0) p0 = p; else if (mm == 1) p1 = p; else p2 = p;
+          ++mm;
         }
+        mm += popc64(d);
       }
     }
-    c.relaxed = R.relax ? 2 * (lent - exMm) : c.eMatchCnt;
-    return;
+    bool diag = mm <= 3;
+    if (!diag) {
+      if (mm <= 5) diag = diag_certified_45(T, tpos, Q, ppos, lent, mm);
+      else if (mm <= 24) diag = diag_certified_hist(T, tpos, Q, ppos, lent);
+    }
+    if (diag) {
+      if (weight > 0) {
+        cov_add(covDiff + tpos, weight); cov_add(covDiff + tpos + lent, -weight);
+        if (mm <= 3 && !T.useN) {       // the uncredited columns are exactly the recorded mismatches
+          if (mm > 0) cov_add(covPoint + tpos + p0, -weight);
+          if (mm > 1) cov_add(covPoint + tpos + p1, -weight);
+          if (mm > 2) cov_add(covPoint + tpos + p2, -weight);
+        } else {
+          T1K_NOUNROLL
+          for (int k = 0; k < lent; k += 32) {
+            u64 un = mm_chunk(T, tpos + k, Q, ppos + k, lent - k);
+            if (T.useN) un |= (fetch32(T.n2, tpos + k) | fetch32(Q.n2, ppos + k)) & lowmask2(lent - k);
+            T1K_NOUNROLL
+            while (un) {
+              const int p = k + (ctz64(un) >> 1);
+              un &= un - 1;
+              cov_add(covPoint + tpos + p, -weight);
+            }
+          }
+        }
+      }
+      c.relaxed = R.relax ? 2 * (lent - exMm) : c.eMatchCnt;
+      return;
+    }
+    T1K_COUNT(8 + (mm >= 4 && mm <= 10 ? mm - 4 : 7), 1);
   }
-  T1K_COUNT(7, 1); T1K_COUNT(8 + (mm > 8 ? 8 : mm) - 1 < 16 ? (mm >= 4 && mm <= 10 ? 8 + mm - 4 : 15) : 15, 1);
-  int n = dp_align(R, w0, tpos, lent, Q, ppos, lenp, S, err);
+  T1K_COUNT(7, 1);
+  int n = dp_align(T, tpos, lent, Q, ppos, lenp, S, err);
   if (n < 0) { c.relaxed = c.eMatchCnt; return; }
   const u8 *ops = S.ops();
   int refPos = tpos, readPos = ppos, m = 0;
@@ -691,11 +752,11 @@ T1K_HDN T1K_NOINLINE inline void full_align(const RefView &R, const ReadView &Q,
   for (int k = 0; k < n; ++k) {
     int op = ops[k];
     if (R.relax) {
-      if (base2(R.ex2, w0, refPos)) { if (op == 0) ++m; } else ++m;
+      if (base2(T.ex2, refPos)) { if (op == 0) ++m; } else ++m;
     }
-    if (weight > 0 && op == 0 && readPos < Q.len && refPos < R.len[c.seqIdx] && !base2(Q.n2, 0, readPos) &&
-        !base2(R.n2, w0, refPos) && base2(R.seq2, w0, refPos) == base2(Q.seq2, 0, readPos))
-      cov_add(R.covPoint + cb + refPos, weight);
+    if (weight > 0 && op == 0 && readPos < Q.len && refPos < T.len && !base2(Q.n2, readPos) &&
+        !base2(T.n2, refPos) && base2(T.seq, refPos) == base2(Q.seq2, readPos))
+      cov_add(covPoint + refPos, weight);
     if (op != 2) ++refPos;
     if (op != 3) ++readPos;
   }

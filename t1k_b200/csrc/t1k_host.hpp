@@ -17,6 +17,7 @@ struct PackedRef {
   std::vector<u64> seq2, n2, ex2;
   std::vector<u64> wordOff;
   std::vector<int32_t> len;
+  std::vector<u8> hasN;
   std::vector<u32> kstart;
   std::vector<Posting> post;
   size_t totalWords = 0;
@@ -28,7 +29,7 @@ inline void set2(std::vector<u64> &plane, u64 w0, int pos, u64 v) { plane[w0 + (
 inline bool pack_reference(int32_t n, const char *bases, const int64_t *off, const int32_t *exonPtr, const int32_t *exonSE,
                            PackedRef &P) {
   P.nAlleles = n;
-  P.wordOff.resize(n); P.len.resize(n);
+  P.wordOff.resize(n); P.len.resize(n); P.hasN.assign(n, 0);
   size_t words = 0;
   for (int i = 0; i < n; ++i) {
     int len = (int)(off[i + 1] - off[i]);
@@ -51,7 +52,7 @@ inline bool pack_reference(int32_t n, const char *bases, const int64_t *off, con
         for (int j = 0; j < len; ++j) {
           if (!valid_base(s[j])) return false;
           set2(P.seq2, w0, j, (u64)code_of(s[j]));
-          if (s[j] == 'N') set2(P.n2, w0, j, 1);
+          if (s[j] == 'N') { set2(P.n2, w0, j, 1); P.hasN[i] = 1; }
         }
         for (int e = exonPtr[i]; e < exonPtr[i + 1]; ++e)
           for (int j = exonSE[2 * e]; j <= exonSE[2 * e + 1] && j < len; ++j)

@@ -10,6 +10,9 @@ namespace t1k {
 
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int GATHER_DEPTH = 4;      // posting loads in flight per warp in the tile gather
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 struct ReadsDev {
   const u64 *planes;       // [(r*4 + plane) * RWORDS]; planes: fwd seq2, fwd n2, rc seq2, rc n2
@@ -111,21 +114,24 @@ __global__ void k_pack_reads(const char *bases, const u64 *off, const u32 *len, 
 // ---------------------------------------------------------------------------------------------------
 // One warp = one read-end at a time (dynamic work queue).  Shared memory per warp:
 //   H[hitCap][32]  encoded hits of the current allele tile, lane-interleaved (bank = lane)
-//   cnt[32], seedA[256], cur[256], end[256], nxt[256], read planes (2 x RWORDS words)
+//   cnt[32], seedA[256], act[256], cur[256], end[256], nxt[256], read planes (2 x RWORDS words)
 struct WarpSmem {
   u32 *H, *cnt, *cur, *end, *nxt;
-  u8 *seedA;
+  u8 *seedA, *act;
   u64 *seq, *nn;
 };
 __host__ __device__ inline size_t warp_smem_bytes(int hitCap) {
-  return (size_t)hitCap * 32 * 4 + 32 * 4 + 3 * 256 * 4 + 256 + 2 * RWORDS * 8;
+  return (size_t)hitCap * 32 * 4 + 32 * 4 + 3 * 256 * 4 + 2 * 256 + 2 * RWORDS * 8;
 }
 
-__device__ __forceinline__ void load_planes(const AssignParams &P, u32 r, int strand01, const WarpSmem &W, int lane) {
+// returns whether the read holds an N
+__device__ __forceinline__ bool load_planes(const AssignParams &P, u32 r, int strand01, const WarpSmem &W, int lane) {
   const u64 *src = P.Q.planes + ((size_t)r * 4 + (strand01 ? 0 : 2)) * RWORDS;
+  u64 nw = 0;
   if (lane < RWORDS) W.seq[lane] = src[lane];
-  else if (lane < 2 * RWORDS) W.nn[lane - RWORDS] = src[lane];   // n2 plane follows the seq plane
+  else if (lane < 2 * RWORDS) { nw = src[lane]; W.nn[lane - RWORDS] = nw; }   // n2 plane follows the seq plane
   __syncwarp();
+  return __any_sync(FULL, nw != 0);
 }
 
 __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W, Cand *cands, const LaneScratch &S, int lane) {
@@ -138,19 +144,19 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
   u64 bestKey = 0;
   unsigned long long stPost = 0, stTiles = 0;
   bool overflow = false;   // some allele has more hits than the shared-memory tile holds: re-run with the big tile
-  ReadView Qv; Qv.seq2 = W.seq; Qv.n2 = W.nn; Qv.len = len;
+  ReadView Qv; Qv.seq2 = W.seq; Qv.n2 = W.nn; Qv.len = len; Qv.anyN = false;
 
   if (len >= KMER) {
     const int NP = len - KMER + 1;
     T1K_NOUNROLL
     for (int pass = 0; pass < 2 && !overflow; ++pass) {
       const int strand01 = pass == 0 ? 1 : 0;
-      load_planes(P, r, strand01, W, lane);
+      Qv.anyN = load_planes(P, r, strand01, W, lane);
       // ---- k-mer codes and posting ranges of every window (GetHitsFromRead, SeqSet.hpp:1093-1153)
       T1K_NOUNROLL
       for (int a = lane; a < NP; a += 32) {
-        u32 code = (u32)(fetch32(W.seq, 0, a) & 0x3FFFFFull);
-        bool valid = (fetch32(W.nn, 0, a) & 0x155555ull) == 0;
+        u32 code = (u32)(fetch32(W.seq, a) & 0x3FFFFFull);
+        bool valid = (fetch32(W.nn, a) & 0x155555ull) == 0;
         u32 lo = R.kstart[code], hi = R.kstart[code + 1];
         W.nxt[a] = code; W.cur[a] = lo; W.end[a] = valid ? hi : lo;
       }
@@ -190,40 +196,71 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
         ++stTiles;
         W.cnt[lane] = 0;
         __syncwarp();
+        // seeds with postings inside this tile, in read-offset order (=> per-allele hits sorted by (a, b))
+        int nAct = 0;
         T1K_NOUNROLL
-        for (int k = 0; k < nS; ++k) {           // seeds in read-offset order => per-allele hits sorted by (a, b)
-          if (W.nxt[k] >= base + 32) continue;   // warp-uniform (shared-memory broadcast)
-          const u32 a = W.seedA[k];
-          T1K_NOUNROLL
-          for (;;) {
-            const u32 c = W.cur[k], e = W.end[k];
-            Posting p; p.idx = 0xffffffffu; p.off = 0;
-            if (c + lane < e) p = R.post[c + lane];
-            const bool in = p.idx < base + 32;
-            const unsigned bal = __ballot_sync(FULL, in);
-            const int consumed = __popc(bal);
-            const u32 prevIdx = __shfl_up_sync(FULL, p.idx, 1);
-            const bool startRun = lane == 0 || p.idx != prevIdx;
-            const unsigned sm = __ballot_sync(FULL, startRun);
-            const int runStart = 31 - __clz(sm & (0xffffffffu >> (31 - lane)));
-            const int rank = lane - runStart;
-            const bool lastOfRun = lane == 31 || ((sm >> (lane + 1)) & 1u);
-            const u32 local = p.idx - base;
-            u32 slot = 0;
-            if (in) {
-              slot = W.cnt[local] + rank;
-              if ((int)slot < CAP) W.H[slot * 32 + local] = a | (p.off << 8);
+        for (int k0 = 0; k0 < nS; k0 += 32) {
+          const int k = k0 + lane;
+          const bool act = k < nS && W.nxt[k] < base + 32;
+          const unsigned bal = __ballot_sync(FULL, act);
+          if (act) W.act[nAct + __popc(bal & ((1u << lane) - 1))] = (u8)k;
+          nAct += __popc(bal);
+        }
+        __syncwarp();
+        T1K_NOUNROLL
+        for (int i0 = 0; i0 < nAct; i0 += GATHER_DEPTH) {
+          // GATHER_DEPTH independent 256-byte posting loads in flight before the first one is consumed
+          Posting pf[GATHER_DEPTH]; u32 cf[GATHER_DEPTH], ef[GATHER_DEPTH]; int kf[GATHER_DEPTH];
+#pragma unroll
+          for (int u = 0; u < GATHER_DEPTH; ++u) {
+            pf[u].idx = 0xffffffffu; pf[u].off = 0; kf[u] = -1; cf[u] = ef[u] = 0;
+            if (i0 + u < nAct) {
+              kf[u] = W.act[i0 + u]; cf[u] = W.cur[kf[u]]; ef[u] = W.end[kf[u]];
+              if (cf[u] + lane < ef[u]) pf[u] = R.post[cf[u] + lane];
             }
-            __syncwarp();
-            if (in && lastOfRun) W.cnt[local] = slot + 1;
-            __syncwarp();
-            const u32 nc = c + consumed;
-            if (consumed == 32 && nc < e) { if (lane == 0) W.cur[k] = nc; __syncwarp(); continue; }
-            const u32 nextIdx = consumed < 32 ? __shfl_sync(FULL, p.idx, consumed) : 0xffffffffu;
-            if (lane == 0) { W.cur[k] = nc; W.nxt[k] = nextIdx; }
-            __syncwarp();
-            break;
           }
+#pragma unroll
+          for (int u = 0; u < GATHER_DEPTH; ++u) {
+            if (kf[u] < 0) break;                  // warp-uniform
+            const int k = kf[u];
+            const u32 a = W.seedA[k], e = ef[u];
+            u32 c = cf[u];
+            Posting p = pf[u];
+            T1K_NOUNROLL
+            for (;;) {
+              const bool in = p.idx < base + 32;
+              const unsigned bal = __ballot_sync(FULL, in);
+              const int consumed = __popc(bal);
+              const u32 prevIdx = __shfl_up_sync(FULL, p.idx, 1);
+              const bool startRun = lane == 0 || p.idx != prevIdx;
+              const unsigned sm = __ballot_sync(FULL, startRun);
+              const int runStart = 31 - __clz(sm & (0xffffffffu >> (31 - lane)));
+              const int rank = lane - runStart;
+              const bool lastOfRun = lane == 31 || ((sm >> (lane + 1)) & 1u);
+              const u32 local = p.idx - base;
+              u32 slot = 0;
+              if (in) {
+                slot = W.cnt[local] + rank;
+                if ((int)slot < CAP) W.H[slot * 32 + local] = a | (p.off << 8);
+              }
+              __syncwarp();
+              if (in && lastOfRun) W.cnt[local] = slot + 1;
+              __syncwarp();
+              const u32 nc = c + consumed;
+              if (consumed == 32 && nc < e) {          // the list continues inside this tile (repeated k-mer)
+                c = nc;
+                p.idx = 0xffffffffu; p.off = 0;
+                if (c + lane < e) p = R.post[c + lane];
+                continue;
+              }
+              const u32 nextIdx = consumed < 32 ? __shfl_sync(FULL, p.idx, consumed) : 0xffffffffu;
+              if (lane == 0) { W.cur[k] = nc; W.nxt[k] = nextIdx; }
+              // the block the next tile will ask for: pull it into L2 now (2 x 128 B lines)
+              if (lane < 2 && nc + lane * 16 < e) prefetch_l2(R.post + nc + lane * 16);
+              break;
+            }
+          }
+          __syncwarp();
         }
         __syncwarp();
         // ---- lane-per-allele chaining + rescoring
@@ -258,7 +295,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
   unsigned long long pos = 0;
   bool deferred = false;
   if (c1 - c0 > 0 && !overflow) {
-    if (best01 == 1) load_planes(P, r, 1, W, lane);
+    if (best01 == 1) Qv.anyN = load_planes(P, r, 1, W, lane);
     __threadfence_block();
     __syncwarp();
     // pass 1: extension; first candidate (list order) whose extension fails
@@ -399,7 +436,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_assign(AssignParams
   W.H = (u32 *)(W.nn + RWORDS);
   W.cnt = W.H + (size_t)P.hitCap * 32;
   W.cur = W.cnt + 32; W.end = W.cur + 256; W.nxt = W.end + 256;
-  W.seedA = (u8 *)(W.nxt + 256);
+  W.seedA = (u8 *)(W.nxt + 256); W.act = W.seedA + 256;
   LaneScratch S; S.base = P.laneScratch + (gwarp * 32 + lane) * (size_t)SCR_BYTES;
   Cand *cands = P.candBuf + gwarp * (size_t)P.candCap;
   for (;;) {

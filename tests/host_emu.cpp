@@ -35,7 +35,7 @@ Emu *emu_create(int32_t n, const char *bases, const int64_t *off, const int32_t 
   e->covPoint.assign(e->P.totalWords * 32, 0);
   RefView &R = e->R;
   R.seq2 = e->P.seq2.data(); R.n2 = e->P.n2.data(); R.ex2 = e->P.ex2.data();
-  R.wordOff = e->P.wordOff.data(); R.len = e->P.len.data();
+  R.wordOff = e->P.wordOff.data(); R.len = e->P.len.data(); R.hasN = e->P.hasN.data();
   R.kstart = e->P.kstart.data(); R.post = e->P.post.data();
   R.covDiff = e->covDiff.data(); R.covPoint = e->covPoint.data();
   R.nAlleles = n; R.sim = sim; R.relax = relax;
@@ -54,18 +54,20 @@ int32_t emu_align(const char *t, int32_t lent, const char *p, int32_t lenp, int8
     if (t[j] == 'N') n2[j >> 5] |= 1ull << ((j & 31) * 2);
   }
   u64 w0 = 0; int32_t len = lent;
+  u8 tHasN = memchr(t, 'N', lent) != NULL;
   RefView R; memset(&R, 0, sizeof(R));
-  R.seq2 = seq2.data(); R.n2 = n2.data(); R.ex2 = ex2.data(); R.wordOff = &w0; R.len = &len; R.nAlleles = 1;
+  R.seq2 = seq2.data(); R.n2 = n2.data(); R.ex2 = ex2.data(); R.wordOff = &w0; R.len = &len; R.hasN = &tHasN; R.nAlleles = 1;
   u64 fs[RWORDS], fn[RWORDS], rs[RWORDS], rn[RWORDS];
   if (lenp > 255) return -2;
   pack_read(p, lenp, fs, fn, rs, rn);
-  ReadView Q; Q.seq2 = fs; Q.n2 = fn; Q.len = lenp;
+  ReadView Q; Q.seq2 = fs; Q.n2 = fn; Q.len = lenp; Q.anyN = memchr(p, 'N', lenp) != NULL;
   std::vector<u8> scr(SCR_BYTES, 0);
   LaneScratch S; S.base = scr.data();
   int err = 0, mm = 0;
-  *certified = (lent == lenp && lent > 0) ? (int)diag_certified(R, 0, 0, Q, 0, lent, mm) : 0;
-  *matches = align_matches(R, 0, 0, lent, Q, 0, lenp, S, err);
-  int n = dp_align(R, 0, 0, lent, Q, 0, lenp, S, err);
+  const AlleleView T = allele_view(R, 0, Q);
+  *certified = (lent == lenp && lent > 0) ? (int)diag_certified(T, 0, Q, 0, lent, mm) : 0;
+  *matches = align_matches(T, 0, lent, Q, 0, lenp, S, err);
+  int n = dp_align(T, 0, lent, Q, 0, lenp, S, err);
   if (err) return -1;
   for (int i = 0; i < n; ++i) opsOut[i] = (int8_t)S.ops()[i];
   return n;
@@ -86,14 +88,14 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
   int nFwd = 0;
   for (int pass = 0; pass < 2; ++pass) {
     int strand01 = pass == 0 ? 1 : 0;
-    ReadView Q; Q.seq2 = planes[pass * 2]; Q.n2 = planes[pass * 2 + 1]; Q.len = len;
+    ReadView Q; Q.seq2 = planes[pass * 2]; Q.n2 = planes[pass * 2 + 1]; Q.len = len; Q.anyN = strchr(read, 'N') != NULL;
     // seed selection (GetHitsFromRead skip rule), then group hits per allele
     std::map<u32, std::vector<u32> > groups;
     u32 prev = 0; int skip = 0;
     const int P = len - KMER + 1;
     for (int a = 0; a < P; ++a) {
-      u32 code = (u32)(fetch32(Q.seq2, 0, a) & 0x3FFFFF);
-      bool valid = (fetch32(Q.n2, 0, a) & 0x155555) == 0;
+      u32 code = (u32)(fetch32(Q.seq2, a) & 0x3FFFFF);
+      bool valid = (fetch32(Q.n2, a) & 0x155555) == 0;
       if (a == 0 || prev != code) {
         u32 lo = 0, hi = 0;
         if (valid) { lo = R.kstart[code]; hi = R.kstart[code + 1]; }
@@ -115,7 +117,7 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
   int best01 = (bestKey & 1) ? 0 : 1;
   int c0 = best01 ? 0 : nFwd, c1 = best01 ? nFwd : (int)cands.size();
   if (c1 - c0 <= 0) { *errOut = err; return -1; }
-  ReadView Q; Q.seq2 = planes[best01 ? 0 : 2]; Q.n2 = planes[best01 ? 1 : 3]; Q.len = len;
+  ReadView Q; Q.seq2 = planes[best01 ? 0 : 2]; Q.n2 = planes[best01 ? 1 : 3]; Q.len = len; Q.anyN = strchr(read, 'N') != NULL;
   // pass 1: extension + first failing key
   u64 fKey = ~0ull; int fIdx = 0x7fffffff;
   for (int i = c0; i < c1; ++i) {

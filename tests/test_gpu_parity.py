@@ -117,8 +117,10 @@ def test_genotype_golden(golden):
     # default EM: every sum in the reference's order -> the reference's doubles, bit for bit
     assert np.array_equal(out["abundance"], q[:, 1])
     assert np.array_equal(out["ec_abundance"], q[:, 2])
+    # `fragmentAssigned` (Genotyper.cpp:564) is set from the pairing result BEFORE SetReadAssignments' cuts, so it
+    # covers every fragment that kept rows (tests/test_dropin.py checks the flag itself through _aligned*.fa)
     frag_has = np.diff(g["frag_ptr"]) > 0
-    assert np.array_equal(out["fragment_assigned"].astype(bool), frag_has)
+    assert (out["fragment_assigned"].astype(bool) | ~frag_has).all()
     # tree-reduction EM: within the north-star tolerance
     fast = Genotyper(ref, g["similarity"], g["relax"], em_fast_sums=True).Genotype(g["reads1"], g["reads2"])
     assert np.array_equal(fast["equivalent_class"], out["equivalent_class"])
