@@ -8,6 +8,7 @@
 #include <chrono>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/t1k_b200.h"
@@ -77,6 +78,18 @@ struct PinnedMem {
     if (e == cudaSuccess) bytes = n;
     return e;
   }
+  // grow to at least n bytes keeping the first `keep` bytes
+  cudaError_t grow(size_t n, size_t keep) {
+    if (n <= bytes) return cudaSuccess;
+    size_t want = std::max(n, bytes + bytes / 2);
+    void *q = nullptr;
+    cudaError_t e = cudaMallocHost(&q, want);
+    if (e != cudaSuccess) return e;
+    if (p && keep) memcpy(q, p, keep);
+    if (p) cudaFreeHost(p);
+    p = q; bytes = want;
+    return cudaSuccess;
+  }
   template <class T> T *as() const { return (T *)p; }
 };
 
@@ -115,13 +128,14 @@ struct T1KRef {
   size_t scratchWarps = 0;
   u64 nPostings = 0;
   bool covDirty = true;
+  PinnedMem pinEntries[2];   // D2H staging of pairing rows (double-buffered by t1k_genotype's chunk pipeline)
   ~T1KRef() { if (stream) cudaStreamDestroy(stream); }
 };
 
 struct T1KAssignment {
   T1KRef *ref = nullptr;
   u32 nReads = 0;
-  DevMem store, storeCtr, readOff, readCnt, readRet;
+  DevMem store, storeCtr, readOff, readCnt, readRet, dMaxCnt;
   u64 storeCap = 0, storeUsed = 0;
   u32 maxCnt = 0;
   unsigned long long stats[4] = {0, 0, 0, 0};
@@ -208,7 +222,7 @@ int setup_assign_launch(T1KRef *r, int maxLen) {
   int big = maxLen - KMER + 1 + 24;
   if (big < 64) big = 64;
   big = (big + 7) & ~7;
-  int small = 72;
+  int small = 64;
   if (const char *env = getenv("T1K_HIT_TILE")) small = std::max(8, atoi(env));
   if (small > big) small = big;
   if (r->gridBlocks[0] && big <= r->hitCap[1]) return T1K_OK;
@@ -272,7 +286,8 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   CK(dBases.alloc(total)); CK(dOff.alloc((size_t)n * 8)); CK(dLen.alloc((size_t)n * 4)); CK(dW.alloc((size_t)n * 4));
   CK(planes.alloc((size_t)n * 4 * RWORDS * 8)); CK(len16.alloc((size_t)n * 2));
   CK(a->readOff.alloc((size_t)n * 8)); CK(a->readCnt.alloc((size_t)n * 4)); CK(a->readRet.alloc((size_t)n * 4));
-  CK(a->storeCtr.alloc(8));
+  CK(a->storeCtr.alloc(8)); CK(a->dMaxCnt.alloc(4));
+  CK(cudaMemsetAsync(a->dMaxCnt.p, 0, 4, st));
   if (n == 0) { guard.a = nullptr; *out = a; return T1K_OK; }
   CK(cudaMemcpyAsync(dBases.p, bases, total, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dOff.p, off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
@@ -298,6 +313,7 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   P.Q.planes = planes.as<u64>(); P.Q.len = len16.as<u16>(); P.Q.weight = dW.as<int32_t>(); P.Q.workList = nullptr; P.Q.nWork = n;
   P.O.store = a->store.as<Rec>(); P.O.storeCtr = a->storeCtr.as<unsigned long long>(); P.O.storeCap = cap;
   P.O.readOff = a->readOff.as<u64>(); P.O.readCnt = a->readCnt.as<u32>(); P.O.readRet = a->readRet.as<int32_t>();
+  P.O.maxCnt = a->dMaxCnt.as<u32>();
   P.O.err = ref->errFlag.as<int>(); P.O.stats = ref->stats.as<unsigned long long>();
   P.candBuf = ref->candBuf.as<Cand>(); P.candCap = ref->candCap; P.laneScratch = ref->laneScratch.as<u8>();
   P.workCtr = ref->workCtr.as<unsigned int>();
@@ -371,6 +387,7 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   unsigned long long used = 0;
   CK(cudaMemcpy(&used, a->storeCtr.p, 8, cudaMemcpyDeviceToHost));
   a->storeUsed = used;
+  CK(cudaMemcpy(&a->maxCnt, a->dMaxCnt.p, 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(a->stats, ref->stats.p, sizeof(a->stats), cudaMemcpyDeviceToHost));
   guard.a = nullptr;
   *out = a;
@@ -530,8 +547,11 @@ namespace {
 // Pairing of fragments [0, nFrag) against the resident lists of `a`.  Rows come back in allele order;
 // `wantOrder` additionally returns the keys that give the reference's own row order.
 struct PairHost {
-  std::vector<u64> rowPtr;            // [nFrag + 1]
-  std::vector<HostEntry> entries;
+  std::vector<u64> rowOff;            // [nFrag] first entry of the fragment's row (rows are dense but in no fragment order)
+  std::vector<u32> rowCnt;            // [nFrag]
+  PinnedMem *pin = nullptr;           // rows land here (pinned: the D2H copy runs at link speed, nothing is zero-filled)
+  size_t nEntries = 0;
+  HostEntry *entries() const { return pin->as<HostEntry>(); }
   std::vector<u64> ordKey; std::vector<u32> ordIdx;
   std::vector<u8> assigned;           // [nFrag] fragmentAssignment.size() > 0 (before the SetReadAssignments cuts)
   float msKernel = 0;
@@ -541,96 +561,75 @@ struct PairHost {
 int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const uint32_t *end2, const uint8_t *hasN, uint32_t nFrag,
                    int maxAssign, bool wantOrder, PairHost &H) {
   cudaStream_t st = ref->stream;
-  H.rowPtr.assign((size_t)nFrag + 1, 0);
+  H.rowOff.assign(nFrag, 0); H.rowCnt.assign(nFrag, 0);
   H.assigned.assign(nFrag, 0);
-  H.entries.clear(); H.ordKey.clear(); H.ordIdx.clear();
+  H.nEntries = 0; H.ordKey.clear(); H.ordIdx.clear();
   if (nFrag == 0) return T1K_OK;
   for (uint32_t i = 0; i < nFrag; ++i)
     if (end1[i] >= a->nReads || (end2 && end2[i] >= a->nReads)) return fail(T1K_ERR_ARG, "t1k_pair_batch: read-end index out of range");
-  DevMem dE1, dE2, dN, dUb, dRowOff, dRowCnt, dDstOff, dOut, dKey, dIdx, dCompact, dCKey, dCIdx, dCtr;
+  DevMem dE1, dE2, dN, dRowOff, dRowCnt, dOut, dKey, dIdx, dCtr, dOutCtr, dB0;
   CK(dE1.alloc((size_t)nFrag * 4));
   CK(cudaMemcpyAsync(dE1.p, end1, (size_t)nFrag * 4, cudaMemcpyHostToDevice, st));
   if (end2) { CK(dE2.alloc((size_t)nFrag * 4)); CK(cudaMemcpyAsync(dE2.p, end2, (size_t)nFrag * 4, cudaMemcpyHostToDevice, st)); }
   if (hasN) { CK(dN.alloc(nFrag)); CK(cudaMemcpyAsync(dN.p, hasN, nFrag, cudaMemcpyHostToDevice, st)); }
-  CK(dUb.alloc((size_t)nFrag * 4)); CK(dCtr.alloc(4));
-  k_pair_bound<<<(nFrag + 255) / 256, 256, 0, st>>>(a->readCnt.as<u32>(), dE1.as<u32>(), end2 ? dE2.as<u32>() : nullptr, 0, nFrag, maxAssign, dUb.as<u32>());
-  CK(cudaGetLastError());
-  std::vector<u32> ub(nFrag);
-  CK(cudaMemcpyAsync(ub.data(), dUb.p, (size_t)nFrag * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  // sub-batches bounded by the upper-bound row space
-  size_t freeB = 0, totB = 0;
-  CK(cudaMemGetInfo(&freeB, &totB));
-  const size_t perSlot = sizeof(PairEntry) * 2 + (wantOrder ? 24 : 0);
-  u64 slotCap = std::max<u64>(1u << 20, std::min<u64>((u64)(freeB * 0.5) / perSlot, 1ull << 28));
+  CK(dCtr.alloc(4)); CK(dOutCtr.alloc(8));
+  CK(dRowOff.alloc((size_t)nFrag * 8)); CK(dRowCnt.alloc((size_t)nFrag * 4));
   cudaEvent_t ev0, ev1;
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
   struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
-  std::vector<u64> rowOff, dstOff; std::vector<u32> rowCnt;
-  u64 allocSlots = 0, allocDense = 0;
-  for (u32 f0 = 0; f0 < nFrag;) {
-    u32 f1 = f0; u64 slots = 0;
-    while (f1 < nFrag && (f1 == f0 || slots + ub[f1] <= slotCap)) { slots += ub[f1]; ++f1; }
-    const u32 m = f1 - f0;
-    rowOff.resize(m);
-    { u64 s = 0; for (u32 i = 0; i < m; ++i) { rowOff[i] = s; s += ub[f0 + i]; } }
-    if (slots > allocSlots) {
-      allocSlots = slots;
-      CK(dOut.alloc(slots * sizeof(PairEntry)));
-      if (wantOrder) { CK(dKey.alloc(slots * 8)); CK(dIdx.alloc(slots * 4)); }
-    }
-    CK(dRowOff.alloc((size_t)m * 8)); CK(dRowCnt.alloc((size_t)m * 4)); CK(dDstOff.alloc((size_t)m * 8));
-    CK(cudaMemcpyAsync(dRowOff.p, rowOff.data(), (size_t)m * 8, cudaMemcpyHostToDevice, st));
+  // output rows are appended through a device counter; a first guess of the capacity, then (rarely) one exact re-run
+  size_t freeB = 0, totB = 0;
+  CK(cudaMemGetInfo(&freeB, &totB));
+  const size_t perEntry = sizeof(PairEntry) + (wantOrder ? 12 : 0);
+  u64 cap = std::max<u64>(1u << 20, (u64)nFrag * 192);
+  if (const char *env = getenv("T1K_PAIR_ROWS")) cap = std::max<u64>(64, strtoull(env, nullptr, 10));
+  cap = std::min<u64>(cap, (u64)(freeB * 0.6) / perEntry);
+  unsigned long long used = 0;
+  for (int attempt = 0;; ++attempt) {
+    CK(dOut.alloc(cap * sizeof(PairEntry)));
+    if (wantOrder) { CK(dKey.alloc(cap * 8)); CK(dIdx.alloc(cap * 4)); }
     CK(cudaMemsetAsync(dCtr.p, 0, 4, st));
+    CK(cudaMemsetAsync(dOutCtr.p, 0, 8, st));
     PairParams P;
     P.R = ref->R; P.store = a->store.as<Rec>(); P.readOff = a->readOff.as<u64>(); P.readCnt = a->readCnt.as<u32>();
     P.end1 = dE1.as<u32>(); P.end2 = end2 ? dE2.as<u32>() : nullptr; P.hasN = hasN ? dN.as<u8>() : nullptr;
-    P.fragBase = f0; P.nFrag = m; P.maxAssign = maxAssign;
-    P.rowOff = dRowOff.as<u64>(); P.out = dOut.as<PairEntry>();
+    P.fragBase = 0; P.nFrag = nFrag; P.maxAssign = maxAssign;
+    P.out = dOut.as<PairEntry>(); P.outCap = cap; P.outCtr = dOutCtr.as<unsigned long long>(); P.rowOff = dRowOff.as<u64>();
     P.ordKey = wantOrder ? dKey.as<u64>() : nullptr; P.ordIdx = wantOrder ? dIdx.as<u32>() : nullptr;
     P.rowCnt = dRowCnt.as<u32>(); P.rowHash = nullptr; P.workCtr = dCtr.as<unsigned int>();
-    const int blocks = std::max(1, std::min<int>((int)((m + 3) / 4), ref->nSM * 8));
+    const int blocks = std::max(1, std::min<int>((int)((nFrag + 3) / 4), ref->nSM * 8));
+    // per-warp scratch: where each allele run of the first mate's list starts in the second mate's list
+    const size_t b0Stride = ((size_t)a->maxCnt + 32) & ~(size_t)31;
+    if (attempt == 0) CK(dB0.alloc((size_t)blocks * 4 * b0Stride * 4));
+    P.b0 = dB0.as<u32>(); P.b0Stride = (u32)b0Stride;
     CK(cudaEventRecord(ev0, st));
     k_pair<<<blocks, 128, 0, st>>>(P);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ev1, st));
-    rowCnt.resize(m);
-    CK(cudaMemcpyAsync(rowCnt.data(), dRowCnt.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&used, dOutCtr.p, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    float ms = 0; CK(cudaEventElapsedTime(&ms, ev0, ev1)); H.msKernel += ms; H.launches += 2;
-    dstOff.resize(m);
-    u64 dense = 0;
-    for (u32 i = 0; i < m; ++i) {
-      const u32 c = rowCnt[i] & 0x7fffffffu;
-      H.assigned[(size_t)f0 + i] = (u8)(rowCnt[i] >> 31);
-      dstOff[i] = dense; dense += c; H.rowPtr[(size_t)f0 + i + 1] = c;
-    }
-    if (dense > 0) {
-      if (dense > allocDense) {
-        allocDense = dense;
-        CK(dCompact.alloc(dense * sizeof(PairEntry)));
-        if (wantOrder) { CK(dCKey.alloc(dense * 8)); CK(dCIdx.alloc(dense * 4)); }
-      }
-      CK(cudaMemcpyAsync(dDstOff.p, dstOff.data(), (size_t)m * 8, cudaMemcpyHostToDevice, st));
-      const size_t threads = (size_t)m * 32;
-      k_pair_compact<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(dOut.as<PairEntry>(), dRowOff.as<u64>(), dDstOff.as<u64>(), dRowCnt.as<u32>(), m,
-                                                                        dCompact.as<PairEntry>(), wantOrder ? dKey.as<u64>() : nullptr,
-                                                                        wantOrder ? dIdx.as<u32>() : nullptr, wantOrder ? dCKey.as<u64>() : nullptr,
-                                                                        wantOrder ? dCIdx.as<u32>() : nullptr);
-      CK(cudaGetLastError());
-      const size_t base = H.entries.size();
-      H.entries.resize(base + dense);
-      CK(cudaMemcpyAsync(H.entries.data() + base, dCompact.p, dense * sizeof(PairEntry), cudaMemcpyDeviceToHost, st));
-      if (wantOrder) {
-        H.ordKey.resize(base + dense); H.ordIdx.resize(base + dense);
-        CK(cudaMemcpyAsync(H.ordKey.data() + base, dCKey.p, dense * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(H.ordIdx.data() + base, dCIdx.p, dense * 4, cudaMemcpyDeviceToHost, st));
-      }
-      CK(cudaStreamSynchronize(st));
-    }
-    f0 = f1;
+    float ms = 0; CK(cudaEventElapsedTime(&ms, ev0, ev1)); H.msKernel += ms; H.launches += 1;
+    if (used <= cap) break;
+    if (attempt >= 2 || used * perEntry > (u64)(freeB * 0.9)) return fail(T1K_ERR_UNSUPPORTED, "fragment rows do not fit in device memory; use smaller batches");
+    cap = used;
   }
-  for (u32 i = 0; i < nFrag; ++i) H.rowPtr[i + 1] += H.rowPtr[i];
+  CK(cudaMemcpyAsync(H.rowOff.data(), dRowOff.p, (size_t)nFrag * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(H.rowCnt.data(), dRowCnt.p, (size_t)nFrag * 4, cudaMemcpyDeviceToHost, st));
+  if (used > 0) {
+    CK(H.pin->grow(used * sizeof(HostEntry), 0));
+    CK(cudaMemcpyAsync(H.entries(), dOut.p, used * sizeof(PairEntry), cudaMemcpyDeviceToHost, st));
+    if (wantOrder) {
+      H.ordKey.resize(used); H.ordIdx.resize(used);
+      CK(cudaMemcpyAsync(H.ordKey.data(), dKey.p, used * 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(H.ordIdx.data(), dIdx.p, used * 4, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CK(cudaStreamSynchronize(st));
+  H.nEntries = used;
+  for (u32 i = 0; i < nFrag; ++i) {
+    H.assigned[i] = (u8)(H.rowCnt[i] >> 31);
+    H.rowCnt[i] &= 0x7fffffffu;
+  }
   return T1K_OK;
 }
 
@@ -645,20 +644,22 @@ int t1k_pair_batch(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
   static_assert(sizeof(T1KReadAssignment) == sizeof(HostEntry) && sizeof(HostEntry) == sizeof(PairEntry), "layout");
   CK(cudaSetDevice(ref->device));
   PairHost H;
+  H.pin = &ref->pinEntries[0];
   if (int rc = pair_fragments(ref, a, end1, end2, has_n, n_frag, max_assign, true, H)) return rc;
   uint64_t *rp = (uint64_t *)malloc(((size_t)n_frag + 1) * 8);
-  T1KReadAssignment *en = (T1KReadAssignment *)malloc(std::max<size_t>(1, H.entries.size()) * sizeof(T1KReadAssignment));
+  T1KReadAssignment *en = (T1KReadAssignment *)malloc(std::max<size_t>(1, H.nEntries) * sizeof(T1KReadAssignment));
   if (!rp || !en) { free(rp); free(en); return fail(T1K_ERR_ARG, "out of host memory"); }
-  memcpy(rp, H.rowPtr.data(), ((size_t)n_frag + 1) * 8);
+  rp[0] = 0;
+  for (uint32_t f = 0; f < n_frag; ++f) rp[f + 1] = rp[f] + H.rowCnt[f];
   // the reference's row order: by the list position of each allele's first candidate (SeqSet.hpp:2440-2455)
   std::vector<u32> idx;
   for (uint32_t f = 0; f < n_frag; ++f) {
-    const u64 b = H.rowPtr[f], e = H.rowPtr[f + 1];
-    idx.resize(e - b);
+    const u64 src = H.rowOff[f], n = H.rowCnt[f], dst = rp[f];
+    idx.resize(n);
     std::iota(idx.begin(), idx.end(), 0u);
-    const u64 *k = H.ordKey.data() + b; const u32 *ki = H.ordIdx.data() + b;
+    const u64 *k = H.ordKey.data() + src; const u32 *ki = H.ordIdx.data() + src;
     std::sort(idx.begin(), idx.end(), [k, ki](u32 x, u32 y) { return k[x] != k[y] ? k[x] < k[y] : ki[x] < ki[y]; });
-    for (u64 j = 0; j < e - b; ++j) memcpy(&en[b + j], &H.entries[b + idx[j]], sizeof(HostEntry));
+    for (u64 j = 0; j < n; ++j) memcpy(&en[dst + j], H.entries() + src + idx[j], sizeof(HostEntry));
   }
   if (fragment_assigned && n_frag) memcpy(fragment_assigned, H.assigned.data(), n_frag);
   *row_ptr = rp; *entries = en;
@@ -921,90 +922,110 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   if (!ref || !reads1 || !prm || !res || stride == 0 || !prm->effective_len) return fail(T1K_ERR_ARG, "t1k_genotype: bad argument");
   CK(cudaSetDevice(ref->device));
   const int32_t nA = ref->nAlleles;
-  double t0 = now_ms();
-  // ---- unique read-ends (Genotyper.cpp:450-454: the reference sorts; only the grouping matters)
-  const size_t nEnds = (size_t)n_frag * (reads2 ? 2 : 1);
-  auto end_ptr = [&](size_t i) { return i < n_frag ? reads1 + i * stride : reads2 + (i - n_frag) * stride; };
-  std::vector<u32> endLen(nEnds), uniqOf(nEnds);
-  std::vector<u8> fragHasN(n_frag, 0);
-  std::vector<size_t> uniqRep;   // representative end of each unique sequence
-  {
-    size_t tabSize = 16; while (tabSize < nEnds * 2) tabSize <<= 1;
-    std::vector<u32> table(tabSize, 0xffffffffu);
-    for (size_t i = 0; i < nEnds; ++i) {
-      const char *s = end_ptr(i);
-      u32 L = 0; u64 h = 1469598103934665603ull; bool hasN = false;
-      while (L < stride && s[L]) { h = (h ^ (u8)s[L]) * 1099511628211ull; hasN |= s[L] == 'N'; ++L; }
-      if (L > T1K_MAX_READ_LEN) return fail(T1K_ERR_ARG, "read longer than T1K_MAX_READ_LEN");
-      endLen[i] = L;
-      if (hasN) fragHasN[i < n_frag ? i : i - n_frag] = 1;
-      size_t slot = (size_t)(h ^ (h >> 29)) & (tabSize - 1);
-      for (;;) {
-        const u32 u = table[slot];
-        if (u == 0xffffffffu) { table[slot] = (u32)uniqRep.size(); uniqOf[i] = (u32)uniqRep.size(); uniqRep.push_back(i); break; }
-        const size_t rep = uniqRep[u];
-        if (endLen[rep] == L && memcmp(end_ptr(rep), s, L) == 0) { uniqOf[i] = u; break; }
-        slot = (slot + 1) & (tabSize - 1);
+  // ---- fragments in chunks through a three-stage pipeline (host prep | device align + pair | host coalesce):
+  //   prep      unique read-ends of the chunk (Genotyper.cpp:450-454 sorts; only the grouping matters) + batch layout
+  //   device    t1k_assign_batch + pairing kernels, rows copied into pinned memory
+  //   coalesce  Genotyper::CoalesceReadAssignments, serial and in chunk order
+  // While the device works on chunk c, helper threads prepare chunk c+1 and coalesce chunk c-1.
+  u32 chunk = 1u << 18;
+  if (const char *env = getenv("T1K_CHUNK_FRAGMENTS")) chunk = (u32)std::max(1l, atol(env));
+  struct Prep {
+    u32 f0 = 0, m = 0;
+    std::vector<u32> e1, e2, table;
+    std::vector<int32_t> w;
+    std::vector<uint64_t> off; std::vector<uint32_t> len; std::vector<char> bases;
+    std::vector<u8> hasN;
+    std::vector<const char *> rep;
+    bool tooLong = false;
+    double ms = 0;
+  } prep[2];
+  const int mates = reads2 ? 2 : 1;
+  auto do_prep = [&](Prep &C, u32 f0, u32 m) {
+    const double t = now_ms();
+    C.f0 = f0; C.m = m; C.tooLong = false;
+    C.e1.resize(m); if (reads2) C.e2.resize(m);
+    C.hasN.assign(m, 0); C.w.clear(); C.rep.clear(); C.len.clear();
+    size_t tabSize = 16; while (tabSize < (size_t)m * mates * 2) tabSize <<= 1;
+    C.table.assign(tabSize, 0xffffffffu);
+    for (u32 i = 0; i < m; ++i) {
+      for (int mate = 0; mate < mates; ++mate) {
+        const char *s = (mate ? reads2 : reads1) + (size_t)(f0 + i) * stride;
+        u32 L = 0; u64 h = 1469598103934665603ull; bool hasN = false;
+        while (L < stride && s[L]) { h = (h ^ (u8)s[L]) * 1099511628211ull; hasN |= s[L] == 'N'; ++L; }
+        if (L > T1K_MAX_READ_LEN) { C.tooLong = true; L = T1K_MAX_READ_LEN; }
+        if (hasN) C.hasN[i] = 1;
+        size_t slot = (size_t)(h ^ (h >> 29)) & (tabSize - 1);
+        u32 u;
+        for (;;) {
+          u = C.table[slot];
+          if (u == 0xffffffffu) { u = (u32)C.rep.size(); C.table[slot] = u; C.rep.push_back(s); C.len.push_back(L); C.w.push_back(0); break; }
+          if (C.len[u] == L && memcmp(C.rep[u], s, L) == 0) break;
+          slot = (slot + 1) & (tabSize - 1);
+        }
+        ++C.w[u];                                   // Genotyper.cpp:149,472: weight = number of duplicates
+        (mate ? C.e2 : C.e1)[i] = u;
       }
     }
-  }
-  const size_t nUniq = uniqRep.size();
-  res->n_unique_ends = nUniq;
-  res->ms_dedup = (float)(now_ms() - t0);
+    C.off.resize(C.rep.size());
+    size_t tot = 0;
+    for (size_t k = 0; k < C.rep.size(); ++k) { C.off[k] = tot; tot += C.len[k]; }
+    C.bases.resize(tot + 1);
+    for (size_t k = 0; k < C.rep.size(); ++k) memcpy(C.bases.data() + C.off[k], C.rep[k], C.len[k]);
+    C.ms = now_ms() - t;
+  };
   CK(cudaMemsetAsync(ref->covDiff.p, 0, ref->paddedBases * 4, ref->stream));
   CK(cudaMemsetAsync(ref->covPoint.p, 0, ref->paddedBases * 4, ref->stream));
   ref->covDirty = true;
-  // ---- fragments in chunks: align the chunk's unique read-ends, pair on the device, coalesce on the host
-  u32 chunk = 1u << 18;
-  if (const char *env = getenv("T1K_CHUNK_FRAGMENTS")) chunk = (u32)std::max(1l, atol(env));
   ReadGroups groups;
-  std::vector<u32> localId(nUniq, 0xffffffffu), chunkUniq, e1, e2;
-  std::vector<int32_t> w;
-  std::vector<uint64_t> off; std::vector<uint32_t> len; std::vector<char> bases;
-  res->n_overlaps = 0; res->n_assignments = 0;
-  res->ms_align = res->ms_pair = res->ms_coalesce = res->ms_em = 0;
+  res->n_unique_ends = 0; res->n_overlaps = 0; res->n_assignments = 0;
+  res->ms_dedup = res->ms_align = res->ms_pair = res->ms_coalesce = res->ms_em = 0;
   res->ms_align_kernel = res->ms_pair_kernel = res->ms_em_kernel = 0;
   res->n_postings = res->n_candidates = 0; res->n_launches = 0;
-  if (res->fragment_assigned) memset(res->fragment_assigned, 0, n_frag);
-  for (u32 f0 = 0; f0 < n_frag; f0 += chunk) {
-    const u32 m = std::min(chunk, n_frag - f0);
-    chunkUniq.clear(); w.clear(); e1.resize(m); if (reads2) e2.resize(m);
+  PairHost pairOut[2];
+  pairOut[0].pin = &ref->pinEntries[0]; pairOut[1].pin = &ref->pinEntries[1];
+  double msCoalesce = 0;
+  auto do_coalesce = [&](const PairHost &H, u32 f0, u32 m) {
+    const double t = now_ms();
+    const HostEntry *ent = H.entries();
     for (u32 i = 0; i < m; ++i) {
-      for (int mate = 0; mate < (reads2 ? 2 : 1); ++mate) {
-        const u32 u = uniqOf[(size_t)f0 + i + (mate ? n_frag : 0)];
-        if (localId[u] == 0xffffffffu) { localId[u] = (u32)chunkUniq.size(); chunkUniq.push_back(u); w.push_back(0); }
-        ++w[localId[u]];
-        (mate ? e2 : e1)[i] = localId[u];
-      }
+      if (H.rowCnt[i]) groups.add(ent + H.rowOff[i], H.rowCnt[i]);
+      if (res->fragment_assigned) res->fragment_assigned[f0 + i] = H.assigned[i];
     }
-    off.resize(chunkUniq.size()); len.resize(chunkUniq.size());
-    size_t tot = 0;
-    for (size_t k = 0; k < chunkUniq.size(); ++k) { off[k] = tot; len[k] = endLen[uniqRep[chunkUniq[k]]]; tot += len[k]; }
-    bases.resize(tot + 1);
-    for (size_t k = 0; k < chunkUniq.size(); ++k) memcpy(bases.data() + off[k], end_ptr(uniqRep[chunkUniq[k]]), len[k]);
-    for (size_t k = 0; k < chunkUniq.size(); ++k) localId[chunkUniq[k]] = 0xffffffffu;
+    msCoalesce += now_ms() - t;
+  };
+  std::thread prepThread, coalThread;
+  struct Joiner { std::thread &a, &b; ~Joiner() { if (a.joinable()) a.join(); if (b.joinable()) b.join(); } } joiner{prepThread, coalThread};
+  const u32 nChunks = n_frag ? (n_frag + chunk - 1) / chunk : 0;
+  if (nChunks) do_prep(prep[0], 0, std::min(chunk, n_frag));
+  for (u32 c = 0; c < nChunks; ++c) {
+    Prep &C = prep[c & 1];
+    res->ms_dedup += (float)C.ms;
+    if (c + 1 < nChunks) {
+      const u32 f0n = (c + 1) * chunk;
+      prepThread = std::thread(do_prep, std::ref(prep[(c + 1) & 1]), f0n, std::min(chunk, n_frag - f0n));
+    }
+    if (C.tooLong) return fail(T1K_ERR_ARG, "read longer than T1K_MAX_READ_LEN");
+    res->n_unique_ends += C.rep.size();
     double ta = now_ms();
     T1KAssignment *a = nullptr;
-    if (int rc = t1k_assign_batch(ref, bases.data(), off.data(), len.data(), w.data(), (uint32_t)chunkUniq.size(), &a)) return rc;
+    if (int rc = t1k_assign_batch(ref, C.bases.data(), C.off.data(), C.len.data(), C.w.data(), (uint32_t)C.rep.size(), &a)) return rc;
     struct AG { T1KAssignment *a; ~AG() { t1k_assignment_destroy(a); } } ag{a};
     res->ms_align += (float)(now_ms() - ta);
     res->n_overlaps += a->storeUsed;
     res->ms_align_kernel += a->msKernel; res->n_postings += a->stats[0]; res->n_candidates += a->stats[1];
     res->n_launches += 2 + a->launches;
     double tp = now_ms();
-    PairHost H;
-    if (int rc = pair_fragments(ref, a, e1.data(), reads2 ? e2.data() : nullptr, fragHasN.data() + f0, m, prm->max_assign, false, H)) return rc;
+    PairHost &H = pairOut[c & 1];     // last read by the coalescing of chunk c-2, which has been joined
+    if (int rc = pair_fragments(ref, a, C.e1.data(), reads2 ? C.e2.data() : nullptr, C.hasN.data(), C.m, prm->max_assign, false, H)) return rc;
     res->ms_pair += (float)(now_ms() - tp);
     res->ms_pair_kernel += H.msKernel; res->n_launches += H.launches;
-    double tc = now_ms();
-    for (u32 i = 0; i < m; ++i) {
-      const u64 b = H.rowPtr[i], e = H.rowPtr[i + 1];
-      if (e > b) groups.add(H.entries.data() + b, (uint32_t)(e - b));
-      if (res->fragment_assigned) res->fragment_assigned[f0 + i] = H.assigned[i];
-    }
-    res->n_assignments += H.entries.size();
-    res->ms_coalesce += (float)(now_ms() - tc);
+    res->n_assignments += H.nEntries;
+    if (coalThread.joinable()) coalThread.join();
+    coalThread = std::thread(do_coalesce, std::cref(H), C.f0, C.m);
+    if (prepThread.joinable()) prepThread.join();
   }
+  if (coalThread.joinable()) coalThread.join();
+  res->ms_coalesce = (float)msCoalesce;
   // ---- read-sharded run: total coverage, every rank's read groups merged in rank order
   T1KComm *comm = (prm->comm && prm->comm->world > 1) ? prm->comm : nullptr;
   uint64_t nAssignAll = res->n_assignments;

@@ -385,11 +385,12 @@ T1K_HDN T1K_NOINLINE inline int dp_align(const AlleleView &T, int tpos, int lent
   return n;
 }
 
-// number of EDIT_MATCH columns of GlobalAlignment(t, lent, p, lenp)  (GetAlignStats, SeqSet.hpp:438-455)
-T1K_HDN T1K_NOINLINE inline int align_matches(const AlleleView &T, int tpos, int lent, const ReadView &Q, int ppos, int lenp,
-                                 const LaneScratch &S, int &err) {
-  if (lent == 0 || lenp == 0) return 0;
-  T1K_COUNT(4, 1);
+// number of EDIT_MATCH columns of GlobalAlignment(t, lent, p, lenp)  (GetAlignStats, SeqSet.hpp:438-455).
+// Hot/cold split: nearly every call is an equal-length stretch of <= 32 columns with <= 3 mismatches (the gap between two
+// seed hits, or a read overhang) and is answered by one XOR + popcount; everything else lives in the cold function so
+// that the hot instruction footprint stays small (the kernel is instruction-cache sensitive).
+T1K_HDN T1K_NOINLINE inline int align_matches_cold(const AlleleView &T, int tpos, int lent, const ReadView &Q, int ppos, int lenp,
+                                      const LaneScratch &S, int &err) {
   if (lent == lenp) {
     int mm;
     if (diag_certified(T, tpos, Q, ppos, lent, mm)) return lent - mm;
@@ -401,6 +402,16 @@ T1K_HDN T1K_NOINLINE inline int align_matches(const AlleleView &T, int tpos, int
   T1K_NOUNROLL
   for (int i = 0; i < n; ++i) c += ops[i] == 0;
   return c;
+}
+T1K_HDN T1K_NOINLINE inline int align_matches(const AlleleView &T, int tpos, int lent, const ReadView &Q, int ppos, int lenp, const LaneScratch &S,
+                                 int &err) {
+  if (lent == 0 || lenp == 0) return 0;
+  T1K_COUNT(4, 1);
+  if (lent == lenp && lent <= 32) {
+    const int mm = popc64(mm_chunk(T, tpos, Q, ppos, lent));
+    if (mm <= 3) return lent - mm;
+  }
+  return align_matches_cold(T, tpos, lent, Q, ppos, lenp, S, err);
 }
 
 // any N inside [s, e] of an N plane that starts at the allele's first word
@@ -489,8 +500,31 @@ T1K_HDN T1K_NOINLINE inline void consume_chain(const RefView &R, const ReadView 
   u64 sk = strand_key(2 * hitLen, re - rs, seqIdx, strand01);
   if (sk > bestStrandKey) bestStrandKey = sk;
   int mc;
-  if (OneDiag && nGap == 0) mc = 2 * hitLen;       // every step overlaps: 2k + sum of 2*(a - pa)
-  else {
+  if (OneDiag) {
+    // every overlapping step adds 2*(a - pa), every gap 2k + 2*matches(gap): mc = 2*hitLen + 2*sum(matches).  The walk
+    // stops at each gap, so that the lanes of a warp reach their (divergent, expensive) gap comparisons together.
+    mc = 2 * hitLen;
+    if (nGap > 0) {
+      const AlleleView T = allele_view(R, seqIdx, Q);
+      const int dg = ss - rs;
+      int j = 1;
+      pa = rs;
+      T1K_NOUNROLL
+      for (;;) {
+        int a = 0;
+        T1K_NOUNROLL
+        while (j < sz) {
+          a = hit_a(C(j));
+          if (a > pa + KMER - 1) break;
+          pa = a; ++j;
+        }
+        if (j >= sz) break;
+        const int g = a - (pa + KMER);
+        mc += 2 * align_matches(T, pa + dg + KMER, g, Q, pa + KMER, g, S, err);
+        pa = a; ++j;
+      }
+    }
+  } else {
     const AlleleView T = allele_view(R, seqIdx, Q);
     mc = 2 * KMER;
     pa = rs; pb = ss;
@@ -499,7 +533,7 @@ T1K_HDN T1K_NOINLINE inline void consume_chain(const RefView &R, const ReadView 
       const u32 h = C(j);
       const int a = hit_a(h), b = hit_b(h);
       const bool aOv = pa + KMER - 1 >= a, bOv = pb + KMER - 1 >= b;
-      if (OneDiag || pb - pa == b - a) {
+      if (pb - pa == b - a) {
         if (aOv) mc += 2 * (a - pa);
         else mc += 2 * KMER + 2 * align_matches(T, pb + KMER, b - (pb + KMER), Q, pa + KMER, a - (pa + KMER), S, err);
       } else if (aOv && !bOv) mc += 2 * (a - pa);
@@ -687,31 +721,15 @@ T1K_HD void cov_add(int32_t *p, int v) {
 // ---- full-read alignment of an extended overlap (SeqSet.hpp:2203-2274): exon-relaxed match count and
 // base coverage.  Coverage is kept as a range-add difference array plus point corrections, so a
 // certified-diagonal record costs 2 + (#uncredited columns) atomics instead of one per base.
-// One pass over the window: mismatch count, exonic mismatch count and (while <= 3, which certifies the diagonal)
-// the mismatch positions themselves; only 4+ mismatches or N columns need a second look at the window.
-T1K_HDN T1K_NOINLINE inline void full_align(const RefView &R, const ReadView &Q, Cand &c, int weight, const LaneScratch &S, int &err) {
-  const AlleleView T = allele_view(R, c.seqIdx, Q);
+// Hot path (full_align): one pass over the window — mismatch count, exonic mismatch count and the first three mismatch
+// positions; <= 3 mismatches certify the diagonal and, without N columns, those positions are the uncredited columns.
+// Cold path (full_align_cold): 4+ mismatches (certificates, DP) and windows with N columns.
+T1K_HDN T1K_NOINLINE inline void full_align_cold(const RefView &R, const ReadView &Q, const AlleleView &T, Cand &c, int weight, int mm, int exMm,
+                                    const LaneScratch &S, int &err) {
   const int tpos = c.eSeqStart, ppos = c.eReadStart;
   const int lent = c.eSeqEnd - c.eSeqStart + 1, lenp = c.eReadEnd - c.eReadStart + 1;
   int32_t *covDiff = R.covDiff + (size_t)R.wordOff[c.seqIdx] * 32, *covPoint = R.covPoint + (size_t)R.wordOff[c.seqIdx] * 32;
-  T1K_COUNT(6, 1);
   if (lent == lenp) {
-    int mm = 0, exMm = 0, p0 = 0, p1 = 0, p2 = 0;
-    T1K_NOUNROLL
-    for (int k = 0; k < lent; k += 32) {
-      u64 d = mm_chunk(T, tpos + k, Q, ppos + k, lent - k);
-      if (d) {
-        if (R.relax) exMm += popc64(d & fetch32(T.ex2, tpos + k));
-        T1K_NOUNROLL
-        while (d && mm < 3) {
-          const int p = k + (ctz64(d) >> 1);
-          d &= d - 1;
-          if (mm == 0) p0 = p; else if (mm == 1) p1 = p; else p2 = p;
-          ++mm;
-        }
-        mm += popc64(d);
-      }
-    }
     bool diag = mm <= 3;
     if (!diag) {
       if (mm <= 5) diag = diag_certified_45(T, tpos, Q, ppos, lent, mm);
@@ -720,21 +738,15 @@ T1K_HDN T1K_NOINLINE inline void full_align(const RefView &R, const ReadView &Q,
     if (diag) {
       if (weight > 0) {
         cov_add(covDiff + tpos, weight); cov_add(covDiff + tpos + lent, -weight);
-        if (mm <= 3 && !T.useN) {       // the uncredited columns are exactly the recorded mismatches
-          if (mm > 0) cov_add(covPoint + tpos + p0, -weight);
-          if (mm > 1) cov_add(covPoint + tpos + p1, -weight);
-          if (mm > 2) cov_add(covPoint + tpos + p2, -weight);
-        } else {
+        T1K_NOUNROLL
+        for (int k = 0; k < lent; k += 32) {
+          u64 un = mm_chunk(T, tpos + k, Q, ppos + k, lent - k);
+          if (T.useN) un |= (fetch32(T.n2, tpos + k) | fetch32(Q.n2, ppos + k)) & lowmask2(lent - k);
           T1K_NOUNROLL
-          for (int k = 0; k < lent; k += 32) {
-            u64 un = mm_chunk(T, tpos + k, Q, ppos + k, lent - k);
-            if (T.useN) un |= (fetch32(T.n2, tpos + k) | fetch32(Q.n2, ppos + k)) & lowmask2(lent - k);
-            T1K_NOUNROLL
-            while (un) {
-              const int p = k + (ctz64(un) >> 1);
-              un &= un - 1;
-              cov_add(covPoint + tpos + p, -weight);
-            }
+          while (un) {
+            const int p = k + (ctz64(un) >> 1);
+            un &= un - 1;
+            cov_add(covPoint + tpos + p, -weight);
           }
         }
       }
@@ -761,6 +773,43 @@ T1K_HDN T1K_NOINLINE inline void full_align(const RefView &R, const ReadView &Q,
     if (op != 3) ++readPos;
   }
   c.relaxed = R.relax ? 2 * m : c.eMatchCnt;
+}
+
+T1K_HDN T1K_NOINLINE inline void full_align(const RefView &R, const ReadView &Q, Cand &c, int weight, const LaneScratch &S, int &err) {
+  const AlleleView T = allele_view(R, c.seqIdx, Q);
+  const int tpos = c.eSeqStart, ppos = c.eReadStart;
+  const int lent = c.eSeqEnd - c.eSeqStart + 1, lenp = c.eReadEnd - c.eReadStart + 1;
+  T1K_COUNT(6, 1);
+  int mm = 0, exMm = 0, p0 = 0, p1 = 0, p2 = 0;
+  if (lent == lenp) {
+    T1K_NOUNROLL
+    for (int k = 0; k < lent; k += 32) {
+      u64 d = mm_chunk(T, tpos + k, Q, ppos + k, lent - k);
+      if (d) {
+        if (R.relax) exMm += popc64(d & fetch32(T.ex2, tpos + k));
+        T1K_NOUNROLL
+        while (d && mm < 3) {
+          const int p = k + (ctz64(d) >> 1);
+          d &= d - 1;
+          if (mm == 0) p0 = p; else if (mm == 1) p1 = p; else p2 = p;
+          ++mm;
+        }
+        mm += popc64(d);
+      }
+    }
+    if (mm <= 3 && !T.useN) {
+      if (weight > 0) {
+        int32_t *covDiff = R.covDiff + (size_t)R.wordOff[c.seqIdx] * 32, *covPoint = R.covPoint + (size_t)R.wordOff[c.seqIdx] * 32;
+        cov_add(covDiff + tpos, weight); cov_add(covDiff + tpos + lent, -weight);
+        if (mm > 0) cov_add(covPoint + tpos + p0, -weight);
+        if (mm > 1) cov_add(covPoint + tpos + p1, -weight);
+        if (mm > 2) cov_add(covPoint + tpos + p2, -weight);
+      }
+      c.relaxed = R.relax ? 2 * (lent - exMm) : c.eMatchCnt;
+      return;
+    }
+  }
+  full_align_cold(R, Q, T, c, weight, mm, exMm, S, err);
 }
 
 // post-extension denominators / keys

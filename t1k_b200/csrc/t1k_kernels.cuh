@@ -10,9 +10,15 @@ namespace t1k {
 
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int GATHER_DEPTH = 4;      // posting loads in flight per warp in the tile gather
+constexpr int GATHER_DEPTH = 4;      // stages of the posting-block ring of the tile gather (power of two)
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cp_async8(void *smemDst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct ReadsDev {
   const u64 *planes;       // [(r*4 + plane) * RWORDS]; planes: fwd seq2, fwd n2, rc seq2, rc n2
@@ -28,6 +34,7 @@ struct AssignOut {
   u64 storeCap;
   u64 *readOff;            // per read-end: first record
   u32 *readCnt;
+  u32 *maxCnt;             // longest record list of the batch (sizes the pairing kernel's per-warp scratch)
   int32_t *readRet;        // AssignRead's return value; -2 = deferred (store full), -3 = deferred (hit tile too small)
   int *err;
   unsigned long long *stats;   // [0] postings visited, [1] candidates, [2] tiles, [3] dp calls (debug/roofline)
@@ -119,9 +126,10 @@ struct WarpSmem {
   u32 *H, *cnt, *cur, *end, *nxt;
   u8 *seedA, *act;
   u64 *seq, *nn;
+  Posting *ring;           // GATHER_DEPTH x 32 postings
 };
 __host__ __device__ inline size_t warp_smem_bytes(int hitCap) {
-  return (size_t)hitCap * 32 * 4 + 32 * 4 + 3 * 256 * 4 + 2 * 256 + 2 * RWORDS * 8;
+  return (size_t)hitCap * 32 * 4 + 32 * 4 + 3 * 256 * 4 + 2 * 256 + 2 * RWORDS * 8 + GATHER_DEPTH * 32 * 8;
 }
 
 // returns whether the read holds an N
@@ -132,6 +140,18 @@ __device__ __forceinline__ bool load_planes(const AssignParams &P, u32 r, int st
   else if (lane < 2 * RWORDS) { nw = src[lane]; W.nn[lane - RWORDS] = nw; }   // n2 plane follows the seq plane
   __syncwarp();
   return __any_sync(FULL, nw != 0);
+}
+
+// stage i of the tile gather: the lane's posting of active seed i (or a sentinel) into the ring; always commits a group
+__device__ __forceinline__ void gather_issue(const RefView &R, const WarpSmem &W, int i, int nAct, int lane) {
+  if (i < nAct) {
+    const int k = W.act[i];
+    const u32 c = W.cur[k] + lane;
+    Posting *dst = W.ring + (i & (GATHER_DEPTH - 1)) * 32 + lane;
+    if (c < W.end[k]) cp_async8(dst, R.post + c);
+    else { Posting none; none.idx = 0xffffffffu; none.off = 0; *dst = none; }
+  }
+  cp_async_commit();
 }
 
 __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W, Cand *cands, const LaneScratch &S, int lane) {
@@ -207,37 +227,40 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
           nAct += __popc(bal);
         }
         __syncwarp();
+        // The 256-byte posting blocks of the active seeds stream through a GATHER_DEPTH-stage cp.async ring in shared
+        // memory (each lane copies and later reads its own 8 bytes), so GATHER_DEPTH - 1 blocks are in flight while one
+        // is scattered into the tile; the loop body exists once (its instruction footprint matters).
         T1K_NOUNROLL
-        for (int i0 = 0; i0 < nAct; i0 += GATHER_DEPTH) {
-          // GATHER_DEPTH independent 256-byte posting loads in flight before the first one is consumed
-          Posting pf[GATHER_DEPTH]; u32 cf[GATHER_DEPTH], ef[GATHER_DEPTH]; int kf[GATHER_DEPTH];
-#pragma unroll
-          for (int u = 0; u < GATHER_DEPTH; ++u) {
-            pf[u].idx = 0xffffffffu; pf[u].off = 0; kf[u] = -1; cf[u] = ef[u] = 0;
-            if (i0 + u < nAct) {
-              kf[u] = W.act[i0 + u]; cf[u] = W.cur[kf[u]]; ef[u] = W.end[kf[u]];
-              if (cf[u] + lane < ef[u]) pf[u] = R.post[cf[u] + lane];
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < GATHER_DEPTH; ++u) {
-            if (kf[u] < 0) break;                  // warp-uniform
-            const int k = kf[u];
-            const u32 a = W.seedA[k], e = ef[u];
-            u32 c = cf[u];
-            Posting p = pf[u];
-            T1K_NOUNROLL
-            for (;;) {
-              const bool in = p.idx < base + 32;
-              const unsigned bal = __ballot_sync(FULL, in);
-              const int consumed = __popc(bal);
-              const u32 prevIdx = __shfl_up_sync(FULL, p.idx, 1);
-              const bool startRun = lane == 0 || p.idx != prevIdx;
-              const unsigned sm = __ballot_sync(FULL, startRun);
+        for (int s0 = 0; s0 < GATHER_DEPTH - 1; ++s0) gather_issue(R, W, s0, nAct, lane);
+        T1K_NOUNROLL
+        for (int i = 0; i < nAct; ++i) {
+          gather_issue(R, W, i + GATHER_DEPTH - 1, nAct, lane);
+          cp_async_wait<GATHER_DEPTH - 1>();
+          const int k = W.act[i];
+          const u32 a = W.seedA[k], e = W.end[k];
+          u32 c = W.cur[k];
+          Posting p = W.ring[(i & (GATHER_DEPTH - 1)) * 32 + lane];
+          T1K_NOUNROLL
+          for (;;) {
+            const bool in = p.idx < base + 32;
+            const unsigned bal = __ballot_sync(FULL, in);
+            const int consumed = __popc(bal);
+            const u32 prevIdx = __shfl_up_sync(FULL, p.idx, 1);
+            const bool dup = lane > 0 && p.idx == prevIdx;
+            const u32 local = p.idx - base;
+            if (!__any_sync(FULL, dup && in)) {
+              // every allele of the tile occurs at most once in this block (the usual case): plain scatter
+              if (in) {
+                const u32 slot = W.cnt[local];
+                if ((int)slot < CAP) W.H[slot * 32 + local] = a | (p.off << 8);
+                W.cnt[local] = slot + 1;
+              }
+            } else {
+              // a k-mer repeated inside an allele: rank the postings of each allele run
+              const unsigned sm = __ballot_sync(FULL, !dup);
               const int runStart = 31 - __clz(sm & (0xffffffffu >> (31 - lane)));
               const int rank = lane - runStart;
               const bool lastOfRun = lane == 31 || ((sm >> (lane + 1)) & 1u);
-              const u32 local = p.idx - base;
               u32 slot = 0;
               if (in) {
                 slot = W.cnt[local] + rank;
@@ -245,23 +268,23 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
               }
               __syncwarp();
               if (in && lastOfRun) W.cnt[local] = slot + 1;
-              __syncwarp();
-              const u32 nc = c + consumed;
-              if (consumed == 32 && nc < e) {          // the list continues inside this tile (repeated k-mer)
-                c = nc;
-                p.idx = 0xffffffffu; p.off = 0;
-                if (c + lane < e) p = R.post[c + lane];
-                continue;
-              }
-              const u32 nextIdx = consumed < 32 ? __shfl_sync(FULL, p.idx, consumed) : 0xffffffffu;
-              if (lane == 0) { W.cur[k] = nc; W.nxt[k] = nextIdx; }
-              // the block the next tile will ask for: pull it into L2 now (2 x 128 B lines)
-              if (lane < 2 && nc + lane * 16 < e) prefetch_l2(R.post + nc + lane * 16);
-              break;
             }
+            __syncwarp();
+            const u32 nc = c + consumed;
+            if (consumed == 32 && nc < e) {          // the list continues inside this tile (repeated k-mer)
+              c = nc;
+              p.idx = 0xffffffffu; p.off = 0;
+              if (c + lane < e) p = R.post[c + lane];
+              continue;
+            }
+            const u32 nextIdx = consumed < 32 ? __shfl_sync(FULL, p.idx, consumed) : 0xffffffffu;
+            if (lane == 0) { W.cur[k] = nc; W.nxt[k] = nextIdx; }
+            // the block the next tile will ask for: pull it into L2 now (2 x 128 B lines)
+            if (lane < 2 && nc + lane * 16 < e) prefetch_l2(R.post + nc + lane * 16);
+            break;
           }
-          __syncwarp();
         }
+        cp_async_wait<0>();
         __syncwarp();
         // ---- lane-per-allele chaining + rescoring
         const int n = (int)W.cnt[lane];
@@ -409,6 +432,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
     P.O.readOff[r] = pos;
     P.O.readCnt[r] = (deferred || overflow) ? 0 : (u32)nFinal;
     P.O.readRet[r] = overflow ? -3 : deferred ? -2 : ret;
+    if (nFinal > 0 && !deferred && !overflow) atomicMax(P.O.maxCnt, (u32)nFinal);
     if (deferred) atomicOr(P.O.err, ERR_STORE);
     if (overflow) atomicOr(P.O.err, ERR_HITS);
   }
@@ -433,7 +457,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_assign(AssignParams
   u8 *sm = (u8 *)t1k_smem + (size_t)warp * ((warp_smem_bytes(P.hitCap) + 15) & ~(size_t)15);
   WarpSmem W;
   W.seq = (u64 *)sm; W.nn = W.seq + RWORDS;
-  W.H = (u32 *)(W.nn + RWORDS);
+  W.ring = (Posting *)(W.nn + RWORDS);
+  W.H = (u32 *)(W.ring + GATHER_DEPTH * 32);
   W.cnt = W.H + (size_t)P.hitCap * 32;
   W.cur = W.cnt + 32; W.end = W.cur + 256; W.nxt = W.end + 256;
   W.seedA = (u8 *)(W.nxt + 256); W.act = W.seedA + 256;

@@ -26,14 +26,20 @@ struct PairParams {
   const u8 *hasN;
   u32 fragBase, nFrag;      // fragments [fragBase, fragBase + nFrag) of the caller's arrays
   int maxAssign;
-  const u64 *rowOff;        // per fragment of this launch: first slot in `out` (upper-bound layout)
+  // rows are appended to `out` through one atomic per fragment (dense, in no particular fragment order); if the
+  // buffer is too small nothing is written and *outCtr tells the host the exact capacity for the re-run
   PairEntry *out;
+  u64 outCap;
+  unsigned long long *outCtr;
+  u64 *rowOff;              // per fragment of this launch: first entry of its row in `out`
   u64 *ordKey;              // optional: list position of the allele's first candidate (reference order)
   u32 *ordIdx;
   u32 *rowCnt;              // per fragment of this launch; bit 31 = the fragment had assignments before the
                             // SetReadAssignments cuts (Genotyper.cpp:564 `fragmentAssigned`)
   u64 *rowHash;             // optional, 2 per fragment: order-free hash of the allele set
   unsigned int *workCtr;
+  u32 *b0;                  // per warp, b0Stride entries: start of each first-list allele run in the second list
+  u32 b0Stride;
 };
 
 struct RV { int seqIdx, ss, se, rs, re, lc, rc, mc, st, relaxed; u64 key; };
@@ -91,6 +97,7 @@ struct AlleleBest {
   bool valid;
   int mc, denom, relaxed, ss, se;
   int ia, jb;               // positions in the lists (jb = -1: no mate)
+  int b0;                   // paired: lower_bound of the allele in the second list
   u64 posKey; int posIdx;   // list position of the allele's first candidate = its rank in `assign`
   int relaxBy;
   RV o1;
@@ -105,7 +112,9 @@ __device__ __forceinline__ bool mates_ok(const RV &a, const RV &b) {
 }
 
 // A[a0,a1) is the run of one allele in the first list; paired mode looks the allele up in B.
-__device__ void eval_allele(const RefView &R, bool paired, const Rec *A, int a0, int a1, const Rec *B, int nB, AlleleBest &out) {
+// b0Hint >= 0: the position found by an earlier pass (lower_bound of the allele in B); out.b0 returns it.
+__device__ void eval_allele(const RefView &R, bool paired, const Rec *A, int a0, int a1, const Rec *B, int nB, AlleleBest &out,
+                            int b0Hint = -1) {
   out.valid = false;
   out.posKey = ~0ull; out.posIdx = 0x7fffffff;
   RV bo1, bo2;
@@ -128,7 +137,8 @@ __device__ void eval_allele(const RefView &R, bool paired, const Rec *A, int a0,
     return;
   }
   const int seqIdx = A[a0].seqIdx;
-  const int b0 = lower_bound_allele(B, nB, seqIdx);
+  const int b0 = b0Hint >= 0 ? b0Hint : lower_bound_allele(B, nB, seqIdx);
+  out.b0 = b0;
   if (b0 >= nB || B[b0].seqIdx != seqIdx) return;
   int bmc = 0, bden = 0;
   for (int ia = a0; ia < a1; ++ia) {
@@ -203,6 +213,7 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
   const Rec *A = L1; int nA = n1;
   if (pe && n1 == 0) { A = L2; nA = n2; }
   const Rec *B = paired ? L2 : NULL; const int nB = paired ? n2 : 0;
+  u32 *b0s = P.b0 + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * P.b0Stride;
   u32 cnt = 0;
   bool assigned = false;
   u64 h0 = 0, h1 = 0;
@@ -215,6 +226,7 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
         int a1 = i + 1;
         while (a1 < nA && A[a1].seqIdx == A[i].seqIdx) ++a1;
         AlleleBest ab; eval_allele(R, paired, A, i, a1, B, nB, ab);
+        if (paired) b0s[i] = (u32)ab.b0;
         if (ab.valid) k1 = max(k1, ((u32)ab.mc << 12) | (u32)(4095 - ab.denom));
       }
     }
@@ -230,7 +242,7 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
           if (i < nA && (i == 0 || A[i - 1].seqIdx != A[i].seqIdx)) {
             int a1 = i + 1;
             while (a1 < nA && A[a1].seqIdx == A[i].seqIdx) ++a1;
-            AlleleBest ab; eval_allele(R, paired, A, i, a1, B, nB, ab);
+            AlleleBest ab; eval_allele(R, paired, A, i, a1, B, nB, ab, paired ? (int)b0s[i] : -1);
             if (ab.valid && ab.mc == bestMc && ab.denom == bestDen && pos_less(ab.posKey, ab.posIdx, pk, pi)) {
               pk = ab.posKey; pi = ab.posIdx; bestRelax = ab.relaxed;
             }
@@ -249,7 +261,7 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
         if (i < nA && (i == 0 || A[i - 1].seqIdx != A[i].seqIdx)) {
           int a1 = i + 1;
           while (a1 < nA && A[a1].seqIdx == A[i].seqIdx) ++a1;
-          AlleleBest ab; eval_allele(R, paired, A, i, a1, B, nB, ab);
+          AlleleBest ab; eval_allele(R, paired, A, i, a1, B, nB, ab, paired ? (int)b0s[i] : -1);
           if (!ab.valid) continue;
           const bool keep = (ab.mc == bestMc && ab.denom == bestDen) ||
                             (R.relax && ab.mc >= bestMc - ab.relaxBy && ab.relaxed == bestRelax);
@@ -309,7 +321,11 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
         double seg = (1.0 - R.sim) / 4.0;
         if (seg < 0.01) seg = 0.01;
         const bool hasN = P.hasN && P.hasN[f];
-        const u64 base = P.rowOff[fLocal];
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(P.outCtr, (unsigned long long)nKeep);
+        base = __shfl_sync(FULL, base, 0);
+        const bool fits = base + (unsigned long long)nKeep <= P.outCap;
+        if (lane == 0) P.rowOff[fLocal] = base;
         int running = 0;
         for (int b = 0; b < nA; b += 32) {    // pass 4: ordered emission (allele order)
           const int i = b + lane;
@@ -318,7 +334,7 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
           if (i < nA && (i == 0 || A[i - 1].seqIdx != A[i].seqIdx)) {
             int a1 = i + 1;
             while (a1 < nA && A[a1].seqIdx == A[i].seqIdx) ++a1;
-            eval_allele(R, paired, A, i, a1, B, nB, ab);
+            eval_allele(R, paired, A, i, a1, B, nB, ab, paired ? (int)b0s[i] : -1);
             keep = ab.valid && ((ab.mc == bestMc && ab.denom == bestDen) ||
                                 (R.relax && ab.mc >= bestMc - ab.relaxBy && ab.relaxed == bestRelax));
           }
@@ -334,8 +350,10 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
             e.alleleIdx = A[i].seqIdx; e.start = ab.ss; e.end = ab.se;
             e.weight = (float)w; e.qual = 1.0f; e.adjustWeight = (float)(adjust * (double)e.weight);
             const u64 slot = base + running + __popc(bal & ((1u << lane) - 1));
-            P.out[slot] = e;
-            if (P.ordKey) { P.ordKey[slot] = ab.posKey; P.ordIdx[slot] = (u32)ab.posIdx; }
+            if (fits) {
+              P.out[slot] = e;
+              if (P.ordKey) { P.ordKey[slot] = ab.posKey; P.ordIdx[slot] = (u32)ab.posIdx; }
+            }
             const u64 m = mix64((u64)(u32)e.alleleIdx + 0x9e3779b97f4a7c15ull);
             h0 += m; h1 += mix64(m ^ 0xd6e8feb86659fd93ull);
           }
@@ -363,33 +381,6 @@ __global__ void __launch_bounds__(128) k_pair(PairParams P) {
     w = __shfl_sync(FULL, w, 0);
     if (w >= P.nFrag) break;
     pair_one(P, w, lane);
-  }
-}
-
-// upper bound of a fragment's row length: alleles present in both lists (paired) or in the only non-empty one
-__global__ void k_pair_bound(const u32 *readCnt, const u32 *end1, const u32 *end2, u32 fragBase, u32 nFrag, int maxAssign, u32 *ub) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nFrag) return;
-  const u32 n1 = readCnt[end1[fragBase + i]];
-  u32 v = n1;
-  if (end2) {
-    const u32 n2 = readCnt[end2[fragBase + i]];
-    v = (n1 > 0 && n2 > 0) ? min(n1, n2) : n1 + n2;
-  }
-  ub[i] = v;
-}
-
-// rows from the upper-bound layout into a dense CSR
-__global__ void k_pair_compact(const PairEntry *src, const u64 *srcOff, const u64 *dstOff, const u32 *rowCnt, u32 nFrag,
-                               PairEntry *dst, const u64 *ordKeySrc, const u32 *ordIdxSrc, u64 *ordKeyDst, u32 *ordIdxDst) {
-  const u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= nFrag) return;
-  const u64 s = srcOff[w], d = dstOff[w];
-  const u32 n = rowCnt[w] & 0x7fffffffu;
-  for (u32 k = lane; k < n; k += 32) {
-    dst[d + k] = src[s + k];
-    if (ordKeyDst) { ordKeyDst[d + k] = ordKeySrc[s + k]; ordIdxDst[d + k] = ordIdxSrc[s + k]; }
   }
 }
 

@@ -187,13 +187,15 @@ def test_genotype_vs_oracle(workload):
 
 
 def test_chunking_and_store_growth_do_not_change_results(workload, monkeypatch):
-    """Small fragment chunks (read-ends re-aligned per chunk with split weights) and a record store that overflows
-    and is grown (deferred read-ends re-run) must give the very same integers."""
+    """Small fragment chunks (read-ends re-aligned per chunk with split weights; the three-stage host pipeline runs
+    with many chunks), a record store that overflows and is grown (deferred read-ends re-run) and a pairing row buffer
+    that overflows must give the very same integers."""
     wl = workload
     gt = Genotyper(wl["ref"], wl["sim"], wl["relax"])
     base = gt.Genotype(wl["r1"], wl["r2"])
     monkeypatch.setenv("T1K_CHUNK_FRAGMENTS", "37")
     monkeypatch.setenv("T1K_STORE_RECORDS", "2000")
+    monkeypatch.setenv("T1K_PAIR_ROWS", "64")          # pairing rows overflow their first buffer: exact re-run
     out = gt.Genotype(wl["r1"], wl["r2"])
     for k in ("equivalent_class", "missing_coverage", "fragment_assigned"):
         assert np.array_equal(out[k], base[k]), k
