@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include <chrono>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -49,18 +50,82 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
     }                                                                                                \
   } while (0)
 
-struct DevMem {   // owning device allocation
+// Device workspace pool.  Every hot-path buffer (record store, pairing rows, EM vectors ...) is taken from and returned
+// to this per-device free list, so a steady-state call performs no cudaMalloc/cudaFree: those are synchronising driver
+// calls whose latency jumps by hundreds of ms when anything else (nvidia-smi polling, another context) holds the
+// driver lock.  Best fit within 2x; cached bytes are capped; an allocation failure trims the cache and retries.
+struct DevPool {
+  struct Block { void *p; size_t bytes; int dev; };
+  std::mutex mu;
+  std::vector<Block> freeList;
+  size_t cached = 0;
+  static constexpr size_t kMaxCached = (size_t)96 << 30;
+
+  cudaError_t get(size_t n, void **out, size_t *got) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      int best = -1;
+      for (size_t i = 0; i < freeList.size(); ++i) {
+        const Block &b = freeList[i];
+        if (b.dev != dev || b.bytes < n || b.bytes > std::max(2 * n, n + ((size_t)64 << 20))) continue;
+        if (best < 0 || b.bytes < freeList[best].bytes) best = (int)i;
+      }
+      if (best >= 0) {
+        *out = freeList[best].p; *got = freeList[best].bytes;
+        cached -= freeList[best].bytes;
+        freeList.erase(freeList.begin() + best);
+        return cudaSuccess;
+      }
+    }
+    const size_t want = n < ((size_t)1 << 20) ? ((n + 511) & ~(size_t)511) : ((n + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1));
+    cudaError_t e = cudaMalloc(out, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      trim(dev, 0);
+      e = cudaMalloc(out, want);
+    }
+    if (e == cudaSuccess) *got = want;
+    return e;
+  }
+  void put(void *p, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    freeList.push_back(Block{p, bytes, dev});
+    cached += bytes;
+    if (cached > kMaxCached) trim_locked(dev, kMaxCached / 2);
+  }
+  void trim(int dev, size_t keep) { std::lock_guard<std::mutex> lk(mu); trim_locked(dev, keep); }
+  void trim_locked(int dev, size_t keep) {     // frees the largest blocks first
+    while (cached > keep) {
+      int big = -1;
+      for (size_t i = 0; i < freeList.size(); ++i)
+        if (freeList[i].dev == dev && (big < 0 || freeList[i].bytes > freeList[big].bytes)) big = (int)i;
+      if (big < 0) break;
+      cudaFree(freeList[big].p);
+      cached -= freeList[big].bytes;
+      freeList.erase(freeList.begin() + big);
+    }
+  }
+  size_t cached_bytes() { std::lock_guard<std::mutex> lk(mu); return cached; }
+};
+DevPool &pool() { static DevPool *p = new DevPool; return *p; }   // leaked on purpose: outlives static destructors
+
+struct DevMem {   // owning device allocation (from the pool)
   void *p = nullptr; size_t bytes = 0;
   DevMem() {}
   DevMem(const DevMem &) = delete;
   DevMem &operator=(const DevMem &) = delete;
   ~DevMem() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  void release() { if (p) pool().put(p, bytes); p = nullptr; bytes = 0; }
   cudaError_t alloc(size_t n) {
-    release();
     if (n == 0) n = 16;
-    cudaError_t e = cudaMalloc(&p, n);
-    if (e == cudaSuccess) bytes = n; else p = nullptr;
+    if (p && bytes >= n && bytes <= std::max(2 * n, n + ((size_t)64 << 20))) return cudaSuccess;   // reuse in place
+    release();
+    cudaError_t e = pool().get(n, &p, &bytes);
+    if (e != cudaSuccess) { p = nullptr; bytes = 0; }
     return e;
   }
   template <class T> T *as() const { return (T *)p; }
@@ -96,6 +161,13 @@ struct PinnedMem {
 double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+
+// T1K_TIMING=1: host-side phase timings on stderr (diagnostics only)
+struct PhaseTimer {
+  bool on; double t;
+  PhaseTimer() : on(getenv("T1K_TIMING") != nullptr), t(now_ms()) {}
+  void lap(const char *what) { if (on) { double n = now_ms(); fprintf(stderr, "[t1k timing] %-28s %9.2f ms\n", what, n - t); t = n; } }
+};
 
 int pick_device(int want, int *out) {
   int n = 0;
@@ -278,7 +350,9 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
     total = std::max(total, (size_t)(off[i] + len[i]));
     maxLen = std::max(maxLen, (int)len[i]);
   }
+  PhaseTimer pt;
   if (int rc = setup_assign_launch(ref, maxLen)) return rc;
+  pt.lap("  assign: launch setup");
   T1KAssignment *a = new T1KAssignment;
   struct Guard { T1KAssignment *a; ~Guard() { delete a; } } guard{a};
   a->ref = ref; a->nReads = n;
@@ -302,12 +376,15 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   // record store: sized from free memory, grown (and only the deferred read-ends re-run) if it fills up
   size_t freeB = 0, totB = 0;
   CK(cudaMemGetInfo(&freeB, &totB));
+  freeB += pool().cached_bytes();
   u64 cap = std::max<u64>((u64)n * 6144, 1u << 20);
   const u64 capMax = (u64)(freeB * 0.70) / sizeof(Rec);
   if (cap > capMax) cap = capMax;
   if (const char *envCap = getenv("T1K_STORE_RECORDS")) cap = std::max<u64>(1024, strtoull(envCap, nullptr, 10));
+  pt.lap("  assign: input alloc + pack");
   CK(a->store.alloc(cap * sizeof(Rec)));
   a->storeCap = cap;
+  pt.lap("  assign: store alloc");
   AssignParams P;
   P.R = ref->R;
   P.Q.planes = planes.as<u64>(); P.Q.len = len16.as<u16>(); P.Q.weight = dW.as<int32_t>(); P.Q.workList = nullptr; P.Q.nWork = n;
@@ -349,6 +426,7 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
     float ms = 0; CK(cudaEventElapsedTime(&ms, ev0, ev1));
     a->msKernel += ms;
     ref->covDirty = true;
+    pt.lap("  assign: kernel round");
     if (err & (ERR_READ_LEN | ERR_READ_CHAR)) return fail(T1K_ERR_ARG, "read contains a character outside ACGTN or is too long");
     if (err & ~(ERR_STORE | ERR_HITS)) return fail(T1K_ERR_UNSUPPORTED, "t1k_assign_batch:" + decode_err(err));
     if (!(err & (ERR_STORE | ERR_HITS))) break;
@@ -369,6 +447,7 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
     todo[0].swap(next[0]); todo[1].swap(next[1]);
     if (err & ERR_STORE) {
       CK(cudaMemGetInfo(&freeB, &totB));
+      freeB += pool().cached_bytes();
       u64 newCap = cap * 2;
       if (newCap * sizeof(Rec) > (u64)(freeB * 0.9)) newCap = (u64)(freeB * 0.9) / sizeof(Rec);
       if (newCap <= cap + 1024 || round > 16) return fail(T1K_ERR_UNSUPPORTED, "overlap record store does not fit in device memory; use smaller batches");
@@ -389,6 +468,7 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   a->storeUsed = used;
   CK(cudaMemcpy(&a->maxCnt, a->dMaxCnt.p, 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(a->stats, ref->stats.p, sizeof(a->stats), cudaMemcpyDeviceToHost));
+  pt.lap("  assign: tail");
   guard.a = nullptr;
   *out = a;
   return T1K_OK;
@@ -549,6 +629,7 @@ namespace {
 struct PairHost {
   std::vector<u64> rowOff;            // [nFrag] first entry of the fragment's row (rows are dense but in no fragment order)
   std::vector<u32> rowCnt;            // [nFrag]
+  std::vector<u64> rowHash;           // [2 * nFrag] order-free hash of the row's allele set (when wantHash)
   PinnedMem *pin = nullptr;           // rows land here (pinned: the D2H copy runs at link speed, nothing is zero-filled)
   size_t nEntries = 0;
   HostEntry *entries() const { return pin->as<HostEntry>(); }
@@ -559,15 +640,17 @@ struct PairHost {
 };
 
 int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const uint32_t *end2, const uint8_t *hasN, uint32_t nFrag,
-                   int maxAssign, bool wantOrder, PairHost &H) {
+                   int maxAssign, bool wantOrder, PairHost &H, bool wantHash = false) {
   cudaStream_t st = ref->stream;
   H.rowOff.assign(nFrag, 0); H.rowCnt.assign(nFrag, 0);
+  H.rowHash.assign(wantHash ? 2 * (size_t)nFrag : 0, 0);
   H.assigned.assign(nFrag, 0);
   H.nEntries = 0; H.ordKey.clear(); H.ordIdx.clear();
   if (nFrag == 0) return T1K_OK;
   for (uint32_t i = 0; i < nFrag; ++i)
     if (end1[i] >= a->nReads || (end2 && end2[i] >= a->nReads)) return fail(T1K_ERR_ARG, "t1k_pair_batch: read-end index out of range");
-  DevMem dE1, dE2, dN, dRowOff, dRowCnt, dOut, dKey, dIdx, dCtr, dOutCtr, dB0;
+  DevMem dE1, dE2, dN, dRowOff, dRowCnt, dOut, dKey, dIdx, dCtr, dOutCtr, dB0, dStage, dStageKey, dStageIdx, dHash;
+  if (wantHash) CK(dHash.alloc((size_t)nFrag * 16));
   CK(dE1.alloc((size_t)nFrag * 4));
   CK(cudaMemcpyAsync(dE1.p, end1, (size_t)nFrag * 4, cudaMemcpyHostToDevice, st));
   if (end2) { CK(dE2.alloc((size_t)nFrag * 4)); CK(cudaMemcpyAsync(dE2.p, end2, (size_t)nFrag * 4, cudaMemcpyHostToDevice, st)); }
@@ -577,9 +660,11 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
   cudaEvent_t ev0, ev1;
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
   struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
+  PhaseTimer pt;
   // output rows are appended through a device counter; a first guess of the capacity, then (rarely) one exact re-run
   size_t freeB = 0, totB = 0;
   CK(cudaMemGetInfo(&freeB, &totB));
+  freeB += pool().cached_bytes();
   const size_t perEntry = sizeof(PairEntry) + (wantOrder ? 12 : 0);
   u64 cap = std::max<u64>(1u << 20, (u64)nFrag * 192);
   if (const char *env = getenv("T1K_PAIR_ROWS")) cap = std::max<u64>(64, strtoull(env, nullptr, 10));
@@ -596,12 +681,20 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
     P.fragBase = 0; P.nFrag = nFrag; P.maxAssign = maxAssign;
     P.out = dOut.as<PairEntry>(); P.outCap = cap; P.outCtr = dOutCtr.as<unsigned long long>(); P.rowOff = dRowOff.as<u64>();
     P.ordKey = wantOrder ? dKey.as<u64>() : nullptr; P.ordIdx = wantOrder ? dIdx.as<u32>() : nullptr;
-    P.rowCnt = dRowCnt.as<u32>(); P.rowHash = nullptr; P.workCtr = dCtr.as<unsigned int>();
+    P.rowCnt = dRowCnt.as<u32>(); P.rowHash = wantHash ? dHash.as<u64>() : nullptr; P.workCtr = dCtr.as<unsigned int>();
     const int blocks = std::max(1, std::min<int>((int)((nFrag + 3) / 4), ref->nSM * 8));
     // per-warp scratch: where each allele run of the first mate's list starts in the second mate's list
     const size_t b0Stride = ((size_t)a->maxCnt + 32) & ~(size_t)31;
-    if (attempt == 0) CK(dB0.alloc((size_t)blocks * 4 * b0Stride * 4));
+    // ... and the staging row: a row longer than -n is cut, so -n entries suffice
+    const size_t stageCap = (maxAssign > 0 && (size_t)maxAssign < b0Stride) ? (size_t)maxAssign : b0Stride;
+    if (attempt == 0) {
+      CK(dB0.alloc((size_t)blocks * 4 * b0Stride * 4));
+      CK(dStage.alloc((size_t)blocks * 4 * stageCap * sizeof(PairEntry)));
+      if (wantOrder) { CK(dStageKey.alloc((size_t)blocks * 4 * stageCap * 8)); CK(dStageIdx.alloc((size_t)blocks * 4 * stageCap * 4)); }
+    }
     P.b0 = dB0.as<u32>(); P.b0Stride = (u32)b0Stride;
+    P.stage = dStage.as<PairEntry>(); P.stageCap = (u32)stageCap;
+    P.stageKey = wantOrder ? dStageKey.as<u64>() : nullptr; P.stageIdx = wantOrder ? dStageIdx.as<u32>() : nullptr;
     CK(cudaEventRecord(ev0, st));
     k_pair<<<blocks, 128, 0, st>>>(P);
     CK(cudaGetLastError());
@@ -609,12 +702,14 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
     CK(cudaMemcpyAsync(&used, dOutCtr.p, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     float ms = 0; CK(cudaEventElapsedTime(&ms, ev0, ev1)); H.msKernel += ms; H.launches += 1;
+    pt.lap("  pair: alloc + kernel");
     if (used <= cap) break;
     if (attempt >= 2 || used * perEntry > (u64)(freeB * 0.9)) return fail(T1K_ERR_UNSUPPORTED, "fragment rows do not fit in device memory; use smaller batches");
     cap = used;
   }
   CK(cudaMemcpyAsync(H.rowOff.data(), dRowOff.p, (size_t)nFrag * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(H.rowCnt.data(), dRowCnt.p, (size_t)nFrag * 4, cudaMemcpyDeviceToHost, st));
+  if (wantHash) CK(cudaMemcpyAsync(H.rowHash.data(), dHash.p, (size_t)nFrag * 16, cudaMemcpyDeviceToHost, st));
   if (used > 0) {
     CK(H.pin->grow(used * sizeof(HostEntry), 0));
     CK(cudaMemcpyAsync(H.entries(), dOut.p, used * sizeof(PairEntry), cudaMemcpyDeviceToHost, st));
@@ -625,6 +720,7 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
     }
   }
   CK(cudaStreamSynchronize(st));
+  pt.lap("  pair: D2H");
   H.nEntries = used;
   for (u32 i = 0; i < nFrag; ++i) {
     H.assigned[i] = (u8)(H.rowCnt[i] >> 31);
@@ -676,6 +772,7 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   CK(cudaSetDevice(dev));
   const int G = p->n_groups, E = p->n_ec;
   const int64_t nnz = p->row_ptr[G];
+  PhaseTimer pt;
   for (int64_t k = 0; k < nnz; ++k) if (p->col[k] < 0 || p->col[k] >= E) return fail(T1K_ERR_ARG, "t1k_em_run: column index out of range");
   // read-sharded E-step: this rank's contiguous row range [g0, g1)
   T1KComm *comm = (p->comm && p->comm->world > 1) ? p->comm : nullptr;
@@ -699,6 +796,7 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
     std::vector<int64_t> cur(colPtr.begin(), colPtr.end() - 1);
     for (int g = g0; g < g1; ++g) for (int64_t k = p->row_ptr[g]; k < p->row_ptr[g + 1]; ++k) rowIdx[cur[p->col[k]]++] = g;
   }
+  pt.lap("  em: validate + CSC");
   cudaStream_t st;
   CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   struct StGuard { cudaStream_t s; ~StGuard() { cudaStreamDestroy(s); } } sg{st};
@@ -720,6 +818,8 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
   struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
   CK(cudaEventRecord(ev0, st));
+  CK(cudaStreamSynchronize(st));
+  pt.lap("  em: alloc + upload");
   uint64_t launches = 0;
   auto em_update = [&](const double *xin, double *xout) -> int {   // Genotyper::EMupdate
     double *psumL = dPsum.as<double>() + g0;    // psum / count stay indexed by the global group id
@@ -771,6 +871,7 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   CK(cudaEventRecord(ev1, st));
   CK(cudaStreamSynchronize(st));
   CK(cudaEventElapsedTime(&r->ms_kernel, ev0, ev1));
+  pt.lap("  em: iterations");
   r->n_launches = launches;
   r->iterations = ret;
   return T1K_OK;
@@ -977,6 +1078,9 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   CK(cudaMemsetAsync(ref->covPoint.p, 0, ref->paddedBases * 4, ref->stream));
   ref->covDirty = true;
   ReadGroups groups;
+  int hostThreads = (int)std::thread::hardware_concurrency() / ((prm->comm && prm->comm->world > 1) ? prm->comm->world : 1);
+  if (const char *env = getenv("T1K_HOST_THREADS")) hostThreads = atoi(env);
+  GroupShards shards(std::max(1, std::min(8, hostThreads)));
   res->n_unique_ends = 0; res->n_overlaps = 0; res->n_assignments = 0;
   res->ms_dedup = res->ms_align = res->ms_pair = res->ms_coalesce = res->ms_em = 0;
   res->ms_align_kernel = res->ms_pair_kernel = res->ms_em_kernel = 0;
@@ -986,11 +1090,8 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   double msCoalesce = 0;
   auto do_coalesce = [&](const PairHost &H, u32 f0, u32 m) {
     const double t = now_ms();
-    const HostEntry *ent = H.entries();
-    for (u32 i = 0; i < m; ++i) {
-      if (H.rowCnt[i]) groups.add(ent + H.rowOff[i], H.rowCnt[i]);
-      if (res->fragment_assigned) res->fragment_assigned[f0 + i] = H.assigned[i];
-    }
+    shards.add_chunk(H.entries(), H.rowOff.data(), H.rowCnt.data(), H.rowHash.data(), m, (int64_t)f0);
+    if (res->fragment_assigned) memcpy(res->fragment_assigned + f0, H.assigned.data(), m);
     msCoalesce += now_ms() - t;
   };
   std::thread prepThread, coalThread;
@@ -1016,7 +1117,7 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     res->n_launches += 2 + a->launches;
     double tp = now_ms();
     PairHost &H = pairOut[c & 1];     // last read by the coalescing of chunk c-2, which has been joined
-    if (int rc = pair_fragments(ref, a, C.e1.data(), reads2 ? C.e2.data() : nullptr, C.hasN.data(), C.m, prm->max_assign, false, H)) return rc;
+    if (int rc = pair_fragments(ref, a, C.e1.data(), reads2 ? C.e2.data() : nullptr, C.hasN.data(), C.m, prm->max_assign, false, H, true)) return rc;
     res->ms_pair += (float)(now_ms() - tp);
     res->ms_pair_kernel += H.msKernel; res->n_launches += H.launches;
     res->n_assignments += H.nEntries;
@@ -1025,6 +1126,11 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     if (prepThread.joinable()) prepThread.join();
   }
   if (coalThread.joinable()) coalThread.join();
+  {
+    const double t = now_ms();
+    shards.gather(groups);
+    msCoalesce += now_ms() - t;
+  }
   res->ms_coalesce = (float)msCoalesce;
   // ---- read-sharded run: total coverage, every rank's read groups merged in rank order
   T1KComm *comm = (prm->comm && prm->comm->world > 1) ? prm->comm : nullptr;
@@ -1055,10 +1161,13 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   res->n_assignments = nAssignAll;
   // ---- FinalizeReadAssignments: equivalence classes + missing coverage
   double tc = now_ms();
+  PhaseTimer pt;
   EquivalenceClasses EC;
   EC.build(groups, nA);
+  pt.lap("equivalence classes");
   res->n_groups = groups.size(); res->n_ec = EC.size(); res->n_alleles = nA;
   if (res->missing_coverage) { if (int rc = t1k_missing_coverage(ref, res->missing_coverage)) return rc; }
+  pt.lap("missing coverage");
   if (res->equivalent_class) memcpy(res->equivalent_class, EC.alleleEc.data(), (size_t)nA * 4);
   res->ms_coalesce += (float)(now_ms() - tc);
   // ---- EM
@@ -1069,6 +1178,8 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   if (EC.size() > 0) {
     EmInputs in;
     in.build(groups, EC, prm->effective_len, prm->seq_weight);
+    pt.lap("EM inputs");
+    if (pt.on) fprintf(stderr, "[t1k timing] groups %d entries %zu ECs %d nnz %zu\n", groups.size(), groups.ent.size(), EC.size(), in.col.size());
     T1KEmProblem ep;
     memset(&ep, 0, sizeof(ep));
     ep.n_groups = groups.size(); ep.n_ec = EC.size();
@@ -1083,6 +1194,7 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     std::vector<double> x(EC.size()), rc(EC.size());
     T1KEmResult er; er.x = x.data(); er.ec_read_count = rc.data(); er.iterations = 0;
     if (int rcode = t1k_em_run(&ep, &er, ref->device)) return rcode;
+    pt.lap("t1k_em_run");
     res->em_iterations = er.iterations;
     res->ms_em_kernel = er.ms_kernel; res->n_launches += er.n_launches;
     if (res->abundance && res->ec_abundance)

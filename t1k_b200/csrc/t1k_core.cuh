@@ -172,15 +172,17 @@ T1K_HD u64 mm_chunk(const AlleleView &T, int tpos, const ReadView &Q, int ppos, 
   return d & lowmask2(nLeft);
 }
 
-// mismatching columns among rows [lo, hi] of the window when row r of the read is paired with allele column r + d
-T1K_HDN T1K_NOINLINE inline int shifted_mm(const AlleleView &T, int tpos, const ReadView &Q, int ppos, int n, int d, int lo, int hi) {
+// mismatching columns among rows [lo, hi] of the window when row r of the read is paired with allele column r + d.
+// The caller only asks whether the count stays <= limit: the scan stops at the first chunk that exceeds it (a shifted
+// comparison of unrelated sequence mismatches within a few columns, so this is almost always the first chunk).
+T1K_HDN T1K_NOINLINE inline int shifted_mm(const AlleleView &T, int tpos, const ReadView &Q, int ppos, int n, int d, int lo, int hi, int limit) {
   if (lo < 0) lo = 0;
   if (lo < -d) lo = -d;
   if (hi > n - 1) hi = n - 1;
   if (hi > n - 1 - d) hi = n - 1 - d;
   int c = 0;
   T1K_NOUNROLL
-  for (int k = lo; k <= hi; k += 32) c += popc64(mm_chunk(T, tpos + k + d, Q, ppos + k, hi - k + 1));
+  for (int k = lo; k <= hi && c <= limit; k += 32) c += popc64(mm_chunk(T, tpos + k + d, Q, ppos + k, hi - k + 1));
   return c;
 }
 
@@ -223,7 +225,7 @@ T1K_HDN T1K_NOINLINE inline bool diag_certified_45(const AlleleView &T, int tpos
               int in = 0;
               T1K_NOUNROLL
               for (int q = 0; q < mm; ++q) in += pos[q] >= A && pos[q] <= B;
-              if (in - shifted_mm(T, tpos, Q, ppos, n, d, A, B - d) > 2 + d) return false;
+              if (in > 2 + d && in - shifted_mm(T, tpos, Q, ppos, n, d, A, B - d, in - 3 - d) > 2 + d) return false;
             }
           }
           // insertion first (allele behind by d): first d rows unpaired, rows [A + d, B] paired with columns r - d
@@ -233,7 +235,7 @@ T1K_HDN T1K_NOINLINE inline bool diag_certified_45(const AlleleView &T, int tpos
               int in = 0;
               T1K_NOUNROLL
               for (int q = 0; q < mm; ++q) in += pos[q] >= A && pos[q] <= B;
-              if (in - shifted_mm(T, tpos, Q, ppos, n, -d, A + d, B) > 2 + d) return false;
+              if (in > 2 + d && in - shifted_mm(T, tpos, Q, ppos, n, -d, A + d, B, in - 3 - d) > 2 + d) return false;
             }
           }
         }
@@ -316,6 +318,11 @@ T1K_HDN T1K_NOINLINE inline int dp_align(const AlleleView &T, int tpos, int lent
     int pb = base2(Q.seq2, ppos + i - 1), pn = T.useN ? base2(Q.n2, ppos + i - 1) : 0;
     int fPrev = negInf, mLeft = negInf;        // f and m of column j-1 in this row
     u8 *drow = dir + (size_t)i * W;
+    // allele columns start..end of this row (at most W - 2 <= 62 of them) as two 32-base words: no loads per cell
+    const int tb = tpos + start - 1;
+    const u64 ts0 = fetch32(T.seq, tb), ts1 = fetch32(T.seq, tb + 32);
+    u64 tn0 = 0, tn1 = 0;
+    if (T.useN) { tn0 = fetch32(T.n2, tb); tn1 = fetch32(T.n2, tb + 32); }
     T1K_NOUNROLL
     for (int jj = 0; jj < W; ++jj) {
       int j = i - lb - 1 + jj;
@@ -331,7 +338,9 @@ T1K_HDN T1K_NOINLINE inline int dp_align(const AlleleView &T, int tpos, int lent
         ev = e1 > e2 ? e1 : e2;
         int f1 = fPrev - 1, f2 = mLeft - 5;
         fv = f1 > f2 ? f1 : f2;
-        bool eq = pn || (T.useN && base2(T.n2, tpos + j - 1)) || base2(T.seq, tpos + j - 1) == pb;
+        const int q = j - start, sh = (q & 31) * 2;
+        const int tbase = (int)(((q < 32 ? ts0 : ts1) >> sh) & 3), tnn = (int)(((q < 32 ? tn0 : tn1) >> sh) & 3);
+        bool eq = pn || tnn || tbase == pb;
         int dv = mDiag + (eq ? 2 : -2);
         mv = dv;
         if (ev > mv) mv = ev;

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -22,6 +23,7 @@ struct HostEntry {   // == PairEntry / T1KReadAssignment
 struct ReadGroups {
   std::vector<int64_t> ptr{0};
   std::vector<HostEntry> ent;
+  std::vector<int64_t> first;          // per group: index of the fragment that created it (orders merged shards)
   std::unordered_map<uint64_t, std::vector<int32_t> > byHash;
   int64_t assignedFragments = 0;
 
@@ -38,10 +40,12 @@ struct ReadGroups {
 
   // row must be sorted by alleleIdx (the pairing kernel emits it that way).  `fragments` = how many fragments the
   // row stands for: 1 for a fragment, the group's own count when another rank's table is merged in.
-  void add(const HostEntry *row, uint32_t n, int64_t fragments = 1) {
+  // `hash`: a precomputed hash of the allele set (the pairing kernel's), else computed here; `fragIdx`: global index
+  // of the fragment (first-appearance order of the groups).
+  void add(const HostEntry *row, uint32_t n, int64_t fragments = 1, const uint64_t *hash = nullptr, int64_t fragIdx = -1) {
     if (n == 0) return;
     assignedFragments += fragments;
-    const uint64_t h = hash_row(row, n);
+    const uint64_t h = hash ? *hash : hash_row(row, n);
     std::vector<int32_t> &cand = byHash[h];
     for (size_t c = 0; c < cand.size(); ++c) {
       const int32_t g = cand[c];
@@ -63,8 +67,59 @@ struct ReadGroups {
     cand.push_back(size());
     ent.insert(ent.end(), row, row + n);
     ptr.push_back((int64_t)ent.size());
+    first.push_back(fragIdx);
   }
 };
+
+// Coalescing on T host threads.  Thread t owns the read groups whose allele-set hash falls into partition t, so every
+// group still sees its fragments in fragment order (float32 sums unchanged) while the partitions proceed in parallel;
+// gather() interleaves the partitions by the fragment that created each group = the single-threaded group order.
+struct GroupShards {
+  std::vector<ReadGroups> part;
+  explicit GroupShards(int T) : part((size_t)(T < 1 ? 1 : T)) {}
+  int threads() const { return (int)part.size(); }
+
+  // rows: entries at ent + off[i], cnt[i] of them, hash[2*i] = allele-set hash, fragments f0 .. f0+m-1
+  void add_chunk(const HostEntry *ent, const uint64_t *off, const uint32_t *cnt, const uint64_t *hash, uint32_t m, int64_t f0);
+
+  void gather(ReadGroups &out) const {
+    struct Ref { int64_t first; int32_t t, g; };
+    std::vector<Ref> order;
+    size_t nEnt = 0;
+    for (int t = 0; t < threads(); ++t) {
+      for (int32_t g = 0; g < part[t].size(); ++g) order.push_back(Ref{part[t].first[g], t, g});
+      nEnt += part[t].ent.size();
+      out.assignedFragments += part[t].assignedFragments;
+    }
+    std::sort(order.begin(), order.end(), [](const Ref &a, const Ref &b) { return a.first < b.first; });
+    out.ent.reserve(out.ent.size() + nEnt);
+    for (size_t k = 0; k < order.size(); ++k) {
+      const ReadGroups &P = part[order[k].t];
+      const int32_t g = order[k].g;
+      out.ent.insert(out.ent.end(), P.ent.begin() + P.ptr[g], P.ent.begin() + P.ptr[g + 1]);
+      out.ptr.push_back((int64_t)out.ent.size());
+      out.first.push_back(P.first[g]);
+    }
+  }
+};
+
+inline void GroupShards::add_chunk(const HostEntry *ent, const uint64_t *off, const uint32_t *cnt, const uint64_t *hash, uint32_t m, int64_t f0) {
+  const int T = threads();
+  auto work = [&](int t) {
+    ReadGroups &G = part[t];
+    for (uint32_t i = 0; i < m; ++i) {
+      if (!cnt[i]) continue;
+      const uint64_t h = hash[2 * (size_t)i] ^ (hash[2 * (size_t)i + 1] * 0x9e3779b97f4a7c15ull);
+      if ((int)((h >> 17) % (uint64_t)T) != t) continue;
+      G.add(ent + off[i], cnt[i], 1, &h, f0 + i);
+    }
+  };
+  if (T == 1) { work(0); return; }
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+  work(0);
+  for (size_t k = 0; k < th.size(); ++k) th[k].join();
+}
 
 // Relocatable image of a group table: [nGroups, nEntries, assignedFragments] then ptr[nGroups+1] then entries.
 inline void serialize_groups(const ReadGroups &G, std::vector<uint8_t> &blob) {

@@ -40,6 +40,9 @@ struct PairParams {
   unsigned int *workCtr;
   u32 *b0;                  // per warp, b0Stride entries: start of each first-list allele run in the second list
   u32 b0Stride;
+  PairEntry *stage;         // per warp, stageCap entries: the fragment's row until the fragment-level cuts are decided
+  u64 *stageKey; u32 *stageIdx;   // with ordKey
+  u32 stageCap;
 };
 
 struct RV { int seqIdx, ss, se, rs, re, lc, rc, mc, st, relaxed; u64 key; };
@@ -213,7 +216,11 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
   const Rec *A = L1; int nA = n1;
   if (pe && n1 == 0) { A = L2; nA = n2; }
   const Rec *B = paired ? L2 : NULL; const int nB = paired ? n2 : 0;
-  u32 *b0s = P.b0 + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * P.b0Stride;
+  const size_t gw = (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  u32 *b0s = P.b0 + gw * P.b0Stride;
+  PairEntry *stage = P.stage + gw * P.stageCap;
+  u64 *stageKey = P.ordKey ? P.stageKey + gw * P.stageCap : NULL;
+  u32 *stageIdx = P.ordKey ? P.stageIdx + gw * P.stageCap : NULL;
   u32 cnt = 0;
   bool assigned = false;
   u64 h0 = 0, h1 = 0;
@@ -253,20 +260,27 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
         const unsigned who = __ballot_sync(FULL, pk == k && pi == ii);
         bestRelax = __shfl_sync(FULL, bestRelax, __ffs(who) - 1);
       }
-      // pass 3: survivors, the representative (first survivor in assign order) and the per-survivor tests
-      int nKeep = 0; bool anySep = false, anyFull = false, dangleFail = false;
+      // pass 3: survivors, the representative (first survivor in assign order), the per-survivor tests, and the
+      // rows themselves, staged in the warp's scratch row (allele order) until the fragment-level decisions are known
+      double seg = (1.0 - R.sim) / 4.0;
+      if (seg < 0.01) seg = 0.01;
+      const bool hasN = P.hasN && P.hasN[f];
+      bool anySep = false, anyFull = false, dangleFail = false;
       u64 rk = ~0ull; int ri = 0x7fffffff; int repIa = -1, repJb = -1;
+      int nKeep = 0;
       for (int b = 0; b < nA; b += 32) {
         const int i = b + lane;
+        bool keep = false;
+        AlleleBest ab;
         if (i < nA && (i == 0 || A[i - 1].seqIdx != A[i].seqIdx)) {
           int a1 = i + 1;
           while (a1 < nA && A[a1].seqIdx == A[i].seqIdx) ++a1;
-          AlleleBest ab; eval_allele(R, paired, A, i, a1, B, nB, ab, paired ? (int)b0s[i] : -1);
-          if (!ab.valid) continue;
-          const bool keep = (ab.mc == bestMc && ab.denom == bestDen) ||
-                            (R.relax && ab.mc >= bestMc - ab.relaxBy && ab.relaxed == bestRelax);
-          if (!keep) continue;
-          ++nKeep;
+          eval_allele(R, paired, A, i, a1, B, nB, ab, paired ? (int)b0s[i] : -1);
+          keep = ab.valid && ((ab.mc == bestMc && ab.denom == bestDen) ||
+                              (R.relax && ab.mc >= bestMc - ab.relaxBy && ab.relaxed == bestRelax));
+        }
+        const unsigned bal = __ballot_sync(FULL, keep);
+        if (keep) {
           const int seqIdx = A[i].seqIdx;
           const bool sep = sep_exact(R, seqIdx, ab.ss, ab.se);
           anySep |= sep;
@@ -276,9 +290,23 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
             if (ab.mc < ab.denom || sep || ab.se - ab.ss + 1 + ab.o1.re - ab.o1.rs + 1 < 3 * HIT_LEN_REQ) dangleFail = true;
             else if ((ab.o1.st == 1 && ab.se + 100 < R.len[seqIdx]) || (ab.o1.st == 0 && ab.ss - 100 >= 0)) dangleFail = true;
           }
+          const u32 slot = (u32)nKeep + __popc(bal & ((1u << lane) - 1));
+          if (slot < P.stageCap) {         // a longer row is dropped by the -n cut anyway
+            const double sim = (double)ab.mc / (double)ab.denom;
+            double w = 1.0;
+            if (sim < 1 - 3 * seg) w = 0.01;
+            else if (sim < 1 - 2 * seg) w = 0.1;
+            else if (sim < 1 - seg) w = 0.5;
+            if (hasN) w /= 10.0;
+            PairEntry e;
+            e.alleleIdx = seqIdx; e.start = ab.ss; e.end = ab.se;
+            e.weight = (float)w; e.qual = 1.0f; e.adjustWeight = 0.0f;
+            stage[slot] = e;
+            if (P.ordKey) { stageKey[slot] = ab.posKey; stageIdx[slot] = (u32)ab.posIdx; }
+          }
         }
+        nKeep += __popc(bal);
       }
-      nKeep = warp_sum_i32(nKeep);
       anySep = __any_sync(FULL, anySep); anyFull = __any_sync(FULL, anyFull); dangleFail = __any_sync(FULL, dangleFail);
       {
         u64 k = rk; int ii = ri;
@@ -318,48 +346,23 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
       if (!drop && anySep) drop = true;
       if (!drop) {
         const double adjust = anyFull ? 1.0 : 0.25;
-        double seg = (1.0 - R.sim) / 4.0;
-        if (seg < 0.01) seg = 0.01;
-        const bool hasN = P.hasN && P.hasN[f];
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(P.outCtr, (unsigned long long)nKeep);
         base = __shfl_sync(FULL, base, 0);
         const bool fits = base + (unsigned long long)nKeep <= P.outCap;
         if (lane == 0) P.rowOff[fLocal] = base;
-        int running = 0;
-        for (int b = 0; b < nA; b += 32) {    // pass 4: ordered emission (allele order)
-          const int i = b + lane;
-          bool keep = false;
-          AlleleBest ab;
-          if (i < nA && (i == 0 || A[i - 1].seqIdx != A[i].seqIdx)) {
-            int a1 = i + 1;
-            while (a1 < nA && A[a1].seqIdx == A[i].seqIdx) ++a1;
-            eval_allele(R, paired, A, i, a1, B, nB, ab, paired ? (int)b0s[i] : -1);
-            keep = ab.valid && ((ab.mc == bestMc && ab.denom == bestDen) ||
-                                (R.relax && ab.mc >= bestMc - ab.relaxBy && ab.relaxed == bestRelax));
+        __syncwarp();
+        for (int k = lane; k < nKeep; k += 32) {     // staged row -> output (coalesced)
+          PairEntry e = stage[k];
+          e.adjustWeight = (float)(adjust * (double)e.weight);
+          if (fits) {
+            P.out[base + k] = e;
+            if (P.ordKey) { P.ordKey[base + k] = stageKey[k]; P.ordIdx[base + k] = stageIdx[k]; }
           }
-          const unsigned bal = __ballot_sync(FULL, keep);
-          if (keep) {
-            const double sim = (double)ab.mc / (double)ab.denom;
-            double w = 1.0;
-            if (sim < 1 - 3 * seg) w = 0.01;
-            else if (sim < 1 - 2 * seg) w = 0.1;
-            else if (sim < 1 - seg) w = 0.5;
-            if (hasN) w /= 10.0;
-            PairEntry e;
-            e.alleleIdx = A[i].seqIdx; e.start = ab.ss; e.end = ab.se;
-            e.weight = (float)w; e.qual = 1.0f; e.adjustWeight = (float)(adjust * (double)e.weight);
-            const u64 slot = base + running + __popc(bal & ((1u << lane) - 1));
-            if (fits) {
-              P.out[slot] = e;
-              if (P.ordKey) { P.ordKey[slot] = ab.posKey; P.ordIdx[slot] = (u32)ab.posIdx; }
-            }
-            const u64 m = mix64((u64)(u32)e.alleleIdx + 0x9e3779b97f4a7c15ull);
-            h0 += m; h1 += mix64(m ^ 0xd6e8feb86659fd93ull);
-          }
-          running += __popc(bal);
+          const u64 m = mix64((u64)(u32)e.alleleIdx + 0x9e3779b97f4a7c15ull);
+          h0 += m; h1 += mix64(m ^ 0xd6e8feb86659fd93ull);
         }
-        cnt = (u32)running;
+        cnt = (u32)nKeep;
       }
     }
   }
