@@ -143,7 +143,17 @@ def reference_arm(args, rank):
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
+def _claim_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON line on stdout.
+    Everything else is sent to stderr; the returned file object is the real stdout for the JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -160,7 +170,7 @@ def main():
     if args.impl == "reference":
         line = reference_arm(args, rank)
         if line is not None:
-            print(json.dumps(line), flush=True)
+            print(json.dumps(line), file=real_stdout, flush=True)
         return
 
     import torch
@@ -244,7 +254,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             ref_line = reference_arm(argparse.Namespace(**{**vars(args), "steps": 1, "warmup": 0}), 0)
             line["cpu_baseline"] = ref_line.get("cpu_baseline") or {"value": None, "unavailable": ref_line.get("unavailable")}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

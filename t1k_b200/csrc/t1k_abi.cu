@@ -199,8 +199,11 @@ struct T1KRef {
   int gridBlocks[2] = {0, 0}, hitCap[2] = {0, 0};
   size_t scratchWarps = 0;
   u64 nPostings = 0;
+  size_t memBudget = 0;      // free device memory right after the reference was uploaded (workspace budget; cudaMemGetInfo is
+                             // a slow driver call, so it is not repeated per batch)
   bool covDirty = true;
   PinnedMem pinEntries[2];   // D2H staging of pairing rows (double-buffered by t1k_genotype's chunk pipeline)
+  PinnedMem pinSend, pinRecv; // read-group tables on their way to / from the peers
   ~T1KRef() { if (stream) cudaStreamDestroy(stream); }
 };
 
@@ -273,6 +276,11 @@ int t1k_ref_create(const T1KRefDesc *d, T1KRef **out) {
   R.kstart = r->kstart.as<u32>(); R.post = r->post.as<Posting>();
   R.covDiff = r->covDiff.as<int32_t>(); R.covPoint = r->covPoint.as<int32_t>();
   R.nAlleles = d->n_alleles; R.sim = d->similarity; R.relax = d->relax_intron;
+  {
+    size_t freeB = 0, totB = 0;
+    if (cudaMemGetInfo(&freeB, &totB) != cudaSuccess) { cudaGetLastError(); freeB = (size_t)8 << 30; }
+    r->memBudget = freeB + pool().cached_bytes();
+  }
   *out = r;
   return T1K_OK;
 }
@@ -374,9 +382,7 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
                                                   ref->errFlag.as<int>());
   CK(cudaGetLastError());
   // record store: sized from free memory, grown (and only the deferred read-ends re-run) if it fills up
-  size_t freeB = 0, totB = 0;
-  CK(cudaMemGetInfo(&freeB, &totB));
-  freeB += pool().cached_bytes();
+  size_t freeB = ref->memBudget;
   u64 cap = std::max<u64>((u64)n * 6144, 1u << 20);
   const u64 capMax = (u64)(freeB * 0.70) / sizeof(Rec);
   if (cap > capMax) cap = capMax;
@@ -446,8 +452,6 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
     first = false;
     todo[0].swap(next[0]); todo[1].swap(next[1]);
     if (err & ERR_STORE) {
-      CK(cudaMemGetInfo(&freeB, &totB));
-      freeB += pool().cached_bytes();
       u64 newCap = cap * 2;
       if (newCap * sizeof(Rec) > (u64)(freeB * 0.9)) newCap = (u64)(freeB * 0.9) / sizeof(Rec);
       if (newCap <= cap + 1024 || round > 16) return fail(T1K_ERR_UNSUPPORTED, "overlap record store does not fit in device memory; use smaller batches");
@@ -662,9 +666,7 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
   struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
   PhaseTimer pt;
   // output rows are appended through a device counter; a first guess of the capacity, then (rarely) one exact re-run
-  size_t freeB = 0, totB = 0;
-  CK(cudaMemGetInfo(&freeB, &totB));
-  freeB += pool().cached_bytes();
+  const size_t freeB = ref->memBudget > a->store.bytes ? ref->memBudget - a->store.bytes : ((size_t)1 << 30);
   const size_t perEntry = sizeof(PairEntry) + (wantOrder ? 12 : 0);
   u64 cap = std::max<u64>(1u << 20, (u64)nFrag * 192);
   if (const char *env = getenv("T1K_PAIR_ROWS")) cap = std::max<u64>(64, strtoull(env, nullptr, 10));
@@ -985,30 +987,30 @@ int t1k_em_partition(const int64_t *row_ptr, int32_t n_groups, int32_t world, in
 
 namespace {
 
-// all-gather of one host blob per rank through device staging (padded to the largest); out[r] = rank r's blob
-int allgather_blobs(T1KRef *ref, T1KComm *comm, const std::vector<uint8_t> &mine, std::vector<std::vector<uint8_t> > &out) {
+// all-gather of one host blob per rank through device staging (padded to the largest); the result lands in pinned
+// memory `recv`: blob r = recv + r * stride, sizes[r] bytes
+int allgather_blobs(T1KRef *ref, T1KComm *comm, const uint8_t *mine, uint64_t myBytes, PinnedMem &recv, uint64_t &stride,
+                    std::vector<uint64_t> &sizes) {
   cudaStream_t st = ref->stream;
   const int W = comm->world;
   DevMem dSizes, dBuf;
   CK(dSizes.alloc((size_t)W * 8));
-  const uint64_t myBytes = mine.size();
   CK(cudaMemcpyAsync(dSizes.as<uint64_t>() + comm->rank, &myBytes, 8, cudaMemcpyHostToDevice, st));
   NK(nccl().AllGather(dSizes.as<uint64_t>() + comm->rank, dSizes.p, 1, NCCL_UINT64, comm->comm, st));
-  std::vector<uint64_t> sizes(W);
+  sizes.assign(W, 0);
   CK(cudaMemcpyAsync(sizes.data(), dSizes.p, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   uint64_t mx = 16;
   for (int r = 0; r < W; ++r) mx = std::max(mx, sizes[r]);
   mx = (mx + 15) & ~15ull;
+  stride = mx;
   CK(dBuf.alloc((size_t)W * mx));
   uint8_t *slot = dBuf.as<uint8_t>() + (size_t)comm->rank * mx;
-  if (myBytes) CK(cudaMemcpyAsync(slot, mine.data(), myBytes, cudaMemcpyHostToDevice, st));
+  if (myBytes) CK(cudaMemcpyAsync(slot, mine, myBytes, cudaMemcpyHostToDevice, st));
   NK(nccl().AllGather(slot, dBuf.p, mx, NCCL_UINT8, comm->comm, st));
-  out.resize(W);
-  for (int r = 0; r < W; ++r) {
-    out[r].resize(sizes[r]);
-    if (sizes[r]) CK(cudaMemcpyAsync(out[r].data(), dBuf.as<uint8_t>() + (size_t)r * mx, sizes[r], cudaMemcpyDeviceToHost, st));
-  }
+  CK(recv.grow((size_t)W * mx, 0));
+  for (int r = 0; r < W; ++r)
+    if (sizes[r]) CK(cudaMemcpyAsync(recv.as<uint8_t>() + (size_t)r * mx, dBuf.as<uint8_t>() + (size_t)r * mx, sizes[r], cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return T1K_OK;
 }
@@ -1138,20 +1140,30 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   if (comm) {
     double tx = now_ms();
     if (int rc = t1k_coverage_allreduce(ref, comm)) return rc;
-    std::vector<uint8_t> mine;
-    serialize_groups(groups, mine);
-    mine.resize(mine.size() + 8);
-    memcpy(mine.data() + mine.size() - 8, &nAssignAll, 8);      // trailer: this rank's assignment count
-    std::vector<std::vector<uint8_t> > all;
-    if (int rc = allgather_blobs(ref, comm, mine, all)) return rc;
-    ReadGroups merged;
+    // this rank's table + trailer {assignments, fragments} into pinned memory, all-gathered, merged on the host threads
+    const size_t tableBytes = serialized_group_bytes(groups);
+    CK(ref->pinSend.grow(tableBytes + 16, 0));
+    serialize_groups(groups, ref->pinSend.as<uint8_t>());
+    const uint64_t trailer[2] = {nAssignAll, (uint64_t)n_frag};
+    memcpy(ref->pinSend.as<uint8_t>() + tableBytes, trailer, 16);
+    uint64_t stride = 0;
+    std::vector<uint64_t> sizes;
+    if (int rc = allgather_blobs(ref, comm, ref->pinSend.as<uint8_t>(), tableBytes + 16, ref->pinRecv, stride, sizes)) return rc;
+    std::vector<GroupBlobView> tables((size_t)comm->world);
+    std::vector<int64_t> fragBase((size_t)comm->world, 0);
     nAssignAll = 0;
+    int64_t fb = 0;
     for (int r = 0; r < comm->world; ++r) {
-      if (all[r].size() < 8 || !merge_groups(merged, all[r].data(), all[r].size() - 8)) return fail(T1K_ERR_NCCL, "malformed read-group table from a peer");
-      uint64_t na; memcpy(&na, all[r].data() + all[r].size() - 8, 8);
-      nAssignAll += na;
+      const uint8_t *blob = ref->pinRecv.as<uint8_t>() + (size_t)r * stride;
+      if (sizes[r] < 16 || !tables[r].parse(blob, sizes[r] - 16)) return fail(T1K_ERR_NCCL, "malformed read-group table from a peer");
+      uint64_t tr[2]; memcpy(tr, blob + sizes[r] - 16, 16);
+      nAssignAll += tr[0];
+      fragBase[r] = fb; fb += (int64_t)tr[1];
     }
+    ReadGroups merged;
+    if (!merge_tables_parallel(tables, fragBase, shards.threads(), merged)) return fail(T1K_ERR_NCCL, "malformed read-group table from a peer");
     groups.ptr.swap(merged.ptr); groups.ent.swap(merged.ent); groups.byHash.swap(merged.byHash);
+    groups.first.swap(merged.first); groups.hashes.swap(merged.hashes);
     groups.assignedFragments = merged.assignedFragments;
     res->ms_coalesce += (float)(now_ms() - tx);
   }

@@ -24,6 +24,7 @@ struct ReadGroups {
   std::vector<int64_t> ptr{0};
   std::vector<HostEntry> ent;
   std::vector<int64_t> first;          // per group: index of the fragment that created it (orders merged shards)
+  std::vector<uint64_t> hashes;        // per group: the allele-set hash it is filed under
   std::unordered_map<uint64_t, std::vector<int32_t> > byHash;
   int64_t assignedFragments = 0;
 
@@ -68,6 +69,7 @@ struct ReadGroups {
     ent.insert(ent.end(), row, row + n);
     ptr.push_back((int64_t)ent.size());
     first.push_back(fragIdx);
+    hashes.push_back(h);
   }
 };
 
@@ -99,6 +101,7 @@ struct GroupShards {
       out.ent.insert(out.ent.end(), P.ent.begin() + P.ptr[g], P.ent.begin() + P.ptr[g + 1]);
       out.ptr.push_back((int64_t)out.ent.size());
       out.first.push_back(P.first[g]);
+      out.hashes.push_back(P.hashes[g]);
     }
   }
 };
@@ -121,36 +124,88 @@ inline void GroupShards::add_chunk(const HostEntry *ent, const uint64_t *off, co
   for (size_t k = 0; k < th.size(); ++k) th[k].join();
 }
 
-// Relocatable image of a group table: [nGroups, nEntries, assignedFragments] then ptr[nGroups+1] then entries.
-inline void serialize_groups(const ReadGroups &G, std::vector<uint8_t> &blob) {
-  const uint64_t hdr[3] = {(uint64_t)G.size(), (uint64_t)G.ent.size(), (uint64_t)G.assignedFragments};
-  blob.resize(sizeof(hdr) + G.ptr.size() * 8 + G.ent.size() * sizeof(HostEntry));
-  uint8_t *p = blob.data();
+// Relocatable image of a group table: [nGroups, nEntries, assignedFragments, 0] then ptr[nGroups+1], hashes[nGroups],
+// first[nGroups], entries.
+struct GroupBlobView {
+  uint64_t nG = 0, nE = 0, assigned = 0;
+  const uint8_t *ptr = nullptr, *hashes = nullptr, *first = nullptr, *ent = nullptr;
+  bool parse(const uint8_t *blob, uint64_t bytes) {
+    uint64_t hdr[4];
+    if (bytes < sizeof(hdr)) return false;
+    memcpy(hdr, blob, sizeof(hdr));
+    nG = hdr[0]; nE = hdr[1]; assigned = hdr[2];
+    if (bytes < sizeof(hdr) + (nG + 1) * 8 + nG * 16 + nE * sizeof(HostEntry)) return false;
+    ptr = blob + sizeof(hdr); hashes = ptr + (nG + 1) * 8; first = hashes + nG * 8; ent = first + nG * 8;
+    return true;
+  }
+  bool row(uint64_t g, int64_t &b, int64_t &e) const {
+    memcpy(&b, ptr + g * 8, 8); memcpy(&e, ptr + (g + 1) * 8, 8);
+    return b >= 0 && e >= b && (uint64_t)e <= nE;
+  }
+  uint64_t hash(uint64_t g) const { uint64_t h; memcpy(&h, hashes + g * 8, 8); return h; }
+  int64_t first_frag(uint64_t g) const { int64_t f; memcpy(&f, first + g * 8, 8); return f; }
+  const HostEntry *entries(int64_t b) const { return (const HostEntry *)(ent + (size_t)b * sizeof(HostEntry)); }   // 8-byte aligned
+};
+
+inline size_t serialized_group_bytes(const ReadGroups &G) {
+  return 4 * 8 + G.ptr.size() * 8 + (size_t)G.size() * 16 + G.ent.size() * sizeof(HostEntry);
+}
+inline void serialize_groups(const ReadGroups &G, uint8_t *p) {
+  const uint64_t hdr[4] = {(uint64_t)G.size(), (uint64_t)G.ent.size(), (uint64_t)G.assignedFragments, 0};
   memcpy(p, hdr, sizeof(hdr)); p += sizeof(hdr);
   memcpy(p, G.ptr.data(), G.ptr.size() * 8); p += G.ptr.size() * 8;
+  if (G.size()) { memcpy(p, G.hashes.data(), (size_t)G.size() * 8); p += (size_t)G.size() * 8; memcpy(p, G.first.data(), (size_t)G.size() * 8); p += (size_t)G.size() * 8; }
   if (!G.ent.empty()) memcpy(p, G.ent.data(), G.ent.size() * sizeof(HostEntry));
+}
+inline void serialize_groups(const ReadGroups &G, std::vector<uint8_t> &blob) {
+  blob.resize(serialized_group_bytes(G));
+  serialize_groups(G, blob.data());
 }
 
 // Merge of another rank's table (read-sharded path): its groups are added in their own order, so merging the ranks'
 // tables in rank order visits the allele sets in the order a single process would first see them shard by shard.
 // float32 weights of equal allele sets add as (sum of rank 0) + (sum of rank 1) + ...
 inline bool merge_groups(ReadGroups &G, const uint8_t *blob, uint64_t bytes) {
-  uint64_t hdr[3];
-  if (bytes < sizeof(hdr)) return false;
-  memcpy(hdr, blob, sizeof(hdr));
-  const uint64_t nG = hdr[0], nE = hdr[1];
-  if (bytes < sizeof(hdr) + (nG + 1) * 8 + nE * sizeof(HostEntry)) return false;
-  const uint8_t *pp = blob + sizeof(hdr), *pe = pp + (nG + 1) * 8;
+  GroupBlobView V;
+  if (!V.parse(blob, bytes)) return false;
   std::vector<HostEntry> row;
-  for (uint64_t g = 0; g < nG; ++g) {
+  for (uint64_t g = 0; g < V.nG; ++g) {
     int64_t b, e;
-    memcpy(&b, pp + g * 8, 8); memcpy(&e, pp + (g + 1) * 8, 8);
-    if (b < 0 || e < b || (uint64_t)e > nE) return false;
-    row.resize((size_t)(e - b));
-    if (e > b) memcpy(row.data(), pe + (size_t)b * sizeof(HostEntry), (size_t)(e - b) * sizeof(HostEntry));
+    if (!V.row(g, b, e)) return false;
+    row.assign(V.entries(b), V.entries(e));
     G.add(row.data(), (uint32_t)(e - b), 0);
   }
-  G.assignedFragments += (int64_t)hdr[2];
+  G.assignedFragments += (int64_t)V.assigned;
+  return true;
+}
+
+// The same merge on T threads: thread t files the groups of hash partition t from rank 0, 1, ... (rank order inside every
+// partition), gather() restores the global first-appearance order from fragBase[r] + first.  All tables must carry
+// hashes of one kind (the pairing kernel's).
+inline bool merge_tables_parallel(const std::vector<GroupBlobView> &tables, const std::vector<int64_t> &fragBase, int T, ReadGroups &out) {
+  GroupShards M(T);
+  T = M.threads();
+  std::vector<char> ok((size_t)T, 1);
+  auto work = [&](int t) {
+    ReadGroups &G = M.part[t];
+    for (size_t r = 0; r < tables.size(); ++r) {
+      const GroupBlobView &V = tables[r];
+      for (uint64_t g = 0; g < V.nG; ++g) {
+        const uint64_t h = V.hash(g);
+        if ((int)((h >> 17) % (uint64_t)T) != t) continue;
+        int64_t b, e;
+        if (!V.row(g, b, e)) { ok[t] = 0; return; }
+        G.add(V.entries(b), (uint32_t)(e - b), 0, &h, fragBase[r] + V.first_frag(g));
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+  work(0);
+  for (size_t k = 0; k < th.size(); ++k) th[k].join();
+  for (int t = 0; t < T; ++t) if (!ok[t]) return false;
+  M.gather(out);
+  for (size_t r = 0; r < tables.size(); ++r) out.assignedFragments += (int64_t)tables[r].assigned;
   return true;
 }
 
