@@ -197,6 +197,7 @@ struct T1KRef {
   u32 candCap = 0;
   // two launch geometries of k_assign: [0] small hit tile (more resident warps), [1] tile for the worst case
   int gridBlocks[2] = {0, 0}, hitCap[2] = {0, 0};
+  int occ = 3;
   size_t scratchWarps = 0;
   u64 nPostings = 0;
   size_t memBudget = 0;      // free device memory right after the reference was uploaded (workspace budget; cudaMemGetInfo is
@@ -302,6 +303,11 @@ int setup_assign_launch(T1KRef *r, int maxLen) {
   int big = maxLen - KMER + 1 + 24;
   if (big < 64) big = 64;
   big = (big + 7) & ~7;
+  // occupancy variant: resident blocks per SM the kernel is compiled for, and the small hit tile that fits beside it
+  int occ = 3;      // measured: 3 blocks/SM at 168 registers (no spills) beats 4 at 128 and 5 at 96
+  if (const char *env = getenv("T1K_ASSIGN_OCC")) occ = atoi(env);
+  if (occ != 2 && occ != 3 && occ != 4) occ = 3;
+  r->occ = occ;
   int small = 64;
   if (const char *env = getenv("T1K_HIT_TILE")) small = std::max(8, atoi(env));
   if (small > big) small = big;
@@ -309,15 +315,16 @@ int setup_assign_launch(T1KRef *r, int maxLen) {
   const int caps[2] = {small, big};
   size_t maxSmem = 0;
   for (int c = 0; c < 2; ++c) maxSmem = std::max(maxSmem, ((warp_smem_bytes(caps[c]) + 15) & ~(size_t)15) * WARPS_PER_BLOCK);
-  CK(cudaFuncSetAttribute(k_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem));
+  const void *kfn = occ == 4 ? (const void *)k_assign<4> : occ == 3 ? (const void *)k_assign<3> : (const void *)k_assign<2>;
+  CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem));
   size_t warps = 0;
   for (int c = 0; c < 2; ++c) {
     const size_t smem = ((warp_smem_bytes(caps[c]) + 15) & ~(size_t)15) * WARPS_PER_BLOCK;
     int perSM = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_assign, WARPS_PER_BLOCK * 32, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kfn, WARPS_PER_BLOCK * 32, smem));
     if (perSM < 1) return fail(T1K_ERR_UNSUPPORTED, "k_assign does not fit on an SM");
     r->hitCap[c] = caps[c];
-    r->gridBlocks[c] = perSM * r->nSM;
+    r->gridBlocks[c] = std::min(perSM, occ) * r->nSM;
     warps = std::max(warps, (size_t)r->gridBlocks[c] * WARPS_PER_BLOCK);
   }
   u64 cap = 2ull * (u64)r->nAlleles + 2048;
@@ -421,7 +428,9 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
       P.hitCap = ref->hitCap[c];
       const size_t smem = ((warp_smem_bytes(ref->hitCap[c]) + 15) & ~(size_t)15) * WARPS_PER_BLOCK;
       CK(cudaMemsetAsync(ref->workCtr.p, 0, sizeof(unsigned int), st));
-      k_assign<<<ref->gridBlocks[c], WARPS_PER_BLOCK * 32, smem, st>>>(P);
+      if (ref->occ == 4) k_assign<4><<<ref->gridBlocks[c], WARPS_PER_BLOCK * 32, smem, st>>>(P);
+      else if (ref->occ == 3) k_assign<3><<<ref->gridBlocks[c], WARPS_PER_BLOCK * 32, smem, st>>>(P);
+      else k_assign<2><<<ref->gridBlocks[c], WARPS_PER_BLOCK * 32, smem, st>>>(P);
       CK(cudaGetLastError());
       ++a->launches;
     }

@@ -412,15 +412,19 @@ T1K_HDN T1K_NOINLINE inline int align_matches_cold(const AlleleView &T, int tpos
   for (int i = 0; i < n; ++i) c += ops[i] == 0;
   return c;
 }
-T1K_HDN T1K_NOINLINE inline int align_matches(const AlleleView &T, int tpos, int lent, const ReadView &Q, int ppos, int lenp, const LaneScratch &S,
-                                 int &err) {
+// the hot part alone: < 0 when the stretch needs the cold path
+T1K_HDN T1K_NOINLINE inline int align_matches_hot(const AlleleView &T, int tpos, int lent, const ReadView &Q, int ppos, int lenp) {
   if (lent == 0 || lenp == 0) return 0;
-  T1K_COUNT(4, 1);
   if (lent == lenp && lent <= 32) {
     const int mm = popc64(mm_chunk(T, tpos, Q, ppos, lent));
     if (mm <= 3) return lent - mm;
   }
-  return align_matches_cold(T, tpos, lent, Q, ppos, lenp, S, err);
+  return -1;
+}
+T1K_HD int align_matches(const AlleleView &T, int tpos, int lent, const ReadView &Q, int ppos, int lenp, const LaneScratch &S, int &err) {
+  T1K_COUNT(4, 1);
+  const int m = align_matches_hot(T, tpos, lent, Q, ppos, lenp);
+  return m >= 0 ? m : align_matches_cold(T, tpos, lent, Q, ppos, lenp, S, err);
 }
 
 // any N inside [s, e] of an N plane that starts at the allele's first word
@@ -567,52 +571,13 @@ struct ChainDirect {   // contiguous run of a hit store
   T1K_HD u32 operator()(int i) const { return p[(size_t)i * stride]; }
 };
 
-// ---- SeqSet::GetOverlapsFromHits for one (strand, allele) group (SeqSet.hpp:1303-1553; filter=0, isRef).
-// hits: n encoded hits at h[i*stride]; on entry sorted by (readOffset, seqOffset); sorted in place by diagonal.
-// Scratch use of the general (multi-diagonal) path: conc/chain/top/link live in S.dir().
-T1K_HDN T1K_NOINLINE inline void chain_allele(const RefView &R, const ReadView &Q, int strand01, int seqIdx, u32 *h, int stride, int n,
-                                 const LaneScratch &S, int &nEmit, u64 &bestStrandKey, int &err) {
-  if (n < 3) return;
-  // insertion sort by (diag, b, a); a single-diagonal group is already in order
-  T1K_NOUNROLL
-  for (int i = 1; i < n; ++i) {
-    u32 v = h[(size_t)i * stride];
-    if (!hit_diag_less(v, h[(size_t)(i - 1) * stride])) continue;
-    int j = i - 1;
-    T1K_NOUNROLL
-    while (j >= 0 && hit_diag_less(v, h[(size_t)j * stride])) { h[(size_t)(j + 1) * stride] = h[(size_t)j * stride]; --j; }
-    h[(size_t)(j + 1) * stride] = v;
-  }
-  int dom = 0;
-  T1K_NOUNROLL
-  for (int s = 0; s < n;) {
-    int e, cur, curCnt = 1, domCnt = 0, prevC;
-    { u32 v = h[(size_t)s * stride]; cur = hit_a(v) - hit_b(v); prevC = cur; }
-    T1K_NOUNROLL
-    for (e = s + 1; e < n; ++e) {
-      u32 v = h[(size_t)e * stride];
-      int c = hit_a(v) - hit_b(v);
-      int diff = c - prevC;               // sorted ascending: diff >= 0
-      if (diff > RADIUS) break;
-      if (diff == 0) ++curCnt;
-      else {
-        if (curCnt > domCnt) { dom = cur; domCnt = curCnt; }
-        cur = c; curCnt = 1;
-      }
-      prevC = c;
-    }
-    if (curCnt > domCnt) dom = cur;
-    int m = e - s;
-    if (m < 3 || m * KMER < HIT_LEN_REQ) { s = e; continue; }
-    u32 first = h[(size_t)s * stride], last = h[(size_t)(e - 1) * stride];
-    if (hit_a(first) - hit_b(first) == hit_a(last) - hit_b(last)) {
-      // one diagonal: every read offset occurs once, (b,a) order == current order, LIS keeps everything
-      ChainDirect cd; cd.p = h + (size_t)s * stride; cd.stride = stride;
-      consume_chain<true>(R, Q, strand01, seqIdx, cd, m, S, nEmit, bestStrandKey, err);
-      s = e; continue;
-    }
+// the multi-diagonal cluster [s, e) of chain_allele: closest-to-dominant hit per read offset, LIS, chain (rare: kept out
+// of line so that the common single-diagonal path stays small)
+T1K_HDN T1K_NOINLINE inline void chain_cluster_general(const RefView &R, const ReadView &Q, int strand01, int seqIdx, u32 *h, int stride, int s, int e,
+                                          int dom, const LaneScratch &S, int &nEmit, u64 &bestStrandKey, int &err) {
+  const int m = e - s;
     // general path (SeqSet.hpp:1437-1456 + LIS :352-436)
-    if ((size_t)m * 12 + 512 > (size_t)SCR_DIR) { err |= ERR_SCRATCH; s = e; continue; }
+    if ((size_t)m * 12 + 512 > (size_t)SCR_DIR) { err |= ERR_SCRATCH; return; }
     u16 *used = (u16 *)S.dir();                 // min |diag - dom| per read offset
     u32 *conc = (u32 *)(S.dir() + 512);
     u32 *chain = conc + m;
@@ -675,22 +640,72 @@ T1K_HDN T1K_NOINLINE inline void chain_allele(const RefView &R, const ReadView &
       if (i == 0 || hit_b(chain[i]) != hit_b(chain[sz - 1])) chain[sz++] = chain[i];
     // the chain was built in S.dir(), which consume_chain's gap DPs overwrite: park it in its own region
     u32 *park = S.chain();
-    if (sz > SCR_CHAIN / 4) { err |= ERR_SCRATCH; s = e; continue; }
+    if (sz > SCR_CHAIN / 4) { err |= ERR_SCRATCH; return; }
     T1K_NOUNROLL
     for (int i = 0; i < sz; ++i) park[i] = chain[i];
     ChainDirect cd; cd.p = park; cd.stride = 1;
     consume_chain<false>(R, Q, strand01, seqIdx, cd, sz, S, nEmit, bestStrandKey, err);
+}
+
+// ---- SeqSet::GetOverlapsFromHits for one (strand, allele) group (SeqSet.hpp:1303-1553; filter=0, isRef).
+// hits: n encoded hits at h[i*stride]; on entry sorted by (readOffset, seqOffset); sorted in place by diagonal.
+// Scratch use of the general (multi-diagonal) path: conc/chain/top/link live in S.dir().
+T1K_HDN T1K_NOINLINE inline void chain_allele(const RefView &R, const ReadView &Q, int strand01, int seqIdx, u32 *h, int stride, int n,
+                                 const LaneScratch &S, int &nEmit, u64 &bestStrandKey, int &err) {
+  if (n < 3) return;
+  // insertion sort by (diag, b, a); a single-diagonal group is already in order
+  T1K_NOUNROLL
+  for (int i = 1; i < n; ++i) {
+    u32 v = h[(size_t)i * stride];
+    if (!hit_diag_less(v, h[(size_t)(i - 1) * stride])) continue;
+    int j = i - 1;
+    T1K_NOUNROLL
+    while (j >= 0 && hit_diag_less(v, h[(size_t)j * stride])) { h[(size_t)(j + 1) * stride] = h[(size_t)j * stride]; --j; }
+    h[(size_t)(j + 1) * stride] = v;
+  }
+  int dom = 0;
+  T1K_NOUNROLL
+  for (int s = 0; s < n;) {
+    int e, cur, curCnt = 1, domCnt = 0, prevC;
+    { u32 v = h[(size_t)s * stride]; cur = hit_a(v) - hit_b(v); prevC = cur; }
+    T1K_NOUNROLL
+    for (e = s + 1; e < n; ++e) {
+      u32 v = h[(size_t)e * stride];
+      int c = hit_a(v) - hit_b(v);
+      int diff = c - prevC;               // sorted ascending: diff >= 0
+      if (diff > RADIUS) break;
+      if (diff == 0) ++curCnt;
+      else {
+        if (curCnt > domCnt) { dom = cur; domCnt = curCnt; }
+        cur = c; curCnt = 1;
+      }
+      prevC = c;
+    }
+    if (curCnt > domCnt) dom = cur;
+    int m = e - s;
+    if (m < 3 || m * KMER < HIT_LEN_REQ) { s = e; continue; }
+    u32 first = h[(size_t)s * stride], last = h[(size_t)(e - 1) * stride];
+    if (hit_a(first) - hit_b(first) == hit_a(last) - hit_b(last)) {
+      // one diagonal: every read offset occurs once, (b,a) order == current order, LIS keeps everything
+      ChainDirect cd; cd.p = h + (size_t)s * stride; cd.stride = stride;
+      consume_chain<true>(R, Q, strand01, seqIdx, cd, m, S, nEmit, bestStrandKey, err);
+      s = e; continue;
+    }
+    chain_cluster_general(R, Q, strand01, seqIdx, h, stride, s, e, dom, S, nEmit, bestStrandKey, err);
     s = e;
   }
 }
 
 // ---- SeqSet::ExtendOverlap (SeqSet.hpp:1994-2100) + the separator tests of AssignRead (SeqSet.hpp:2163-2169)
-T1K_HDN T1K_NOINLINE inline void extend_cand(const RefView &R, const ReadView &Q, Cand &c, const LaneScratch &S, int &err) {
+// HOT: only the one-word comparisons are allowed; returns false (c untouched) when an overhang needs the cold path, so
+// that the caller can run those candidates together afterwards instead of stalling the warp on a few lanes.
+template <bool HOT>
+T1K_HDN T1K_NOINLINE inline bool extend_cand(const RefView &R, const ReadView &Q, Cand &c, const LaneScratch &S, int &err) {
   const AlleleView T = allele_view(R, c.seqIdx, Q);
   const int clen = T.len, len = Q.len;
   int rs = c.readStart, re = c.readEnd, ss = c.seqStart, se = c.seqEnd;
   u8 flags = 0;
-  if (sep_in_range(T, ss, se)) { c.flags = CF_SEP; return; }
+  if (sep_in_range(T, ss, se)) { c.flags = CF_SEP; return true; }
   if (sep_in_range(T, ss - rs, se + (len - re - 1))) flags |= CF_NEEDCLIP;
   int lo = imin(rs, ss), leftClip = 0, rightClip = 0;
   if (rs > ss) leftClip = rs - ss;
@@ -699,7 +714,8 @@ T1K_HDN T1K_NOINLINE inline void extend_cand(const RefView &R, const ReadView &Q
     for (int i = 0; i < lo; ++i)
       if (base2(T.n2, ss - i - 1)) { leftClip = lo - i; lo = i; break; }
   }
-  int m = align_matches(T, ss - lo, lo, Q, rs - lo, lo, S, err);
+  int m = HOT ? align_matches_hot(T, ss - lo, lo, Q, rs - lo, lo) : align_matches(T, ss - lo, lo, Q, rs - lo, lo, S, err);
+  if (HOT && m < 0) return false;
   int ro = imin(len - 1 - re, clen - 1 - se);
   if (len - 1 - re > clen - 1 - se) rightClip = len - 1 - re - (clen - 1 - se);
   if (T.hasN) {
@@ -707,7 +723,11 @@ T1K_HDN T1K_NOINLINE inline void extend_cand(const RefView &R, const ReadView &Q
     for (int i = 0; i < ro; ++i)
       if (base2(T.n2, se + 1 + i)) { rightClip = ro - i; ro = i; break; }
   }
-  m += align_matches(T, se + 1, ro, Q, re + 1, ro, S, err);
+  {
+    const int m2 = HOT ? align_matches_hot(T, se + 1, ro, Q, re + 1, ro) : align_matches(T, se + 1, ro, Q, re + 1, ro, S, err);
+    if (HOT && m2 < 0) return false;
+    m += m2;
+  }
   c.eReadStart = (u8)(rs - lo); c.eReadEnd = (u8)(re + ro);
   c.eSeqStart = ss - lo; c.eSeqEnd = se + ro;
   int mc = 2 * m + c.matchCnt;
@@ -717,6 +737,7 @@ T1K_HDN T1K_NOINLINE inline void extend_cand(const RefView &R, const ReadView &Q
   c.relaxed = mc;                                  // SeqSet.hpp:2068 (before the clip bonus)
   c.eMatchCnt = mc + 2 * leftClip + 2 * rightClip;
   c.flags = flags;
+  return true;
 }
 
 T1K_HD void cov_add(int32_t *p, int v) {
@@ -784,7 +805,9 @@ T1K_HDN T1K_NOINLINE inline void full_align_cold(const RefView &R, const ReadVie
   c.relaxed = R.relax ? 2 * m : c.eMatchCnt;
 }
 
-T1K_HDN T1K_NOINLINE inline void full_align(const RefView &R, const ReadView &Q, Cand &c, int weight, const LaneScratch &S, int &err) {
+// HOT: returns false (nothing written, no coverage added) when the window needs full_align_cold.
+template <bool HOT>
+T1K_HDN T1K_NOINLINE inline bool full_align(const RefView &R, const ReadView &Q, Cand &c, int weight, const LaneScratch &S, int &err) {
   const AlleleView T = allele_view(R, c.seqIdx, Q);
   const int tpos = c.eSeqStart, ppos = c.eReadStart;
   const int lent = c.eSeqEnd - c.eSeqStart + 1, lenp = c.eReadEnd - c.eReadStart + 1;
@@ -806,6 +829,8 @@ T1K_HDN T1K_NOINLINE inline void full_align(const RefView &R, const ReadView &Q,
         mm += popc64(d);
       }
     }
+  }
+  if (lent == lenp) {
     if (mm <= 3 && !T.useN) {
       if (weight > 0) {
         int32_t *covDiff = R.covDiff + (size_t)R.wordOff[c.seqIdx] * 32, *covPoint = R.covPoint + (size_t)R.wordOff[c.seqIdx] * 32;
@@ -815,10 +840,12 @@ T1K_HDN T1K_NOINLINE inline void full_align(const RefView &R, const ReadView &Q,
         if (mm > 2) cov_add(covPoint + tpos + p2, -weight);
       }
       c.relaxed = R.relax ? 2 * (lent - exMm) : c.eMatchCnt;
-      return;
+      return true;
     }
   }
+  if (HOT) return false;
   full_align_cold(R, Q, T, c, weight, mm, exMm, S, err);
+  return true;
 }
 
 // post-extension denominators / keys

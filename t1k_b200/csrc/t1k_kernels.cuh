@@ -51,37 +51,24 @@ struct AssignParams {
   int hitCap;              // hits per allele kept in shared memory
 };
 
-__device__ __forceinline__ u32 warp_min_u32(u32 v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
-  return v;
-}
-__device__ __forceinline__ int warp_max_i32(int v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
-  return v;
-}
-__device__ __forceinline__ int warp_sum_i32(int v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-  return v;
-}
+// warp reductions on the redux unit (one instruction per 32-bit reduction; the kernel is instruction-footprint bound)
+__device__ __forceinline__ u32 warp_min_u32(u32 v) { return __reduce_min_sync(FULL, v); }
+__device__ __forceinline__ int warp_max_i32(int v) { return __reduce_max_sync(FULL, v); }
+__device__ __forceinline__ int warp_sum_i32(int v) { return __reduce_add_sync(FULL, v); }
 __device__ __forceinline__ u64 warp_max_u64(u64 v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) { u64 t = __shfl_xor_sync(FULL, v, o); v = t > v ? t : v; }
-  return v;
+  const u32 hi = __reduce_max_sync(FULL, (u32)(v >> 32));
+  const u32 lo = __reduce_max_sync(FULL, (u32)(v >> 32) == hi ? (u32)v : 0u);
+  return ((u64)hi << 32) | lo;
 }
 __device__ __forceinline__ u64 warp_min_u64(u64 v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) { u64 t = __shfl_xor_sync(FULL, v, o); v = t < v ? t : v; }
-  return v;
+  const u32 hi = __reduce_min_sync(FULL, (u32)(v >> 32));
+  const u32 lo = __reduce_min_sync(FULL, (u32)(v >> 32) == hi ? (u32)v : 0xffffffffu);
+  return ((u64)hi << 32) | lo;
 }
 // lexicographic min of (key, idx) over the warp
 __device__ __forceinline__ void warp_min_pair(u64 &key, int &idx) {
-  u64 k = warp_min_u64(key);
-  int i = key == k ? idx : 0x7fffffff;
-#pragma unroll
-  for (int o = 16; o; o >>= 1) i = min(i, __shfl_xor_sync(FULL, i, o));
+  const u64 k = warp_min_u64(key);
+  const int i = __reduce_min_sync(FULL, key == k ? idx : 0x7fffffff);
   key = k; idx = i;
 }
 __device__ __forceinline__ bool pair_less(u64 k, int i, u64 fk, int fi) { return k < fk || (k == fk && i < fi); }
@@ -322,15 +309,41 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
     __threadfence_block();
     __syncwarp();
     // pass 1: extension; first candidate (list order) whose extension fails
+    // Two-speed loop: every candidate first tries the hot path (one-word overhang comparisons); the few that need
+    // certificates or the DP are queued (W.cur is free after the gather) and run 32 at a time, all lanes busy.
     u64 fKey = ~0ull; int fIdx = 0x7fffffff;
+    int qn = 0;
     T1K_NOUNROLL
-    for (int i = c0 + lane; i < c1; i += 32) {
-      Cand c = cands[i];
-      extend_cand(R, Qv, c, S, err);
-      cands[i] = c;
-      if (!(c.flags & CF_SEP) && !(c.flags & CF_RET)) {
-        u64 k = cand_key_pre(c);
-        if (pair_less(k, i, fKey, fIdx)) { fKey = k; fIdx = i; }
+    for (int b = c0; b < c1 || qn > 0; b += 32) {
+      int i = b + lane;
+      bool have = i < c1, cold = false;
+      Cand c;
+      if (have) { c = cands[i]; cold = !extend_cand<true>(R, Qv, c, S, err); }
+      const unsigned bal = __ballot_sync(FULL, cold);
+      if (cold) { W.cur[qn + __popc(bal & ((1u << lane) - 1))] = (u32)i; have = false; }
+      qn += __popc(bal);
+      __syncwarp();
+      if (qn >= 32 || (b + 32 >= c1 && qn > 0)) {          // flush a full batch, or the remainder at the end
+        const int take = min(qn, 32);
+        if (lane < take) {
+          if (have) {                                       // this lane's hot result first
+            cands[i] = c;
+            if (!(c.flags & CF_SEP) && !(c.flags & CF_RET)) { u64 k = cand_key_pre(c); if (pair_less(k, i, fKey, fIdx)) { fKey = k; fIdx = i; } }
+          }
+          i = (int)W.cur[qn - take + lane];
+          c = cands[i];
+          extend_cand<false>(R, Qv, c, S, err);
+          have = true;
+        }
+        qn -= take;
+        __syncwarp();
+      }
+      if (have) {
+        cands[i] = c;
+        if (!(c.flags & CF_SEP) && !(c.flags & CF_RET)) {
+          u64 k = cand_key_pre(c);
+          if (pair_less(k, i, fKey, fIdx)) { fKey = k; fIdx = i; }
+        }
       }
     }
     warp_min_pair(fKey, fIdx);
@@ -367,13 +380,34 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
     if (!deferred) {
       // pass 4: full-read alignment of everything within 10 of the best (Q8)
       if (weight >= 0) {
+        int qn = 0;                                          // same two-speed structure as the extension pass
         T1K_NOUNROLL
-        for (int i = c0 + lane; i < c1; i += 32) {
-          Cand c = cands[i];
-          if (!(c.flags & CF_INCLUDE)) continue;
-          if (c.eMatchCnt >= bestMc - 10) full_align(R, Qv, c, weight, S, err);
-          else c.relaxed = 0;
-          cands[i].relaxed = c.relaxed;
+        for (int b = c0; b < c1 || qn > 0; b += 32) {
+          const int i = b + lane;
+          bool cold = false;
+          if (i < c1) {
+            Cand c = cands[i];
+            if (c.flags & CF_INCLUDE) {
+              if (c.eMatchCnt >= bestMc - 10) cold = !full_align<true>(R, Qv, c, weight, S, err);
+              else c.relaxed = 0;
+              if (!cold) cands[i].relaxed = c.relaxed;
+            }
+          }
+          const unsigned bal = __ballot_sync(FULL, cold);
+          if (cold) W.cur[qn + __popc(bal & ((1u << lane) - 1))] = (u32)i;
+          qn += __popc(bal);
+          __syncwarp();
+          if (qn >= 32 || (b + 32 >= c1 && qn > 0)) {
+            const int take = min(qn, 32);
+            if (lane < take) {
+              const int j = (int)W.cur[qn - take + lane];
+              Cand c = cands[j];
+              full_align<false>(R, Qv, c, weight, S, err);
+              cands[j].relaxed = c.relaxed;
+            }
+            qn -= take;
+            __syncwarp();
+          }
         }
       }
       __syncwarp();
@@ -438,10 +472,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
   }
   err = __reduce_or_sync(FULL, (unsigned)err);
   if (lane == 0 && err) atomicOr(P.O.err, err);
-  if (P.O.stats) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) stPost += __shfl_xor_sync(FULL, stPost, o);
-  }
+  if (P.O.stats) stPost = __reduce_add_sync(FULL, (u32)stPost);     // < 2^32 postings per read-end
   if (lane == 0 && P.O.stats) {
     atomicAdd(P.O.stats + 0, stPost);
     atomicAdd(P.O.stats + 1, (unsigned long long)nCand);
@@ -451,7 +482,9 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
 
 extern __shared__ u64 t1k_smem[];
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) k_assign(AssignParams P) {
+// MINB = resident blocks per SM the register budget is compiled for (4: 128 registers, 5: 96, 6: 80)
+template <int MINB>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_assign(AssignParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t gwarp = (size_t)blockIdx.x * WARPS_PER_BLOCK + warp;
   u8 *sm = (u8 *)t1k_smem + (size_t)warp * ((warp_smem_bytes(P.hitCap) + 15) & ~(size_t)15);

@@ -237,8 +237,7 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
         if (ab.valid) k1 = max(k1, ((u32)ab.mc << 12) | (u32)(4095 - ab.denom));
       }
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) k1 = max(k1, __shfl_xor_sync(FULL, k1, o));
+    k1 = __reduce_max_sync(FULL, k1);
     if (k1 != 0) {
       const int bestMc = (int)(k1 >> 12), bestDen = 4095 - (int)(k1 & 4095);
       // pass 2: relaxedMatchCnt of the first allele (assign order) that reaches the best

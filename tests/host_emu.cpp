@@ -121,7 +121,7 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
   // pass 1: extension + first failing key
   u64 fKey = ~0ull; int fIdx = 0x7fffffff;
   for (int i = c0; i < c1; ++i) {
-    extend_cand(R, Q, cands[i], S, err);
+    extend_cand<false>(R, Q, cands[i], S, err);
     Cand &c = cands[i];
     if (!(c.flags & CF_SEP) && !(c.flags & CF_RET)) {
       u64 k = cand_key_pre(c);
@@ -151,7 +151,7 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
     Cand &c = cands[i];
     if (!(c.flags & CF_INCLUDE)) continue;
     if (weight >= 0) {
-      if (c.eMatchCnt >= bestMc - 10) full_align(R, Q, c, weight, S, err);
+      if (c.eMatchCnt >= bestMc - 10) full_align<false>(R, Q, c, weight, S, err);
       else c.relaxed = 0;
     }
   }
