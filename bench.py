@@ -94,6 +94,19 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(fragments_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE k_assign launch from the committed ncu capture
+    (profiles/k_assign_traffic.json, written by tools/ncu_traffic.py); None unless the capture's launch size is the bench's."""
+    p = os.path.join(ROOT, "profiles", "k_assign_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        t = json.load(f)
+    if int(t.get("fragments_per_launch", -1)) != int(fragments_per_launch):
+        return None, "profiles/k_assign_traffic.json is for %s fragments per launch" % t.get("fragments_per_launch")
+    return int(t["dram_bytes_per_launch"]), t.get("source")
+
+
 def reference_arm(args, rank):
     """The reference's own CPU implementation (oracle/_ref/genotyper, compiled unmodified from /root/reference) on the
     box's host cores, all threads, on a bounded sample of the same workload.  Rate = slope between two sample sizes so
@@ -226,9 +239,13 @@ def main():
     # roofline of the dominant kernel (k_assign): algorithmic bytes per read-end = ceil(L/4) + 8 B per posting read +
     # 40 B per record kept, over the CUDA-event duration of its launches in the last timed step
     peak, peak_src = measured_peaks()
-    alg_bytes = 38 * out["n_unique_ends"] + 8 * out["n_postings"] + 40 * out["n_overlaps"]
-    k_ms = out["ms_align_kernel"]
+    # k_assign is launched once per chunk of T1K_CHUNK_FRAGMENTS fragments (default 2^18): per-launch figures = per-step / chunks
+    chunk = int(os.environ.get("T1K_CHUNK_FRAGMENTS", 1 << 18))
+    n_chunks = max(1, -(-args.pairs // chunk))
+    alg_bytes = (38 * out["n_unique_ends"] + 8 * out["n_postings"] + 40 * out["n_overlaps"]) / n_chunks
+    k_ms = out["ms_align_kernel"] / n_chunks
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    traffic, traffic_src = measured_traffic(min(args.pairs, chunk))
     d2h = int(out["n_assignments"] * 24 + out["n_unique_ends"] * 16)
     line = {
         "metric": METRIC, "value": total_frag / dev_max if dev_max > 0 else 0.0, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -246,7 +263,8 @@ def main():
                                                             "ms_pair_kernel", "ms_em_kernel")}},
         "gpu_launches": launches,
         "roofline": {"kernel": "k_assign", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": k_ms,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
+                     "kernel_ms": k_ms, "launches_per_step": n_chunks,
                      "note": "k_assign is integer-ALU/latency bound (chaining + banded alignment per (read, allele)); HBM fraction is honest but not its roof"},
         "clocks": clocks,
     }

@@ -189,7 +189,7 @@ struct T1KRef {
   std::vector<u64> wordOff;
   std::vector<int32_t> len;
   size_t paddedBases = 0;
-  DevMem seq2, n2, ex2, dWordOff, dLen, dHasN, kstart, post, covDiff, covPoint, covFinal;
+  DevMem seq2, n2, ex2, dWordOff, dLen, dHasN, dMeta, dSimThr, kstart, post, covDiff, covPoint, covFinal;
   RefView R;
   cudaStream_t stream = nullptr;
   // launch state of k_assign, sized on first use
@@ -211,7 +211,7 @@ struct T1KRef {
 struct T1KAssignment {
   T1KRef *ref = nullptr;
   u32 nReads = 0;
-  DevMem store, storeCtr, readOff, readCnt, readRet, dMaxCnt;
+  DevMem store, storeCtr, readOff, readCnt, readRet, readTop, dMaxCnt;
   u64 storeCap = 0, storeUsed = 0;
   u32 maxCnt = 0;
   unsigned long long stats[4] = {0, 0, 0, 0};
@@ -259,9 +259,12 @@ int t1k_ref_create(const T1KRefDesc *d, T1KRef **out) {
     if (e == cudaSuccess) e = cudaMemcpy(r->dst.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice); \
     if (e != cudaSuccess) { delete r; return fail(T1K_ERR_CUDA, std::string("t1k_ref_create upload: ") + cudaGetErrorString(e)); } \
   } while (0)
-  UP(seq2, P.seq2); UP(n2, P.n2); UP(ex2, P.ex2); UP(dWordOff, P.wordOff); UP(dLen, P.len); UP(dHasN, P.hasN); UP(kstart, P.kstart);
+  UP(seq2, P.seq2); UP(n2, P.n2); UP(ex2, P.ex2); UP(dWordOff, P.wordOff); UP(dLen, P.len); UP(dHasN, P.hasN); UP(dMeta, P.meta); UP(kstart, P.kstart);
   if (P.post.empty()) P.post.resize(1);
   UP(post, P.post);
+  std::vector<u16> simThr(2 * SIM_DEN);
+  sim_threshold_table(d->similarity, simThr.data());
+  UP(dSimThr, simThr);
 #undef UP
   const size_t covBytes = r->paddedBases * sizeof(int32_t);
   e = r->covDiff.alloc(covBytes);
@@ -273,7 +276,7 @@ int t1k_ref_create(const T1KRefDesc *d, T1KRef **out) {
   if (e != cudaSuccess) { delete r; return fail(T1K_ERR_CUDA, std::string("t1k_ref_create: ") + cudaGetErrorString(e)); }
   RefView &R = r->R;
   R.seq2 = r->seq2.as<u64>(); R.n2 = r->n2.as<u64>(); R.ex2 = r->ex2.as<u64>();
-  R.wordOff = r->dWordOff.as<u64>(); R.len = r->dLen.as<int32_t>(); R.hasN = r->dHasN.as<u8>();
+  R.wordOff = r->dWordOff.as<u64>(); R.len = r->dLen.as<int32_t>(); R.hasN = r->dHasN.as<u8>(); R.meta = r->dMeta.as<AlleleMeta>(); R.simThr = r->dSimThr.as<u16>();
   R.kstart = r->kstart.as<u32>(); R.post = r->post.as<Posting>();
   R.covDiff = r->covDiff.as<int32_t>(); R.covPoint = r->covPoint.as<int32_t>();
   R.nAlleles = d->n_alleles; R.sim = d->similarity; R.relax = d->relax_intron;
@@ -374,7 +377,7 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   DevMem dBases, dOff, dLen, dW, planes, len16;
   CK(dBases.alloc(total)); CK(dOff.alloc((size_t)n * 8)); CK(dLen.alloc((size_t)n * 4)); CK(dW.alloc((size_t)n * 4));
   CK(planes.alloc((size_t)n * 4 * RWORDS * 8)); CK(len16.alloc((size_t)n * 2));
-  CK(a->readOff.alloc((size_t)n * 8)); CK(a->readCnt.alloc((size_t)n * 4)); CK(a->readRet.alloc((size_t)n * 4));
+  CK(a->readOff.alloc((size_t)n * 8)); CK(a->readCnt.alloc((size_t)n * 4)); CK(a->readRet.alloc((size_t)n * 4)); CK(a->readTop.alloc((size_t)n * 4));
   CK(a->storeCtr.alloc(8)); CK(a->dMaxCnt.alloc(4));
   CK(cudaMemsetAsync(a->dMaxCnt.p, 0, 4, st));
   if (n == 0) { guard.a = nullptr; *out = a; return T1K_OK; }
@@ -402,10 +405,11 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   P.R = ref->R;
   P.Q.planes = planes.as<u64>(); P.Q.len = len16.as<u16>(); P.Q.weight = dW.as<int32_t>(); P.Q.workList = nullptr; P.Q.nWork = n;
   P.O.store = a->store.as<Rec>(); P.O.storeCtr = a->storeCtr.as<unsigned long long>(); P.O.storeCap = cap;
-  P.O.readOff = a->readOff.as<u64>(); P.O.readCnt = a->readCnt.as<u32>(); P.O.readRet = a->readRet.as<int32_t>();
+  P.O.readOff = a->readOff.as<u64>(); P.O.readCnt = a->readCnt.as<u32>(); P.O.readRet = a->readRet.as<int32_t>(); P.O.readTop = a->readTop.as<u32>();
   P.O.maxCnt = a->dMaxCnt.as<u32>();
   P.O.err = ref->errFlag.as<int>(); P.O.stats = ref->stats.as<unsigned long long>();
   P.candBuf = ref->candBuf.as<Cand>(); P.candCap = ref->candCap; P.laneScratch = ref->laneScratch.as<u8>();
+  { const char *env = getenv("T1K_NO_FAST"); P.noFast = (env && atoi(env) != 0) ? 1 : 0; }
   P.workCtr = ref->workCtr.as<unsigned int>();
   DevMem workList[2];
   std::vector<int32_t> hRet;
@@ -673,6 +677,8 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
   cudaEvent_t ev0, ev1;
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
   struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
+  int pairOcc = 4;
+  if (const char *env = getenv("T1K_PAIR_OCC")) pairOcc = atoi(env) == 3 ? 3 : 4;
   PhaseTimer pt;
   // output rows are appended through a device counter; a first guess of the capacity, then (rarely) one exact re-run
   const size_t freeB = ref->memBudget > a->store.bytes ? ref->memBudget - a->store.bytes : ((size_t)1 << 30);
@@ -687,7 +693,7 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
     CK(cudaMemsetAsync(dCtr.p, 0, 4, st));
     CK(cudaMemsetAsync(dOutCtr.p, 0, 8, st));
     PairParams P;
-    P.R = ref->R; P.store = a->store.as<Rec>(); P.readOff = a->readOff.as<u64>(); P.readCnt = a->readCnt.as<u32>();
+    P.R = ref->R; P.store = a->store.as<Rec>(); P.readOff = a->readOff.as<u64>(); P.readCnt = a->readCnt.as<u32>(); P.readTop = a->readTop.as<u32>();
     P.end1 = dE1.as<u32>(); P.end2 = end2 ? dE2.as<u32>() : nullptr; P.hasN = hasN ? dN.as<u8>() : nullptr;
     P.fragBase = 0; P.nFrag = nFrag; P.maxAssign = maxAssign;
     P.out = dOut.as<PairEntry>(); P.outCap = cap; P.outCtr = dOutCtr.as<unsigned long long>(); P.rowOff = dRowOff.as<u64>();
@@ -699,7 +705,7 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
     // ... and the staging row: a row longer than -n is cut, so -n entries suffice
     const size_t stageCap = (maxAssign > 0 && (size_t)maxAssign < b0Stride) ? (size_t)maxAssign : b0Stride;
     if (attempt == 0) {
-      CK(dB0.alloc((size_t)blocks * 4 * b0Stride * 4));
+      CK(dB0.alloc((size_t)blocks * 4 * b0Stride * 2 * 4));      // per warp: b0[b0Stride] + keys[b0Stride]
       CK(dStage.alloc((size_t)blocks * 4 * stageCap * sizeof(PairEntry)));
       if (wantOrder) { CK(dStageKey.alloc((size_t)blocks * 4 * stageCap * 8)); CK(dStageIdx.alloc((size_t)blocks * 4 * stageCap * 4)); }
     }
@@ -707,7 +713,7 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
     P.stage = dStage.as<PairEntry>(); P.stageCap = (u32)stageCap;
     P.stageKey = wantOrder ? dStageKey.as<u64>() : nullptr; P.stageIdx = wantOrder ? dStageIdx.as<u32>() : nullptr;
     CK(cudaEventRecord(ev0, st));
-    k_pair<<<blocks, 128, 0, st>>>(P);
+    if (pairOcc == 3) k_pair<3><<<blocks, 128, 0, st>>>(P); else k_pair<4><<<blocks, 128, 0, st>>>(P);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ev1, st));
     CK(cudaMemcpyAsync(&used, dOutCtr.p, 8, cudaMemcpyDeviceToHost, st));

@@ -26,7 +26,7 @@
 
 // host-emulation-only call-site counters (tests/host_emu.cpp); compiled out of the device build
 #if !defined(__CUDACC__) && defined(T1K_EMU_COUNTERS)
-extern long long t1k_emu_counters[16];
+extern long long t1k_emu_counters[32];
 #define T1K_COUNT(i, v) (t1k_emu_counters[i] += (v))
 #else
 #define T1K_COUNT(i, v) ((void)0)
@@ -50,7 +50,10 @@ constexpr u64 M55 = 0x5555555555555555ull;
 
 struct Posting { u32 idx, off; };
 
+struct alignas(16) AlleleMeta { u64 wordOff; int32_t len; u32 hasN; };   // one 16-byte load instead of three dependent-free ones
+
 struct RefView {
+  const AlleleMeta *meta;
   const u64 *seq2, *n2, *ex2;
   const u64 *wordOff;    // [nAlleles] first word of allele
   const int32_t *len;    // [nAlleles]
@@ -62,7 +65,27 @@ struct RefView {
   int32_t nAlleles;
   double sim;
   int32_t relax;
+  // simThr[w * SIM_DEN + den] = smallest matchCnt whose (double)matchCnt / (double)den is NOT below the threshold
+  // (w = 0: refSeqSimilarity, w = 1: the 0.95 of SeqSet.hpp:2178), built on the host with the same double division, so
+  // `sim < threshold` becomes an integer compare (the inlined double divisions were a tenth of the kernel's code)
+  const u16 *simThr;
 };
+constexpr int SIM_DEN = 4096;
+T1K_HDN inline void sim_threshold_table(double sim, u16 *thr) {      // host side: 2 * SIM_DEN entries
+  const double lim[2] = {sim, 0.95};
+  for (int w = 0; w < 2; ++w)
+    for (int den = 0; den < SIM_DEN; ++den) {
+      int mc = 0;
+      while (mc < 65535 && den > 0 && (double)mc / (double)den < lim[w]) ++mc;
+      thr[w * SIM_DEN + den] = (u16)mc;
+    }
+}
+T1K_HDN T1K_NOINLINE inline bool sim_below_slow(double lim, int mc, int den) { return (double)mc / (double)den < lim; }
+// (double)mc / (double)den < (w == 0 ? R.sim : 0.95)
+T1K_HD bool sim_below(const RefView &R, int mc, int den, int w) {
+  if (den > 0 && den < SIM_DEN && mc >= 0) return mc < (int)R.simThr[w * SIM_DEN + den];
+  return sim_below_slow(w == 0 ? R.sim : 0.95, mc, den);
+}
 
 struct ReadView {        // one strand of one read-end
   const u64 *seq2, *n2;  // RWORDS words each
@@ -88,8 +111,13 @@ struct Cand {
   int32_t eSeqStart, eSeqEnd;
   u8 eReadStart, eReadEnd, leftClip, rightClip;
   int32_t eMatchCnt, relaxed;
+  // CF_FA: the full-read alignment is the pure diagonal with <= 3 mismatches, known already from the seeding stage:
+  // read positions of the mismatches (bytes 0-2), their number (bits 24-25) and the exonic ones among them (bits 26-27)
+  u32 mmPos;
 };
-enum { CF_SEP = 1, CF_NEEDCLIP = 2, CF_RET = 4, CF_INCLUDE = 8 };
+enum { CF_SEP = 1, CF_NEEDCLIP = 2, CF_RET = 4, CF_INCLUDE = 8,
+       CF_PRE = 16,       // extension fields already filled by diag_fast (ExtendOverlap need not run)
+       CF_FA = 32 };      // full-read alignment already known (mmPos)
 
 // final record kept resident in HBM for pairing: 32 B
 struct Rec {
@@ -136,6 +164,14 @@ T1K_HD int ctz64(u64 x) {
 T1K_HD int imin(int a, int b) { return a < b ? a : b; }
 T1K_HD int imax(int a, int b) { return a > b ? a : b; }
 T1K_HD int iabs(int a) { return a < 0 ? -a : a; }
+
+T1K_HD void cov_add(int32_t *p, int v) {
+#ifdef __CUDA_ARCH__
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+}
 
 // 32 bases starting at base `pos` (>= 0) of a plane
 T1K_HD u64 fetch32(const u64 *plane, int pos) {
@@ -443,7 +479,7 @@ T1K_HD bool sep_in_range(const AlleleView &T, int s, int e) {
 }
 
 // IsOverlapLowComplex (SeqSet.hpp:458-485)
-T1K_HD bool low_complex(const ReadView &Q, int s, int e) {
+T1K_HDN T1K_NOINLINE inline bool low_complex(const ReadView &Q, int s, int e) {
   int cnt[4] = {0, 0, 0, 0};
   int n = e - s + 1;
   T1K_NOUNROLL
@@ -556,14 +592,193 @@ T1K_HDN T1K_NOINLINE inline void consume_chain(const RefView &R, const ReadView 
       pa = a; pb = b;
     }
   }
-  double sim = (double)mc / (double)(se - ss + 1 + re - rs + 1);
-  if (low_complex(Q, rs, re)) sim = 0;
-  if (sim < R.sim) return;
+  bool below = sim_below(R, mc, se - ss + 1 + re - rs + 1, 0);
+  if (!below && low_complex(Q, rs, re)) below = 0.0 < R.sim;        // similarity forced to 0 (SeqSet.hpp:1840-1842)
+  if (below) return;
   if (nEmit >= MAX_EMIT) { err |= ERR_EMIT; return; }
   Cand &c = S.emit()[nEmit++];
   c.seqIdx = seqIdx; c.seqStart = ss; c.seqEnd = se;
   c.readStart = (u8)rs; c.readEnd = (u8)re; c.strand01 = (u8)strand01; c.flags = 0;
-  c.matchCnt = (u16)mc; c.pad = 0;
+  c.matchCnt = (u16)mc; c.pad = 0; c.mmPos = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Seed table of one read strand, one u32 per read position a:
+//   bits 0-7   number of seeds <= a            bits 8-15  number of seeds s <= a whose distance to the previous seed is > k-1
+//   bits 16-23 first seed >= a (255: none)     bits 24-31 last seed <= a (255: none)
+// "Seed" = a k-mer position GetHitsFromRead actually looks up with a non-empty posting list (SeqSet.hpp:1093-1153 after
+// the skip rule).  Built once per strand (one lane); diag_fast below answers its range questions from it.
+T1K_HDN inline void seed_table_build(const u8 *seedA, int nS, int len, u32 *stab) {
+  int k = 0, cnt = 0, big = 0, last = 255;
+  T1K_NOUNROLL
+  for (int a = 0; a < len; ++a) {
+    if (k < nS && seedA[k] == a) {
+      if (last != 255 && a - last > KMER - 1) ++big;
+      ++cnt; last = a; ++k;
+    }
+    stab[a] = (u32)cnt | ((u32)big << 8) | ((u32)last << 24);
+  }
+  int nxt = 255;
+  T1K_NOUNROLL
+  for (int a = len - 1; a >= 0; --a) {
+    if ((stab[a] >> 24) == (u32)a) nxt = a;
+    stab[a] |= (u32)nxt << 16;
+  }
+}
+// a k-mer of one repeated base: the only k-mers the index build may drop although the allele holds them (KmerIndex.hpp:107-130, Q1)
+T1K_HD bool kmer_homopolymer(u32 code) { return code == 0u || code == 0x155555u || code == 0x2AAAAAu || code == 0x3FFFFFu; }
+
+constexpr int FAST_MAX_LEN = 160;    // read length the fast path handles (5 words of 32 bases)
+
+// ---- The common case of GetOverlapsFromHits + GetOverlapsFromRead + ExtendOverlap + the full-read alignment in one
+// pass over the read-vs-allele mismatch mask of ONE diagonal, without walking the hit list.
+//
+// Claim: let d = seqOffset - readOffset of the allele's first hit, [pLo, pHi) the read positions that fall inside the
+// allele on that diagonal and suppose the window holds no N on either side.  A seed at a (pLo <= a, a + k <= pHi) whose k
+// bases all match is a hit (a, a + d) of this allele (the index holds every non-homopolymer k-mer of every allele, and the
+// strand is only eligible when no seed is a homopolymer).  If the NUMBER of such seeds equals the number n of postings the
+// gather counted for this allele, the allele's hit list is exactly that set: one diagonal, one cluster, the LIS keeps
+// everything (SeqSet.hpp:1303-1553) and the chain statistics follow from the mismatch positions alone:
+//   * consecutive seeds inside a mismatch-free stretch are "touching" iff their distance is <= k-1 (checked through the
+//     table's big-gap counter; a stretch with a wider step falls back), so the touching runs are the stretches that hold
+//     at least one seed: hitLen = sum(last - first + k);
+//   * the gap between two runs holds the mismatches in between; with <= 32 columns and <= 3 mismatches GlobalAlignment
+//     of the gap is the pure diagonal (DESIGN.md "diagonal certificate"): matches = columns - mismatches.
+// Everything else (count mismatch = hits on other diagonals, N in the window, long or dirty gaps, reads > 160 bases)
+// returns false with nothing written and the caller runs chain_allele on the gathered hit list.
+// The same mismatch positions give ExtendOverlap (both overhangs lie on the diagonal) and the full-read alignment.
+// lcMemo: per-lane memo of IsOverlapLowComplex for the last (readStart, readEnd) of this strand (0 = empty).
+T1K_HDN T1K_NOINLINE inline bool diag_fast(const RefView &R, const ReadView &Q, int strand01, int seqIdx, int n, u32 h0, const u32 *stab,
+                              Cand &out, bool &emitted, u64 &bestStrandKey, u32 &lcMemo) {
+  emitted = false;
+  const int len = Q.len;
+  const int d = hit_b(h0) - hit_a(h0);
+#ifdef __CUDA_ARCH__
+  const uint4 mt = *reinterpret_cast<const uint4 *>(R.meta + seqIdx);
+  const u64 w0 = (u64)mt.x | ((u64)mt.y << 32);
+  const int clen = (int)mt.z;
+  const bool alleleHasN = mt.w != 0;
+#else
+  const u64 w0 = R.meta[seqIdx].wordOff;
+  const int clen = R.meta[seqIdx].len;
+  const bool alleleHasN = R.meta[seqIdx].hasN != 0;
+#endif
+  const int pLo = d < 0 ? -d : 0, pHi = imin(len, clen - d);
+  const int W = pHi - pLo;
+  if (W < KMER) return false;
+  // All allele words of the window in one round trip (the loads are independent; the window spans <= 5 chunks of 32
+  // bases = <= 6 words, and the pad word after the allele makes word nW readable), then the mismatch masks of the chunks.
+  const u64 *tp = R.seq2 + w0 + ((pLo + d) >> 5);
+  const int sh = ((pLo + d) & 31) * 2;
+  const int nW = (W + 31) >> 5;
+  u64 tw[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) tw[j] = j <= nW ? tp[j] : 0;
+  if (alleleHasN && n_in_range(R.n2 + w0, pLo + d, pHi - 1 + d)) return false;
+  u64 t0 = tw[0], t1 = tw[1], t2 = tw[2], t3 = tw[3], t4 = tw[4], t5 = tw[5];     // word queue: later words move up
+  int exMm = 0;
+  // streaming state over the mismatches (ascending) and the closing sentinel pHi
+  int prevMis = pLo - 1;
+  int rs = -1, lastL = 0, hitLen = 0, cntSum = 0, gapMatches = 0, mmRun = 0, mmLeft = 0, mmTot = 0;
+  u32 mmPos = 0;
+  bool ok = true;
+  T1K_NOUNROLL
+  for (int c0 = 0; ok; c0 += 32) {
+    const bool closing = c0 >= W;          // one extra round for the sentinel
+    u64 m = 0;
+    if (!closing) {
+      const u64 t = (t0 >> sh) | ((t1 << 1) << (63 - sh));
+      t0 = t1; t1 = t2; t2 = t3; t3 = t4; t4 = t5;
+      const u64 x = t ^ fetch32(Q.seq2, pLo + c0);
+      m = (x | (x >> 1)) & M55 & lowmask2(W - c0);
+      if (m && R.relax) exMm += popc64(m & fetch32(R.ex2 + w0, pLo + d + c0));
+    }
+    T1K_NOUNROLL
+    while (m || closing) {
+      int p;
+      if (m) { p = pLo + c0 + (ctz64(m) >> 1); m &= m - 1; }
+      else p = pHi;
+      // k-mer starts of the mismatch-free stretch (prevMis, p): [prevMis + 1, p - k]
+      const int lo = prevMis + 1, hi = p - KMER;
+      if (hi >= lo) {
+        const int f = (int)((stab[lo] >> 16) & 255);
+        if (f <= hi) {                      // (255 = none)
+          const u32 tl = stab[hi], tf = stab[f];
+          const int l = (int)(tl >> 24);
+          if (((tl >> 8) & 255) != ((tf >> 8) & 255)) { ok = false; break; }     // a step > k-1 inside the stretch
+          if (rs < 0) { rs = f; mmLeft = mmRun; }
+          else {
+            const int g = f - (lastL + KMER);
+            if (g > 32 || mmRun > 3) { ok = false; break; }
+            gapMatches += g - mmRun;
+          }
+          hitLen += l - f + KMER;
+          cntSum += (int)(tl & 255) - (int)(tf & 255) + 1;
+          lastL = l; mmRun = 0;
+        }
+      }
+      if (p == pHi) break;
+      if (mmTot < 3) mmPos |= (u32)p << (8 * mmTot);
+      ++mmTot; ++mmRun; prevMis = p;
+    }
+    if (closing) break;
+  }
+  T1K_COUNT(16, 1);
+  if (!ok) T1K_COUNT(21, 1); else if (cntSum < n) T1K_COUNT(22, 1); else if (cntSum > n) T1K_COUNT(23, 1);
+  if (!ok || cntSum != n) return false;
+  T1K_COUNT(17, 1);
+  // ---- from here on the result is the reference's: the tail of consume_chain<true>
+  if (hitLen < HIT_LEN_REQ) return true;
+  const int re = lastL + KMER - 1, mmRight = mmRun;
+  const u64 sk = strand_key(2 * hitLen, re - rs, seqIdx, strand01);
+  if (sk > bestStrandKey) bestStrandKey = sk;
+  const int mc = 2 * hitLen + 2 * gapMatches;
+  bool below = sim_below(R, mc, 2 * (re - rs + 1), 0);
+  if (!below) {
+    const u32 key = 0x10000u | (u32)rs | ((u32)re << 8);
+    if ((lcMemo & 0x1FFFFu) != key) lcMemo = key | (low_complex(Q, rs, re) ? 0x20000u : 0u);
+    if (lcMemo & 0x20000u) below = 0.0 < R.sim;
+  }
+  if (below) return true;
+  Cand &c = out;
+  c.seqIdx = seqIdx; c.seqStart = rs + d; c.seqEnd = re + d;
+  c.readStart = (u8)rs; c.readEnd = (u8)re; c.strand01 = (u8)strand01; c.flags = 0;
+  c.matchCnt = (u16)mc; c.pad = 0; c.mmPos = 0;
+  emitted = true;
+  // ---- ExtendOverlap on the same diagonal (SeqSet.hpp:1994-2100): overhangs [pLo, rs) and (re, pHi)
+  const int lo = rs - pLo, ro = pHi - 1 - re;
+  if ((lo <= 32 && mmLeft <= 3) && (ro <= 32 && mmRight <= 3)) {
+    const int mcE = mc + 2 * (lo - mmLeft + ro - mmRight);
+    const int leftClip = pLo, rightClip = len - pHi;
+    u8 flags = CF_PRE;
+    if (d < 0 || d + len > clen) flags |= CF_NEEDCLIP;
+    if (!sim_below(R, mcE, 2 * W, 0)) flags |= CF_RET;
+    c.eReadStart = (u8)pLo; c.eReadEnd = (u8)(pHi - 1);
+    c.eSeqStart = pLo + d; c.eSeqEnd = pHi - 1 + d;
+    c.leftClip = (u8)leftClip; c.rightClip = (u8)rightClip;
+    c.relaxed = mcE;
+    c.eMatchCnt = mcE + 2 * leftClip + 2 * rightClip;
+    // ---- the full-read alignment of [pLo, pHi) (SeqSet.hpp:2203-2274): <= 3 mismatches certify the diagonal
+    T1K_COUNT(18, 1);
+    if (mmTot <= 3) { T1K_COUNT(19, 1); flags |= CF_FA; c.mmPos = mmPos | ((u32)mmTot << 24) | ((u32)exMm << 26); }
+    c.flags = flags;
+  }
+  return true;
+}
+
+// full-read alignment of a CF_FA candidate: coverage and the exon-relaxed count from the stored mismatch positions
+T1K_HD void full_align_known(const RefView &R, Cand &c, int weight) {
+  const int mm = (int)((c.mmPos >> 24) & 3), exMm = (int)((c.mmPos >> 26) & 3);
+  const int lent = c.eSeqEnd - c.eSeqStart + 1;
+  if (weight > 0) {
+    const size_t cb = (size_t)R.wordOff[c.seqIdx] * 32;
+    const int dd = c.eSeqStart - (int)c.eReadStart;
+    cov_add(R.covDiff + cb + c.eSeqStart, weight); cov_add(R.covDiff + cb + c.eSeqStart + lent, -weight);
+    if (mm > 0) cov_add(R.covPoint + cb + dd + (int)(c.mmPos & 255), -weight);
+    if (mm > 1) cov_add(R.covPoint + cb + dd + (int)((c.mmPos >> 8) & 255), -weight);
+    if (mm > 2) cov_add(R.covPoint + cb + dd + (int)((c.mmPos >> 16) & 255), -weight);
+  }
+  c.relaxed = R.relax ? 2 * (lent - exMm) : c.eMatchCnt;
 }
 
 struct ChainDirect {   // contiguous run of a hit store
@@ -688,7 +903,7 @@ T1K_HDN T1K_NOINLINE inline void chain_allele(const RefView &R, const ReadView &
     if (hit_a(first) - hit_b(first) == hit_a(last) - hit_b(last)) {
       // one diagonal: every read offset occurs once, (b,a) order == current order, LIS keeps everything
       ChainDirect cd; cd.p = h + (size_t)s * stride; cd.stride = stride;
-      consume_chain<true>(R, Q, strand01, seqIdx, cd, m, S, nEmit, bestStrandKey, err);
+      consume_chain<false>(R, Q, strand01, seqIdx, cd, m, S, nEmit, bestStrandKey, err);   // (the <true> variant is the same function specialised; one copy keeps the kernel's code small)
       s = e; continue;
     }
     chain_cluster_general(R, Q, strand01, seqIdx, h, stride, s, e, dom, S, nEmit, bestStrandKey, err);
@@ -731,21 +946,12 @@ T1K_HDN T1K_NOINLINE inline bool extend_cand(const RefView &R, const ReadView &Q
   c.eReadStart = (u8)(rs - lo); c.eReadEnd = (u8)(re + ro);
   c.eSeqStart = ss - lo; c.eSeqEnd = se + ro;
   int mc = 2 * m + c.matchCnt;
-  double sim = (double)mc / (double)((re + ro) - (rs - lo) + 1 + (se + ro) - (ss - lo) + 1);
-  if (!(sim < R.sim)) flags |= CF_RET;
+  if (!sim_below(R, mc, (re + ro) - (rs - lo) + 1 + (se + ro) - (ss - lo) + 1, 0)) flags |= CF_RET;
   c.leftClip = (u8)leftClip; c.rightClip = (u8)rightClip;
   c.relaxed = mc;                                  // SeqSet.hpp:2068 (before the clip bonus)
   c.eMatchCnt = mc + 2 * leftClip + 2 * rightClip;
   c.flags = flags;
   return true;
-}
-
-T1K_HD void cov_add(int32_t *p, int v) {
-#ifdef __CUDA_ARCH__
-  atomicAdd(p, v);
-#else
-  *p += v;
-#endif
 }
 
 // ---- full-read alignment of an extended overlap (SeqSet.hpp:2203-2274): exon-relaxed match count and

@@ -18,6 +18,7 @@ struct PackedRef {
   std::vector<u64> wordOff;
   std::vector<int32_t> len;
   std::vector<u8> hasN;
+  std::vector<AlleleMeta> meta;
   std::vector<u32> kstart;
   std::vector<Posting> post;
   size_t totalWords = 0;
@@ -83,6 +84,8 @@ inline bool pack_reference(int32_t n, const char *bases, const int64_t *off, con
       // cnt[c] now = start of bucket c; fill pass advances it
     }
   }
+  P.meta.resize(n);
+  for (int i = 0; i < n; ++i) { P.meta[i].wordOff = P.wordOff[i]; P.meta[i].len = P.len[i]; P.meta[i].hasN = P.hasN[i]; }
   return true;
 }
 

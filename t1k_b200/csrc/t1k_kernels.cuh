@@ -17,6 +17,10 @@ __device__ __forceinline__ void cp_async8(void *smemDst, const void *gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void *smemDst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -34,6 +38,7 @@ struct AssignOut {
   u64 storeCap;
   u64 *readOff;            // per read-end: first record
   u32 *readCnt;
+  u32 *readTop;            // per read-end: max over its records of matchCnt << 12 | (4095 - denominator) (pairing's "is anything better" test)
   u32 *maxCnt;             // longest record list of the batch (sizes the pairing kernel's per-warp scratch)
   int32_t *readRet;        // AssignRead's return value; -2 = deferred (store full), -3 = deferred (hit tile too small)
   int *err;
@@ -49,6 +54,7 @@ struct AssignParams {
   u8 *laneScratch;         // per lane SCR_BYTES
   unsigned int *workCtr;
   int hitCap;              // hits per allele kept in shared memory
+  int noFast;              // 1: every allele goes through the hit-list path (A/B switch, T1K_NO_FAST)
 };
 
 // warp reductions on the redux unit (one instruction per 32-bit reduction; the kernel is instruction-footprint bound)
@@ -108,15 +114,17 @@ __global__ void k_pack_reads(const char *bases, const u64 *off, const u32 *len, 
 // ---------------------------------------------------------------------------------------------------
 // One warp = one read-end at a time (dynamic work queue).  Shared memory per warp:
 //   H[hitCap][32]  encoded hits of the current allele tile, lane-interleaved (bank = lane)
-//   cnt[32], seedA[256], act[256], cur[256], end[256], nxt[256], read planes (2 x RWORDS words)
+//   cnt[32], seedA[256], act[256], cur[256], end[256], nxt[256], stab[256] (seed table of diag_fast),
+//   read planes (2 x RWORDS words)
 struct WarpSmem {
-  u32 *H, *cnt, *cur, *end, *nxt;
+  u32 *H, *cnt, *cur, *end, *nxt, *stab;
   u8 *seedA, *act;
   u64 *seq, *nn;
   Posting *ring;           // GATHER_DEPTH x 32 postings
+  u32 *ringX;              // GATHER_DEPTH: allele id of the posting that follows each ring block (0xffffffff: list ends)
 };
 __host__ __device__ inline size_t warp_smem_bytes(int hitCap) {
-  return (size_t)hitCap * 32 * 4 + 32 * 4 + 3 * 256 * 4 + 2 * 256 + 2 * RWORDS * 8 + GATHER_DEPTH * 32 * 8;
+  return (size_t)hitCap * 32 * 4 + 32 * 4 + 4 * 256 * 4 + 2 * 256 + 2 * RWORDS * 8 + GATHER_DEPTH * 32 * 8 + GATHER_DEPTH * 4;
 }
 
 // returns whether the read holds an N
@@ -135,8 +143,15 @@ __device__ __forceinline__ void gather_issue(const RefView &R, const WarpSmem &W
     const int k = W.act[i];
     const u32 c = W.cur[k] + lane;
     Posting *dst = W.ring + (i & (GATHER_DEPTH - 1)) * 32 + lane;
-    if (c < W.end[k]) cp_async8(dst, R.post + c);
+    const u32 e = W.end[k];
+    if (c < e) cp_async8(dst, R.post + c);
     else { Posting none; none.idx = 0xffffffffu; none.off = 0; *dst = none; }
+    // the 33rd posting's allele id: tells where the list goes on without a dependent load after the block is consumed
+    if (lane == 0) {
+      u32 *dx = W.ringX + (i & (GATHER_DEPTH - 1));
+      if (c + 32 < e) cp_async4(dx, &R.post[c + 32].idx);
+      else *dx = 0xffffffffu;
+    }
   }
   cp_async_commit();
 }
@@ -169,7 +184,10 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
       }
       __syncwarp();
       // ---- the sequential skip rule (list >= 100, not first/last, <= K/2 in a row; Q2)
+      // The strand is eligible for diag_fast when the read holds no N, fits 5 words and no seed is a homopolymer k-mer
+      // (see the claim above diag_fast); lane 0 then also builds the seed table.
       int nS = 0;
+      bool strandFast = !Qv.anyN && len <= FAST_MAX_LEN && !P.noFast;
       if (lane == 0) {
         u32 prev = 0; int skip = 0;
         T1K_NOUNROLL
@@ -180,12 +198,15 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
             int size = (int)(hi - lo);
             if (size >= 100 && a != 0 && a != NP - 1 && skip < KMER / 2) { ++skip; continue; }
             skip = 0;
-            if (size > 0) { W.seedA[nS] = (u8)a; W.cur[nS] = lo; W.end[nS] = hi; ++nS; }
+            if (size > 0) { W.seedA[nS] = (u8)a; W.cur[nS] = lo; W.end[nS] = hi; ++nS; if (kmer_homopolymer(code)) strandFast = false; }
           }
           prev = code;
         }
+        if (strandFast) seed_table_build(W.seedA, nS, len, W.stab);
       }
       nS = __shfl_sync(FULL, nS, 0);
+      strandFast = __shfl_sync(FULL, (int)strandFast, 0) != 0;
+      u32 lcMemo = 0;
       __syncwarp();
       T1K_NOUNROLL
       for (int k = lane; k < nS; k += 32) { W.nxt[k] = R.post[W.cur[k]].idx; stPost += W.end[k] - W.cur[k]; }
@@ -227,6 +248,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
           const u32 a = W.seedA[k], e = W.end[k];
           u32 c = W.cur[k];
           Posting p = W.ring[(i & (GATHER_DEPTH - 1)) * 32 + lane];
+          bool first = true;                 // p came through the ring (ringX knows what follows it)
           T1K_NOUNROLL
           for (;;) {
             const bool in = p.idx < base + 32;
@@ -258,13 +280,17 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
             }
             __syncwarp();
             const u32 nc = c + consumed;
-            if (consumed == 32 && nc < e) {          // the list continues inside this tile (repeated k-mer)
-              c = nc;
+            u32 nextIdx;                             // allele id of the first posting left in the list (all branches warp-uniform)
+            if (consumed < 32) nextIdx = __shfl_sync(FULL, p.idx, consumed);
+            else if (nc >= e) nextIdx = 0xffffffffu;
+            else if (first) nextIdx = __shfl_sync(FULL, lane == 0 ? W.ringX[i & (GATHER_DEPTH - 1)] : 0u, 0);
+            else nextIdx = 0;                        // unknown: look at the next block
+            if (consumed == 32 && nc < e && nextIdx < base + 32) {   // the list continues inside this tile (repeated k-mer)
+              c = nc; first = false;
               p.idx = 0xffffffffu; p.off = 0;
               if (c + lane < e) p = R.post[c + lane];
               continue;
             }
-            const u32 nextIdx = consumed < 32 ? __shfl_sync(FULL, p.idx, consumed) : 0xffffffffu;
             if (lane == 0) { W.cur[k] = nc; W.nxt[k] = nextIdx; }
             // the block the next tile will ask for: pull it into L2 now (2 x 128 B lines)
             if (lane < 2 && nc + lane * 16 < e) prefetch_l2(R.post + nc + lane * 16);
@@ -277,7 +303,14 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
         const int n = (int)W.cnt[lane];
         int nEmit = 0;
         if (__any_sync(FULL, n > CAP)) { overflow = true; break; }
-        if (n >= 3) chain_allele(R, Qv, strand01, (int)(base + lane), W.H + lane, 32, n, S, nEmit, laneKey, err);
+        // all lanes first try the mismatch-mask path (uniform work); the few it declines walk their hit lists
+        Cand fc;
+        bool fastEmit = false, handled = n < 3;
+        if (strandFast && n >= 3) {
+          handled = diag_fast(R, Qv, strand01, (int)(base + lane), n, W.H[lane], W.stab, fc, fastEmit, laneKey, lcMemo);
+          if (fastEmit) nEmit = 1;
+        }
+        if (!handled) chain_allele(R, Qv, strand01, (int)(base + lane), W.H + lane, 32, n, S, nEmit, laneKey, err);
         // ---- ordered emission (allele order == lane order)
         int incl = nEmit;
 #pragma unroll
@@ -286,9 +319,12 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
         if (tot > 0) {
           if (nCand + tot > P.candCap) err |= ERR_CAND;
           else {
-            const Cand *em = S.emit();
-            T1K_NOUNROLL
-            for (int j = 0; j < nEmit; ++j) cands[nCand + incl - nEmit + j] = em[j];
+            if (fastEmit) cands[nCand + incl - 1] = fc;
+            else {
+              const Cand *em = S.emit();
+              T1K_NOUNROLL
+              for (int j = 0; j < nEmit; ++j) cands[nCand + incl - nEmit + j] = em[j];
+            }
             nCand += tot;
           }
         }
@@ -308,17 +344,28 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
     if (best01 == 1) Qv.anyN = load_planes(P, r, 1, W, lane);
     __threadfence_block();
     __syncwarp();
-    // pass 1: extension; first candidate (list order) whose extension fails
-    // Two-speed loop: every candidate first tries the hot path (one-word overhang comparisons); the few that need
-    // certificates or the DP are queued (W.cur is free after the gather) and run 32 at a time, all lanes busy.
-    u64 fKey = ~0ull; int fIdx = 0x7fffffff;
+    // pass 1: extension; the first candidate (list order) whose extension fails, and the first one that succeeds.
+    // Two-speed loop: candidates the seeding stage already extended (CF_PRE) cost nothing; the others are queued
+    // (W.cur is free after the gather) and extended 32 at a time, all lanes busy.
+    u64 fKey = ~0ull; int fIdx = 0x7fffffff;        // first failing (not CF_RET)
+    u64 rKey = ~0ull; int rIdx = 0x7fffffff;        // first returned (CF_RET)
+    auto note = [&](const Cand &c, int i) {
+      if (c.flags & CF_SEP) return;
+      const u64 k = cand_key_pre(c);
+      if (c.flags & CF_RET) { if (pair_less(k, i, rKey, rIdx)) { rKey = k; rIdx = i; } }
+      else if (pair_less(k, i, fKey, fIdx)) { fKey = k; fIdx = i; }
+    };
     int qn = 0;
     T1K_NOUNROLL
     for (int b = c0; b < c1 || qn > 0; b += 32) {
       int i = b + lane;
-      bool have = i < c1, cold = false;
+      bool have = i < c1, cold = false, pre = false;
       Cand c;
-      if (have) { c = cands[i]; cold = !extend_cand<true>(R, Qv, c, S, err); }
+      if (have) {
+        c = cands[i];
+        pre = (c.flags & CF_PRE) != 0;              // extension already known from the seeding stage
+        cold = !pre;                                // the others are queued and extended 32 at a time
+      }
       const unsigned bal = __ballot_sync(FULL, cold);
       if (cold) { W.cur[qn + __popc(bal & ((1u << lane) - 1))] = (u32)i; have = false; }
       qn += __popc(bal);
@@ -327,59 +374,60 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
         const int take = min(qn, 32);
         if (lane < take) {
           if (have) {                                       // this lane's hot result first
-            cands[i] = c;
-            if (!(c.flags & CF_SEP) && !(c.flags & CF_RET)) { u64 k = cand_key_pre(c); if (pair_less(k, i, fKey, fIdx)) { fKey = k; fIdx = i; } }
+            if (!pre) cands[i] = c;
+            note(c, i);
           }
           i = (int)W.cur[qn - take + lane];
           c = cands[i];
           extend_cand<false>(R, Qv, c, S, err);
-          have = true;
+          have = true; pre = false;
         }
         qn -= take;
         __syncwarp();
       }
       if (have) {
-        cands[i] = c;
-        if (!(c.flags & CF_SEP) && !(c.flags & CF_RET)) {
-          u64 k = cand_key_pre(c);
-          if (pair_less(k, i, fKey, fIdx)) { fKey = k; fIdx = i; }
-        }
+        if (!pre) cands[i] = c;
+        note(c, i);
       }
     }
     warp_min_pair(fKey, fIdx);
+    warp_min_pair(rKey, rIdx);
     __syncwarp();
-    // pass 2: goodMatchCnt
-    int good = -1;
-    T1K_NOUNROLL
-    for (int i = c0 + lane; i < c1; i += 32) {
-      const Cand &c = cands[i];
-      if ((c.flags & CF_SEP) || !(c.flags & CF_RET)) continue;
-      if (pair_less(cand_key_pre(c), i, fKey, fIdx)) good = max(good, (int)c.matchCnt);
-    }
-    good = warp_max_i32(good);
-    // pass 3: inclusion
+    // goodMatchCnt (SeqSet.hpp:2156-2186) = the largest matchCnt among the returned candidates that precede the first
+    // failing one.  The list order is matchCnt-descending, so that is the first returned candidate if it precedes the
+    // failure, and nothing otherwise: no pass of its own.
+    const int good = pair_less(rKey, rIdx, fKey, fIdx) ? 2047 - (int)(rKey >> 53) : -1;
+    // pass 2: inclusion; the list head under the post-extension order (for the > 1000 cut, SeqSet.hpp:2290-2298)
     int bestMc = -1, nInc = 0;
+    u64 bKey = ~0ull; int bIdx = 0x7fffffff;
     T1K_NOUNROLL
     for (int i = c0 + lane; i < c1; i += 32) {
-      Cand &c = cands[i];
+      Cand c = cands[i];
       if ((c.flags & CF_SEP) || !(c.flags & CF_RET)) continue;
       bool before = pair_less(cand_key_pre(c), i, fKey, fIdx);
-      double sim = (double)c.matchCnt / (double)cand_denom_pre(c);
-      if (!before && (int)c.matchCnt < good && (!(c.flags & CF_NEEDCLIP) || sim < 0.95)) continue;
-      c.flags |= CF_INCLUDE;
+      if (!before && (int)c.matchCnt < good && (!(c.flags & CF_NEEDCLIP) || sim_below(R, c.matchCnt, cand_denom_pre(c), 1))) continue;
+      cands[i].flags = c.flags | CF_INCLUDE;
       bestMc = max(bestMc, c.eMatchCnt);
       ++nInc;
+      const u64 k = cand_key_post(c);
+      if (pair_less(k, i, bKey, bIdx)) { bKey = k; bIdx = i; }
     }
     bestMc = warp_max_i32(bestMc);
     nInc = warp_sum_i32(nInc);
+    warp_min_pair(bKey, bIdx);
     __syncwarp();
     // reserve the store before touching coverage, so that a full store can be retried without double counting
     if (lane == 0 && nInc > 0) pos = atomicAdd(P.O.storeCtr, (unsigned long long)nInc);
     pos = __shfl_sync(FULL, pos, 0);
     if (nInc > 0 && pos + nInc > P.O.storeCap) deferred = true;
     if (!deferred) {
-      // pass 4: full-read alignment of everything within 10 of the best (Q8)
-      if (weight >= 0) {
+      const bool usePost = nInc > 1000;      // SeqSet.hpp:2290-2298
+      double cutSim = 0;
+      if (usePost) { const Cand cb = cands[bIdx]; cutSim = (double)cb.eMatchCnt / (double)cand_denom_post(cb) - 0.1; }
+      u64 cKey = ~0ull; int cIdx = 0x7fffffff;       // first candidate (post order) the cut removes
+      // pass 3: full-read alignment of everything within 10 of the best (Q8); where the cut starts
+      {
+        const bool doAlign = weight >= 0;
         int qn = 0;                                          // same two-speed structure as the extension pass
         T1K_NOUNROLL
         for (int b = c0; b < c1 || qn > 0; b += 32) {
@@ -388,9 +436,16 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
           if (i < c1) {
             Cand c = cands[i];
             if (c.flags & CF_INCLUDE) {
-              if (c.eMatchCnt >= bestMc - 10) cold = !full_align<true>(R, Qv, c, weight, S, err);
-              else c.relaxed = 0;
-              if (!cold) cands[i].relaxed = c.relaxed;
+              if (usePost && i != bIdx && (double)c.eMatchCnt / (double)cand_denom_post(c) < cutSim) {
+                const u64 k = cand_key_post(c);
+                if (pair_less(k, i, cKey, cIdx)) { cKey = k; cIdx = i; }
+              }
+              if (doAlign) {
+                if (c.eMatchCnt < bestMc - 10) c.relaxed = 0;
+                else if (c.flags & CF_FA) full_align_known(R, c, weight);
+                else cold = true;
+                if (!cold) cands[i].relaxed = c.relaxed;
+              }
             }
           }
           const unsigned bal = __ballot_sync(FULL, cold);
@@ -410,42 +465,22 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
           }
         }
       }
+      warp_min_pair(cKey, cIdx);
       __syncwarp();
-      const bool usePost = nInc > 1000;      // SeqSet.hpp:2290-2298
-      if (usePost) {
-        u64 bKey = ~0ull; int bIdx = 0x7fffffff;
-        T1K_NOUNROLL
-        for (int i = c0 + lane; i < c1; i += 32) if (cands[i].flags & CF_INCLUDE) {
-          u64 k = cand_key_post(cands[i]);
-          if (pair_less(k, i, bKey, bIdx)) { bKey = k; bIdx = i; }
-        }
-        warp_min_pair(bKey, bIdx);
-        const double bestSim = (double)cands[bIdx].eMatchCnt / (double)cand_denom_post(cands[bIdx]);
-        u64 cKey = ~0ull; int cIdx = 0x7fffffff;
-        T1K_NOUNROLL
-        for (int i = c0 + lane; i < c1; i += 32) if ((cands[i].flags & CF_INCLUDE) && i != bIdx) {
-          double sim = (double)cands[i].eMatchCnt / (double)cand_denom_post(cands[i]);
-          if (sim < bestSim - 0.1) {
-            u64 k = cand_key_post(cands[i]);
-            if (pair_less(k, i, cKey, cIdx)) { cKey = k; cIdx = i; }
-          }
-        }
-        warp_min_pair(cKey, cIdx);
-        T1K_NOUNROLL
-        for (int i = c0 + lane; i < c1; i += 32) if (cands[i].flags & CF_INCLUDE) {
-          u64 k = cand_key_post(cands[i]);
-          if (!pair_less(k, i, cKey, cIdx)) cands[i].flags &= ~CF_INCLUDE;
-        }
-        __syncwarp();
-      }
-      // pass 5: ordered compaction into the store (allele order is kept: pairing binary-searches it)
+      // pass 4: ordered compaction into the store (allele order is kept: pairing searches it), minus the cut
       int running = 0;
+      u32 top = 0;
       T1K_NOUNROLL
       for (int b = c0; b < c1; b += 32) {
         const int i = b + lane;
         bool inc = false;
         Cand c;
-        if (i < c1) { c = cands[i]; inc = (c.flags & CF_INCLUDE) != 0; }
+        u64 kPost = 0;
+        if (i < c1) {
+          c = cands[i];
+          inc = (c.flags & CF_INCLUDE) != 0;
+          if (inc && usePost) { kPost = cand_key_post(c); inc = pair_less(kPost, i, cKey, cIdx); }
+        }
         const unsigned bal = __ballot_sync(FULL, inc);
         if (inc) {
           Rec o;
@@ -453,11 +488,14 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
           o.packed = (u32)c.eReadStart | ((u32)c.eReadEnd << 8) | ((u32)c.leftClip << 16) | ((u32)c.rightClip << 24);
           o.mcStrand = (u32)c.eMatchCnt | ((u32)c.strand01 << 31);
           o.relaxed = c.relaxed;
-          o.key = usePost ? cand_key_post(c) : cand_key_pre(c);
+          o.key = usePost ? kPost : cand_key_pre(c);
+          top = max(top, ((u32)c.eMatchCnt << 12) | (u32)(4095 - cand_denom_post(c)));
           P.O.store[pos + running + __popc(bal & ((1u << lane) - 1))] = o;
         }
         running += __popc(bal);
       }
+      top = __reduce_max_sync(FULL, top);
+      if (lane == 0) P.O.readTop[r] = top;
       nFinal = running;
       ret = nFinal;
     }
@@ -491,10 +529,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_assign(AssignPar
   WarpSmem W;
   W.seq = (u64 *)sm; W.nn = W.seq + RWORDS;
   W.ring = (Posting *)(W.nn + RWORDS);
-  W.H = (u32 *)(W.ring + GATHER_DEPTH * 32);
+  W.ringX = (u32 *)(W.ring + GATHER_DEPTH * 32);
+  W.H = W.ringX + GATHER_DEPTH;
   W.cnt = W.H + (size_t)P.hitCap * 32;
-  W.cur = W.cnt + 32; W.end = W.cur + 256; W.nxt = W.end + 256;
-  W.seedA = (u8 *)(W.nxt + 256); W.act = W.seedA + 256;
+  W.cur = W.cnt + 32; W.end = W.cur + 256; W.nxt = W.end + 256; W.stab = W.nxt + 256;
+  W.seedA = (u8 *)(W.stab + 256); W.act = W.seedA + 256;
   LaneScratch S; S.base = P.laneScratch + (gwarp * 32 + lane) * (size_t)SCR_BYTES;
   Cand *cands = P.candBuf + gwarp * (size_t)P.candCap;
   for (;;) {

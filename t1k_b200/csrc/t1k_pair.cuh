@@ -22,6 +22,7 @@ struct PairParams {
   const Rec *store;
   const u64 *readOff;
   const u32 *readCnt;
+  const u32 *readTop;       // per read-end: max matchCnt << 12 | (4095 - denominator) over its records (k_assign)
   const u32 *end1, *end2;   // end2 == NULL: single-end data
   const u8 *hasN;
   u32 fragBase, nFrag;      // fragments [fragBase, fragBase + nFrag) of the caller's arrays
@@ -86,13 +87,27 @@ __device__ __forceinline__ bool sep_exact(const RefView &R, int seqIdx, int s, i
   return n_in_range(R, R.wordOff[seqIdx], s, e);
 }
 
-__device__ __forceinline__ int lower_bound_allele(const Rec *L, int n, int seqIdx) {
-  int lo = 0, hi = n;
+__device__ __forceinline__ int lower_bound_allele(const Rec *L, int n, int seqIdx, int lo = 0, int hi = -1) {
+  if (hi < 0) hi = n;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
     if (L[mid].seqIdx < seqIdx) lo = mid + 1; else hi = mid;
   }
   return lo;
+}
+// The same lower bound, galloping outwards from a guess.  Both mates' lists are in allele order and mostly hold the same
+// alleles, so the run of allele A[i] in B sits near i + (offset of the previous run): two or three probes of records the
+// neighbouring lanes load anyway, instead of log2(n) dependent loads spread over the whole list.
+__device__ __forceinline__ int lower_bound_allele_near(const Rec *L, int n, int seqIdx, int guess) {
+  int g = guess < 0 ? 0 : guess > n ? n : guess;
+  if (g >= n || L[g].seqIdx >= seqIdx) {        // answer <= g: walk down
+    int hi = g, step = 1, lo = g - 1;
+    while (lo >= 0 && L[lo].seqIdx >= seqIdx) { hi = lo; step <<= 1; lo = hi - step; }
+    return lower_bound_allele(L, n, seqIdx, lo < 0 ? 0 : lo + 1, hi);
+  }
+  int lo = g + 1, step = 1, p = g + 1;          // L[g] < seqIdx: walk up
+  while (p < n && L[p].seqIdx < seqIdx) { lo = p + 1; step <<= 1; p = lo - 1 + step; }
+  return lower_bound_allele(L, n, seqIdx, lo, p < n ? p : n);
 }
 
 // best fragment of one allele (the per-seqIdx slot of SeqSet.hpp:2440-2455)
@@ -116,8 +131,9 @@ __device__ __forceinline__ bool mates_ok(const RV &a, const RV &b) {
 
 // A[a0,a1) is the run of one allele in the first list; paired mode looks the allele up in B.
 // b0Hint >= 0: the position found by an earlier pass (lower_bound of the allele in B); out.b0 returns it.
+// b0Guess (used when b0Hint < 0): where to start looking for the allele in B.
 __device__ void eval_allele(const RefView &R, bool paired, const Rec *A, int a0, int a1, const Rec *B, int nB, AlleleBest &out,
-                            int b0Hint = -1) {
+                            int b0Hint = -1, int b0Guess = 0) {
   out.valid = false;
   out.posKey = ~0ull; out.posIdx = 0x7fffffff;
   RV bo1, bo2;
@@ -140,7 +156,7 @@ __device__ void eval_allele(const RefView &R, bool paired, const Rec *A, int a0,
     return;
   }
   const int seqIdx = A[a0].seqIdx;
-  const int b0 = b0Hint >= 0 ? b0Hint : lower_bound_allele(B, nB, seqIdx);
+  const int b0 = b0Hint >= 0 ? b0Hint : lower_bound_allele_near(B, nB, seqIdx, b0Guess);
   out.b0 = b0;
   if (b0 >= nB || B[b0].seqIdx != seqIdx) return;
   int bmc = 0, bden = 0;
@@ -217,7 +233,7 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
   if (pe && n1 == 0) { A = L2; nA = n2; }
   const Rec *B = paired ? L2 : NULL; const int nB = paired ? n2 : 0;
   const size_t gw = (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
-  u32 *b0s = P.b0 + gw * P.b0Stride;
+  u32 *b0s = P.b0 + gw * P.b0Stride * 2;    // b0[b0Stride] then keys[b0Stride]
   PairEntry *stage = P.stage + gw * P.stageCap;
   u64 *stageKey = P.ordKey ? P.stageKey + gw * P.stageCap : NULL;
   u32 *stageIdx = P.ordKey ? P.stageIdx + gw * P.stageCap : NULL;
@@ -226,15 +242,28 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
   u64 h0 = 0, h1 = 0;
   if (nA > 0) {
     // pass 1: best (matchCnt, similarity) over the alleles (SeqSet.hpp:2477-2487)
+    // Every run start i keeps its (matchCnt, denominator) key in the warp's scratch: the later passes re-derive only the
+    // alleles that can survive.  `delta` = offset of the previous chunk's last run in B, the guess for this chunk.
     u32 k1 = 0;
+    u32 *keys = b0s + P.b0Stride;
+    int delta = 0;
     for (int b = 0; b < nA; b += 32) {
       const int i = b + lane;
-      if (i < nA && (i == 0 || A[i - 1].seqIdx != A[i].seqIdx)) {
+      int myDelta = 0x7fffffff;
+      const bool runStart = i < nA && (i == 0 || A[i - 1].seqIdx != A[i].seqIdx);
+      if (i < nA && !runStart) keys[i] = 0xffffffffu;        // later passes find the run starts without touching the records
+      if (runStart) {
         int a1 = i + 1;
         while (a1 < nA && A[a1].seqIdx == A[i].seqIdx) ++a1;
-        AlleleBest ab; eval_allele(R, paired, A, i, a1, B, nB, ab);
-        if (paired) b0s[i] = (u32)ab.b0;
-        if (ab.valid) k1 = max(k1, ((u32)ab.mc << 12) | (u32)(4095 - ab.denom));
+        AlleleBest ab; eval_allele(R, paired, A, i, a1, B, nB, ab, -1, i + delta);
+        if (paired) { b0s[i] = (u32)ab.b0; myDelta = ab.b0 - i; }
+        const u32 key = ab.valid ? (((u32)ab.mc << 12) | (u32)(4095 - ab.denom)) : 0u;
+        keys[i] = key;
+        k1 = max(k1, key);
+      }
+      if (paired) {
+        const unsigned has = __ballot_sync(FULL, myDelta != 0x7fffffff);
+        if (has) delta = __shfl_sync(FULL, myDelta, 31 - __clz(has));
       }
     }
     k1 = __reduce_max_sync(FULL, k1);
@@ -245,7 +274,7 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
       if (R.relax) {
         for (int b = 0; b < nA; b += 32) {
           const int i = b + lane;
-          if (i < nA && (i == 0 || A[i - 1].seqIdx != A[i].seqIdx)) {
+          if (i < nA && keys[i] == k1) {
             int a1 = i + 1;
             while (a1 < nA && A[a1].seqIdx == A[i].seqIdx) ++a1;
             AlleleBest ab; eval_allele(R, paired, A, i, a1, B, nB, ab, paired ? (int)b0s[i] : -1);
@@ -271,7 +300,13 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
         const int i = b + lane;
         bool keep = false;
         AlleleBest ab;
-        if (i < nA && (i == 0 || A[i - 1].seqIdx != A[i].seqIdx)) {
+        // candidates only: the best key itself, or (relaxed mode) a matchCnt within relaxBy <= 4 of the best
+        bool cand = false;
+        if (i < nA) {
+          const u32 key = keys[i];                       // 0xffffffff: not the first record of its allele; 0: no valid pair
+          cand = key == k1 || (R.relax && key != 0 && key != 0xffffffffu && (int)(key >> 12) >= bestMc - 4);
+        }
+        if (cand) {
           int a1 = i + 1;
           while (a1 < nA && A[a1].seqIdx == A[i].seqIdx) ++a1;
           eval_allele(R, paired, A, i, a1, B, nB, ab, paired ? (int)b0s[i] : -1);
@@ -321,6 +356,10 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
         const int d1 = rv_denom(o1), d2 = rv_denom(o2);
         const double s1 = (double)o1.mc / (double)d1, s2 = (double)o2.mc / (double)d2;
         bool filter = false;
+        // nothing in a list can beat the chosen mate unless the list's best (matchCnt, denominator) key exceeds the mate's
+        const u32 key1 = ((u32)o1.mc << 12) | (u32)(4095 - d1), key2 = ((u32)o2.mc << 12) | (u32)(4095 - d2);
+        const bool scanA = P.readTop[A == L1 ? e1 : P.end2[f]] > key1, scanB = P.readTop[B == L1 ? e1 : P.end2[f]] > key2;
+        if (scanA)
         for (int i = lane; i < nA; i += 32) {
           const RV x = load_rv(A + i);
           bool better = x.mc > o1.mc;
@@ -329,6 +368,7 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
           if (truncated_mate(R, x, o1, o2)) filter = true;
           else if ((double)x.mc / (double)rv_denom(x) > s2 + 0.1) filter = true;
         }
+        if (scanB)
         for (int j = lane; j < nB; j += 32) {
           const RV x = load_rv(B + j);
           bool better = x.mc > o2.mc;
@@ -375,7 +415,10 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
   }
 }
 
-__global__ void __launch_bounds__(128) k_pair(PairParams P) {
+// MINB = resident blocks per SM the register budget is compiled for (3: no spills; 4: 128 registers, 16 warps/SM —
+// the kernel waits on dependent loads of the record lists, so the extra warps pay)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_pair(PairParams P) {
   const int lane = threadIdx.x & 31;
   for (;;) {
     u32 w = 0;

@@ -11,12 +11,14 @@
 #include "../t1k_b200/csrc/t1k_core.cuh"
 #include "../t1k_b200/csrc/t1k_host.hpp"
 
-long long t1k_emu_counters[16];
+long long t1k_emu_counters[32];
 using namespace t1k;
 
 struct Emu {
+  bool noFast = false;     // run everything through the general hit-list path (A/B check of the diagonal fast path)
   PackedRef P;
   std::vector<int32_t> covDiff, covPoint;
+  std::vector<u16> simThr;
   RefView R;
   std::vector<u8> scratch;
 };
@@ -35,7 +37,8 @@ Emu *emu_create(int32_t n, const char *bases, const int64_t *off, const int32_t 
   e->covPoint.assign(e->P.totalWords * 32, 0);
   RefView &R = e->R;
   R.seq2 = e->P.seq2.data(); R.n2 = e->P.n2.data(); R.ex2 = e->P.ex2.data();
-  R.wordOff = e->P.wordOff.data(); R.len = e->P.len.data(); R.hasN = e->P.hasN.data();
+  R.wordOff = e->P.wordOff.data(); R.len = e->P.len.data(); R.hasN = e->P.hasN.data(); R.meta = e->P.meta.data();
+  e->simThr.resize(2 * SIM_DEN); sim_threshold_table(sim, e->simThr.data()); R.simThr = e->simThr.data();
   R.kstart = e->P.kstart.data(); R.post = e->P.post.data();
   R.covDiff = e->covDiff.data(); R.covPoint = e->covPoint.data();
   R.nAlleles = n; R.sim = sim; R.relax = relax;
@@ -43,6 +46,7 @@ Emu *emu_create(int32_t n, const char *bases, const int64_t *off, const int32_t 
   return e;
 }
 void emu_destroy(Emu *e) { delete e; }
+void emu_set_fast(Emu *e, int on) { e->noFast = !on; }
 
 // dp_align / diag_certified on a single pair of strings; returns number of ops, fills ops, *certified
 int32_t emu_align(const char *t, int32_t lent, const char *p, int32_t lenp, int8_t *opsOut, int32_t *certified,
@@ -93,6 +97,8 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
     std::map<u32, std::vector<u32> > groups;
     u32 prev = 0; int skip = 0;
     const int P = len - KMER + 1;
+    u8 seedA[256]; int nS = 0;
+    bool strandFast = !Q.anyN && len <= FAST_MAX_LEN && !E->noFast;     // the kernel's eligibility rule (t1k_kernels.cuh)
     for (int a = 0; a < P; ++a) {
       u32 code = (u32)(fetch32(Q.seq2, a) & 0x3FFFFF);
       bool valid = (fetch32(Q.n2, a) & 0x155555) == 0;
@@ -102,15 +108,38 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
         int size = (int)(hi - lo);
         if (size >= 100 && a != 0 && a != P - 1 && skip < KMER / 2) { ++skip; continue; }
         skip = 0;
+        if (size > 0) { seedA[nS++] = (u8)a; if (kmer_homopolymer(code)) strandFast = false; }
         for (u32 j = lo; j < hi; ++j) groups[R.post[j].idx].push_back((u32)a | (R.post[j].off << 8));
       }
       prev = code;
     }
+    u32 stab[256];
+    if (strandFast) seed_table_build(seedA, nS, len, stab);
+    u32 lcMemo = 0;
     for (std::map<u32, std::vector<u32> >::iterator it = groups.begin(); it != groups.end(); ++it) {
       int nEmit = 0;
       std::vector<u32> &h = it->second;
+      if ((int)h.size() < 3) continue;
+      t1k_emu_counters[20] += 1;
+      if (strandFast) {
+        Cand fc; bool emitted = false;
+        if (diag_fast(R, Q, strand01, (int)it->first, (int)h.size(), h[0], stab, fc, emitted, bestKey, lcMemo)) {
+          if (emitted) cands.push_back(fc);
+          continue;
+        }
+      }
+      if (strandFast && getenv("EMU_DEBUG")) {
+        static int shown = 0;
+        bool one = true; for (size_t q = 1; q < h.size(); ++q) if (hit_b(h[q]) - hit_a(h[q]) != hit_b(h[0]) - hit_a(h[0])) one = false;
+        if (one && shown < 5) { ++shown;
+          fprintf(stderr, "allele %d n=%d d=%d hits:", (int)it->first, (int)h.size(), hit_b(h[0]) - hit_a(h[0]));
+          for (size_t q = 0; q < h.size(); ++q) fprintf(stderr, " %d", hit_a(h[q]));
+          fprintf(stderr, "\n seeds:"); for (int q = 0; q < nS; ++q) fprintf(stderr, " %d", seedA[q]);
+          fprintf(stderr, "\n");
+        }
+      }
       chain_allele(R, Q, strand01, (int)it->first, h.data(), 1, (int)h.size(), S, nEmit, bestKey, err);
-      for (int k = 0; k < nEmit; ++k) cands.push_back(S.emit()[k]);
+      for (int k = 0; k < nEmit; ++k) { Cand c = S.emit()[k]; c.mmPos = 0; cands.push_back(c); }
     }
     if (pass == 0) nFwd = (int)cands.size();
   }
@@ -121,7 +150,7 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
   // pass 1: extension + first failing key
   u64 fKey = ~0ull; int fIdx = 0x7fffffff;
   for (int i = c0; i < c1; ++i) {
-    extend_cand<false>(R, Q, cands[i], S, err);
+    if (!(cands[i].flags & CF_PRE)) extend_cand<false>(R, Q, cands[i], S, err);
     Cand &c = cands[i];
     if (!(c.flags & CF_SEP) && !(c.flags & CF_RET)) {
       u64 k = cand_key_pre(c);
@@ -151,8 +180,9 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
     Cand &c = cands[i];
     if (!(c.flags & CF_INCLUDE)) continue;
     if (weight >= 0) {
-      if (c.eMatchCnt >= bestMc - 10) full_align<false>(R, Q, c, weight, S, err);
-      else c.relaxed = 0;
+      if (c.eMatchCnt < bestMc - 10) c.relaxed = 0;
+      else if (c.flags & CF_FA) full_align_known(R, c, weight);
+      else full_align<false>(R, Q, c, weight, S, err);
     }
   }
   bool usePost = nInc > 1000;

@@ -32,6 +32,8 @@ def emu():
     lib.emu_assign.restype = C.c_int32
     lib.emu_assign.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     lib.emu_coverage.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.emu_set_fast.argtypes = [C.c_void_p, C.c_int32]
+    lib.emu_counters.restype = C.POINTER(C.c_longlong)
     lib.emu_align.restype = C.c_int32
     lib.emu_align.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
@@ -61,6 +63,87 @@ def test_lane_code_matches_reference_golden(emu, name):
         cov.append(out)
     assert np.array_equal(np.concatenate(cov), g["cov"])
     emu.emu_destroy(E)
+
+
+def _emu_assign_all(emu, E, reads, weight=1):
+    buf = np.zeros(1 << 16, dtype=O.OVERLAP_DT)
+    out = []
+    for s in reads:
+        err = C.c_int32(0)
+        n = emu.emu_assign(E, s, weight, O._p(buf), len(buf), C.byref(err))
+        assert err.value == 0
+        out.append((n, np.stack([buf[k][:max(n, 0)] for k in O.OVERLAP_DT.names], axis=1).copy()))
+    return out
+
+
+def _ab_workloads():
+    from t1k_b200 import synth
+    rng = np.random.default_rng(77)
+    # (records, reads, similarity, relax)
+    rna = W.small_rna_ref(seed=21)
+    r1, r2 = W.reads_for(rna, 150, read_len=150, seed=22, err=0.004, n_rate=0.0005, indel_rate=0.02, insert=(200, 400))
+    yield "rna150", rna, [r.tobytes() for r in r1] + [r.tobytes() for r in r2], 0.97, False
+    dna = W.small_dna_ref(seed=23)
+    r1, r2 = W.reads_for(dna, 150, read_len=100, seed=24, err=0.01, n_rate=0.002, indel_rate=0.05)
+    yield "dna100_relax", dna, [r.tobytes() for r in r1] + [r.tobytes() for r in r2], 0.9, True
+    # low-complexity / homopolymer / tandem-repeat alleles and reads: the cases the eligibility rule must catch
+    base = bytearray(synth.make_hla_rna_ref(genes=[("G", 1)], length=600, n_sites=10, min_sub=0, max_sub=0, seed=25)[0][2])
+    base[100:130] = b"A" * 30
+    base[200:240] = b"AC" * 20
+    base[300:345] = b"ACG" * 15
+    base[400:415] = b"T" * 15
+    recs = []
+    for i in range(40):
+        s = bytearray(base)
+        for _ in range(int(rng.integers(0, 6))):
+            s[int(rng.integers(0, len(s)))] = b"ACGT"[int(rng.integers(0, 4))]
+        if i % 7 == 3:
+            s = s[:int(rng.integers(300, 600))]           # truncated alleles: clips at the allele end
+        recs.append(("G*%02d:01" % i, "", bytes(s)))
+    reads = []
+    comp = bytes.maketrans(b"ACGTN", b"TGCAN")
+    for _ in range(400):
+        a = recs[int(rng.integers(0, len(recs)))][2]
+        L = int(rng.integers(40, 200))
+        st = int(rng.integers(-20, len(a) - 20))
+        r = bytearray(a[max(st, 0):max(st, 0) + L])
+        if st < 0:
+            r = bytearray(bytes(rng.choice(list(b"ACGT"), size=-st).astype(np.uint8))) + r     # overhang before the allele start
+        if len(r) < 20:
+            continue
+        for _ in range(int(rng.integers(0, 5))):
+            r[int(rng.integers(0, len(r)))] = b"ACGTN"[int(rng.integers(0, 5 if rng.integers(0, 4) == 0 else 4))]
+        if rng.integers(0, 10) == 0 and len(r) > 30:
+            k = int(rng.integers(5, len(r) - 5)); del r[k:k + int(rng.integers(1, 4))]
+        r = bytes(r)
+        reads.append(r.translate(comp)[::-1] if rng.integers(0, 2) else r)
+    yield "repeats", recs, reads, 0.8, False
+
+
+def test_diagonal_fast_path_equals_general_path(emu):
+    """diag_fast (mismatch-mask path of t1k_core.cuh) and chain_allele + extend_cand + full_align (hit-list path) give the
+    same AssignRead records and the same coverage on every workload; the fast path must actually be taken."""
+    for name, recs, reads, sim, relax in _ab_workloads():
+        ref = RefSet(recs)
+        bases, off, ptr, se = ref.packed()
+        res, covs, taken = [], [], []
+        for fast in (1, 0):
+            E = emu.emu_create(ref.n, bases, O._p(off), O._p(ptr), O._p(se), sim, int(relax))
+            emu.emu_set_fast(E, fast)
+            c0 = emu.emu_counters()[17]
+            res.append(_emu_assign_all(emu, E, reads, weight=2))
+            taken.append(emu.emu_counters()[17] - c0)
+            cov = []
+            for a in range(ref.n):
+                out = np.zeros(len(ref.seqs[a]), dtype=np.int32)
+                emu.emu_coverage(E, a, O._p(out))
+                cov.append(out)
+            covs.append(np.concatenate(cov))
+            emu.emu_destroy(E)
+        assert taken[0] > 0 and taken[1] == 0, (name, taken)
+        for i, ((n1, a), (n0, b)) in enumerate(zip(*res)):
+            assert n1 == n0 and np.array_equal(a, b), (name, i, reads[i])
+        assert np.array_equal(covs[0], covs[1]), name
 
 
 def test_banded_dp_and_diagonal_certificate(emu):

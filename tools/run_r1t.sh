@@ -1,0 +1,7 @@
+set -x
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests -m gpu -x -q ) 2>&1 | tail -8
+python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_r1t_fast.json 2> gpurun_out/bench_r1t_fast.err; tail -3 gpurun_out/bench_r1t_fast.err; cat gpurun_out/bench_r1t_fast.json
+T1K_NO_FAST=1 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_r1t_nofast.json 2> gpurun_out/bench_r1t_nofast.err; cat gpurun_out/bench_r1t_nofast.json
+ncu --set full --clock-control none --import-source on -k regex:k_assign -c 1 -o gpurun_out/prof_assign_r1t -f python bench.py --pairs 50000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_r1t.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_pair -c 1 -o gpurun_out/prof_pair_r1t -f python bench.py --pairs 50000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_pair_r1t.log 2>&1
