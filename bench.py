@@ -239,11 +239,14 @@ def main():
     # roofline of the dominant kernel (k_assign): algorithmic bytes per read-end = ceil(L/4) + 8 B per posting read +
     # 40 B per record kept, over the CUDA-event duration of its launches in the last timed step
     peak, peak_src = measured_peaks()
-    # k_assign is launched once per chunk of T1K_CHUNK_FRAGMENTS fragments (default 2^18): per-launch figures = per-step / chunks
+    # k_assign is launched once per chunk of fragments (T1K_CHUNK_FRAGMENTS = 2^18, a small first chunk to start the
+    # pipeline): per-launch figures are quoted for a full-size launch = per-step x (chunk / fragments per step)
     chunk = int(os.environ.get("T1K_CHUNK_FRAGMENTS", 1 << 18))
-    n_chunks = max(1, -(-args.pairs // chunk))
-    alg_bytes = (38 * out["n_unique_ends"] + 8 * out["n_postings"] + 40 * out["n_overlaps"]) / n_chunks
-    k_ms = out["ms_align_kernel"] / n_chunks
+    per_launch = min(args.pairs, chunk) / float(args.pairs)
+    first = min(chunk, int(os.environ.get("T1K_FIRST_CHUNK", chunk)))
+    n_chunks = 1 + max(0, -(-(args.pairs - first) // chunk)) if args.pairs > first else 1
+    alg_bytes = (38 * out["n_unique_ends"] + 8 * out["n_postings"] + 40 * out["n_overlaps"]) * per_launch
+    k_ms = out["ms_align_kernel"] * per_launch
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     traffic, traffic_src = measured_traffic(min(args.pairs, chunk))
     d2h = int(out["n_assignments"] * 24 + out["n_unique_ends"] * 16)

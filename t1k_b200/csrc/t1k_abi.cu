@@ -805,13 +805,14 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   std::vector<int64_t> rowPtrL((size_t)Gl + 1);
   for (int g = 0; g <= Gl; ++g) rowPtrL[g] = p->row_ptr[g0 + g] - k0;
   // CSC of the local rows with ascending group order inside every column => fixed summation order
-  std::vector<int64_t> colPtr((size_t)E + 1, 0);
-  for (int64_t k = 0; k < nnzL; ++k) ++colPtr[p->col[k0 + k] + 1];
-  for (int e = 0; e < E; ++e) colPtr[e + 1] += colPtr[e];
-  std::vector<int32_t> rowIdx((size_t)std::max<int64_t>(nnzL, 1));
+  std::vector<int64_t> colPtr;
+  std::vector<int32_t> rowIdx;
   {
-    std::vector<int64_t> cur(colPtr.begin(), colPtr.end() - 1);
-    for (int g = g0; g < g1; ++g) for (int64_t k = p->row_ptr[g]; k < p->row_ptr[g + 1]; ++k) rowIdx[cur[p->col[k]]++] = g;
+    int hostThreads = (int)std::thread::hardware_concurrency() / (comm ? comm->world : 1);
+    if (const char *env = getenv("T1K_HOST_THREADS")) hostThreads = atoi(env);
+    const int32_t *colp = p->col;
+    transpose_csr(rowPtrL.data(), Gl, [colp, k0](int64_t k) { return colp[k0 + k]; }, E, std::max(1, std::min(8, hostThreads)), colPtr, rowIdx);
+    for (size_t k = 0; k < (size_t)nnzL; ++k) rowIdx[k] += g0;       // global group ids
   }
   pt.lap("  em: validate + CSC");
   cudaStream_t st;
@@ -845,7 +846,7 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
       k_em_colsum<<<gCol, 256, 0, st>>>(E, dColPtr.as<int64_t>(), dRowIdx.as<int32_t>(), dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
     } else {
       if (Gl) k_em_rowsum_seq<<<(Gl + 127) / 128, 128, 0, st>>>(Gl, dRowPtr.as<int64_t>(), dCol.as<int32_t>(), xin, psumL);
-      k_em_colsum_seq<<<(E + 63) / 64, 64, 0, st>>>(E, dColPtr.as<int64_t>(), dRowIdx.as<int32_t>(), dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
+      k_em_colsum_seq<<<(unsigned)(((size_t)E * 32 + 255) / 256), 256, 0, st>>>(E, dColPtr.as<int64_t>(), dRowIdx.as<int32_t>(), dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
     }
     CK(cudaGetLastError());
     // the one exchange of the EM: per-EC expected read counts summed over the row shards (NVLink all-reduce)
@@ -1058,37 +1059,79 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     double ms = 0;
   } prep[2];
   const int mates = reads2 ? 2 : 1;
-  auto do_prep = [&](Prep &C, u32 f0, u32 m) {
+  // Unique read-ends of a chunk in two fork-join phases: (1) length, N flag and hash of every read-end (reads split
+  // across the threads), (2) one open-addressing table per hash partition (a thread owns a partition).  The unique
+  // index of a read-end = partition offset + rank inside the partition: deterministic for a given thread count, and
+  // nothing downstream depends on the order of the unique read-ends.
+  int prepThreads = std::max(1, std::min(8, (int)std::thread::hardware_concurrency() / ((prm->comm && prm->comm->world > 1) ? prm->comm->world : 1) / 2));
+  if (const char *env = getenv("T1K_PREP_THREADS")) prepThreads = std::max(1, atoi(env));
+  auto do_prep = [&, prepThreads](Prep &C, u32 f0, u32 m) {
     const double t = now_ms();
     C.f0 = f0; C.m = m; C.tooLong = false;
     C.e1.resize(m); if (reads2) C.e2.resize(m);
-    C.hasN.assign(m, 0); C.w.clear(); C.rep.clear(); C.len.clear();
-    size_t tabSize = 16; while (tabSize < (size_t)m * mates * 2) tabSize <<= 1;
-    C.table.assign(tabSize, 0xffffffffu);
-    for (u32 i = 0; i < m; ++i) {
-      for (int mate = 0; mate < mates; ++mate) {
-        const char *s = (mate ? reads2 : reads1) + (size_t)(f0 + i) * stride;
+    C.hasN.assign(m, 0);
+    const size_t nEnds = (size_t)m * mates;
+    const int T = nEnds < 4096 ? 1 : prepThreads;
+    std::vector<u64> hashes(nEnds);
+    std::vector<u32> lens(nEnds);
+    std::vector<u8> tooLong((size_t)T, 0);
+    auto end_ptr = [&](size_t k) { return ((k % mates) ? reads2 : reads1) + (size_t)(f0 + k / mates) * stride; };
+    run_threads(T, [&](int tIdx) {
+      const size_t k0 = nEnds * tIdx / T, k1 = nEnds * (tIdx + 1) / T;
+      for (size_t k = k0; k < k1; ++k) {
+        const char *s = end_ptr(k);
         u32 L = 0; u64 h = 1469598103934665603ull; bool hasN = false;
         while (L < stride && s[L]) { h = (h ^ (u8)s[L]) * 1099511628211ull; hasN |= s[L] == 'N'; ++L; }
-        if (L > T1K_MAX_READ_LEN) { C.tooLong = true; L = T1K_MAX_READ_LEN; }
-        if (hasN) C.hasN[i] = 1;
-        size_t slot = (size_t)(h ^ (h >> 29)) & (tabSize - 1);
+        if (L > T1K_MAX_READ_LEN) { tooLong[tIdx] = 1; L = T1K_MAX_READ_LEN; }
+        if (hasN) C.hasN[k / mates] = 1;          // both mates of a fragment belong to the same thread's range or write the same value
+        hashes[k] = h ^ (h >> 29); lens[k] = L;
+      }
+    });
+    for (int i = 0; i < T; ++i) if (tooLong[i]) C.tooLong = true;
+    struct Part { std::vector<u32> table, first, cnt; };      // first: read-end index of each unique, cnt: duplicates
+    std::vector<Part> parts((size_t)T);
+    std::vector<u32> local(nEnds);                             // rank of the read-end's unique inside its partition
+    run_threads(T, [&](int tIdx) {
+      Part &P = parts[tIdx];
+      size_t mine = 0;
+      for (size_t k = 0; k < nEnds; ++k) mine += (int)((hashes[k] >> 40) % (u64)T) == tIdx;
+      size_t tabSize = 16; while (tabSize < mine * 2) tabSize <<= 1;
+      P.table.assign(tabSize, 0xffffffffu);
+      for (size_t k = 0; k < nEnds; ++k) {
+        if ((int)((hashes[k] >> 40) % (u64)T) != tIdx) continue;
+        const char *s = end_ptr(k);
+        const u32 L = lens[k];
+        size_t slot = (size_t)hashes[k] & (tabSize - 1);
         u32 u;
         for (;;) {
-          u = C.table[slot];
-          if (u == 0xffffffffu) { u = (u32)C.rep.size(); C.table[slot] = u; C.rep.push_back(s); C.len.push_back(L); C.w.push_back(0); break; }
-          if (C.len[u] == L && memcmp(C.rep[u], s, L) == 0) break;
+          u = P.table[slot];
+          if (u == 0xffffffffu) { u = (u32)P.first.size(); P.table[slot] = u; P.first.push_back((u32)k); P.cnt.push_back(0); break; }
+          if (lens[P.first[u]] == L && memcmp(end_ptr(P.first[u]), s, L) == 0) break;
           slot = (slot + 1) & (tabSize - 1);
         }
-        ++C.w[u];                                   // Genotyper.cpp:149,472: weight = number of duplicates
-        (mate ? C.e2 : C.e1)[i] = u;
+        ++P.cnt[u];                                 // Genotyper.cpp:149,472: weight = number of duplicates
+        local[k] = u;
       }
-    }
-    C.off.resize(C.rep.size());
+    });
+    std::vector<u32> base((size_t)T + 1, 0);
+    for (int i = 0; i < T; ++i) base[i + 1] = base[i] + (u32)parts[i].first.size();
+    const size_t nU = base[T];
+    C.rep.resize(nU); C.len.resize(nU); C.w.resize(nU); C.off.resize(nU);
+    for (int i = 0; i < T; ++i)
+      for (size_t u = 0; u < parts[i].first.size(); ++u) {
+        const size_t k = parts[i].first[u];
+        C.rep[base[i] + u] = end_ptr(k); C.len[base[i] + u] = lens[k]; C.w[base[i] + u] = (int32_t)parts[i].cnt[u];
+      }
     size_t tot = 0;
-    for (size_t k = 0; k < C.rep.size(); ++k) { C.off[k] = tot; tot += C.len[k]; }
+    for (size_t k = 0; k < nU; ++k) { C.off[k] = tot; tot += C.len[k]; }
     C.bases.resize(tot + 1);
-    for (size_t k = 0; k < C.rep.size(); ++k) memcpy(C.bases.data() + C.off[k], C.rep[k], C.len[k]);
+    run_threads(T, [&](int tIdx) {
+      for (size_t k = nEnds * tIdx / T; k < nEnds * (tIdx + 1) / T; ++k) {
+        const u32 u = base[(int)((hashes[k] >> 40) % (u64)T)] + local[k];
+        ((k % mates) ? C.e2 : C.e1)[k / mates] = u;
+      }
+      for (size_t k = nU * tIdx / T; k < nU * (tIdx + 1) / T; ++k) memcpy(C.bases.data() + C.off[k], C.rep[k], C.len[k]);
+    });
     C.ms = now_ms() - t;
   };
   CK(cudaMemsetAsync(ref->covDiff.p, 0, ref->paddedBases * 4, ref->stream));
@@ -1113,15 +1156,24 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   };
   std::thread prepThread, coalThread;
   struct Joiner { std::thread &a, &b; ~Joiner() { if (a.joinable()) a.join(); if (b.joinable()) b.join(); } } joiner{prepThread, coalThread};
-  const u32 nChunks = n_frag ? (n_frag + chunk - 1) / chunk : 0;
-  if (nChunks) do_prep(prep[0], 0, std::min(chunk, n_frag));
+  // chunk boundaries: the first chunk is small, because its preparation is the one stage nothing can overlap with
+  std::vector<std::pair<u32, u32>> chunks;      // (first fragment, count)
+  {
+    u32 f0 = 0;
+    u32 firstChunk = chunk;        // (a smaller first chunk starts the device earlier but de-duplicates less: T1K_FIRST_CHUNK)
+    if (const char *env = getenv("T1K_FIRST_CHUNK")) firstChunk = (u32)std::max(1l, atol(env));
+    while (f0 < n_frag) {
+      const u32 m = std::min(chunks.empty() ? firstChunk : chunk, n_frag - f0);
+      chunks.push_back(std::make_pair(f0, m));
+      f0 += m;
+    }
+  }
+  const u32 nChunks = (u32)chunks.size();
+  if (nChunks) do_prep(prep[0], chunks[0].first, chunks[0].second);
   for (u32 c = 0; c < nChunks; ++c) {
     Prep &C = prep[c & 1];
     res->ms_dedup += (float)C.ms;
-    if (c + 1 < nChunks) {
-      const u32 f0n = (c + 1) * chunk;
-      prepThread = std::thread(do_prep, std::ref(prep[(c + 1) & 1]), f0n, std::min(chunk, n_frag - f0n));
-    }
+    if (c + 1 < nChunks) prepThread = std::thread(do_prep, std::ref(prep[(c + 1) & 1]), chunks[c + 1].first, chunks[c + 1].second);
     if (C.tooLong) return fail(T1K_ERR_ARG, "read longer than T1K_MAX_READ_LEN");
     res->n_unique_ends += C.rep.size();
     double ta = now_ms();
@@ -1190,7 +1242,7 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   double tc = now_ms();
   PhaseTimer pt;
   EquivalenceClasses EC;
-  EC.build(groups, nA);
+  EC.build(groups, nA, shards.threads());
   pt.lap("equivalence classes");
   res->n_groups = groups.size(); res->n_ec = EC.size(); res->n_alleles = nA;
   if (res->missing_coverage) { if (int rc = t1k_missing_coverage(ref, res->missing_coverage)) return rc; }
@@ -1204,7 +1256,7 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   if (res->ec_abundance) memset(res->ec_abundance, 0, (size_t)nA * 8);
   if (EC.size() > 0) {
     EmInputs in;
-    in.build(groups, EC, prm->effective_len, prm->seq_weight);
+    in.build(groups, EC, prm->effective_len, prm->seq_weight, shards.threads());
     pt.lap("EM inputs");
     if (pt.on) fprintf(stderr, "[t1k timing] groups %d entries %zu ECs %d nnz %zu\n", groups.size(), groups.ent.size(), EC.size(), in.col.size());
     T1KEmProblem ep;

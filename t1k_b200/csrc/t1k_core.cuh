@@ -544,6 +544,9 @@ T1K_HDN T1K_NOINLINE inline int align_matches_cold(const AlleleView &T, int tpos
     if (diag_certified(T, tpos, Q, ppos, lent, mm)) return lent - mm;
   }
   T1K_COUNT(5, 1);
+#if !defined(__CUDACC__) && defined(T1K_EMU_COUNTERS)
+  if (lent == lenp) { int mmx; diag_certified(T, tpos, Q, ppos, lent, mmx); T1K_COUNT(24 + (mmx >= 11 ? 7 : mmx < 4 ? 0 : mmx - 4), 1); }
+#endif
   int n = dp_align(T, tpos, lent, Q, ppos, lenp, S, err);
   int c = 0;
   const u8 *ops = S.ops();

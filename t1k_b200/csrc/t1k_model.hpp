@@ -3,6 +3,7 @@
 // equivalence classes, EM problem assembly, allele abundances).  Plain C++, no CUDA.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -225,30 +226,87 @@ inline void partition_rows(const int64_t *rowPtr, int32_t nGroups, int32_t world
 // Genotyper::FinalizeReadAssignments + BuildAlleleEquivalentClass (Genotyper.hpp:912-939, 1072-1139).
 // RemoveLowMAPQAlleleInEquivalentClass (:1330-1368) keeps the members whose summed qual is maximal; every
 // assignment has qual 1 and EC members share their read groups, so it keeps all of them.
+// ---- small fork-join helpers for the serial tail of the host model (deterministic: every thread owns a contiguous
+// range and results are concatenated in range order, so the output is the single-threaded one)
+// inputs smaller than this stay single-threaded (T1K_PAR_MIN overrides: the parity tests force the threaded path)
+inline size_t par_min_entries() {
+  const char *e = getenv("T1K_PAR_MIN");
+  return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)1 << 16;
+}
+template <class F> inline void run_threads(int n, F fn) {
+  if (n <= 1) { fn(0); return; }
+  std::vector<std::thread> th;
+  for (int t = 1; t < n; ++t) th.emplace_back(fn, t);
+  fn(0);
+  for (size_t t = 0; t < th.size(); ++t) th[t].join();
+}
+// contiguous row ranges with about equal numbers of entries: bounds[t] .. bounds[t + 1]
+inline std::vector<int32_t> balanced_ranges(const int64_t *ptr, int32_t nRows, int threads) {
+  std::vector<int32_t> b((size_t)threads + 1, nRows);
+  b[0] = 0;
+  const int64_t nnz = nRows > 0 ? ptr[nRows] - ptr[0] : 0;
+  int32_t r = 0;
+  for (int t = 1; t < threads; ++t) {
+    const int64_t want = ptr[0] + nnz * t / threads;
+    while (r < nRows && ptr[r] < want) ++r;
+    b[t] = r;
+  }
+  return b;
+}
+// CSR (row -> column ids, colOf(k) for entry k) to CSC with ascending row order inside every column
+template <class ColOf>
+inline void transpose_csr(const int64_t *rowPtr, int32_t nRows, ColOf colOf, int32_t nCols, int threads, std::vector<int64_t> &colPtr,
+                          std::vector<int32_t> &rowIdx) {
+  const int64_t nnz = nRows > 0 ? rowPtr[nRows] - rowPtr[0] : 0, k0 = nRows > 0 ? rowPtr[0] : 0;
+  if (threads < 1) threads = 1;
+  if ((size_t)nnz < par_min_entries()) threads = 1;
+  const std::vector<int32_t> b = balanced_ranges(rowPtr, nRows, threads);
+  std::vector<std::vector<int64_t> > cnt((size_t)threads, std::vector<int64_t>((size_t)nCols, 0));
+  run_threads(threads, [&](int t) {
+    std::vector<int64_t> &c = cnt[t];
+    for (int64_t k = rowPtr[b[t]]; k < rowPtr[b[t + 1]]; ++k) ++c[colOf(k)];
+  });
+  colPtr.assign((size_t)nCols + 1, 0);
+  for (int32_t c = 0; c < nCols; ++c) {
+    int64_t run = colPtr[c];
+    for (int t = 0; t < threads; ++t) { const int64_t n = cnt[t][c]; cnt[t][c] = run; run += n; }     // cnt becomes the thread's cursor
+    colPtr[c + 1] = run;
+  }
+  rowIdx.resize((size_t)std::max<int64_t>(nnz, 1));
+  run_threads(threads, [&](int t) {
+    std::vector<int64_t> &cur = cnt[t];
+    for (int32_t r = b[t]; r < b[t + 1]; ++r)
+      for (int64_t k = rowPtr[r]; k < rowPtr[r + 1]; ++k) rowIdx[cur[colOf(k)]++] = r;
+  });
+  (void)k0;
+}
+
 struct EquivalenceClasses {
   std::vector<int32_t> ecPtr{0}, ecAlleles, alleleEc;
 
-  void build(const ReadGroups &G, int32_t nAlleles) {
+  void build(const ReadGroups &G, int32_t nAlleles, int threads = 1) {
     const int32_t readCnt = G.size();
-    std::vector<int64_t> inPtr(nAlleles + 1, 0);
-    for (size_t k = 0; k < G.ent.size(); ++k) ++inPtr[G.ent[k].alleleIdx + 1];
-    for (int32_t a = 0; a < nAlleles; ++a) inPtr[a + 1] += inPtr[a];
-    std::vector<int32_t> in(G.ent.size());
-    {
-      std::vector<int64_t> cur(inPtr.begin(), inPtr.end() - 1);
-      for (int32_t g = 0; g < readCnt; ++g)
-        for (int64_t k = G.ptr[g]; k < G.ptr[g + 1]; ++k) in[cur[G.ent[k].alleleIdx]++] = g;
-    }
+    // readsInAllele (Genotyper.hpp:912-939): the groups of every allele, ascending
+    std::vector<int64_t> inPtr;
+    std::vector<int32_t> in;
+    const HostEntry *ent = G.ent.data();
+    transpose_csr(G.ptr.data(), readCnt, [ent](int64_t k) { return ent[k].alleleIdx; }, nAlleles, threads, inPtr, in);
     struct FP { int32_t a, b; };
     std::vector<FP> fp(nAlleles);
-    for (int32_t a = 0; a < nAlleles; ++a) {
-      int32_t b = -1;
-      if (inPtr[a + 1] > inPtr[a]) {
-        b = 0;
-        for (int64_t k = inPtr[a]; k < inPtr[a + 1]; ++k)
-          b = (int32_t)(((uint32_t)b * (uint32_t)readCnt + (uint32_t)in[k]) % 1000003u);   // Genotyper.hpp:1089
-      }
-      fp[a].a = a; fp[a].b = b;
+    {
+      const int T = G.ent.size() < par_min_entries() ? 1 : std::max(1, threads);
+      const std::vector<int32_t> ab = balanced_ranges(inPtr.data(), nAlleles, T);
+      run_threads(T, [&](int t) {
+        for (int32_t a = ab[t]; a < ab[t + 1]; ++a) {
+          int32_t b = -1;
+          if (inPtr[a + 1] > inPtr[a]) {
+            b = 0;
+            for (int64_t k = inPtr[a]; k < inPtr[a + 1]; ++k)
+              b = (int32_t)(((uint32_t)b * (uint32_t)readCnt + (uint32_t)in[k]) % 1000003u);   // Genotyper.hpp:1089
+          }
+          fp[a].a = a; fp[a].b = b;
+        }
+      });
     }
     std::sort(fp.begin(), fp.end(), [](const FP &x, const FP &y) { return x.b != y.b ? y.b < x.b : x.a < y.a; });
     alleleEc.assign(nAlleles, -1);
@@ -283,20 +341,34 @@ struct EmInputs {
   std::vector<int32_t> col, ecLen;
   std::vector<double> count, x0;
 
-  void build(const ReadGroups &G, const EquivalenceClasses &EC, const int32_t *effectiveLen, const int32_t *seqWeight) {
+  void build(const ReadGroups &G, const EquivalenceClasses &EC, const int32_t *effectiveLen, const int32_t *seqWeight, int threads = 1) {
     const int32_t n = G.size(), E = EC.size();
-    rowPtr.assign(1, 0); col.clear(); count.resize(n);
-    std::vector<int32_t> stamp(E, -1);
-    for (int32_t g = 0; g < n; ++g) {
-      float c = G.ent[G.ptr[g]].weight;
-      for (int64_t k = G.ptr[g] + 1; k < G.ptr[g + 1]; ++k) if (G.ent[k].weight > c) c = G.ent[k].weight;
-      count[g] = c;
-      for (int64_t k = G.ptr[g]; k < G.ptr[g + 1]; ++k) {
-        const int32_t e = EC.alleleEc[G.ent[k].alleleIdx];
-        if (stamp[e] != g) { stamp[e] = g; col.push_back(e); }
+    count.resize(n);
+    if (threads < 1 || G.ent.size() < par_min_entries()) threads = 1;
+    const std::vector<int32_t> b = balanced_ranges(G.ptr.data(), n, threads);
+    std::vector<std::vector<int32_t> > cols((size_t)threads);
+    std::vector<int64_t> rowLen((size_t)n, 0);
+    run_threads(threads, [&](int t) {
+      std::vector<int32_t> stamp(E, -1);
+      std::vector<int32_t> &out = cols[t];
+      for (int32_t g = b[t]; g < b[t + 1]; ++g) {
+        float c = G.ent[G.ptr[g]].weight;
+        for (int64_t k = G.ptr[g] + 1; k < G.ptr[g + 1]; ++k) if (G.ent[k].weight > c) c = G.ent[k].weight;
+        count[g] = c;
+        const size_t before = out.size();
+        for (int64_t k = G.ptr[g]; k < G.ptr[g + 1]; ++k) {
+          const int32_t e = EC.alleleEc[G.ent[k].alleleIdx];
+          if (stamp[e] != g) { stamp[e] = g; out.push_back(e); }
+        }
+        rowLen[g] = (int64_t)(out.size() - before);
       }
-      rowPtr.push_back((int64_t)col.size());
-    }
+    });
+    rowPtr.assign((size_t)n + 1, 0);
+    for (int32_t g = 0; g < n; ++g) rowPtr[g + 1] = rowPtr[g] + rowLen[g];
+    col.resize((size_t)rowPtr[n]);
+    run_threads(threads, [&](int t) {
+      if (!cols[t].empty()) memcpy(col.data() + rowPtr[b[t]], cols[t].data(), cols[t].size() * sizeof(int32_t));
+    });
     ecLen.resize(E); x0.resize(E);
     for (int32_t e = 0; e < E; ++e) {
       int32_t len = effectiveLen[EC.ecAlleles[EC.ecPtr[e]]];

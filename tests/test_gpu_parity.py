@@ -188,14 +188,15 @@ def test_genotype_vs_oracle(workload):
 
 def test_chunking_and_store_growth_do_not_change_results(workload, monkeypatch):
     """Small fragment chunks (read-ends re-aligned per chunk with split weights; the three-stage host pipeline runs
-    with many chunks), a record store that overflows and is grown (deferred read-ends re-run) and a pairing row buffer
-    that overflows must give the very same integers."""
+    with many chunks), a record store that overflows and is grown (deferred read-ends re-run), a pairing row buffer
+    that overflows and the multi-threaded host tail must give the very same integers."""
     wl = workload
     gt = Genotyper(wl["ref"], wl["sim"], wl["relax"])
     base = gt.Genotype(wl["r1"], wl["r2"])
     monkeypatch.setenv("T1K_CHUNK_FRAGMENTS", "37")
     monkeypatch.setenv("T1K_STORE_RECORDS", "2000")
     monkeypatch.setenv("T1K_PAIR_ROWS", "64")          # pairing rows overflow their first buffer: exact re-run
+    monkeypatch.setenv("T1K_PAR_MIN", "1")             # the threaded host tail (EC build, EM inputs, CSC) on small inputs too
     out = gt.Genotype(wl["r1"], wl["r2"])
     for k in ("equivalent_class", "missing_coverage", "fragment_assigned"):
         assert np.array_equal(out[k], base[k]), k
