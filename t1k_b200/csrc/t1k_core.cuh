@@ -307,6 +307,44 @@ T1K_HDN T1K_NOINLINE inline bool diag_certified_hist(const AlleleView &T, int tp
   return excess <= 1;
 }
 
+// Interval certificate (any number of diagonal mismatches <= 24).  A connected excursion from the diagonal over rows
+// A..B with k segments at shifts d_1..d_k (k + 1 gap events, U unpaired rows) changes the score by
+//     4 * (a_I - nu - |U| - (k + 1)),     a_I = diagonal mismatches in A..B, nu = mismatches of the shifted pairs,
+// and a_I <= a_P + |U| (a_P = diagonal mismatches on paired rows), so a gain needs sum_s (a_{P_s} - nu_s) >= k + 2.
+// Per segment a_{P_s} - nu_s <= G_d := the largest sum over a row interval of (+1: diagonal mismatch that shift d turns
+// into a match, -1: diagonal match that shift d turns into a mismatch).  If G_d <= 1 for every shift of the band the sum
+// is at most k: no excursion gains, the traceback stays on the diagonal.  G_d <= 1 iff between every two consecutive
+// "+1" rows of shift d lies at least one "-1" row.
+T1K_HDN T1K_NOINLINE inline bool diag_certified_interval(const AlleleView &T, int tpos, const ReadView &Q, int ppos, int n) {
+  int pos[24];
+  int mm = 0;
+  T1K_NOUNROLL
+  for (int k = 0; k < n; k += 32) {
+    u64 m = mm_chunk(T, tpos + k, Q, ppos + k, n - k);
+    T1K_NOUNROLL
+    while (m) { if (mm >= 24) return false; pos[mm++] = k + (ctz64(m) >> 1); m &= m - 1; }
+  }
+  T1K_NOUNROLL
+  for (int d = -BAND; d <= BAND; ++d) {
+    if (d == 0) continue;
+    const int lo = d < 0 ? -d : 0, hi = d > 0 ? n - 1 - d : n - 1;      // rows that have a column at this shift
+    int prevPlus = -1, both = 0;                                        // both: mismatch rows since prevPlus that stay mismatches
+    T1K_NOUNROLL
+    for (int q = 0; q < mm; ++q) {
+      const int r = pos[q];
+      if (r < lo || r > hi) continue;
+      if (!base_eq(T, tpos + r + d, Q, ppos + r)) { ++both; continue; }
+      if (prevPlus >= 0) {
+        // "-1" rows in (prevPlus, r) = shifted mismatches there minus the `both` rows; one is enough
+        if (r - prevPlus - 1 <= both) return false;
+        if (shifted_mm(T, tpos, Q, ppos, n, d, prevPlus + 1, r - 1, both) <= both) return false;
+      }
+      prevPlus = r; both = 0;
+    }
+  }
+  return true;
+}
+
 T1K_HD bool diag_certified(const AlleleView &T, int tpos, const ReadView &Q, int ppos, int n, int &mmOut) {
   int mm = 0;
   if (n <= 32) mm = popc64(mm_chunk(T, tpos, Q, ppos, n));     // the gap between two seed hits: one word
@@ -316,9 +354,10 @@ T1K_HD bool diag_certified(const AlleleView &T, int tpos, const ReadView &Q, int
   }
   mmOut = mm;
   if (mm <= 3) return true;
-  if (mm <= 5) return diag_certified_45(T, tpos, Q, ppos, n, mm);
+  // 4-5: the cheap sufficient tests first, the exact enumeration only when they cannot tell
+  if (mm <= 5) return diag_certified_interval(T, tpos, Q, ppos, n) || diag_certified_45(T, tpos, Q, ppos, n, mm);
   if (mm > 24) return false;
-  return diag_certified_hist(T, tpos, Q, ppos, n);
+  return diag_certified_hist(T, tpos, Q, ppos, n) || diag_certified_interval(T, tpos, Q, ppos, n);
 }
 
 // The equal-length case of dp_align below (99.9 % of the calls): band 5 on both sides, 13 window columns, the two rolling
@@ -750,14 +789,17 @@ constexpr int FAST_MAX_LEN = 160;    // read length the fast path handles (5 wor
 //     at least one seed: hitLen = sum(last - first + k);
 //   * the gap between two runs holds the mismatches in between; with <= 32 columns and <= 3 mismatches GlobalAlignment
 //     of the gap is the pure diagonal (DESIGN.md "diagonal certificate"): matches = columns - mismatches.
-// Everything else (count mismatch = hits on other diagonals, N in the window, long or dirty gaps, reads > 160 bases)
-// returns false with nothing written and the caller runs chain_allele on the gathered hit list.
+//     A longer or dirtier gap runs the same align_matches_cold as the hit-list walk would.
+// Everything else (count mismatch = hits on other diagonals, N in the window, a seed step > k-1 inside a stretch, reads
+// > 160 bases) returns false with nothing written and the caller runs chain_allele on the gathered hit list.
 // The same mismatch positions give ExtendOverlap (both overhangs lie on the diagonal) and the full-read alignment.
 // lcMemo: per-lane memo of IsOverlapLowComplex for the last (readStart, readEnd) of this strand (0 = empty).
-T1K_HDN T1K_NOINLINE inline bool diag_fast(const RefView &R, const ReadView &Q, int strand01, int seqIdx, int n, u32 h0, const u32 *stab,
-                              Cand &out, bool &emitted, u64 &bestStrandKey, u32 &lcMemo) {
+// hits/stride: the allele's gathered hit list (only consulted when one or two postings are not on the diagonal).
+T1K_HDN T1K_NOINLINE inline bool diag_fast(const RefView &R, const ReadView &Q, int strand01, int seqIdx, int n, const u32 *hits, int stride,
+                              const u32 *stab, Cand &out, bool &emitted, u64 &bestStrandKey, u32 &lcMemo, const LaneScratch &S, int &err) {
   emitted = false;
   const int len = Q.len;
+  const u32 h0 = hits[0];
   const int d = hit_b(h0) - hit_a(h0);
 #ifdef __CUDA_ARCH__
   const uint4 mt = *reinterpret_cast<const uint4 *>(R.meta + seqIdx);
@@ -815,8 +857,13 @@ T1K_HDN T1K_NOINLINE inline bool diag_fast(const RefView &R, const ReadView &Q, 
           if (rs < 0) { rs = f; mmLeft = mmRun; }
           else {
             const int g = f - (lastL + KMER);
-            if (g > 32 || mmRun > 3) { ok = false; break; }
-            gapMatches += g - mmRun;
+            if (g > 32 || mmRun > 3) {
+              // a long or dirty gap: the same GlobalAlignment the hit-list walk would run (certificates, else the band
+              // DP), the rest of the allele stays on this path.  No N in the window => the N planes are not consulted.
+              AlleleView T;
+              T.seq = R.seq2 + w0; T.n2 = R.n2 + w0; T.ex2 = R.ex2 + w0; T.len = clen; T.hasN = alleleHasN; T.useN = false;
+              gapMatches += align_matches_cold(T, lastL + KMER + d, g, Q, lastL + KMER, g, S, err);
+            } else gapMatches += g - mmRun;
           }
           hitLen += l - f + KMER;
           cntSum += (int)(tl & 255) - (int)(tf & 255) + 1;
@@ -831,7 +878,24 @@ T1K_HDN T1K_NOINLINE inline bool diag_fast(const RefView &R, const ReadView &Q, 
   }
   T1K_COUNT(16, 1);
   if (!ok) T1K_COUNT(21, 1); else if (cntSum < n) T1K_COUNT(22, 1); else if (cntSum > n) T1K_COUNT(23, 1);
-  if (!ok || cntSum != n) return false;
+  if (!ok || cntSum > n) return false;
+  if (cntSum < n) {
+    // One or two postings off the diagonal (a k-mer of the read that also occurs elsewhere in the allele).  If every one
+    // of them lies more than RADIUS diagonals away, the diagonal sort puts a cluster break on both sides of the main
+    // diagonal (SeqSet.hpp:1369-1374), so its cluster is exactly the seeds found above, and the strays form clusters of
+    // fewer than three hits, which are dropped (SeqSet.hpp:1399-1404): the result is the single-diagonal one.
+    const int extra = n - cntSum;
+    if (extra > 2) return false;
+    int far = 0, onDiag = 0;
+    T1K_NOUNROLL
+    for (int i = 0; i < n; ++i) {
+      const u32 h = hits[(size_t)i * stride];
+      const int dd = hit_b(h) - hit_a(h) - d;
+      onDiag += dd == 0;
+      far += dd > RADIUS || dd < -RADIUS;
+    }
+    if (onDiag != cntSum || far != extra) return false;
+  }
   T1K_COUNT(17, 1);
   // ---- from here on the result is the reference's: the tail of consume_chain<true>
   if (hitLen < HIT_LEN_REQ) return true;
@@ -1074,8 +1138,8 @@ T1K_HDN T1K_NOINLINE inline void full_align_cold(const RefView &R, const ReadVie
   if (lent == lenp) {
     bool diag = mm <= 3;
     if (!diag) {
-      if (mm <= 5) diag = diag_certified_45(T, tpos, Q, ppos, lent, mm);
-      else if (mm <= 24) diag = diag_certified_hist(T, tpos, Q, ppos, lent);
+      if (mm <= 5) diag = diag_certified_interval(T, tpos, Q, ppos, lent) || diag_certified_45(T, tpos, Q, ppos, lent, mm);
+      else if (mm <= 24) diag = diag_certified_hist(T, tpos, Q, ppos, lent) || diag_certified_interval(T, tpos, Q, ppos, lent);
     }
     if (diag) {
       if (weight > 0) {

@@ -202,12 +202,47 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
           }
           prev = code;
         }
-        if (strandFast) seed_table_build(W.seedA, nS, len, W.stab);
       }
       nS = __shfl_sync(FULL, nS, 0);
       strandFast = __shfl_sync(FULL, (int)strandFast, 0) != 0;
       u32 lcMemo = 0;
       __syncwarp();
+      if (strandFast) {
+        // seed table (see seed_table_build), warp-cooperative: seed / wide-step bit masks in W.cnt (free until the first
+        // tile), then every lane derives the entries of its read positions from the masks
+        if (lane < 16) W.cnt[lane] = 0;
+        __syncwarp();
+        T1K_NOUNROLL
+        for (int k = lane; k < nS; k += 32) {
+          const int a = W.seedA[k];
+          atomicOr(&W.cnt[a >> 5], 1u << (a & 31));
+          if (k > 0 && a - (int)W.seedA[k - 1] > KMER - 1) atomicOr(&W.cnt[8 + (a >> 5)], 1u << (a & 31));
+        }
+        __syncwarp();
+        T1K_NOUNROLL
+        for (int a = lane; a < len; a += 32) {
+          const int wi = a >> 5, bit = a & 31;             // wi is warp-uniform
+          u32 cnt = 0, big = 0;
+          T1K_NOUNROLL
+          for (int w = 0; w < wi; ++w) { cnt += __popc(W.cnt[w]); big += __popc(W.cnt[8 + w]); }
+          const u32 upTo = 0xffffffffu >> (31 - bit);
+          const u32 cw = W.cnt[wi] & upTo;
+          cnt += __popc(cw); big += __popc(W.cnt[8 + wi] & upTo);
+          u32 last = 255, nxt = 255;
+          {
+            int w = wi; u32 m = cw;
+            T1K_NOUNROLL
+            for (;;) { if (m) { last = (u32)(w * 32 + 31 - __clz(m)); break; } if (--w < 0) break; m = W.cnt[w]; }
+          }
+          {
+            int w = wi; u32 m = W.cnt[wi] & (0xffffffffu << bit);
+            T1K_NOUNROLL
+            for (;;) { if (m) { nxt = (u32)(w * 32 + __ffs(m) - 1); break; } if (++w >= 8) break; m = W.cnt[w]; }
+          }
+          W.stab[a] = cnt | (big << 8) | (nxt << 16) | (last << 24);
+        }
+        __syncwarp();
+      }
       T1K_NOUNROLL
       for (int k = lane; k < nS; k += 32) { W.nxt[k] = R.post[W.cur[k]].idx; stPost += W.end[k] - W.cur[k]; }
       __syncwarp();
@@ -307,7 +342,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
         Cand fc;
         bool fastEmit = false, handled = n < 3;
         if (strandFast && n >= 3) {
-          handled = diag_fast(R, Qv, strand01, (int)(base + lane), n, W.H[lane], W.stab, fc, fastEmit, laneKey, lcMemo);
+          handled = diag_fast(R, Qv, strand01, (int)(base + lane), n, W.H + lane, 32, W.stab, fc, fastEmit, laneKey, lcMemo, S, err);
           if (fastEmit) nEmit = 1;
         }
         if (!handled) chain_allele(R, Qv, strand01, (int)(base + lane), W.H + lane, 32, n, S, nEmit, laneKey, err);

@@ -123,7 +123,7 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
       t1k_emu_counters[20] += 1;
       if (strandFast) {
         Cand fc; bool emitted = false;
-        if (diag_fast(R, Q, strand01, (int)it->first, (int)h.size(), h[0], stab, fc, emitted, bestKey, lcMemo)) {
+        if (diag_fast(R, Q, strand01, (int)it->first, (int)h.size(), h.data(), 1, stab, fc, emitted, bestKey, lcMemo, S, err)) {
           if (emitted) cands.push_back(fc);
           continue;
         }

@@ -183,6 +183,50 @@ def test_banded_dp_and_diagonal_certificate(emu):
     assert certified > 300
 
 
+def test_diagonal_certificates_are_sound_on_clustered_mismatches(emu):
+    """Equal-length pairs with 3-13 clustered substitutions, periodic / low-complexity sequence and displaced segments (the
+    inputs where a gapped path can beat the diagonal): dp_align_eq == GlobalAlignment op for op, and whenever a
+    certificate (<= 3, exact 4-5 enumeration, shift histogram, interval) fires the reference alignment has no indel."""
+    rng = np.random.default_rng(99)
+    alpha = np.frombuffer(b"ACGT", dtype=np.uint8)
+    certified_by_mm = {}
+    for it in range(5000):
+        n = int(rng.integers(8, 170))
+        mode = it % 4
+        if mode == 0:
+            t = alpha[rng.integers(0, 4, size=n)].copy()
+        elif mode == 1:
+            t = np.resize(alpha[rng.integers(0, 4, size=int(rng.integers(1, 7)))], n).copy()
+        elif mode == 2:
+            t = alpha[rng.integers(0, 2, size=n)].copy()
+        else:
+            t = np.resize(alpha[rng.integers(0, 4, size=int(rng.integers(2, 12)))], n).copy()
+            for _ in range(int(rng.integers(0, 4))):
+                t[rng.integers(0, n)] = alpha[rng.integers(0, 4)]
+        p = t.copy()
+        if it % 5 == 0 and n > 20:             # a displaced segment: the indel-favouring case
+            k = int(rng.integers(1, n - 12)); d = int(rng.integers(1, 5)); k2 = int(rng.integers(k, n - d))
+            p = np.concatenate([p[:k], p[k + d:k2 + d], alpha[rng.integers(0, 4, size=d)], p[k2 + d:]])[:n]
+            if len(p) < n:
+                p = np.concatenate([p, alpha[rng.integers(0, 4, size=n - len(p))]])
+        c0 = int(rng.integers(0, n))
+        for _ in range(int(rng.integers(3, 14))):
+            j = int(np.clip(c0 + rng.integers(-12, 13), 0, n - 1)) if it % 2 else int(rng.integers(0, n))
+            p[j] = alpha[rng.integers(0, 4)]
+        tb, pb = t.tobytes(), p.tobytes()
+        _, ops = O.global_alignment(tb, pb)
+        out = np.zeros(2 * n + 16, dtype=np.int8)
+        cert, matches = C.c_int32(0), C.c_int32(0)
+        k = emu.emu_align(tb, n, pb, n, O._p(out), C.byref(cert), C.byref(matches))
+        assert k == len(ops) and np.array_equal(out[:k], ops), (tb, pb)
+        assert matches.value == int((ops == 0).sum())
+        if cert.value:
+            mm = int((t != p).sum())
+            certified_by_mm[mm] = certified_by_mm.get(mm, 0) + 1
+            assert set(ops.tolist()) <= {0, 1}, (tb, pb)
+    assert sum(v for m, v in certified_by_mm.items() if m >= 6) > 500      # the interval certificate is exercised
+
+
 def test_parse_helpers():
     assert parse_exons("7 50 221 623 783", 3000) == [(50, 221), (623, 783)]
     assert parse_exons("", 100) == [(0, 99)]
