@@ -260,7 +260,7 @@ int t1k_ref_create(const T1KRefDesc *d, T1KRef **out) {
     if (e != cudaSuccess) { delete r; return fail(T1K_ERR_CUDA, std::string("t1k_ref_create upload: ") + cudaGetErrorString(e)); } \
   } while (0)
   UP(seq2, P.seq2); UP(n2, P.n2); UP(ex2, P.ex2); UP(dWordOff, P.wordOff); UP(dLen, P.len); UP(dHasN, P.hasN); UP(dMeta, P.meta); UP(kstart, P.kstart);
-  if (P.post.empty()) P.post.resize(1);
+  P.post.resize(P.post.size() + 64);       // slack: the gather's TMA copies read a fixed 34 postings from any cursor
   UP(post, P.post);
   std::vector<u16> simThr(2 * SIM_DEN);
   sim_threshold_table(d->similarity, simThr.data());
@@ -410,6 +410,7 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   P.O.err = ref->errFlag.as<int>(); P.O.stats = ref->stats.as<unsigned long long>();
   P.candBuf = ref->candBuf.as<Cand>(); P.candCap = ref->candCap; P.laneScratch = ref->laneScratch.as<u8>();
   { const char *env = getenv("T1K_NO_FAST"); P.noFast = (env && atoi(env) != 0) ? 1 : 0; }
+  { const char *env = getenv("T1K_TUNE"); P.tune = env ? atoi(env) : 0; }
   P.workCtr = ref->workCtr.as<unsigned int>();
   DevMem workList[2];
   std::vector<int32_t> hRet;

@@ -316,30 +316,29 @@ T1K_HDN T1K_NOINLINE inline bool diag_certified_hist(const AlleleView &T, int tp
 // is at most k: no excursion gains, the traceback stays on the diagonal.  G_d <= 1 iff between every two consecutive
 // "+1" rows of shift d lies at least one "-1" row.
 T1K_HDN T1K_NOINLINE inline bool diag_certified_interval(const AlleleView &T, int tpos, const ReadView &Q, int ppos, int n) {
-  int pos[24];
-  int mm = 0;
-  T1K_NOUNROLL
-  for (int k = 0; k < n; k += 32) {
-    u64 m = mm_chunk(T, tpos + k, Q, ppos + k, n - k);
-    T1K_NOUNROLL
-    while (m) { if (mm >= 24) return false; pos[mm++] = k + (ctz64(m) >> 1); m &= m - 1; }
-  }
   T1K_NOUNROLL
   for (int d = -BAND; d <= BAND; ++d) {
     if (d == 0) continue;
     const int lo = d < 0 ? -d : 0, hi = d > 0 ? n - 1 - d : n - 1;      // rows that have a column at this shift
-    int prevPlus = -1, both = 0;                                        // both: mismatch rows since prevPlus that stay mismatches
+    bool pending = false;                                               // a "+1" row with no "-1" row after it yet
     T1K_NOUNROLL
-    for (int q = 0; q < mm; ++q) {
-      const int r = pos[q];
-      if (r < lo || r > hi) continue;
-      if (!base_eq(T, tpos + r + d, Q, ppos + r)) { ++both; continue; }
-      if (prevPlus >= 0) {
-        // "-1" rows in (prevPlus, r) = shifted mismatches there minus the `both` rows; one is enough
-        if (r - prevPlus - 1 <= both) return false;
-        if (shifted_mm(T, tpos, Q, ppos, n, d, prevPlus + 1, r - 1, both) <= both) return false;
+    for (int r = lo; r <= hi; r += 32) {
+      const int cnt = hi - r + 1;
+      const u64 a = mm_chunk(T, tpos + r, Q, ppos + r, cnt);            // diagonal mismatches of rows r .. r+31
+      const u64 sft = mm_chunk(T, tpos + r + d, Q, ppos + r, cnt);      // mismatches of the same rows at shift d
+      u64 plus = a & ~sft;
+      const u64 minus = ~a & sft;
+      u64 done = 0;                                                     // bits at and below the last "+1" row handled
+      T1K_NOUNROLL
+      while (plus) {
+        const u64 b = plus & (~plus + 1);                               // lowest "+1" row
+        const u64 below = b - 1;
+        if (pending && (minus & below & ~done) == 0) return false;      // two "+1" rows with no "-1" row between: G_d >= 2
+        pending = true;
+        done = below | b;
+        plus &= plus - 1;
       }
-      prevPlus = r; both = 0;
+      if (minus & ~done) pending = false;
     }
   }
   return true;

@@ -24,6 +24,35 @@ __device__ __forceinline__ void cp_async4(void *smemDst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- TMA (bulk async copy engine), 1-D form: one lane moves a whole posting block global -> shared and the block's
+// mbarrier flips when the bytes have landed (cp.async.bulk + mbarrier complete_tx; source, destination and size are
+// multiples of 16 bytes)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smemDst, const void *gsrc, unsigned bytes, u64 *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smemDst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "T1K_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra T1K_MBAR_DONE;\n"
+      "bra T1K_MBAR_WAIT;\n"
+      "T1K_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+constexpr int RING_POSTINGS = 34;      // 32 postings of the block + the one that follows + 1 for the 16-byte alignment of the source
+constexpr int RING_BYTES = RING_POSTINGS * 8;
+
 struct ReadsDev {
   const u64 *planes;       // [(r*4 + plane) * RWORDS]; planes: fwd seq2, fwd n2, rc seq2, rc n2
   const u16 *len;
@@ -55,6 +84,7 @@ struct AssignParams {
   unsigned int *workCtr;
   int hitCap;              // hits per allele kept in shared memory
   int noFast;              // 1: every allele goes through the hit-list path (A/B switch, T1K_NO_FAST)
+  int tune;                // A/B switches (T1K_TUNE): bit 0 = no L2 prefetch of the next tile's posting block
 };
 
 // warp reductions on the redux unit (one instruction per 32-bit reduction; the kernel is instruction-footprint bound)
@@ -120,11 +150,11 @@ struct WarpSmem {
   u32 *H, *cnt, *cur, *end, *nxt, *stab;
   u8 *seedA, *act;
   u64 *seq, *nn;
-  Posting *ring;           // GATHER_DEPTH x 32 postings
-  u32 *ringX;              // GATHER_DEPTH: allele id of the posting that follows each ring block (0xffffffff: list ends)
+  Posting *ring;           // GATHER_DEPTH x RING_POSTINGS postings (TMA destination, 16-byte aligned stages)
+  u64 *bars;               // GATHER_DEPTH mbarriers, one per ring stage
 };
 __host__ __device__ inline size_t warp_smem_bytes(int hitCap) {
-  return (size_t)hitCap * 32 * 4 + 32 * 4 + 4 * 256 * 4 + 2 * 256 + 2 * RWORDS * 8 + GATHER_DEPTH * 32 * 8 + GATHER_DEPTH * 4;
+  return (size_t)hitCap * 32 * 4 + 32 * 4 + 4 * 256 * 4 + 2 * 256 + 2 * RWORDS * 8 + GATHER_DEPTH * RING_BYTES + GATHER_DEPTH * 8;
 }
 
 // returns whether the read holds an N
@@ -137,26 +167,20 @@ __device__ __forceinline__ bool load_planes(const AssignParams &P, u32 r, int st
   return __any_sync(FULL, nw != 0);
 }
 
-// stage i of the tile gather: the lane's posting of active seed i (or a sentinel) into the ring; always commits a group
+// stage i of the tile gather: one TMA copy brings the 32-posting block of active seed i (from the even posting at or
+// below its cursor, so that the source is 16-byte aligned) plus the posting that follows it into ring stage i mod DEPTH
 __device__ __forceinline__ void gather_issue(const RefView &R, const WarpSmem &W, int i, int nAct, int lane) {
-  if (i < nAct) {
+  if (i < nAct && lane == 0) {
     const int k = W.act[i];
-    const u32 c = W.cur[k] + lane;
-    Posting *dst = W.ring + (i & (GATHER_DEPTH - 1)) * 32 + lane;
-    const u32 e = W.end[k];
-    if (c < e) cp_async8(dst, R.post + c);
-    else { Posting none; none.idx = 0xffffffffu; none.off = 0; *dst = none; }
-    // the 33rd posting's allele id: tells where the list goes on without a dependent load after the block is consumed
-    if (lane == 0) {
-      u32 *dx = W.ringX + (i & (GATHER_DEPTH - 1));
-      if (c + 32 < e) cp_async4(dx, &R.post[c + 32].idx);
-      else *dx = 0xffffffffu;
-    }
+    const u32 c0 = W.cur[k] & ~1u;
+    const int st = i & (GATHER_DEPTH - 1);
+    mbar_expect_tx(W.bars + st, RING_BYTES);
+    tma_load_1d(W.ring + st * RING_POSTINGS, R.post + c0, RING_BYTES, W.bars + st);    // (the posting array is padded: reading past a list's end is harmless)
   }
-  cp_async_commit();
 }
 
-__device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W, Cand *cands, const LaneScratch &S, int lane) {
+// ringPhase: bit s = phase parity the warp waits for next on ring stage s (the mbarriers live as long as the warp)
+__device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W, Cand *cands, const LaneScratch &S, int lane, u32 &ringPhase) {
   const RefView &R = P.R;
   const int len = P.Q.len[r];
   const int weight = P.Q.weight[r];
@@ -278,12 +302,17 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
         T1K_NOUNROLL
         for (int i = 0; i < nAct; ++i) {
           gather_issue(R, W, i + GATHER_DEPTH - 1, nAct, lane);
-          cp_async_wait<GATHER_DEPTH - 1>();
+          const int st = i & (GATHER_DEPTH - 1);
+          mbar_wait(W.bars + st, (ringPhase >> st) & 1u);
+          ringPhase ^= 1u << st;
           const int k = W.act[i];
           const u32 a = W.seedA[k], e = W.end[k];
           u32 c = W.cur[k];
-          Posting p = W.ring[(i & (GATHER_DEPTH - 1)) * 32 + lane];
-          bool first = true;                 // p came through the ring (ringX knows what follows it)
+          const Posting *blk = W.ring + st * RING_POSTINGS + (c & 1u);     // blk[j] = posting c + j
+          Posting p; p.idx = 0xffffffffu; p.off = 0;
+          if (c + lane < e) p = blk[lane];
+          const u32 follow = c + 32 < e ? blk[32].idx : 0xffffffffu;        // allele id of the posting after the block (broadcast read)
+          bool first = true;                 // p came through the ring (`follow` knows what comes after it)
           T1K_NOUNROLL
           for (;;) {
             const bool in = p.idx < base + 32;
@@ -318,7 +347,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
             u32 nextIdx;                             // allele id of the first posting left in the list (all branches warp-uniform)
             if (consumed < 32) nextIdx = __shfl_sync(FULL, p.idx, consumed);
             else if (nc >= e) nextIdx = 0xffffffffu;
-            else if (first) nextIdx = __shfl_sync(FULL, lane == 0 ? W.ringX[i & (GATHER_DEPTH - 1)] : 0u, 0);
+            else if (first) nextIdx = follow;
             else nextIdx = 0;                        // unknown: look at the next block
             if (consumed == 32 && nc < e && nextIdx < base + 32) {   // the list continues inside this tile (repeated k-mer)
               c = nc; first = false;
@@ -327,12 +356,9 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
               continue;
             }
             if (lane == 0) { W.cur[k] = nc; W.nxt[k] = nextIdx; }
-            // the block the next tile will ask for: pull it into L2 now (2 x 128 B lines)
-            if (lane < 2 && nc + lane * 16 < e) prefetch_l2(R.post + nc + lane * 16);
             break;
           }
         }
-        cp_async_wait<0>();
         __syncwarp();
         // ---- lane-per-allele chaining + rescoring
         const int n = (int)W.cnt[lane];
@@ -564,20 +590,24 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_assign(AssignPar
   WarpSmem W;
   W.seq = (u64 *)sm; W.nn = W.seq + RWORDS;
   W.ring = (Posting *)(W.nn + RWORDS);
-  W.ringX = (u32 *)(W.ring + GATHER_DEPTH * 32);
-  W.H = W.ringX + GATHER_DEPTH;
+  W.bars = (u64 *)(W.ring + GATHER_DEPTH * RING_POSTINGS);
+  W.H = (u32 *)(W.bars + GATHER_DEPTH);
+  if (lane < GATHER_DEPTH) mbar_init(W.bars + lane, 1);
+  mbar_fence_init();
+  __syncwarp();
   W.cnt = W.H + (size_t)P.hitCap * 32;
   W.cur = W.cnt + 32; W.end = W.cur + 256; W.nxt = W.end + 256; W.stab = W.nxt + 256;
   W.seedA = (u8 *)(W.stab + 256); W.act = W.seedA + 256;
   LaneScratch S; S.base = P.laneScratch + (gwarp * 32 + lane) * (size_t)SCR_BYTES;
   Cand *cands = P.candBuf + gwarp * (size_t)P.candCap;
+  u32 ringPhase = 0;
   for (;;) {
     u32 w = 0;
     if (lane == 0) w = atomicAdd(P.workCtr, 1u);
     w = __shfl_sync(FULL, w, 0);
     if (w >= P.Q.nWork) break;
     const u32 r = P.Q.workList ? P.Q.workList[w] : w;
-    assign_one_read(P, r, W, cands, S, lane);
+    assign_one_read(P, r, W, cands, S, lane, ringPhase);
     __syncwarp();
   }
 }
