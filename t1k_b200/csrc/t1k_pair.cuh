@@ -249,6 +249,11 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
     int delta = 0;
     for (int b = 0; b < nA; b += 32) {
       const int i = b + lane;
+      {   // the records the next two rounds will touch: into L2 now (both lists are walked front to back)
+        const int ip = i + 64;
+        if (ip < nA) prefetch_l2(A + ip);
+        if (paired) { const int g = ip + delta; if (g >= 0 && g < nB) prefetch_l2(B + g); }
+      }
       int myDelta = 0x7fffffff;
       const bool runStart = i < nA && (i == 0 || A[i - 1].seqIdx != A[i].seqIdx);
       if (i < nA && !runStart) keys[i] = 0xffffffffu;        // later passes find the run starts without touching the records
