@@ -422,6 +422,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
       int i = b + lane;
       bool have = i < c1, cold = false, pre = false;
       Cand c;
+      if (i + 64 < c1) prefetch_l2(&cands[i + 64]);       // the candidate buffers live in HBM: next rounds' records into L2
       if (have) {
         c = cands[i];
         pre = (c.flags & CF_PRE) != 0;              // extension already known from the seeding stage
@@ -463,6 +464,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
     u64 bKey = ~0ull; int bIdx = 0x7fffffff;
     T1K_NOUNROLL
     for (int i = c0 + lane; i < c1; i += 32) {
+      if (i + 64 < c1) prefetch_l2(&cands[i + 64]);
       Cand c = cands[i];
       if ((c.flags & CF_SEP) || !(c.flags & CF_RET)) continue;
       bool before = pair_less(cand_key_pre(c), i, fKey, fIdx);
@@ -494,6 +496,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
         for (int b = c0; b < c1 || qn > 0; b += 32) {
           const int i = b + lane;
           bool cold = false;
+          if (i + 64 < c1) prefetch_l2(&cands[i + 64]);
           if (i < c1) {
             Cand c = cands[i];
             if (c.flags & CF_INCLUDE) {
@@ -537,6 +540,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
         bool inc = false;
         Cand c;
         u64 kPost = 0;
+        if (i + 64 < c1) prefetch_l2(&cands[i + 64]);
         if (i < c1) {
           c = cands[i];
           inc = (c.flags & CF_INCLUDE) != 0;
