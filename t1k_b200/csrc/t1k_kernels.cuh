@@ -10,7 +10,7 @@ namespace t1k {
 
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int GATHER_DEPTH = 4;      // stages of the posting-block ring of the tile gather (power of two)
+constexpr int GATHER_DEPTH = 8;      // stages of the posting-block ring of the tile gather (power of two)
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async8(void *smemDst, const void *gsrc) {
