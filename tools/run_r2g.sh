@@ -9,3 +9,4 @@ timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_d
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2g.csv python bench.py --pairs 200000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches_r2g.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_assign -c 1 -o gpurun_out/prof_assign_r2g -f python bench.py --pairs 50000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_r2g.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_pair -c 1 -o gpurun_out/prof_pair_r2g -f python bench.py --pairs 50000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_pair_r2g.log 2>&1
+T1K_TIMING=1 timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_r2g_timing.json 2> gpurun_out/bench_r2g_timing.err; grep "t1k timing" gpurun_out/bench_r2g_timing.err | grep -v "assign: \(launch\|input\|store\|tail\)" | tail -22
