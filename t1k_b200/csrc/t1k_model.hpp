@@ -7,11 +7,23 @@
 #include <string.h>
 
 #include <algorithm>
+#include <memory>
 #include <thread>
 #include <unordered_map>
 #include <vector>
 
 namespace t1k {
+
+// vector storage that is NOT zero-filled on resize: the big entry arrays are sized once and then filled (and first
+// touched) by several threads in parallel
+template <class T> struct NoInitAlloc : std::allocator<T> {
+  template <class U> struct rebind { typedef NoInitAlloc<U> other; };
+  NoInitAlloc() {}
+  template <class U> NoInitAlloc(const NoInitAlloc<U> &) {}
+  template <class U, class... A> void construct(U *p, A &&...a) {
+    if (sizeof...(A) == 0) ::new ((void *)p) U; else ::new ((void *)p) U(static_cast<A &&>(a)...);
+  }
+};
 
 struct HostEntry {   // == PairEntry / T1KReadAssignment
   int32_t alleleIdx, start, end;
@@ -23,7 +35,7 @@ struct HostEntry {   // == PairEntry / T1KReadAssignment
 // fragment order; start/end follow the reference's update rule verbatim (including end <- start, :893-894).
 struct ReadGroups {
   std::vector<int64_t> ptr{0};
-  std::vector<HostEntry> ent;
+  std::vector<HostEntry, NoInitAlloc<HostEntry> > ent;
   std::vector<int64_t> first;          // per group: index of the fragment that created it (orders merged shards)
   std::vector<uint64_t> hashes;        // per group: the allele-set hash it is filed under
   std::unordered_map<uint64_t, std::vector<int32_t> > byHash;
@@ -85,25 +97,39 @@ struct GroupShards {
   // rows: entries at ent + off[i], cnt[i] of them, hash[2*i] = allele-set hash, fragments f0 .. f0+m-1
   void add_chunk(const HostEntry *ent, const uint64_t *off, const uint32_t *cnt, const uint64_t *hash, uint32_t m, int64_t f0);
 
+  // partitions interleaved by the fragment that created each group; the entry copy (hundreds of MB) runs on the
+  // partitions' threads, every thread touching its own range of the destination first
   void gather(ReadGroups &out) const {
     struct Ref { int64_t first; int32_t t, g; };
     std::vector<Ref> order;
-    size_t nEnt = 0;
     for (int t = 0; t < threads(); ++t) {
       for (int32_t g = 0; g < part[t].size(); ++g) order.push_back(Ref{part[t].first[g], t, g});
-      nEnt += part[t].ent.size();
       out.assignedFragments += part[t].assignedFragments;
     }
     std::sort(order.begin(), order.end(), [](const Ref &a, const Ref &b) { return a.first < b.first; });
-    out.ent.reserve(out.ent.size() + nEnt);
-    for (size_t k = 0; k < order.size(); ++k) {
+    const size_t g0 = out.first.size(), nG = order.size();
+    out.ptr.resize(g0 + nG + 1); out.first.resize(g0 + nG); out.hashes.resize(g0 + nG);
+    for (size_t k = 0; k < nG; ++k) {
       const ReadGroups &P = part[order[k].t];
       const int32_t g = order[k].g;
-      out.ent.insert(out.ent.end(), P.ent.begin() + P.ptr[g], P.ent.begin() + P.ptr[g + 1]);
-      out.ptr.push_back((int64_t)out.ent.size());
-      out.first.push_back(P.first[g]);
-      out.hashes.push_back(P.hashes[g]);
+      out.ptr[g0 + k + 1] = out.ptr[g0 + k] + (P.ptr[g + 1] - P.ptr[g]);
+      out.first[g0 + k] = P.first[g];
+      out.hashes[g0 + k] = P.hashes[g];
     }
+    out.ent.resize((size_t)out.ptr[g0 + nG]);
+    const int T = nG < 1024 ? 1 : threads();
+    auto copy = [&](int t) {
+      for (size_t k = nG * t / T; k < nG * (t + 1) / T; ++k) {
+        const ReadGroups &P = part[order[k].t];
+        const int32_t g = order[k].g;
+        const int64_t n = P.ptr[g + 1] - P.ptr[g];
+        if (n) memcpy(out.ent.data() + out.ptr[g0 + k], P.ent.data() + P.ptr[g], (size_t)n * sizeof(HostEntry));
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(copy, t);
+    copy(0);
+    for (size_t k = 0; k < th.size(); ++k) th[k].join();
   }
 };
 
@@ -156,7 +182,16 @@ inline void serialize_groups(const ReadGroups &G, uint8_t *p) {
   memcpy(p, hdr, sizeof(hdr)); p += sizeof(hdr);
   memcpy(p, G.ptr.data(), G.ptr.size() * 8); p += G.ptr.size() * 8;
   if (G.size()) { memcpy(p, G.hashes.data(), (size_t)G.size() * 8); p += (size_t)G.size() * 8; memcpy(p, G.first.data(), (size_t)G.size() * 8); p += (size_t)G.size() * 8; }
-  if (!G.ent.empty()) memcpy(p, G.ent.data(), G.ent.size() * sizeof(HostEntry));
+  if (!G.ent.empty()) {
+    const size_t bytes = G.ent.size() * sizeof(HostEntry);
+    const int T = bytes < ((size_t)8 << 20) ? 1 : 8;
+    const uint8_t *src = (const uint8_t *)G.ent.data();
+    auto copy = [&](int t) { const size_t a = bytes * t / T, b = bytes * (t + 1) / T; memcpy(p + a, src + a, b - a); };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(copy, t);
+    copy(0);
+    for (size_t k = 0; k < th.size(); ++k) th[k].join();
+  }
 }
 inline void serialize_groups(const ReadGroups &G, std::vector<uint8_t> &blob) {
   blob.resize(serialized_group_bytes(G));
