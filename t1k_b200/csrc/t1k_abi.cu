@@ -410,7 +410,6 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   P.O.err = ref->errFlag.as<int>(); P.O.stats = ref->stats.as<unsigned long long>();
   P.candBuf = ref->candBuf.as<Cand>(); P.candCap = ref->candCap; P.laneScratch = ref->laneScratch.as<u8>();
   { const char *env = getenv("T1K_NO_FAST"); P.noFast = (env && atoi(env) != 0) ? 1 : 0; }
-  { const char *env = getenv("T1K_TUNE"); P.tune = env ? atoi(env) : 0; }
   P.workCtr = ref->workCtr.as<unsigned int>();
   DevMem workList[2];
   std::vector<int32_t> hRet;
@@ -1049,90 +1048,13 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   // While the device works on chunk c, helper threads prepare chunk c+1 and coalesce chunk c-1.
   u32 chunk = 1u << 18;
   if (const char *env = getenv("T1K_CHUNK_FRAGMENTS")) chunk = (u32)std::max(1l, atol(env));
-  struct Prep {
-    u32 f0 = 0, m = 0;
-    std::vector<u32> e1, e2, table;
-    std::vector<int32_t> w;
-    std::vector<uint64_t> off; std::vector<uint32_t> len; std::vector<char> bases;
-    std::vector<u8> hasN;
-    std::vector<const char *> rep;
-    bool tooLong = false;
-    double ms = 0;
-  } prep[2];
-  const int mates = reads2 ? 2 : 1;
-  // Unique read-ends of a chunk in two fork-join phases: (1) length, N flag and hash of every read-end (reads split
-  // across the threads), (2) one open-addressing table per hash partition (a thread owns a partition).  The unique
-  // index of a read-end = partition offset + rank inside the partition: deterministic for a given thread count, and
-  // nothing downstream depends on the order of the unique read-ends.
+  typedef ReadEndChunk Prep;
+  Prep prep[2];
   int prepThreads = std::max(1, std::min(8, (int)std::thread::hardware_concurrency() / ((prm->comm && prm->comm->world > 1) ? prm->comm->world : 1) / 2));
   if (const char *env = getenv("T1K_PREP_THREADS")) prepThreads = std::max(1, atoi(env));
   auto do_prep = [&, prepThreads](Prep &C, u32 f0, u32 m) {
     const double t = now_ms();
-    C.f0 = f0; C.m = m; C.tooLong = false;
-    C.e1.resize(m); if (reads2) C.e2.resize(m);
-    C.hasN.assign(m, 0);
-    const size_t nEnds = (size_t)m * mates;
-    const int T = nEnds < 4096 ? 1 : prepThreads;
-    std::vector<u64> hashes(nEnds);
-    std::vector<u32> lens(nEnds);
-    std::vector<u8> tooLong((size_t)T, 0);
-    auto end_ptr = [&](size_t k) { return ((k % mates) ? reads2 : reads1) + (size_t)(f0 + k / mates) * stride; };
-    run_threads(T, [&](int tIdx) {
-      const size_t k0 = nEnds * tIdx / T, k1 = nEnds * (tIdx + 1) / T;
-      for (size_t k = k0; k < k1; ++k) {
-        const char *s = end_ptr(k);
-        u32 L = 0; u64 h = 1469598103934665603ull; bool hasN = false;
-        while (L < stride && s[L]) { h = (h ^ (u8)s[L]) * 1099511628211ull; hasN |= s[L] == 'N'; ++L; }
-        if (L > T1K_MAX_READ_LEN) { tooLong[tIdx] = 1; L = T1K_MAX_READ_LEN; }
-        if (hasN) C.hasN[k / mates] = 1;          // both mates of a fragment belong to the same thread's range or write the same value
-        hashes[k] = h ^ (h >> 29); lens[k] = L;
-      }
-    });
-    for (int i = 0; i < T; ++i) if (tooLong[i]) C.tooLong = true;
-    struct Part { std::vector<u32> table, first, cnt; };      // first: read-end index of each unique, cnt: duplicates
-    std::vector<Part> parts((size_t)T);
-    std::vector<u32> local(nEnds);                             // rank of the read-end's unique inside its partition
-    run_threads(T, [&](int tIdx) {
-      Part &P = parts[tIdx];
-      size_t mine = 0;
-      for (size_t k = 0; k < nEnds; ++k) mine += (int)((hashes[k] >> 40) % (u64)T) == tIdx;
-      size_t tabSize = 16; while (tabSize < mine * 2) tabSize <<= 1;
-      P.table.assign(tabSize, 0xffffffffu);
-      for (size_t k = 0; k < nEnds; ++k) {
-        if ((int)((hashes[k] >> 40) % (u64)T) != tIdx) continue;
-        const char *s = end_ptr(k);
-        const u32 L = lens[k];
-        size_t slot = (size_t)hashes[k] & (tabSize - 1);
-        u32 u;
-        for (;;) {
-          u = P.table[slot];
-          if (u == 0xffffffffu) { u = (u32)P.first.size(); P.table[slot] = u; P.first.push_back((u32)k); P.cnt.push_back(0); break; }
-          if (lens[P.first[u]] == L && memcmp(end_ptr(P.first[u]), s, L) == 0) break;
-          slot = (slot + 1) & (tabSize - 1);
-        }
-        ++P.cnt[u];                                 // Genotyper.cpp:149,472: weight = number of duplicates
-        local[k] = u;
-      }
-    });
-    std::vector<u32> base((size_t)T + 1, 0);
-    for (int i = 0; i < T; ++i) base[i + 1] = base[i] + (u32)parts[i].first.size();
-    const size_t nU = base[T];
-    C.rep.resize(nU); C.len.resize(nU); C.w.resize(nU); C.off.resize(nU);
-    for (int i = 0; i < T; ++i)
-      for (size_t u = 0; u < parts[i].first.size(); ++u) {
-        const size_t k = parts[i].first[u];
-        C.rep[base[i] + u] = end_ptr(k); C.len[base[i] + u] = lens[k]; C.w[base[i] + u] = (int32_t)parts[i].cnt[u];
-      }
-    size_t tot = 0;
-    for (size_t k = 0; k < nU; ++k) { C.off[k] = tot; tot += C.len[k]; }
-    C.bases.resize(tot + 1);
-    run_threads(T, [&](int tIdx) {
-      for (size_t k = nEnds * tIdx / T; k < nEnds * (tIdx + 1) / T; ++k) {
-        const u32 u = base[(int)((hashes[k] >> 40) % (u64)T)] + local[k];
-        ((k % mates) ? C.e2 : C.e1)[k / mates] = u;
-      }
-      for (size_t k = nU * tIdx / T; k < nU * (tIdx + 1) / T; ++k) memcpy(C.bases.data() + C.off[k], C.rep[k], C.len[k]);
-    });
+    unique_read_ends(reads1, reads2, stride, f0, m, T1K_MAX_READ_LEN, prepThreads, C);
     C.ms = now_ms() - t;
   };
   CK(cudaMemsetAsync(ref->covDiff.p, 0, ref->paddedBases * 4, ref->stream));

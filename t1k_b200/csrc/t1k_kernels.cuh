@@ -13,17 +13,6 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int GATHER_DEPTH = 8;      // stages of the posting-block ring of the tile gather (power of two)
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void cp_async8(void *smemDst, const void *gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *smemDst, const void *gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // ---- TMA (bulk async copy engine), 1-D form: one lane moves a whole posting block global -> shared and the block's
 // mbarrier flips when the bytes have landed (cp.async.bulk + mbarrier complete_tx; source, destination and size are
 // multiples of 16 bytes)
@@ -84,7 +73,6 @@ struct AssignParams {
   unsigned int *workCtr;
   int hitCap;              // hits per allele kept in shared memory
   int noFast;              // 1: every allele goes through the hit-list path (A/B switch, T1K_NO_FAST)
-  int tune;                // A/B switches (T1K_TUNE): bit 0 = no L2 prefetch of the next tile's posting block
 };
 
 // warp reductions on the redux unit (one instruction per 32-bit reduction; the kernel is instruction-footprint bound)
@@ -143,9 +131,9 @@ __global__ void k_pack_reads(const char *bases, const u64 *off, const u32 *len, 
 
 // ---------------------------------------------------------------------------------------------------
 // One warp = one read-end at a time (dynamic work queue).  Shared memory per warp:
+//   read planes (2 x RWORDS words), posting ring (GATHER_DEPTH x 272 B, TMA destination) + one mbarrier per stage,
 //   H[hitCap][32]  encoded hits of the current allele tile, lane-interleaved (bank = lane)
-//   cnt[32], seedA[256], act[256], cur[256], end[256], nxt[256], stab[256] (seed table of diag_fast),
-//   read planes (2 x RWORDS words)
+//   cnt[32], cur[256], end[256], nxt[256], stab[256] (seed table of diag_fast), seedA[256], act[256]
 struct WarpSmem {
   u32 *H, *cnt, *cur, *end, *nxt, *stab;
   u8 *seedA, *act;

@@ -316,6 +316,93 @@ inline void transpose_csr(const int64_t *rowPtr, int32_t nRows, ColOf colOf, int
   (void)k0;
 }
 
+// ---- unique read-ends of a chunk of fragments (the de-duplication of Genotyper.cpp:450-454: only the grouping matters)
+// in two fork-join phases: (1) length, N flag and hash of every read-end (reads split across the threads), (2) one
+// open-addressing table per hash partition (a thread owns a partition).  The unique index of a read-end = partition
+// offset + rank inside the partition: deterministic for a given thread count, and nothing downstream depends on the
+// order of the unique read-ends.  reads1/reads2: fixed-stride, NUL-padded rows (reads2 may be NULL: single-end).
+struct ReadEndChunk {
+  uint32_t f0 = 0, m = 0;
+  std::vector<uint32_t> e1, e2;                 // per fragment: unique read-end of each mate
+  std::vector<int32_t> w;                       // per unique read-end: number of duplicates (Genotyper.cpp:149,472)
+  std::vector<uint64_t> off; std::vector<uint32_t> len; std::vector<char> bases;     // the unique read-ends, concatenated
+  std::vector<uint8_t> hasN;                    // per fragment: some mate holds an N
+  std::vector<const char *> rep;
+  bool tooLong = false;
+  double ms = 0;
+};
+inline void unique_read_ends(const char *reads1, const char *reads2, uint32_t stride, uint32_t f0, uint32_t m, uint32_t maxLen, int threads,
+                             ReadEndChunk &C) {
+  typedef uint64_t u64; typedef uint32_t u32; typedef uint8_t u8;
+  const int mates = reads2 ? 2 : 1;
+  C.f0 = f0; C.m = m; C.tooLong = false;
+  C.e1.resize(m); if (reads2) C.e2.resize(m); else C.e2.clear();
+  C.hasN.assign(m, 0);
+  const size_t nEnds = (size_t)m * mates;
+  const int T = nEnds < 4096 ? 1 : std::max(1, threads);
+  std::vector<u64> hashes(nEnds);
+  std::vector<u32> lens(nEnds);
+  std::vector<u8> tooLong((size_t)T, 0);
+  auto end_ptr = [&](size_t k) { return ((k % mates) ? reads2 : reads1) + (size_t)(f0 + k / mates) * stride; };
+  run_threads(T, [&](int tIdx) {
+    // whole fragments per thread, so that a fragment's N flag has one writer
+    const size_t k0 = (size_t)m * tIdx / T * mates, k1 = (size_t)m * (tIdx + 1) / T * mates;
+    for (size_t k = k0; k < k1; ++k) {
+      const char *s = end_ptr(k);
+      u32 L = 0; u64 h = 1469598103934665603ull; bool hasN = false;
+      while (L < stride && s[L]) { h = (h ^ (u8)s[L]) * 1099511628211ull; hasN |= s[L] == 'N'; ++L; }
+      if (L > maxLen) { tooLong[tIdx] = 1; L = maxLen; }
+      if (hasN) C.hasN[k / mates] = 1;
+      hashes[k] = h ^ (h >> 29); lens[k] = L;
+    }
+  });
+  for (int i = 0; i < T; ++i) if (tooLong[i]) C.tooLong = true;
+  struct Part { std::vector<u32> table, first, cnt; };      // first: read-end index of each unique, cnt: duplicates
+  std::vector<Part> parts((size_t)T);
+  std::vector<u32> local(nEnds);                             // rank of the read-end's unique inside its partition
+  run_threads(T, [&](int tIdx) {
+    Part &P = parts[tIdx];
+    size_t mine = 0;
+    for (size_t k = 0; k < nEnds; ++k) mine += (int)((hashes[k] >> 40) % (u64)T) == tIdx;
+    size_t tabSize = 16; while (tabSize < mine * 2) tabSize <<= 1;
+    P.table.assign(tabSize, 0xffffffffu);
+    for (size_t k = 0; k < nEnds; ++k) {
+      if ((int)((hashes[k] >> 40) % (u64)T) != tIdx) continue;
+      const char *s = end_ptr(k);
+      const u32 L = lens[k];
+      size_t slot = (size_t)hashes[k] & (tabSize - 1);
+      u32 u;
+      for (;;) {
+        u = P.table[slot];
+        if (u == 0xffffffffu) { u = (u32)P.first.size(); P.table[slot] = u; P.first.push_back((u32)k); P.cnt.push_back(0); break; }
+        if (lens[P.first[u]] == L && memcmp(end_ptr(P.first[u]), s, L) == 0) break;
+        slot = (slot + 1) & (tabSize - 1);
+      }
+      ++P.cnt[u];
+      local[k] = u;
+    }
+  });
+  std::vector<u32> base((size_t)T + 1, 0);
+  for (int i = 0; i < T; ++i) base[i + 1] = base[i] + (u32)parts[i].first.size();
+  const size_t nU = base[T];
+  C.rep.resize(nU); C.len.resize(nU); C.w.resize(nU); C.off.resize(nU);
+  for (int i = 0; i < T; ++i)
+    for (size_t u = 0; u < parts[i].first.size(); ++u) {
+      const size_t k = parts[i].first[u];
+      C.rep[base[i] + u] = end_ptr(k); C.len[base[i] + u] = lens[k]; C.w[base[i] + u] = (int32_t)parts[i].cnt[u];
+    }
+  size_t tot = 0;
+  for (size_t k = 0; k < nU; ++k) { C.off[k] = tot; tot += C.len[k]; }
+  C.bases.resize(tot + 1);
+  run_threads(T, [&](int tIdx) {
+    for (size_t k = nEnds * tIdx / T; k < nEnds * (tIdx + 1) / T; ++k) {
+      const u32 u = base[(int)((hashes[k] >> 40) % (u64)T)] + local[k];
+      ((k % mates) ? C.e2 : C.e1)[k / mates] = u;
+    }
+    for (size_t k = nU * tIdx / T; k < nU * (tIdx + 1) / T; ++k) memcpy(C.bases.data() + C.off[k], C.rep[k], C.len[k]);
+  });
+}
+
 struct EquivalenceClasses {
   std::vector<int32_t> ecPtr{0}, ecAlleles, alleleEc;
 

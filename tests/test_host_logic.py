@@ -227,6 +227,28 @@ def test_diagonal_certificates_are_sound_on_clustered_mismatches(emu):
     assert sum(v for m, v in certified_by_mm.items() if m >= 6) > 500      # the interval certificate is exercised
 
 
+def test_threaded_host_model_equals_single_thread():
+    """tests/host_model_check.cpp: sharded coalescing + gather, CSR transposition, equivalence classes, EM inputs and the
+    rank-table merge of t1k_model.hpp give, for every thread count, exactly the single-threaded result (and the sharded
+    coalescing gives the plain fragment-order one)."""
+    src = os.path.join(ROOT, "tests", "host_model_check.cpp")
+    so = os.path.join(ROOT, "tests", "_build", "libhostmodelcheck.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    deps = [src, os.path.join(ROOT, "t1k_b200", "csrc", "t1k_model.hpp")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-w", "-std=c++14", "-pthread", "-shared", "-fPIC", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.host_model_check.restype = C.c_int
+    lib.host_model_check.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    for seed, n_frag, n_alleles, n_sets in ((1, 4000, 300, 60), (2, 20000, 2000, 700), (3, 300, 50, 5), (4, 2, 10, 1)):
+        assert lib.host_model_check(seed, n_frag, n_alleles, n_sets) == 0, (seed, n_frag)
+    # the two-phase read-end de-duplication of the chunk pipeline (unique_read_ends)
+    lib.dedup_check.restype = C.c_int
+    lib.dedup_check.argtypes = [C.c_int, C.c_int, C.c_int]
+    for seed, n_frag, paired in ((1, 9000, 1), (2, 5000, 0), (3, 40, 1), (4, 1, 1)):
+        assert lib.dedup_check(seed, n_frag, paired) == 0, (seed, n_frag, paired)
+
+
 def test_parse_helpers():
     assert parse_exons("7 50 221 623 783", 3000) == [(50, 221), (623, 783)]
     assert parse_exons("", 100) == [(0, 99)]
