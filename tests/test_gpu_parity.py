@@ -205,6 +205,26 @@ def test_chunking_and_store_growth_do_not_change_results(workload, monkeypatch):
     assert np.array_equal(out["abundance"], base["abundance"])
 
 
+def test_fast_path_and_hit_list_path_agree_on_device(workload, monkeypatch):
+    """T1K_NO_FAST=1 sends every allele group through the hit-list path (chain_allele, extend_cand, full_align) instead of
+    the mismatch-mask fast path: records, coverage and the whole-flow outputs must be identical."""
+    wl = workload
+    uniq, w, e1, e2 = uniq_batch(wl["r1"], wl["r2"])
+    res = []
+    for no_fast in ("0", "1"):
+        monkeypatch.setenv("T1K_NO_FAST", no_fast)
+        ss = SeqSet(wl["ref"], wl["sim"], wl["relax"])
+        row, ret, rec = ss.AssignRead(uniq, w).fetch()
+        out = Genotyper(wl["ref"], wl["sim"], wl["relax"]).Genotype(wl["r1"], wl["r2"])
+        res.append((row, ret, rec_rows(rec), ss.GetBaseCoverage(), out))
+    a, b = res
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(a[3], b[3])
+    for k in ("equivalent_class", "missing_coverage", "fragment_assigned", "abundance"):
+        assert np.array_equal(a[4][k], b[4][k]), k
+    assert a[4]["em_iterations"] == b[4]["em_iterations"] and a[4]["n_assignments"] == b[4]["n_assignments"]
+
+
 def test_em_vs_oracle(workload):
     wl = workload
     R = O.genotype_pipeline(wl["orc"], wl["r1"], wl["r2"], wl["ref"].names, wl["sw"])
