@@ -204,7 +204,7 @@ struct T1KRef {
                              // a slow driver call, so it is not repeated per batch)
   bool covDirty = true;
   PinnedMem pinEntries[2];   // D2H staging of pairing rows (double-buffered by t1k_genotype's chunk pipeline)
-  PinnedMem pinSend, pinRecv; // read-group tables on their way to / from the peers
+  PinnedMem pinSend, pinRecv, pinRecv2; // read-group tables on their way to / from the peers
   ~T1KRef() { if (stream) cudaStreamDestroy(stream); }
 };
 
@@ -1151,7 +1151,25 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
       fragBase[r] = fb; fb += (int64_t)tr[1];
     }
     ReadGroups merged;
-    if (!merge_tables_parallel(tables, fragBase, shards.threads(), merged)) return fail(T1K_ERR_NCCL, "malformed read-group table from a peer");
+    const char *partEnv = getenv("T1K_MERGE_PARTITIONED");
+    if (partEnv && atoi(partEnv) != 0) {
+      // opt-in: every rank merges 1/world of the allele sets, the merged partitions are exchanged and interleaved
+      ReadGroups mine;
+      if (!merge_tables_partition(tables, fragBase, comm->rank, comm->world, shards.threads(), mine)) return fail(T1K_ERR_NCCL, "malformed read-group table from a peer");
+      int64_t assignedAll = 0;
+      for (int r = 0; r < comm->world; ++r) assignedAll += (int64_t)tables[r].assigned;
+      const size_t partBytes = serialized_group_bytes(mine);
+      CK(ref->pinSend.grow(partBytes, 0));         // the first exchange's send buffer is no longer needed (tables live in pinRecv)
+      serialize_groups(mine, ref->pinSend.as<uint8_t>());
+      uint64_t stride2 = 0;
+      std::vector<uint64_t> sizes2;
+      if (int rc = allgather_blobs(ref, comm, ref->pinSend.as<uint8_t>(), partBytes, ref->pinRecv2, stride2, sizes2)) return rc;
+      std::vector<GroupBlobView> parts((size_t)comm->world);
+      for (int r = 0; r < comm->world; ++r)
+        if (!parts[r].parse(ref->pinRecv2.as<uint8_t>() + (size_t)r * stride2, sizes2[r])) return fail(T1K_ERR_NCCL, "malformed merged partition from a peer");
+      if (!assemble_partitions(parts, shards.threads(), merged)) return fail(T1K_ERR_NCCL, "malformed merged partition from a peer");
+      merged.assignedFragments = assignedAll;
+    } else if (!merge_tables_parallel(tables, fragBase, shards.threads(), merged)) return fail(T1K_ERR_NCCL, "malformed read-group table from a peer");
     groups.ptr.swap(merged.ptr); groups.ent.swap(merged.ent); groups.byHash.swap(merged.byHash);
     groups.first.swap(merged.first); groups.hashes.swap(merged.hashes);
     groups.assignedFragments = merged.assignedFragments;

@@ -316,6 +316,63 @@ inline void transpose_csr(const int64_t *rowPtr, int32_t nRows, ColOf colOf, int
   (void)k0;
 }
 
+// ---- The same merge with the work divided over the ranks (opt-in, T1K_MERGE_PARTITIONED): rank r merges only the hash
+// partitions it owns (partition space = world x T; thread t of rank r takes partition r*T + t) from every rank's table,
+// the ranks exchange their merged partitions, and assemble_partitions() interleaves them by the creating fragment.
+// Every group is still merged by exactly one thread in rank order, so the result equals merge_tables_parallel's; the
+// per-rank merge work is 1/world of it.
+inline bool merge_tables_partition(const std::vector<GroupBlobView> &tables, const std::vector<int64_t> &fragBase, int rank, int world, int T,
+                                   ReadGroups &mine) {
+  GroupShards M(T);
+  T = M.threads();
+  const uint64_t P = (uint64_t)world * (uint64_t)T;
+  std::vector<char> ok((size_t)T, 1);
+  run_threads(T, [&](int t) {
+    ReadGroups &G = M.part[t];
+    const uint64_t own = (uint64_t)rank * (uint64_t)T + (uint64_t)t;
+    for (size_t r = 0; r < tables.size(); ++r) {
+      const GroupBlobView &V = tables[r];
+      for (uint64_t g = 0; g < V.nG; ++g) {
+        const uint64_t h = V.hash(g);
+        if ((h >> 17) % P != own) continue;
+        int64_t b, e;
+        if (!V.row(g, b, e)) { ok[t] = 0; return; }
+        G.add(V.entries(b), (uint32_t)(e - b), 0, &h, fragBase[r] + V.first_frag(g));
+      }
+    }
+  });
+  for (int t = 0; t < T; ++t) if (!ok[t]) return false;
+  M.gather(mine);
+  return true;
+}
+// parts[r] = rank r's merged partitions (`first` already global); out = all groups in first-appearance order
+inline bool assemble_partitions(const std::vector<GroupBlobView> &parts, int T, ReadGroups &out) {
+  struct Ref { int64_t first; uint32_t r; uint64_t g; };
+  std::vector<Ref> order;
+  for (size_t r = 0; r < parts.size(); ++r)
+    for (uint64_t g = 0; g < parts[r].nG; ++g) order.push_back(Ref{parts[r].first_frag(g), (uint32_t)r, g});
+  std::sort(order.begin(), order.end(), [](const Ref &a, const Ref &b) { return a.first < b.first; });
+  const size_t nG = order.size();
+  out.ptr.assign(nG + 1, 0); out.first.resize(nG); out.hashes.resize(nG);
+  for (size_t k = 0; k < nG; ++k) {
+    int64_t b, e;
+    if (!parts[order[k].r].row(order[k].g, b, e)) return false;
+    out.ptr[k + 1] = out.ptr[k] + (e - b);
+    out.first[k] = order[k].first;
+    out.hashes[k] = parts[order[k].r].hash(order[k].g);
+  }
+  out.ent.resize((size_t)out.ptr[nG]);
+  if (T < 1 || nG < 1024) T = 1;
+  run_threads(T, [&](int t) {
+    for (size_t k = nG * t / T; k < nG * (t + 1) / T; ++k) {
+      int64_t b, e;
+      parts[order[k].r].row(order[k].g, b, e);
+      if (e > b) memcpy(out.ent.data() + out.ptr[k], parts[order[k].r].entries(b), (size_t)(e - b) * sizeof(HostEntry));
+    }
+  });
+  return true;
+}
+
 // ---- unique read-ends of a chunk of fragments (the de-duplication of Genotyper.cpp:450-454: only the grouping matters)
 // in two fork-join phases: (1) length, N flag and hash of every read-end (reads split across the threads), (2) one
 // open-addressing table per hash partition (a thread owns a partition).  The unique index of a read-end = partition

@@ -169,6 +169,40 @@ extern "C" int host_model_check(int seed, int nFrag, int nAlleles, int nSets) {
       if (!merge_tables_parallel(views, fragBase, T, m)) return 8;
       if (!same_groups(m, m1)) return 9;
     }
+    // ---- rank-partitioned merge (T1K_MERGE_PARTITIONED): three "ranks", every rank merges its hash partitions, the
+    // partitions are serialised, exchanged and interleaved; equal to the full merge of the same three tables
+    {
+      const int W = 3;
+      const int cut[W + 1] = {0, nFrag / 4, nFrag / 4 + nFrag / 3, nFrag};
+      ReadGroups shard[W];
+      std::vector<std::vector<uint8_t> > b3(W);
+      std::vector<GroupBlobView> v3(W);
+      std::vector<int64_t> fb3(W);
+      for (int r = 0; r < W; ++r) {
+        GroupShards S(2);
+        S.add_chunk(ent.data(), off.data() + cut[r], cnt.data() + cut[r], hash.data() + 2 * (size_t)cut[r], (uint32_t)(cut[r + 1] - cut[r]), 0);
+        S.gather(shard[r]);
+        serialize_groups(shard[r], b3[r]);
+        if (!v3[r].parse(b3[r].data(), b3[r].size())) return 12;
+        fb3[r] = cut[r];
+      }
+      ReadGroups full;
+      if (!merge_tables_parallel(v3, fb3, 4, full)) return 13;
+      for (int T = 1; T <= 5; T += 2) {
+        std::vector<std::vector<uint8_t> > pb(W);
+        std::vector<GroupBlobView> pv(W);
+        for (int r = 0; r < W; ++r) {
+          ReadGroups mine;
+          if (!merge_tables_partition(v3, fb3, r, W, T, mine)) return 14;
+          serialize_groups(mine, pb[r]);
+          if (!pv[r].parse(pb[r].data(), pb[r].size())) return 15;
+        }
+        ReadGroups asm_;
+        if (!assemble_partitions(pv, T, asm_)) return 16;
+        asm_.assignedFragments = full.assignedFragments;
+        if (!same_groups(asm_, full)) return 17;
+      }
+    }
     // the merged table has the single-process groups in the single-process order (float32 sums may differ in the last
     // bit: per-rank partial sums), so compare structure and allele ids
     if (!same_vec(m1.ptr, ref.ptr) || m1.assignedFragments != ref.assignedFragments) return 10;
