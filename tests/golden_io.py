@@ -42,3 +42,14 @@ def uniq_overlaps(g, i):
 
 def frag_rows(g, i):
     return g["frag_as"][g["frag_ptr"][i]:g["frag_ptr"][i + 1]]
+
+
+def load_hla_scale():
+    """Outputs of the unmodified reference on the bench configuration (tests/golden/make_golden_hla.py); the 30,000-allele
+    reference itself is regenerated from bench.make_workload(n_pairs, seed)."""
+    z = np.load(os.path.join(GOLDEN, "hla_scale", "reference_outputs.npz"))
+    g = {k: z[k] for k in z.files}
+    g["uniq_seq"] = [s.encode() if isinstance(s, str) else bytes(s) for s in g["uniq_seq"].tolist()]
+    for k in ("n_pairs", "seed", "iters", "aligned", "n_groups", "n_ec"):
+        g[k] = int(g[k])
+    return g

@@ -225,6 +225,27 @@ def test_fast_path_and_hit_list_path_agree_on_device(workload, monkeypatch):
     assert a[4]["em_iterations"] == b[4]["em_iterations"] and a[4]["n_assignments"] == b[4]["n_assignments"]
 
 
+def test_bench_configuration_against_the_reference_golden():
+    """The device path on the bench configuration (30,000 alleles, > 1000 cut active) against the UNMODIFIED reference's
+    records (tests/golden/hla_scale) and whole-flow summary."""
+    import bench
+    g = G.load_hla_scale()
+    recs, ref, r1, r2 = bench.make_workload(g["n_pairs"], g["seed"])
+    ss = SeqSet(ref, 0.97, False)
+    row, ret, rec = ss.AssignRead(g["uniq_seq"], g["uniq_weight"]).fetch()
+    rows = rec_rows(rec)
+    for i in range(len(g["uniq_seq"])):
+        want = g["uniq_ov"][g["uniq_ptr"][i]:g["uniq_ptr"][i + 1]]
+        assert np.array_equal(rows[int(row[i]):int(row[i + 1])], want), "read-end %d" % i
+    out = Genotyper(ref, 0.97, False).Genotype(r1, r2)
+    assert out["assigned_fragments"] == g["aligned"]
+    assert out["n_groups"] == g["n_groups"] and out["n_ec"] == g["n_ec"]
+    assert out["em_iterations"] == g["iters"]
+    q = g["q"]
+    assert np.array_equal(out["equivalent_class"], q[:, 0].astype(np.int32))
+    assert np.array_equal(out["abundance"], q[:, 1])
+
+
 def test_em_vs_oracle(workload):
     wl = workload
     R = O.genotype_pipeline(wl["orc"], wl["r1"], wl["r2"], wl["ref"].names, wl["sw"])

@@ -146,6 +146,63 @@ def test_diagonal_fast_path_equals_general_path(emu):
         assert np.array_equal(covs[0], covs[1]), name
 
 
+def test_lane_code_matches_oracle_on_the_bench_workload(emu):
+    """The bench configuration itself (30,000 HLA-RNA-like alleles x 1,100 bp, 150 bp reads, -s 0.97; ~3.5 k records per
+    read-end, the > 1000 cut active): AssignRead records and coverage of the product's lane code == the oracle's."""
+    import bench
+    recs, ref, r1, r2 = bench.make_workload(20, 321)
+    kept, w = O.collapse_reference(recs)
+    orc = O.Oracle(kept, 0.97, False, O.seq_weights(kept, w))
+    bases, off, ptr, se = ref.packed()
+    E = emu.emu_create(ref.n, bases, O._p(off), O._p(ptr), O._p(se), 0.97, 0)
+    buf = np.zeros(1 << 16, dtype=O.OVERLAP_DT)
+    n_rec = 0
+    for i, s in enumerate([r.tobytes() for r in r1] + [r.tobytes() for r in r2]):
+        err = C.c_int32(0)
+        n = emu.emu_assign(E, s, 2, O._p(buf), len(buf), C.byref(err))
+        assert err.value == 0
+        oret, ov = orc.assign(s, 2)
+        assert n == oret, i
+        got = np.stack([buf[k][:max(n, 0)] for k in O.OVERLAP_DT.names], axis=1) if n > 0 else np.zeros((0, 10), np.int32)
+        want = np.stack([ov[k] for k in O.OVERLAP_DT.names], axis=1) if len(ov) else np.zeros((0, 10), np.int32)
+        assert np.array_equal(got, want), i
+        n_rec += max(n, 0)
+    assert n_rec > 50000
+    cov = []
+    for a in range(ref.n):
+        out = np.zeros(len(ref.seqs[a]), dtype=np.int32)
+        emu.emu_coverage(E, a, O._p(out))
+        cov.append(out)
+    assert np.array_equal(np.concatenate(cov), np.concatenate([orc.coverage(k) for k in range(ref.n)]))
+    emu.emu_destroy(E)
+
+
+def test_oracle_and_lane_code_match_the_reference_on_the_bench_configuration(emu):
+    """tests/golden/hla_scale: AssignRead records of the UNMODIFIED reference on the 30,000-allele bench reference (the > 1000
+    cut of SeqSet.hpp:2290-2298 is active on every read-end).  The oracle and the product's lane code reproduce them."""
+    import bench
+    g = G.load_hla_scale()
+    recs, ref, r1, r2 = bench.make_workload(g["n_pairs"], g["seed"])
+    assert np.array_equal(r1, g["reads1"]) and np.array_equal(r2, g["reads2"])       # the generator still makes the golden's inputs
+    kept, w = O.collapse_reference(recs)
+    orc = O.Oracle(kept, 0.97, False, O.seq_weights(kept, w))
+    bases, off, ptr, se = ref.packed()
+    E = emu.emu_create(ref.n, bases, O._p(off), O._p(ptr), O._p(se), 0.97, 0)
+    buf = np.zeros(1 << 16, dtype=O.OVERLAP_DT)
+    assert len(g["uniq_seq"]) > 20 and g["uniq_ptr"][-1] > 100000
+    for i, s in enumerate(g["uniq_seq"]):
+        want = g["uniq_ov"][g["uniq_ptr"][i]:g["uniq_ptr"][i + 1]]
+        oret, ov = orc.assign(s, int(g["uniq_weight"][i]))
+        got_o = np.stack([ov[k] for k in O.OVERLAP_DT.names], axis=1) if len(ov) else np.zeros((0, 10), np.int32)
+        assert np.array_equal(got_o, want), ("oracle", i)
+        err = C.c_int32(0)
+        n = emu.emu_assign(E, s, int(g["uniq_weight"][i]), O._p(buf), len(buf), C.byref(err))
+        assert err.value == 0
+        got = np.stack([buf[k][:max(n, 0)] for k in O.OVERLAP_DT.names], axis=1) if n > 0 else np.zeros((0, 10), np.int32)
+        assert np.array_equal(got, want), ("lane code", i)
+    emu.emu_destroy(E)
+
+
 def test_banded_dp_and_diagonal_certificate(emu):
     """dp_align == AlignAlgo::GlobalAlignment op for op (oracle) on random pairs incl. N, indels and band edges;
     whenever the diagonal certificate fires, the reference alignment is the pure diagonal."""
