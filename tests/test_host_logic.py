@@ -201,6 +201,13 @@ def test_oracle_and_lane_code_match_the_reference_on_the_bench_configuration(emu
         got = np.stack([buf[k][:max(n, 0)] for k in O.OVERLAP_DT.names], axis=1) if n > 0 else np.zeros((0, 10), np.int32)
         assert np.array_equal(got, want), ("lane code", i)
     emu.emu_destroy(E)
+    # pairing, coalescing, equivalence classes and EM of the oracle against the reference's whole-flow outputs
+    orc.coverage_reset()
+    R = O.genotype_pipeline(orc, r1, r2, ref.names, O.seq_weights(kept, w))
+    assert R["assigned"] == g["aligned"] and len(R["groups"]) == g["n_groups"] and len(R["ecs"]) == g["n_ec"]
+    assert R["iters"] == g["iters"]
+    assert np.array_equal(R["allele_ec"], g["q"][:, 0].astype(np.int32))
+    assert np.array_equal(R["abundance"], g["q"][:, 1])
 
 
 def test_banded_dp_and_diagonal_certificate(emu):
