@@ -13,9 +13,12 @@
 
 namespace {
 
-const int K = 11;            // Genotyper.cpp:207
+// k-mer length and required hit length of the oracle in use.  The genotyper fixes them (Genotyper.cpp:207, SeqSet.hpp:764);
+// the candidate filter of fastq-extractor derives its own (FastqExtractor.cpp:381-418).  Single-threaded test code: every
+// extern entry point loads them from its oracle object before doing anything.
+int K = 11;                  // Genotyper.cpp:207
 const int RADIUS = 10;       // SeqSet.hpp:763
-const int HIT_LEN_REQ = 31;  // SeqSet.hpp:764
+int HIT_LEN_REQ = 31;        // SeqSet.hpp:764
 const int BAND = 5;          // AlignAlgo.hpp:215
 
 // nucToNum & 3 (Genotyper.cpp:37-40, KmerCode.hpp:99): A0 C1 G2 T3, everything else -1&3 = 3
@@ -57,10 +60,20 @@ bool ov_less(const Ov &a, const Ov &b) {
 
 struct T1KOracle {
   std::vector<Allele> al;
-  std::vector<uint32_t> kstart;   // 4^K + 1
+  std::vector<uint32_t> kstart;   // 4^K + 1 (k <= 12); longer k-mers: `codes` (sorted, distinct) + cstart
+  std::vector<uint32_t> codes, cstart;
   std::vector<Posting> post;      // per k-mer: (allele asc, offset asc) = insertion order of KmerIndex.hpp:58-71
   double sim;
   bool relax;
+  int k, hitLenReq;
+  // posting range of one k-mer (KmerIndex::Search, KmerIndex.hpp:93-105)
+  void range(uint32_t code, uint32_t &lo, uint32_t &hi) const {
+    if (!kstart.empty()) { lo = kstart[code]; hi = kstart[code + 1]; return; }
+    std::vector<uint32_t>::const_iterator it = std::lower_bound(codes.begin(), codes.end(), code);
+    if (it == codes.end() || *it != code) { lo = hi = 0; return; }
+    const size_t i = (size_t)(it - codes.begin());
+    lo = cstart[i]; hi = cstart[i + 1];
+  }
 };
 
 namespace {
@@ -72,7 +85,7 @@ struct KStream {
   KStream() : code(0), bad(-1) {}
   void push(char c) {
     if (bad != -1) ++bad;
-    code = ((code << 2) & ((1u << (2 * K)) - 1)) | (uint32_t)code2(c);
+    code = ((code << 2) & (uint32_t)((1ull << (2 * K)) - 1)) | (uint32_t)code2(c);
     if (c == 'N') bad = 0;
     if (bad >= K) bad = -1;
   }
@@ -80,7 +93,8 @@ struct KStream {
 };
 
 // KmerIndex::BuildIndexFromRead, KmerIndex.hpp:107-130 (incl. the i==kl quirk, Q1)
-void index_allele(std::vector<std::vector<Posting> > &lists, const std::string &s, int id) {
+struct Triple { uint32_t code; Posting p; };
+void index_allele(std::vector<Triple> &lists, const std::string &s, int id) {
   int len = (int)s.size();
   if (len < K) return;
   KStream ks; uint32_t prev = 0;
@@ -89,8 +103,8 @@ void index_allele(std::vector<std::vector<Posting> > &lists, const std::string &
   for (; i < len; ++i) {
     ks.push(s[i]);
     if (ks.valid() && (i == K || ks.code != prev)) {
-      Posting p; p.idx = (uint32_t)id; p.off = (uint32_t)(i - K + 1);
-      lists[ks.code].push_back(p);
+      Triple t; t.code = ks.code; t.p.idx = (uint32_t)id; t.p.off = (uint32_t)(i - K + 1);
+      lists.push_back(t);
     }
     prev = ks.code;
   }
@@ -189,7 +203,7 @@ void collect_hits(const T1KOracle &o, const std::string &r, int strand, uint32_t
     ks.push(r[i]);
     if (i == K - 1 || prev != ks.code) {
       uint32_t lo = 0, hi = 0;
-      if (ks.valid()) { lo = o.kstart[ks.code]; hi = o.kstart[ks.code + 1]; }
+      if (ks.valid()) o.range(ks.code, lo, hi);
       int size = (int)(hi - lo);
       if (size >= 100 && i != K - 1 && i != len - 1 && skip < K / 2) { ++skip; continue; }
       skip = 0;
@@ -636,12 +650,32 @@ double assignment_weight(const T1KOracle &o, double similarity, bool hasN) {
 
 extern "C" {
 
+static void build_index(T1KOracle *o, std::vector<Triple> &lists) {
+  // stable by code => inside a k-mer the postings keep their insertion order (allele asc, offset asc)
+  std::stable_sort(lists.begin(), lists.end(), [](const Triple &a, const Triple &b) { return a.code < b.code; });
+  o->post.resize(lists.size());
+  for (size_t i = 0; i < lists.size(); ++i) o->post[i] = lists[i].p;
+  o->kstart.clear(); o->codes.clear(); o->cstart.clear();
+  if (K <= 12) {
+    o->kstart.assign(((size_t)1 << (2 * K)) + 1, 0);
+    for (size_t i = 0; i < lists.size(); ++i) ++o->kstart[lists[i].code + 1];
+    for (size_t c = 0; c + 1 < o->kstart.size(); ++c) o->kstart[c + 1] += o->kstart[c];
+  } else {
+    for (size_t i = 0; i < lists.size(); ++i)
+      if (i == 0 || lists[i].code != lists[i - 1].code) { o->codes.push_back(lists[i].code); o->cstart.push_back((uint32_t)i); }
+    o->cstart.push_back((uint32_t)lists.size());
+  }
+}
+static inline void use(const T1KOracle *o) { K = o->k; HIT_LEN_REQ = o->hitLenReq; }
+
 T1KOracle *t1ko_create(int32_t n, const char *bases, const int64_t *off, const int32_t *exonPtr, const int32_t *exonSE,
                        const int32_t *seqWeight, double similarity, int32_t relaxIntron) {
   T1KOracle *o = new T1KOracle;
   o->sim = similarity; o->relax = relaxIntron != 0;
+  o->k = 11; o->hitLenReq = 31;
+  use(o);
   o->al.resize(n);
-  std::vector<std::vector<Posting> > lists((size_t)1 << (2 * K));
+  std::vector<Triple> lists;
   for (int i = 0; i < n; ++i) {
     Allele &a = o->al[i];
     a.seq.assign(bases + off[i], bases + off[i + 1]);
@@ -660,11 +694,74 @@ T1KOracle *t1ko_create(int32_t n, const char *bases, const int64_t *off, const i
     a.weight = seqWeight ? seqWeight[i] : 1;
     index_allele(lists, a.seq, i);
   }
-  o->kstart.assign(((size_t)1 << (2 * K)) + 1, 0);
-  for (size_t c = 0; c < lists.size(); ++c) o->kstart[c + 1] = o->kstart[c] + (uint32_t)lists[c].size();
-  o->post.resize(o->kstart.back());
-  for (size_t c = 0; c < lists.size(); ++c) std::copy(lists[c].begin(), lists[c].end(), o->post.begin() + o->kstart[c]);
+  build_index(o, lists);
   return o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The candidate filter of fastq-extractor.  Set-up as FastqExtractor.cpp:272-273,381-418:
+// k = max(9, SeqSet::InferKmerLength) over ALL reference sequences as loaded by InputRefFa (no collapsing of identical
+// sequences, SeqSet.hpp:872-904), hitLenRequired = max(27 paired / 23 single, mean read length / 5, k).
+int32_t t1ko_infer_kmer_length(int64_t totalLength) {   // SeqSet::InferKmerLength, SeqSet.hpp:2830-2845
+  int ret = 0;
+  while (totalLength) { ++ret; totalLength /= 4; }
+  return ret + 1;
+}
+T1KOracle *t1ko_filter_create(int32_t n, const char *bases, const int64_t *off, int32_t k, int32_t hitLenRequired, double similarity) {
+  if (k < 1 || k > 15) return NULL;
+  T1KOracle *o = new T1KOracle;
+  o->sim = similarity; o->relax = false;
+  o->k = k; o->hitLenReq = hitLenRequired;
+  use(o);
+  o->al.resize(n);
+  std::vector<Triple> lists;
+  for (int i = 0; i < n; ++i) {
+    Allele &a = o->al[i];
+    a.seq.assign(bases + off[i], bases + off[i + 1]);
+    a.effLen = (int)a.seq.size(); a.weight = 1;
+    index_allele(lists, a.seq, i);
+  }
+  build_index(o, lists);
+  return o;
+}
+// IsLowComplexity, FastqExtractor.cpp:89-112
+int32_t t1ko_is_low_complexity(const char *seq) {
+  int cnt[5] = {0, 0, 0, 0, 0};
+  int i;
+  for (i = 0; seq[i]; ++i) { if (seq[i] == 'N') ++cnt[4]; else ++cnt[code2(seq[i])]; }
+  if (cnt[0] >= i / 2 || cnt[1] >= i / 2 || cnt[2] >= i / 2 || cnt[3] >= i / 2 || cnt[4] >= i / 10) return 1;
+  int lowCnt = 0;
+  for (i = 0; i < 4; ++i) if (cnt[i] <= 2) ++lowCnt;
+  return lowCnt >= 2;
+}
+// SeqSet::HasHitInSet, SeqSet.hpp:1915-1990
+int32_t t1ko_has_hit_in_set(T1KOracle *o, const char *readC) {
+  use(o);
+  const std::string read(readC);
+  const int len = (int)read.size();
+  if (len < K) return 0;
+  std::vector<Hit> hits;
+  uint32_t prev = 0;
+  collect_hits(*o, read, 1, prev, hits);
+  collect_hits(*o, revcomp(read), -1, prev, hits);
+  if (hits.empty()) return 0;
+  // buckets per (strand tag, sequence) in arrival order; the first largest one, strand -1 first (:1929-1957)
+  std::map<std::pair<int, uint32_t>, std::vector<Hit> > buckets;
+  for (size_t i = 0; i < hits.size(); ++i) buckets[std::make_pair(hits[i].strand == 1 ? 1 : 0, hits[i].idx)].push_back(hits[i]);
+  int mx = -1;
+  const std::vector<Hit> *best = NULL;
+  for (std::map<std::pair<int, uint32_t>, std::vector<Hit> >::const_iterator it = buckets.begin(); it != buckets.end(); ++it)
+    if ((int)it->second.size() > mx) { mx = (int)it->second.size(); best = &it->second; }     // map order = (tag, idx) ascending
+  if (K * mx < HIT_LEN_REQ) return 0;
+  std::vector<Ov> ovs;
+  chain_group(best->data(), (int)best->size(), ovs);
+  const int mismatchThreshold = (int)(len * (1 - o->sim)) * K;
+  for (size_t i = 0; i < ovs.size(); ++i) if (len - ovs[i].matchCnt / 2 <= mismatchThreshold) return 1;
+  return 0;
+}
+// IsGoodCandidate, FastqExtractor.cpp:114-119
+int32_t t1ko_is_good_candidate(T1KOracle *o, const char *read) {
+  return !t1ko_is_low_complexity(read) && t1ko_has_hit_in_set(o, read);
 }
 
 void t1ko_destroy(T1KOracle *o) { delete o; }
@@ -678,6 +775,7 @@ int32_t t1ko_global_alignment(const char *t, int32_t lent, const char *p, int32_
 }
 
 int32_t t1ko_assign_read(T1KOracle *o, const char *read, int32_t weight, OracleOverlap *out, int32_t cap) {
+  use(o);
   std::vector<Ov> a;
   int ret = assign_read(*o, std::string(read), weight, a);
   for (size_t i = 0; i < a.size() && (int)i < cap; ++i) {
@@ -716,6 +814,7 @@ int32_t t1ko_missing_coverage(T1KOracle *o, int32_t allele) {
 // ReadAssignmentToFragmentAssignment + Genotyper::SetReadAssignments (Genotyper.hpp:778-832)
 int32_t t1ko_fragment_assign(T1KOracle *o, const OracleOverlap *p1, int32_t n1, const OracleOverlap *p2, int32_t n2,
                              int32_t hasN, int32_t maxAssign, OracleAssignment *out, int32_t cap) {
+  use(o);
   std::vector<Ov> a(n1), b;
   for (int i = 0; i < n1; ++i) a[i] = from_pod(p1[i]);
   if (p2) { b.resize(n2); for (int i = 0; i < n2; ++i) b[i] = from_pod(p2[i]); }

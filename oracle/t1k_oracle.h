@@ -37,6 +37,14 @@ T1KOracle *t1ko_create(int32_t nAlleles, const char *bases, const int64_t *off, 
                        const int32_t *exonSE, const int32_t *seqWeight, double similarity, int32_t relaxIntron);
 void t1ko_destroy(T1KOracle *o);
 
+/* ---- candidate filter of fastq-extractor: FastqExtractor.cpp:89-119, SeqSet::HasHitInSet SeqSet.hpp:1915-1990.
+ * The reference set is loaded as InputRefFa does (every record, no collapsing); k and hitLenRequired as main() derives them. */
+int32_t t1ko_infer_kmer_length(int64_t totalLength);
+T1KOracle *t1ko_filter_create(int32_t nSeqs, const char *bases, const int64_t *off, int32_t k, int32_t hitLenRequired, double similarity);
+int32_t t1ko_is_low_complexity(const char *read);
+int32_t t1ko_has_hit_in_set(T1KOracle *o, const char *read);
+int32_t t1ko_is_good_candidate(T1KOracle *o, const char *read);
+
 /* AlignAlgo::GlobalAlignment.  ops receives 0 M,1 X,2 I,3 D; returns score, *nOps set. */
 int32_t t1ko_global_alignment(const char *t, int32_t lent, const char *p, int32_t lenp, int8_t *ops, int32_t *nOps);
 

@@ -50,6 +50,15 @@ def lib():
         L.t1ko_em.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_double, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.t1ko_infer_kmer_length.restype = C.c_int32
+        L.t1ko_infer_kmer_length.argtypes = [C.c_int64]
+        L.t1ko_filter_create.restype = C.c_void_p
+        L.t1ko_filter_create.argtypes = [C.c_int32, C.c_char_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double]
+        for f in (L.t1ko_has_hit_in_set, L.t1ko_is_good_candidate):
+            f.restype = C.c_int32
+            f.argtypes = [C.c_void_p, C.c_char_p]
+        L.t1ko_is_low_complexity.restype = C.c_int32
+        L.t1ko_is_low_complexity.argtypes = [C.c_char_p]
         _lib = L
     return _lib
 
@@ -454,3 +463,40 @@ def seq_weights(records, weights):
     for k, w in zip(keys, weights):
         tot[k] = tot.get(k, 0) + w
     return [tot[k] for k in keys]
+
+
+class CandidateFilter:
+    """The candidate filter of fastq-extractor as the oracle restates it: FastqExtractor.cpp main()'s
+    set-up (k = max(9, InferKmerLength), hitLenRequired = max(27 | 23, mean length of the first 1000 reads // 5, k)),
+    IsGoodCandidate per read, a pair is kept if either mate is good (FastqExtractor.cpp:199-212)."""
+
+    def __init__(self, records, reads1, paired, similarity=0.8):
+        seqs = [r[2] for r in records]
+        bases = b"".join(seqs)
+        off = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum([len(x) for x in seqs], out=off[1:])
+        first = reads1[:1000]
+        hit_len = 27 if paired else 23
+        mean5 = sum(len(r) for r in first) // (len(first) * 5)
+        if mean5 > hit_len:
+            hit_len = mean5
+        k = 9
+        inferred = lib().t1ko_infer_kmer_length(int(off[-1]))
+        if inferred > k:
+            k = inferred
+            if k > hit_len:
+                hit_len = k
+        self.k, self.hit_len = k, hit_len
+        self.h = lib().t1ko_filter_create(len(seqs), bases, _p(off), k, hit_len, similarity)
+        assert self.h
+
+    def good(self, read):
+        return bool(lib().t1ko_is_good_candidate(self.h, read))
+
+    def keep_pair(self, r1, r2=None):
+        return self.good(r1) or (r2 is not None and self.good(r2))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().t1ko_destroy(self.h)
+            self.h = None

@@ -1,0 +1,51 @@
+"""SURVEY.md 8f N1 (next row, oracle stage): the oracle's restatement of fastq-extractor's candidate filter
+(IsLowComplexity + SeqSet::HasHitInSet with the extractor's own k / hitLenRequired set-up) against what the UNMODIFIED
+reference binary kept (tests/golden/filter/*.npz, made by tests/golden/make_golden_filter.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import golden_io as G
+import oracle_py as O
+
+FILTER_DIR = os.path.join(G.GOLDEN, "filter")
+NAMES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(FILTER_DIR, "*.npz")))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_candidate_filter_matches_reference_binary(name):
+    z = np.load(os.path.join(FILTER_DIR, name + ".npz"))
+    if name.startswith("recipe_"):                      # large reference: regenerated from the recipe of make_golden_filter.py
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("make_golden_filter", os.path.join(G.GOLDEN, "make_golden_filter.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        recs = mod.big_ref()
+    else:
+        recs = G.parse_fasta_bytes(z["fasta"].tobytes())
+    paired = bool(int(z["paired"]))
+    r1 = [bytes(x) for x in z["reads1"]]
+    r2 = [bytes(x) for x in z["reads2"]] if paired else None
+    f = O.CandidateFilter(recs, r1, paired, float(z["similarity"]))
+    if name == "recipe_k13":
+        assert f.k == 13                                # the sorted-code index of the oracle (k > 12)
+    got = np.asarray([f.keep_pair(r1[i], r2[i] if paired else None) for i in range(len(r1))], dtype=np.uint8)
+    want = z["kept"]
+    assert 0 < want.sum() < len(want)                  # the fixture has both outcomes
+    assert np.array_equal(got, want), np.flatnonzero(got != want)[:10]
+
+
+def test_kmer_length_inference_and_low_complexity():
+    L = O.lib()
+    # SeqSet::InferKmerLength (SeqSet.hpp:2830-2845): number of base-4 digits of the total length + 1
+    assert L.t1ko_infer_kmer_length(0) == 1
+    assert L.t1ko_infer_kmer_length(3) == 2
+    assert L.t1ko_infer_kmer_length(98000) == 10
+    assert L.t1ko_infer_kmer_length(33_000_000) == 14
+    # IsLowComplexity (FastqExtractor.cpp:89-112)
+    assert L.t1ko_is_low_complexity(b"A" * 60) == 1
+    assert L.t1ko_is_low_complexity(b"ACGT" * 20) == 0
+    assert L.t1ko_is_low_complexity(b"ACACACACACACACACACACACAC") == 1            # two letters absent
+    assert L.t1ko_is_low_complexity(b"ACGTNNNNNNNNNNACGTACGTACGTACGTACGT") == 1   # >= 10 % N
