@@ -1,5 +1,5 @@
 // DRAFT for SURVEY.md §8f N1 (candidate filter of fastq-extractor) — lane-level building blocks with a RUNTIME k-mer
-// length, checked on the CPU against the oracle / the reference binary (tests/filter_emu.cpp).  Not yet part of the
+// length, checked on the CPU against the reference binary (tests/filter_emu.cpp).  Not yet part of the
 // product library: the kernel around them (streaming reads, per-(strand, sequence) hit counting over allele tiles, best
 // bucket, this chaining) and its C-ABI entry point need GPU time to validate and measure.
 //
