@@ -522,22 +522,22 @@ int t1k_assignment_fetch(T1KAssignment *a, uint64_t *row_ptr, int32_t *ret, T1KO
   const u64 used = std::min(a->storeUsed, a->storeCap);
   std::vector<Rec> st(used);
   CK(cudaMemcpy(st.data(), a->store.p, used * sizeof(Rec), cudaMemcpyDeviceToHost));
-  // unpack into the reference's output order: list-order key, then candidate order (== store order)
+  // unpack into the reference's output order (rec_before: list-order key, then store position / extended coordinates)
   std::vector<u32> idx;
   u64 w = 0;
   for (u32 i = 0; i < n; ++i) {
     idx.resize(cnt[i]);
     std::iota(idx.begin(), idx.end(), 0u);
     const Rec *L = st.data() + off[i];
-    std::stable_sort(idx.begin(), idx.end(), [L](u32 x, u32 y) { return L[x].key < L[y].key; });
+    std::sort(idx.begin(), idx.end(), [L](u32 x, u32 y) { return rec_before(L[x], x, L[y], y); });
     for (u32 k = 0; k < cnt[i]; ++k, ++w) {
       const Rec &r = L[idx[k]];
       T1KOverlap &o = records[w];
       o.seqIdx = r.seqIdx; o.seqStart = r.seqStart; o.seqEnd = r.seqEnd;
-      o.readStart = (int32_t)(r.packed & 255); o.readEnd = (int32_t)((r.packed >> 8) & 255);
-      o.leftClip = (int32_t)((r.packed >> 16) & 255); o.rightClip = (int32_t)(r.packed >> 24);
-      o.matchCnt = (int32_t)(r.mcStrand & 0x7fffffffu); o.strand = (r.mcStrand >> 31) ? 1 : -1;
-      o.relaxedMatchCnt = r.relaxed;
+      o.readStart = r.readStart; o.readEnd = r.readEnd;
+      o.leftClip = r.leftClip; o.rightClip = r.rightClip;
+      o.matchCnt = rec_mc(r.mcx); o.strand = rec_strand01(r.mcx) ? 1 : -1;
+      o.relaxedMatchCnt = rec_relaxed(r.mcx);
     }
   }
   return T1K_OK;

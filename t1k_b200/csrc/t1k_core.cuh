@@ -119,14 +119,31 @@ enum { CF_SEP = 1, CF_NEEDCLIP = 2, CF_RET = 4, CF_INCLUDE = 8,
        CF_PRE = 16,       // extension fields already filled by diag_fast (ExtendOverlap need not run)
        CF_FA = 32 };      // full-read alignment already known (mmPos)
 
-// final record kept resident in HBM for pairing: 32 B
+// final record kept resident in HBM for pairing: 32 B.  Positions are 16 bits wide (reads of any supported length).
 struct Rec {
   int32_t seqIdx, seqStart, seqEnd;
-  u32 packed;            // readStart | readEnd<<8 | leftClip<<16 | rightClip<<24
-  u32 mcStrand;          // matchCnt | strand01<<31
-  int32_t relaxed;
-  u64 key;               // list-order key (ascending = the reference's output order)
+  u16 readStart, readEnd, leftClip, rightClip;
+  u32 mcx;               // matchCnt | relaxedMatchCnt << 14 | strand01 << 31
+  u64 key;               // list-order key (order_key) | bit 0: the list is in post-extension order (the > 1000 cut ran)
 };
+T1K_HD u32 rec_mcx(int matchCnt, int relaxed, int strand01) { return (u32)matchCnt | ((u32)relaxed << 14) | ((u32)strand01 << 31); }
+T1K_HD int rec_mc(u32 mcx) { return (int)(mcx & 0x3FFFu); }
+T1K_HD int rec_relaxed(u32 mcx) { return (int)((mcx >> 14) & 0x3FFFu); }
+T1K_HD int rec_strand01(u32 mcx) { return (int)(mcx >> 31); }
+// The reference's output order of one read-end's records (`assign`, SeqSet.hpp:2300) from the stored fields.  The store keeps
+// a list in allele order and, inside one allele, in (readStart, readEnd, seqStart, seqEnd) order of the SEED overlaps, so
+// for a list in pre-extension order `key` and the store position reproduce _overlap::operator< (SeqSet.hpp:103-127) down to
+// its last field.  A list the > 1000 cut re-sorted (SeqSet.hpp:2290-2298; bit 0 of key) is ordered on the extended fields,
+// which the record itself holds.
+T1K_HD bool rec_before(const Rec &a, long long ia, const Rec &b, long long ib) {
+  if (a.key != b.key) return a.key < b.key;
+  if (!(a.key & 1) || a.seqIdx != b.seqIdx) return ia < ib;
+  if (a.readStart != b.readStart) return a.readStart < b.readStart;
+  if (a.readEnd != b.readEnd) return a.readEnd < b.readEnd;
+  if (a.seqStart != b.seqStart) return a.seqStart < b.seqStart;
+  if (a.seqEnd != b.seqEnd) return a.seqEnd < b.seqEnd;
+  return ia < ib;
+}
 
 // per-lane scratch in global memory
 constexpr int SCR_OPS = 1024;
@@ -658,12 +675,14 @@ T1K_HD u64 strand_key(int matchCnt, int span, int seqIdx, int strand01) {
   return ((u64)matchCnt << 40) | ((u64)span << 32) | ((u64)(0xFFFFFFu - (u32)seqIdx) << 1) | (u64)(strand01 ? 0 : 1);
 }
 
-// list-order key, ascending = _overlap::operator< order (matchCnt desc, similarity desc == denominator asc
-// for equal matchCnt, read span desc, seqIdx asc, readStart asc)
-T1K_HD u64 order_key(int matchCnt, int denom, int span, int seqIdx, int readStart) {
-  return ((u64)(2047 - matchCnt) << 53) | ((u64)denom << 41) | ((u64)(255 - span) << 33) | ((u64)seqIdx << 9) |
-         ((u64)readStart << 1);
+// list-order key, ascending = _overlap::operator< order (SeqSet.hpp:103-127): matchCnt desc, similarity desc (== denominator
+// asc for equal matchCnt), read span desc.  The remaining fields (seqIdx, strand, readStart, readEnd, seqStart, seqEnd) are
+// the order the candidates are EMITTED in — allele tiles ascending, one strand per range, and sort_emitted below inside an
+// allele — so ties on the key fall to the candidate index.  Bit 0 stays free (Rec::key).
+T1K_HD u64 order_key(int matchCnt, int denom, int span) {
+  return ((u64)(16383 - matchCnt) << 50) | ((u64)denom << 35) | ((u64)(16383 - span) << 21);
 }
+T1K_HD int order_key_mc(u64 key) { return 16383 - (int)(key >> 50); }
 
 // ---- chain consumer: GetOverlapsFromHits tail (SeqSet.hpp:1500-1550) + the matchCnt recomputation of
 // GetOverlapsFromRead (SeqSet.hpp:1697-1845).  `C` yields the LIS chain as encoded hits; read and allele offsets
@@ -950,6 +969,27 @@ T1K_HD void full_align_known(const RefView &R, Cand &c, int weight) {
   c.relaxed = R.relax ? 2 * (lent - exMm) : c.eMatchCnt;
 }
 
+// The seed overlaps one (strand, allele) group emitted, into the tail order of _overlap::operator< (readStart, readEnd,
+// seqStart, seqEnd; SeqSet.hpp:117-125): clusters come out by ascending diagonal, i.e. by DEscending seqStart for equal
+// read coordinates (an allele that holds a segment twice), the reference lists them ascending.  n is almost always 1.
+T1K_HD bool cand_tail_less(const Cand &a, const Cand &b) {
+  if (a.readStart != b.readStart) return a.readStart < b.readStart;
+  if (a.readEnd != b.readEnd) return a.readEnd < b.readEnd;
+  if (a.seqStart != b.seqStart) return a.seqStart < b.seqStart;
+  return a.seqEnd < b.seqEnd;
+}
+T1K_HDN T1K_NOINLINE inline void sort_emitted(Cand *e, int n) {
+  T1K_NOUNROLL
+  for (int i = 1; i < n; ++i) {
+    if (!cand_tail_less(e[i], e[i - 1])) continue;
+    const Cand v = e[i];
+    int j = i - 1;
+    T1K_NOUNROLL
+    while (j >= 0 && cand_tail_less(v, e[j])) { e[j + 1] = e[j]; --j; }
+    e[j + 1] = v;
+  }
+}
+
 struct ChainDirect {   // contiguous run of a hit store
   const u32 *p; int stride;
   T1K_HD u32 operator()(int i) const { return p[(size_t)i * stride]; }
@@ -1229,10 +1269,10 @@ T1K_HD int cand_denom_post(const Cand &c) {
   return c.eSeqEnd - c.eSeqStart + 1 + c.eReadEnd - c.eReadStart + 1 + 2 * c.leftClip + 2 * c.rightClip;
 }
 T1K_HD u64 cand_key_pre(const Cand &c) {
-  return order_key(c.matchCnt, cand_denom_pre(c), c.readEnd - c.readStart, c.seqIdx, c.readStart);
+  return order_key(c.matchCnt, cand_denom_pre(c), c.readEnd - c.readStart);
 }
 T1K_HD u64 cand_key_post(const Cand &c) {
-  return order_key(c.eMatchCnt, cand_denom_post(c), c.eReadEnd - c.eReadStart, c.seqIdx, c.eReadStart);
+  return order_key(c.eMatchCnt, cand_denom_post(c), c.eReadEnd - c.eReadStart);
 }
 
 }  // namespace t1k

@@ -56,7 +56,7 @@ struct AssignOut {
   u64 storeCap;
   u64 *readOff;            // per read-end: first record
   u32 *readCnt;
-  u32 *readTop;            // per read-end: max over its records of matchCnt << 12 | (4095 - denominator) (pairing's "is anything better" test)
+  u32 *readTop;            // per read-end: max over its records of matchCnt << 16 | (65535 - denominator) (pairing's "is anything better" test)
   u32 *maxCnt;             // longest record list of the batch (sizes the pairing kernel's per-warp scratch)
   int32_t *readRet;        // AssignRead's return value; -2 = deferred (store full), -3 = deferred (hit tile too small)
   int *err;
@@ -359,7 +359,10 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
           handled = diag_fast(R, Qv, strand01, (int)(base + lane), n, W.H + lane, 32, W.stab, fc, fastEmit, laneKey, lcMemo, S, err);
           if (fastEmit) nEmit = 1;
         }
-        if (!handled) chain_allele(R, Qv, strand01, (int)(base + lane), W.H + lane, 32, n, S, nEmit, laneKey, err);
+        if (!handled) {
+          chain_allele(R, Qv, strand01, (int)(base + lane), W.H + lane, 32, n, S, nEmit, laneKey, err);
+          if (nEmit > 1) sort_emitted(S.emit(), nEmit);       // several clusters on one allele: the tail order of _overlap::operator<
+        }
         // ---- ordered emission (allele order == lane order)
         int incl = nEmit;
 #pragma unroll
@@ -446,7 +449,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
     // goodMatchCnt (SeqSet.hpp:2156-2186) = the largest matchCnt among the returned candidates that precede the first
     // failing one.  The list order is matchCnt-descending, so that is the first returned candidate if it precedes the
     // failure, and nothing otherwise: no pass of its own.
-    const int good = pair_less(rKey, rIdx, fKey, fIdx) ? 2047 - (int)(rKey >> 53) : -1;
+    const int good = pair_less(rKey, rIdx, fKey, fIdx) ? order_key_mc(rKey) : -1;
     // pass 2: inclusion; the list head under the post-extension order (for the > 1000 cut, SeqSet.hpp:2290-2298)
     int bestMc = -1, nInc = 0;
     u64 bKey = ~0ull; int bIdx = 0x7fffffff;
@@ -538,11 +541,10 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
         if (inc) {
           Rec o;
           o.seqIdx = c.seqIdx; o.seqStart = c.eSeqStart; o.seqEnd = c.eSeqEnd;
-          o.packed = (u32)c.eReadStart | ((u32)c.eReadEnd << 8) | ((u32)c.leftClip << 16) | ((u32)c.rightClip << 24);
-          o.mcStrand = (u32)c.eMatchCnt | ((u32)c.strand01 << 31);
-          o.relaxed = c.relaxed;
-          o.key = usePost ? kPost : cand_key_pre(c);
-          top = max(top, ((u32)c.eMatchCnt << 12) | (u32)(4095 - cand_denom_post(c)));
+          o.readStart = c.eReadStart; o.readEnd = c.eReadEnd; o.leftClip = c.leftClip; o.rightClip = c.rightClip;
+          o.mcx = rec_mcx(c.eMatchCnt, c.relaxed, c.strand01);
+          o.key = usePost ? (kPost | 1ull) : cand_key_pre(c);
+          top = max(top, ((u32)c.eMatchCnt << 16) | (u32)(65535 - cand_denom_post(c)));
           P.O.store[pos + running + __popc(bal & ((1u << lane) - 1))] = o;
         }
         running += __popc(bal);

@@ -22,7 +22,7 @@ struct PairParams {
   const Rec *store;
   const u64 *readOff;
   const u32 *readCnt;
-  const u32 *readTop;       // per read-end: max matchCnt << 12 | (4095 - denominator) over its records (k_assign)
+  const u32 *readTop;       // per read-end: max matchCnt << 16 | (65535 - denominator) over its records (k_assign)
   const u32 *end1, *end2;   // end2 == NULL: single-end data
   const u8 *hasN;
   u32 fragBase, nFrag;      // fragments [fragBase, fragBase + nFrag) of the caller's arrays
@@ -53,9 +53,9 @@ __device__ __forceinline__ RV load_rv(const Rec *p) {
   const uint4 b = *(reinterpret_cast<const uint4 *>(p) + 1);
   RV r;
   r.seqIdx = (int)a.x; r.ss = (int)a.y; r.se = (int)a.z;
-  r.rs = a.w & 255; r.re = (a.w >> 8) & 255; r.lc = (a.w >> 16) & 255; r.rc = a.w >> 24;
-  r.mc = (int)(b.x & 0x7fffffffu); r.st = (int)(b.x >> 31);
-  r.relaxed = (int)b.y;
+  r.rs = a.w & 0xffff; r.re = a.w >> 16; r.lc = b.x & 0xffff; r.rc = b.x >> 16;
+  r.mc = rec_mc(b.y); r.st = rec_strand01(b.y);
+  r.relaxed = rec_relaxed(b.y);
   r.key = (u64)b.z | ((u64)b.w << 32);
   return r;
 }
@@ -122,6 +122,18 @@ struct AlleleBest {
 };
 
 __device__ __forceinline__ bool pos_less(u64 k, int i, u64 k2, int i2) { return k < k2 || (k == k2 && i < i2); }
+// list order of two records of ONE allele run of one list (rec_before, t1k_core.cuh): key, then — in a list the > 1000 cut
+// re-sorted — the extended coordinates, else the store position.  `b` is only consulted on a key tie of a re-sorted list.
+__device__ __forceinline__ bool run_pos_less(const RV &a, int ia, u64 kb, int ib, const Rec *L) {
+  if (a.key != kb) return a.key < kb;
+  if (!(a.key & 1) || ib < 0 || ib == 0x7fffffff) return ia < ib;
+  const RV b = load_rv(L + ib);
+  if (a.rs != b.rs) return a.rs < b.rs;
+  if (a.re != b.re) return a.re < b.re;
+  if (a.ss != b.ss) return a.ss < b.ss;
+  if (a.se != b.se) return a.se < b.se;
+  return ia < ib;
+}
 
 // mate compatibility (SeqSet.hpp:2366-2380)
 __device__ __forceinline__ bool mates_ok(const RV &a, const RV &b) {
@@ -141,12 +153,12 @@ __device__ void eval_allele(const RefView &R, bool paired, const Rec *A, int a0,
   if (!paired) {
     for (int ia = a0; ia < a1; ++ia) {
       const RV a = load_rv(A + ia);
-      if (pos_less(a.key, ia, out.posKey, out.posIdx)) { out.posKey = a.key; out.posIdx = ia; }
+      if (run_pos_less(a, ia, out.posKey, out.posIdx, A)) { out.posKey = a.key; out.posIdx = ia; }
       bool better;
       if (!out.valid) better = true;
       else if (rv_less(a, bo1)) better = true;
       else if (rv_less(bo1, a)) better = false;
-      else better = pos_less(a.key, ia, bKeyA, out.ia);
+      else better = run_pos_less(a, ia, bKeyA, out.ia, A);
       if (better) { out.valid = true; bo1 = a; bKeyA = a.key; out.ia = ia; out.jb = -1; }
     }
     if (out.valid) {
@@ -167,7 +179,7 @@ __device__ void eval_allele(const RefView &R, bool paired, const Rec *A, int a0,
       const RV b = load_rv(B + jb);
       if (b.seqIdx != seqIdx) break;
       if (!mates_ok(a, b)) continue;
-      if (pos_less(a.key, ia, out.posKey, out.posIdx)) { out.posKey = a.key; out.posIdx = ia; }
+      if (run_pos_less(a, ia, out.posKey, out.posIdx, A)) { out.posKey = a.key; out.posIdx = ia; }
       const int mc = a.mc + b.mc, den = dA + rv_denom(b);
       bool better;
       if (!out.valid) better = true;
@@ -175,8 +187,8 @@ __device__ void eval_allele(const RefView &R, bool paired, const Rec *A, int a0,
       else if (den != bden) better = den < bden;
       else if (rv_less(a, bo1)) better = true;
       else if (rv_less(bo1, a)) better = false;
-      else if (ia != out.ia) better = pos_less(a.key, ia, bKeyA, out.ia);
-      else better = pos_less(b.key, jb, bKeyB, out.jb);
+      else if (ia != out.ia) better = run_pos_less(a, ia, bKeyA, out.ia, A);
+      else better = run_pos_less(b, jb, bKeyB, out.jb, B);
       if (better) { out.valid = true; bmc = mc; bden = den; bo1 = a; bo2 = b; bKeyA = a.key; bKeyB = b.key; out.ia = ia; out.jb = jb; }
     }
   }
@@ -262,7 +274,7 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
         while (a1 < nA && A[a1].seqIdx == A[i].seqIdx) ++a1;
         AlleleBest ab; eval_allele(R, paired, A, i, a1, B, nB, ab, -1, i + delta);
         if (paired) { b0s[i] = (u32)ab.b0; myDelta = ab.b0 - i; }
-        const u32 key = ab.valid ? (((u32)ab.mc << 12) | (u32)(4095 - ab.denom)) : 0u;
+        const u32 key = ab.valid ? (((u32)ab.mc << 16) | (u32)(65535 - ab.denom)) : 0u;
         keys[i] = key;
         k1 = max(k1, key);
       }
@@ -273,7 +285,7 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
     }
     k1 = __reduce_max_sync(FULL, k1);
     if (k1 != 0) {
-      const int bestMc = (int)(k1 >> 12), bestDen = 4095 - (int)(k1 & 4095);
+      const int bestMc = (int)(k1 >> 16), bestDen = 65535 - (int)(k1 & 65535);
       // pass 2: relaxedMatchCnt of the first allele (assign order) that reaches the best
       u64 pk = ~0ull; int pi = 0x7fffffff; int bestRelax = 0;
       if (R.relax) {
@@ -309,7 +321,7 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
         bool cand = false;
         if (i < nA) {
           const u32 key = keys[i];                       // 0xffffffff: not the first record of its allele; 0: no valid pair
-          cand = key == k1 || (R.relax && key != 0 && key != 0xffffffffu && (int)(key >> 12) >= bestMc - 4);
+          cand = key == k1 || (R.relax && key != 0 && key != 0xffffffffu && (int)(key >> 16) >= bestMc - 4);
         }
         if (cand) {
           int a1 = i + 1;
@@ -362,7 +374,7 @@ __device__ void pair_one(const PairParams &P, u32 fLocal, int lane) {
         const double s1 = (double)o1.mc / (double)d1, s2 = (double)o2.mc / (double)d2;
         bool filter = false;
         // nothing in a list can beat the chosen mate unless the list's best (matchCnt, denominator) key exceeds the mate's
-        const u32 key1 = ((u32)o1.mc << 12) | (u32)(4095 - d1), key2 = ((u32)o2.mc << 12) | (u32)(4095 - d2);
+        const u32 key1 = ((u32)o1.mc << 16) | (u32)(65535 - d1), key2 = ((u32)o2.mc << 16) | (u32)(65535 - d2);
         const bool scanA = P.readTop[A == L1 ? e1 : P.end2[f]] > key1, scanB = P.readTop[B == L1 ? e1 : P.end2[f]] > key2;
         if (scanA)
         for (int i = lane; i < nA; i += 32) {

@@ -139,6 +139,7 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
         }
       }
       chain_allele(R, Q, strand01, (int)it->first, h.data(), 1, (int)h.size(), S, nEmit, bestKey, err);
+      if (nEmit > 1) sort_emitted(S.emit(), nEmit);
       for (int k = 0; k < nEmit; ++k) { Cand c = S.emit()[k]; c.mmPos = 0; cands.push_back(c); }
     }
     if (pass == 0) nFwd = (int)cands.size();
@@ -206,10 +207,24 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
       if (k > cKey || (k == cKey && i >= cIdx)) cands[i].flags &= ~CF_INCLUDE;
     }
   }
+  // the records as the kernel's compaction pass stores them (candidate order) and the order t1k_assignment_fetch returns
+  std::vector<Rec> recs; std::vector<int> recCand;
+  for (int i = c0; i < c1; ++i) if (cands[i].flags & CF_INCLUDE) {
+    const Cand &c = cands[i];
+    Rec o;
+    o.seqIdx = c.seqIdx; o.seqStart = c.eSeqStart; o.seqEnd = c.eSeqEnd;
+    o.readStart = c.eReadStart; o.readEnd = c.eReadEnd; o.leftClip = c.leftClip; o.rightClip = c.rightClip;
+    o.mcx = rec_mcx(c.eMatchCnt, c.relaxed, c.strand01);
+    o.key = usePost ? (cand_key_post(c) | 1ull) : cand_key_pre(c);
+    recs.push_back(o); recCand.push_back(i);
+  }
   std::vector<std::pair<u64, int> > order;
-  for (int i = c0; i < c1; ++i) if (cands[i].flags & CF_INCLUDE)
-    order.push_back(std::make_pair(usePost ? cand_key_post(cands[i]) : cand_key_pre(cands[i]), i));
-  std::sort(order.begin(), order.end());
+  {
+    std::vector<int> idx(recs.size());
+    for (size_t k = 0; k < idx.size(); ++k) idx[k] = (int)k;
+    std::sort(idx.begin(), idx.end(), [&](int x, int y) { return rec_before(recs[x], x, recs[y], y); });
+    for (size_t k = 0; k < idx.size(); ++k) order.push_back(std::make_pair(recs[idx[k]].key, recCand[idx[k]]));
+  }
   int w = 0;
   for (size_t k = 0; k < order.size() && w < cap; ++k, ++w) {
     const Cand &c = cands[order[k].second];

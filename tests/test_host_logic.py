@@ -144,6 +144,15 @@ def test_diagonal_fast_path_equals_general_path(emu):
         for i, ((n1, a), (n0, b)) in enumerate(zip(*res)):
             assert n1 == n0 and np.array_equal(a, b), (name, i, reads[i])
         assert np.array_equal(covs[0], covs[1]), name
+        # ... and both equal the oracle (a comparison of the product with itself proves nothing about the reference)
+        kept, _ = O.collapse_reference(recs)
+        assert len(kept) == ref.n
+        orc = O.Oracle(kept, sim, relax)
+        for i, s in enumerate(reads):
+            oret, ov = orc.assign(s, 2)
+            want = np.stack([ov[k] for k in O.OVERLAP_DT.names], axis=1) if len(ov) else np.zeros((0, 10), np.int32)
+            assert res[0][i][0] == oret and np.array_equal(res[0][i][1], want), (name, i, s)
+        assert np.array_equal(covs[0], np.concatenate([orc.coverage(a) for a in range(ref.n)])), name
 
 
 def test_lane_code_matches_oracle_on_the_bench_workload(emu):
