@@ -158,6 +158,14 @@ struct PinnedMem {
   template <class T> T *as() const { return (T *)p; }
 };
 
+// The runtime's "last error" is per host thread and survives until somebody reads it: an error that other code of the
+// process (or an unchecked call) left behind must not be mistaken for the failure of the next kernel launch here.  Every
+// compute entry point clears it on entry; T1K_DEBUG_STALE=1 reports what was pending.
+void stale(const char *tag) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess && getenv("T1K_DEBUG_STALE")) fprintf(stderr, "[t1k] pending CUDA error at %s: %s\n", tag, cudaGetErrorString(e));
+}
+
 double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -189,17 +197,16 @@ struct T1KRef {
   std::vector<u64> wordOff;
   std::vector<int32_t> len;
   size_t paddedBases = 0;
-  DevMem seq2, n2, ex2, dWordOff, dLen, dHasN, dMeta, dSimThr, kstart, post, covDiff, covPoint, covFinal;
+  DevMem seq2, n2, ex2, dWordOff, dLen, dHasN, dMeta, dSimThr, kinfo, entries, covDiff, covPoint, covFinal;
   RefView R;
   cudaStream_t stream = nullptr;
   // launch state of k_assign, sized on first use
-  DevMem candBuf, laneScratch, workCtr, errFlag, stats;
+  DevMem candBuf, laneScratch, hitBuf, workCtr, errFlag, stats;
   u32 candCap = 0;
-  // two launch geometries of k_assign: [0] small hit tile (more resident warps), [1] tile for the worst case
-  int gridBlocks[2] = {0, 0}, hitCap[2] = {0, 0};
-  int occ = 3;
+  int gridBlocks = 0, hitCap = 0, seedCap = 0;
+  int occ = 4;
   size_t scratchWarps = 0;
-  u64 nPostings = 0;
+  u64 nPostings = 0, nEntries = 0;
   size_t memBudget = 0;      // free device memory right after the reference was uploaded (workspace budget; cudaMemGetInfo is
                              // a slow driver call, so it is not repeated per batch)
   bool covDirty = true;
@@ -210,6 +217,7 @@ struct T1KRef {
 
 struct T1KAssignment {
   T1KRef *ref = nullptr;
+  int device = 0;          // (kept here: the assignment may be destroyed after its reference)
   u32 nReads = 0;
   DevMem store, storeCtr, readOff, readCnt, readRet, readTop, dMaxCnt;
   u64 storeCap = 0, storeUsed = 0;
@@ -259,9 +267,12 @@ int t1k_ref_create(const T1KRefDesc *d, T1KRef **out) {
     if (e == cudaSuccess) e = cudaMemcpy(r->dst.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice); \
     if (e != cudaSuccess) { delete r; return fail(T1K_ERR_CUDA, std::string("t1k_ref_create upload: ") + cudaGetErrorString(e)); } \
   } while (0)
-  UP(seq2, P.seq2); UP(n2, P.n2); UP(ex2, P.ex2); UP(dWordOff, P.wordOff); UP(dLen, P.len); UP(dHasN, P.hasN); UP(dMeta, P.meta); UP(kstart, P.kstart);
-  P.post.resize(P.post.size() + 64);       // slack: the gather's TMA copies read a fixed 34 postings from any cursor
-  UP(post, P.post);
+  UP(seq2, P.seq2); UP(n2, P.n2); UP(ex2, P.ex2); UP(dWordOff, P.wordOff); UP(dLen, P.len); UP(dHasN, P.hasN); UP(dMeta, P.meta);
+  for (size_t k = 0; k < P.entries.size(); ++k)
+    if (P.entries[k].more >= 65535u) { delete r; return fail(T1K_ERR_UNSUPPORTED, "a k-mer occurs at more than 65535 offsets inside one tile of 32 alleles"); }
+  r->nEntries = P.entries.size();
+  P.entries.resize(P.entries.size() + 4, KmerEntry{0xffffffffu, 0, 0, 0});
+  UP(kinfo, P.kinfo); UP(entries, P.entries);
   std::vector<u16> simThr(2 * SIM_DEN);
   sim_threshold_table(d->similarity, simThr.data());
   UP(dSimThr, simThr);
@@ -277,7 +288,7 @@ int t1k_ref_create(const T1KRefDesc *d, T1KRef **out) {
   RefView &R = r->R;
   R.seq2 = r->seq2.as<u64>(); R.n2 = r->n2.as<u64>(); R.ex2 = r->ex2.as<u64>();
   R.wordOff = r->dWordOff.as<u64>(); R.len = r->dLen.as<int32_t>(); R.hasN = r->dHasN.as<u8>(); R.meta = r->dMeta.as<AlleleMeta>(); R.simThr = r->dSimThr.as<u16>();
-  R.kstart = r->kstart.as<u32>(); R.post = r->post.as<Posting>();
+  R.kstart = nullptr; R.post = nullptr; R.kinfo = r->kinfo.as<KmerInfo>(); R.entries = r->entries.as<KmerEntry>();
   R.covDiff = r->covDiff.as<int32_t>(); R.covPoint = r->covPoint.as<int32_t>();
   R.nAlleles = d->n_alleles; R.sim = d->similarity; R.relax = d->relax_intron;
   {
@@ -301,41 +312,37 @@ int t1k_ref_n_alleles(const T1KRef *ref) { return ref ? ref->nAlleles : 0; }
 
 namespace {
 
-// persistent launch geometries of k_assign for reads up to maxLen bases
+// persistent launch geometry of k_assign for reads up to maxLen bases
+const void *assign_kernel(int occ) {
+  return occ >= 6 ? (const void *)k_assign<6> : occ == 5 ? (const void *)k_assign<5> : occ == 4 ? (const void *)k_assign<4>
+       : occ == 3 ? (const void *)k_assign<3> : (const void *)k_assign<2>;
+}
 int setup_assign_launch(T1KRef *r, int maxLen) {
-  int big = maxLen - KMER + 1 + 24;
-  if (big < 64) big = 64;
-  big = (big + 7) & ~7;
-  // occupancy variant: resident blocks per SM the kernel is compiled for, and the small hit tile that fits beside it
-  int occ = 3;      // measured: 3 blocks/SM at 168 registers (no spills) beats 4 at 128 and 5 at 96
+  int seedCap = std::max(64, (maxLen - KMER + 1 + 31) & ~31);
+  // resident blocks per SM the kernel is compiled for (register budget): T1K_ASSIGN_OCC
+  int occ = 4;
   if (const char *env = getenv("T1K_ASSIGN_OCC")) occ = atoi(env);
-  if (occ != 2 && occ != 3 && occ != 4) occ = 3;
+  if (occ < 2 || occ > 6) occ = 4;
+  int hitCap = 1024;     // hits of one allele the hit-list path holds (HBM scratch; a 255-base read has <= 245 seeds)
+  if (const char *env = getenv("T1K_HIT_CAP")) hitCap = std::max(64, atoi(env));
+  if (r->gridBlocks && seedCap <= r->seedCap && occ == r->occ && hitCap == r->hitCap) return T1K_OK;
   r->occ = occ;
-  int small = 64;
-  if (const char *env = getenv("T1K_HIT_TILE")) small = std::max(8, atoi(env));
-  if (small > big) small = big;
-  if (r->gridBlocks[0] && big <= r->hitCap[1]) return T1K_OK;
-  const int caps[2] = {small, big};
-  size_t maxSmem = 0;
-  for (int c = 0; c < 2; ++c) maxSmem = std::max(maxSmem, ((warp_smem_bytes(caps[c]) + 15) & ~(size_t)15) * WARPS_PER_BLOCK);
-  const void *kfn = occ == 4 ? (const void *)k_assign<4> : occ == 3 ? (const void *)k_assign<3> : (const void *)k_assign<2>;
-  CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem));
-  size_t warps = 0;
-  for (int c = 0; c < 2; ++c) {
-    const size_t smem = ((warp_smem_bytes(caps[c]) + 15) & ~(size_t)15) * WARPS_PER_BLOCK;
-    int perSM = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kfn, WARPS_PER_BLOCK * 32, smem));
-    if (perSM < 1) return fail(T1K_ERR_UNSUPPORTED, "k_assign does not fit on an SM");
-    r->hitCap[c] = caps[c];
-    r->gridBlocks[c] = std::min(perSM, occ) * r->nSM;
-    warps = std::max(warps, (size_t)r->gridBlocks[c] * WARPS_PER_BLOCK);
-  }
+  const void *kfn = assign_kernel(occ);
+  const size_t smem = warp_smem_bytes(seedCap) * WARPS_PER_BLOCK;
+  CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int perSM = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kfn, WARPS_PER_BLOCK * 32, smem));
+  if (perSM < 1) return fail(T1K_ERR_UNSUPPORTED, "k_assign does not fit on an SM");
+  r->seedCap = seedCap; r->hitCap = hitCap;
+  r->gridBlocks = std::min(perSM, occ) * r->nSM;
+  const size_t warps = (size_t)r->gridBlocks * WARPS_PER_BLOCK;
   u64 cap = 2ull * (u64)r->nAlleles + 2048;
   if (cap > (1u << 20)) cap = 1u << 20;
   r->candCap = (u32)cap;
   r->scratchWarps = warps;
   CK(r->candBuf.alloc(warps * r->candCap * sizeof(Cand)));
   CK(r->laneScratch.alloc(warps * 32 * (size_t)SCR_BYTES));
+  CK(r->hitBuf.alloc(warps * (size_t)hitCap * 32 * sizeof(u32)));
   CK(r->workCtr.alloc(sizeof(unsigned int)));
   CK(r->errFlag.alloc(sizeof(int)));
   CK(r->stats.alloc(4 * sizeof(unsigned long long)));
@@ -348,7 +355,7 @@ std::string decode_err(int err) {
   if (err & ERR_SCRATCH) s += " chaining scratch overflow;";
   if (err & ERR_EMIT) s += " more than MAX_EMIT seed overlaps for one (read, allele);";
   if (err & ERR_CAND) s += " candidate buffer overflow;";
-  if (err & ERR_HITS) s += " more k-mer hits on one allele than the largest shared-memory tile holds;";
+  if (err & ERR_HITS) s += " more k-mer hits of one read on one allele than the hit-list scratch holds (T1K_HIT_CAP);";
   return s;
 }
 
@@ -369,11 +376,12 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
     maxLen = std::max(maxLen, (int)len[i]);
   }
   PhaseTimer pt;
+  stale("t1k_assign_batch");
   if (int rc = setup_assign_launch(ref, maxLen)) return rc;
   pt.lap("  assign: launch setup");
   T1KAssignment *a = new T1KAssignment;
   struct Guard { T1KAssignment *a; ~Guard() { delete a; } } guard{a};
-  a->ref = ref; a->nReads = n;
+  a->ref = ref; a->device = ref->device; a->nReads = n;
   DevMem dBases, dOff, dLen, dW, planes, len16;
   CK(dBases.alloc(total)); CK(dOff.alloc((size_t)n * 8)); CK(dLen.alloc((size_t)n * 4)); CK(dW.alloc((size_t)n * 4));
   CK(planes.alloc((size_t)n * 4 * RWORDS * 8)); CK(len16.alloc((size_t)n * 2));
@@ -411,33 +419,34 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   P.candBuf = ref->candBuf.as<Cand>(); P.candCap = ref->candCap; P.laneScratch = ref->laneScratch.as<u8>();
   { const char *env = getenv("T1K_NO_FAST"); P.noFast = (env && atoi(env) != 0) ? 1 : 0; }
   P.workCtr = ref->workCtr.as<unsigned int>();
-  DevMem workList[2];
+  P.hitBuf = ref->hitBuf.as<u32>(); P.hitCap = ref->hitCap; P.seedCap = ref->seedCap;
+  DevMem workList;
   std::vector<int32_t> hRet;
-  std::vector<u32> todo[2];          // pending read-ends per launch geometry; empty + first == everything
+  std::vector<u32> todo;            // read-ends waiting for a larger store; empty + first == everything
   bool first = true;
   cudaEvent_t ev0, ev1;
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
   struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
+  const size_t smem = warp_smem_bytes(ref->seedCap) * WARPS_PER_BLOCK;
   for (int round = 0;; ++round) {
     if (round > 0) CK(cudaMemsetAsync(ref->errFlag.p, 0, sizeof(int), st));   // round 0 keeps k_pack_reads' flags
-    CK(cudaEventRecord(ev0, st));
-    for (int c = 0; c < 2; ++c) {
-      if (!(first && c == 0) && todo[c].empty()) continue;
-      if (first && c == 0) { P.Q.workList = nullptr; P.Q.nWork = n; }
-      else {
-        CK(workList[c].alloc(todo[c].size() * 4));
-        CK(cudaMemcpyAsync(workList[c].p, todo[c].data(), todo[c].size() * 4, cudaMemcpyHostToDevice, st));
-        P.Q.workList = workList[c].as<u32>(); P.Q.nWork = (u32)todo[c].size();
-      }
-      P.hitCap = ref->hitCap[c];
-      const size_t smem = ((warp_smem_bytes(ref->hitCap[c]) + 15) & ~(size_t)15) * WARPS_PER_BLOCK;
-      CK(cudaMemsetAsync(ref->workCtr.p, 0, sizeof(unsigned int), st));
-      if (ref->occ == 4) k_assign<4><<<ref->gridBlocks[c], WARPS_PER_BLOCK * 32, smem, st>>>(P);
-      else if (ref->occ == 3) k_assign<3><<<ref->gridBlocks[c], WARPS_PER_BLOCK * 32, smem, st>>>(P);
-      else k_assign<2><<<ref->gridBlocks[c], WARPS_PER_BLOCK * 32, smem, st>>>(P);
-      CK(cudaGetLastError());
-      ++a->launches;
+    if (first) { P.Q.workList = nullptr; P.Q.nWork = n; }
+    else {
+      CK(workList.alloc(todo.size() * 4));
+      CK(cudaMemcpyAsync(workList.p, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, st));
+      P.Q.workList = workList.as<u32>(); P.Q.nWork = (u32)todo.size();
     }
+    CK(cudaMemsetAsync(ref->workCtr.p, 0, sizeof(unsigned int), st));
+    CK(cudaEventRecord(ev0, st));
+    switch (ref->occ) {
+      case 6: k_assign<6><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
+      case 5: k_assign<5><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
+      case 4: k_assign<4><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
+      case 3: k_assign<3><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
+      default: k_assign<2><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
+    }
+    CK(cudaGetLastError());
+    ++a->launches;
     CK(cudaEventRecord(ev1, st));
     int err = 0;
     CK(cudaMemcpyAsync(&err, ref->errFlag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -447,24 +456,17 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
     ref->covDirty = true;
     pt.lap("  assign: kernel round");
     if (err & (ERR_READ_LEN | ERR_READ_CHAR)) return fail(T1K_ERR_ARG, "read contains a character outside ACGTN or is too long");
-    if (err & ~(ERR_STORE | ERR_HITS)) return fail(T1K_ERR_UNSUPPORTED, "t1k_assign_batch:" + decode_err(err));
-    if (!(err & (ERR_STORE | ERR_HITS))) break;
-    // deferred read-ends (they added no coverage): -3 moves to the big-tile geometry, -2 waits for a larger store
+    if (err & ~ERR_STORE) return fail(T1K_ERR_UNSUPPORTED, "t1k_assign_batch:" + decode_err(err));
+    if (!(err & ERR_STORE)) break;
+    // deferred read-ends (they added no coverage) wait for a larger store
     hRet.resize(n);
     CK(cudaMemcpy(hRet.data(), a->readRet.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
-    std::vector<u32> next[2];
-    auto scan = [&](u32 i, int c) {
-      if (hRet[i] == -2) next[c].push_back(i);
-      else if (hRet[i] == -3) { if (c == 1) return false; next[1].push_back(i); }
-      return true;
-    };
-    bool ok = true;
-    if (first) { for (u32 i = 0; i < n; ++i) ok &= scan(i, 0); }
-    else for (int c = 0; c < 2; ++c) for (size_t k = 0; k < todo[c].size(); ++k) ok &= scan(todo[c][k], c);
-    if (!ok) return fail(T1K_ERR_UNSUPPORTED, "t1k_assign_batch:" + decode_err(ERR_HITS));
+    std::vector<u32> next;
+    if (first) { for (u32 i = 0; i < n; ++i) if (hRet[i] == -2) next.push_back(i); }
+    else for (size_t k = 0; k < todo.size(); ++k) if (hRet[todo[k]] == -2) next.push_back(todo[k]);
     first = false;
-    todo[0].swap(next[0]); todo[1].swap(next[1]);
-    if (err & ERR_STORE) {
+    todo.swap(next);
+    {
       u64 newCap = cap * 2;
       if (newCap * sizeof(Rec) > (u64)(freeB * 0.9)) newCap = (u64)(freeB * 0.9) / sizeof(Rec);
       if (newCap <= cap + 1024 || round > 16) return fail(T1K_ERR_UNSUPPORTED, "overlap record store does not fit in device memory; use smaller batches");
@@ -478,7 +480,7 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
       cap = newCap; a->storeCap = cap;
       P.O.store = a->store.as<Rec>(); P.O.storeCap = cap;
     }
-    if (todo[0].empty() && todo[1].empty()) break;
+    if (todo.empty()) break;
   }
   unsigned long long used = 0;
   CK(cudaMemcpy(&used, a->storeCtr.p, 8, cudaMemcpyDeviceToHost));
@@ -494,13 +496,13 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
 int t1k_assignment_stats(const T1KAssignment *a, T1KAssignStats *out) {
   if (!a || !out) return fail(T1K_ERR_ARG, "t1k_assignment_stats: bad argument");
   out->postings = a->stats[0]; out->candidates = a->stats[1]; out->tiles = a->stats[2]; out->records = a->storeUsed;
-  out->ms_kernel = a->msKernel; out->grid_blocks = a->ref->gridBlocks[0]; out->hit_cap = a->ref->hitCap[0]; out->n_sm = a->ref->nSM;
+  out->ms_kernel = a->msKernel; out->grid_blocks = a->ref->gridBlocks; out->hit_cap = a->ref->hitCap; out->n_sm = a->ref->nSM;
   return T1K_OK;
 }
 
 void t1k_assignment_destroy(T1KAssignment *a) {
   if (!a) return;
-  if (a->ref) cudaSetDevice(a->ref->device);
+  cudaSetDevice(a->device);
   delete a;
 }
 
@@ -591,6 +593,7 @@ __global__ void k_missing_coverage(RefView R, const int32_t *covFinal, int32_t *
 
 int finalize_coverage(T1KRef *ref) {
   if (!ref->covDirty) return T1K_OK;
+  stale("coverage");
   k_cov_prefix<<<(ref->nAlleles + 127) / 128, 128, 0, ref->stream>>>(ref->R, ref->covFinal.as<int32_t>());
   CK(cudaGetLastError());
   ref->covDirty = false;
@@ -756,6 +759,7 @@ int t1k_pair_batch(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
   if (!ref || !a || !row_ptr || !entries || (n_frag > 0 && !end1)) return fail(T1K_ERR_ARG, "t1k_pair_batch: bad argument");
   static_assert(sizeof(T1KReadAssignment) == sizeof(HostEntry) && sizeof(HostEntry) == sizeof(PairEntry), "layout");
   CK(cudaSetDevice(ref->device));
+  stale("t1k_pair_batch");
   PairHost H;
   H.pin = &ref->pinEntries[0];
   if (int rc = pair_fragments(ref, a, end1, end2, has_n, n_frag, max_assign, true, H)) return rc;
@@ -787,6 +791,7 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   int dev;
   if (int rc = pick_device(device, &dev)) return rc;
   CK(cudaSetDevice(dev));
+  stale("t1k_em_run");
   const int G = p->n_groups, E = p->n_ec;
   const int64_t nnz = p->row_ptr[G];
   PhaseTimer pt;

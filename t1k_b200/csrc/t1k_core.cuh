@@ -49,6 +49,16 @@ constexpr int MAX_EMIT = 48;        // seed overlaps one (strand, allele) group 
 constexpr u64 M55 = 0x5555555555555555ull;
 
 struct Posting { u32 idx, off; };
+// The k-mer index as the device reads it.  The postings of one k-mer (allele, offset), which the reference keeps as one
+// list in allele order (KmerIndex.hpp:58-71), are regrouped by TILE (32 consecutive allele ids) and offset: one entry
+// says "this k-mer occurs at offset `off` in the alleles tile*32 + {bits of mask}".  Alleles of one gene are neighbours in
+// the reference file and share most k-mers at the same offset, so an entry stands for up to 32 postings: the index
+// shrinks from 8 B per posting towards 0.5 B, and a warp that sweeps the allele axis tile by tile with one lane per
+// allele gets its hits from one broadcast word per seed instead of a posting scatter.
+//   more = number of further entries of the same (k-mer, tile) that follow this one (other offsets: a k-mer repeated
+//   inside an allele, or alleles of the tile that carry an indel before it), in ascending offset order.
+struct alignas(16) KmerEntry { u32 tile, off, mask, more; };
+struct KmerInfo { u32 estart, pstart; };   // per k-mer code: first entry, first posting (posting COUNT drives the skip rule, SeqSet.hpp:1109)
 
 struct alignas(16) AlleleMeta { u64 wordOff; int32_t len; u32 hasN; };   // one 16-byte load instead of three dependent-free ones
 
@@ -58,8 +68,10 @@ struct RefView {
   const u64 *wordOff;    // [nAlleles] first word of allele
   const int32_t *len;    // [nAlleles]
   const u8 *hasN;        // [nAlleles] the allele holds at least one N (separator)
-  const u32 *kstart;     // [4^K + 1]
+  const u32 *kstart;     // [4^K + 1]   (host emulation / tests; the device reads kinfo + entries)
   const Posting *post;
+  const KmerInfo *kinfo; // [4^K + 1]
+  const KmerEntry *entries;
   int32_t *covDiff;      // range-add difference array, indexed by padded base (wordOff*32 + pos)
   int32_t *covPoint;     // point corrections
   int32_t nAlleles;
@@ -812,13 +824,13 @@ constexpr int FAST_MAX_LEN = 160;    // read length the fast path handles (5 wor
 // > 160 bases) returns false with nothing written and the caller runs chain_allele on the gathered hit list.
 // The same mismatch positions give ExtendOverlap (both overhangs lie on the diagonal) and the full-read alignment.
 // lcMemo: per-lane memo of IsOverlapLowComplex for the last (readStart, readEnd) of this strand (0 = empty).
-// hits/stride: the allele's gathered hit list (only consulted when one or two postings are not on the diagonal).
-T1K_HDN T1K_NOINLINE inline bool diag_fast(const RefView &R, const ReadView &Q, int strand01, int seqIdx, int n, const u32 *hits, int stride,
+// n: hits of the allele; d: seqOffset - readOffset of its FIRST hit (smallest readOffset, then smallest seqOffset);
+// onDiag / far: how many of the n hits lie on diagonal d / more than RADIUS diagonals away from it (the tile sweep counts
+// them while it streams the index entries; only consulted when one or two postings are not on the diagonal).
+T1K_HDN T1K_NOINLINE inline bool diag_fast(const RefView &R, const ReadView &Q, int strand01, int seqIdx, int n, int d, int onDiag, int far,
                               const u32 *stab, Cand &out, bool &emitted, u64 &bestStrandKey, u32 &lcMemo, const LaneScratch &S, int &err) {
   emitted = false;
   const int len = Q.len;
-  const u32 h0 = hits[0];
-  const int d = hit_b(h0) - hit_a(h0);
 #ifdef __CUDA_ARCH__
   const uint4 mt = *reinterpret_cast<const uint4 *>(R.meta + seqIdx);
   const u64 w0 = (u64)mt.x | ((u64)mt.y << 32);
@@ -904,14 +916,6 @@ T1K_HDN T1K_NOINLINE inline bool diag_fast(const RefView &R, const ReadView &Q, 
     // fewer than three hits, which are dropped (SeqSet.hpp:1399-1404): the result is the single-diagonal one.
     const int extra = n - cntSum;
     if (extra > 2) return false;
-    int far = 0, onDiag = 0;
-    T1K_NOUNROLL
-    for (int i = 0; i < n; ++i) {
-      const u32 h = hits[(size_t)i * stride];
-      const int dd = hit_b(h) - hit_a(h) - d;
-      onDiag += dd == 0;
-      far += dd > RADIUS || dd < -RADIUS;
-    }
     if (onDiag != cntSum || far != extra) return false;
   }
   T1K_COUNT(17, 1);

@@ -3,6 +3,8 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "t1k_core.cuh"
@@ -21,8 +23,39 @@ struct PackedRef {
   std::vector<AlleleMeta> meta;
   std::vector<u32> kstart;
   std::vector<Posting> post;
+  // the device's form of the index (see KmerEntry in t1k_core.cuh): per k-mer the postings regrouped by
+  // (tile of 32 consecutive alleles, offset) with one allele bit mask per entry
+  std::vector<KmerInfo> kinfo;        // [4^K + 1]
+  std::vector<KmerEntry> entries;
   size_t totalWords = 0;
 };
+
+// postings (sorted by k-mer, allele, offset) -> tile entries sorted by (k-mer, tile, offset).  An allele's hits of one
+// k-mer stay in ascending offset order, which is the order GetHitsFromRead appends them in (SeqSet.hpp:1124-1150).
+inline void build_tile_index(PackedRef &P) {
+  const size_t nK = (size_t)1 << (2 * KMER);
+  P.kinfo.assign(nK + 1, KmerInfo{0, 0});
+  P.entries.clear();
+  std::vector<std::pair<u32, u32> > cur;      // (offset, allele bit) of the tile being collected
+  for (size_t c = 0; c < nK; ++c) {
+    P.kinfo[c].estart = (u32)P.entries.size(); P.kinfo[c].pstart = P.kstart[c];
+    const u32 lo = P.kstart[c], hi = P.kstart[c + 1];
+    for (u32 j = lo; j < hi;) {
+      const u32 tile = P.post[j].idx >> 5;
+      cur.clear();
+      for (; j < hi && (P.post[j].idx >> 5) == tile; ++j) cur.push_back(std::make_pair(P.post[j].off, P.post[j].idx & 31u));
+      std::stable_sort(cur.begin(), cur.end(), [](const std::pair<u32, u32> &x, const std::pair<u32, u32> &y) { return x.first < y.first; });
+      const size_t first = P.entries.size();
+      for (size_t q = 0; q < cur.size(); ++q) {
+        if (q == 0 || cur[q].first != cur[q - 1].first) { KmerEntry e; e.tile = tile; e.off = cur[q].first; e.mask = 0; e.more = 0; P.entries.push_back(e); }
+        P.entries.back().mask |= 1u << cur[q].second;
+      }
+      const size_t cnt = P.entries.size() - first;
+      for (size_t q = 0; q < cnt; ++q) P.entries[first + q].more = (u32)(cnt - 1 - q);
+    }
+  }
+  P.kinfo[nK].estart = (u32)P.entries.size(); P.kinfo[nK].pstart = P.kstart[nK];
+}
 
 inline void set2(std::vector<u64> &plane, u64 w0, int pos, u64 v) { plane[w0 + (pos >> 5)] |= v << ((pos & 31) * 2); }
 
@@ -86,6 +119,7 @@ inline bool pack_reference(int32_t n, const char *bases, const int64_t *off, con
   }
   P.meta.resize(n);
   for (int i = 0; i < n; ++i) { P.meta[i].wordOff = P.wordOff[i]; P.meta[i].len = P.len[i]; P.meta[i].hasN = P.hasN[i]; }
+  build_tile_index(P);
   return true;
 }
 

@@ -43,9 +43,10 @@ def _reads_to_batch(reads):
 class Assignment:
     """Per-read-end overlap lists resident on the device (result of SeqSet.AssignRead)."""
 
-    def __init__(self, handle, n):
+    def __init__(self, handle, n, owner=None):
         self.h = handle
         self.n = n
+        self._owner = owner       # the SeqSet whose reference the lists point into stays alive as long as they do
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -99,7 +100,7 @@ class SeqSet:
         w = np.ones(n, dtype=np.int32) if weights is None else np.ascontiguousarray(weights, dtype=np.int32)
         h = C.c_void_p()
         L.check(L.lib().t1k_assign_batch(self.h, L.ptr(bases), L.ptr(off), L.ptr(lens), L.ptr(w), n, C.byref(h)))
-        return Assignment(h, n)
+        return Assignment(h, n, self)
 
     def ReadAssignmentToFragmentAssignment(self, assignment: Assignment, end1, end2=None, has_n=None, max_assign=2000,
                                            with_assigned=False):

@@ -39,7 +39,7 @@ Emu *emu_create(int32_t n, const char *bases, const int64_t *off, const int32_t 
   R.seq2 = e->P.seq2.data(); R.n2 = e->P.n2.data(); R.ex2 = e->P.ex2.data();
   R.wordOff = e->P.wordOff.data(); R.len = e->P.len.data(); R.hasN = e->P.hasN.data(); R.meta = e->P.meta.data();
   e->simThr.resize(2 * SIM_DEN); sim_threshold_table(sim, e->simThr.data()); R.simThr = e->simThr.data();
-  R.kstart = e->P.kstart.data(); R.post = e->P.post.data();
+  R.kstart = e->P.kstart.data(); R.post = e->P.post.data(); R.kinfo = e->P.kinfo.data(); R.entries = e->P.entries.data();
   R.covDiff = e->covDiff.data(); R.covPoint = e->covPoint.data();
   R.nAlleles = n; R.sim = sim; R.relax = relax;
   e->scratch.assign(SCR_BYTES, 0);
@@ -77,7 +77,9 @@ int32_t emu_align(const char *t, int32_t lent, const char *p, int32_t lenp, int8
   return n;
 }
 
-// SeqSet::AssignRead through the product's lane code
+// SeqSet::AssignRead through the product's lane code.  The warp orchestration of k_assign (t1k_kernels.cuh) is restated
+// sequentially: seeds with the skip rule, the sweep over allele tiles of the tile index (KmerEntry) with the streaming
+// per-allele counters of the mismatch-mask path, the hit list only for the alleles that path declines.
 int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, int32_t cap, int32_t *errOut) {
   const RefView &R = E->R;
   int len = (int)strlen(read);
@@ -93,54 +95,68 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
   for (int pass = 0; pass < 2; ++pass) {
     int strand01 = pass == 0 ? 1 : 0;
     ReadView Q; Q.seq2 = planes[pass * 2]; Q.n2 = planes[pass * 2 + 1]; Q.len = len; Q.anyN = strchr(read, 'N') != NULL;
-    // seed selection (GetHitsFromRead skip rule), then group hits per allele
-    std::map<u32, std::vector<u32> > groups;
+    // seed selection (GetHitsFromRead skip rule)
     u32 prev = 0; int skip = 0;
     const int P = len - KMER + 1;
-    u8 seedA[256]; int nS = 0;
+    u8 seedA[256]; u32 cur[256], end[256]; int nS = 0;
     bool strandFast = !Q.anyN && len <= FAST_MAX_LEN && !E->noFast;     // the kernel's eligibility rule (t1k_kernels.cuh)
     for (int a = 0; a < P; ++a) {
       u32 code = (u32)(fetch32(Q.seq2, a) & 0x3FFFFF);
       bool valid = (fetch32(Q.n2, a) & 0x155555) == 0;
       if (a == 0 || prev != code) {
-        u32 lo = 0, hi = 0;
-        if (valid) { lo = R.kstart[code]; hi = R.kstart[code + 1]; }
-        int size = (int)(hi - lo);
+        u32 lo = 0, hi = 0; int size = 0;
+        if (valid) { lo = R.kinfo[code].estart; hi = R.kinfo[code + 1].estart; size = (int)(R.kinfo[code + 1].pstart - R.kinfo[code].pstart); }
         if (size >= 100 && a != 0 && a != P - 1 && skip < KMER / 2) { ++skip; continue; }
         skip = 0;
-        if (size > 0) { seedA[nS++] = (u8)a; if (kmer_homopolymer(code)) strandFast = false; }
-        for (u32 j = lo; j < hi; ++j) groups[R.post[j].idx].push_back((u32)a | (R.post[j].off << 8));
+        if (size > 0) { seedA[nS] = (u8)a; cur[nS] = lo; end[nS] = hi; ++nS; if (kmer_homopolymer(code)) strandFast = false; }
       }
       prev = code;
     }
     u32 stab[256];
     if (strandFast) seed_table_build(seedA, nS, len, stab);
     u32 lcMemo = 0;
-    for (std::map<u32, std::vector<u32> >::iterator it = groups.begin(); it != groups.end(); ++it) {
-      int nEmit = 0;
-      std::vector<u32> &h = it->second;
-      if ((int)h.size() < 3) continue;
-      t1k_emu_counters[20] += 1;
-      if (strandFast) {
-        Cand fc; bool emitted = false;
-        if (diag_fast(R, Q, strand01, (int)it->first, (int)h.size(), h.data(), 1, stab, fc, emitted, bestKey, lcMemo, S, err)) {
-          if (emitted) cands.push_back(fc);
-          continue;
+    for (;;) {
+      u32 T = 0xffffffffu;
+      for (int k = 0; k < nS; ++k) if (cur[k] < end[k]) T = std::min(T, R.entries[cur[k]].tile);
+      if (T == 0xffffffffu) break;
+      for (int lane = 0; lane < 32; ++lane) {
+        // sweep 1: the allele's hit count, first diagonal, hits on / far off that diagonal
+        int n = 0, d0 = 0, onDiag = 0, far = 0;
+        std::vector<u32> h;
+        for (int k = 0; k < nS; ++k) {
+          if (cur[k] >= end[k] || R.entries[cur[k]].tile != T) continue;
+          const u32 more = R.entries[cur[k]].more;
+          for (u32 j = 0; j <= more; ++j) {
+            const KmerEntry &e = R.entries[cur[k] + j];
+            if (!((e.mask >> lane) & 1u)) continue;
+            const int dg = (int)e.off - (int)seedA[k];
+            if (n == 0) d0 = dg;
+            const int dd = dg - d0;
+            ++n; onDiag += dd == 0; far += dd > RADIUS || dd < -RADIUS;
+            h.push_back((u32)seedA[k] | (e.off << 8));        // (sweep 2 of the kernel: only for declined alleles)
+          }
         }
-      }
-      if (strandFast && getenv("EMU_DEBUG")) {
-        static int shown = 0;
-        bool one = true; for (size_t q = 1; q < h.size(); ++q) if (hit_b(h[q]) - hit_a(h[q]) != hit_b(h[0]) - hit_a(h[0])) one = false;
-        if (one && shown < 5) { ++shown;
-          fprintf(stderr, "allele %d n=%d d=%d hits:", (int)it->first, (int)h.size(), hit_b(h[0]) - hit_a(h[0]));
-          for (size_t q = 0; q < h.size(); ++q) fprintf(stderr, " %d", hit_a(h[q]));
-          fprintf(stderr, "\n seeds:"); for (int q = 0; q < nS; ++q) fprintf(stderr, " %d", seedA[q]);
-          fprintf(stderr, "\n");
+        if (n < 3) continue;
+        const int seqIdx = (int)(T * 32 + lane);
+        int nEmit = 0;
+        t1k_emu_counters[20] += 1;
+        if (strandFast) {
+          Cand fc; bool emitted = false;
+          if (diag_fast(R, Q, strand01, seqIdx, n, d0, onDiag, far, stab, fc, emitted, bestKey, lcMemo, S, err)) {
+            if (emitted) {
+              if (!(fc.flags & CF_PRE)) { extend_cand<false>(R, Q, fc, S, err); fc.flags |= CF_PRE; }     // a long or dirty overhang
+              cands.push_back(fc);
+            }
+            continue;
+          }
         }
+        chain_allele(R, Q, strand01, seqIdx, h.data(), 1, n, S, nEmit, bestKey, err);
+        if (nEmit > 1) sort_emitted(S.emit(), nEmit);
+        // the kernel extends the seed overlaps of the hit-list path right where they are emitted
+        std::vector<Cand> em(S.emit(), S.emit() + nEmit);
+        for (int k = 0; k < nEmit; ++k) { Cand c = em[k]; c.mmPos = 0; extend_cand<false>(R, Q, c, S, err); c.flags |= CF_PRE; cands.push_back(c); }
       }
-      chain_allele(R, Q, strand01, (int)it->first, h.data(), 1, (int)h.size(), S, nEmit, bestKey, err);
-      if (nEmit > 1) sort_emitted(S.emit(), nEmit);
-      for (int k = 0; k < nEmit; ++k) { Cand c = S.emit()[k]; c.mmPos = 0; cands.push_back(c); }
+      for (int k = 0; k < nS; ++k) if (cur[k] < end[k] && R.entries[cur[k]].tile == T) cur[k] += 1 + R.entries[cur[k]].more;
     }
     if (pass == 0) nFwd = (int)cands.size();
   }
@@ -151,7 +167,6 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
   // pass 1: extension + first failing key
   u64 fKey = ~0ull; int fIdx = 0x7fffffff;
   for (int i = c0; i < c1; ++i) {
-    if (!(cands[i].flags & CF_PRE)) extend_cand<false>(R, Q, cands[i], S, err);
     Cand &c = cands[i];
     if (!(c.flags & CF_SEP) && !(c.flags & CF_RET)) {
       u64 k = cand_key_pre(c);
