@@ -26,7 +26,7 @@
 
 // host-emulation-only call-site counters (tests/host_emu.cpp); compiled out of the device build
 #if !defined(__CUDACC__) && defined(T1K_EMU_COUNTERS)
-extern long long t1k_emu_counters[32];
+extern long long t1k_emu_counters[128];
 #define T1K_COUNT(i, v) (t1k_emu_counters[i] += (v))
 #else
 #define T1K_COUNT(i, v) ((void)0)
@@ -827,9 +827,15 @@ constexpr int FAST_MAX_LEN = 160;    // read length the fast path handles (5 wor
 // n: hits of the allele; d: seqOffset - readOffset of its FIRST hit (smallest readOffset, then smallest seqOffset);
 // onDiag / far: how many of the n hits lie on diagonal d / more than RADIUS diagonals away from it (the tile sweep counts
 // them while it streams the index entries; only consulted when one or two postings are not on the diagonal).
-T1K_HDN T1K_NOINLINE inline bool diag_fast(const RefView &R, const ReadView &Q, int strand01, int seqIdx, int n, int d, int onDiag, int far,
-                              const u32 *stab, Cand &out, bool &emitted, u64 &bestStrandKey, u32 &lcMemo, const LaneScratch &S, int &err) {
+// hot: the caller runs this for all 32 alleles of a tile at once; work that only a few alleles need and that would stall
+// the warp — the GlobalAlignment of a long or dirty gap, a long or dirty overhang for ExtendOverlap — is not done: the
+// function returns DF_DEFER (nothing written, the hit-count certificate already passed) and the caller queues the allele
+// and runs it again with hot = false together with 31 other deferred alleles.
+enum { DF_DECLINED = 0, DF_DONE = 1, DF_DEFER = 2 };
+T1K_HDN T1K_NOINLINE inline int diag_fast(const RefView &R, const ReadView &Q, int strand01, int seqIdx, int n, int d, int onDiag, int far,
+                              const u32 *stab, bool hot, Cand &out, bool &emitted, u64 &bestStrandKey, u32 &lcMemo, const LaneScratch &S, int &err) {
   emitted = false;
+  bool needCold = false;
   const int len = Q.len;
 #ifdef __CUDA_ARCH__
   const uint4 mt = *reinterpret_cast<const uint4 *>(R.meta + seqIdx);
@@ -843,7 +849,7 @@ T1K_HDN T1K_NOINLINE inline bool diag_fast(const RefView &R, const ReadView &Q, 
 #endif
   const int pLo = d < 0 ? -d : 0, pHi = imin(len, clen - d);
   const int W = pHi - pLo;
-  if (W < KMER) return false;
+  if (W < KMER) return DF_DECLINED;
   // All allele words of the window in one round trip (the loads are independent; the window spans <= 5 chunks of 32
   // bases = <= 6 words, and the pad word after the allele makes word nW readable), then the mismatch masks of the chunks.
   const u64 *tp = R.seq2 + w0 + ((pLo + d) >> 5);
@@ -852,7 +858,7 @@ T1K_HDN T1K_NOINLINE inline bool diag_fast(const RefView &R, const ReadView &Q, 
   u64 tw[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) tw[j] = j <= nW ? tp[j] : 0;
-  if (alleleHasN && n_in_range(R.n2 + w0, pLo + d, pHi - 1 + d)) return false;
+  if (alleleHasN && n_in_range(R.n2 + w0, pLo + d, pHi - 1 + d)) return DF_DECLINED;
   u64 t0 = tw[0], t1 = tw[1], t2 = tw[2], t3 = tw[3], t4 = tw[4], t5 = tw[5];     // word queue: later words move up
   int exMm = 0;
   // streaming state over the mismatches (ascending) and the closing sentinel pHi
@@ -890,9 +896,13 @@ T1K_HDN T1K_NOINLINE inline bool diag_fast(const RefView &R, const ReadView &Q, 
             if (g > 32 || mmRun > 3) {
               // a long or dirty gap: the same GlobalAlignment the hit-list walk would run (certificates, else the band
               // DP), the rest of the allele stays on this path.  No N in the window => the N planes are not consulted.
+              if (hot) needCold = true;
+              else {
               AlleleView T;
               T.seq = R.seq2 + w0; T.n2 = R.n2 + w0; T.ex2 = R.ex2 + w0; T.len = clen; T.hasN = alleleHasN; T.useN = false;
+              T1K_COUNT(32, 1); T1K_COUNT(33, g > 32); T1K_COUNT(40 + (mmRun > 15 ? 15 : mmRun), 1); T1K_COUNT(60 + (g / 8 > 15 ? 15 : g / 8), 1);
               gapMatches += align_matches_cold(T, lastL + KMER + d, g, Q, lastL + KMER, g, S, err);
+              }
             } else gapMatches += g - mmRun;
           }
           hitLen += l - f + KMER;
@@ -908,19 +918,20 @@ T1K_HDN T1K_NOINLINE inline bool diag_fast(const RefView &R, const ReadView &Q, 
   }
   T1K_COUNT(16, 1);
   if (!ok) T1K_COUNT(21, 1); else if (cntSum < n) T1K_COUNT(22, 1); else if (cntSum > n) T1K_COUNT(23, 1);
-  if (!ok || cntSum > n) return false;
+  if (!ok || cntSum > n) return DF_DECLINED;
   if (cntSum < n) {
     // One or two postings off the diagonal (a k-mer of the read that also occurs elsewhere in the allele).  If every one
     // of them lies more than RADIUS diagonals away, the diagonal sort puts a cluster break on both sides of the main
     // diagonal (SeqSet.hpp:1369-1374), so its cluster is exactly the seeds found above, and the strays form clusters of
     // fewer than three hits, which are dropped (SeqSet.hpp:1399-1404): the result is the single-diagonal one.
     const int extra = n - cntSum;
-    if (extra > 2) return false;
-    if (onDiag != cntSum || far != extra) return false;
+    if (extra > 2) return DF_DECLINED;
+    if (onDiag != cntSum || far != extra) return DF_DECLINED;
   }
   T1K_COUNT(17, 1);
   // ---- from here on the result is the reference's: the tail of consume_chain<true>
-  if (hitLen < HIT_LEN_REQ) return true;
+  if (hitLen < HIT_LEN_REQ) return DF_DONE;
+  if (needCold) return DF_DEFER;
   const int re = lastL + KMER - 1, mmRight = mmRun;
   const u64 sk = strand_key(2 * hitLen, re - rs, seqIdx, strand01);
   if (sk > bestStrandKey) bestStrandKey = sk;
@@ -931,15 +942,17 @@ T1K_HDN T1K_NOINLINE inline bool diag_fast(const RefView &R, const ReadView &Q, 
     if ((lcMemo & 0x1FFFFu) != key) lcMemo = key | (low_complex(Q, rs, re) ? 0x20000u : 0u);
     if (lcMemo & 0x20000u) below = 0.0 < R.sim;
   }
-  if (below) return true;
+  if (below) return DF_DONE;
+  // ---- ExtendOverlap on the same diagonal (SeqSet.hpp:1994-2100): overhangs [pLo, rs) and (re, pHi)
+  const int lo = rs - pLo, ro = pHi - 1 - re;
+  const bool hotExt = (lo <= 32 && mmLeft <= 3) && (ro <= 32 && mmRight <= 3);
+  if (hot && !hotExt) return DF_DEFER;
   Cand &c = out;
   c.seqIdx = seqIdx; c.seqStart = rs + d; c.seqEnd = re + d;
   c.readStart = (u8)rs; c.readEnd = (u8)re; c.strand01 = (u8)strand01; c.flags = 0;
   c.matchCnt = (u16)mc; c.pad = 0; c.mmPos = 0;
   emitted = true;
-  // ---- ExtendOverlap on the same diagonal (SeqSet.hpp:1994-2100): overhangs [pLo, rs) and (re, pHi)
-  const int lo = rs - pLo, ro = pHi - 1 - re;
-  if ((lo <= 32 && mmLeft <= 3) && (ro <= 32 && mmRight <= 3)) {
+  if (hotExt) {
     const int mcE = mc + 2 * (lo - mmLeft + ro - mmRight);
     const int leftClip = pLo, rightClip = len - pHi;
     u8 flags = CF_PRE;
@@ -955,7 +968,7 @@ T1K_HDN T1K_NOINLINE inline bool diag_fast(const RefView &R, const ReadView &Q, 
     if (mmTot <= 3) { T1K_COUNT(19, 1); flags |= CF_FA; c.mmPos = mmPos | ((u32)mmTot << 24) | ((u32)exMm << 26); }
     c.flags = flags;
   }
-  return true;
+  return DF_DONE;
 }
 
 // full-read alignment of a CF_FA candidate: coverage and the exon-relaxed count from the stored mismatch positions

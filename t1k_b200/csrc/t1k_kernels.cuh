@@ -116,14 +116,18 @@ __global__ void k_pack_reads(const char *bases, const u64 *off, const u32 *len, 
 //   seq/nn    the strand's 2-bit planes
 //   cur[S], end[S]  entry cursor / end of every seed; stab[256] seed table of diag_fast; bits[16] its bit masks
 //   seedA[S]  read offset of every seed; adv[S] entries the current tile consumed from the seed
+//   q0[64], q1[64]  alleles whose mismatch-mask evaluation was deferred (DF_DEFER): {allele, diagonal, hits, hits on the
+//             diagonal}, {hits far off it, reserved candidate slot}; run 32 at a time
 struct WarpSmem {
-  uint4 *ent;
+  uint4 *ent, *q0;
   u64 *seq, *nn;
+  uint2 *q1;
   u32 *cur, *end, *stab, *bits;
   u16 *seedA, *adv;
 };
+constexpr int DEFER_CAP = 64;
 __host__ __device__ inline size_t warp_smem_bytes(int seedCap) {
-  return ((size_t)seedCap * (16 + 4 + 4 + 2 + 2) + 2 * RWORDS * 8 + 256 * 4 + 16 * 4 + 15) & ~(size_t)15;
+  return ((size_t)seedCap * (16 + 4 + 4 + 2 + 2) + DEFER_CAP * 24 + 2 * RWORDS * 8 + 256 * 4 + 16 * 4 + 15) & ~(size_t)15;
 }
 
 // returns whether the read holds an N
@@ -235,6 +239,31 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
         if (c.flags & CF_RET) { if (pair_less(k, i, rKey, rIdx)) { rKey = k; rIdx = i; } }
         else if (pair_less(k, i, fKey, fIdx)) { fKey = k; fIdx = i; }
       };
+      // the deferred alleles, `take` at a time with all lanes busy: the whole evaluation incl. dirty gaps and overhangs
+      int qn = 0;
+      auto run_deferred = [&](int take) {
+        if (lane < take) {
+          const uint4 e0 = W.q0[qn - take + lane];
+          const uint2 e1 = W.q1[qn - take + lane];
+          Cand c;
+          bool em = false;
+          const int df = diag_fast(R, Qv, strand01, (int)e0.x, (int)e0.z, (int)e0.y, (int)e0.w, (int)e1.x, W.stab, false, c, em, laneKey, lcMemo, S, err);
+          if (df == DF_DECLINED) err |= ERR_SCRATCH;        // (cannot happen: the hit-count certificate passed in hot mode)
+          if (df == DF_DONE && em) {
+            if (!(c.flags & CF_PRE)) { extend_cand<false>(R, Qv, c, S, err); c.flags |= CF_PRE; }     // a long or dirty overhang
+            cands[e1.y] = c;
+            note(c, (int)e1.y);
+          } else {
+            Cand v;                                         // nothing to emit: the reserved slot stays void
+            v.seqIdx = (int32_t)e0.x; v.seqStart = v.seqEnd = 0; v.readStart = v.readEnd = 0; v.strand01 = (u8)strand01; v.flags = CF_SEP;
+            v.matchCnt = 0; v.pad = 0; v.eSeqStart = v.eSeqEnd = 0; v.eReadStart = v.eReadEnd = v.leftClip = v.rightClip = 0;
+            v.eMatchCnt = 0; v.relaxed = 0; v.mmPos = 0;
+            cands[e1.y] = v;
+          }
+        }
+        qn -= take;
+        __syncwarp();
+      };
       // ---- allele tiles (32 consecutive allele ids) in ascending order: the smallest tile any seed still has an entry for
       T1K_NOUNROLL
       for (;;) {
@@ -290,13 +319,12 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
         // ---- lane per allele: the mismatch-mask path first (uniform work); the few alleles it declines get their hit list
         int nEmit = 0;
         Cand fc;
-        bool fastEmit = false, handled = n < 3;
+        bool fastEmit = false, handled = n < 3, defer = false;
         if (strandFast && n >= 3) {
-          handled = diag_fast(R, Qv, strand01, (int)(T * 32 + lane), n, d0, onDiag, far, W.stab, fc, fastEmit, laneKey, lcMemo, S, err);
-          if (fastEmit) {
-            nEmit = 1;
-            if (!(fc.flags & CF_PRE)) { extend_cand<false>(R, Qv, fc, S, err); fc.flags |= CF_PRE; }     // a long or dirty overhang
-          }
+          const int df = diag_fast(R, Qv, strand01, (int)(T * 32 + lane), n, d0, onDiag, far, W.stab, true, fc, fastEmit, laneKey, lcMemo, S, err);
+          handled = df != DF_DECLINED;
+          defer = df == DF_DEFER;          // needs work the other lanes do not: queued, its candidate slot reserved
+          if (fastEmit || defer) nEmit = 1;
         }
         if (__any_sync(FULL, !handled)) {
           // sweep 2: hit lists (readOffset | seqOffset << 8, in (readOffset, seqOffset) order) of the declined alleles into the
@@ -343,16 +371,25 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
           if (nCand + tot > P.candCap) err |= ERR_CAND;
           else {
             const int at = (int)nCand + incl - nEmit;
-            if (fastEmit) { cands[at] = fc; note(fc, at); }
+            const unsigned balD = __ballot_sync(FULL, defer);
+            if (defer) {
+              const int q = qn + __popc(balD & ((1u << lane) - 1));
+              W.q0[q] = make_uint4(T * 32 + lane, (u32)d0, (u32)n, (u32)onDiag);
+              W.q1[q] = make_uint2((u32)far, (u32)at);
+            } else if (fastEmit) { cands[at] = fc; note(fc, at); }
             else {
               const Cand *em = S.emit();
               T1K_NOUNROLL
               for (int j = 0; j < nEmit; ++j) { const Cand c = em[j]; cands[at + j] = c; note(c, at + j); }
             }
             nCand += tot;
+            qn += __popc(balD);
           }
         }
+        if (qn >= 32) { __syncwarp(); run_deferred(32); }
       }
+      T1K_NOUNROLL
+      while (qn > 0) { __syncwarp(); run_deferred(min(qn, 32)); }
       bestKey = max(bestKey, warp_max_u64(laneKey));
       warp_min_pair(fKey, fIdx);
       warp_min_pair(rKey, rIdx);
@@ -519,9 +556,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_assign(AssignPar
   const int SC = P.seedCap;
   u8 *sm = (u8 *)t1k_smem + (size_t)warp * warp_smem_bytes(SC);
   WarpSmem W;
-  W.ent = (uint4 *)sm;
-  W.seq = (u64 *)(W.ent + SC); W.nn = W.seq + RWORDS;
-  W.cur = (u32 *)(W.nn + RWORDS); W.end = W.cur + SC; W.stab = W.end + SC; W.bits = W.stab + 256;
+  W.ent = (uint4 *)sm; W.q0 = W.ent + SC;
+  W.seq = (u64 *)(W.q0 + DEFER_CAP); W.nn = W.seq + RWORDS;
+  W.q1 = (uint2 *)(W.nn + RWORDS);
+  W.cur = (u32 *)(W.q1 + DEFER_CAP); W.end = W.cur + SC; W.stab = W.end + SC; W.bits = W.stab + 256;
   W.seedA = (u16 *)(W.bits + 16); W.adv = W.seedA + SC;
   LaneScratch S; S.base = P.laneScratch + (gwarp * 32 + lane) * (size_t)SCR_BYTES;
   Cand *cands = P.candBuf + gwarp * (size_t)P.candCap;

@@ -11,7 +11,7 @@
 #include "../t1k_b200/csrc/t1k_core.cuh"
 #include "../t1k_b200/csrc/t1k_host.hpp"
 
-long long t1k_emu_counters[32];
+long long t1k_emu_counters[128];
 using namespace t1k;
 
 struct Emu {
@@ -142,7 +142,14 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
         t1k_emu_counters[20] += 1;
         if (strandFast) {
           Cand fc; bool emitted = false;
-          if (diag_fast(R, Q, strand01, seqIdx, n, d0, onDiag, far, stab, fc, emitted, bestKey, lcMemo, S, err)) {
+          // the kernel's two-speed protocol: every allele of a tile in hot mode; the deferred ones again, in full mode
+          int df = diag_fast(R, Q, strand01, seqIdx, n, d0, onDiag, far, stab, true, fc, emitted, bestKey, lcMemo, S, err);
+          if (df == DF_DEFER) {
+            t1k_emu_counters[34] += 1;
+            df = diag_fast(R, Q, strand01, seqIdx, n, d0, onDiag, far, stab, false, fc, emitted, bestKey, lcMemo, S, err);
+            if (df != DF_DONE) err |= 1 << 20;          // a deferred allele never declines
+          }
+          if (df == DF_DONE) {
             if (emitted) {
               if (!(fc.flags & CF_PRE)) { extend_cand<false>(R, Q, fc, S, err); fc.flags |= CF_PRE; }     // a long or dirty overhang
               cands.push_back(fc);
