@@ -200,9 +200,10 @@ struct T1KRef {
   DevMem seq2, n2, ex2, dWordOff, dLen, dHasN, dMeta, dSimThr, kinfo, entries, covDiff, covPoint, covFinal;
   RefView R;
   cudaStream_t stream = nullptr;
-  // launch state of k_assign, sized on first use
-  DevMem candBuf, laneScratch, hitBuf, workCtr, errFlag, stats;
-  u32 candCap = 0;
+  // launch state of the AssignRead kernels (k_seed / k_deferred / k_passes / k_align), sized on first use
+  DevMem candPool, laneScratch, hitBuf, workCtr, errFlag, stats, dq, aq, qCtr;
+  u32 candCap = 0, dqCap = 0, aqCap = 0;
+  u64 arenaCands = 0;
   int gridBlocks = 0, hitCap = 0, seedCap = 0;
   int occ = 4;
   size_t scratchWarps = 0;
@@ -312,37 +313,48 @@ int t1k_ref_n_alleles(const T1KRef *ref) { return ref ? ref->nAlleles : 0; }
 
 namespace {
 
-// persistent launch geometry of k_assign for reads up to maxLen bases
-const void *assign_kernel(int occ) {
-  return occ >= 6 ? (const void *)k_assign<6> : occ == 5 ? (const void *)k_assign<5> : occ == 4 ? (const void *)k_assign<4>
-       : occ == 3 ? (const void *)k_assign<3> : (const void *)k_assign<2>;
+// persistent launch geometry of the AssignRead kernels for reads up to maxLen bases
+const void *seed_kernel(int occ) {
+  return occ >= 8 ? (const void *)k_seed<8> : occ == 7 ? (const void *)k_seed<7> : occ == 6 ? (const void *)k_seed<6> : occ == 5 ? (const void *)k_seed<5>
+       : occ == 4 ? (const void *)k_seed<4> : occ == 3 ? (const void *)k_seed<3> : (const void *)k_seed<2>;
 }
 int setup_assign_launch(T1KRef *r, int maxLen) {
   int seedCap = std::max(64, (maxLen - KMER + 1 + 31) & ~31);
-  // resident blocks per SM the kernel is compiled for (register budget): T1K_ASSIGN_OCC
+  // resident blocks per SM k_seed is compiled for (register budget): T1K_ASSIGN_OCC
   int occ = 4;
   if (const char *env = getenv("T1K_ASSIGN_OCC")) occ = atoi(env);
-  if (occ < 2 || occ > 6) occ = 4;
+  if (occ < 2 || occ > 8) occ = 4;
   int hitCap = 1024;     // hits of one allele the hit-list path holds (HBM scratch; a 255-base read has <= 245 seeds)
   if (const char *env = getenv("T1K_HIT_CAP")) hitCap = std::max(64, atoi(env));
   if (r->gridBlocks && seedCap <= r->seedCap && occ == r->occ && hitCap == r->hitCap) return T1K_OK;
   r->occ = occ;
-  const void *kfn = assign_kernel(occ);
+  const void *kfn = seed_kernel(occ);
   const size_t smem = warp_smem_bytes(seedCap) * WARPS_PER_BLOCK;
   CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int perSM = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kfn, WARPS_PER_BLOCK * 32, smem));
-  if (perSM < 1) return fail(T1K_ERR_UNSUPPORTED, "k_assign does not fit on an SM");
+  if (perSM < 1) return fail(T1K_ERR_UNSUPPORTED, "k_seed does not fit on an SM");
   r->seedCap = seedCap; r->hitCap = hitCap;
   r->gridBlocks = std::min(perSM, occ) * r->nSM;
   const size_t warps = (size_t)r->gridBlocks * WARPS_PER_BLOCK;
   u64 cap = 2ull * (u64)r->nAlleles + 2048;
   if (cap > (1u << 20)) cap = 1u << 20;
   r->candCap = (u32)cap;
+  // candidate pool: one arena per k_seed warp; a warp takes read-ends while the arena can hold a worst-case read-end
+  u64 arena = std::max<u64>(cap, ((u64)4 << 20) / sizeof(Cand));
+  if (const char *env = getenv("T1K_ARENA_CANDS")) arena = std::max<u64>(cap, strtoull(env, nullptr, 10));
+  if (warps * arena >= ((u64)1 << 32)) arena = (((u64)1 << 32) - 1) / warps;
+  if (arena < cap) return fail(T1K_ERR_UNSUPPORTED, "candidate pool: too many alleles for this launch geometry");
+  r->arenaCands = arena;
   r->scratchWarps = warps;
-  CK(r->candBuf.alloc(warps * r->candCap * sizeof(Cand)));
+  r->dqCap = 16u << 20; r->aqCap = 32u << 20;      // 512 MB each; a full queue is not an error (the work is done in place)
+  if (const char *env = getenv("T1K_QUEUE_ITEMS")) r->dqCap = r->aqCap = (u32)std::max(0l, atol(env));
+  CK(r->candPool.alloc(warps * arena * sizeof(Cand)));
   CK(r->laneScratch.alloc(warps * 32 * (size_t)SCR_BYTES));
   CK(r->hitBuf.alloc(warps * (size_t)hitCap * 32 * sizeof(u32)));
+  CK(r->dq.alloc(std::max<size_t>(1, r->dqCap) * sizeof(DeferItem)));
+  CK(r->aq.alloc(std::max<size_t>(1, r->aqCap) * sizeof(AlignItem)));
+  CK(r->qCtr.alloc(2 * sizeof(unsigned int)));
   CK(r->workCtr.alloc(sizeof(unsigned int)));
   CK(r->errFlag.alloc(sizeof(int)));
   CK(r->stats.alloc(4 * sizeof(unsigned long long)));
@@ -416,7 +428,13 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   P.O.readOff = a->readOff.as<u64>(); P.O.readCnt = a->readCnt.as<u32>(); P.O.readRet = a->readRet.as<int32_t>(); P.O.readTop = a->readTop.as<u32>();
   P.O.maxCnt = a->dMaxCnt.as<u32>();
   P.O.err = ref->errFlag.as<int>(); P.O.stats = ref->stats.as<unsigned long long>();
-  P.candBuf = ref->candBuf.as<Cand>(); P.candCap = ref->candCap; P.laneScratch = ref->laneScratch.as<u8>();
+  P.candPool = ref->candPool.as<Cand>(); P.arenaCands = ref->arenaCands; P.candCap = ref->candCap; P.laneScratch = ref->laneScratch.as<u8>();
+  DevMem dState, dStab;
+  CK(dState.alloc((size_t)n * sizeof(ReadState))); CK(dStab.alloc((size_t)n * 2 * 256 * sizeof(u32)));
+  P.state = dState.as<ReadState>(); P.stabBuf = dStab.as<u32>();
+  P.dq = ref->dq.as<DeferItem>(); P.dqCap = ref->dqCap; P.dqCtr = ref->qCtr.as<unsigned int>();
+  P.aq = ref->aq.as<AlignItem>(); P.aqCap = ref->aqCap; P.aqCtr = ref->qCtr.as<unsigned int>() + 1;
+  P.workBegin = 0; P.workEnd = 0;
   { const char *env = getenv("T1K_NO_FAST"); P.noFast = (env && atoi(env) != 0) ? 1 : 0; }
   P.workCtr = ref->workCtr.as<unsigned int>();
   P.hitBuf = ref->hitBuf.as<u32>(); P.hitCap = ref->hitCap; P.seedCap = ref->seedCap;
@@ -438,15 +456,35 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
     }
     CK(cudaMemsetAsync(ref->workCtr.p, 0, sizeof(unsigned int), st));
     CK(cudaEventRecord(ev0, st));
-    switch (ref->occ) {
-      case 6: k_assign<6><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
-      case 5: k_assign<5><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
-      case 4: k_assign<4><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
-      case 3: k_assign<3><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
-      default: k_assign<2><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
+    // rounds: k_seed takes read-ends until the warps' candidate arenas are full, then the other three kernels finish them
+    const u32 nWork = P.Q.nWork;
+    for (u32 done = 0; done < nWork;) {
+      CK(cudaMemsetAsync(ref->qCtr.p, 0, 2 * sizeof(unsigned int), st));
+      switch (ref->occ) {
+        case 8: k_seed<8><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
+        case 7: k_seed<7><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
+        case 6: k_seed<6><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
+        case 5: k_seed<5><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
+        case 4: k_seed<4><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
+        case 3: k_seed<3><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
+        default: k_seed<2><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
+      }
+      CK(cudaGetLastError());
+      k_deferred<<<ref->gridBlocks, WARPS_PER_BLOCK * 32, 0, st>>>(P);
+      CK(cudaGetLastError());
+      unsigned int taken = 0;
+      CK(cudaMemcpyAsync(&taken, ref->workCtr.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      const u32 roundEnd = std::min<u32>(taken, nWork);
+      if (roundEnd <= done) return fail(T1K_ERR_UNSUPPORTED, "t1k_assign_batch: the seeding kernel made no progress");
+      P.workBegin = done; P.workEnd = roundEnd;
+      k_passes<<<ref->gridBlocks, WARPS_PER_BLOCK * 32, 0, st>>>(P);
+      CK(cudaGetLastError());
+      k_align<<<ref->gridBlocks, WARPS_PER_BLOCK * 32, 0, st>>>(P);
+      CK(cudaGetLastError());
+      a->launches += 4;
+      done = roundEnd;
     }
-    CK(cudaGetLastError());
-    ++a->launches;
     CK(cudaEventRecord(ev1, st));
     int err = 0;
     CK(cudaMemcpyAsync(&err, ref->errFlag.p, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -971,6 +971,207 @@ T1K_HDN T1K_NOINLINE inline int diag_fast(const RefView &R, const ReadView &Q, i
   return DF_DONE;
 }
 
+// ---- The same evaluation, bit-parallel: what the lanes of a tile run in hot mode (one allele per lane, no data-dependent
+// loop in the common case, so the 32 alleles of a tile stay in lock-step).  Everything lives in 5 words of the 2-bit
+// space indexed by READ position (bit 2p = position p; reads up to 160 bases):
+//   M     mismatches of the read against the allele on diagonal d inside the window [pLo, pHi)
+//   S     the strand's seeds (seed_bits2, built once per strand)
+//   H     seeds whose k bases are all inside the window and match = S & ~(M or outside, OR-ed over the k positions)
+//   U     positions covered by the k-mers of H (H dilated by k)
+// The hit-count certificate is popcount(H) == n (or the one/two far strays rule) exactly as in diag_fast.  Given it, the
+// allele's hits are the seeds of H on one diagonal, and (see consume_chain) hitLen = |U|; two consecutive hits either overlap
+// or are separated by a gap that the reference aligns globally: with <= 3 mismatches the gap's alignment is the pure diagonal
+// (DESIGN.md "diagonal certificate", any length), so matchCnt = 2 * (span - mismatches inside the span).  A gap with more
+// mismatches, or an overhang with more than 3, needs the real alignment: DF_DEFER.  lcp: prefix base counts of the strand
+// (lc_prefix_build) for IsOverlapLowComplex.
+T1K_HD u64 shr2w(u64 lo, u64 hi, int s) { return (lo >> s) | (hi << (64 - s)); }       // 0 < s < 64
+T1K_HD u64 shl2w(u64 hi, u64 lo, int s) { return (hi << s) | (lo >> (64 - s)); }
+// bits 2p (p in [a, b)) of word j (positions 32j .. 32j+31)
+T1K_HD u64 range_mask2(int j, int a, int b) {
+  int lo = a - 32 * j, hi = b - 32 * j;
+  lo = lo < 0 ? 0 : lo > 32 ? 32 : lo; hi = hi < 0 ? 0 : hi > 32 ? 32 : hi;
+  return hi > lo ? (lowmask2(hi) & ~lowmask2(lo) & M55) : 0ull;
+}
+// IsOverlapLowComplex (SeqSet.hpp:458-485) from prefix counts: lcp[p] = number of A | C << 8 | G << 16 | T << 24 among the
+// bases [0, p) of an N-free strand
+T1K_HD bool low_complex_lcp(const u32 *lcp, int s, int e) {
+  const u32 a = lcp[e + 1], b = lcp[s];
+  const int n = e - s + 1;
+  int low = 0, lowTotal = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (int)((a >> (8 * i)) & 255) - (int)((b >> (8 * i)) & 255);
+    if (c <= 2) { ++low; lowTotal += c; }
+  }
+  if (lowTotal * 7 >= n) return false;
+  return low >= 2;
+}
+T1K_HDN inline void lc_prefix_build(const ReadView &Q, u32 *lcp) {       // len + 1 entries (host / one lane)
+  u32 c = 0;
+  for (int p = 0; p <= Q.len; ++p) { lcp[p] = c; if (p < Q.len) c += 1u << (8 * base2(Q.seq2, p)); }
+}
+T1K_HDN inline void seed_bits2_build(const u16 *seedA, int nS, u32 *s2) {  // 10 u32 = 5 words of the 2-bit space
+  for (int i = 0; i < 10; ++i) s2[i] = 0;
+  for (int k = 0; k < nS; ++k) s2[seedA[k] >> 4] |= 1u << (2 * (seedA[k] & 15));
+}
+
+T1K_HDN T1K_NOINLINE inline int diag_hot(const RefView &R, const ReadView &Q, int strand01, int seqIdx, int n, int d, int onDiag, int far,
+                             const u64 *S2, const u32 *lcp, Cand &out, bool &emitted, u64 &bestStrandKey) {
+  emitted = false;
+  const int len = Q.len;
+#ifdef __CUDA_ARCH__
+  const uint4 mt = *reinterpret_cast<const uint4 *>(R.meta + seqIdx);
+  const u64 w0 = (u64)mt.x | ((u64)mt.y << 32);
+  const int clen = (int)mt.z;
+  const bool alleleHasN = mt.w != 0;
+#else
+  const u64 w0 = R.meta[seqIdx].wordOff;
+  const int clen = R.meta[seqIdx].len;
+  const bool alleleHasN = R.meta[seqIdx].hasN != 0;
+#endif
+  const int pLo = d < 0 ? -d : 0, pHi = imin(len, clen - d);
+  const int W = pHi - pLo;
+  if (W < KMER) return DF_DECLINED;
+  if (alleleHasN && n_in_range(R.n2 + w0, pLo + d, pHi - 1 + d)) return DF_DECLINED;
+  // allele bases at read positions 32j .. 32j+31 = allele positions 32j + d ..: six consecutive words (the planes are padded,
+  // so words before the first / after the last allele are readable; what lies outside the window is masked)
+  const u64 *tp = R.seq2 + (long long)w0 + (long long)(d >> 5);
+  const int sh = (d & 31) * 2;
+  u64 tw[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) tw[j] = tp[j];
+  u64 M[5], B[6];
+  int mmTot = 0;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const u64 t = sh ? shr2w(tw[j], tw[j + 1], sh) : tw[j];
+    const u64 x = t ^ Q.seq2[j];
+    const u64 in = range_mask2(j, pLo, pHi);
+    M[j] = (x | (x >> 1)) & in;
+    B[j] = M[j] | (~in & M55);
+    mmTot += popc64(M[j]);
+  }
+  B[5] = M55;
+  // H: seeds whose k-mer [a, a+k) holds no B bit: OR of B over shifts 0 .. k-1 (towards lower positions), k = 11
+  u64 H[5];
+  {
+    u64 w2[6], w4[6];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) w2[j] = B[j] | shr2w(B[j], B[j + 1], 2);
+    w2[5] = M55;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) w4[j] = w2[j] | shr2w(w2[j], w2[j + 1], 4);
+    w4[5] = M55;
+    u64 w8[6];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) w8[j] = w4[j] | shr2w(w4[j], w4[j + 1], 8);
+    w8[5] = M55;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) H[j] = S2[j] & ~(w8[j] | shr2w(w4[j], w4[j + 1], 14));
+  }
+  int cntSum = 0;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) cntSum += popc64(H[j]);
+  if (cntSum > n) return DF_DECLINED;
+  if (cntSum < n) {
+    // one or two postings off the diagonal, each more than RADIUS diagonals away (see diag_fast)
+    const int extra = n - cntSum;
+    if (extra > 2) return DF_DECLINED;
+    if (onDiag != cntSum || far != extra) return DF_DECLINED;
+  }
+  if (cntSum == 0) return DF_DONE;
+  // U: H dilated by k towards higher positions
+  u64 U[5];
+  {
+    u64 u2[5], u4[5], u8[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) u2[j] = H[j] | (j ? shl2w(H[j], H[j - 1], 2) : (H[j] << 2));
+#pragma unroll
+    for (int j = 0; j < 5; ++j) u4[j] = u2[j] | (j ? shl2w(u2[j], u2[j - 1], 4) : (u2[j] << 4));
+#pragma unroll
+    for (int j = 0; j < 5; ++j) u8[j] = u4[j] | (j ? shl2w(u4[j], u4[j - 1], 8) : (u4[j] << 8));
+#pragma unroll
+    for (int j = 0; j < 5; ++j) U[j] = u8[j] | (j ? shl2w(u4[j], u4[j - 1], 14) : (u4[j] << 14));
+  }
+  int hitLen = 0, rs = 0, lastL = 0;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) hitLen += popc64(U[j]);
+#pragma unroll
+  for (int j = 4; j >= 0; --j) if (H[j]) rs = 32 * j + (ctz64(H[j]) >> 1);
+#pragma unroll
+  for (int j = 0; j < 5; ++j) if (H[j]) {
+#ifdef __CUDA_ARCH__
+    lastL = 32 * j + ((63 - __clzll((long long)H[j])) >> 1);
+#else
+    lastL = 32 * j + ((63 - __builtin_clzll(H[j])) >> 1);
+#endif
+  }
+  if (hitLen < HIT_LEN_REQ) return DF_DONE;
+  const int re = lastL + KMER - 1;
+  int mmInside = 0, mmLeft = 0;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) { mmInside += popc64(M[j] & range_mask2(j, rs, re + 1)); mmLeft += popc64(M[j] & range_mask2(j, 0, rs)); }
+  const int mmRight = mmTot - mmInside - mmLeft;
+  if (mmInside > 3) {
+    // does one gap (a maximal stretch of [rs, re] that U does not cover) hold more than 3 mismatches?
+    int cnt = 0; bool pendingU = false, dirty = false;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      u64 g = M[j] & range_mask2(j, rs, re + 1), done = 0;
+      T1K_NOUNROLL
+      while (g) {
+        const u64 b = g & (~g + 1), below = b - 1;
+        if (pendingU || (U[j] & below & ~done)) cnt = 0;
+        ++cnt; dirty |= cnt > 3; pendingU = false;
+        done = below | b; g &= g - 1;
+      }
+      pendingU |= (U[j] & ~done) != 0;
+    }
+    if (dirty) return DF_DEFER;
+  }
+  const u64 sk = strand_key(2 * hitLen, re - rs, seqIdx, strand01);
+  if (sk > bestStrandKey) bestStrandKey = sk;
+  const int mc = 2 * (re - rs + 1 - mmInside);
+  bool below = sim_below(R, mc, 2 * (re - rs + 1), 0);
+  if (!below && low_complex_lcp(lcp, rs, re)) below = 0.0 < R.sim;
+  if (below) return DF_DONE;
+  // ---- ExtendOverlap on the same diagonal (SeqSet.hpp:1994-2100): overhangs [pLo, rs) and (re, pHi)
+  if (mmLeft > 3 || mmRight > 3) return DF_DEFER;
+  Cand &c = out;
+  c.seqIdx = seqIdx; c.seqStart = rs + d; c.seqEnd = re + d;
+  c.readStart = (u8)rs; c.readEnd = (u8)re; c.strand01 = (u8)strand01;
+  c.matchCnt = (u16)mc; c.pad = 0; c.mmPos = 0;
+  emitted = true;
+  const int mcE = 2 * (W - mmTot);
+  const int leftClip = pLo, rightClip = len - pHi;
+  u8 flags = CF_PRE;
+  if (d < 0 || d + len > clen) flags |= CF_NEEDCLIP;
+  if (!sim_below(R, mcE, 2 * W, 0)) flags |= CF_RET;
+  c.eReadStart = (u8)pLo; c.eReadEnd = (u8)(pHi - 1);
+  c.eSeqStart = pLo + d; c.eSeqEnd = pHi - 1 + d;
+  c.leftClip = (u8)leftClip; c.rightClip = (u8)rightClip;
+  c.relaxed = mcE;
+  c.eMatchCnt = mcE + 2 * leftClip + 2 * rightClip;
+  // ---- the full-read alignment of [pLo, pHi) (SeqSet.hpp:2203-2274): <= 3 mismatches certify the diagonal
+  if (mmTot <= 3) {
+    u32 mmPos = 0; int k = 0, exMm = 0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      u64 m = M[j];
+      T1K_NOUNROLL
+      while (m) { mmPos |= (u32)(32 * j + (ctz64(m) >> 1)) << (8 * k); ++k; m &= m - 1; }
+    }
+    if (R.relax && mmTot > 0) {
+#pragma unroll
+      for (int j = 0; j < 5; ++j) if (M[j]) exMm += popc64(M[j] & fetch32(R.ex2 + w0, 32 * j + d));
+    }
+    flags |= CF_FA;
+    c.mmPos = mmPos | ((u32)mmTot << 24) | ((u32)exMm << 26);
+  }
+  c.flags = flags;
+  return DF_DONE;
+}
+
 // full-read alignment of a CF_FA candidate: coverage and the exon-relaxed count from the stored mismatch positions
 T1K_HD void full_align_known(const RefView &R, Cand &c, int weight) {
   const int mm = (int)((c.mmPos >> 24) & 3), exMm = (int)((c.mmPos >> 26) & 3);

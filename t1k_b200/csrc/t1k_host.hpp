@@ -64,13 +64,13 @@ inline bool pack_reference(int32_t n, const char *bases, const int64_t *off, con
                            PackedRef &P) {
   P.nAlleles = n;
   P.wordOff.resize(n); P.len.resize(n); P.hasN.assign(n, 0);
-  size_t words = 0;
+  size_t words = 8;                           // pad words before the first allele: diag_hot reads read-aligned windows
   for (int i = 0; i < n; ++i) {
     int len = (int)(off[i + 1] - off[i]);
     P.wordOff[i] = words; P.len[i] = len;
     words += (size_t)(len + 31) / 32 + 2;     // >= 1 pad word after every allele (coverage diff writes at len)
   }
-  words += 2;
+  words += 8;                                 // ... and after the last one
   P.totalWords = words;
   P.seq2.assign(words, 0); P.n2.assign(words, 0); P.ex2.assign(words, 0);
   const size_t nK = (size_t)1 << (2 * KMER);

@@ -41,15 +41,43 @@ struct AssignOut {
   unsigned long long *stats;   // [0] postings visited, [1] candidates, [2] tiles, [3] alleles on the hit-list path (debug/roofline)
 };
 
+// ---- AssignRead runs as rounds of four kernels over a slice of the batch (the code a warp executes in steady state stays
+// small enough for the instruction caches, and work that only a few lanes of a warp would do runs item-parallel instead):
+//   k_seed      warp per read-end: seeds, sweep over the allele tiles of the index, mismatch-mask evaluation (diag_fast,
+//               hot mode) -> candidates in the warp's arena of the candidate pool; alleles that need a dirty-gap alignment
+//               or a dirty overhang -> DeferItem queue (their candidate slot reserved)
+//   k_deferred  thread per DeferItem: the full evaluation, candidate written into its slot
+//   k_passes    warp per read-end: AssignRead proper (ordered scan, inclusion, > 1000 cut, records into the store);
+//               full-read alignments that are not known from the seeding stage -> AlignItem queue
+//   k_align     thread per AlignItem: full-read alignment (certificates / band DP), coverage, relaxedMatchCnt patched
+//               into the record
+// State of one read-end between the kernels of a round:
+struct alignas(16) ReadState {
+  u64 candOff;             // first candidate in the pool
+  u32 nFwd, nCand;         // candidates of the forward strand / of both strands
+  u64 bestKey;             // strand-selection key (max; bit 0: the reverse strand won)
+  // per strand (0 = forward): order word (order key | candidate index) of the first candidate in list order whose extension
+  // fails / succeeds (goodMatchCnt of SeqSet.hpp:2156-2186 follows from those two: the list is matchCnt-descending)
+  u64 fOrd[2], rOrd[2];
+};
+struct DeferItem { u32 read, seqIdx; int32_t d0; u32 n, onDiag, far, at, pass; };      // at: candidate index inside the read-end's list
+struct AlignItem { u32 read, cand; u64 recSlot; };                                     // recSlot: store index of the record (~0: cut away)
+
 struct AssignParams {
   RefView R;
   ReadsDev Q;
   AssignOut O;
-  Cand *candBuf;           // per warp
-  u32 candCap;
+  Cand *candPool;          // arenaCands candidates per warp of k_seed
+  u64 arenaCands;
+  u32 candCap;             // most candidates one read-end may produce (both strands)
+  ReadState *state;        // [reads of the batch]
+  u32 *stabBuf;            // [reads][2 strands][256]: seed tables of the strands that deferred something (k_deferred reads them)
+  DeferItem *dq; unsigned int *dqCtr; u32 dqCap;
+  AlignItem *aq; unsigned int *aqCtr; u32 aqCap;
   u8 *laneScratch;         // per lane SCR_BYTES
   u32 *hitBuf;             // per warp hitCap x 32: hit lists of the alleles of a tile that take the hit-list path (lane-interleaved)
-  unsigned int *workCtr;
+  unsigned int *workCtr;   // next position of the work list (persists over the rounds of a batch)
+  u32 workBegin, workEnd;  // k_passes: the positions this round's k_seed took
   int hitCap;              // hits per allele the hit-list path holds
   int seedCap;             // seeds per strand the shared-memory tables hold (>= longest read - k + 1, multiple of 32, >= 64)
   int noFast;              // 1: every allele goes through the hit-list path (A/B switch, T1K_NO_FAST)
@@ -109,25 +137,31 @@ __global__ void k_pack_reads(const char *bases, const u64 *off, const u32 *len, 
   }
 }
 
+// order word of a candidate: list-order key (bits 63..21) | index in the read-end's candidate list (< 2^20).  Ascending =
+// _overlap::operator< order including its tie-breaks (see order_key), one 64-bit compare / atomicMin.
+__device__ __forceinline__ u64 ord_word(u64 key, int idx) { return key | (u64)(u32)idx; }
+constexpr u64 ORD_NONE = ~0ull;
+
 // ---------------------------------------------------------------------------------------------------
-// One warp = one read-end at a time (dynamic work queue).  Shared memory per warp (seedCap = S):
+// k_seed.  One warp = one read-end at a time (dynamic work queue).  Shared memory per warp (seedCap = S):
 //   ent[S]    the CURRENT index entry {tile, off, mask, more} of every seed (cp.async destination); during seeding the
 //             same storage holds {code, postings, first entry, end entry} of every k-mer window
 //   seq/nn    the strand's 2-bit planes
 //   cur[S], end[S]  entry cursor / end of every seed; stab[256] seed table of diag_fast; bits[16] its bit masks
 //   seedA[S]  read offset of every seed; adv[S] entries the current tile consumed from the seed
-//   q0[64], q1[64]  alleles whose mismatch-mask evaluation was deferred (DF_DEFER): {allele, diagonal, hits, hits on the
-//             diagonal}, {hits far off it, reserved candidate slot}; run 32 at a time
+//   q0[64], q1[64]  staging of deferred alleles (DF_DEFER): {allele, diagonal, hits, hits on the diagonal}, {hits far off
+//             it, reserved candidate slot}; moved to the DeferItem queue 32 at a time
+//   s2[5]     the strand's seeds in the 2-bit space, lcp[256] prefix base counts (diag_hot)
 struct WarpSmem {
   uint4 *ent, *q0;
-  u64 *seq, *nn;
+  u64 *seq, *nn, *s2;
   uint2 *q1;
-  u32 *cur, *end, *stab, *bits;
+  u32 *cur, *end, *stab, *bits, *lcp;
   u16 *seedA, *adv;
 };
 constexpr int DEFER_CAP = 64;
 __host__ __device__ inline size_t warp_smem_bytes(int seedCap) {
-  return ((size_t)seedCap * (16 + 4 + 4 + 2 + 2) + DEFER_CAP * 24 + 2 * RWORDS * 8 + 256 * 4 + 16 * 4 + 15) & ~(size_t)15;
+  return ((size_t)seedCap * (16 + 4 + 4 + 2 + 2) + DEFER_CAP * 24 + (2 * RWORDS + 6) * 8 + 2 * 256 * 4 + 16 * 4 + 15) & ~(size_t)15;
 }
 
 // returns whether the read holds an N
@@ -140,19 +174,24 @@ __device__ __forceinline__ bool load_planes(const AssignParams &P, u32 r, int st
   return __any_sync(FULL, nw != 0);
 }
 
-__device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W, Cand *cands, u32 *hitTile, const LaneScratch &S, int lane) {
+__device__ __forceinline__ Cand void_cand(u32 seqIdx, int strand01) {
+  Cand v;                                         // a reserved slot that turned out to hold nothing: skipped like CF_SEP
+  v.seqIdx = (int32_t)seqIdx; v.seqStart = v.seqEnd = 0; v.readStart = v.readEnd = 0; v.strand01 = (u8)strand01; v.flags = CF_SEP;
+  v.matchCnt = 0; v.pad = 0; v.eSeqStart = v.eSeqEnd = 0; v.eReadStart = v.eReadEnd = v.leftClip = v.rightClip = 0;
+  v.eMatchCnt = 0; v.relaxed = 0; v.mmPos = 0;
+  return v;
+}
+
+// returns the number of candidates written to cands[]
+__device__ u32 seed_one_read(const AssignParams &P, u32 r, const WarpSmem &W, Cand *cands, u64 candOff, u32 *hitTile, const LaneScratch &S, int lane) {
   const RefView &R = P.R;
   const int len = P.Q.len[r];
-  const int weight = P.Q.weight[r];
   const int CAP = P.hitCap;
   int err = 0;
   u32 nCand = 0, nFwd = 0;
   u64 bestKey = 0;
   unsigned long long stPost = 0, stTiles = 0, stSlow = 0;
-  // per strand, in list order (_overlap::operator<): the first candidate whose extension fails and the first one whose
-  // extension succeeds (goodMatchCnt of SeqSet.hpp:2156-2186 follows from those two: the list is matchCnt-descending)
-  u64 fKeyF = ~0ull, rKeyF = ~0ull, fKeyR = ~0ull, rKeyR = ~0ull;
-  int fIdxF = 0x7fffffff, rIdxF = 0x7fffffff, fIdxR = 0x7fffffff, rIdxR = 0x7fffffff;
+  u64 fOrdF = ORD_NONE, rOrdF = ORD_NONE, fOrdR = ORD_NONE, rOrdR = ORD_NONE;
   ReadView Qv; Qv.seq2 = W.seq; Qv.n2 = W.nn; Qv.len = len; Qv.anyN = false;
 
   if (len >= KMER) {
@@ -228,21 +267,60 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
           W.stab[a] = cnt | (big << 8) | (nxt << 16) | (last << 24);
         }
       }
+      if (strandFast) {
+        // diag_hot's strand tables: seeds as bits of the 2-bit space, prefix base counts
+        u32 *s2w = (u32 *)W.s2;
+        if (lane < 10) s2w[lane] = 0;
+        __syncwarp();
+        T1K_NOUNROLL
+        for (int k = lane; k < nS; k += 32) { const int a = W.seedA[k]; atomicOr(&s2w[a >> 4], 1u << (2 * (a & 15))); }
+        T1K_NOUNROLL
+        for (int a = lane; a <= len; a += 32) {
+          const int wi = a >> 5, bit = a & 31;
+          u32 c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+          T1K_NOUNROLL
+          for (int w = 0; w <= wi; ++w) {
+            const u64 x = W.seq[w], keep = w < wi ? M55 : (lowmask2(bit) & M55);
+            const u64 lo = x & M55, hi = (x >> 1) & M55;
+            c0 += __popcll(~lo & ~hi & keep); c1 += __popcll(lo & ~hi & keep); c2 += __popcll(~lo & hi & keep); c3 += __popcll(lo & hi & keep);
+          }
+          W.lcp[a] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+        }
+      }
       // first entry of every seed (the window table is dead now)
       T1K_NOUNROLL
       for (int k = lane; k < nS; k += 32) cp_async16(&W.ent[k], R.entries + W.cur[k]);
       u64 laneKey = 0;
-      u64 fKey = ~0ull, rKey = ~0ull; int fIdx = 0x7fffffff, rIdx = 0x7fffffff;
+      u64 fOrd = ORD_NONE, rOrd = ORD_NONE;
       auto note = [&](const Cand &c, int i) {
         if (c.flags & CF_SEP) return;
-        const u64 k = cand_key_pre(c);
-        if (c.flags & CF_RET) { if (pair_less(k, i, rKey, rIdx)) { rKey = k; rIdx = i; } }
-        else if (pair_less(k, i, fKey, fIdx)) { fKey = k; fIdx = i; }
+        const u64 k = ord_word(cand_key_pre(c), i);
+        if (c.flags & CF_RET) rOrd = min(rOrd, k); else fOrd = min(fOrd, k);
       };
-      // the deferred alleles, `take` at a time with all lanes busy: the whole evaluation incl. dirty gaps and overhangs
+      // deferred alleles leave the warp `take` at a time: into the DeferItem queue, or — queue full — evaluated right here
       int qn = 0;
-      auto run_deferred = [&](int take) {
-        if (lane < take) {
+      bool stabSaved = false;
+      auto flush_deferred = [&](int take) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(P.dqCtr, (unsigned int)take);
+        base = __shfl_sync(FULL, base, 0);
+        if (base + (unsigned int)take <= P.dqCap) {
+          if (!stabSaved) {          // k_deferred needs this strand's seed table
+            u32 *dst = P.stabBuf + ((size_t)r * 2 + pass) * 256;
+            T1K_NOUNROLL
+            for (int a = lane; a < len; a += 32) dst[a] = W.stab[a];
+            stabSaved = true;
+          }
+          if (lane < take) {
+            const uint4 e0 = W.q0[qn - take + lane];
+            const uint2 e1 = W.q1[qn - take + lane];
+            DeferItem it;
+            it.read = r; it.seqIdx = e0.x; it.d0 = (int32_t)e0.y; it.n = e0.z; it.onDiag = e0.w; it.far = e1.x; it.at = e1.y; it.pass = (u32)pass;
+            P.dq[base + lane] = it;
+          }
+        } else if (lane < take) {
+          // (the counter has moved on: the slots of this batch that still lie inside the queue become no-ops)
+          if (base + (unsigned int)lane < P.dqCap) { DeferItem nop; nop.read = 0xffffffffu; nop.seqIdx = 0; nop.d0 = 0; nop.n = nop.onDiag = nop.far = nop.at = nop.pass = 0; P.dq[base + lane] = nop; }
           const uint4 e0 = W.q0[qn - take + lane];
           const uint2 e1 = W.q1[qn - take + lane];
           Cand c;
@@ -253,13 +331,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
             if (!(c.flags & CF_PRE)) { extend_cand<false>(R, Qv, c, S, err); c.flags |= CF_PRE; }     // a long or dirty overhang
             cands[e1.y] = c;
             note(c, (int)e1.y);
-          } else {
-            Cand v;                                         // nothing to emit: the reserved slot stays void
-            v.seqIdx = (int32_t)e0.x; v.seqStart = v.seqEnd = 0; v.readStart = v.readEnd = 0; v.strand01 = (u8)strand01; v.flags = CF_SEP;
-            v.matchCnt = 0; v.pad = 0; v.eSeqStart = v.eSeqEnd = 0; v.eReadStart = v.eReadEnd = v.leftClip = v.rightClip = 0;
-            v.eMatchCnt = 0; v.relaxed = 0; v.mmPos = 0;
-            cands[e1.y] = v;
-          }
+          } else cands[e1.y] = void_cand(e0.x, strand01);
         }
         qn -= take;
         __syncwarp();
@@ -321,7 +393,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
         Cand fc;
         bool fastEmit = false, handled = n < 3, defer = false;
         if (strandFast && n >= 3) {
-          const int df = diag_fast(R, Qv, strand01, (int)(T * 32 + lane), n, d0, onDiag, far, W.stab, true, fc, fastEmit, laneKey, lcMemo, S, err);
+          const int df = diag_hot(R, Qv, strand01, (int)(T * 32 + lane), n, d0, onDiag, far, W.s2, W.lcp, fc, fastEmit, laneKey);
           handled = df != DF_DECLINED;
           defer = df == DF_DEFER;          // needs work the other lanes do not: queued, its candidate slot reserved
           if (fastEmit || defer) nEmit = 1;
@@ -386,41 +458,131 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
             qn += __popc(balD);
           }
         }
-        if (qn >= 32) { __syncwarp(); run_deferred(32); }
+        if (qn >= 32) { __syncwarp(); flush_deferred(32); }
       }
       T1K_NOUNROLL
-      while (qn > 0) { __syncwarp(); run_deferred(min(qn, 32)); }
+      while (qn > 0) { __syncwarp(); flush_deferred(min(qn, 32)); }
       bestKey = max(bestKey, warp_max_u64(laneKey));
-      warp_min_pair(fKey, fIdx);
-      warp_min_pair(rKey, rIdx);
-      if (pass == 0) { fKeyF = fKey; fIdxF = fIdx; rKeyF = rKey; rIdxF = rIdx; nFwd = nCand; }
-      else { fKeyR = fKey; fIdxR = fIdx; rKeyR = rKey; rIdxR = rIdx; }
+      fOrd = warp_min_u64(fOrd);
+      rOrd = warp_min_u64(rOrd);
+      if (pass == 0) { fOrdF = fOrd; rOrdF = rOrd; nFwd = nCand; }
+      else { fOrdR = fOrd; rOrdR = rOrd; }
     }
   }
-  // ---- AssignRead proper (SeqSet.hpp:2132-2300) on the best strand's candidates
-  const int best01 = (bestKey & 1) ? 0 : 1;
-  const int c0 = best01 ? 0 : (int)nFwd, c1 = best01 ? (int)nFwd : (int)nCand;
-  const u64 fKey = best01 ? fKeyF : fKeyR, rKey = best01 ? rKeyF : rKeyR;
-  const int fIdx = best01 ? fIdxF : fIdxR, rIdx = best01 ? rIdxF : rIdxR;
+  if (lane == 0) {
+    ReadState st;
+    st.candOff = candOff; st.nFwd = nFwd; st.nCand = nCand; st.bestKey = bestKey;
+    st.fOrd[0] = fOrdF; st.fOrd[1] = fOrdR; st.rOrd[0] = rOrdF; st.rOrd[1] = rOrdR;
+    P.state[r] = st;
+  }
+  err = __reduce_or_sync(FULL, (unsigned)err);
+  if (lane == 0 && err) atomicOr(P.O.err, err);
+  if (P.O.stats) { stSlow = __reduce_add_sync(FULL, (u32)stSlow); }
+  if (lane == 0 && P.O.stats) {
+    atomicAdd(P.O.stats + 0, stPost);
+    atomicAdd(P.O.stats + 1, (unsigned long long)nCand);
+    atomicAdd(P.O.stats + 2, stTiles);
+    atomicAdd(P.O.stats + 3, stSlow);
+  }
+  return nCand;
+}
+
+extern __shared__ u64 t1k_smem[];
+
+// MINB = resident blocks per SM the register budget is compiled for
+template <int MINB>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_seed(AssignParams P) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t gwarp = (size_t)blockIdx.x * WARPS_PER_BLOCK + warp;
+  const int SC = P.seedCap;
+  u8 *sm = (u8 *)t1k_smem + (size_t)warp * warp_smem_bytes(SC);
+  WarpSmem W;
+  W.ent = (uint4 *)sm; W.q0 = W.ent + SC;
+  W.seq = (u64 *)(W.q0 + DEFER_CAP); W.nn = W.seq + RWORDS; W.s2 = W.nn + RWORDS;
+  W.q1 = (uint2 *)(W.s2 + 6);
+  W.cur = (u32 *)(W.q1 + DEFER_CAP); W.end = W.cur + SC; W.stab = W.end + SC; W.lcp = W.stab + 256; W.bits = W.lcp + 256;
+  W.seedA = (u16 *)(W.bits + 16); W.adv = W.seedA + SC;
+  LaneScratch S; S.base = P.laneScratch + (gwarp * 32 + lane) * (size_t)SCR_BYTES;
+  u32 *hitTile = P.hitBuf + gwarp * (size_t)P.hitCap * 32;
+  const u64 arena0 = gwarp * P.arenaCands;
+  u64 used = 0;
+  // a warp takes read-ends while its arena of the candidate pool can hold the most a read-end may produce
+  while (used + P.candCap <= P.arenaCands) {
+    u32 w = 0;
+    if (lane == 0) w = atomicAdd(P.workCtr, 1u);
+    w = __shfl_sync(FULL, w, 0);
+    if (w >= P.Q.nWork) break;
+    const u32 r = P.Q.workList ? P.Q.workList[w] : w;
+    used += seed_one_read(P, r, W, P.candPool + arena0 + used, arena0 + used, hitTile, S, lane);
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_deferred: thread per DeferItem
+__global__ void __launch_bounds__(128) k_deferred(AssignParams P) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nThreads = (size_t)gridDim.x * blockDim.x;
+  const u32 nItems = min(*P.dqCtr, P.dqCap);
+  LaneScratch S; S.base = P.laneScratch + tid * (size_t)SCR_BYTES;
+  const RefView &R = P.R;
+  int err = 0;
+  for (size_t i = tid; i < nItems; i += nThreads) {
+    const DeferItem it = P.dq[i];
+    if (it.read == 0xffffffffu) continue;
+    const int strand01 = it.pass == 0 ? 1 : 0;
+    const u64 *pl = P.Q.planes + ((size_t)it.read * 4 + (strand01 ? 0 : 2)) * RWORDS;
+    ReadView Q; Q.seq2 = pl; Q.n2 = pl + RWORDS; Q.len = P.Q.len[it.read]; Q.anyN = false;     // (deferring strands hold no N)
+    ReadState *st = P.state + it.read;
+    Cand *slot = P.candPool + st->candOff + it.at;
+    Cand c;
+    bool em = false;
+    u64 laneKey = 0; u32 lcMemo = 0;
+    const int df = diag_fast(R, Q, strand01, (int)it.seqIdx, (int)it.n, it.d0, (int)it.onDiag, (int)it.far,
+                             P.stabBuf + ((size_t)it.read * 2 + it.pass) * 256, false, c, em, laneKey, lcMemo, S, err);
+    if (df == DF_DECLINED) err |= ERR_SCRATCH;        // (cannot happen: the hit-count certificate passed in hot mode)
+    if (df == DF_DONE && em) {
+      if (!(c.flags & CF_PRE)) { extend_cand<false>(R, Q, c, S, err); c.flags |= CF_PRE; }     // a long or dirty overhang
+      *slot = c;
+      if (!(c.flags & CF_SEP)) {
+        const u64 k = ord_word(cand_key_pre(c), (int)it.at);
+        atomicMin((unsigned long long *)((c.flags & CF_RET) ? &st->rOrd[it.pass] : &st->fOrd[it.pass]), (unsigned long long)k);
+      }
+    } else *slot = void_cand(it.seqIdx, strand01);
+    if (laneKey) atomicMax((unsigned long long *)&st->bestKey, (unsigned long long)laneKey);
+  }
+  if (err) atomicOr(P.O.err, err);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_passes: AssignRead proper (SeqSet.hpp:2132-2300) on the best strand's candidates, warp per read-end
+__device__ void passes_one_read(const AssignParams &P, u32 r, u32 *qCand, u64 *qSlot, const LaneScratch &S, int lane) {
+  const RefView &R = P.R;
+  const ReadState st = P.state[r];
+  const int weight = P.Q.weight[r];
+  const Cand *cands = P.candPool + st.candOff;
+  int err = 0;
+  const int best01 = (st.bestKey & 1) ? 0 : 1;
+  const int c0 = best01 ? 0 : (int)st.nFwd, c1 = best01 ? (int)st.nFwd : (int)st.nCand;
+  const u64 fOrd = best01 ? st.fOrd[0] : st.fOrd[1], rOrd = best01 ? st.rOrd[0] : st.rOrd[1];
   int ret = -1, nFinal = 0;
   unsigned long long pos = 0;
   bool deferred = false;
   if (c1 - c0 > 0) {
-    if (best01 == 1) Qv.anyN = load_planes(P, r, 1, W, lane);
-    __threadfence_block();
-    __syncwarp();
+    const u64 *pl = P.Q.planes + ((size_t)r * 4 + (best01 ? 0 : 2)) * RWORDS;
+    ReadView Qv; Qv.seq2 = pl; Qv.n2 = pl + RWORDS; Qv.len = P.Q.len[r];
+    { u64 nw = lane < RWORDS ? pl[RWORDS + lane] : 0; Qv.anyN = __any_sync(FULL, nw != 0); }
     // goodMatchCnt (SeqSet.hpp:2156-2186) = the largest matchCnt among the returned candidates that precede the first
     // failing one = the first returned candidate if it precedes the failure, and nothing otherwise.
-    const int good = pair_less(rKey, rIdx, fKey, fIdx) ? order_key_mc(rKey) : -1;
+    const int good = rOrd < fOrd ? order_key_mc(rOrd) : -1;
     auto included = [&](const Cand &c, int i) {          // the ordered scan's verdict on one candidate (SeqSet.hpp:2163-2186)
       if ((c.flags & CF_SEP) || !(c.flags & CF_RET)) return false;
-      if (pair_less(cand_key_pre(c), i, fKey, fIdx)) return true;
+      if (ord_word(cand_key_pre(c), i) < fOrd) return true;
       return !((int)c.matchCnt < good && (!(c.flags & CF_NEEDCLIP) || sim_below(R, c.matchCnt, cand_denom_pre(c), 1)));
     };
     // pass A (read-only): what is kept, the best matchCnt, the head of the post-extension order and the smallest
     // similarity (as an exact fraction), which tells whether the > 1000 cut (SeqSet.hpp:2290-2298) removes anything
     int bestMc = -1, nInc = 0;
-    u64 bKey = ~0ull; int bIdx = 0x7fffffff;
+    u64 bOrd = ORD_NONE;
     int minNum = 1, minDen = 0;                          // minDen == 0: none yet
     T1K_NOUNROLL
     for (int i = c0 + lane; i < c1; i += 32) {
@@ -429,28 +591,27 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
       if (!included(c, i)) continue;
       bestMc = max(bestMc, c.eMatchCnt);
       ++nInc;
-      const u64 k = cand_key_post(c);
-      if (pair_less(k, i, bKey, bIdx)) { bKey = k; bIdx = i; }
+      bOrd = min(bOrd, ord_word(cand_key_post(c), i));
       const int den = cand_denom_post(c);
       if (minDen == 0 || (long long)c.eMatchCnt * minDen < (long long)minNum * den) { minNum = c.eMatchCnt; minDen = den; }
     }
     bestMc = warp_max_i32(bestMc);
     nInc = warp_sum_i32(nInc);
-    warp_min_pair(bKey, bIdx);
+    bOrd = warp_min_u64(bOrd);
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
       const int on = __shfl_xor_sync(FULL, minNum, o), od = __shfl_xor_sync(FULL, minDen, o);
       if (od != 0 && (minDen == 0 || (long long)on * minDen < (long long)minNum * od)) { minNum = on; minDen = od; }
     }
-    __syncwarp();
     // reserve the store before touching coverage, so that a full store can be retried without double counting
     if (lane == 0 && nInc > 0) pos = atomicAdd(P.O.storeCtr, (unsigned long long)nInc);
     pos = __shfl_sync(FULL, pos, 0);
     if (nInc > 0 && pos + nInc > P.O.storeCap) deferred = true;
     if (!deferred && nInc > 0) {
       const bool usePost = nInc > 1000;      // SeqSet.hpp:2290-2298
-      u64 cKey = ~0ull; int cIdx = 0x7fffffff;       // first candidate (post order) the cut removes
+      u64 cOrd = ORD_NONE;                   // first candidate (post order) the cut removes
       if (usePost) {
+        const int bIdx = (int)(bOrd & 0xFFFFFu);
         const Cand cb = cands[bIdx];
         const double cutSim = (double)cb.eMatchCnt / (double)cand_denom_post(cb) - 0.1;
         if ((double)minNum / (double)minDen < cutSim) {
@@ -458,31 +619,48 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
           for (int i = c0 + lane; i < c1; i += 32) {
             const Cand c = cands[i];
             if (!included(c, i) || i == bIdx) continue;
-            if ((double)c.eMatchCnt / (double)cand_denom_post(c) < cutSim) {
-              const u64 k = cand_key_post(c);
-              if (pair_less(k, i, cKey, cIdx)) { cKey = k; cIdx = i; }
-            }
+            if ((double)c.eMatchCnt / (double)cand_denom_post(c) < cutSim) cOrd = min(cOrd, ord_word(cand_key_post(c), i));
           }
-          warp_min_pair(cKey, cIdx);
+          cOrd = warp_min_u64(cOrd);
         }
       }
-      // pass B: full-read alignment + coverage of everything within 10 of the best (Q8) and ordered compaction into the
-      // store (allele order is kept: pairing searches it), minus the cut.  Two-speed: candidates whose full-read alignment
-      // the seeding stage already knows (CF_FA) cost nothing; the others are queued (W.cur: candidate, W.end: store slot)
-      // and aligned 32 at a time, all lanes busy.
+      // pass B: ordered compaction into the store (allele order is kept: pairing searches it), minus the cut, and the
+      // full-read alignment + coverage of everything within 10 of the best (Q8).  Alignments the seeding stage already knows
+      // (CF_FA) cost nothing; the others leave as AlignItems (k_align patches relaxedMatchCnt into the record), or —
+      // queue full — are aligned here 32 at a time.
       const bool doAlign = weight >= 0;
       int running = 0, qn = 0;
       u32 top = 0;
-      auto emit_rec = [&](const Cand &c, u32 slot) {
+      auto emit_rec = [&](const Cand &c, u64 slot) {
         Rec o;
         o.seqIdx = c.seqIdx; o.seqStart = c.eSeqStart; o.seqEnd = c.eSeqEnd;
         o.readStart = c.eReadStart; o.readEnd = c.eReadEnd; o.leftClip = c.leftClip; o.rightClip = c.rightClip;
         o.mcx = rec_mcx(c.eMatchCnt, c.relaxed, c.strand01);
         o.key = usePost ? (cand_key_post(c) | 1ull) : cand_key_pre(c);
-        P.O.store[pos + slot] = o;
+        P.O.store[slot] = o;
+      };
+      auto flush_cold = [&](int take) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(P.aqCtr, (unsigned int)take);
+        base = __shfl_sync(FULL, base, 0);
+        if (lane < take) {
+          const u32 j = qCand[qn - take + lane];
+          const u64 sl = qSlot[qn - take + lane];
+          if (base + (unsigned int)take <= P.aqCap) {
+            AlignItem it; it.read = r; it.cand = j; it.recSlot = sl;
+            P.aq[base + lane] = it;
+          } else {
+            if (base + (unsigned int)lane < P.aqCap) { AlignItem nop; nop.read = 0xffffffffu; nop.cand = 0; nop.recSlot = ~0ull; P.aq[base + lane] = nop; }
+            Cand cc = cands[j];
+            full_align<false>(R, Qv, cc, weight, S, err);
+            if (sl != ~0ull) emit_rec(cc, sl);
+          }
+        }
+        qn -= take;
+        __syncwarp();
       };
       T1K_NOUNROLL
-      for (int b = c0; b < c1 || qn > 0; b += 32) {
+      for (int b = c0; b < c1; b += 32) {
         const int i = b + lane;
         bool inc = false, cold = false, wr = false;
         Cand c;
@@ -491,7 +669,7 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
           c = cands[i];
           inc = included(c, i);
           if (inc) {
-            wr = !usePost || pair_less(cand_key_post(c), i, cKey, cIdx);
+            wr = !usePost || ord_word(cand_key_post(c), i) < cOrd;
             if (doAlign) {
               if (c.eMatchCnt < bestMc - 10) c.relaxed = 0;
               else if (c.flags & CF_FA) full_align_known(R, c, weight);
@@ -500,28 +678,22 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
           }
         }
         const unsigned balW = __ballot_sync(FULL, wr), balC = __ballot_sync(FULL, cold);
-        const u32 slot = (u32)running + __popc(balW & ((1u << lane) - 1));
-        if (wr) top = max(top, ((u32)c.eMatchCnt << 16) | (u32)(65535 - cand_denom_post(c)));
+        const u64 slot = pos + (u64)running + __popc(balW & ((1u << lane) - 1));
+        if (wr) {
+          top = max(top, ((u32)c.eMatchCnt << 16) | (u32)(65535 - cand_denom_post(c)));
+          emit_rec(c, slot);                         // (a cold candidate's relaxedMatchCnt is patched in by k_align)
+        }
         if (cold) {
           const int q = qn + __popc(balC & ((1u << lane) - 1));
-          W.cur[q] = (u32)i; W.end[q] = wr ? slot : 0xffffffffu;
-        } else if (wr) emit_rec(c, slot);
+          qCand[q] = (u32)i; qSlot[q] = wr ? slot : ~0ull;
+        }
         running += __popc(balW);
         qn += __popc(balC);
         __syncwarp();
-        if (qn >= 32 || (b + 32 >= c1 && qn > 0)) {          // flush a full batch, or the remainder at the end
-          const int take = min(qn, 32);
-          if (lane < take) {
-            const int j = (int)W.cur[qn - take + lane];
-            const u32 sl = W.end[qn - take + lane];
-            Cand cc = cands[j];
-            full_align<false>(R, Qv, cc, weight, S, err);
-            if (sl != 0xffffffffu) emit_rec(cc, sl);
-          }
-          qn -= take;
-          __syncwarp();
-        }
+        if (qn >= 32) flush_cold(32);
       }
+      T1K_NOUNROLL
+      while (qn > 0) flush_cold(min(qn, 32));
       top = __reduce_max_sync(FULL, top);
       if (lane == 0) P.O.readTop[r] = top;
       nFinal = running;
@@ -537,42 +709,45 @@ __device__ void assign_one_read(const AssignParams &P, u32 r, const WarpSmem &W,
   }
   err = __reduce_or_sync(FULL, (unsigned)err);
   if (lane == 0 && err) atomicOr(P.O.err, err);
-  if (P.O.stats) { stSlow = __reduce_add_sync(FULL, (u32)stSlow); }
-  if (lane == 0 && P.O.stats) {
-    atomicAdd(P.O.stats + 0, stPost);
-    atomicAdd(P.O.stats + 1, (unsigned long long)nCand);
-    atomicAdd(P.O.stats + 2, stTiles);
-    atomicAdd(P.O.stats + 3, stSlow);
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_passes(AssignParams P) {
+  __shared__ u32 qCandS[WARPS_PER_BLOCK][DEFER_CAP];
+  __shared__ u64 qSlotS[WARPS_PER_BLOCK][DEFER_CAP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t gwarp = (size_t)blockIdx.x * WARPS_PER_BLOCK + warp, nWarps = (size_t)gridDim.x * WARPS_PER_BLOCK;
+  LaneScratch S; S.base = P.laneScratch + (gwarp * 32 + lane) * (size_t)SCR_BYTES;
+  for (size_t w = P.workBegin + gwarp; w < P.workEnd; w += nWarps) {
+    const u32 r = P.Q.workList ? P.Q.workList[w] : (u32)w;
+    passes_one_read(P, r, qCandS[warp], qSlotS[warp], S, lane);
+    __syncwarp();
   }
 }
 
-extern __shared__ u64 t1k_smem[];
-
-// MINB = resident blocks per SM the register budget is compiled for
-template <int MINB>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_assign(AssignParams P) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t gwarp = (size_t)blockIdx.x * WARPS_PER_BLOCK + warp;
-  const int SC = P.seedCap;
-  u8 *sm = (u8 *)t1k_smem + (size_t)warp * warp_smem_bytes(SC);
-  WarpSmem W;
-  W.ent = (uint4 *)sm; W.q0 = W.ent + SC;
-  W.seq = (u64 *)(W.q0 + DEFER_CAP); W.nn = W.seq + RWORDS;
-  W.q1 = (uint2 *)(W.nn + RWORDS);
-  W.cur = (u32 *)(W.q1 + DEFER_CAP); W.end = W.cur + SC; W.stab = W.end + SC; W.bits = W.stab + 256;
-  W.seedA = (u16 *)(W.bits + 16); W.adv = W.seedA + SC;
-  LaneScratch S; S.base = P.laneScratch + (gwarp * 32 + lane) * (size_t)SCR_BYTES;
-  Cand *cands = P.candBuf + gwarp * (size_t)P.candCap;
-  u32 *hitTile = P.hitBuf + gwarp * (size_t)P.hitCap * 32;
-  for (;;) {
-    u32 w = 0;
-    if (lane == 0) w = atomicAdd(P.workCtr, 1u);
-    w = __shfl_sync(FULL, w, 0);
-    if (w >= P.Q.nWork) break;
-    const u32 r = P.Q.workList ? P.Q.workList[w] : w;
-    assign_one_read(P, r, W, cands, hitTile, S, lane);
-    __syncwarp();
+// ---------------------------------------------------------------------------------------------------
+// k_align: thread per AlignItem
+__global__ void __launch_bounds__(128) k_align(AssignParams P) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nThreads = (size_t)gridDim.x * blockDim.x;
+  const u32 nItems = min(*P.aqCtr, P.aqCap);
+  LaneScratch S; S.base = P.laneScratch + tid * (size_t)SCR_BYTES;
+  const RefView &R = P.R;
+  int err = 0;
+  for (size_t i = tid; i < nItems; i += nThreads) {
+    const AlignItem it = P.aq[i];
+    if (it.read == 0xffffffffu) continue;
+    const ReadState *st = P.state + it.read;
+    const int best01 = (st->bestKey & 1) ? 0 : 1;
+    const u64 *pl = P.Q.planes + ((size_t)it.read * 4 + (best01 ? 0 : 2)) * RWORDS;
+    ReadView Q; Q.seq2 = pl; Q.n2 = pl + RWORDS; Q.len = P.Q.len[it.read];
+    u64 nw = 0;
+#pragma unroll
+    for (int k = 0; k < RWORDS; ++k) nw |= pl[RWORDS + k];
+    Q.anyN = nw != 0;
+    Cand c = P.candPool[st->candOff + it.cand];
+    full_align<false>(R, Q, c, P.Q.weight[it.read], S, err);
+    if (it.recSlot != ~0ull) P.O.store[it.recSlot].mcx = rec_mcx(c.eMatchCnt, c.relaxed, c.strand01);
   }
+  if (err) atomicOr(P.O.err, err);
 }
 
 }  // namespace t1k

@@ -115,6 +115,15 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
     u32 stab[256];
     if (strandFast) seed_table_build(seedA, nS, len, stab);
     u32 lcMemo = 0;
+    u32 s2[10], lcp[260];
+    u64 S2[5];
+    if (strandFast) {
+      u16 seedA16[256];
+      for (int k = 0; k < nS; ++k) seedA16[k] = seedA[k];
+      seed_bits2_build(seedA16, nS, s2);
+      for (int j = 0; j < 5; ++j) S2[j] = (u64)s2[2 * j] | ((u64)s2[2 * j + 1] << 32);
+      lc_prefix_build(Q, lcp);
+    }
     for (;;) {
       u32 T = 0xffffffffu;
       for (int k = 0; k < nS; ++k) if (cur[k] < end[k]) T = std::min(T, R.entries[cur[k]].tile);
@@ -143,12 +152,46 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
         if (strandFast) {
           Cand fc; bool emitted = false;
           // the kernel's two-speed protocol: every allele of a tile in hot mode; the deferred ones again, in full mode
-          int df = diag_fast(R, Q, strand01, seqIdx, n, d0, onDiag, far, stab, true, fc, emitted, bestKey, lcMemo, S, err);
-          if (df == DF_DEFER) {
-            t1k_emu_counters[34] += 1;
-            df = diag_fast(R, Q, strand01, seqIdx, n, d0, onDiag, far, stab, false, fc, emitted, bestKey, lcMemo, S, err);
-            if (df != DF_DONE) err |= 1 << 20;          // a deferred allele never declines
+          // The kernel's protocol: every allele of a tile through the bit-parallel diag_hot; the deferred ones through the
+          // streaming diag_fast (full mode, k_deferred).  A/B: whenever both finish, they must agree field for field.
+          u64 keyHot = bestKey, keyFull = bestKey;
+          int df = diag_hot(R, Q, strand01, seqIdx, n, d0, onDiag, far, S2, lcp, fc, emitted, keyHot);
+          {
+            Cand fc2; bool em2 = false; u32 memo2 = 0;
+            memset(&fc2, 0, sizeof(fc2));
+            const int df2 = diag_fast(R, Q, strand01, seqIdx, n, d0, onDiag, far, stab, false, fc2, em2, keyFull, memo2, S, err);
+            t1k_emu_counters[35 + df] += 1;
+            if (df == DF_DEFER) {
+              t1k_emu_counters[34] += 1;
+              if (df2 != DF_DONE) err |= 1 << 20;          // a deferred allele never declines
+              df = df2; fc = fc2; emitted = em2; keyHot = keyFull;
+            } else if (df == DF_DONE && df2 == DF_DONE) {
+              bool same = emitted == em2 && keyHot == keyFull;
+              if (same && emitted && !(fc2.flags & CF_PRE)) {
+                // the streaming path leaves an overhang longer than one word to ExtendOverlap proper; the bit-parallel path
+                // knows that <= 3 mismatches make it the diagonal whatever its length: same result, no mismatch memo
+                extend_cand<false>(R, Q, fc2, S, err); fc2.flags |= CF_PRE;
+                if (fc.flags & CF_FA) { fc2.flags |= CF_FA; fc2.mmPos = fc.mmPos; }
+              }
+              if (same && emitted) {
+                same = fc.seqIdx == fc2.seqIdx && fc.seqStart == fc2.seqStart && fc.seqEnd == fc2.seqEnd && fc.readStart == fc2.readStart &&
+                       fc.readEnd == fc2.readEnd && fc.strand01 == fc2.strand01 && fc.matchCnt == fc2.matchCnt && fc.flags == fc2.flags;
+                if (same && (fc.flags & CF_PRE))
+                  same = fc.eSeqStart == fc2.eSeqStart && fc.eSeqEnd == fc2.eSeqEnd && fc.eReadStart == fc2.eReadStart && fc.eReadEnd == fc2.eReadEnd &&
+                         fc.leftClip == fc2.leftClip && fc.rightClip == fc2.rightClip && fc.eMatchCnt == fc2.eMatchCnt && fc.relaxed == fc2.relaxed &&
+                         fc.mmPos == fc2.mmPos;
+              }
+              if (!same) {
+                err |= 1 << 21; t1k_emu_counters[39] += 1;
+                if (getenv("EMU_DEBUG"))
+                  fprintf(stderr, "A/B allele %d n=%d d=%d strand %d: em %d/%d key %llx/%llx | rs %d/%d re %d/%d mc %d/%d flags %x/%x | eRs %d/%d eRe %d/%d eMc %d/%d relaxed %d/%d mmPos %x/%x lc %d/%d clips %d,%d/%d,%d\n",
+                          seqIdx, n, d0, strand01, (int)emitted, (int)em2, (unsigned long long)keyHot, (unsigned long long)keyFull, fc.readStart, fc2.readStart,
+                          fc.readEnd, fc2.readEnd, fc.matchCnt, fc2.matchCnt, fc.flags, fc2.flags, fc.eReadStart, fc2.eReadStart, fc.eReadEnd, fc2.eReadEnd,
+                          fc.eMatchCnt, fc2.eMatchCnt, fc.relaxed, fc2.relaxed, fc.mmPos, fc2.mmPos, 0, 0, fc.leftClip, fc.rightClip, fc2.leftClip, fc2.rightClip);
+              }
+            } else if (df == DF_DECLINED && df2 != DF_DECLINED) err |= 1 << 22;   // the hot path declines nothing the streaming path takes
           }
+          bestKey = keyHot;
           if (df == DF_DONE) {
             if (emitted) {
               if (!(fc.flags & CF_PRE)) { extend_cand<false>(R, Q, fc, S, err); fc.flags |= CF_PRE; }     // a long or dirty overhang
