@@ -196,8 +196,9 @@ struct T1KRef {
   std::vector<int64_t> offset;       // caller's concatenated layout
   std::vector<u64> wordOff;
   std::vector<int32_t> len;
-  size_t paddedBases = 0;
-  DevMem seq2, n2, ex2, dWordOff, dLen, dHasN, dMeta, dSimThr, kinfo, entries, covDiff, covPoint, covFinal;
+  size_t paddedBases = 0, covEntries = 0;
+  std::vector<u64> covOff;
+  DevMem seq2, n2, ex2, dWordOff, dLen, dHasN, dMeta, dSimThr, kinfo, entries, covDiff, covPoint, covFinal, dCovOff;
   RefView R;
   cudaStream_t stream = nullptr;
   // launch state of the AssignRead kernels (k_seed / k_deferred / k_passes / k_align), sized on first use
@@ -205,7 +206,7 @@ struct T1KRef {
   u32 candCap = 0, dqCap = 0, aqCap = 0;
   u64 arenaCands = 0;
   int gridBlocks = 0, hitCap = 0, seedCap = 0;
-  int occ = 4;
+  int occ = 6;
   size_t scratchWarps = 0;
   u64 nPostings = 0, nEntries = 0;
   size_t memBudget = 0;      // free device memory right after the reference was uploaded (workspace budget; cudaMemGetInfo is
@@ -257,6 +258,7 @@ int t1k_ref_create(const T1KRefDesc *d, T1KRef **out) {
   r->offset.assign(d->offset, d->offset + d->n_alleles + 1);
   r->wordOff = P.wordOff; r->len = P.len;
   r->paddedBases = P.totalWords * 32;
+  r->covEntries = P.covEntries; r->covOff = P.covOff;
   r->nPostings = P.post.size();
   cudaDeviceProp prop;
   cudaError_t e = cudaGetDeviceProperties(&prop, dev);
@@ -273,12 +275,12 @@ int t1k_ref_create(const T1KRefDesc *d, T1KRef **out) {
     if (P.entries[k].more >= 65535u) { delete r; return fail(T1K_ERR_UNSUPPORTED, "a k-mer occurs at more than 65535 offsets inside one tile of 32 alleles"); }
   r->nEntries = P.entries.size();
   P.entries.resize(P.entries.size() + 4, KmerEntry{0xffffffffu, 0, 0, 0});
-  UP(kinfo, P.kinfo); UP(entries, P.entries);
+  UP(kinfo, P.kinfo); UP(entries, P.entries); UP(dCovOff, P.covOff);
   std::vector<u16> simThr(2 * SIM_DEN);
   sim_threshold_table(d->similarity, simThr.data());
   UP(dSimThr, simThr);
 #undef UP
-  const size_t covBytes = r->paddedBases * sizeof(int32_t);
+  const size_t covBytes = r->covEntries * sizeof(int32_t);
   e = r->covDiff.alloc(covBytes);
   if (e == cudaSuccess) e = r->covPoint.alloc(covBytes);
   if (e == cudaSuccess) e = r->covFinal.alloc(covBytes);
@@ -290,7 +292,7 @@ int t1k_ref_create(const T1KRefDesc *d, T1KRef **out) {
   R.seq2 = r->seq2.as<u64>(); R.n2 = r->n2.as<u64>(); R.ex2 = r->ex2.as<u64>();
   R.wordOff = r->dWordOff.as<u64>(); R.len = r->dLen.as<int32_t>(); R.hasN = r->dHasN.as<u8>(); R.meta = r->dMeta.as<AlleleMeta>(); R.simThr = r->dSimThr.as<u16>();
   R.kstart = nullptr; R.post = nullptr; R.kinfo = r->kinfo.as<KmerInfo>(); R.entries = r->entries.as<KmerEntry>();
-  R.covDiff = r->covDiff.as<int32_t>(); R.covPoint = r->covPoint.as<int32_t>();
+  R.covDiff = r->covDiff.as<int32_t>(); R.covPoint = r->covPoint.as<int32_t>(); R.covOff = r->dCovOff.as<u64>();
   R.nAlleles = d->n_alleles; R.sim = d->similarity; R.relax = d->relax_intron;
   {
     size_t freeB = 0, totB = 0;
@@ -321,9 +323,9 @@ const void *seed_kernel(int occ) {
 int setup_assign_launch(T1KRef *r, int maxLen) {
   int seedCap = std::max(64, (maxLen - KMER + 1 + 31) & ~31);
   // resident blocks per SM k_seed is compiled for (register budget): T1K_ASSIGN_OCC
-  int occ = 4;
+  int occ = 6;      // measured: 6 blocks/SM (80 registers) beats 4, 5 and 8
   if (const char *env = getenv("T1K_ASSIGN_OCC")) occ = atoi(env);
-  if (occ < 2 || occ > 8) occ = 4;
+  if (occ < 2 || occ > 8) occ = 6;
   int hitCap = 1024;     // hits of one allele the hit-list path holds (HBM scratch; a 255-base read has <= 245 seeds)
   if (const char *env = getenv("T1K_HIT_CAP")) hitCap = std::max(64, atoi(env));
   if (r->gridBlocks && seedCap <= r->seedCap && occ == r->occ && hitCap == r->hitCap) return T1K_OK;
@@ -590,10 +592,10 @@ namespace {
 __global__ void k_cov_prefix(RefView R, int32_t *covFinal) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= R.nAlleles) return;
-  const size_t cb = (size_t)R.wordOff[a] * 32;
+  const size_t cb = (size_t)R.covOff[a];        // (the threads of a warp walk the 32 interleaved alleles of a tile: coalesced)
   int run = 0;
   const int n = R.len[a];
-  for (int j = 0; j < n; ++j) { run += R.covDiff[cb + j]; covFinal[cb + j] = run + R.covPoint[cb + j]; }
+  for (int j = 0; j < n; ++j) { const size_t k = cb + (size_t)COV_STRIDE * j; run += R.covDiff[k]; covFinal[k] = run + R.covPoint[k]; }
 }
 
 // SeqSet::GetSeqMissingBaseCoverage(a, 0.01) (SeqSet.hpp:2717-2755), one warp per allele: the median of the
@@ -603,11 +605,11 @@ __global__ void k_missing_coverage(RefView R, const int32_t *covFinal, int32_t *
   const int lane = threadIdx.x & 31;
   if (a >= R.nAlleles) return;
   const u64 w0 = R.wordOff[a];
-  const size_t cb = (size_t)w0 * 32;
+  const size_t cb = (size_t)R.covOff[a];
   const int n = R.len[a];
   int nEx = 0, mx = 0;
   for (int j = lane; j < n; j += 32)
-    if (base2(R.ex2, w0, j)) { ++nEx; const int c = base2(R.n2, w0, j) ? 0 : covFinal[cb + j]; mx = max(mx, c); }
+    if (base2(R.ex2, w0, j)) { ++nEx; const int c = base2(R.n2, w0, j) ? 0 : covFinal[cb + (size_t)COV_STRIDE * j]; mx = max(mx, c); }
   nEx = warp_sum_i32(nEx); mx = warp_max_i32(mx);
   if (nEx == 0) { if (lane == 0) out[a] = 0; return; }
   const int k = nEx / 2;            // median = element k of the sorted list
@@ -616,7 +618,7 @@ __global__ void k_missing_coverage(RefView R, const int32_t *covFinal, int32_t *
     const int mid = lo + (hi - lo) / 2;
     int c = 0;
     for (int j = lane; j < n; j += 32)
-      if (base2(R.ex2, w0, j)) { const int v = base2(R.n2, w0, j) ? 0 : covFinal[cb + j]; c += v <= mid; }
+      if (base2(R.ex2, w0, j)) { const int v = base2(R.n2, w0, j) ? 0 : covFinal[cb + (size_t)COV_STRIDE * j]; c += v <= mid; }
     c = warp_sum_i32(c);
     if (c >= k + 1) hi = mid; else lo = mid + 1;
   }
@@ -624,7 +626,7 @@ __global__ void k_missing_coverage(RefView R, const int32_t *covFinal, int32_t *
   if (cutoff < 1) cutoff = 1;
   int miss = 0;
   for (int j = lane; j < n; j += 32)
-    if (base2(R.ex2, w0, j)) { const int v = base2(R.n2, w0, j) ? 0 : covFinal[cb + j]; miss += (double)v < cutoff; }
+    if (base2(R.ex2, w0, j)) { const int v = base2(R.n2, w0, j) ? 0 : covFinal[cb + (size_t)COV_STRIDE * j]; miss += (double)v < cutoff; }
   miss = warp_sum_i32(miss);
   if (lane == 0) out[a] = miss;
 }
@@ -646,19 +648,19 @@ int t1k_coverage_fetch(T1KRef *ref, int32_t *out) {
   if (!ref || !out) return fail(T1K_ERR_ARG, "t1k_coverage_fetch: bad argument");
   CK(cudaSetDevice(ref->device));
   if (int rc = finalize_coverage(ref)) return rc;
-  std::vector<int32_t> h(ref->paddedBases);
-  CK(cudaMemcpyAsync(h.data(), ref->covFinal.p, ref->paddedBases * 4, cudaMemcpyDeviceToHost, ref->stream));
+  std::vector<int32_t> h(ref->covEntries);
+  CK(cudaMemcpyAsync(h.data(), ref->covFinal.p, ref->covEntries * 4, cudaMemcpyDeviceToHost, ref->stream));
   CK(cudaStreamSynchronize(ref->stream));
   for (int32_t a = 0; a < ref->nAlleles; ++a)
-    memcpy(out + ref->offset[a], h.data() + (size_t)ref->wordOff[a] * 32, (size_t)ref->len[a] * 4);
+    for (int32_t j = 0; j < ref->len[a]; ++j) out[ref->offset[a] + j] = h[(size_t)ref->covOff[a] + (size_t)COV_STRIDE * j];
   return T1K_OK;
 }
 
 int t1k_coverage_reset(T1KRef *ref) {
   if (!ref) return fail(T1K_ERR_ARG, "t1k_coverage_reset: bad argument");
   CK(cudaSetDevice(ref->device));
-  CK(cudaMemsetAsync(ref->covDiff.p, 0, ref->paddedBases * 4, ref->stream));
-  CK(cudaMemsetAsync(ref->covPoint.p, 0, ref->paddedBases * 4, ref->stream));
+  CK(cudaMemsetAsync(ref->covDiff.p, 0, ref->covEntries * 4, ref->stream));
+  CK(cudaMemsetAsync(ref->covPoint.p, 0, ref->covEntries * 4, ref->stream));
   CK(cudaStreamSynchronize(ref->stream));
   ref->covDirty = true;
   return T1K_OK;
@@ -978,8 +980,8 @@ int t1k_coverage_allreduce(T1KRef *ref, T1KComm *comm) {
   if (comm->world == 1) return T1K_OK;
   CK(cudaSetDevice(ref->device));
   // coverage = prefix(covDiff) + covPoint is linear in both arrays: sum them where they lie
-  NK(nccl().AllReduce(ref->covDiff.p, ref->covDiff.p, ref->paddedBases, NCCL_INT32, NCCL_SUM, comm->comm, ref->stream));
-  NK(nccl().AllReduce(ref->covPoint.p, ref->covPoint.p, ref->paddedBases, NCCL_INT32, NCCL_SUM, comm->comm, ref->stream));
+  NK(nccl().AllReduce(ref->covDiff.p, ref->covDiff.p, ref->covEntries, NCCL_INT32, NCCL_SUM, comm->comm, ref->stream));
+  NK(nccl().AllReduce(ref->covPoint.p, ref->covPoint.p, ref->covEntries, NCCL_INT32, NCCL_SUM, comm->comm, ref->stream));
   CK(cudaStreamSynchronize(ref->stream));
   ref->covDirty = true;
   return T1K_OK;
@@ -1100,8 +1102,8 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     unique_read_ends(reads1, reads2, stride, f0, m, T1K_MAX_READ_LEN, prepThreads, C);
     C.ms = now_ms() - t;
   };
-  CK(cudaMemsetAsync(ref->covDiff.p, 0, ref->paddedBases * 4, ref->stream));
-  CK(cudaMemsetAsync(ref->covPoint.p, 0, ref->paddedBases * 4, ref->stream));
+  CK(cudaMemsetAsync(ref->covDiff.p, 0, ref->covEntries * 4, ref->stream));
+  CK(cudaMemsetAsync(ref->covPoint.p, 0, ref->covEntries * 4, ref->stream));
   ref->covDirty = true;
   ReadGroups groups;
   int hostThreads = (int)std::thread::hardware_concurrency() / ((prm->comm && prm->comm->world > 1) ? prm->comm->world : 1);

@@ -72,8 +72,12 @@ struct RefView {
   const Posting *post;
   const KmerInfo *kinfo; // [4^K + 1]
   const KmerEntry *entries;
-  int32_t *covDiff;      // range-add difference array, indexed by padded base (wordOff*32 + pos)
-  int32_t *covPoint;     // point corrections
+  // coverage: range-add difference array + point corrections.  Layout: the 32 alleles of a tile are interleaved position by
+  // position (entry of allele a, base p = covOff[a] + 32 * p, covOff[a] = first entry of the tile + (a & 31)), so the lanes of
+  // a warp, which hold neighbouring alleles at the same read-relative position, hit neighbouring words: their atomics
+  // coalesce into a few sectors instead of 32 sectors kilobytes apart.
+  int32_t *covDiff, *covPoint;
+  const u64 *covOff;     // [nAlleles]
   int32_t nAlleles;
   double sim;
   int32_t relax;
@@ -194,6 +198,7 @@ T1K_HD int imin(int a, int b) { return a < b ? a : b; }
 T1K_HD int imax(int a, int b) { return a > b ? a : b; }
 T1K_HD int iabs(int a) { return a < 0 ? -a : a; }
 
+constexpr int COV_STRIDE = 32;
 T1K_HD void cov_add(int32_t *p, int v) {
 #ifdef __CUDA_ARCH__
   atomicAdd(p, v);
@@ -209,6 +214,9 @@ T1K_HD u64 fetch32(const u64 *plane, int pos) {
   return (p[0] >> sh) | ((p[1] << 1) << (63 - sh));      // branch-free funnel shift (sh in 0..62)
 }
 T1K_HD u64 fetch32(const u64 *plane, u64 w0, int pos) { return fetch32(plane + w0, pos); }
+// 128-bit funnel shifts of a two-word value, 0 < s < 64
+T1K_HD u64 shr2w(u64 lo, u64 hi, int s) { return (lo >> s) | (hi << (64 - s)); }
+T1K_HD u64 shl2w(u64 hi, u64 lo, int s) { return (hi << s) | (lo >> (64 - s)); }
 T1K_HD int base2(const u64 *plane, int pos) { return (int)((plane[pos >> 5] >> ((pos & 31) * 2)) & 3); }
 T1K_HD int base2(const u64 *plane, u64 w0, int pos) { return base2(plane + w0, pos); }
 T1K_HD u64 lowmask2(int nBases) { return nBases >= 32 ? ~0ull : ((1ull << (2 * nBases)) - 1); }
@@ -344,7 +352,7 @@ T1K_HDN T1K_NOINLINE inline bool diag_certified_hist(const AlleleView &T, int tp
 // into a match, -1: diagonal match that shift d turns into a mismatch).  If G_d <= 1 for every shift of the band the sum
 // is at most k: no excursion gains, the traceback stays on the diagonal.  G_d <= 1 iff between every two consecutive
 // "+1" rows of shift d lies at least one "-1" row.
-T1K_HDN T1K_NOINLINE inline bool diag_certified_interval(const AlleleView &T, int tpos, const ReadView &Q, int ppos, int n) {
+T1K_HDN T1K_NOINLINE inline bool diag_certified_interval_n(const AlleleView &T, int tpos, const ReadView &Q, int ppos, int n) {
   T1K_NOUNROLL
   for (int d = -BAND; d <= BAND; ++d) {
     if (d == 0) continue;
@@ -372,6 +380,50 @@ T1K_HDN T1K_NOINLINE inline bool diag_certified_interval(const AlleleView &T, in
   }
   return true;
 }
+// The same test for windows without N (the usual case), 32 rows at a time for all ten shifts at once: the allele bases
+// tpos + r - 5 .. tpos + r + 36 are fetched once per 32 rows and every shift is a funnel shift of those two words.
+T1K_HDN T1K_NOINLINE inline bool diag_certified_interval(const AlleleView &T, int tpos, const ReadView &Q, int ppos, int n) {
+  if (T.useN) return diag_certified_interval_n(T, tpos, Q, ppos, n);
+  u32 pendingBits = 0;                                                  // bit d + BAND: shift d has a "+1" row with no "-1" row after it yet
+  T1K_NOUNROLL
+  for (int r0 = 0; r0 < n; r0 += 32) {
+    const int cnt = n - r0 < 32 ? n - r0 : 32;
+    const u64 q = fetch32(Q.seq2, ppos + r0);
+    const u64 tl = fetch32(T.seq, tpos + r0 - BAND), th = fetch32(T.seq, tpos + r0 - BAND + 32);
+    const u64 rows = lowmask2(cnt) & M55;
+    u64 a;
+    { const u64 x = shr2w(tl, th, 2 * BAND) ^ q; a = (x | (x >> 1)) & rows; }
+    T1K_NOUNROLL
+    for (int d = -BAND; d <= BAND; ++d) {
+      if (d == 0) continue;
+      const u64 t = d == -BAND ? tl : shr2w(tl, th, 2 * (d + BAND));
+      const u64 x = t ^ q;
+      // rows of this chunk that have a column at shift d: max(0, -d) <= r <= min(n - 1, n - 1 - d)
+      u64 vm = rows;
+      if (r0 < BAND || r0 + 32 + BAND > n) {          // only the first and the last rows lack a column at some shift
+        const int lo = (d < 0 ? -d : 0) - r0, hi = (d > 0 ? n - 1 - d : n - 1) - r0 + 1;
+        vm = (hi <= 0 ? 0ull : hi >= 32 ? ~0ull : ((1ull << (2 * hi)) - 1)) & ~(lo <= 0 ? 0ull : lo >= 32 ? ~0ull : ((1ull << (2 * lo)) - 1)) & rows;
+      }
+      const u64 sft = (x | (x >> 1)) & vm;
+      u64 plus = a & ~sft & vm;
+      const u64 minus = ~a & sft;
+      bool pending = (pendingBits >> (d + BAND)) & 1u;
+      u64 done = 0;
+      T1K_NOUNROLL
+      while (plus) {
+        const u64 b = plus & (~plus + 1);
+        const u64 below = b - 1;
+        if (pending && (minus & below & ~done) == 0) return false;
+        pending = true;
+        done = below | b;
+        plus &= plus - 1;
+      }
+      if (minus & ~done) pending = false;
+      pendingBits = (pendingBits & ~(1u << (d + BAND))) | ((u32)pending << (d + BAND));
+    }
+  }
+  return true;
+}
 
 T1K_HD bool diag_certified(const AlleleView &T, int tpos, const ReadView &Q, int ppos, int n, int &mmOut) {
   int mm = 0;
@@ -385,7 +437,7 @@ T1K_HD bool diag_certified(const AlleleView &T, int tpos, const ReadView &Q, int
   // 4-5: the cheap sufficient tests first, the exact enumeration only when they cannot tell
   if (mm <= 5) return diag_certified_interval(T, tpos, Q, ppos, n) || diag_certified_45(T, tpos, Q, ppos, n, mm);
   if (mm > 24) return false;
-  return diag_certified_hist(T, tpos, Q, ppos, n) || diag_certified_interval(T, tpos, Q, ppos, n);
+  return diag_certified_interval(T, tpos, Q, ppos, n) || diag_certified_hist(T, tpos, Q, ppos, n);
 }
 
 // The equal-length case of dp_align below (99.9 % of the calls): band 5 on both sides, 13 window columns, the two rolling
@@ -836,6 +888,7 @@ T1K_HDN T1K_NOINLINE inline int diag_fast(const RefView &R, const ReadView &Q, i
                               const u32 *stab, bool hot, Cand &out, bool &emitted, u64 &bestStrandKey, u32 &lcMemo, const LaneScratch &S, int &err) {
   emitted = false;
   bool needCold = false;
+  u32 coldGap[4]; int nColdGap = 0;      // full mode: the first dirty gaps (read position | length << 16)
   const int len = Q.len;
 #ifdef __CUDA_ARCH__
   const uint4 mt = *reinterpret_cast<const uint4 *>(R.meta + seqIdx);
@@ -897,6 +950,7 @@ T1K_HDN T1K_NOINLINE inline int diag_fast(const RefView &R, const ReadView &Q, i
               // a long or dirty gap: the same GlobalAlignment the hit-list walk would run (certificates, else the band
               // DP), the rest of the allele stays on this path.  No N in the window => the N planes are not consulted.
               if (hot) needCold = true;
+              else if (nColdGap < 4) { coldGap[nColdGap++] = (u32)(lastL + KMER) | ((u32)g << 16); }       // aligned after the scan, see below
               else {
               AlleleView T;
               T.seq = R.seq2 + w0; T.n2 = R.n2 + w0; T.ex2 = R.ex2 + w0; T.len = clen; T.hasN = alleleHasN; T.useN = false;
@@ -932,6 +986,17 @@ T1K_HDN T1K_NOINLINE inline int diag_fast(const RefView &R, const ReadView &Q, i
   // ---- from here on the result is the reference's: the tail of consume_chain<true>
   if (hitLen < HIT_LEN_REQ) return DF_DONE;
   if (needCold) return DF_DEFER;
+  if (nColdGap > 0) {
+    // the dirty gaps of the scan, aligned here so that the lanes of a warp (every one on an allele of its own in k_deferred)
+    // run their alignments together instead of one after the other from inside the scan
+    AlleleView T;
+    T.seq = R.seq2 + w0; T.n2 = R.n2 + w0; T.ex2 = R.ex2 + w0; T.len = clen; T.hasN = alleleHasN; T.useN = false;
+    T1K_NOUNROLL
+    for (int i = 0; i < nColdGap; ++i) {
+      const int gp = (int)(coldGap[i] & 0xffffu), g = (int)(coldGap[i] >> 16);
+      gapMatches += align_matches_cold(T, gp + d, g, Q, gp, g, S, err);
+    }
+  }
   const int re = lastL + KMER - 1, mmRight = mmRun;
   const u64 sk = strand_key(2 * hitLen, re - rs, seqIdx, strand01);
   if (sk > bestStrandKey) bestStrandKey = sk;
@@ -984,8 +1049,11 @@ T1K_HDN T1K_NOINLINE inline int diag_fast(const RefView &R, const ReadView &Q, i
 // (DESIGN.md "diagonal certificate", any length), so matchCnt = 2 * (span - mismatches inside the span).  A gap with more
 // mismatches, or an overhang with more than 3, needs the real alignment: DF_DEFER.  lcp: prefix base counts of the strand
 // (lc_prefix_build) for IsOverlapLowComplex.
-T1K_HD u64 shr2w(u64 lo, u64 hi, int s) { return (lo >> s) | (hi << (64 - s)); }       // 0 < s < 64
-T1K_HD u64 shl2w(u64 hi, u64 lo, int s) { return (hi << s) | (lo >> (64 - s)); }
+// bits 2p (p < b) of word j (positions 32j .. 32j+31)
+T1K_HD u64 below_mask2(int j, int b) {
+  const int hi = b - 32 * j;
+  return hi <= 0 ? 0ull : hi >= 32 ? M55 : (((1ull << (2 * hi)) - 1) & M55);
+}
 // bits 2p (p in [a, b)) of word j (positions 32j .. 32j+31)
 T1K_HD u64 range_mask2(int j, int a, int b) {
   int lo = a - 32 * j, hi = b - 32 * j;
@@ -1046,7 +1114,7 @@ T1K_HDN T1K_NOINLINE inline int diag_hot(const RefView &R, const ReadView &Q, in
   for (int j = 0; j < 5; ++j) {
     const u64 t = sh ? shr2w(tw[j], tw[j + 1], sh) : tw[j];
     const u64 x = t ^ Q.seq2[j];
-    const u64 in = range_mask2(j, pLo, pHi);
+    const u64 in = below_mask2(j, pHi) & ~below_mask2(j, pLo);
     M[j] = (x | (x >> 1)) & in;
     B[j] = M[j] | (~in & M55);
     mmTot += popc64(M[j]);
@@ -1109,15 +1177,20 @@ T1K_HDN T1K_NOINLINE inline int diag_hot(const RefView &R, const ReadView &Q, in
   if (hitLen < HIT_LEN_REQ) return DF_DONE;
   const int re = lastL + KMER - 1;
   int mmInside = 0, mmLeft = 0;
+  u64 SP[5];                         // M restricted to the span [rs, re]
 #pragma unroll
-  for (int j = 0; j < 5; ++j) { mmInside += popc64(M[j] & range_mask2(j, rs, re + 1)); mmLeft += popc64(M[j] & range_mask2(j, 0, rs)); }
+  for (int j = 0; j < 5; ++j) {
+    const u64 bl = below_mask2(j, rs), bh = below_mask2(j, re + 1);
+    SP[j] = M[j] & bh & ~bl;
+    mmInside += popc64(SP[j]); mmLeft += popc64(M[j] & bl);
+  }
   const int mmRight = mmTot - mmInside - mmLeft;
   if (mmInside > 3) {
     // does one gap (a maximal stretch of [rs, re] that U does not cover) hold more than 3 mismatches?
     int cnt = 0; bool pendingU = false, dirty = false;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
-      u64 g = M[j] & range_mask2(j, rs, re + 1), done = 0;
+      u64 g = SP[j], done = 0;
       T1K_NOUNROLL
       while (g) {
         const u64 b = g & (~g + 1), below = b - 1;
@@ -1177,12 +1250,12 @@ T1K_HD void full_align_known(const RefView &R, Cand &c, int weight) {
   const int mm = (int)((c.mmPos >> 24) & 3), exMm = (int)((c.mmPos >> 26) & 3);
   const int lent = c.eSeqEnd - c.eSeqStart + 1;
   if (weight > 0) {
-    const size_t cb = (size_t)R.wordOff[c.seqIdx] * 32;
+    const size_t cb = (size_t)R.covOff[c.seqIdx];
     const int dd = c.eSeqStart - (int)c.eReadStart;
-    cov_add(R.covDiff + cb + c.eSeqStart, weight); cov_add(R.covDiff + cb + c.eSeqStart + lent, -weight);
-    if (mm > 0) cov_add(R.covPoint + cb + dd + (int)(c.mmPos & 255), -weight);
-    if (mm > 1) cov_add(R.covPoint + cb + dd + (int)((c.mmPos >> 8) & 255), -weight);
-    if (mm > 2) cov_add(R.covPoint + cb + dd + (int)((c.mmPos >> 16) & 255), -weight);
+    cov_add(R.covDiff + cb + (size_t)COV_STRIDE * c.eSeqStart, weight); cov_add(R.covDiff + cb + (size_t)COV_STRIDE * (c.eSeqStart + lent), -weight);
+    if (mm > 0) cov_add(R.covPoint + cb + (size_t)COV_STRIDE * (dd + (int)(c.mmPos & 255)), -weight);
+    if (mm > 1) cov_add(R.covPoint + cb + (size_t)COV_STRIDE * (dd + (int)((c.mmPos >> 8) & 255)), -weight);
+    if (mm > 2) cov_add(R.covPoint + cb + (size_t)COV_STRIDE * (dd + (int)((c.mmPos >> 16) & 255)), -weight);
   }
   c.relaxed = R.relax ? 2 * (lent - exMm) : c.eMatchCnt;
 }
@@ -1391,16 +1464,16 @@ T1K_HDN T1K_NOINLINE inline void full_align_cold(const RefView &R, const ReadVie
                                     const LaneScratch &S, int &err) {
   const int tpos = c.eSeqStart, ppos = c.eReadStart;
   const int lent = c.eSeqEnd - c.eSeqStart + 1, lenp = c.eReadEnd - c.eReadStart + 1;
-  int32_t *covDiff = R.covDiff + (size_t)R.wordOff[c.seqIdx] * 32, *covPoint = R.covPoint + (size_t)R.wordOff[c.seqIdx] * 32;
+  int32_t *covDiff = R.covDiff + (size_t)R.covOff[c.seqIdx], *covPoint = R.covPoint + (size_t)R.covOff[c.seqIdx];
   if (lent == lenp) {
     bool diag = mm <= 3;
     if (!diag) {
       if (mm <= 5) diag = diag_certified_interval(T, tpos, Q, ppos, lent) || diag_certified_45(T, tpos, Q, ppos, lent, mm);
-      else if (mm <= 24) diag = diag_certified_hist(T, tpos, Q, ppos, lent) || diag_certified_interval(T, tpos, Q, ppos, lent);
+      else if (mm <= 24) diag = diag_certified_interval(T, tpos, Q, ppos, lent) || diag_certified_hist(T, tpos, Q, ppos, lent);
     }
     if (diag) {
       if (weight > 0) {
-        cov_add(covDiff + tpos, weight); cov_add(covDiff + tpos + lent, -weight);
+        cov_add(covDiff + (size_t)COV_STRIDE * tpos, weight); cov_add(covDiff + (size_t)COV_STRIDE * (tpos + lent), -weight);
         T1K_NOUNROLL
         for (int k = 0; k < lent; k += 32) {
           u64 un = mm_chunk(T, tpos + k, Q, ppos + k, lent - k);
@@ -1409,7 +1482,7 @@ T1K_HDN T1K_NOINLINE inline void full_align_cold(const RefView &R, const ReadVie
           while (un) {
             const int p = k + (ctz64(un) >> 1);
             un &= un - 1;
-            cov_add(covPoint + tpos + p, -weight);
+            cov_add(covPoint + (size_t)COV_STRIDE * (tpos + p), -weight);
           }
         }
       }
@@ -1431,7 +1504,7 @@ T1K_HDN T1K_NOINLINE inline void full_align_cold(const RefView &R, const ReadVie
     }
     if (weight > 0 && op == 0 && readPos < Q.len && refPos < T.len && !base2(Q.n2, readPos) &&
         !base2(T.n2, refPos) && base2(T.seq, refPos) == base2(Q.seq2, readPos))
-      cov_add(covPoint + refPos, weight);
+      cov_add(covPoint + (size_t)COV_STRIDE * refPos, weight);
     if (op != 2) ++refPos;
     if (op != 3) ++readPos;
   }
@@ -1466,11 +1539,11 @@ T1K_HDN T1K_NOINLINE inline bool full_align(const RefView &R, const ReadView &Q,
   if (lent == lenp) {
     if (mm <= 3 && !T.useN) {
       if (weight > 0) {
-        int32_t *covDiff = R.covDiff + (size_t)R.wordOff[c.seqIdx] * 32, *covPoint = R.covPoint + (size_t)R.wordOff[c.seqIdx] * 32;
-        cov_add(covDiff + tpos, weight); cov_add(covDiff + tpos + lent, -weight);
-        if (mm > 0) cov_add(covPoint + tpos + p0, -weight);
-        if (mm > 1) cov_add(covPoint + tpos + p1, -weight);
-        if (mm > 2) cov_add(covPoint + tpos + p2, -weight);
+        int32_t *covDiff = R.covDiff + (size_t)R.covOff[c.seqIdx], *covPoint = R.covPoint + (size_t)R.covOff[c.seqIdx];
+        cov_add(covDiff + (size_t)COV_STRIDE * tpos, weight); cov_add(covDiff + (size_t)COV_STRIDE * (tpos + lent), -weight);
+        if (mm > 0) cov_add(covPoint + (size_t)COV_STRIDE * (tpos + p0), -weight);
+        if (mm > 1) cov_add(covPoint + (size_t)COV_STRIDE * (tpos + p1), -weight);
+        if (mm > 2) cov_add(covPoint + (size_t)COV_STRIDE * (tpos + p2), -weight);
       }
       c.relaxed = R.relax ? 2 * (lent - exMm) : c.eMatchCnt;
       return true;

@@ -25,6 +25,8 @@ struct PackedRef {
   std::vector<Posting> post;
   // the device's form of the index (see KmerEntry in t1k_core.cuh): per k-mer the postings regrouped by
   // (tile of 32 consecutive alleles, offset) with one allele bit mask per entry
+  std::vector<u64> covOff;            // [nAlleles] first coverage entry of the allele (tile-interleaved layout, see RefView)
+  size_t covEntries = 0;
   std::vector<KmerInfo> kinfo;        // [4^K + 1]
   std::vector<KmerEntry> entries;
   size_t totalWords = 0;
@@ -119,6 +121,16 @@ inline bool pack_reference(int32_t n, const char *bases, const int64_t *off, con
   }
   P.meta.resize(n);
   for (int i = 0; i < n; ++i) { P.meta[i].wordOff = P.wordOff[i]; P.meta[i].len = P.len[i]; P.meta[i].hasN = P.hasN[i]; }
+  // coverage layout: per tile of 32 alleles, 32 x (longest allele of the tile + 2) interleaved entries
+  P.covOff.resize(n);
+  size_t cov = 0;
+  for (int t0 = 0; t0 < n; t0 += 32) {
+    int longest = 0;
+    for (int i = t0; i < n && i < t0 + 32; ++i) longest = std::max(longest, P.len[i]);
+    for (int i = t0; i < n && i < t0 + 32; ++i) P.covOff[i] = cov + (size_t)(i - t0);
+    cov += (size_t)32 * ((size_t)longest + 2);
+  }
+  P.covEntries = cov;
   build_tile_index(P);
   return true;
 }

@@ -353,7 +353,33 @@ __device__ u32 seed_one_read(const AssignParams &P, u32 r, const WarpSmem &W, Ca
         T1K_NOUNROLL
         for (int k0 = 0; k0 < nS; k0 += 32) {
           const int k = k0 + lane;
-          unsigned bal = __ballot_sync(FULL, k < nS && W.ent[k].x == T);
+          uint4 me = make_uint4(0xffffffffu, 0, 0, 0);
+          if (k < nS) me = W.ent[k];
+          const bool act = me.x == T;
+          unsigned bal = __ballot_sync(FULL, act);
+          if (bal == 0) continue;
+          // Usual case: every active seed of the chunk has ONE entry in this tile and all lie on one diagonal D (the alleles of
+          // a tile are neighbours of one gene).  Then lane = seed holds a 32-allele mask, and the per-allele hit counts are the
+          // column sums of that 32 x 32 bit matrix: transposed through five butterfly shuffles instead of walking the seeds.
+          const int dgk = (int)me.y - (int)W.seedA[k < nS ? k : 0];
+          const int D = __shfl_sync(FULL, dgk, __ffs(bal) - 1);
+          if (!__any_sync(FULL, act && (me.w != 0 || dgk != D))) {
+            u32 x = act ? me.z : 0u;
+            u32 m = 0x0000ffffu;
+#pragma unroll
+            for (int j = 16; j; j >>= 1) {
+              const u32 y = __shfl_xor_sync(FULL, x, j);
+              x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
+              m ^= m << (j >> 1);
+            }
+            const int c = __popc(x);                    // hits of allele T*32 + lane from this chunk's seeds, all on diagonal D
+            if (c) {
+              if (n == 0) d0 = D;
+              const int dd = D - d0;
+              n += c; onDiag += dd == 0 ? c : 0; far += ((dd > RADIUS) | (dd < -RADIUS)) ? c : 0;
+            }
+            continue;
+          }
           T1K_NOUNROLL
           while (bal) {
             const int kk = k0 + __ffs(bal) - 1;

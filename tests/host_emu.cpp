@@ -33,14 +33,14 @@ Emu *emu_create(int32_t n, const char *bases, const int64_t *off, const int32_t 
                 double sim, int32_t relax) {
   Emu *e = new Emu;
   if (!pack_reference(n, bases, off, exonPtr, exonSE, e->P)) { delete e; return NULL; }
-  e->covDiff.assign(e->P.totalWords * 32, 0);
-  e->covPoint.assign(e->P.totalWords * 32, 0);
+  e->covDiff.assign(e->P.covEntries, 0);
+  e->covPoint.assign(e->P.covEntries, 0);
   RefView &R = e->R;
   R.seq2 = e->P.seq2.data(); R.n2 = e->P.n2.data(); R.ex2 = e->P.ex2.data();
   R.wordOff = e->P.wordOff.data(); R.len = e->P.len.data(); R.hasN = e->P.hasN.data(); R.meta = e->P.meta.data();
   e->simThr.resize(2 * SIM_DEN); sim_threshold_table(sim, e->simThr.data()); R.simThr = e->simThr.data();
   R.kstart = e->P.kstart.data(); R.post = e->P.post.data(); R.kinfo = e->P.kinfo.data(); R.entries = e->P.entries.data();
-  R.covDiff = e->covDiff.data(); R.covPoint = e->covPoint.data();
+  R.covDiff = e->covDiff.data(); R.covPoint = e->covPoint.data(); R.covOff = e->P.covOff.data();
   R.nAlleles = n; R.sim = sim; R.relax = relax;
   e->scratch.assign(SCR_BYTES, 0);
   return e;
@@ -52,12 +52,13 @@ void emu_set_fast(Emu *e, int on) { e->noFast = !on; }
 int32_t emu_align(const char *t, int32_t lent, const char *p, int32_t lenp, int8_t *opsOut, int32_t *certified,
                   int32_t *matches) {
   // build a one-allele reference holding t and a read holding p
-  std::vector<u64> seq2((lent + 31) / 32 + 3, 0), n2(seq2.size(), 0), ex2(seq2.size(), 0);
+  // (two pad words in front, as in the packed reference: the certificates read a few bases before the window)
+  std::vector<u64> seq2((lent + 31) / 32 + 5, 0), n2(seq2.size(), 0), ex2(seq2.size(), 0);
   for (int j = 0; j < lent; ++j) {
-    seq2[j >> 5] |= (u64)code_of(t[j]) << ((j & 31) * 2);
-    if (t[j] == 'N') n2[j >> 5] |= 1ull << ((j & 31) * 2);
+    seq2[2 + (j >> 5)] |= (u64)code_of(t[j]) << ((j & 31) * 2);
+    if (t[j] == 'N') n2[2 + (j >> 5)] |= 1ull << ((j & 31) * 2);
   }
-  u64 w0 = 0; int32_t len = lent;
+  u64 w0 = 2; int32_t len = lent;
   u8 tHasN = memchr(t, 'N', lent) != NULL;
   RefView R; memset(&R, 0, sizeof(R));
   R.seq2 = seq2.data(); R.n2 = n2.data(); R.ex2 = ex2.data(); R.wordOff = &w0; R.len = &len; R.hasN = &tHasN; R.nAlleles = 1;
@@ -112,6 +113,7 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
       }
       prev = code;
     }
+    t1k_emu_counters[52] += 1; t1k_emu_counters[53] += nS;
     u32 stab[256];
     if (strandFast) seed_table_build(seedA, nS, len, stab);
     u32 lcMemo = 0;
@@ -128,6 +130,8 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
       u32 T = 0xffffffffu;
       for (int k = 0; k < nS; ++k) if (cur[k] < end[k]) T = std::min(T, R.entries[cur[k]].tile);
       if (T == 0xffffffffu) break;
+      t1k_emu_counters[50] += 1;
+      for (int k = 0; k < nS; ++k) if (cur[k] < end[k] && R.entries[cur[k]].tile == T) t1k_emu_counters[51] += 1 + R.entries[cur[k]].more;
       for (int lane = 0; lane < 32; ++lane) {
         // sweep 1: the allele's hit count, first diagonal, hits on / far off that diagonal
         int n = 0, d0 = 0, onDiag = 0, far = 0;
@@ -304,9 +308,9 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
 
 // coverage of one allele = prefix(covDiff) + covPoint
 void emu_coverage(Emu *E, int32_t allele, int32_t *out) {
-  size_t cb = (size_t)E->P.wordOff[allele] * 32;
+  size_t cb = (size_t)E->P.covOff[allele];
   int run = 0;
-  for (int j = 0; j < E->P.len[allele]; ++j) { run += E->covDiff[cb + j]; out[j] = run + E->covPoint[cb + j]; }
+  for (int j = 0; j < E->P.len[allele]; ++j) { run += E->covDiff[cb + (size_t)COV_STRIDE * j]; out[j] = run + E->covPoint[cb + (size_t)COV_STRIDE * j]; }
 }
 
 }  // extern "C"
