@@ -150,8 +150,9 @@ typedef struct {
   const int32_t *allele_major, *allele_gene; int32_t n_major, n_gene;
   int32_t em_fast_sums;        /* T1KEmProblem.fast_sums */
   /* read-sharded run: reads1/reads2 are THIS rank's fragments.  Alignment + pairing + coalescing run per rank with no
-   * data-path collective; then one int32 all-reduce of the base coverage, one all-gather of the per-rank read-group
-   * tables (merged in rank order on every rank) and the sharded EM.  Per-allele outputs are identical on all ranks;
+   * data-path collective; then a status exchange (a failure on one rank fails every rank instead of hanging the others),
+   * one int32 all-reduce of the base coverage, the read-group tables merged 1/world per rank (all-to-all of the hash
+   * partitions, all-gather of the merged partitions) and the sharded EM.  Per-allele outputs are identical on all ranks;
    * fragment_assigned / n_unique_ends / n_overlaps / timings are this rank's.  NULL = single GPU. */
   T1KComm *comm;
 } T1KGenotypeParams;
@@ -169,6 +170,11 @@ typedef struct {
   float ms_align_kernel, ms_pair_kernel, ms_em_kernel;      /* device time (CUDA events) inside k_assign / k_pair / the EM kernels */
   uint64_t n_postings, n_candidates;                        /* k-mer postings read and seed overlaps chained (roofline accounting) */
   uint64_t n_launches;                                      /* kernels launched by this call */
+  float ms_prep_wait;                                       /* part of ms_dedup the device stage had to wait for (not overlapped) */
+  float ms_exchange;                                        /* read-sharded run: status / table exchange + merge (inside ms_coalesce) */
+  uint64_t n_pair_records;                                  /* overlap records of both mates summed over the fragments (k_pair roofline) */
+  uint64_t em_nnz;                                          /* non-zeros of the read-group x EC matrix */
+  int32_t em_updates;                                       /* EMupdate calls (3 per SQUAREM iteration) */
 } T1KGenotypeResult;
 
 int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t stride, uint32_t n_frag,

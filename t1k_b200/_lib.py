@@ -64,7 +64,9 @@ class GenotypeResult(C.Structure):
                 ("n_assignments", C.c_uint64), ("avg_alleles_per_read", C.c_double), ("ms_dedup", C.c_float),
                 ("ms_align", C.c_float), ("ms_pair", C.c_float), ("ms_coalesce", C.c_float), ("ms_em", C.c_float),
                 ("ms_align_kernel", C.c_float), ("ms_pair_kernel", C.c_float), ("ms_em_kernel", C.c_float),
-                ("n_postings", C.c_uint64), ("n_candidates", C.c_uint64), ("n_launches", C.c_uint64)]
+                ("n_postings", C.c_uint64), ("n_candidates", C.c_uint64), ("n_launches", C.c_uint64),
+                ("ms_prep_wait", C.c_float), ("ms_exchange", C.c_float), ("n_pair_records", C.c_uint64), ("em_nnz", C.c_uint64),
+                ("em_updates", C.c_int32)]
 
 
 class AssignStats(C.Structure):

@@ -697,6 +697,7 @@ struct PairHost {
   std::vector<u8> assigned;           // [nFrag] fragmentAssignment.size() > 0 (before the SetReadAssignments cuts)
   float msKernel = 0;
   u32 launches = 1;
+  uint64_t nPairRecords = 0;          // records of both mates' lists summed over the fragments (k_pair's algorithmic reads)
 };
 
 int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const uint32_t *end2, const uint8_t *hasN, uint32_t nFrag,
@@ -705,8 +706,17 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
   H.rowOff.assign(nFrag, 0); H.rowCnt.assign(nFrag, 0);
   H.rowHash.assign(wantHash ? 2 * (size_t)nFrag : 0, 0);
   H.assigned.assign(nFrag, 0);
-  H.nEntries = 0; H.ordKey.clear(); H.ordIdx.clear();
+  H.nEntries = 0; H.ordKey.clear(); H.ordIdx.clear(); H.nPairRecords = 0;
   if (nFrag == 0) return T1K_OK;
+  {
+    std::vector<u32> cnt(a->nReads);
+    if (a->nReads) CK(cudaMemcpyAsync(cnt.data(), a->readCnt.p, (size_t)a->nReads * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i < nFrag; ++i) {
+      if (end1[i] < a->nReads) H.nPairRecords += cnt[end1[i]];
+      if (end2 && end2[i] < a->nReads) H.nPairRecords += cnt[end2[i]];
+    }
+  }
   for (uint32_t i = 0; i < nFrag; ++i)
     if (end1[i] >= a->nReads || (end2 && end2[i] >= a->nReads)) return fail(T1K_ERR_ARG, "t1k_pair_batch: read-end index out of range");
   DevMem dE1, dE2, dN, dRowOff, dRowCnt, dOut, dKey, dIdx, dCtr, dOutCtr, dB0, dStage, dStageKey, dStageIdx, dHash;
@@ -1076,6 +1086,47 @@ int allgather_blobs(T1KRef *ref, T1KComm *comm, const uint8_t *mine, uint64_t my
   return T1K_OK;
 }
 
+// every rank contributes `n` words; all[r * n + i] = word i of rank r
+int allgather_u64(T1KRef *ref, T1KComm *comm, const uint64_t *mine, int n, std::vector<uint64_t> &all) {
+  cudaStream_t st = ref->stream;
+  const int W = comm->world;
+  DevMem d;
+  CK(d.alloc((size_t)W * n * 8));
+  CK(cudaMemcpyAsync(d.as<uint64_t>() + (size_t)comm->rank * n, mine, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  NK(nccl().AllGather(d.as<uint64_t>() + (size_t)comm->rank * n, d.p, (size_t)n, NCCL_UINT64, comm->comm, st));
+  all.assign((size_t)W * n, 0);
+  CK(cudaMemcpyAsync(all.data(), d.p, (size_t)W * n * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return T1K_OK;
+}
+
+// all-to-all of host blobs through device staging over NVLink (ncclSend / ncclRecv in one group): `send` holds this rank's
+// blobs for rank 0, 1, ... back to back (sendBytes[r] each, multiples of 16); bytesFrom[s] = what rank s sends to this
+// rank (from the size exchange); the incoming blobs land back to back in pinned memory `recv`.
+int alltoall_blobs(T1KRef *ref, T1KComm *comm, const uint8_t *send, const std::vector<size_t> &sendBytes, const std::vector<uint64_t> &bytesFrom,
+                   PinnedMem &recv, std::vector<size_t> &recvOff) {
+  cudaStream_t st = ref->stream;
+  const int W = comm->world;
+  size_t totSend = 0, totRecv = 0;
+  std::vector<size_t> sendOff((size_t)W + 1, 0);
+  recvOff.assign((size_t)W + 1, 0);
+  for (int r = 0; r < W; ++r) { sendOff[r + 1] = sendOff[r] + sendBytes[r]; recvOff[r + 1] = recvOff[r] + (size_t)bytesFrom[r]; }
+  totSend = sendOff[W]; totRecv = recvOff[W];
+  DevMem dSend, dRecv;
+  CK(dSend.alloc(std::max<size_t>(totSend, 16))); CK(dRecv.alloc(std::max<size_t>(totRecv, 16)));
+  if (totSend) CK(cudaMemcpyAsync(dSend.p, send, totSend, cudaMemcpyHostToDevice, st));
+  NK(nccl().GroupStart());
+  for (int r = 0; r < W; ++r) {
+    if (sendBytes[r]) NK(nccl().Send(dSend.as<uint8_t>() + sendOff[r], sendBytes[r], NCCL_UINT8, r, comm->comm, st));
+    if (bytesFrom[r]) NK(nccl().Recv(dRecv.as<uint8_t>() + recvOff[r], (size_t)bytesFrom[r], NCCL_UINT8, r, comm->comm, st));
+  }
+  NK(nccl().GroupEnd());
+  CK(recv.grow(std::max<size_t>(totRecv, 16), 0));
+  if (totRecv) CK(cudaMemcpyAsync(recv.p, dRecv.p, totRecv, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return T1K_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1113,6 +1164,7 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   res->ms_dedup = res->ms_align = res->ms_pair = res->ms_coalesce = res->ms_em = 0;
   res->ms_align_kernel = res->ms_pair_kernel = res->ms_em_kernel = 0;
   res->n_postings = res->n_candidates = 0; res->n_launches = 0;
+  res->ms_prep_wait = res->ms_exchange = 0; res->n_pair_records = 0; res->em_nnz = 0; res->em_updates = 0;
   PairHost pairOut[2];
   pairOut[0].pin = &ref->pinEntries[0]; pairOut[1].pin = &ref->pinEntries[1];
   double msCoalesce = 0;
@@ -1137,7 +1189,12 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     }
   }
   const u32 nChunks = (u32)chunks.size();
-  if (nChunks) do_prep(prep[0], chunks[0].first, chunks[0].second);
+  double msPrepWait = 0;
+  uint64_t nPairRecords = 0;
+  // the rank-local stage (no collective inside): returns this rank's status instead of leaving early, so that in a
+  // read-sharded run every rank reaches the status exchange below
+  auto local_stage = [&]() -> int {
+  { const double t = now_ms(); if (nChunks) do_prep(prep[0], chunks[0].first, chunks[0].second); msPrepWait += now_ms() - t; }
   for (u32 c = 0; c < nChunks; ++c) {
     Prep &C = prep[c & 1];
     res->ms_dedup += (float)C.ms;
@@ -1158,67 +1215,89 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     res->ms_pair += (float)(now_ms() - tp);
     res->ms_pair_kernel += H.msKernel; res->n_launches += H.launches;
     res->n_assignments += H.nEntries;
+    nPairRecords += H.nPairRecords;
     if (coalThread.joinable()) coalThread.join();
     coalThread = std::thread(do_coalesce, std::cref(H), C.f0, C.m);
-    if (prepThread.joinable()) prepThread.join();
+    { const double t = now_ms(); if (prepThread.joinable()) prepThread.join(); msPrepWait += now_ms() - t; }
   }
   if (coalThread.joinable()) coalThread.join();
-  {
+  return T1K_OK;
+  };
+  int localRc = local_stage();
+  std::string localErr = g_err;
+  if (prepThread.joinable()) prepThread.join();
+  if (coalThread.joinable()) coalThread.join();
+  T1KComm *comm = (prm->comm && prm->comm->world > 1) ? prm->comm : nullptr;
+  if (!comm && localRc) return localRc;
+  if (!localRc) {
     const double t = now_ms();
     shards.gather(groups);
     msCoalesce += now_ms() - t;
   }
   res->ms_coalesce = (float)msCoalesce;
-  // ---- read-sharded run: total coverage, every rank's read groups merged in rank order
-  T1KComm *comm = (prm->comm && prm->comm->world > 1) ? prm->comm : nullptr;
+  res->ms_prep_wait = (float)msPrepWait; res->n_pair_records = nPairRecords; res->ms_exchange = 0;
+  // ---- read-sharded run: total coverage; the read-group tables merged with the work divided over the
+  // ranks: the hash space of the allele sets is cut into world x T partitions, every rank sends each peer the groups of the
+  // partitions that peer owns (all-to-all over NVLink), merges its own partitions from all ranks in rank order (float32
+  // weights add as per-rank partial sums, as when the ranks' tables are merged one after the other), and the merged
+  // partitions are all-gathered and interleaved by the fragment that created each group = the single-process order.
   uint64_t nAssignAll = res->n_assignments;
   if (comm) {
     double tx = now_ms();
+    const int W = comm->world, T = shards.threads();
+    // status + sizes: {status, assignments, fragments, bytes for rank 0 .. W-1}
+    PartitionPlan plan;
+    if (!localRc) plan_partitions(groups, W, T, plan); else { plan.bytes.assign((size_t)W, 0); plan.groupsOf.assign((size_t)W, std::vector<int32_t>()); plan.total = 0; }
+    std::vector<uint64_t> mineW((size_t)W + 4, 0), allW;
+    mineW[0] = (uint64_t)localRc; mineW[1] = nAssignAll; mineW[2] = (uint64_t)n_frag; mineW[3] = (uint64_t)groups.assignedFragments;
+    for (int r = 0; r < W; ++r) mineW[4 + r] = (uint64_t)plan.bytes[r];
+    if (int rc = allgather_u64(ref, comm, mineW.data(), W + 4, allW)) return rc;
+    for (int r = 0; r < W; ++r)
+      if (allW[(size_t)r * (W + 4)] != 0) {
+        if (localRc) { g_err = localErr; return localRc; }
+        return fail(T1K_ERR_NCCL, "rank " + std::to_string(r) + " of the read-sharded run failed before the exchange");
+      }
     if (int rc = t1k_coverage_allreduce(ref, comm)) return rc;
-    // this rank's table + trailer {assignments, fragments} into pinned memory, all-gathered, merged on the host threads
-    const size_t tableBytes = serialized_group_bytes(groups);
-    CK(ref->pinSend.grow(tableBytes + 16, 0));
-    serialize_groups(groups, ref->pinSend.as<uint8_t>());
-    const uint64_t trailer[2] = {nAssignAll, (uint64_t)n_frag};
-    memcpy(ref->pinSend.as<uint8_t>() + tableBytes, trailer, 16);
-    uint64_t stride = 0;
-    std::vector<uint64_t> sizes;
-    if (int rc = allgather_blobs(ref, comm, ref->pinSend.as<uint8_t>(), tableBytes + 16, ref->pinRecv, stride, sizes)) return rc;
-    std::vector<GroupBlobView> tables((size_t)comm->world);
-    std::vector<int64_t> fragBase((size_t)comm->world, 0);
+    std::vector<int64_t> fragBase((size_t)W, 0);
+    std::vector<uint64_t> bytesFrom((size_t)W, 0);
     nAssignAll = 0;
-    int64_t fb = 0;
-    for (int r = 0; r < comm->world; ++r) {
-      const uint8_t *blob = ref->pinRecv.as<uint8_t>() + (size_t)r * stride;
-      if (sizes[r] < 16 || !tables[r].parse(blob, sizes[r] - 16)) return fail(T1K_ERR_NCCL, "malformed read-group table from a peer");
-      uint64_t tr[2]; memcpy(tr, blob + sizes[r] - 16, 16);
-      nAssignAll += tr[0];
-      fragBase[r] = fb; fb += (int64_t)tr[1];
+    int64_t fb = 0, assignedAll = 0;
+    for (int r = 0; r < W; ++r) {
+      const uint64_t *w = &allW[(size_t)r * (W + 4)];
+      nAssignAll += w[1]; fragBase[r] = fb; fb += (int64_t)w[2]; assignedAll += (int64_t)w[3];
+      bytesFrom[r] = w[4 + comm->rank];
     }
-    ReadGroups merged;
-    const char *partEnv = getenv("T1K_MERGE_PARTITIONED");
-    if (partEnv && atoi(partEnv) != 0) {
-      // opt-in: every rank merges 1/world of the allele sets, the merged partitions are exchanged and interleaved
-      ReadGroups mine;
-      if (!merge_tables_partition(tables, fragBase, comm->rank, comm->world, shards.threads(), mine)) return fail(T1K_ERR_NCCL, "malformed read-group table from a peer");
-      int64_t assignedAll = 0;
-      for (int r = 0; r < comm->world; ++r) assignedAll += (int64_t)tables[r].assigned;
-      const size_t partBytes = serialized_group_bytes(mine);
-      CK(ref->pinSend.grow(partBytes, 0));         // the first exchange's send buffer is no longer needed (tables live in pinRecv)
-      serialize_groups(mine, ref->pinSend.as<uint8_t>());
-      uint64_t stride2 = 0;
-      std::vector<uint64_t> sizes2;
-      if (int rc = allgather_blobs(ref, comm, ref->pinSend.as<uint8_t>(), partBytes, ref->pinRecv2, stride2, sizes2)) return rc;
-      std::vector<GroupBlobView> parts((size_t)comm->world);
-      for (int r = 0; r < comm->world; ++r)
-        if (!parts[r].parse(ref->pinRecv2.as<uint8_t>() + (size_t)r * stride2, sizes2[r])) return fail(T1K_ERR_NCCL, "malformed merged partition from a peer");
-      if (!assemble_partitions(parts, shards.threads(), merged)) return fail(T1K_ERR_NCCL, "malformed merged partition from a peer");
-      merged.assignedFragments = assignedAll;
-    } else if (!merge_tables_parallel(tables, fragBase, shards.threads(), merged)) return fail(T1K_ERR_NCCL, "malformed read-group table from a peer");
+    CK(ref->pinSend.grow(std::max<size_t>(plan.total, 16), 0));
+    serialize_partitions(groups, plan, ref->pinSend.as<uint8_t>(), T);
+    std::vector<size_t> recvOff;
+    if (int rc = alltoall_blobs(ref, comm, ref->pinSend.as<uint8_t>(), plan.bytes, bytesFrom, ref->pinRecv, recvOff)) return rc;
+    std::vector<GroupBlobView> tables((size_t)W);
+    int mergeRc = 0;
+    for (int r = 0; r < W && !mergeRc; ++r)
+      if (!tables[r].parse(ref->pinRecv.as<uint8_t>() + recvOff[r], bytesFrom[r])) mergeRc = 1;
+    ReadGroups mine, merged;
+    if (!mergeRc && !merge_tables_partition(tables, fragBase, comm->rank, W, T, mine)) mergeRc = 1;
+    // second exchange: status + the merged partitions
+    const size_t partBytes = mergeRc ? 0 : serialized_group_bytes(mine);
+    CK(ref->pinSend.grow(std::max<size_t>(partBytes, 16), 0));         // (the first exchange's send buffer is no longer needed)
+    if (!mergeRc) serialize_groups(mine, ref->pinSend.as<uint8_t>());
+    const uint64_t st2 = (uint64_t)mergeRc;
+    std::vector<uint64_t> allSt;
+    if (int rc = allgather_u64(ref, comm, &st2, 1, allSt)) return rc;
+    for (int r = 0; r < W; ++r) if (allSt[r]) return fail(T1K_ERR_NCCL, "malformed read-group table on rank " + std::to_string(r));
+    uint64_t stride2 = 0;
+    std::vector<uint64_t> sizes2;
+    if (int rc = allgather_blobs(ref, comm, ref->pinSend.as<uint8_t>(), partBytes, ref->pinRecv2, stride2, sizes2)) return rc;
+    std::vector<GroupBlobView> parts((size_t)W);
+    for (int r = 0; r < W; ++r)
+      if (!parts[r].parse(ref->pinRecv2.as<uint8_t>() + (size_t)r * stride2, sizes2[r])) return fail(T1K_ERR_NCCL, "malformed merged partition from a peer");
+    if (!assemble_partitions(parts, T, merged)) return fail(T1K_ERR_NCCL, "malformed merged partition from a peer");
+    merged.assignedFragments = assignedAll;
     groups.ptr.swap(merged.ptr); groups.ent.swap(merged.ent); groups.byHash.swap(merged.byHash);
     groups.first.swap(merged.first); groups.hashes.swap(merged.hashes);
     groups.assignedFragments = merged.assignedFragments;
-    res->ms_coalesce += (float)(now_ms() - tx);
+    res->ms_exchange = (float)(now_ms() - tx);
+    res->ms_coalesce += res->ms_exchange;
   }
   res->assigned_fragments = (int32_t)groups.assignedFragments;
   // Genotyper::GetAverageReadAssignmentCnt (Genotyper.hpp:941-955) averages over the coalesced read groups
@@ -1262,6 +1341,7 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     pt.lap("t1k_em_run");
     res->em_iterations = er.iterations;
     res->ms_em_kernel = er.ms_kernel; res->n_launches += er.n_launches;
+    res->em_nnz = (uint64_t)in.col.size(); res->em_updates = 3 * er.iterations;
     if (res->abundance && res->ec_abundance)
       set_allele_abundance(rc.data(), in.ecLen.data(), EC.ecPtr.data(), EC.ecAlleles.data(), EC.size(), nA, res->abundance, res->ec_abundance);
   }

@@ -27,6 +27,10 @@ struct NcclApi {
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
   std::string error;
 
@@ -46,6 +50,10 @@ struct NcclApi {
     T1K_SYM(AllReduce, "ncclAllReduce");
     T1K_SYM(AllGather, "ncclAllGather");
     T1K_SYM(Broadcast, "ncclBroadcast");
+    T1K_SYM(Send, "ncclSend");
+    T1K_SYM(Recv, "ncclRecv");
+    T1K_SYM(GroupStart, "ncclGroupStart");
+    T1K_SYM(GroupEnd, "ncclGroupEnd");
     T1K_SYM(GetErrorString, "ncclGetErrorString");
 #undef T1K_SYM
     return true;

@@ -25,6 +25,8 @@ template <class T> struct NoInitAlloc : std::allocator<T> {
   }
 };
 
+template <class F> inline void run_threads(int n, F fn);
+
 struct HostEntry {   // == PairEntry / T1KReadAssignment
   int32_t alleleIdx, start, end;
   float weight, qual, adjustWeight;
@@ -196,6 +198,62 @@ inline void serialize_groups(const ReadGroups &G, uint8_t *p) {
 inline void serialize_groups(const ReadGroups &G, std::vector<uint8_t> &blob) {
   blob.resize(serialized_group_bytes(G));
   serialize_groups(G, blob.data());
+}
+
+// The table split by the rank that merges each group: the hash space is cut into world x T partitions, rank r owns the
+// partitions r*T .. r*T + T - 1 (thread t of rank r merges partition r*T + t, see merge_tables_partition).  One blob per owner,
+// same format as serialize_groups (assigned = 0), written back to back into `out`; bytes[r] = size of the blob for rank r.
+struct PartitionPlan {
+  std::vector<std::vector<int32_t> > groupsOf;      // [world] group ids, ascending
+  std::vector<size_t> bytes;                        // [world]
+  size_t total = 0;
+};
+inline void plan_partitions(const ReadGroups &G, int world, int T, PartitionPlan &pl) {
+  const uint64_t P = (uint64_t)world * (uint64_t)(T < 1 ? 1 : T);
+  pl.groupsOf.assign((size_t)world, std::vector<int32_t>());
+  std::vector<size_t> nE((size_t)world, 0);
+  for (int32_t g = 0; g < G.size(); ++g) {
+    const int owner = (int)(((G.hashes[g] >> 17) % P) / (uint64_t)(T < 1 ? 1 : T));
+    pl.groupsOf[owner].push_back(g);
+    nE[owner] += (size_t)(G.ptr[g + 1] - G.ptr[g]);
+  }
+  pl.bytes.assign((size_t)world, 0);
+  pl.total = 0;
+  for (int r = 0; r < world; ++r) {
+    const size_t nG = pl.groupsOf[r].size();
+    pl.bytes[r] = (4 * 8 + (nG + 1) * 8 + nG * 16 + nE[r] * sizeof(HostEntry) + 15) & ~(size_t)15;
+    pl.total += pl.bytes[r];
+  }
+}
+inline void serialize_partitions(const ReadGroups &G, const PartitionPlan &pl, uint8_t *out, int threads) {
+  const int world = (int)pl.groupsOf.size();
+  std::vector<size_t> at((size_t)world + 1, 0);
+  for (int r = 0; r < world; ++r) at[r + 1] = at[r] + pl.bytes[r];
+  run_threads(std::max(1, std::min(threads, world)), [&](int t) {
+    const int nT = std::max(1, std::min(threads, world));
+    for (int r = t; r < world; r += nT) {
+      const std::vector<int32_t> &ids = pl.groupsOf[r];
+      const size_t nG = ids.size();
+      uint8_t *p = out + at[r];
+      size_t nE = 0;
+      for (size_t k = 0; k < nG; ++k) nE += (size_t)(G.ptr[ids[k] + 1] - G.ptr[ids[k]]);
+      const uint64_t hdr[4] = {(uint64_t)nG, (uint64_t)nE, 0, 0};
+      memcpy(p, hdr, sizeof(hdr)); p += sizeof(hdr);
+      int64_t *ptr = (int64_t *)p; p += (nG + 1) * 8;
+      uint64_t *hs = (uint64_t *)p; p += nG * 8;
+      int64_t *fi = (int64_t *)p; p += nG * 8;
+      HostEntry *en = (HostEntry *)p;
+      int64_t run = 0;
+      for (size_t k = 0; k < nG; ++k) {
+        const int32_t g = ids[k];
+        const int64_t n = G.ptr[g + 1] - G.ptr[g];
+        ptr[k] = run; hs[k] = G.hashes[g]; fi[k] = G.first[g];
+        if (n) memcpy(en + run, G.ent.data() + G.ptr[g], (size_t)n * sizeof(HostEntry));
+        run += n;
+      }
+      ptr[nG] = run;
+    }
+  });
 }
 
 // Merge of another rank's table (read-sharded path): its groups are added in their own order, so merging the ranks'

@@ -129,12 +129,14 @@ def revcomp(a: np.ndarray) -> np.ndarray:
 
 
 def simulate_pairs(records, n_pairs, read_len=150, insert=(300, 450), err=0.002, n_rate=0.0,
-                   alleles_per_gene=2, seed=1, gene_of=None, single_end=False, indel_rate=0.0, src_seed=None):
+                   alleles_per_gene=2, seed=1, gene_of=None, single_end=False, indel_rate=0.0, src_seed=None,
+                   start_frac=(0.0, 1.0)):
     """Draw n_pairs FR fragments uniformly from `alleles_per_gene` alleles of every gene.
     Returns (reads1, reads2) as uint8 arrays [n, read_len] (reads2 None if single_end),
     plus the list of source allele indices.  Substitution errors at rate `err`, 'N' at
     `n_rate`, single-base indels (read-level) at `indel_rate` per read.  `src_seed` draws the source alleles from
-    their own stream, so that shards of one sample (different `seed`) come from the same alleles."""
+    their own stream, so that shards of one sample (different `seed`) come from the same alleles.  `start_frac` restricts
+    the fragment starts to that fraction of every source allele (a small sample with the duplicate rate of a deep one)."""
     rng = np.random.default_rng(seed)
     src_rng = rng if src_seed is None else np.random.default_rng(src_seed)
     if gene_of is None:
@@ -151,7 +153,7 @@ def simulate_pairs(records, n_pairs, read_len=150, insert=(300, 450), err=0.002,
     which = rng.integers(0, len(src), size=n_pairs)
     ins = rng.integers(insert[0], insert[1] + 1, size=n_pairs)
     flip = rng.integers(0, 2, size=n_pairs).astype(bool)
-    u = rng.random(n_pairs)
+    u = start_frac[0] + rng.random(n_pairs) * (start_frac[1] - start_frac[0])
     r1 = np.empty((n_pairs, read_len), dtype=np.uint8)
     r2 = None if single_end else np.empty((n_pairs, read_len), dtype=np.uint8)
     ar = np.arange(read_len)

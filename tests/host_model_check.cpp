@@ -201,6 +201,33 @@ extern "C" int host_model_check(int seed, int nFrag, int nAlleles, int nSets) {
         if (!assemble_partitions(pv, T, asm_)) return 16;
         asm_.assignedFragments = full.assignedFragments;
         if (!same_groups(asm_, full)) return 17;
+        // the product's exchange: every rank splits its table by owner (plan_partitions / serialize_partitions), rank r gets
+        // only the blobs addressed to it (the all-to-all), merges them, and the merged partitions assemble to the same table
+        std::vector<PartitionPlan> plans(W);
+        std::vector<std::vector<uint8_t> > sendBuf(W);
+        for (int s = 0; s < W; ++s) {
+          plan_partitions(shard[s], W, T, plans[s]);
+          sendBuf[s].assign(plans[s].total + 16, 0);
+          serialize_partitions(shard[s], plans[s], sendBuf[s].data(), T);
+        }
+        std::vector<std::vector<uint8_t> > pb2(W);
+        std::vector<GroupBlobView> pv2(W);
+        for (int r = 0; r < W; ++r) {
+          std::vector<GroupBlobView> in(W);
+          for (int s = 0; s < W; ++s) {
+            size_t at = 0;
+            for (int q = 0; q < r; ++q) at += plans[s].bytes[q];
+            if (!in[s].parse(sendBuf[s].data() + at, plans[s].bytes[r])) return 18;
+          }
+          ReadGroups mine;
+          if (!merge_tables_partition(in, fb3, r, W, T, mine)) return 19;
+          serialize_groups(mine, pb2[r]);
+          if (!pv2[r].parse(pb2[r].data(), pb2[r].size())) return 20;
+        }
+        ReadGroups asm2;
+        if (!assemble_partitions(pv2, T, asm2)) return 21;
+        asm2.assignedFragments = full.assignedFragments;
+        if (!same_groups(asm2, full)) return 22;
       }
     }
     // the merged table has the single-process groups in the single-process order (float32 sums may differ in the last
