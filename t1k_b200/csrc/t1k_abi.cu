@@ -706,7 +706,7 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
   H.rowOff.assign(nFrag, 0); H.rowCnt.assign(nFrag, 0);
   H.rowHash.assign(wantHash ? 2 * (size_t)nFrag : 0, 0);
   H.assigned.assign(nFrag, 0);
-  H.nEntries = 0; H.ordKey.clear(); H.ordIdx.clear(); H.nPairRecords = 0;
+  H.nEntries = 0; H.ordKey.clear(); H.ordIdx.clear(); H.nPairRecords = 0; H.msKernel = 0; H.launches = 0;
   if (nFrag == 0) return T1K_OK;
   {
     std::vector<u32> cnt(a->nReads);
@@ -874,7 +874,9 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   struct StGuard { cudaStream_t s; ~StGuard() { cudaStreamDestroy(s); } } sg{st};
   DevMem dRowPtr, dCol, dColPtr, dRowIdx, dCount, dLen, dPsum, dRc, dX0, dX1, dX2, dX3, dDiff, dTmpA, dTmpB;
-  const bool fast = p->fast_sums != 0;
+  // reference-order sums only where they can give the reference's bits: one GPU; a row-sharded run adds the per-rank sums in
+  // another order anyway (documented tolerance 1e-5), so it takes the tree reductions
+  const bool fast = p->fast_sums != 0 || comm != nullptr;
   CK(dTmpA.alloc((size_t)E * 8)); CK(dTmpB.alloc((size_t)E * 8));
   CK(dRowPtr.alloc(((size_t)Gl + 1) * 8)); CK(dCol.alloc((size_t)nnzL * 4)); CK(dColPtr.alloc(((size_t)E + 1) * 8)); CK(dRowIdx.alloc((size_t)nnzL * 4));
   CK(dCount.alloc((size_t)G * 8)); CK(dLen.alloc((size_t)E * 4)); CK(dPsum.alloc((size_t)G * 8)); CK(dRc.alloc((size_t)E * 8));
@@ -916,8 +918,10 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   int ret = 0;
   std::vector<double> hRc(E), hX(E);
   const bool mask = p->n_alleles > 0 && p->ec_allele_ptr && p->ec_alleles && p->allele_major && p->allele_gene;
-  for (int t = 0; t < maxIter; ++t) {     // Genotyper.hpp:1234-1314
-    ++ret;
+  // One SQUAREM iteration (Genotyper.hpp:1236-1287: EMupdate x0->x1, x1->x2, extrapolation -> x3, EMupdate x3->x1, advance) is the
+  // same eleven kernels (+ three all-reduces) on the same buffers every time: captured once into a CUDA graph and replayed.
+  // The host only reads diffSum (8 bytes) after each replay — the reference's stop test decides iteration by iteration.
+  auto iteration = [&]() -> int {
     if (int rc = em_update(dX0.as<double>(), dX1.as<double>())) return rc;
     if (int rc = em_update(dX1.as<double>(), dX2.as<double>())) return rc;
     if (fast) k_em_squarem<<<1, 1024, 0, st>>>(E, dX0.as<double>(), dX1.as<double>(), dX2.as<double>(), p->min_squarem_alpha, dX3.as<double>());
@@ -927,11 +931,39 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
     else k_em_advance_seq<<<1, 1024, 0, st>>>(E, dX0.as<double>(), dX1.as<double>(), dTmpA.as<double>(), dDiff.as<double>());
     CK(cudaGetLastError());
     launches += 2;
+    return T1K_OK;
+  };
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graphExec = nullptr;
+  struct GraphGuard { cudaGraph_t &g; cudaGraphExec_t &e; ~GraphGuard() { if (e) cudaGraphExecDestroy(e); if (g) cudaGraphDestroy(g); } } gg{graph, graphExec};
+  bool useGraph = getenv("T1K_EM_NO_GRAPH") == nullptr;
+  uint64_t launchesPerIter = 0;
+  if (useGraph) {
+    const uint64_t before = launches;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); useGraph = false; }
+    else {
+      const int rcCap = iteration();
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rcCap != T1K_OK || ce != cudaSuccess || cudaGraphInstantiate(&graphExec, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        useGraph = false;
+        if (rcCap != T1K_OK && comm) return rcCap;       // (a failed collective inside the capture is not recoverable)
+      }
+    }
+    launchesPerIter = launches - before;
+    launches = before;
+  }
+  for (int t = 0; t < maxIter; ++t) {     // Genotyper.hpp:1234-1314
+    ++ret;
+    if (useGraph) { CK(cudaGraphLaunch(graphExec, st)); launches += launchesPerIter; }
+    else if (int rc = iteration()) return rc;
     double diff = 0;
     CK(cudaMemcpyAsync(&diff, dDiff.p, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (diff < 1e-5 && t < maxIter - 2) t = maxIter - 2;
     if (t > 0 && t % 10 == 0 && mask) {
+      // the every-10 low-abundance mask (Genotyper.hpp:1292-1313) runs once or twice per sample, on the host in the reference's
+      // own summation order, on a 8 E-byte copy of ecReadCount
       CK(cudaMemcpyAsync(hRc.data(), dRc.p, (size_t)E * 8, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       em_mask(hRc.data(), p->ec_len, p->ec_allele_ptr, p->ec_alleles, E, p->n_alleles, p->allele_major, p->allele_gene, p->n_major,
