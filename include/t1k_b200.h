@@ -23,7 +23,7 @@ enum {
   T1K_ERR_NCCL = 5
 };
 
-#define T1K_MAX_READ_LEN 255
+#define T1K_MAX_READ_LEN 1000
 #define T1K_KMER 11
 
 typedef struct T1KRef T1KRef;               /* allele reference + k-mer index + coverage, resident in HBM */

@@ -205,7 +205,7 @@ struct T1KRef {
   DevMem candPool, laneScratch, hitBuf, workCtr, errFlag, stats, dq, aq, qCtr;
   u32 candCap = 0, dqCap = 0, aqCap = 0;
   u64 arenaCands = 0;
-  int gridBlocks = 0, hitCap = 0, seedCap = 0;
+  int gridBlocks = 0, hitCap = 0, seedCap = 0, scrLen = 0;
   int occ = 6;
   size_t scratchWarps = 0;
   u64 nPostings = 0, nEntries = 0;
@@ -251,7 +251,7 @@ int t1k_ref_create(const T1KRefDesc *d, T1KRef **out) {
   if (!pack_reference(d->n_alleles, d->bases, d->offset, d->exon_ptr, d->exon_se, P))
     return fail(T1K_ERR_ARG, "reference contains a character outside ACGTN");
   for (int i = 0; i < d->n_alleles; ++i)
-    if (P.len[i] >= (1 << 24)) return fail(T1K_ERR_UNSUPPORTED, "allele longer than 2^24 bases");
+    if (P.len[i] >= (1 << 22)) return fail(T1K_ERR_UNSUPPORTED, "allele longer than 2^22 bases");
   T1KRef *r = new T1KRef;
   r->device = dev;
   r->nAlleles = d->n_alleles;
@@ -326,17 +326,19 @@ int setup_assign_launch(T1KRef *r, int maxLen) {
   int occ = 6;      // measured: 6 blocks/SM (80 registers) beats 4, 5 and 8
   if (const char *env = getenv("T1K_ASSIGN_OCC")) occ = atoi(env);
   if (occ < 2 || occ > 8) occ = 6;
-  int hitCap = 1024;     // hits of one allele the hit-list path holds (HBM scratch; a 255-base read has <= 245 seeds)
+  int hitCap = std::max(1024, 2 * maxLen);     // hits of one allele the hit-list path holds (HBM scratch; a read has <= len - 10 seeds)
   if (const char *env = getenv("T1K_HIT_CAP")) hitCap = std::max(64, atoi(env));
-  if (r->gridBlocks && seedCap <= r->seedCap && occ == r->occ && hitCap == r->hitCap) return T1K_OK;
+  const int scrLen = maxLen <= 255 ? 255 : MAX_READ_LEN;       // per-lane scratch: two sizes
+  if (r->gridBlocks && seedCap <= r->seedCap && occ == r->occ && hitCap <= r->hitCap && scrLen <= r->scrLen) return T1K_OK;
   r->occ = occ;
   const void *kfn = seed_kernel(occ);
-  const size_t smem = warp_smem_bytes(seedCap) * WARPS_PER_BLOCK;
+  const int rwords = read_words(scrLen);
+  const size_t smem = warp_smem_bytes(seedCap, rwords) * WARPS_PER_BLOCK;
   CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int perSM = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kfn, WARPS_PER_BLOCK * 32, smem));
   if (perSM < 1) return fail(T1K_ERR_UNSUPPORTED, "k_seed does not fit on an SM");
-  r->seedCap = seedCap; r->hitCap = hitCap;
+  r->seedCap = seedCap; r->hitCap = hitCap; r->scrLen = scrLen;
   r->gridBlocks = std::min(perSM, occ) * r->nSM;
   const size_t warps = (size_t)r->gridBlocks * WARPS_PER_BLOCK;
   u64 cap = 2ull * (u64)r->nAlleles + 2048;
@@ -352,7 +354,7 @@ int setup_assign_launch(T1KRef *r, int maxLen) {
   r->dqCap = 16u << 20; r->aqCap = 32u << 20;      // 512 MB each; a full queue is not an error (the work is done in place)
   if (const char *env = getenv("T1K_QUEUE_ITEMS")) r->dqCap = r->aqCap = (u32)std::max(0l, atol(env));
   CK(r->candPool.alloc(warps * arena * sizeof(Cand)));
-  CK(r->laneScratch.alloc(warps * 32 * (size_t)SCR_BYTES));
+  CK(r->laneScratch.alloc(warps * 32 * scr_bytes(scrLen)));
   CK(r->hitBuf.alloc(warps * (size_t)hitCap * 32 * sizeof(u32)));
   CK(r->dq.alloc(std::max<size_t>(1, r->dqCap) * sizeof(DeferItem)));
   CK(r->aq.alloc(std::max<size_t>(1, r->aqCap) * sizeof(AlignItem)));
@@ -398,7 +400,8 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   a->ref = ref; a->device = ref->device; a->nReads = n;
   DevMem dBases, dOff, dLen, dW, planes, len16;
   CK(dBases.alloc(total)); CK(dOff.alloc((size_t)n * 8)); CK(dLen.alloc((size_t)n * 4)); CK(dW.alloc((size_t)n * 4));
-  CK(planes.alloc((size_t)n * 4 * RWORDS * 8)); CK(len16.alloc((size_t)n * 2));
+  const int rwords = read_words(ref->scrLen);
+  CK(planes.alloc((size_t)n * 4 * rwords * 8)); CK(len16.alloc((size_t)n * 2));
   CK(a->readOff.alloc((size_t)n * 8)); CK(a->readCnt.alloc((size_t)n * 4)); CK(a->readRet.alloc((size_t)n * 4)); CK(a->readTop.alloc((size_t)n * 4));
   CK(a->storeCtr.alloc(8)); CK(a->dMaxCnt.alloc(4));
   CK(cudaMemsetAsync(a->dMaxCnt.p, 0, 4, st));
@@ -410,7 +413,7 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   CK(cudaMemsetAsync(ref->errFlag.p, 0, sizeof(int), st));
   CK(cudaMemsetAsync(ref->stats.p, 0, 4 * sizeof(unsigned long long), st));
   CK(cudaMemsetAsync(a->storeCtr.p, 0, 8, st));
-  k_pack_reads<<<(n + 127) / 128, 128, 0, st>>>(dBases.as<char>(), dOff.as<u64>(), dLen.as<u32>(), n, planes.as<u64>(), len16.as<u16>(),
+  k_pack_reads<<<(n + 127) / 128, 128, 0, st>>>(dBases.as<char>(), dOff.as<u64>(), dLen.as<u32>(), n, rwords, planes.as<u64>(), len16.as<u16>(),
                                                   ref->errFlag.as<int>());
   CK(cudaGetLastError());
   // record store: sized from free memory, grown (and only the deferred read-ends re-run) if it fills up
@@ -425,7 +428,7 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   pt.lap("  assign: store alloc");
   AssignParams P;
   P.R = ref->R;
-  P.Q.planes = planes.as<u64>(); P.Q.len = len16.as<u16>(); P.Q.weight = dW.as<int32_t>(); P.Q.workList = nullptr; P.Q.nWork = n;
+  P.Q.planes = planes.as<u64>(); P.Q.rwords = rwords; P.Q.maxLen = ref->scrLen; P.Q.len = len16.as<u16>(); P.Q.weight = dW.as<int32_t>(); P.Q.workList = nullptr; P.Q.nWork = n;
   P.O.store = a->store.as<Rec>(); P.O.storeCtr = a->storeCtr.as<unsigned long long>(); P.O.storeCap = cap;
   P.O.readOff = a->readOff.as<u64>(); P.O.readCnt = a->readCnt.as<u32>(); P.O.readRet = a->readRet.as<int32_t>(); P.O.readTop = a->readTop.as<u32>();
   P.O.maxCnt = a->dMaxCnt.as<u32>();
@@ -447,7 +450,7 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   cudaEvent_t ev0, ev1;
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
   struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
-  const size_t smem = warp_smem_bytes(ref->seedCap) * WARPS_PER_BLOCK;
+  const size_t smem = warp_smem_bytes(ref->seedCap, rwords) * WARPS_PER_BLOCK;
   for (int round = 0;; ++round) {
     if (round > 0) CK(cudaMemsetAsync(ref->errFlag.p, 0, sizeof(int), st));   // round 0 keeps k_pack_reads' flags
     if (first) { P.Q.workList = nullptr; P.Q.nWork = n; }

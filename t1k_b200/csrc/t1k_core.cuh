@@ -43,7 +43,10 @@ constexpr int KMER = 11;
 constexpr int RADIUS = 10;          // SeqSet.hpp:763
 constexpr int HIT_LEN_REQ = 31;     // SeqSet.hpp:764
 constexpr int BAND = 5;             // AlignAlgo.hpp:215
-constexpr int RWORDS = 9;           // packed words per read strand plane (255 bases + fetch slack)
+constexpr int MAX_READ_LEN = 1000;  // == T1K_MAX_READ_LEN (positions are 10 bits in the hit encoding)
+constexpr int RWORDS = 9;           // packed words per read strand plane of a batch of reads up to 255 bases (+ fetch slack)
+constexpr int MAX_RWORDS = 33;      // ... up to MAX_READ_LEN bases
+T1K_HD int read_words(int maxLen) { return maxLen <= 255 ? RWORDS : MAX_RWORDS; }
 constexpr int MAX_BAND_W = 64;      // widest DP band kept (band = 11 + |lent-lenp| + 2 sentinels)
 constexpr int MAX_EMIT = 48;        // seed overlaps one (strand, allele) group may emit
 constexpr u64 M55 = 0x5555555555555555ull;
@@ -104,7 +107,7 @@ T1K_HD bool sim_below(const RefView &R, int mc, int den, int w) {
 }
 
 struct ReadView {        // one strand of one read-end
-  const u64 *seq2, *n2;  // RWORDS words each
+  const u64 *seq2, *n2;  // read_words(longest read of the batch) words each
   int len;
   bool anyN;             // the read holds at least one N
 };
@@ -119,13 +122,14 @@ struct AlleleView {
 };
 
 // candidate = seed overlap that passed the similarity filter of GetOverlapsFromRead (SeqSet.hpp:1893-1908)
-struct Cand {
+struct alignas(16) Cand {                  // 48 bytes: three 16-byte loads
   int32_t seqIdx, seqStart, seqEnd;
-  u8 readStart, readEnd, strand01, flags;   // strand01: 1 = same strand (+1), 0 = reverse (-1)
-  u16 matchCnt, pad;
+  u16 readStart, readEnd;
+  u8 strand01, flags;                      // strand01: 1 = same strand (+1), 0 = reverse (-1)
+  u16 matchCnt;
   // filled by the extension stage (SeqSet::ExtendOverlap, SeqSet.hpp:1994-2100)
   int32_t eSeqStart, eSeqEnd;
-  u8 eReadStart, eReadEnd, leftClip, rightClip;
+  u16 eReadStart, eReadEnd, leftClip, rightClip;
   int32_t eMatchCnt, relaxed;
   // CF_FA: the full-read alignment is the pure diagonal with <= 3 mismatches, known already from the seeding stage:
   // read positions of the mismatches (bytes 0-2), their number (bits 24-25) and the exonic ones among them (bits 26-27)
@@ -161,22 +165,32 @@ T1K_HD bool rec_before(const Rec &a, long long ia, const Rec &b, long long ib) {
   return ia < ib;
 }
 
-// per-lane scratch in global memory
-constexpr int SCR_OPS = 1024;
+// per-lane scratch in global memory, sized for the longest read of the batch:
+//   ops    edit string of one alignment (<= lent + lenp + 8 entries)
+//   rows   rolling DP rows of dp_align
+//   dir    direction nibbles of the band ((lenp + 1) x band width), also the chaining scratch of chain_cluster_general
+//   emit   seed overlaps one (strand, allele) group emitted
+//   chain  a LIS chain (strictly increasing read offsets)
 constexpr int SCR_ROWS = 4 * (MAX_BAND_W + 2) * 4;
-constexpr int SCR_DIR = 258 * MAX_BAND_W;
 constexpr int SCR_EMIT = MAX_EMIT * (int)sizeof(Cand);
-constexpr int SCR_CHAIN = 256 * 4;   // a LIS chain has strictly increasing read offsets: <= 245 entries
-constexpr int SCR_BYTES = ((SCR_OPS + SCR_ROWS + SCR_DIR + SCR_EMIT + SCR_CHAIN + 255) / 256) * 256;
+T1K_HD int scr_ops(int maxLen) { return (2 * maxLen + 128 + 15) & ~15; }
+T1K_HD int scr_dir(int maxLen) { return ((maxLen + 3) * MAX_BAND_W + 15) & ~15; }
+T1K_HD int scr_chain(int maxLen) { return (maxLen + 8 + 3) & ~3; }              // entries
+T1K_HD size_t scr_bytes(int maxLen) { return (((size_t)scr_ops(maxLen) + SCR_ROWS + scr_dir(maxLen) + SCR_EMIT + 4 * (size_t)scr_chain(maxLen)) + 255) & ~(size_t)255; }
 
 struct LaneScratch {
   u8 *base;
+  int opsCap, dirBytes, chainCap;
   T1K_HD u8 *ops() const { return base; }
-  T1K_HD int *rows() const { return (int *)(base + SCR_OPS); }
-  T1K_HD u8 *dir() const { return base + SCR_OPS + SCR_ROWS; }
-  T1K_HD Cand *emit() const { return (Cand *)(base + SCR_OPS + SCR_ROWS + SCR_DIR); }
-  T1K_HD u32 *chain() const { return (u32 *)(base + SCR_OPS + SCR_ROWS + SCR_DIR + SCR_EMIT); }
+  T1K_HD int *rows() const { return (int *)(base + opsCap); }
+  T1K_HD u8 *dir() const { return base + opsCap + SCR_ROWS; }
+  T1K_HD Cand *emit() const { return (Cand *)(base + opsCap + SCR_ROWS + dirBytes); }
+  T1K_HD u32 *chain() const { return (u32 *)(base + opsCap + SCR_ROWS + dirBytes + SCR_EMIT); }
 };
+T1K_HD LaneScratch lane_scratch(u8 *base, int maxLen) {
+  LaneScratch S; S.base = base; S.opsCap = scr_ops(maxLen); S.dirBytes = scr_dir(maxLen); S.chainCap = scr_chain(maxLen);
+  return S;
+}
 
 enum { ERR_BAND = 1, ERR_SCRATCH = 2, ERR_EMIT = 4, ERR_CAND = 8, ERR_STORE = 16, ERR_HITS = 32, ERR_READ_LEN = 64, ERR_READ_CHAR = 128 };
 
@@ -446,7 +460,7 @@ T1K_HD bool diag_certified(const AlleleView &T, int tpos, const ReadView &Q, int
 T1K_HDN T1K_NOINLINE inline int dp_align_eq(const AlleleView &T, int tpos, const ReadView &Q, int ppos, int n, const LaneScratch &S, int &err) {
   u8 *ops = S.ops();
   constexpr int LB = BAND, WW = 2 * BAND + 3;       // columns i-LB-1 .. i+LB+1
-  if (n > 256 || 2 * n + 8 > SCR_OPS) { err |= ERR_BAND; return -1; }
+  if (2 * n + 8 > S.opsCap || (n + 1) * 8 > S.dirBytes) { err |= ERR_BAND; return -1; }
   const int negInf = (n + 1) * (n + 1) * -4;
   const int stale = -4 + (n + 1) * -4;              // e[0][j], AlignAlgo.hpp:268 (Q5)
   u64 *dirRow = (u64 *)S.dir();                     // [n + 1] direction nibbles of row i, column window index jj at bits 4*jj
@@ -510,7 +524,7 @@ T1K_HDN T1K_NOINLINE inline int dp_align_eq(const AlleleView &T, int tpos, const
   int ti = n, tj = n, mat = 0, k = 0;
   T1K_NOUNROLL
   while (ti > 0 || tj > 0) {
-    if (k >= SCR_OPS - 2) { err |= ERR_BAND; return -1; }
+    if (k >= S.opsCap - 2) { err |= ERR_BAND; return -1; }
     const int b = (ti > 0 && tj > 0) ? (int)((dirRow[ti] >> (4 * (tj - ti + LB + 1))) & 15) : 0;
     if (mat == 0) {
       int a;
@@ -556,7 +570,7 @@ T1K_HDN T1K_NOINLINE inline int dp_align(const AlleleView &T, int tpos, int lent
   if (lent > lenp) rb += lent - lenp; else if (lent < lenp) lb += lenp - lent;
   const int W = lb + rb + 3;          // columns i-lb-1 .. i+rb+1
   T1K_COUNT(0, 1); T1K_COUNT(1, (long long)lenp * W); T1K_COUNT(lent == lenp ? 2 : 3, 1);
-  if (W > MAX_BAND_W || lenp > 256 || lent + lenp + 8 > SCR_OPS) { err |= ERR_BAND; return -1; }
+  if (W > MAX_BAND_W || (lenp + 1) * W > S.dirBytes || lent + lenp + 8 > S.opsCap) { err |= ERR_BAND; return -1; }
   const int negInf = (lent + 1) * (lenp + 1) * -4;
   const int stale = -4 + (lenp + 1) * -4;   // e[0][j], AlignAlgo.hpp:268 (Q5)
   int *mP = S.rows(), *eP = mP + (MAX_BAND_W + 2), *mC = eP + (MAX_BAND_W + 2), *eC = mC + (MAX_BAND_W + 2);
@@ -618,7 +632,7 @@ T1K_HDN T1K_NOINLINE inline int dp_align(const AlleleView &T, int tpos, int lent
   int ti = lenp, tj = lent, mat = 0, n = 0;
   T1K_NOUNROLL
   while (ti > 0 || tj > 0) {
-    if (n >= SCR_OPS - 2) { err |= ERR_BAND; return -1; }
+    if (n >= S.opsCap - 2) { err |= ERR_BAND; return -1; }
     if (mat == 0) {
       int a;
       if (ti > 0 && tj > 0) {
@@ -724,9 +738,11 @@ T1K_HDN T1K_NOINLINE inline bool low_complex(const ReadView &Q, int s, int e) {
   return low >= 2;
 }
 
-// hit encoding: readOffset | seqOffset << 8
-T1K_HD int hit_a(u32 h) { return (int)(h & 255); }
-T1K_HD int hit_b(u32 h) { return (int)(h >> 8); }
+// hit encoding: readOffset (10 bits) | seqOffset << 10 (alleles up to 4 Mbases)
+constexpr int HIT_SHIFT = 10;
+T1K_HD u32 hit_make(int a, u32 b) { return (u32)a | (b << HIT_SHIFT); }
+T1K_HD int hit_a(u32 h) { return (int)(h & ((1u << HIT_SHIFT) - 1)); }
+T1K_HD int hit_b(u32 h) { return (int)(h >> HIT_SHIFT); }
 T1K_HD bool hit_diag_less(u32 x, u32 y) {   // CompSortHitCoordDiff (SeqSet.hpp:266-274): (a-b, b, a)
   int cx = hit_a(x) - hit_b(x), cy = hit_a(y) - hit_b(y);
   if (cx != cy) return cx < cy;
@@ -825,8 +841,8 @@ T1K_HDN T1K_NOINLINE inline void consume_chain(const RefView &R, const ReadView 
   if (nEmit >= MAX_EMIT) { err |= ERR_EMIT; return; }
   Cand &c = S.emit()[nEmit++];
   c.seqIdx = seqIdx; c.seqStart = ss; c.seqEnd = se;
-  c.readStart = (u8)rs; c.readEnd = (u8)re; c.strand01 = (u8)strand01; c.flags = 0;
-  c.matchCnt = (u16)mc; c.pad = 0; c.mmPos = 0;
+  c.readStart = (u16)rs; c.readEnd = (u16)re; c.strand01 = (u8)strand01; c.flags = 0;
+  c.matchCnt = (u16)mc; c.mmPos = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -835,7 +851,7 @@ T1K_HDN T1K_NOINLINE inline void consume_chain(const RefView &R, const ReadView 
 //   bits 16-23 first seed >= a (255: none)     bits 24-31 last seed <= a (255: none)
 // "Seed" = a k-mer position GetHitsFromRead actually looks up with a non-empty posting list (SeqSet.hpp:1093-1153 after
 // the skip rule).  Built once per strand (one lane); diag_fast below answers its range questions from it.
-T1K_HDN inline void seed_table_build(const u8 *seedA, int nS, int len, u32 *stab) {
+T1K_HDN inline void seed_table_build(const u16 *seedA, int nS, int len, u32 *stab) {
   int k = 0, cnt = 0, big = 0, last = 255;
   T1K_NOUNROLL
   for (int a = 0; a < len; ++a) {
@@ -1014,8 +1030,8 @@ T1K_HDN T1K_NOINLINE inline int diag_fast(const RefView &R, const ReadView &Q, i
   if (hot && !hotExt) return DF_DEFER;
   Cand &c = out;
   c.seqIdx = seqIdx; c.seqStart = rs + d; c.seqEnd = re + d;
-  c.readStart = (u8)rs; c.readEnd = (u8)re; c.strand01 = (u8)strand01; c.flags = 0;
-  c.matchCnt = (u16)mc; c.pad = 0; c.mmPos = 0;
+  c.readStart = (u16)rs; c.readEnd = (u16)re; c.strand01 = (u8)strand01; c.flags = 0;
+  c.matchCnt = (u16)mc; c.mmPos = 0;
   emitted = true;
   if (hotExt) {
     const int mcE = mc + 2 * (lo - mmLeft + ro - mmRight);
@@ -1023,9 +1039,9 @@ T1K_HDN T1K_NOINLINE inline int diag_fast(const RefView &R, const ReadView &Q, i
     u8 flags = CF_PRE;
     if (d < 0 || d + len > clen) flags |= CF_NEEDCLIP;
     if (!sim_below(R, mcE, 2 * W, 0)) flags |= CF_RET;
-    c.eReadStart = (u8)pLo; c.eReadEnd = (u8)(pHi - 1);
+    c.eReadStart = (u16)pLo; c.eReadEnd = (u16)(pHi - 1);
     c.eSeqStart = pLo + d; c.eSeqEnd = pHi - 1 + d;
-    c.leftClip = (u8)leftClip; c.rightClip = (u8)rightClip;
+    c.leftClip = (u16)leftClip; c.rightClip = (u16)rightClip;
     c.relaxed = mcE;
     c.eMatchCnt = mcE + 2 * leftClip + 2 * rightClip;
     // ---- the full-read alignment of [pLo, pHi) (SeqSet.hpp:2203-2274): <= 3 mismatches certify the diagonal
@@ -1212,17 +1228,17 @@ T1K_HDN T1K_NOINLINE inline int diag_hot(const RefView &R, const ReadView &Q, in
   if (mmLeft > 3 || mmRight > 3) return DF_DEFER;
   Cand &c = out;
   c.seqIdx = seqIdx; c.seqStart = rs + d; c.seqEnd = re + d;
-  c.readStart = (u8)rs; c.readEnd = (u8)re; c.strand01 = (u8)strand01;
-  c.matchCnt = (u16)mc; c.pad = 0; c.mmPos = 0;
+  c.readStart = (u16)rs; c.readEnd = (u16)re; c.strand01 = (u8)strand01;
+  c.matchCnt = (u16)mc; c.mmPos = 0;
   emitted = true;
   const int mcE = 2 * (W - mmTot);
   const int leftClip = pLo, rightClip = len - pHi;
   u8 flags = CF_PRE;
   if (d < 0 || d + len > clen) flags |= CF_NEEDCLIP;
   if (!sim_below(R, mcE, 2 * W, 0)) flags |= CF_RET;
-  c.eReadStart = (u8)pLo; c.eReadEnd = (u8)(pHi - 1);
+  c.eReadStart = (u16)pLo; c.eReadEnd = (u16)(pHi - 1);
   c.eSeqStart = pLo + d; c.eSeqEnd = pHi - 1 + d;
-  c.leftClip = (u8)leftClip; c.rightClip = (u8)rightClip;
+  c.leftClip = (u16)leftClip; c.rightClip = (u16)rightClip;
   c.relaxed = mcE;
   c.eMatchCnt = mcE + 2 * leftClip + 2 * rightClip;
   // ---- the full-read alignment of [pLo, pHi) (SeqSet.hpp:2203-2274): <= 3 mismatches certify the diagonal
@@ -1292,9 +1308,10 @@ T1K_HDN T1K_NOINLINE inline void chain_cluster_general(const RefView &R, const R
                                           int dom, const LaneScratch &S, int &nEmit, u64 &bestStrandKey, int &err) {
   const int m = e - s;
     // general path (SeqSet.hpp:1437-1456 + LIS :352-436)
-    if ((size_t)m * 12 + 512 > (size_t)SCR_DIR) { err |= ERR_SCRATCH; return; }
+    const size_t usedBytes = ((size_t)2 * (size_t)(Q.len + 1) + 15) & ~(size_t)15;
+    if ((size_t)m * 12 + usedBytes > (size_t)S.dirBytes) { err |= ERR_SCRATCH; return; }
     u16 *used = (u16 *)S.dir();                 // min |diag - dom| per read offset
-    u32 *conc = (u32 *)(S.dir() + 512);
+    u32 *conc = (u32 *)(S.dir() + usedBytes);
     u32 *chain = conc + m;
     u16 *top = (u16 *)(chain + m);
     u16 *link = top + m;
@@ -1355,7 +1372,7 @@ T1K_HDN T1K_NOINLINE inline void chain_cluster_general(const RefView &R, const R
       if (i == 0 || hit_b(chain[i]) != hit_b(chain[sz - 1])) chain[sz++] = chain[i];
     // the chain was built in S.dir(), which consume_chain's gap DPs overwrite: park it in its own region
     u32 *park = S.chain();
-    if (sz > SCR_CHAIN / 4) { err |= ERR_SCRATCH; return; }
+    if (sz > S.chainCap) { err |= ERR_SCRATCH; return; }
     T1K_NOUNROLL
     for (int i = 0; i < sz; ++i) park[i] = chain[i];
     ChainDirect cd; cd.p = park; cd.stride = 1;
@@ -1443,11 +1460,11 @@ T1K_HDN T1K_NOINLINE inline bool extend_cand(const RefView &R, const ReadView &Q
     if (HOT && m2 < 0) return false;
     m += m2;
   }
-  c.eReadStart = (u8)(rs - lo); c.eReadEnd = (u8)(re + ro);
+  c.eReadStart = (u16)(rs - lo); c.eReadEnd = (u16)(re + ro);
   c.eSeqStart = ss - lo; c.eSeqEnd = se + ro;
   int mc = 2 * m + c.matchCnt;
   if (!sim_below(R, mc, (re + ro) - (rs - lo) + 1 + (se + ro) - (ss - lo) + 1, 0)) flags |= CF_RET;
-  c.leftClip = (u8)leftClip; c.rightClip = (u8)rightClip;
+  c.leftClip = (u16)leftClip; c.rightClip = (u16)rightClip;
   c.relaxed = mc;                                  // SeqSet.hpp:2068 (before the clip bonus)
   c.eMatchCnt = mc + 2 * leftClip + 2 * rightClip;
   c.flags = flags;

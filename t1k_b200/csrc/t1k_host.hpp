@@ -136,8 +136,8 @@ inline bool pack_reference(int32_t n, const char *bases, const int64_t *off, con
 }
 
 // pack one read (both strands) into planes of RWORDS words each; returns false on invalid characters
-inline bool pack_read(const char *s, int len, u64 *fseq, u64 *fn, u64 *rseq, u64 *rn) {
-  for (int w = 0; w < RWORDS; ++w) fseq[w] = fn[w] = rseq[w] = rn[w] = 0;
+inline bool pack_read(const char *s, int len, u64 *fseq, u64 *fn, u64 *rseq, u64 *rn, int rwords = RWORDS) {
+  for (int w = 0; w < rwords; ++w) fseq[w] = fn[w] = rseq[w] = rn[w] = 0;
   for (int j = 0; j < len; ++j) {
     char c = s[j];
     if (!valid_base(c)) return false;

@@ -21,7 +21,9 @@ __device__ __forceinline__ void cp_async16(void *smemDst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 struct ReadsDev {
-  const u64 *planes;       // [(r*4 + plane) * RWORDS]; planes: fwd seq2, fwd n2, rc seq2, rc n2
+  const u64 *planes;       // [(r*4 + plane) * rwords]; planes: fwd seq2, fwd n2, rc seq2, rc n2
+  int rwords;              // words per plane = read_words(longest read of the batch)
+  int maxLen;              // longest read of the batch (sizes the per-lane scratch)
   const u16 *len;
   const int32_t *weight;
   const u32 *workList;     // optional indirection (deferred re-runs); NULL = identity
@@ -74,7 +76,7 @@ struct AssignParams {
   u32 *stabBuf;            // [reads][2 strands][256]: seed tables of the strands that deferred something (k_deferred reads them)
   DeferItem *dq; unsigned int *dqCtr; u32 dqCap;
   AlignItem *aq; unsigned int *aqCtr; u32 aqCap;
-  u8 *laneScratch;         // per lane SCR_BYTES
+  u8 *laneScratch;         // per lane scr_bytes(Q.maxLen)
   u32 *hitBuf;             // per warp hitCap x 32: hit lists of the alleles of a tile that take the hit-list path (lane-interleaved)
   unsigned int *workCtr;   // next position of the work list (persists over the rounds of a batch)
   u32 workBegin, workEnd;  // k_passes: the positions this round's k_seed took
@@ -107,16 +109,16 @@ __device__ __forceinline__ bool pair_less(u64 k, int i, u64 fk, int fi) { return
 
 // ---------------------------------------------------------------------------------------------------
 // ASCII reads -> 2-bit planes of both strands (rc: SeqSet::ReverseComplement, SeqSet.hpp:2103-2114)
-__global__ void k_pack_reads(const char *bases, const u64 *off, const u32 *len, u32 n, u64 *planes, u16 *lenOut, int *err) {
+__global__ void k_pack_reads(const char *bases, const u64 *off, const u32 *len, u32 n, int RW, u64 *planes, u16 *lenOut, int *err) {
   u32 r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const char *s = bases + off[r];
   int L = (int)len[r];
-  u64 *out = planes + (size_t)r * 4 * RWORDS;
-  if (L > 255) { atomicOr(err, ERR_READ_LEN); L = 0; }
+  u64 *out = planes + (size_t)r * 4 * RW;
+  if (L > (RW - 1) * 32 || L > MAX_READ_LEN) { atomicOr(err, ERR_READ_LEN); L = 0; }
   lenOut[r] = (u16)L;
   u64 fs = 0, fn = 0;
-  for (int w = 0; w < RWORDS; ++w) { out[w] = 0; out[RWORDS + w] = 0; out[2 * RWORDS + w] = 0; out[3 * RWORDS + w] = 0; }
+  for (int w = 0; w < RW; ++w) { out[w] = 0; out[RW + w] = 0; out[2 * RW + w] = 0; out[3 * RW + w] = 0; }
   for (int j = 0; j < L; ++j) {
     char c = s[j];
     int v = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : c == 'N' ? 4 : 5;
@@ -124,7 +126,7 @@ __global__ void k_pack_reads(const char *bases, const u64 *off, const u32 *len, 
     int sh = (j & 31) * 2;
     fs |= (u64)(v == 4 ? 3 : v) << sh;
     fn |= (u64)(v == 4) << sh;
-    if ((j & 31) == 31 || j == L - 1) { out[j >> 5] = fs; out[RWORDS + (j >> 5)] = fn; fs = fn = 0; }
+    if ((j & 31) == 31 || j == L - 1) { out[j >> 5] = fs; out[RW + (j >> 5)] = fn; fs = fn = 0; }
   }
   u64 rs = 0, rn = 0;
   for (int j = 0; j < L; ++j) {
@@ -133,7 +135,7 @@ __global__ void k_pack_reads(const char *bases, const u64 *off, const u32 *len, 
     int sh = (j & 31) * 2;
     rs |= (u64)(v == 4 ? 3 : v) << sh;
     rn |= (u64)(v == 4) << sh;
-    if ((j & 31) == 31 || j == L - 1) { out[2 * RWORDS + (j >> 5)] = rs; out[3 * RWORDS + (j >> 5)] = rn; rs = rn = 0; }
+    if ((j & 31) == 31 || j == L - 1) { out[2 * RW + (j >> 5)] = rs; out[3 * RW + (j >> 5)] = rn; rs = rn = 0; }
   }
 }
 
@@ -160,16 +162,20 @@ struct WarpSmem {
   u16 *seedA, *adv;
 };
 constexpr int DEFER_CAP = 64;
-__host__ __device__ inline size_t warp_smem_bytes(int seedCap) {
-  return ((size_t)seedCap * (16 + 4 + 4 + 2 + 2) + DEFER_CAP * 24 + (2 * RWORDS + 6) * 8 + 2 * 256 * 4 + 16 * 4 + 15) & ~(size_t)15;
+__host__ __device__ inline size_t warp_smem_bytes(int seedCap, int rwords) {
+  return ((size_t)seedCap * (16 + 4 + 4 + 2 + 2) + DEFER_CAP * 24 + (2 * rwords + 6) * 8 + 2 * 256 * 4 + 16 * 4 + 15) & ~(size_t)15;
 }
 
 // returns whether the read holds an N
 __device__ __forceinline__ bool load_planes(const AssignParams &P, u32 r, int strand01, const WarpSmem &W, int lane) {
-  const u64 *src = P.Q.planes + ((size_t)r * 4 + (strand01 ? 0 : 2)) * RWORDS;
+  const int RW = P.Q.rwords;
+  const u64 *src = P.Q.planes + ((size_t)r * 4 + (strand01 ? 0 : 2)) * RW;
   u64 nw = 0;
-  if (lane < RWORDS) W.seq[lane] = src[lane];
-  else if (lane < 2 * RWORDS) { nw = src[lane]; W.nn[lane - RWORDS] = nw; }   // n2 plane follows the seq plane
+  T1K_NOUNROLL
+  for (int w = lane; w < 2 * RW; w += 32) {              // n2 plane follows the seq plane
+    const u64 x = src[w];
+    if (w < RW) W.seq[w] = x; else { nw |= x; W.nn[w - RW] = x; }
+  }
   __syncwarp();
   return __any_sync(FULL, nw != 0);
 }
@@ -177,7 +183,7 @@ __device__ __forceinline__ bool load_planes(const AssignParams &P, u32 r, int st
 __device__ __forceinline__ Cand void_cand(u32 seqIdx, int strand01) {
   Cand v;                                         // a reserved slot that turned out to hold nothing: skipped like CF_SEP
   v.seqIdx = (int32_t)seqIdx; v.seqStart = v.seqEnd = 0; v.readStart = v.readEnd = 0; v.strand01 = (u8)strand01; v.flags = CF_SEP;
-  v.matchCnt = 0; v.pad = 0; v.eSeqStart = v.eSeqEnd = 0; v.eReadStart = v.eReadEnd = v.leftClip = v.rightClip = 0;
+  v.matchCnt = 0; v.eSeqStart = v.eSeqEnd = 0; v.eReadStart = v.eReadEnd = v.leftClip = v.rightClip = 0;
   v.eMatchCnt = 0; v.relaxed = 0; v.mmPos = 0;
   return v;
 }
@@ -442,7 +448,7 @@ __device__ u32 seed_one_read(const AssignParams &P, u32 r, const WarpSmem &W, Ca
               for (u32 j = 0; j < nAdv; ++j) {
                 const uint4 e = *reinterpret_cast<const uint4 *>(R.entries + (c1 - nAdv + j));
                 if (!handled && ((e.z >> lane) & 1u)) {
-                  if (cnt < CAP) hitTile[(size_t)cnt * 32 + lane] = a | (e.y << 8);
+                  if (cnt < CAP) hitTile[(size_t)cnt * 32 + lane] = hit_make((int)a, e.y);
                   ++cnt;
                 }
               }
@@ -521,14 +527,15 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_seed(AssignParam
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t gwarp = (size_t)blockIdx.x * WARPS_PER_BLOCK + warp;
   const int SC = P.seedCap;
-  u8 *sm = (u8 *)t1k_smem + (size_t)warp * warp_smem_bytes(SC);
+  const int RW = P.Q.rwords;
+  u8 *sm = (u8 *)t1k_smem + (size_t)warp * warp_smem_bytes(SC, RW);
   WarpSmem W;
   W.ent = (uint4 *)sm; W.q0 = W.ent + SC;
-  W.seq = (u64 *)(W.q0 + DEFER_CAP); W.nn = W.seq + RWORDS; W.s2 = W.nn + RWORDS;
+  W.seq = (u64 *)(W.q0 + DEFER_CAP); W.nn = W.seq + RW; W.s2 = W.nn + RW;
   W.q1 = (uint2 *)(W.s2 + 6);
   W.cur = (u32 *)(W.q1 + DEFER_CAP); W.end = W.cur + SC; W.stab = W.end + SC; W.lcp = W.stab + 256; W.bits = W.lcp + 256;
   W.seedA = (u16 *)(W.bits + 16); W.adv = W.seedA + SC;
-  LaneScratch S; S.base = P.laneScratch + (gwarp * 32 + lane) * (size_t)SCR_BYTES;
+  const LaneScratch S = lane_scratch(P.laneScratch + (gwarp * 32 + lane) * scr_bytes(P.Q.maxLen), P.Q.maxLen);
   u32 *hitTile = P.hitBuf + gwarp * (size_t)P.hitCap * 32;
   const u64 arena0 = gwarp * P.arenaCands;
   u64 used = 0;
@@ -549,15 +556,15 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_seed(AssignParam
 __global__ void __launch_bounds__(128) k_deferred(AssignParams P) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nThreads = (size_t)gridDim.x * blockDim.x;
   const u32 nItems = min(*P.dqCtr, P.dqCap);
-  LaneScratch S; S.base = P.laneScratch + tid * (size_t)SCR_BYTES;
+  const LaneScratch S = lane_scratch(P.laneScratch + tid * scr_bytes(P.Q.maxLen), P.Q.maxLen);
   const RefView &R = P.R;
   int err = 0;
   for (size_t i = tid; i < nItems; i += nThreads) {
     const DeferItem it = P.dq[i];
     if (it.read == 0xffffffffu) continue;
     const int strand01 = it.pass == 0 ? 1 : 0;
-    const u64 *pl = P.Q.planes + ((size_t)it.read * 4 + (strand01 ? 0 : 2)) * RWORDS;
-    ReadView Q; Q.seq2 = pl; Q.n2 = pl + RWORDS; Q.len = P.Q.len[it.read]; Q.anyN = false;     // (deferring strands hold no N)
+    const u64 *pl = P.Q.planes + ((size_t)it.read * 4 + (strand01 ? 0 : 2)) * P.Q.rwords;
+    ReadView Q; Q.seq2 = pl; Q.n2 = pl + P.Q.rwords; Q.len = P.Q.len[it.read]; Q.anyN = false;     // (deferring strands hold no N)
     ReadState *st = P.state + it.read;
     Cand *slot = P.candPool + st->candOff + it.at;
     Cand c;
@@ -594,9 +601,10 @@ __device__ void passes_one_read(const AssignParams &P, u32 r, u32 *qCand, u64 *q
   unsigned long long pos = 0;
   bool deferred = false;
   if (c1 - c0 > 0) {
-    const u64 *pl = P.Q.planes + ((size_t)r * 4 + (best01 ? 0 : 2)) * RWORDS;
-    ReadView Qv; Qv.seq2 = pl; Qv.n2 = pl + RWORDS; Qv.len = P.Q.len[r];
-    { u64 nw = lane < RWORDS ? pl[RWORDS + lane] : 0; Qv.anyN = __any_sync(FULL, nw != 0); }
+    const int RW = P.Q.rwords;
+    const u64 *pl = P.Q.planes + ((size_t)r * 4 + (best01 ? 0 : 2)) * RW;
+    ReadView Qv; Qv.seq2 = pl; Qv.n2 = pl + RW; Qv.len = P.Q.len[r];
+    { u64 nw = 0; for (int w = lane; w < RW; w += 32) nw |= pl[RW + w]; Qv.anyN = __any_sync(FULL, nw != 0); }
     // goodMatchCnt (SeqSet.hpp:2156-2186) = the largest matchCnt among the returned candidates that precede the first
     // failing one = the first returned candidate if it precedes the failure, and nothing otherwise.
     const int good = rOrd < fOrd ? order_key_mc(rOrd) : -1;
@@ -742,7 +750,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_passes(AssignParams P)
   __shared__ u64 qSlotS[WARPS_PER_BLOCK][DEFER_CAP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t gwarp = (size_t)blockIdx.x * WARPS_PER_BLOCK + warp, nWarps = (size_t)gridDim.x * WARPS_PER_BLOCK;
-  LaneScratch S; S.base = P.laneScratch + (gwarp * 32 + lane) * (size_t)SCR_BYTES;
+  const LaneScratch S = lane_scratch(P.laneScratch + (gwarp * 32 + lane) * scr_bytes(P.Q.maxLen), P.Q.maxLen);
   for (size_t w = P.workBegin + gwarp; w < P.workEnd; w += nWarps) {
     const u32 r = P.Q.workList ? P.Q.workList[w] : (u32)w;
     passes_one_read(P, r, qCandS[warp], qSlotS[warp], S, lane);
@@ -755,7 +763,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_passes(AssignParams P)
 __global__ void __launch_bounds__(128) k_align(AssignParams P) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nThreads = (size_t)gridDim.x * blockDim.x;
   const u32 nItems = min(*P.aqCtr, P.aqCap);
-  LaneScratch S; S.base = P.laneScratch + tid * (size_t)SCR_BYTES;
+  const LaneScratch S = lane_scratch(P.laneScratch + tid * scr_bytes(P.Q.maxLen), P.Q.maxLen);
   const RefView &R = P.R;
   int err = 0;
   for (size_t i = tid; i < nItems; i += nThreads) {
@@ -763,11 +771,12 @@ __global__ void __launch_bounds__(128) k_align(AssignParams P) {
     if (it.read == 0xffffffffu) continue;
     const ReadState *st = P.state + it.read;
     const int best01 = (st->bestKey & 1) ? 0 : 1;
-    const u64 *pl = P.Q.planes + ((size_t)it.read * 4 + (best01 ? 0 : 2)) * RWORDS;
-    ReadView Q; Q.seq2 = pl; Q.n2 = pl + RWORDS; Q.len = P.Q.len[it.read];
+    const int RW = P.Q.rwords;
+    const u64 *pl = P.Q.planes + ((size_t)it.read * 4 + (best01 ? 0 : 2)) * RW;
+    ReadView Q; Q.seq2 = pl; Q.n2 = pl + RW; Q.len = P.Q.len[it.read];
     u64 nw = 0;
-#pragma unroll
-    for (int k = 0; k < RWORDS; ++k) nw |= pl[RWORDS + k];
+    T1K_NOUNROLL
+    for (int k = 0; k < RW; ++k) nw |= pl[RW + k];
     Q.anyN = nw != 0;
     Cand c = P.candPool[st->candOff + it.cand];
     full_align<false>(R, Q, c, P.Q.weight[it.read], S, err);

@@ -42,7 +42,7 @@ Emu *emu_create(int32_t n, const char *bases, const int64_t *off, const int32_t 
   R.kstart = e->P.kstart.data(); R.post = e->P.post.data(); R.kinfo = e->P.kinfo.data(); R.entries = e->P.entries.data();
   R.covDiff = e->covDiff.data(); R.covPoint = e->covPoint.data(); R.covOff = e->P.covOff.data();
   R.nAlleles = n; R.sim = sim; R.relax = relax;
-  e->scratch.assign(SCR_BYTES, 0);
+  e->scratch.assign(scr_bytes(MAX_READ_LEN), 0);
   return e;
 }
 void emu_destroy(Emu *e) { delete e; }
@@ -62,12 +62,12 @@ int32_t emu_align(const char *t, int32_t lent, const char *p, int32_t lenp, int8
   u8 tHasN = memchr(t, 'N', lent) != NULL;
   RefView R; memset(&R, 0, sizeof(R));
   R.seq2 = seq2.data(); R.n2 = n2.data(); R.ex2 = ex2.data(); R.wordOff = &w0; R.len = &len; R.hasN = &tHasN; R.nAlleles = 1;
-  u64 fs[RWORDS], fn[RWORDS], rs[RWORDS], rn[RWORDS];
-  if (lenp > 255) return -2;
-  pack_read(p, lenp, fs, fn, rs, rn);
+  u64 fs[MAX_RWORDS], fn[MAX_RWORDS], rs[MAX_RWORDS], rn[MAX_RWORDS];
+  if (lenp > MAX_READ_LEN) return -2;
+  pack_read(p, lenp, fs, fn, rs, rn, MAX_RWORDS);
   ReadView Q; Q.seq2 = fs; Q.n2 = fn; Q.len = lenp; Q.anyN = memchr(p, 'N', lenp) != NULL;
-  std::vector<u8> scr(SCR_BYTES, 0);
-  LaneScratch S; S.base = scr.data();
+  std::vector<u8> scr(scr_bytes(MAX_READ_LEN), 0);
+  const LaneScratch S = lane_scratch(scr.data(), MAX_READ_LEN);
   int err = 0, mm = 0;
   const AlleleView T = allele_view(R, 0, Q);
   *certified = (lent == lenp && lent > 0) ? (int)diag_certified(T, 0, Q, 0, lent, mm) : 0;
@@ -85,10 +85,10 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
   const RefView &R = E->R;
   int len = (int)strlen(read);
   *errOut = 0;
-  if (len < KMER || len > 255) return -1;
-  u64 planes[4][RWORDS];
-  if (!pack_read(read, len, planes[0], planes[1], planes[2], planes[3])) { *errOut = -1; return -1; }
-  LaneScratch S; S.base = E->scratch.data();
+  if (len < KMER || len > MAX_READ_LEN) return -1;
+  u64 planes[4][MAX_RWORDS];
+  if (!pack_read(read, len, planes[0], planes[1], planes[2], planes[3], MAX_RWORDS)) { *errOut = -1; return -1; }
+  const LaneScratch S = lane_scratch(E->scratch.data(), MAX_READ_LEN);
   int err = 0;
   std::vector<Cand> cands;
   u64 bestKey = 0;
@@ -99,7 +99,7 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
     // seed selection (GetHitsFromRead skip rule)
     u32 prev = 0; int skip = 0;
     const int P = len - KMER + 1;
-    u8 seedA[256]; u32 cur[256], end[256]; int nS = 0;
+    u16 seedA[1024]; u32 cur[1024], end[1024]; int nS = 0;
     bool strandFast = !Q.anyN && len <= FAST_MAX_LEN && !E->noFast;     // the kernel's eligibility rule (t1k_kernels.cuh)
     for (int a = 0; a < P; ++a) {
       u32 code = (u32)(fetch32(Q.seq2, a) & 0x3FFFFF);
@@ -109,7 +109,7 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
         if (valid) { lo = R.kinfo[code].estart; hi = R.kinfo[code + 1].estart; size = (int)(R.kinfo[code + 1].pstart - R.kinfo[code].pstart); }
         if (size >= 100 && a != 0 && a != P - 1 && skip < KMER / 2) { ++skip; continue; }
         skip = 0;
-        if (size > 0) { seedA[nS] = (u8)a; cur[nS] = lo; end[nS] = hi; ++nS; if (kmer_homopolymer(code)) strandFast = false; }
+        if (size > 0) { seedA[nS] = (u16)a; cur[nS] = lo; end[nS] = hi; ++nS; if (kmer_homopolymer(code)) strandFast = false; }
       }
       prev = code;
     }
@@ -120,9 +120,7 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
     u32 s2[10], lcp[260];
     u64 S2[5];
     if (strandFast) {
-      u16 seedA16[256];
-      for (int k = 0; k < nS; ++k) seedA16[k] = seedA[k];
-      seed_bits2_build(seedA16, nS, s2);
+      seed_bits2_build(seedA, nS, s2);
       for (int j = 0; j < 5; ++j) S2[j] = (u64)s2[2 * j] | ((u64)s2[2 * j + 1] << 32);
       lc_prefix_build(Q, lcp);
     }
@@ -146,7 +144,7 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
             if (n == 0) d0 = dg;
             const int dd = dg - d0;
             ++n; onDiag += dd == 0; far += dd > RADIUS || dd < -RADIUS;
-            h.push_back((u32)seedA[k] | (e.off << 8));        // (sweep 2 of the kernel: only for declined alleles)
+            h.push_back(hit_make((int)seedA[k], e.off));        // (sweep 2 of the kernel: only for declined alleles)
           }
         }
         if (n < 3) continue;

@@ -113,3 +113,62 @@ def test_device_matches_reference_on_duplications(name):
             assert np.array_equal(ss.GetBaseCoverage(), g["cov"])
         finally:
             os.environ.pop("T1K_NO_FAST", None)
+
+
+# ------------------------------------------------------------------------------------------------
+# reads longer than 255 bases (tests/long_workloads.py, goldens from the unmodified reference)
+import long_workloads as LW  # noqa: E402
+
+LONG = {name: (recs, reads, sim, relax) for name, recs, reads, sim, relax in LW.cases()}
+
+
+def _golden_long(name):
+    z = np.load(os.path.join(HERE, "golden", "long", name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize("name", sorted(LONG))
+def test_oracle_matches_reference_on_long_reads(name):
+    recs, reads, sim, relax = LONG[name]
+    g = _golden_long(name)
+    kept, w = O.collapse_reference(recs)
+    orc = O.Oracle(kept, sim, relax, O.seq_weights(kept, w))
+    for i, s in enumerate(reads):
+        ret, ov = orc.assign(s, int(g["weight"]))
+        assert ret == g["ret"][i], i
+        got = np.stack([ov[k] for k in O.OVERLAP_DT.names], axis=1) if len(ov) else np.zeros((0, 10), np.int32)
+        assert np.array_equal(got, g["ov"][g["ptr"][i]:g["ptr"][i + 1]]), i
+    assert np.array_equal(np.concatenate([orc.coverage(a) for a in range(len(kept))]), g["cov"])
+
+
+@pytest.mark.parametrize("name", sorted(LONG))
+def test_lane_code_matches_reference_on_long_reads(emu, name):  # noqa: F811
+    recs, reads, sim, relax = LONG[name]
+    g = _golden_long(name)
+    out, cov = _emu_run(emu, recs, reads, sim, relax, int(g["weight"]))
+    for i, (n, rows) in enumerate(out):
+        assert n == g["ret"][i], i
+        assert np.array_equal(rows, g["ov"][g["ptr"][i]:g["ptr"][i + 1]]), i
+    assert np.array_equal(cov, g["cov"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(LONG))
+def test_device_matches_reference_on_long_reads(name):
+    from t1k_b200.genotyper import SeqSet
+    recs, reads, sim, relax = LONG[name]
+    g = _golden_long(name)
+    ref = RefSet(recs)
+    ss = SeqSet(ref, sim, relax)
+    a = ss.AssignRead(reads, [int(g["weight"])] * len(reads))
+    row_ptr, ret, rec = a.fetch()
+    assert np.array_equal(ret, g["ret"])
+    assert np.array_equal(row_ptr.astype(np.int64), g["ptr"])
+    got = np.stack([rec[k] for k in O.OVERLAP_DT.names], axis=1) if len(rec) else np.zeros((0, 10), np.int32)
+    assert np.array_equal(got, g["ov"])
+    assert np.array_equal(ss.GetBaseCoverage(), g["cov"])
+    # a batch that mixes short and long reads takes the long-read geometry for all of them
+    mixed = [reads[0][:120], reads[1], reads[2][:200]]
+    b = ss.AssignRead(mixed)
+    _, ret2, _ = b.fetch()
+    assert ret2[1] == g["ret"][1]

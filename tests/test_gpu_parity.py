@@ -329,7 +329,7 @@ def test_empty_and_invalid_inputs():
         ss.AssignRead([b"ACGTACGTACGTXACGTACGTACGT"], [1])
     assert e.value.code == 3
     with pytest.raises(T1KError) as e:
-        ss.AssignRead([b"A" * 300], [1])
+        ss.AssignRead([b"A" * 1001], [1])                  # T1K_MAX_READ_LEN = 1000
     assert e.value.code == 3
     gt = Genotyper(ref, 0.8, False)
     rng = np.random.default_rng(1)
