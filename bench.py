@@ -259,6 +259,78 @@ def deep_set_rate(config, pairs):
     return len(np.unique(allv)) / float(pairs)
 
 
+def filter_stage(args, real_stdout):
+    """the candidate filter of fastq-extractor (k_filter through t1k_filter_batch) on a WGS-like read set:
+    150 bp pairs, 2 % drawn from the HLA-RNA-like reference (candidates), 98 % random sequence (the bulk of a genome).  The
+    CPU baseline is the unmodified fastq-extractor binary (oracle/_ref/fastq-extractor) on a bounded sample."""
+    import torch
+    from t1k_b200 import synth
+    from t1k_b200.extractor import CandidateFilter
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    n = args.pairs or 4000000
+    recs, ref = make_reference(2)
+    rng = np.random.default_rng(5)
+    n_cand = n // 50
+    _, _, c1, c2 = make_workload(n_cand, seed=77, config=2)
+    alpha = np.frombuffer(b"ACGT", dtype=np.uint8)
+    r1 = alpha[rng.integers(0, 4, size=(n, 150), dtype=np.uint8)]
+    r2 = alpha[rng.integers(0, 4, size=(n, 150), dtype=np.uint8)]
+    where = rng.choice(n, size=n_cand, replace=False)
+    r1[where] = c1
+    r2[where] = c2
+    f = CandidateFilter(recs, [r.tobytes() for r in r1[:1000]], True, 0.8)
+    both = np.concatenate([r1, r2])
+
+    def step():
+        return f.IsGoodCandidate(both, with_stats=True)
+
+    for _ in range(args.warmup):
+        good, st = step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ms_k = 0.0
+    for _ in range(args.steps):
+        good, st = step()
+        ms_k += st["ms_kernel"]
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    kept = int((good[:n] | good[n:]).sum())
+    peak, peak_src = measured_peaks()
+    # algorithmic bytes per read: its packed bases + two 8-byte table entries per k-mer window of both strands (+ 16 B per entry swept)
+    alg = (both.shape[0] * ((150 + 3) // 4) + 16 * st["windows"] + 16 * st["entries"])
+    ms = ms_k / args.steps
+    line = {"metric": "reads/sec through the fastq-extractor candidate filter (150bp PE, HLA ref, WGS-like mix)", "value": 2 * n * args.steps / (ms_k * 1e-3),
+            "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8 / u32 (2-bit bases, k-mer codes)", "data": "synthetic",
+            "config": {"workload": "SURVEY 8f N1: %d read pairs x 150 bp, 2 %% from the HLA-RNA-like reference, 98 %% random; k = %d, hitLenRequired = %d" % (n, f.k, f.hit_len),
+                       "kept_pairs": kept, "reads_chained": int(st["chained"]), "value_basis": "CUDA-event time of k_filter, reads resident in HBM"},
+            "e2e": {"value": 2 * n * args.steps / wall, "unit": "reads/s", "h2d_bytes_per_step": int(both.nbytes), "d2h_bytes_per_step": int(both.shape[0])},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"kernel": "k_filter", "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg),
+                         "note": "bytes = packed read + 16 B per k-mer window looked up (two 8-byte entries of the 4^k table, random access) + 16 B per index entry swept"}}
+    exe = os.path.join(ROOT, "oracle", "_ref", "fastq-extractor")
+    if not args.no_cpu_baseline and os.path.exists(exe):
+        m = min(n, 200000)
+        td = tempfile.mkdtemp(prefix="t1kfilt_")
+        try:
+            fa = os.path.join(td, "ref.fa")
+            synth.write_fasta(fa, recs)
+            synth.write_fastq(os.path.join(td, "a_1.fq"), r1[:m])
+            synth.write_fastq(os.path.join(td, "a_2.fq"), r2[:m])
+            cores = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            subprocess.run([exe, "-f", fa, "-1", os.path.join(td, "a_1.fq"), "-2", os.path.join(td, "a_2.fq"), "-t", str(cores), "-o", os.path.join(td, "out")],
+                           check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 2 * m / dt, "unit": "reads/s", "cores": cores, "kind": "reference",
+                                    "sample": "first %d pairs of the same set through the stock fastq-extractor -t %d (wall clock incl. index build and FASTQ parsing)" % (m, cores)}
+        finally:
+            shutil.rmtree(td, ignore_errors=True)
+    print(json.dumps(line), file=real_stdout, flush=True)
+
+
 def _claim_stdout():
     """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON line on stdout.
     Everything else is sent to stderr; the returned file object is the real stdout for the JSON line."""
@@ -288,7 +360,11 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=0, help="fragments of the CPU reference sample (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the multi-GPU check against a one-GPU run of the union")
+    ap.add_argument("--stage", default="genotype", choices=["genotype", "filter"], help="filter: SURVEY 8f N1, the extractor's candidate filter")
     args = ap.parse_args()
+    if args.stage == "filter":
+        filter_stage(args, real_stdout)
+        return
     cfg = CONFIGS[args.config]
     if not args.pairs:
         args.pairs = int(os.environ.get("T1K_BENCH_PAIRS", cfg["pairs"]))

@@ -180,6 +180,33 @@ typedef struct {
 int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t stride, uint32_t n_frag,
                  const T1KGenotypeParams *params, T1KGenotypeResult *res /* caller-allocated arrays */);
 
+/* ---- the candidate filter of fastq-extractor, the stage in front of the hot path.
+ * IsGoodCandidate (FastqExtractor.cpp:113-118) = !IsLowComplexity (:89-112) && SeqSet::HasHitInSet (SeqSet.hpp:1915-1990) for a
+ * batch of reads against the sequences of the extraction reference.  kmer_length / hit_len_required are what
+ * FastqExtractor.cpp:381-418 sets up (k = max(9, SeqSet::InferKmerLength(total length)); hitLenRequired from the mean read
+ * length); kmer_length = 0 infers k from the total length as the reference does. */
+typedef struct T1KFilter T1KFilter;
+typedef struct {
+  int32_t n_seqs;
+  const char *bases;        /* concatenated upper-case ACGTN */
+  const int64_t *offset;    /* [n_seqs+1] */
+  int32_t kmer_length;      /* 0 = max(9, InferKmerLength) */
+  int32_t hit_len_required;
+  double similarity;        /* -s of fastq-extractor (SeqSet::SetRefSeqSimilarity) */
+  int32_t device;           /* CUDA device ordinal, -1 = current */
+} T1KFilterDesc;
+typedef struct {
+  uint64_t windows, entries, chained;   /* k-mer windows looked up, index entries swept, reads that reached the chaining */
+  float ms_kernel;                      /* device time of k_filter (CUDA events) */
+  int32_t kmer_length;
+} T1KFilterStats;
+int t1k_filter_create(const T1KFilterDesc *desc, T1KFilter **out);
+void t1k_filter_destroy(T1KFilter *f);
+/* good[i] = IsGoodCandidate(read i); a read pair is kept when either mate is good (FastqExtractor.cpp:199-212).
+ * stats may be NULL. */
+int t1k_filter_batch(T1KFilter *f, const char *bases, const uint64_t *off, const uint32_t *len, uint32_t n_reads,
+                     uint8_t *good, T1KFilterStats *stats);
+
 /* ---- multi-GPU plumbing.  The launcher (torchrun + torch.distributed, MPI, a shared file ...) moves the 128-byte
  * unique id from rank 0 to the other ranks; everything on the data path is NCCL over NVLink. */
 #define T1K_UNIQUE_ID_BYTES 128

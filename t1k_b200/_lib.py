@@ -26,7 +26,8 @@ EXPORTS = ["t1k_last_error", "t1k_device_count", "t1k_ref_create", "t1k_ref_dest
            "t1k_coverage_fetch", "t1k_coverage_reset", "t1k_missing_coverage", "t1k_pair_batch", "t1k_free",
            "t1k_em_run", "t1k_genotype", "t1k_comm_unique_id", "t1k_comm_create", "t1k_comm_destroy",
            "t1k_coverage_allreduce", "t1k_groups_create", "t1k_groups_destroy", "t1k_groups_add_fragments",
-           "t1k_groups_serialize", "t1k_groups_merge", "t1k_groups_fetch", "t1k_em_partition"]
+           "t1k_groups_serialize", "t1k_groups_merge", "t1k_groups_fetch", "t1k_em_partition",
+           "t1k_filter_create", "t1k_filter_destroy", "t1k_filter_batch"]
 
 UNIQUE_ID_BYTES = 128
 
@@ -67,6 +68,16 @@ class GenotypeResult(C.Structure):
                 ("n_postings", C.c_uint64), ("n_candidates", C.c_uint64), ("n_launches", C.c_uint64),
                 ("ms_prep_wait", C.c_float), ("ms_exchange", C.c_float), ("n_pair_records", C.c_uint64), ("em_nnz", C.c_uint64),
                 ("em_updates", C.c_int32)]
+
+
+class FilterDesc(C.Structure):
+    _fields_ = [("n_seqs", C.c_int32), ("bases", C.c_char_p), ("offset", C.c_void_p), ("kmer_length", C.c_int32),
+                ("hit_len_required", C.c_int32), ("similarity", C.c_double), ("device", C.c_int32)]
+
+
+class FilterStats(C.Structure):
+    _fields_ = [("windows", C.c_uint64), ("entries", C.c_uint64), ("chained", C.c_uint64), ("ms_kernel", C.c_float),
+                ("kmer_length", C.c_int32)]
 
 
 class AssignStats(C.Structure):
@@ -125,6 +136,10 @@ def lib():
         L.t1k_groups_fetch.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                        C.c_void_p, C.c_void_p]
         L.t1k_em_partition.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.t1k_filter_create.argtypes = [C.POINTER(FilterDesc), C.POINTER(C.c_void_p)]
+        L.t1k_filter_destroy.argtypes = [C.c_void_p]
+        L.t1k_filter_destroy.restype = None
+        L.t1k_filter_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(FilterStats)]
         _lib = L
     return _lib
 

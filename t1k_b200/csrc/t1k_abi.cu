@@ -19,6 +19,7 @@
 #include "t1k_kernels.cuh"
 #include "t1k_model.hpp"
 #include "t1k_pair.cuh"
+#include "t1k_filter.cuh"
 
 using namespace t1k;
 
@@ -1381,6 +1382,130 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
       set_allele_abundance(rc.data(), in.ecLen.data(), EC.ecPtr.data(), EC.ecAlleles.data(), EC.size(), nA, res->abundance, res->ec_abundance);
   }
   res->ms_em = (float)(now_ms() - te);
+  return T1K_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// candidate filter of fastq-extractor
+struct T1KFilter {
+  int device = 0, nSM = 0, k = 0, hitLenReq = 0;
+  double sim = 0.8;
+  DevMem kinfo, entries, present, workCtr, errFlag, stats, hitBuf;
+  cudaStream_t stream = nullptr;
+  int gridBlocks = 0, seedCap = 0, rwords = 0, hitCap = 4096;
+  ~T1KFilter() { if (stream) cudaStreamDestroy(stream); }
+};
+
+extern "C" {
+
+int t1k_filter_create(const T1KFilterDesc *d, T1KFilter **out) {
+  if (!d || !out || d->n_seqs <= 0 || !d->bases || !d->offset) return fail(T1K_ERR_ARG, "t1k_filter_create: bad argument");
+  *out = nullptr;
+  int dev;
+  if (int rc = pick_device(d->device, &dev)) return rc;
+  CK(cudaSetDevice(dev));
+  int k = d->kmer_length;
+  if (k == 0) {                      // SeqSet::InferKmerLength (SeqSet.hpp:2830-2845) under the extractor's floor of 9
+    int64_t tot = d->offset[d->n_seqs] - d->offset[0];
+    int digits = 0;
+    while (tot) { ++digits; tot /= 4; }
+    k = std::max(9, digits + 1);
+  }
+  if (k < 1 || k > 15) return fail(T1K_ERR_UNSUPPORTED, "candidate filter: k-mer length outside 1..15");
+  std::vector<KmerInfo> kinfo;
+  std::vector<KmerEntry> entries;
+  if (!build_filter_index(d->n_seqs, d->bases, d->offset, k, kinfo, entries)) return fail(T1K_ERR_ARG, "reference contains a character outside ACGTN");
+  for (size_t i = 0; i < entries.size(); ++i)
+    if (entries[i].off >= (1u << 22)) return fail(T1K_ERR_UNSUPPORTED, "sequence longer than 2^22 bases");
+  entries.resize(entries.size() + 4, KmerEntry{0xffffffffu, 0, 0, 0});
+  std::vector<u32> present((kinfo.size() + 31) / 32, 0);
+  for (size_t c = 0; c + 1 < kinfo.size(); ++c) if (kinfo[c + 1].pstart > kinfo[c].pstart) present[c >> 5] |= 1u << (c & 31);
+  T1KFilter *f = new T1KFilter;
+  f->device = dev; f->k = k; f->hitLenReq = d->hit_len_required; f->sim = d->similarity;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+  if (e == cudaSuccess) { f->nSM = prop.multiProcessorCount; e = f->kinfo.alloc(kinfo.size() * sizeof(KmerInfo)); }
+  if (e == cudaSuccess) e = cudaMemcpy(f->kinfo.p, kinfo.data(), kinfo.size() * sizeof(KmerInfo), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = f->entries.alloc(entries.size() * sizeof(KmerEntry));
+  if (e == cudaSuccess) e = cudaMemcpy(f->entries.p, entries.data(), entries.size() * sizeof(KmerEntry), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = f->present.alloc(present.size() * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(f->present.p, present.data(), present.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = f->workCtr.alloc(4);
+  if (e == cudaSuccess) e = f->errFlag.alloc(4);
+  if (e == cudaSuccess) e = f->stats.alloc(3 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete f; return fail(T1K_ERR_CUDA, std::string("t1k_filter_create: ") + cudaGetErrorString(e)); }
+  *out = f;
+  return T1K_OK;
+}
+
+void t1k_filter_destroy(T1KFilter *f) {
+  if (!f) return;
+  cudaSetDevice(f->device);
+  delete f;
+}
+
+int t1k_filter_batch(T1KFilter *f, const char *bases, const uint64_t *off, const uint32_t *len, uint32_t n, uint8_t *good, T1KFilterStats *stats) {
+  if (!f || (n > 0 && (!bases || !off || !len || !good))) return fail(T1K_ERR_ARG, "t1k_filter_batch: bad argument");
+  CK(cudaSetDevice(f->device));
+  stale("t1k_filter_batch");
+  if (stats) { stats->windows = stats->entries = stats->chained = 0; stats->ms_kernel = 0; stats->kmer_length = f->k; }
+  if (n == 0) return T1K_OK;
+  cudaStream_t st = f->stream;
+  size_t total = 0; int maxLen = 1;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (len[i] > T1K_MAX_READ_LEN) return fail(T1K_ERR_ARG, "read longer than T1K_MAX_READ_LEN");
+    total = std::max(total, (size_t)(off[i] + len[i]));
+    maxLen = std::max(maxLen, (int)len[i]);
+  }
+  const int rwords = read_words(maxLen <= 255 ? 255 : MAX_READ_LEN);
+  const int seedCap = std::max(64, (maxLen + 31) & ~31);
+  const size_t smem = filter_smem_bytes(seedCap, rwords) * WARPS_PER_BLOCK;
+  if (!f->gridBlocks || seedCap > f->seedCap || rwords != f->rwords) {
+    CK(cudaFuncSetAttribute((const void *)k_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int perSM = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, (const void *)k_filter, WARPS_PER_BLOCK * 32, smem));
+    if (perSM < 1) return fail(T1K_ERR_UNSUPPORTED, "k_filter does not fit on an SM");
+    f->gridBlocks = perSM * f->nSM; f->seedCap = seedCap; f->rwords = rwords;
+    CK(f->hitBuf.alloc((size_t)f->gridBlocks * WARPS_PER_BLOCK * ((size_t)4 * f->hitCap + filt::FILTER_USED_BYTES / 4) * sizeof(u32)));
+  }
+  DevMem dBases, dOff, dLen, planes, len16, dGood;
+  CK(dBases.alloc(total)); CK(dOff.alloc((size_t)n * 8)); CK(dLen.alloc((size_t)n * 4));
+  CK(planes.alloc((size_t)n * 4 * rwords * 8)); CK(len16.alloc((size_t)n * 2)); CK(dGood.alloc(n));
+  CK(cudaMemcpyAsync(dBases.p, bases, total, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dOff.p, off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dLen.p, len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(f->errFlag.p, 0, 4, st));
+  CK(cudaMemsetAsync(f->workCtr.p, 0, 4, st));
+  CK(cudaMemsetAsync(f->stats.p, 0, 3 * sizeof(unsigned long long), st));
+  k_pack_reads<<<(n + 127) / 128, 128, 0, st>>>(dBases.as<char>(), dOff.as<u64>(), dLen.as<u32>(), n, rwords, planes.as<u64>(), len16.as<u16>(), f->errFlag.as<int>());
+  CK(cudaGetLastError());
+  FilterParams P;
+  P.kinfo = f->kinfo.as<KmerInfo>(); P.entries = f->entries.as<KmerEntry>(); P.present = f->present.as<u32>(); P.k = f->k; P.hitLenReq = f->hitLenReq; P.sim = f->sim;
+  P.planes = planes.as<u64>(); P.rwords = rwords; P.len = len16.as<u16>(); P.nReads = n; P.good = dGood.as<u8>();
+  P.hitBuf = f->hitBuf.as<u32>(); P.hitCap = f->hitCap; P.seedCap = f->seedCap; P.workCtr = f->workCtr.as<unsigned int>();
+  P.err = f->errFlag.as<int>(); P.stats = f->stats.as<unsigned long long>();
+  cudaEvent_t ev0, ev1;
+  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+  struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
+  CK(cudaEventRecord(ev0, st));
+  k_filter<<<f->gridBlocks, WARPS_PER_BLOCK * 32, filter_smem_bytes(f->seedCap, rwords) * WARPS_PER_BLOCK, st>>>(P);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ev1, st));
+  int err = 0;
+  unsigned long long hs[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(good, dGood.p, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&err, f->errFlag.p, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hs, f->stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (err & (ERR_READ_LEN | ERR_READ_CHAR)) return fail(T1K_ERR_ARG, "read contains a character outside ACGTN or is too long");
+  if (err) return fail(T1K_ERR_UNSUPPORTED, "t1k_filter_batch:" + decode_err(err));
+  if (stats) {
+    stats->windows = hs[0]; stats->entries = hs[1]; stats->chained = hs[2];
+    CK(cudaEventElapsedTime(&stats->ms_kernel, ev0, ev1));
+  }
   return T1K_OK;
 }
 

@@ -1,7 +1,6 @@
-// DRAFT for SURVEY.md §8f N1 (candidate filter of fastq-extractor) — lane-level building blocks with a RUNTIME k-mer
-// length, checked on the CPU against the reference binary (tests/filter_emu.cpp).  Not yet part of the
-// product library: the kernel around them (streaming reads, per-(strand, sequence) hit counting over allele tiles, best
-// bucket, this chaining) and its C-ABI entry point need GPU time to validate and measure.
+// SURVEY.md §8f N1 (candidate filter of fastq-extractor) — lane-level building blocks with a RUNTIME k-mer length.  The
+// kernel around them is k_filter (t1k_filter.cuh), the C-ABI entry point t1k_filter_batch; tests/filter_emu.cpp runs the
+// same code sequentially on the CPU against what the reference binary keeps.
 //
 // Reference: IsLowComplexity FastqExtractor.cpp:89-112, SeqSet::HasHitInSet SeqSet.hpp:1915-1990 (GetHitsFromRead
 // :1071-1229 with kmerLength = max(9, InferKmerLength), GetOverlapsFromHits :1232-1556 with filter = 0).
@@ -42,7 +41,7 @@ T1K_HD bool read_low_complexity(const u64 *seq2, const u64 *n2, int len) {
 // The k-mers GetHitsFromRead looks up on one strand (skip rule Q2 with skipLimit = k / 2; `prev` is the previous looked-at
 // code and survives from the forward into the reverse pass as in the reference).  Returns the number of seeds;
 // seedA / lo / hi receive read offset and posting range of each.
-T1K_HDN inline int seed_list(const IndexView &I, const u64 *seq2, const u64 *n2, int len, u32 &prev, u8 *seedA, u32 *lo, u32 *hi) {
+T1K_HDN inline int seed_list(const IndexView &I, const u64 *seq2, const u64 *n2, int len, u32 &prev, u16 *seedA, u32 *lo, u32 *hi) {
   const int k = I.k, NP = len - k + 1;
   const u64 codeMask = (1ull << (2 * k)) - 1, nMask = codeMask & M55;
   int nS = 0, skip = 0;
@@ -56,7 +55,7 @@ T1K_HDN inline int seed_list(const IndexView &I, const u64 *seq2, const u64 *n2,
       const int size = (int)(h - l);
       if (size >= 100 && a != 0 && a != NP - 1 && skip < k / 2) { ++skip; continue; }
       skip = 0;
-      if (size > 0) { seedA[nS] = (u8)a; lo[nS] = l; hi[nS] = h; ++nS; }
+      if (size > 0) { seedA[nS] = (u16)a; lo[nS] = l; hi[nS] = h; ++nS; }
     }
     prev = code;
   }
@@ -81,8 +80,9 @@ T1K_HD int chain_span(const u32 *c, int n, int k, bool onRead) {
 }
 
 // GetOverlapsFromHits (filter = 0, reference sequences) on the hits of ONE (strand, sequence) bucket: the largest hit
-// length (= matchCnt / 2) over the overlaps it would emit, 0 if none.  h: n encoded hits (readOffset | seqOffset << 8) in
-// (readOffset, seqOffset) order, sorted in place by diagonal.  scratch: 12 * n + 512 bytes.
+// length (= matchCnt / 2) over the overlaps it would emit, 0 if none.  h: n encoded hits (hit_make(readOffset, seqOffset)) in
+// (readOffset, seqOffset) order, sorted in place by diagonal.  scratch: 12 * n + FILTER_USED_BYTES bytes.
+constexpr int FILTER_USED_BYTES = 2 * 1024;      // min |diagonal - dominant| per read offset (read offsets < 1024)
 T1K_HDN inline int bucket_best_hit_len(u32 *h, int n, int k, int hitLenReq, u8 *scratch) {
   if (n < 3) return 0;
   T1K_NOUNROLL
@@ -112,7 +112,7 @@ T1K_HDN inline int bucket_best_hit_len(u32 *h, int n, int k, int hitLenReq, u8 *
     if (m < 3 || m * k < hitLenReq) { s = e; continue; }
     // per read offset the hits closest to the dominant diagonal (SeqSet.hpp:1437-1456), in (seqOffset, readOffset) order
     u16 *used = (u16 *)scratch;
-    u32 *conc = (u32 *)(scratch + 512);
+    u32 *conc = (u32 *)(scratch + FILTER_USED_BYTES);
     u32 *chain = conc + m;
     u16 *top = (u16 *)(chain + m);
     u16 *link = top + m;

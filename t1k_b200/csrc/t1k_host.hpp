@@ -32,31 +32,73 @@ struct PackedRef {
   size_t totalWords = 0;
 };
 
+inline int code_of(char c);
+inline bool valid_base(char c);
 // postings (sorted by k-mer, allele, offset) -> tile entries sorted by (k-mer, tile, offset).  An allele's hits of one
 // k-mer stay in ascending offset order, which is the order GetHitsFromRead appends them in (SeqSet.hpp:1124-1150).
-inline void build_tile_index(PackedRef &P) {
-  const size_t nK = (size_t)1 << (2 * KMER);
-  P.kinfo.assign(nK + 1, KmerInfo{0, 0});
-  P.entries.clear();
+inline void build_tile_index(size_t nK, const std::vector<u32> &kstart, const std::vector<Posting> &post, std::vector<KmerInfo> &kinfo,
+                             std::vector<KmerEntry> &entries) {
+  kinfo.assign(nK + 1, KmerInfo{0, 0});
+  entries.clear();
   std::vector<std::pair<u32, u32> > cur;      // (offset, allele bit) of the tile being collected
   for (size_t c = 0; c < nK; ++c) {
-    P.kinfo[c].estart = (u32)P.entries.size(); P.kinfo[c].pstart = P.kstart[c];
-    const u32 lo = P.kstart[c], hi = P.kstart[c + 1];
+    kinfo[c].estart = (u32)entries.size(); kinfo[c].pstart = kstart[c];
+    const u32 lo = kstart[c], hi = kstart[c + 1];
     for (u32 j = lo; j < hi;) {
-      const u32 tile = P.post[j].idx >> 5;
+      const u32 tile = post[j].idx >> 5;
       cur.clear();
-      for (; j < hi && (P.post[j].idx >> 5) == tile; ++j) cur.push_back(std::make_pair(P.post[j].off, P.post[j].idx & 31u));
+      for (; j < hi && (post[j].idx >> 5) == tile; ++j) cur.push_back(std::make_pair(post[j].off, post[j].idx & 31u));
       std::stable_sort(cur.begin(), cur.end(), [](const std::pair<u32, u32> &x, const std::pair<u32, u32> &y) { return x.first < y.first; });
-      const size_t first = P.entries.size();
+      const size_t first = entries.size();
       for (size_t q = 0; q < cur.size(); ++q) {
-        if (q == 0 || cur[q].first != cur[q - 1].first) { KmerEntry e; e.tile = tile; e.off = cur[q].first; e.mask = 0; e.more = 0; P.entries.push_back(e); }
-        P.entries.back().mask |= 1u << cur[q].second;
+        if (q == 0 || cur[q].first != cur[q - 1].first) { KmerEntry e; e.tile = tile; e.off = cur[q].first; e.mask = 0; e.more = 0; entries.push_back(e); }
+        entries.back().mask |= 1u << cur[q].second;
       }
-      const size_t cnt = P.entries.size() - first;
-      for (size_t q = 0; q < cnt; ++q) P.entries[first + q].more = (u32)(cnt - 1 - q);
+      const size_t cnt = entries.size() - first;
+      for (size_t q = 0; q < cnt; ++q) entries[first + q].more = (u32)(cnt - 1 - q);
     }
   }
-  P.kinfo[nK].estart = (u32)P.entries.size(); P.kinfo[nK].pstart = P.kstart[nK];
+  kinfo[nK].estart = (u32)entries.size(); kinfo[nK].pstart = kstart[nK];
+}
+inline void build_tile_index(PackedRef &P) { build_tile_index((size_t)1 << (2 * KMER), P.kstart, P.post, P.kinfo, P.entries); }
+
+// Postings of a sequence set for a RUNTIME k-mer length (the candidate filter of fastq-extractor: k = max(9,
+// SeqSet::InferKmerLength), FastqExtractor.cpp:272,411-418), in KmerIndex::BuildIndexFromRead order incl. the i == kl quirk
+// (KmerIndex.hpp:107-130, Q1); then the tile form.  Returns false on a character outside ACGTN.
+inline bool build_filter_index(int32_t n, const char *bases, const int64_t *off, int k, std::vector<KmerInfo> &kinfo, std::vector<KmerEntry> &entries) {
+  const size_t nK = (size_t)1 << (2 * k);
+  std::vector<u32> cnt(nK + 1, 0), kstart;
+  std::vector<Posting> post;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int i = 0; i < n; ++i) {
+      const char *s = bases + off[i];
+      const int len = (int)(off[i + 1] - off[i]);
+      if (len < k) continue;
+      u32 code = 0, prev = 0; int bad = -1;
+      const u32 mask = (u32)(nK - 1);
+      for (int j = 0; j < len; ++j) {
+        if (pass == 0 && !valid_base(s[j])) return false;
+        if (bad != -1) ++bad;
+        code = (code >> 2) | ((u32)code_of(s[j]) << (2 * (k - 1)));      // first base of the window in the low bits
+        if (s[j] == 'N') bad = 0;
+        if (bad >= k) bad = -1;
+        if (j < k - 1) continue;
+        code &= mask;
+        if (bad == -1 && (j == k || code != prev)) {
+          if (pass == 0) ++cnt[code + 1];
+          else { Posting p; p.idx = (u32)i; p.off = (u32)(j - k + 1); post[cnt[code]++] = p; }
+        }
+        prev = code;
+      }
+    }
+    if (pass == 0) {
+      for (size_t c = 0; c < nK; ++c) cnt[c + 1] += cnt[c];
+      kstart = cnt;
+      post.resize(cnt[nK]);
+    }
+  }
+  build_tile_index(nK, kstart, post, kinfo, entries);
+  return true;
 }
 
 inline void set2(std::vector<u64> &plane, u64 w0, int pos, u64 v) { plane[w0 + (pos >> 5)] |= v << ((pos & 31) * 2); }

@@ -1,4 +1,4 @@
-// TEST HARNESS ONLY.  Runs the draft lane code of the candidate filter (t1k_b200/csrc/t1k_filter_lane.cuh)
+// TEST HARNESS ONLY.  Runs the lane code of the candidate filter (t1k_b200/csrc/t1k_filter_lane.cuh)
 // sequentially on the CPU: index build with a runtime k (KmerIndex::BuildIndexFromRead order and quirk), seeds of both
 // strands, per-(strand, sequence) buckets, the best bucket, its chaining, the verdict.  The orchestration the future
 // kernel will do warp-wide is plain loops here.
@@ -57,12 +57,12 @@ FEmu *femu_create(int32_t n, const char *bases, const int64_t *off, int32_t k, i
 }
 void femu_destroy(FEmu *E) { delete E; }
 
-// IsGoodCandidate (FastqExtractor.cpp:114-119); -1: read not usable by the packed path (invalid character, > 255 bases)
+// IsGoodCandidate (FastqExtractor.cpp:114-119); -1: read not usable by the packed path (invalid character, > 1000 bases)
 int32_t femu_good_candidate(FEmu *E, const char *read) {
   const int len = (int)strlen(read);
-  if (len > 255) return -1;
-  u64 fs[RWORDS], fn[RWORDS], rs[RWORDS], rn[RWORDS];
-  if (!pack_read(read, len, fs, fn, rs, rn)) return -1;
+  if (len > MAX_READ_LEN) return -1;
+  u64 fs[MAX_RWORDS], fn[MAX_RWORDS], rs[MAX_RWORDS], rn[MAX_RWORDS];
+  if (!pack_read(read, len, fs, fn, rs, rn, MAX_RWORDS)) return -1;
   if (filt::read_low_complexity(fs, fn, len)) return 0;
   if (len < E->k) return 0;
   filt::IndexView I;
@@ -70,18 +70,18 @@ int32_t femu_good_candidate(FEmu *E, const char *read) {
   std::map<std::pair<int, u32>, std::vector<u32> > buckets;      // (tag: 0 = reverse strand first, sequence) -> hits in arrival order
   u32 prev = 0;
   for (int pass = 0; pass < 2; ++pass) {
-    u8 seedA[256]; u32 lo[256], hi[256];
+    u16 seedA[1024]; u32 lo[1024], hi[1024];
     const int nS = filt::seed_list(I, pass == 0 ? fs : rs, pass == 0 ? fn : rn, len, prev, seedA, lo, hi);
     for (int s = 0; s < nS; ++s)
       for (u32 j = lo[s]; j < hi[s]; ++j)
-        buckets[std::make_pair(pass == 0 ? 1 : 0, E->post[j].idx)].push_back((u32)seedA[s] | (E->post[j].off << 8));
+        buckets[std::make_pair(pass == 0 ? 1 : 0, E->post[j].idx)].push_back(hit_make((int)seedA[s], E->post[j].off));
   }
   int mx = -1;
   std::vector<u32> *best = NULL;
   for (std::map<std::pair<int, u32>, std::vector<u32> >::iterator it = buckets.begin(); it != buckets.end(); ++it)
     if ((int)it->second.size() > mx) { mx = (int)it->second.size(); best = &it->second; }
   if (!best || E->k * mx < E->hitLenReq) return 0;
-  std::vector<u8> scratch((size_t)12 * best->size() + 512);
+  std::vector<u8> scratch((size_t)12 * best->size() + filt::FILTER_USED_BYTES);
   const int bestLen = filt::bucket_best_hit_len(best->data(), (int)best->size(), E->k, E->hitLenReq, scratch.data());
   return filt::hit_length_passes(len, bestLen, E->k, E->sim) ? 1 : 0;
 }

@@ -103,3 +103,33 @@ def test_draft_lane_code_of_the_filter_matches_reference_binary(femu, name):
         got[i] = g
     femu.femu_destroy(E)
     assert np.array_equal(got, z["kept"]), np.flatnonzero(got != z["kept"])[:10]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_device_filter_matches_reference_binary(name):
+    """k_filter through the C ABI (t1k_filter_batch) keeps exactly the pairs the unmodified fastq-extractor keeps."""
+    from t1k_b200.extractor import CandidateFilter
+    z = np.load(os.path.join(FILTER_DIR, name + ".npz"))
+    if name.startswith("recipe_"):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("make_golden_filter", os.path.join(G.GOLDEN, "make_golden_filter.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        recs = mod.big_ref()
+    else:
+        recs = G.parse_fasta_bytes(z["fasta"].tobytes())
+    paired = bool(int(z["paired"]))
+    r1 = [bytes(x) for x in z["reads1"]]
+    r2 = [bytes(x) for x in z["reads2"]] if paired else None
+    f = CandidateFilter(recs, r1, paired, float(z["similarity"]))
+    orc = O.CandidateFilter(recs, r1, paired, float(z["similarity"]))
+    assert (f.k, f.hit_len) == (orc.k, orc.hit_len)
+    got = f.keep_pairs(r1, r2)
+    assert np.array_equal(got, z["kept"]), np.flatnonzero(got != z["kept"])[:10]
+    # per read against the oracle (both mates, incl. the reads of kept pairs the pair rule never looks at)
+    reads = r1 + (r2 or [])
+    g, st = f.IsGoodCandidate(reads, with_stats=True)
+    want = np.asarray([orc.good(r) for r in reads], dtype=np.uint8)
+    assert np.array_equal(g, want), np.flatnonzero(g != want)[:10]
+    assert st["windows"] > 0 and st["kmer_length"] == f.k
