@@ -155,6 +155,10 @@ typedef struct {
    * partitions, all-gather of the merged partitions) and the sharded EM.  Per-allele outputs are identical on all ranks;
    * fragment_assigned / n_unique_ends / n_overlaps / timings are this rank's.  NULL = single GPU. */
   T1KComm *comm;
+  /* optional: the coalesced read groups (Genotyper::readAssignments after CoalesceReadAssignments) as a T1KGroups handle for
+   * t1k_groups_fetch / t1k_groups_destroy — what a driver needs to continue with the reference's own
+   * FinalizeReadAssignments / allele selection.  NULL = not wanted. */
+  T1KGroups **groups_out;
 } T1KGenotypeParams;
 
 typedef struct {
@@ -175,6 +179,8 @@ typedef struct {
   uint64_t n_pair_records;                                  /* overlap records of both mates summed over the fragments (k_pair roofline) */
   uint64_t em_nnz;                                          /* non-zeros of the read-group x EC matrix */
   int32_t em_updates;                                       /* EMupdate calls (3 per SQUAREM iteration) */
+  double *ec_read_count;                                    /* optional, caller-allocated [n_alleles]: ecReadCount of EC e at [e] (the argument
+                                                               of Genotyper::SetAlleleAbundance, Genotyper.hpp:957) */
 } T1KGenotypeResult;
 
 int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t stride, uint32_t n_frag,

@@ -197,12 +197,72 @@ int main(int argc, char *argv[]) {
   T1KRef *ref = NULL;
   T1K_CALL(t1k_ref_create(&desc, &ref));
 
+  int alignedFragmentCnt = 0;
+  bool emDone = false;
+  int emIterCntLib = 0;
+  std::vector<double> libRc;
+  std::vector<int32_t> libEc;
+  const bool pipelined = !outputReadAssignment && getenv("T1K_DROPIN_SYNC") == NULL;
+  const double tHot0 = (double)clock() / CLOCKS_PER_SEC;
+  struct timespec tw0; clock_gettime(CLOCK_MONOTONIC, &tw0);
+  if (pipelined) {
+    // ---- PHASE A + B + coalescing in ONE call: t1k_genotype runs the chunk pipeline (host de-duplication | device alignment +
+    // pairing | host coalescing overlapped) and hands back the coalesced read groups = Genotyper::readAssignments.  The
+    // per-fragment rows never leave the library, so this path is taken when --outputReadAssignment does not ask for them.
+    const uint32_t stride = (uint32_t)maxReadLength + 1;
+    std::vector<char> buf1((size_t)readCnt * stride, 0), buf2(hasMate ? (size_t)readCnt * stride : 0, 0);
+    for (int i = 0; i < readCnt; ++i) {
+      strcpy(&buf1[(size_t)i * stride], reads1[i].seq);
+      if (hasMate) strcpy(&buf2[(size_t)i * stride], reads2[i].seq);
+    }
+    std::vector<int32_t> seqWeight(alleleCnt), effLen(alleleCnt), alleleMajor(alleleCnt), alleleGene(alleleCnt);
+    for (int i = 0; i < alleleCnt; ++i) {
+      seqWeight[i] = refSet.GetSeqWeight(i); effLen[i] = refSet.GetSeqEffectiveLen(i);
+      alleleMajor[i] = genotyper.alleleInfo[i].majorAlleleIdx; alleleGene[i] = genotyper.alleleInfo[i].geneIdx;
+    }
+    T1KGroups *grp = NULL;
+    T1KGenotypeParams prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.max_assign = maxAssignCnt; prm.min_squarem_alpha = minSquaremAlpha; prm.filter_frac = filterFrac;
+    prm.seq_weight = seqWeight.data(); prm.effective_len = effLen.data();
+    prm.allele_major = alleleMajor.data(); prm.allele_gene = alleleGene.data();
+    prm.n_major = genotyper.majorAlleleCnt; prm.n_gene = genotyper.geneCnt;
+    prm.em_fast_sums = 0; prm.comm = NULL; prm.groups_out = &grp;
+    std::vector<double> abundance(alleleCnt), ecAbundance(alleleCnt);
+    std::vector<int32_t> missing(alleleCnt);
+    std::vector<uint8_t> fragAssigned(readCnt > 0 ? readCnt : 1, 0);
+    libRc.assign(alleleCnt, 0.0); libEc.assign(alleleCnt, -1);
+    T1KGenotypeResult res;
+    memset(&res, 0, sizeof(res));
+    res.abundance = abundance.data(); res.ec_abundance = ecAbundance.data(); res.equivalent_class = libEc.data();
+    res.missing_coverage = missing.data(); res.fragment_assigned = fragAssigned.data(); res.ec_read_count = libRc.data();
+    T1K_CALL(t1k_genotype(ref, buf1.data(), hasMate ? buf2.data() : NULL, stride, (uint32_t)readCnt, &prm, &res));
+    int32_t nG = 0; uint64_t nE = 0, nAssigned = 0;
+    T1K_CALL(t1k_groups_fetch(grp, &nG, &nE, &nAssigned, NULL, NULL));
+    std::vector<int64_t> gptr((size_t)nG + 1);
+    std::vector<T1KReadAssignment> gent(nE > 0 ? nE : 1);
+    T1K_CALL(t1k_groups_fetch(grp, &nG, &nE, &nAssigned, gptr.data(), gent.data()));
+    t1k_groups_destroy(grp);
+    static_assert(sizeof(struct _readAssignment) == sizeof(T1KReadAssignment), "T1KReadAssignment mirrors _readAssignment");
+    genotyper.readAssignments.resize(nG);
+    for (int g = 0; g < nG; ++g) {
+      std::vector<struct _readAssignment> &dst = genotyper.readAssignments[g];
+      dst.resize((size_t)(gptr[g + 1] - gptr[g]));
+      if (!dst.empty()) memcpy(&dst[0], &gent[gptr[g]], dst.size() * sizeof(T1KReadAssignment));
+    }
+    genotyper.readCnt = nG;
+    for (int i = 0; i < readCnt; ++i) reads1[i].fragmentAssigned = fragAssigned[i] != 0;
+    alignedFragmentCnt = (int)nAssigned;
+    emDone = true; emIterCntLib = res.em_iterations;
+    if (getenv("T1K_TIMING"))
+      fprintf(stderr, "[t1k drop-in] t1k_genotype: dedup %.0f ms (waited %.0f), align %.0f, pair %.0f, coalesce %.0f, em %.0f\n", res.ms_dedup, res.ms_prep_wait,
+              res.ms_align, res.ms_pair, res.ms_coalesce, res.ms_em);
+  }
   // ---- PHASE A + B in fragment chunks; coalescing stays the reference's (serial, order-sensitive)
   FILE *fpAssign = NULL;
   if (outputReadAssignment) { snprintf(buffer, sizeof(buffer), "%s_assign.tsv", outputPrefix); fpAssign = fopen(buffer, "w"); }
   const int coalesceSize = 500000;          // Genotyper.cpp:523
   const int chunk = 250000;                 // device batch (two per coalescing block)
-  int alignedFragmentCnt = 0;
   std::unordered_map<std::string, uint32_t> uniq;
   std::vector<const char *> uniqSeq;
   std::vector<int32_t> weight;
@@ -210,7 +270,7 @@ int main(int argc, char *argv[]) {
   std::vector<uint64_t> off;
   std::vector<uint8_t> hasN, assigned;
   std::string bases;
-  for (int start = 0; start < readCnt; start += coalesceSize) {
+  for (int start = 0; start < readCnt && !pipelined; start += coalesceSize) {
     const int end = std::min(start + coalesceSize, readCnt);       // [start, end)
     for (int c0 = start; c0 < end; c0 += chunk) {
       const int c1 = std::min(c0 + chunk, end), m = c1 - c0;
@@ -273,8 +333,33 @@ int main(int argc, char *argv[]) {
            genotyper.GetAverageReadAssignmentCnt());
 
   // ---- PHASE C
+  bool sameEc = emDone;
+  for (int i = 0; i < alleleCnt && sameEc; ++i) sameEc = libEc[i] == genotyper.alleleInfo[i].equivalentClass;
+  if (getenv("T1K_TIMING")) {
+    struct timespec tw1; clock_gettime(CLOCK_MONOTONIC, &tw1);
+    fprintf(stderr, "[t1k drop-in] hot path + FinalizeReadAssignments: %.0f ms wall (%s path)\n",
+            (tw1.tv_sec - tw0.tv_sec) * 1e3 + (tw1.tv_nsec - tw0.tv_nsec) / 1e6, pipelined ? "pipelined" : "synchronous");
+    (void)tHot0;
+  }
   if (fpAbundance) genotyper.InitAlleleAbundance(fpAbundance);
-  else {
+  else if (sameEc) {
+    // the library's EM already ran inside t1k_genotype on the very equivalence classes the reference's FinalizeReadAssignments
+    // has just rebuilt (same members, same numbering): its ecReadCount goes straight into the reference's SetAlleleAbundance
+    const int E = (int)genotyper.equivalentClassToAlleles.size();
+    struct _ecInfo *ecInfo = new struct _ecInfo[E > 0 ? E : 1];
+    for (int e = 0; e < E; ++e) {
+      const std::vector<int> &members = genotyper.equivalentClassToAlleles[e];
+      int length = refSet.GetSeqEffectiveLen(members[0]), missing = genotyper.alleleInfo[members[0]].missingCoverage;
+      for (size_t j = 0; j < members.size(); ++j) {
+        length = std::min(length, refSet.GetSeqEffectiveLen(members[j]));
+        missing = std::min(missing, genotyper.alleleInfo[members[j]].missingCoverage);
+      }
+      ecInfo[e].length = length; ecInfo[e].missingCoverage = missing;
+    }
+    genotyper.SetAlleleAbundance(libRc.data(), ecInfo);           // Genotyper.hpp:1316
+    delete[] ecInfo;
+    PrintLog("Finish allele quantification in %d EM iterations.", emIterCntLib);
+  } else {
     // inputs exactly as QuantifyAlleleEquivalentClass assembles them (Genotyper.hpp:1155-1232)
     const int G = genotyper.readCnt, E = (int)genotyper.equivalentClassToAlleles.size();
     std::vector<int64_t> rowPtr(1, 0);

@@ -54,7 +54,7 @@ class GenotypeParams(C.Structure):
     _fields_ = [("max_assign", C.c_int32), ("min_squarem_alpha", C.c_double), ("filter_frac", C.c_double),
                 ("seq_weight", C.c_void_p), ("effective_len", C.c_void_p), ("allele_major", C.c_void_p),
                 ("allele_gene", C.c_void_p), ("n_major", C.c_int32), ("n_gene", C.c_int32), ("em_fast_sums", C.c_int32),
-                ("comm", C.c_void_p)]
+                ("comm", C.c_void_p), ("groups_out", C.c_void_p)]
 
 
 class GenotypeResult(C.Structure):
@@ -67,7 +67,7 @@ class GenotypeResult(C.Structure):
                 ("ms_align_kernel", C.c_float), ("ms_pair_kernel", C.c_float), ("ms_em_kernel", C.c_float),
                 ("n_postings", C.c_uint64), ("n_candidates", C.c_uint64), ("n_launches", C.c_uint64),
                 ("ms_prep_wait", C.c_float), ("ms_exchange", C.c_float), ("n_pair_records", C.c_uint64), ("em_nnz", C.c_uint64),
-                ("em_updates", C.c_int32)]
+                ("em_updates", C.c_int32), ("ec_read_count", C.c_void_p)]
 
 
 class FilterDesc(C.Structure):

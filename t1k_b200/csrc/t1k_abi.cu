@@ -1380,8 +1380,15 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     res->em_nnz = (uint64_t)in.col.size(); res->em_updates = 3 * er.iterations;
     if (res->abundance && res->ec_abundance)
       set_allele_abundance(rc.data(), in.ecLen.data(), EC.ecPtr.data(), EC.ecAlleles.data(), EC.size(), nA, res->abundance, res->ec_abundance);
+    if (res->ec_read_count) memcpy(res->ec_read_count, rc.data(), (size_t)EC.size() * 8);
   }
   res->ms_em = (float)(now_ms() - te);
+  if (prm->groups_out) {
+    T1KGroups *g = new T1KGroups;
+    g->G.ptr.swap(groups.ptr); g->G.ent.swap(groups.ent); g->G.first.swap(groups.first); g->G.hashes.swap(groups.hashes);
+    g->G.assignedFragments = groups.assignedFragments;
+    *prm->groups_out = g;
+  }
   return T1K_OK;
 }
 

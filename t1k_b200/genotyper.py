@@ -194,7 +194,7 @@ class Genotyper:
         prm = L.GenotypeParams(self.max_assign, self.min_squarem_alpha, self.filter_frac, L.ptr(ref.seq_weight),
                                L.ptr(ref.effective_len), L.ptr(ref.allele_major), L.ptr(ref.allele_gene),
                                len(ref.major_names), len(ref.gene_names), int(bool(self.em_fast_sums)),
-                               comm.h if comm is not None else None)
+                               comm.h if comm is not None else None, None)
         out = dict(abundance=np.zeros(ref.n), ec_abundance=np.zeros(ref.n),
                    equivalent_class=np.zeros(ref.n, dtype=np.int32), missing_coverage=np.zeros(ref.n, dtype=np.int32),
                    fragment_assigned=np.zeros(n, dtype=np.uint8))

@@ -25,13 +25,27 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("name", sorted(CASES))
-def test_outputs_identical_to_reference_binary(name):
+def _hla_scale():
+    """the bench configuration itself: 30,000 HLA-RNA-like alleles, 2,000 x 150 bp pairs, -s 0.97"""
+    import bench
+    recs, ref, r1, r2 = bench.make_workload(2000, 4711)
+    return recs, r1, r2
+
+
+@pytest.mark.parametrize("with_assign", [True, False], ids=["synchronous+assign_tsv", "pipelined"])
+@pytest.mark.parametrize("name", sorted(CASES) + ["hla_scale_2000"])
+def test_outputs_identical_to_reference_binary(name, with_assign):
+    """with --outputReadAssignment the driver takes the synchronous entry points (t1k_assign_batch / t1k_pair_batch, rows in the
+    reference's order, the reference's own CoalesceReadAssignments); without it the pipelined t1k_genotype call."""
     if not (os.path.exists(OURS) and os.path.exists(REF)):
         pytest.skip("integration driver / reference binary not built (needs the T1K checkout at build time)")
-    factory, flags, kw, single = CASES[name]
-    recs = factory()
-    r1, r2 = W.reads_for(recs, 500, seed=75, **kw)
+    if name == "hla_scale_2000":
+        recs, r1, r2 = _hla_scale()
+        flags, single = ["-s", "0.97"], False
+    else:
+        factory, flags, kw, single = CASES[name]
+        recs = factory()
+        r1, r2 = W.reads_for(recs, 500, seed=75, **kw)
     td = tempfile.mkdtemp(prefix="t1kdrop_")
     fa = os.path.join(td, "ref.fa")
     synth.write_fasta(fa, recs)
@@ -42,11 +56,13 @@ def test_outputs_identical_to_reference_binary(name):
     outs = {}
     for tag, exe in (("ref", REF), ("ours", OURS)):
         prefix = os.path.join(td, tag)
-        cmd = [exe, "-f", fa] + (["-u", p1] if single else ["-1", p1, "-2", p2]) + ["-o", prefix, "-t", "2", "--outputReadAssignment"] + flags
+        cmd = [exe, "-f", fa] + (["-u", p1] if single else ["-1", p1, "-2", p2]) + ["-o", prefix, "-t", str(os.cpu_count() or 2)] + flags
+        if with_assign:
+            cmd.append("--outputReadAssignment")
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         assert res.returncode == 0, res.stderr[-2000:]
         outs[tag] = (prefix, res.stderr)
-    suffixes = ["_genotype.tsv", "_allele.tsv", "_assign.tsv"] + (["_aligned.fa"] if single else ["_aligned_1.fa", "_aligned_2.fa"])
+    suffixes = ["_genotype.tsv", "_allele.tsv"] + (["_assign.tsv"] if with_assign else []) + (["_aligned.fa"] if single else ["_aligned_1.fa", "_aligned_2.fa"])
     for sfx in suffixes:
         a, b = outs["ref"][0] + sfx, outs["ours"][0] + sfx
         assert os.path.exists(a) and os.path.exists(b), sfx
