@@ -331,6 +331,48 @@ def filter_stage(args, real_stdout):
     print(json.dumps(line), file=real_stdout, flush=True)
 
 
+def dropin_stage(args, real_stdout):
+    """The drop-in `genotyper` binary (integration/_build/genotyper_b200: the reference's driver with the hot path forwarded to the
+    C ABI) on FASTQ files of the config's workload: wall clock of its hot path (between the reference's own log points
+    "Start read assignment" and the EM) and of the whole process incl. FASTQ parsing and the reference's allele selection."""
+    import re
+    from t1k_b200 import synth
+    exe = os.path.join(ROOT, "integration", "_build", "genotyper_b200")
+    if not os.path.exists(exe):
+        print(json.dumps({"stage": "dropin", "unavailable": "integration/_build/genotyper_b200 was not built (needs the T1K checkout at build time)"}), file=real_stdout, flush=True)
+        return
+    cfg = CONFIGS[args.config]
+    n = args.pairs or cfg["pairs"]
+    recs, ref, r1, r2 = make_workload(n, seed=100, config=args.config)
+    td = tempfile.mkdtemp(prefix="t1kdropin_")
+    try:
+        fa = os.path.join(td, "ref.fa")
+        synth.write_fasta(fa, recs)
+        p1, p2 = os.path.join(td, "r_1.fq"), os.path.join(td, "r_2.fq")
+        synth.write_fastq(p1, r1)
+        if r2 is not None:
+            synth.write_fastq(p2, r2)
+        cmd = [exe, "-f", fa, "-s", str(cfg["sim"]), "-o", os.path.join(td, "out"), "-t", str(os.cpu_count() or 1)] + (["-u", p1] if r2 is None else ["-1", p1, "-2", p2])
+        if cfg["relax"]:
+            cmd.append("--relaxIntronAlign")
+        runs = []
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            res = subprocess.run(cmd, env=dict(os.environ, T1K_TIMING="1"), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, check=True)
+            wall = time.perf_counter() - t0
+            m = re.search(r"hot path \+ FinalizeReadAssignments: (\d+) ms wall \((\w+) path\)", res.stderr)
+            if it >= args.warmup:
+                runs.append((wall, float(m.group(1)) / 1e3 if m else None, m.group(2) if m else None))
+    finally:
+        shutil.rmtree(td, ignore_errors=True)
+    hot = float(np.mean([r[1] for r in runs if r[1] is not None])) if runs and runs[0][1] is not None else None
+    wall = float(np.mean([r[0] for r in runs]))
+    print(json.dumps({"stage": "dropin", "metric": cfg["metric"], "unit": UNIT, "value": n / hot if hot else None, "fragments": n, "path": runs[0][2],
+                      "hot_path_s": hot, "process_wall_s": wall, "process_fragments_per_s": n / wall,
+                      "config": {"workload": cfg["workload"], "what": "drop-in genotyper binary on FASTQ files: hot path = reads in RAM -> abundances set (t1k_genotype + the reference's "
+                                 "FinalizeReadAssignments); process wall adds reference loading, FASTQ parsing, allele selection and the writers"}}), file=real_stdout, flush=True)
+
+
 def _claim_stdout():
     """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON line on stdout.
     Everything else is sent to stderr; the returned file object is the real stdout for the JSON line."""
@@ -360,10 +402,14 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=0, help="fragments of the CPU reference sample (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the multi-GPU check against a one-GPU run of the union")
-    ap.add_argument("--stage", default="genotype", choices=["genotype", "filter"], help="filter: SURVEY 8f N1, the extractor's candidate filter")
+    ap.add_argument("--stage", default="genotype", choices=["genotype", "filter", "dropin"],
+                    help="filter: SURVEY 8f N1, the extractor's candidate filter; dropin: the drop-in genotyper binary on FASTQ files")
     args = ap.parse_args()
     if args.stage == "filter":
         filter_stage(args, real_stdout)
+        return
+    if args.stage == "dropin":
+        dropin_stage(args, real_stdout)
         return
     cfg = CONFIGS[args.config]
     if not args.pairs:

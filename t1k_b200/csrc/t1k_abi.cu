@@ -352,14 +352,14 @@ int setup_assign_launch(T1KRef *r, int maxLen) {
   if (arena < cap) return fail(T1K_ERR_UNSUPPORTED, "candidate pool: too many alleles for this launch geometry");
   r->arenaCands = arena;
   r->scratchWarps = warps;
-  r->dqCap = 16u << 20; r->aqCap = 32u << 20;      // 512 MB each; a full queue is not an error (the work is done in place)
+  r->dqCap = 48u << 20; r->aqCap = 48u << 20;      // 1.5 GB + 0.75 GB; a full queue is not an error (the work is done in place)
   if (const char *env = getenv("T1K_QUEUE_ITEMS")) r->dqCap = r->aqCap = (u32)std::max(0l, atol(env));
   CK(r->candPool.alloc(warps * arena * sizeof(Cand)));
   CK(r->laneScratch.alloc(warps * 32 * scr_bytes(scrLen)));
   CK(r->hitBuf.alloc(warps * (size_t)hitCap * 32 * sizeof(u32)));
   CK(r->dq.alloc(std::max<size_t>(1, r->dqCap) * sizeof(DeferItem)));
   CK(r->aq.alloc(std::max<size_t>(1, r->aqCap) * sizeof(AlignItem)));
-  CK(r->qCtr.alloc(2 * sizeof(unsigned int)));
+  CK(r->qCtr.alloc(4 * sizeof(unsigned int)));
   CK(r->workCtr.alloc(sizeof(unsigned int)));
   CK(r->errFlag.alloc(sizeof(int)));
   CK(r->stats.alloc(4 * sizeof(unsigned long long)));
@@ -440,6 +440,9 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   P.state = dState.as<ReadState>(); P.stabBuf = dStab.as<u32>();
   P.dq = ref->dq.as<DeferItem>(); P.dqCap = ref->dqCap; P.dqCtr = ref->qCtr.as<unsigned int>();
   P.aq = ref->aq.as<AlignItem>(); P.aqCap = ref->aqCap; P.aqCtr = ref->qCtr.as<unsigned int>() + 1;
+  // the DP queue of k_align reuses the DeferItem queue's storage: k_deferred is done with it by then
+  P.dpq = (AlignItem *)ref->dq.p; P.dpqCap = (u32)std::min<size_t>((size_t)ref->dqCap * sizeof(DeferItem) / sizeof(AlignItem), 0xffffffffu); P.dpqCtr = ref->qCtr.as<unsigned int>() + 2;
+  P.queueMargin = (u32)std::min<size_t>(ref->dqCap / 2, ref->scratchWarps * 2048);
   P.workBegin = 0; P.workEnd = 0;
   { const char *env = getenv("T1K_NO_FAST"); P.noFast = (env && atoi(env) != 0) ? 1 : 0; }
   P.workCtr = ref->workCtr.as<unsigned int>();
@@ -465,7 +468,7 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
     // rounds: k_seed takes read-ends until the warps' candidate arenas are full, then the other three kernels finish them
     const u32 nWork = P.Q.nWork;
     for (u32 done = 0; done < nWork;) {
-      CK(cudaMemsetAsync(ref->qCtr.p, 0, 2 * sizeof(unsigned int), st));
+      CK(cudaMemsetAsync(ref->qCtr.p, 0, 4 * sizeof(unsigned int), st));
       switch (ref->occ) {
         case 8: k_seed<8><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
         case 7: k_seed<7><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
@@ -488,7 +491,9 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
       CK(cudaGetLastError());
       k_align<<<ref->gridBlocks, WARPS_PER_BLOCK * 32, 0, st>>>(P);
       CK(cudaGetLastError());
-      a->launches += 4;
+      k_align_dp<<<ref->gridBlocks, WARPS_PER_BLOCK * 32, 0, st>>>(P);
+      CK(cudaGetLastError());
+      a->launches += 5;
       done = roundEnd;
     }
     CK(cudaEventRecord(ev1, st));

@@ -1477,8 +1477,10 @@ T1K_HDN T1K_NOINLINE inline bool extend_cand(const RefView &R, const ReadView &Q
 // Hot path (full_align): one pass over the window — mismatch count, exonic mismatch count and the first three mismatch
 // positions; <= 3 mismatches certify the diagonal and, without N columns, those positions are the uncredited columns.
 // Cold path (full_align_cold): 4+ mismatches (certificates, DP) and windows with N columns.
-T1K_HDN T1K_NOINLINE inline void full_align_cold(const RefView &R, const ReadView &Q, const AlleleView &T, Cand &c, int weight, int mm, int exMm,
-                                    const LaneScratch &S, int &err) {
+// allowDp = false: returns false (nothing written, no coverage added) when only the band DP can tell — the caller collects those
+// and runs them together (k_align_dp), instead of one lane of a warp running a 150-row DP while 31 wait.
+T1K_HDN T1K_NOINLINE inline bool full_align_cold(const RefView &R, const ReadView &Q, const AlleleView &T, Cand &c, int weight, int mm, int exMm,
+                                    const LaneScratch &S, int &err, bool allowDp = true) {
   const int tpos = c.eSeqStart, ppos = c.eReadStart;
   const int lent = c.eSeqEnd - c.eSeqStart + 1, lenp = c.eReadEnd - c.eReadStart + 1;
   int32_t *covDiff = R.covDiff + (size_t)R.covOff[c.seqIdx], *covPoint = R.covPoint + (size_t)R.covOff[c.seqIdx];
@@ -1504,13 +1506,14 @@ T1K_HDN T1K_NOINLINE inline void full_align_cold(const RefView &R, const ReadVie
         }
       }
       c.relaxed = R.relax ? 2 * (lent - exMm) : c.eMatchCnt;
-      return;
+      return true;
     }
     T1K_COUNT(8 + (mm >= 4 && mm <= 10 ? mm - 4 : 7), 1);
   }
+  if (!allowDp) return false;
   T1K_COUNT(7, 1);
   int n = dp_align(T, tpos, lent, Q, ppos, lenp, S, err);
-  if (n < 0) { c.relaxed = c.eMatchCnt; return; }
+  if (n < 0) { c.relaxed = c.eMatchCnt; return true; }
   const u8 *ops = S.ops();
   int refPos = tpos, readPos = ppos, m = 0;
   T1K_NOUNROLL
@@ -1526,11 +1529,12 @@ T1K_HDN T1K_NOINLINE inline void full_align_cold(const RefView &R, const ReadVie
     if (op != 3) ++readPos;
   }
   c.relaxed = R.relax ? 2 * m : c.eMatchCnt;
+  return true;
 }
 
-// HOT: returns false (nothing written, no coverage added) when the window needs full_align_cold.
+// HOT: returns false (nothing written, no coverage added) when the window needs full_align_cold.  allowDp: see full_align_cold.
 template <bool HOT>
-T1K_HDN T1K_NOINLINE inline bool full_align(const RefView &R, const ReadView &Q, Cand &c, int weight, const LaneScratch &S, int &err) {
+T1K_HDN T1K_NOINLINE inline bool full_align(const RefView &R, const ReadView &Q, Cand &c, int weight, const LaneScratch &S, int &err, bool allowDp = true) {
   const AlleleView T = allele_view(R, c.seqIdx, Q);
   const int tpos = c.eSeqStart, ppos = c.eReadStart;
   const int lent = c.eSeqEnd - c.eSeqStart + 1, lenp = c.eReadEnd - c.eReadStart + 1;
@@ -1567,8 +1571,7 @@ T1K_HDN T1K_NOINLINE inline bool full_align(const RefView &R, const ReadView &Q,
     }
   }
   if (HOT) return false;
-  full_align_cold(R, Q, T, c, weight, mm, exMm, S, err);
-  return true;
+  return full_align_cold(R, Q, T, c, weight, mm, exMm, S, err, allowDp);
 }
 
 // post-extension denominators / keys

@@ -76,6 +76,7 @@ struct AssignParams {
   u32 *stabBuf;            // [reads][2 strands][256]: seed tables of the strands that deferred something (k_deferred reads them)
   DeferItem *dq; unsigned int *dqCtr; u32 dqCap;
   AlignItem *aq; unsigned int *aqCtr; u32 aqCap;
+  AlignItem *dpq; unsigned int *dpqCtr; u32 dpqCap;     // AlignItems whose alignment needs the band DP (k_align -> k_align_dp)
   u8 *laneScratch;         // per lane scr_bytes(Q.maxLen)
   u32 *hitBuf;             // per warp hitCap x 32: hit lists of the alleles of a tile that take the hit-list path (lane-interleaved)
   unsigned int *workCtr;   // next position of the work list (persists over the rounds of a batch)
@@ -83,6 +84,7 @@ struct AssignParams {
   int hitCap;              // hits per allele the hit-list path holds
   int seedCap;             // seeds per strand the shared-memory tables hold (>= longest read - k + 1, multiple of 32, >= 64)
   int noFast;              // 1: every allele goes through the hit-list path (A/B switch, T1K_NO_FAST)
+  u32 queueMargin;         // k_seed takes no new read-end once the DeferItem queue is this close to full
 };
 
 // warp reductions on the redux unit (one instruction per 32-bit reduction)
@@ -541,6 +543,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_seed(AssignParam
   u64 used = 0;
   // a warp takes read-ends while its arena of the candidate pool can hold the most a read-end may produce
   while (used + P.candCap <= P.arenaCands) {
+    // (soft limit: when the item queues are nearly full the round ends early rather than falling back to in-place evaluation)
+    if (*(volatile unsigned int *)P.dqCtr + P.queueMargin > P.dqCap) break;
     u32 w = 0;
     if (lane == 0) w = atomicAdd(P.workCtr, 1u);
     w = __shfl_sync(FULL, w, 0);
@@ -759,29 +763,60 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_passes(AssignParams P)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_align: thread per AlignItem
+// k_align: thread per AlignItem — mismatch count, certificates, coverage.  The few items only the band DP can decide are
+// compacted into a second queue and run by k_align_dp with every lane on a DP of its own.
+__device__ __forceinline__ void align_item(const AssignParams &P, const AlignItem &it, const LaneScratch &S, int &err, bool allowDp, bool &done) {
+  const RefView &R = P.R;
+  const ReadState *st = P.state + it.read;
+  const int best01 = (st->bestKey & 1) ? 0 : 1;
+  const int RW = P.Q.rwords;
+  const u64 *pl = P.Q.planes + ((size_t)it.read * 4 + (best01 ? 0 : 2)) * RW;
+  ReadView Q; Q.seq2 = pl; Q.n2 = pl + RW; Q.len = P.Q.len[it.read];
+  u64 nw = 0;
+  T1K_NOUNROLL
+  for (int k = 0; k < RW; ++k) nw |= pl[RW + k];
+  Q.anyN = nw != 0;
+  Cand c = P.candPool[st->candOff + it.cand];
+  done = full_align<false>(R, Q, c, P.Q.weight[it.read], S, err, allowDp);
+  if (done && it.recSlot != ~0ull) P.O.store[it.recSlot].mcx = rec_mcx(c.eMatchCnt, c.relaxed, c.strand01);
+}
+
 __global__ void __launch_bounds__(128) k_align(AssignParams P) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nThreads = (size_t)gridDim.x * blockDim.x;
   const u32 nItems = min(*P.aqCtr, P.aqCap);
   const LaneScratch S = lane_scratch(P.laneScratch + tid * scr_bytes(P.Q.maxLen), P.Q.maxLen);
-  const RefView &R = P.R;
+  const int lane = threadIdx.x & 31;
   int err = 0;
-  for (size_t i = tid; i < nItems; i += nThreads) {
-    const AlignItem it = P.aq[i];
-    if (it.read == 0xffffffffu) continue;
-    const ReadState *st = P.state + it.read;
-    const int best01 = (st->bestKey & 1) ? 0 : 1;
-    const int RW = P.Q.rwords;
-    const u64 *pl = P.Q.planes + ((size_t)it.read * 4 + (best01 ? 0 : 2)) * RW;
-    ReadView Q; Q.seq2 = pl; Q.n2 = pl + RW; Q.len = P.Q.len[it.read];
-    u64 nw = 0;
-    T1K_NOUNROLL
-    for (int k = 0; k < RW; ++k) nw |= pl[RW + k];
-    Q.anyN = nw != 0;
-    Cand c = P.candPool[st->candOff + it.cand];
-    full_align<false>(R, Q, c, P.Q.weight[it.read], S, err);
-    if (it.recSlot != ~0ull) P.O.store[it.recSlot].mcx = rec_mcx(c.eMatchCnt, c.relaxed, c.strand01);
+  const size_t nRound = ((size_t)nItems + nThreads - 1) / nThreads;
+  for (size_t rnd = 0; rnd < nRound; ++rnd) {
+    const size_t i = rnd * nThreads + tid;
+    bool needDp = false;
+    AlignItem it;
+    if (i < nItems) {
+      it = P.aq[i];
+      if (it.read != 0xffffffffu) { bool done = true; align_item(P, it, S, err, false, done); needDp = !done; }
+    }
+    const unsigned bal = __ballot_sync(FULL, needDp);
+    if (bal) {
+      unsigned int base = 0;
+      if (lane == 0) base = atomicAdd(P.dpqCtr, (unsigned int)__popc(bal));
+      base = __shfl_sync(FULL, base, 0);
+      if (needDp) {
+        const unsigned int at = base + __popc(bal & ((1u << lane) - 1));
+        if (at < P.dpqCap) P.dpq[at] = it;
+        else { bool done; align_item(P, it, S, err, true, done); }          // queue full: right here
+      }
+    }
   }
+  if (err) atomicOr(P.O.err, err);
+}
+
+__global__ void __launch_bounds__(128) k_align_dp(AssignParams P) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nThreads = (size_t)gridDim.x * blockDim.x;
+  const u32 nItems = min(*P.dpqCtr, P.dpqCap);
+  const LaneScratch S = lane_scratch(P.laneScratch + tid * scr_bytes(P.Q.maxLen), P.Q.maxLen);
+  int err = 0;
+  for (size_t i = tid; i < nItems; i += nThreads) { bool done; align_item(P, P.dpq[i], S, err, true, done); }
   if (err) atomicOr(P.O.err, err);
 }
 
