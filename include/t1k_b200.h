@@ -181,6 +181,8 @@ typedef struct {
   int32_t em_updates;                                       /* EMupdate calls (3 per SQUAREM iteration) */
   double *ec_read_count;                                    /* optional, caller-allocated [n_alleles]: ecReadCount of EC e at [e] (the argument
                                                                of Genotyper::SetAlleleAbundance, Genotyper.hpp:957) */
+  int32_t *ec_allele_ptr, *ec_alleles;                      /* optional, caller-allocated [n_alleles+1] / [n_alleles]: members of every EC in the
+                                                               order of Genotyper::equivalentClassToAlleles (Genotyper.hpp:1072-1139) */
 } T1KGenotypeResult;
 
 int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t stride, uint32_t n_frag,

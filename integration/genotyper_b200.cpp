@@ -201,7 +201,8 @@ int main(int argc, char *argv[]) {
   bool emDone = false;
   int emIterCntLib = 0;
   std::vector<double> libRc;
-  std::vector<int32_t> libEc;
+  std::vector<int32_t> libEc, libEcPtr, libEcAlleles, libMissing;
+  int libEcCnt = 0;
   const bool pipelined = !outputReadAssignment && getenv("T1K_DROPIN_SYNC") == NULL;
   const double tHot0 = (double)clock() / CLOCKS_PER_SEC;
   struct timespec tw0; clock_gettime(CLOCK_MONOTONIC, &tw0);
@@ -229,13 +230,14 @@ int main(int argc, char *argv[]) {
     prm.n_major = genotyper.majorAlleleCnt; prm.n_gene = genotyper.geneCnt;
     prm.em_fast_sums = 0; prm.comm = NULL; prm.groups_out = &grp;
     std::vector<double> abundance(alleleCnt), ecAbundance(alleleCnt);
-    std::vector<int32_t> missing(alleleCnt);
     std::vector<uint8_t> fragAssigned(readCnt > 0 ? readCnt : 1, 0);
     libRc.assign(alleleCnt, 0.0); libEc.assign(alleleCnt, -1);
+    libEcPtr.assign(alleleCnt + 1, 0); libEcAlleles.assign(alleleCnt > 0 ? alleleCnt : 1, 0); libMissing.assign(alleleCnt, 0);
     T1KGenotypeResult res;
     memset(&res, 0, sizeof(res));
     res.abundance = abundance.data(); res.ec_abundance = ecAbundance.data(); res.equivalent_class = libEc.data();
-    res.missing_coverage = missing.data(); res.fragment_assigned = fragAssigned.data(); res.ec_read_count = libRc.data();
+    res.missing_coverage = libMissing.data(); res.fragment_assigned = fragAssigned.data(); res.ec_read_count = libRc.data();
+    res.ec_allele_ptr = libEcPtr.data(); res.ec_alleles = libEcAlleles.data();
     T1K_CALL(t1k_genotype(ref, buf1.data(), hasMate ? buf2.data() : NULL, stride, (uint32_t)readCnt, &prm, &res));
     int32_t nG = 0; uint64_t nE = 0, nAssigned = 0;
     T1K_CALL(t1k_groups_fetch(grp, &nG, &nE, &nAssigned, NULL, NULL));
@@ -253,7 +255,7 @@ int main(int argc, char *argv[]) {
     genotyper.readCnt = nG;
     for (int i = 0; i < readCnt; ++i) reads1[i].fragmentAssigned = fragAssigned[i] != 0;
     alignedFragmentCnt = (int)nAssigned;
-    emDone = true; emIterCntLib = res.em_iterations;
+    emDone = true; emIterCntLib = res.em_iterations; libEcCnt = res.n_ec;
     if (getenv("T1K_TIMING"))
       fprintf(stderr, "[t1k drop-in] t1k_genotype: dedup %.0f ms (waited %.0f), align %.0f, pair %.0f, coalesce %.0f, em %.0f\n", res.ms_dedup, res.ms_prep_wait,
               res.ms_align, res.ms_pair, res.ms_coalesce, res.ms_em);
@@ -317,8 +319,20 @@ int main(int argc, char *argv[]) {
   PrintLog("Finish read end assignments.");
   if (fpAssign) fclose(fpAssign);
 
-  // ---- base coverage back into the reference's allele records, then its own FinalizeReadAssignments
-  {
+  // ---- FinalizeReadAssignments (Genotyper.hpp:912-939).  Pipelined path: the library has already built what it builds — the
+  // equivalence classes in the reference's own order and every allele's missing coverage — so the driver only fills the
+  // reference's structures (T1K_DROPIN_REF_FINALIZE=1 runs the reference's serial code instead: same result, seconds slower).
+  if (pipelined && getenv("T1K_DROPIN_REF_FINALIZE") == NULL) {
+    for (int g = 0; g < genotyper.readCnt; ++g) {
+      const std::vector<struct _readAssignment> &ra = genotyper.readAssignments[g];
+      for (size_t j = 0; j < ra.size(); ++j) { struct _pair np; np.a = g; np.b = (int)j; genotyper.readsInAllele[ra[j].alleleIdx].push_back(np); }
+    }
+    genotyper.equivalentClassToAlleles.clear();
+    for (int e = 0; e < libEcCnt; ++e)
+      genotyper.equivalentClassToAlleles.push_back(std::vector<int>(libEcAlleles.begin() + libEcPtr[e], libEcAlleles.begin() + libEcPtr[e + 1]));
+    for (int i = 0; i < alleleCnt; ++i) { genotyper.alleleInfo[i].equivalentClass = libEc[i]; genotyper.alleleInfo[i].missingCoverage = libMissing[i]; }
+    genotyper.RemoveLowMAPQAlleleInEquivalentClass();              // (end of BuildAlleleEquivalentClass, Genotyper.hpp:1136)
+  } else {
     std::vector<int32_t> cov(refBases.size());
     T1K_CALL(t1k_coverage_fetch(ref, cov.data()));
     for (int i = 0; i < alleleCnt; ++i) {
@@ -327,8 +341,8 @@ int main(int argc, char *argv[]) {
       for (int j = 0; j < n; ++j)
         if (s[j] != 'N') refSet.seqs[i].posWeight[j].count[(int)nucToNum[s[j] - 'A']] = cov[refOff[i] + j];
     }
+    genotyper.FinalizeReadAssignments();
   }
-  genotyper.FinalizeReadAssignments();
   PrintLog("Finish read fragment assignments. %d read fragments can be assigned (average %.2lf alleles/read).", alignedFragmentCnt,
            genotyper.GetAverageReadAssignmentCnt());
 

@@ -67,7 +67,8 @@ class GenotypeResult(C.Structure):
                 ("ms_align_kernel", C.c_float), ("ms_pair_kernel", C.c_float), ("ms_em_kernel", C.c_float),
                 ("n_postings", C.c_uint64), ("n_candidates", C.c_uint64), ("n_launches", C.c_uint64),
                 ("ms_prep_wait", C.c_float), ("ms_exchange", C.c_float), ("n_pair_records", C.c_uint64), ("em_nnz", C.c_uint64),
-                ("em_updates", C.c_int32), ("ec_read_count", C.c_void_p)]
+                ("em_updates", C.c_int32), ("ec_read_count", C.c_void_p),
+                ("ec_allele_ptr", C.c_void_p), ("ec_alleles", C.c_void_p)]
 
 
 class FilterDesc(C.Structure):

@@ -1354,6 +1354,10 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   if (res->missing_coverage) { if (int rc = t1k_missing_coverage(ref, res->missing_coverage)) return rc; }
   pt.lap("missing coverage");
   if (res->equivalent_class) memcpy(res->equivalent_class, EC.alleleEc.data(), (size_t)nA * 4);
+  if (res->ec_allele_ptr && res->ec_alleles) {
+    memcpy(res->ec_allele_ptr, EC.ecPtr.data(), EC.ecPtr.size() * 4);
+    if (!EC.ecAlleles.empty()) memcpy(res->ec_alleles, EC.ecAlleles.data(), EC.ecAlleles.size() * 4);
+  }
   res->ms_coalesce += (float)(now_ms() - tc);
   // ---- EM
   double te = now_ms();
