@@ -26,6 +26,7 @@ using namespace t1k;
 namespace {
 
 thread_local std::string g_err;
+thread_local bool g_emTrusted = false;
 
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
@@ -854,7 +855,8 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   const int G = p->n_groups, E = p->n_ec;
   const int64_t nnz = p->row_ptr[G];
   PhaseTimer pt;
-  for (int64_t k = 0; k < nnz; ++k) if (p->col[k] < 0 || p->col[k] >= E) return fail(T1K_ERR_ARG, "t1k_em_run: column index out of range");
+  if (!g_emTrusted)        // (t1k_genotype builds the matrix itself)
+    for (int64_t k = 0; k < nnz; ++k) if (p->col[k] < 0 || p->col[k] >= E) return fail(T1K_ERR_ARG, "t1k_em_run: column index out of range");
   // read-sharded E-step: this rank's contiguous row range [g0, g1)
   T1KComm *comm = (p->comm && p->comm->world > 1) ? p->comm : nullptr;
   int g0 = 0, g1 = G;
@@ -1270,7 +1272,7 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   if (coalThread.joinable()) coalThread.join();
   T1KComm *comm = (prm->comm && prm->comm->world > 1) ? prm->comm : nullptr;
   if (!comm && localRc) return localRc;
-  if (!localRc) {
+  if (!localRc && !comm) {          // (a read-sharded run sends the shards' groups straight to their owners)
     const double t = now_ms();
     shards.gather(groups);
     msCoalesce += now_ms() - t;
@@ -1283,14 +1285,19 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   // weights add as per-rank partial sums, as when the ranks' tables are merged one after the other), and the merged
   // partitions are all-gathered and interleaved by the fragment that created each group = the single-process order.
   uint64_t nAssignAll = res->n_assignments;
+  CompactGroups compactGroups;
+  bool useCompact = false;
   if (comm) {
     double tx = now_ms();
     const int W = comm->world, T = shards.threads();
     // status + sizes: {status, assignments, fragments, bytes for rank 0 .. W-1}
-    PartitionPlan plan;
-    if (!localRc) plan_partitions(groups, W, T, plan); else { plan.bytes.assign((size_t)W, 0); plan.groupsOf.assign((size_t)W, std::vector<int32_t>()); plan.total = 0; }
+    ShardPlan plan;
+    int64_t assignedLocal = 0;
+    for (int t = 0; t < shards.threads(); ++t) assignedLocal += shards.part[t].assignedFragments;
+    if (!localRc) plan_partitions(shards, W, T, plan);
+    else { plan.bytes.assign((size_t)W, 0); plan.groupsOf.assign((size_t)W, std::vector<std::pair<int32_t, int32_t> >()); plan.total = 0; }
     std::vector<uint64_t> mineW((size_t)W + 4, 0), allW;
-    mineW[0] = (uint64_t)localRc; mineW[1] = nAssignAll; mineW[2] = (uint64_t)n_frag; mineW[3] = (uint64_t)groups.assignedFragments;
+    mineW[0] = (uint64_t)localRc; mineW[1] = nAssignAll; mineW[2] = (uint64_t)n_frag; mineW[3] = (uint64_t)assignedLocal;
     for (int r = 0; r < W; ++r) mineW[4 + r] = (uint64_t)plan.bytes[r];
     if (int rc = allgather_u64(ref, comm, mineW.data(), W + 4, allW)) return rc;
     for (int r = 0; r < W; ++r)
@@ -1309,7 +1316,7 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
       bytesFrom[r] = w[4 + comm->rank];
     }
     CK(ref->pinSend.grow(std::max<size_t>(plan.total, 16), 0));
-    serialize_partitions(groups, plan, ref->pinSend.as<uint8_t>(), T);
+    serialize_partitions(shards, plan, ref->pinSend.as<uint8_t>(), T);
     std::vector<size_t> recvOff;
     if (int rc = alltoall_blobs(ref, comm, ref->pinSend.as<uint8_t>(), plan.bytes, bytesFrom, ref->pinRecv, recvOff)) return rc;
     std::vector<GroupBlobView> tables((size_t)W);
@@ -1318,10 +1325,13 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
       if (!tables[r].parse(ref->pinRecv.as<uint8_t>() + recvOff[r], bytesFrom[r])) mergeRc = 1;
     ReadGroups mine, merged;
     if (!mergeRc && !merge_tables_partition(tables, fragBase, comm->rank, W, T, mine)) mergeRc = 1;
-    // second exchange: status + the merged partitions
-    const size_t partBytes = mergeRc ? 0 : serialized_group_bytes(mine);
+    // second exchange: status + the merged partitions.  The global tail (equivalence classes, EM inputs) reads only the allele ids
+    // and the count of every group, so the partitions travel in compact form (4 bytes per entry instead of 24) unless the caller
+    // wants the whole table back (groups_out).
+    const bool compact = prm->groups_out == nullptr;
+    const size_t partBytes = mergeRc ? 0 : (compact ? compact_group_bytes(mine) : serialized_group_bytes(mine));
     CK(ref->pinSend.grow(std::max<size_t>(partBytes, 16), 0));         // (the first exchange's send buffer is no longer needed)
-    if (!mergeRc) serialize_groups(mine, ref->pinSend.as<uint8_t>());
+    if (!mergeRc) { if (compact) serialize_compact(mine, ref->pinSend.as<uint8_t>(), T); else serialize_groups(mine, ref->pinSend.as<uint8_t>()); }
     const uint64_t st2 = (uint64_t)mergeRc;
     std::vector<uint64_t> allSt;
     if (int rc = allgather_u64(ref, comm, &st2, 1, allSt)) return rc;
@@ -1329,28 +1339,37 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     uint64_t stride2 = 0;
     std::vector<uint64_t> sizes2;
     if (int rc = allgather_blobs(ref, comm, ref->pinSend.as<uint8_t>(), partBytes, ref->pinRecv2, stride2, sizes2)) return rc;
-    std::vector<GroupBlobView> parts((size_t)W);
-    for (int r = 0; r < W; ++r)
-      if (!parts[r].parse(ref->pinRecv2.as<uint8_t>() + (size_t)r * stride2, sizes2[r])) return fail(T1K_ERR_NCCL, "malformed merged partition from a peer");
-    if (!assemble_partitions(parts, T, merged)) return fail(T1K_ERR_NCCL, "malformed merged partition from a peer");
-    merged.assignedFragments = assignedAll;
-    groups.ptr.swap(merged.ptr); groups.ent.swap(merged.ent); groups.byHash.swap(merged.byHash);
-    groups.first.swap(merged.first); groups.hashes.swap(merged.hashes);
-    groups.assignedFragments = merged.assignedFragments;
+    if (compact) {
+      std::vector<const uint8_t *> blobs((size_t)W);
+      for (int r = 0; r < W; ++r) blobs[r] = ref->pinRecv2.as<uint8_t>() + (size_t)r * stride2;
+      if (!assemble_compact(blobs, sizes2, T, compactGroups)) return fail(T1K_ERR_NCCL, "malformed merged partition from a peer");
+      useCompact = true;
+      groups.assignedFragments = assignedAll;
+    } else {
+      std::vector<GroupBlobView> parts((size_t)W);
+      for (int r = 0; r < W; ++r)
+        if (!parts[r].parse(ref->pinRecv2.as<uint8_t>() + (size_t)r * stride2, sizes2[r])) return fail(T1K_ERR_NCCL, "malformed merged partition from a peer");
+      if (!assemble_partitions(parts, T, merged)) return fail(T1K_ERR_NCCL, "malformed merged partition from a peer");
+      merged.assignedFragments = assignedAll;
+      groups.ptr.swap(merged.ptr); groups.ent.swap(merged.ent); groups.byHash.swap(merged.byHash);
+      groups.first.swap(merged.first); groups.hashes.swap(merged.hashes);
+      groups.assignedFragments = merged.assignedFragments;
+    }
     res->ms_exchange = (float)(now_ms() - tx);
     res->ms_coalesce += res->ms_exchange;
   }
   res->assigned_fragments = (int32_t)groups.assignedFragments;
   // Genotyper::GetAverageReadAssignmentCnt (Genotyper.hpp:941-955) averages over the coalesced read groups
-  res->avg_alleles_per_read = groups.size() ? (double)groups.ent.size() / (double)groups.size() : 0.0;
+  const GroupsView GV = useCompact ? compactGroups.view() : view_of(groups);
+  res->avg_alleles_per_read = GV.n ? (double)GV.entries() / (double)GV.n : 0.0;
   res->n_assignments = nAssignAll;
   // ---- FinalizeReadAssignments: equivalence classes + missing coverage
   double tc = now_ms();
   PhaseTimer pt;
   EquivalenceClasses EC;
-  EC.build(groups, nA, shards.threads());
+  EC.build(GV, nA, shards.threads());
   pt.lap("equivalence classes");
-  res->n_groups = groups.size(); res->n_ec = EC.size(); res->n_alleles = nA;
+  res->n_groups = GV.n; res->n_ec = EC.size(); res->n_alleles = nA;
   if (res->missing_coverage) { if (int rc = t1k_missing_coverage(ref, res->missing_coverage)) return rc; }
   pt.lap("missing coverage");
   if (res->equivalent_class) memcpy(res->equivalent_class, EC.alleleEc.data(), (size_t)nA * 4);
@@ -1366,12 +1385,12 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   if (res->ec_abundance) memset(res->ec_abundance, 0, (size_t)nA * 8);
   if (EC.size() > 0) {
     EmInputs in;
-    in.build(groups, EC, prm->effective_len, prm->seq_weight, shards.threads());
+    in.build(GV, EC, prm->effective_len, prm->seq_weight, shards.threads());
     pt.lap("EM inputs");
-    if (pt.on) fprintf(stderr, "[t1k timing] groups %d entries %zu ECs %d nnz %zu\n", groups.size(), groups.ent.size(), EC.size(), in.col.size());
+    if (pt.on) fprintf(stderr, "[t1k timing] groups %d entries %lld ECs %d nnz %zu\n", GV.n, (long long)GV.entries(), EC.size(), in.col.size());
     T1KEmProblem ep;
     memset(&ep, 0, sizeof(ep));
-    ep.n_groups = groups.size(); ep.n_ec = EC.size();
+    ep.n_groups = GV.n; ep.n_ec = EC.size();
     ep.row_ptr = in.rowPtr.data(); ep.col = in.col.data(); ep.count = in.count.data(); ep.ec_len = in.ecLen.data(); ep.x0 = in.x0.data();
     ep.min_squarem_alpha = prm->min_squarem_alpha; ep.filter_frac = prm->filter_frac; ep.fast_sums = prm->em_fast_sums;
     ep.comm = comm;
@@ -1382,7 +1401,10 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     }
     std::vector<double> x(EC.size()), rc(EC.size());
     T1KEmResult er; er.x = x.data(); er.ec_read_count = rc.data(); er.iterations = 0;
-    if (int rcode = t1k_em_run(&ep, &er, ref->device)) return rcode;
+    g_emTrusted = true;
+    const int rcode = t1k_em_run(&ep, &er, ref->device);
+    g_emTrusted = false;
+    if (rcode) return rcode;
     pt.lap("t1k_em_run");
     res->em_iterations = er.iterations;
     res->ms_em_kernel = er.ms_kernel; res->n_launches += er.n_launches;

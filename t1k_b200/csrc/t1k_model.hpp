@@ -88,6 +88,26 @@ struct ReadGroups {
   }
 };
 
+// What the global tail (equivalence classes, EM inputs) reads of the group table: the allele ids of every group and the group's
+// count (largest summed weight, Genotyper.hpp:1159-1163).  Either a view of a full table, or the compact form the ranks of a
+// read-sharded run exchange (4 bytes per entry instead of 24).
+struct GroupsView {
+  int32_t n = 0;
+  const int64_t *ptr = nullptr;
+  const HostEntry *ent = nullptr;      // full table ...
+  const int32_t *allele = nullptr;     // ... or compact: allele ids
+  const double *count = nullptr;       //                  and counts
+  int64_t entries() const { return n > 0 ? ptr[n] : 0; }
+  int32_t allele_at(int64_t k) const { return ent ? ent[k].alleleIdx : allele[k]; }
+  double count_of(int32_t g) const {
+    if (!ent) return count[g];
+    float c = ent[ptr[g]].weight;
+    for (int64_t k = ptr[g] + 1; k < ptr[g + 1]; ++k) if (ent[k].weight > c) c = ent[k].weight;
+    return c;
+  }
+};
+inline GroupsView view_of(const ReadGroups &G) { GroupsView v; v.n = G.size(); v.ptr = G.ptr.data(); v.ent = G.ent.data(); return v; }
+
 // Coalescing on T host threads.  Thread t owns the read groups whose allele-set hash falls into partition t, so every
 // group still sees its fragments in fragment order (float32 sums unchanged) while the partitions proceed in parallel;
 // gather() interleaves the partitions by the fragment that created each group = the single-threaded group order.
@@ -246,6 +266,65 @@ inline void serialize_partitions(const ReadGroups &G, const PartitionPlan &pl, u
       int64_t run = 0;
       for (size_t k = 0; k < nG; ++k) {
         const int32_t g = ids[k];
+        const int64_t n = G.ptr[g + 1] - G.ptr[g];
+        ptr[k] = run; hs[k] = G.hashes[g]; fi[k] = G.first[g];
+        if (n) memcpy(en + run, G.ent.data() + G.ptr[g], (size_t)n * sizeof(HostEntry));
+        run += n;
+      }
+      ptr[nG] = run;
+    }
+  });
+}
+
+// The same split taken straight from the coalescing shards of this rank (no gathered table in between): the groups of a blob
+// need no particular order, the owner files them by hash and orders them by their creating fragment.
+struct ShardPlan {
+  std::vector<std::vector<std::pair<int32_t, int32_t> > > groupsOf;      // [world] (shard, group)
+  std::vector<size_t> bytes;
+  size_t total = 0;
+};
+inline void plan_partitions(const GroupShards &S, int world, int T, ShardPlan &pl) {
+  const uint64_t P = (uint64_t)world * (uint64_t)(T < 1 ? 1 : T);
+  pl.groupsOf.assign((size_t)world, std::vector<std::pair<int32_t, int32_t> >());
+  std::vector<size_t> nE((size_t)world, 0);
+  for (int t = 0; t < S.threads(); ++t) {
+    const ReadGroups &G = S.part[t];
+    for (int32_t g = 0; g < G.size(); ++g) {
+      const int owner = (int)(((G.hashes[g] >> 17) % P) / (uint64_t)(T < 1 ? 1 : T));
+      pl.groupsOf[owner].push_back(std::make_pair((int32_t)t, g));
+      nE[owner] += (size_t)(G.ptr[g + 1] - G.ptr[g]);
+    }
+  }
+  pl.bytes.assign((size_t)world, 0);
+  pl.total = 0;
+  for (int r = 0; r < world; ++r) {
+    const size_t nG = pl.groupsOf[r].size();
+    pl.bytes[r] = (4 * 8 + (nG + 1) * 8 + nG * 16 + nE[r] * sizeof(HostEntry) + 15) & ~(size_t)15;
+    pl.total += pl.bytes[r];
+  }
+}
+inline void serialize_partitions(const GroupShards &S, const ShardPlan &pl, uint8_t *out, int threads) {
+  const int world = (int)pl.groupsOf.size();
+  std::vector<size_t> at((size_t)world + 1, 0);
+  for (int r = 0; r < world; ++r) at[r + 1] = at[r] + pl.bytes[r];
+  const int nT = std::max(1, std::min(threads, world));
+  run_threads(nT, [&](int t) {
+    for (int r = t; r < world; r += nT) {
+      const std::vector<std::pair<int32_t, int32_t> > &ids = pl.groupsOf[r];
+      const size_t nG = ids.size();
+      uint8_t *p = out + at[r];
+      size_t nE = 0;
+      for (size_t k = 0; k < nG; ++k) { const ReadGroups &G = S.part[ids[k].first]; nE += (size_t)(G.ptr[ids[k].second + 1] - G.ptr[ids[k].second]); }
+      const uint64_t hdr[4] = {(uint64_t)nG, (uint64_t)nE, 0, 0};
+      memcpy(p, hdr, sizeof(hdr)); p += sizeof(hdr);
+      int64_t *ptr = (int64_t *)p; p += (nG + 1) * 8;
+      uint64_t *hs = (uint64_t *)p; p += nG * 8;
+      int64_t *fi = (int64_t *)p; p += nG * 8;
+      HostEntry *en = (HostEntry *)p;
+      int64_t run = 0;
+      for (size_t k = 0; k < nG; ++k) {
+        const ReadGroups &G = S.part[ids[k].first];
+        const int32_t g = ids[k].second;
         const int64_t n = G.ptr[g + 1] - G.ptr[g];
         ptr[k] = run; hs[k] = G.hashes[g]; fi[k] = G.first[g];
         if (n) memcpy(en + run, G.ent.data() + G.ptr[g], (size_t)n * sizeof(HostEntry));
@@ -431,6 +510,71 @@ inline bool assemble_partitions(const std::vector<GroupBlobView> &parts, int T, 
   return true;
 }
 
+// ---- compact form of a merged partition for the global tail of a read-sharded run: [nG, nE], ptr[nG+1], first[nG], count[nG]
+// (double), allele[nE] (int32)
+inline size_t compact_group_bytes(const ReadGroups &G) { return (2 * 8 + (size_t)(G.size() + 1) * 8 + (size_t)G.size() * 16 + G.ent.size() * 4 + 15) & ~(size_t)15; }
+inline void serialize_compact(const ReadGroups &G, uint8_t *p, int threads) {
+  const uint64_t hdr[2] = {(uint64_t)G.size(), (uint64_t)G.ent.size()};
+  memcpy(p, hdr, sizeof(hdr)); p += sizeof(hdr);
+  memcpy(p, G.ptr.data(), G.ptr.size() * 8); p += G.ptr.size() * 8;
+  const int32_t nG = G.size();
+  int64_t *first = (int64_t *)p; p += (size_t)nG * 8;
+  double *cnt = (double *)p; p += (size_t)nG * 8;
+  int32_t *al = (int32_t *)p;
+  const GroupsView V = view_of(G);
+  const int T = G.ent.size() < par_min_entries() ? 1 : std::max(1, threads);
+  const std::vector<int32_t> b = balanced_ranges(G.ptr.data(), nG, T);
+  run_threads(T, [&](int t) {
+    for (int32_t g = b[t]; g < b[t + 1]; ++g) {
+      first[g] = G.first[g]; cnt[g] = V.count_of(g);
+      for (int64_t k = G.ptr[g]; k < G.ptr[g + 1]; ++k) al[k] = G.ent[k].alleleIdx;
+    }
+  });
+}
+struct CompactGroups {
+  std::vector<int64_t> ptr{0};
+  std::vector<int32_t> allele;
+  std::vector<double> count;
+  GroupsView view() const { GroupsView v; v.n = (int32_t)ptr.size() - 1; v.ptr = ptr.data(); v.allele = allele.data(); v.count = count.data(); return v; }
+};
+// blobs[r] / bytes[r]: rank r's compact partition; out = all groups in first-appearance order
+inline bool assemble_compact(const std::vector<const uint8_t *> &blobs, const std::vector<uint64_t> &bytes, int T, CompactGroups &out) {
+  struct Ref { int64_t first; uint32_t r; uint32_t g; };
+  struct View { uint64_t nG, nE; const int64_t *ptr, *first; const double *cnt; const int32_t *al; };
+  std::vector<View> V(blobs.size());
+  std::vector<Ref> order;
+  for (size_t r = 0; r < blobs.size(); ++r) {
+    if (bytes[r] < 16) return false;
+    uint64_t hdr[2]; memcpy(hdr, blobs[r], 16);
+    View &v = V[r];
+    v.nG = hdr[0]; v.nE = hdr[1];
+    if (bytes[r] < 16 + (v.nG + 1) * 8 + v.nG * 16 + v.nE * 4) return false;
+    v.ptr = (const int64_t *)(blobs[r] + 16); v.first = v.ptr + v.nG + 1; v.cnt = (const double *)(v.first + v.nG); v.al = (const int32_t *)(v.cnt + v.nG);
+    for (uint64_t g = 0; g < v.nG; ++g) {
+      if (v.ptr[g] < 0 || v.ptr[g + 1] < v.ptr[g] || (uint64_t)v.ptr[g + 1] > v.nE) return false;
+      order.push_back(Ref{v.first[g], (uint32_t)r, (uint32_t)g});
+    }
+  }
+  std::sort(order.begin(), order.end(), [](const Ref &a, const Ref &b) { return a.first < b.first; });
+  const size_t nG = order.size();
+  out.ptr.assign(nG + 1, 0); out.count.resize(nG);
+  for (size_t k = 0; k < nG; ++k) {
+    const View &v = V[order[k].r];
+    out.ptr[k + 1] = out.ptr[k] + (v.ptr[order[k].g + 1] - v.ptr[order[k].g]);
+    out.count[k] = v.cnt[order[k].g];
+  }
+  out.allele.resize((size_t)out.ptr[nG]);
+  if (T < 1 || nG < 1024) T = 1;
+  run_threads(T, [&](int t) {
+    for (size_t k = nG * t / T; k < nG * (t + 1) / T; ++k) {
+      const View &v = V[order[k].r];
+      const int64_t b = v.ptr[order[k].g], e = v.ptr[order[k].g + 1];
+      if (e > b) memcpy(out.allele.data() + out.ptr[k], v.al + b, (size_t)(e - b) * 4);
+    }
+  });
+  return true;
+}
+
 // ---- unique read-ends of a chunk of fragments (the de-duplication of Genotyper.cpp:450-454: only the grouping matters)
 // in two fork-join phases: (1) length, N flag and hash of every read-end (reads split across the threads), (2) one
 // open-addressing table per hash partition (a thread owns a partition).  The unique index of a read-end = partition
@@ -521,17 +665,17 @@ inline void unique_read_ends(const char *reads1, const char *reads2, uint32_t st
 struct EquivalenceClasses {
   std::vector<int32_t> ecPtr{0}, ecAlleles, alleleEc;
 
-  void build(const ReadGroups &G, int32_t nAlleles, int threads = 1) {
-    const int32_t readCnt = G.size();
+  void build(const ReadGroups &G, int32_t nAlleles, int threads = 1) { build(view_of(G), nAlleles, threads); }
+  void build(const GroupsView &G, int32_t nAlleles, int threads = 1) {
+    const int32_t readCnt = G.n;
     // readsInAllele (Genotyper.hpp:912-939): the groups of every allele, ascending
     std::vector<int64_t> inPtr;
     std::vector<int32_t> in;
-    const HostEntry *ent = G.ent.data();
-    transpose_csr(G.ptr.data(), readCnt, [ent](int64_t k) { return ent[k].alleleIdx; }, nAlleles, threads, inPtr, in);
+    transpose_csr(G.ptr, readCnt, [&G](int64_t k) { return G.allele_at(k); }, nAlleles, threads, inPtr, in);
     struct FP { int32_t a, b; };
     std::vector<FP> fp(nAlleles);
     {
-      const int T = G.ent.size() < par_min_entries() ? 1 : std::max(1, threads);
+      const int T = (size_t)G.entries() < par_min_entries() ? 1 : std::max(1, threads);
       const std::vector<int32_t> ab = balanced_ranges(inPtr.data(), nAlleles, T);
       run_threads(T, [&](int t) {
         for (int32_t a = ab[t]; a < ab[t + 1]; ++a) {
@@ -579,22 +723,23 @@ struct EmInputs {
   std::vector<double> count, x0;
 
   void build(const ReadGroups &G, const EquivalenceClasses &EC, const int32_t *effectiveLen, const int32_t *seqWeight, int threads = 1) {
-    const int32_t n = G.size(), E = EC.size();
+    build(view_of(G), EC, effectiveLen, seqWeight, threads);
+  }
+  void build(const GroupsView &G, const EquivalenceClasses &EC, const int32_t *effectiveLen, const int32_t *seqWeight, int threads = 1) {
+    const int32_t n = G.n, E = EC.size();
     count.resize(n);
-    if (threads < 1 || G.ent.size() < par_min_entries()) threads = 1;
-    const std::vector<int32_t> b = balanced_ranges(G.ptr.data(), n, threads);
+    if (threads < 1 || (size_t)G.entries() < par_min_entries()) threads = 1;
+    const std::vector<int32_t> b = balanced_ranges(G.ptr, n, threads);
     std::vector<std::vector<int32_t> > cols((size_t)threads);
     std::vector<int64_t> rowLen((size_t)n, 0);
     run_threads(threads, [&](int t) {
       std::vector<int32_t> stamp(E, -1);
       std::vector<int32_t> &out = cols[t];
       for (int32_t g = b[t]; g < b[t + 1]; ++g) {
-        float c = G.ent[G.ptr[g]].weight;
-        for (int64_t k = G.ptr[g] + 1; k < G.ptr[g + 1]; ++k) if (G.ent[k].weight > c) c = G.ent[k].weight;
-        count[g] = c;
+        count[g] = G.count_of(g);
         const size_t before = out.size();
         for (int64_t k = G.ptr[g]; k < G.ptr[g + 1]; ++k) {
-          const int32_t e = EC.alleleEc[G.ent[k].alleleIdx];
+          const int32_t e = EC.alleleEc[G.allele_at(k)];
           if (stamp[e] != g) { stamp[e] = g; out.push_back(e); }
         }
         rowLen[g] = (int64_t)(out.size() - before);

@@ -1,15 +1,21 @@
-# One round of GPU evidence (run through gpurun): parity tests, smoke, the default bench line + reference arm, the DRAM-traffic
-# capture at the bench's launch size, the launch list, full ncu captures of k_assign / k_pair, host timing.  Outputs in gpurun_out/.
-# Summaries for profiles/: tools/ncu_summary.py, ncu_src.py, ncu_stalls.py, ncu_traffic.py.
+# One round of GPU evidence (run through gpurun): parity tests, smoke, the default bench line + reference arm, per-kernel DRAM
+# traffic at the bench's launch size, the launch list, full ncu captures of the AssignRead kernels / k_pair / EM, host timing, the
+# other configs and stages.  Outputs in gpurun_out/ (TAG = suffix).  Summaries for profiles/: tools/ncu_summary.py, ncu_src.py,
+# ncu_kernels.py, ncu_traffic.py.
+TAG=${1:-round}
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total --format=csv,noheader; nproc
-( time timeout 600 python -m pytest tests -m gpu -x -q ) 2>&1 | tail -5
+( time timeout 900 python -m pytest tests -m gpu -x -q ) 2>&1 | tail -5
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 600 python bench.py > gpurun_out/bench_round_default.json 2> gpurun_out/bench_round_default.err; tail -3 gpurun_out/bench_round_default.err; cat gpurun_out/bench_round_default.json
-timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_round_reference.json 2> gpurun_out/bench_round_reference.err; cat gpurun_out/bench_round_reference.json
-timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_assign -c 1 --csv --log-file gpurun_out/traffic_round.csv python bench.py --pairs 262144 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_traffic_round.log 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_round.csv python bench.py --pairs 200000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches_round.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_assign -c 1 -o gpurun_out/prof_assign_round -f python bench.py --pairs 50000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_round.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_pair -c 1 -o gpurun_out/prof_pair_round -f python bench.py --pairs 50000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_pair_round.log 2>&1
-T1K_TIMING=1 timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_round_timing.json 2> gpurun_out/bench_round_timing.err; grep "t1k timing" gpurun_out/bench_round_timing.err | grep -v "assign: \(launch\|input\|store\|tail\)" | tail -22
+timeout 900 python bench.py > gpurun_out/bench_${TAG}_default.json 2> gpurun_out/bench_${TAG}_default.err; tail -3 gpurun_out/bench_${TAG}_default.err; cat gpurun_out/bench_${TAG}_default.json
+timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_${TAG}_reference.json 2> gpurun_out/bench_${TAG}_reference.err; cat gpurun_out/bench_${TAG}_reference.json
+M="gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__thread_inst_executed_per_inst_executed.ratio,dram__bytes_read.sum,dram__bytes_write.sum"
+timeout 600 ncu --metrics $M --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --pairs 262144 --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_launches_${TAG}.log 2>&1
+for k in k_seed k_deferred k_passes k_align k_pair k_em_colsum k_em_rowsum; do
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -o gpurun_out/prof_${k}_${TAG} -f python bench.py --pairs 50000 --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_full_${k}_${TAG}.log 2>&1
+done
+T1K_TIMING=1 timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_${TAG}_timing.json 2> gpurun_out/bench_${TAG}_timing.err; grep "t1k timing" gpurun_out/bench_${TAG}_timing.err | grep -v "assign: \(launch\|input\|store\|tail\)" | tail -24
+for c in 3 4; do timeout 900 python bench.py --config $c --steps 2 --warmup 1 > gpurun_out/bench_${TAG}_config$c.json 2> gpurun_out/bench_${TAG}_config$c.err; cat gpurun_out/bench_${TAG}_config$c.json; done
+timeout 600 python bench.py --stage filter --steps 3 --warmup 1 > gpurun_out/bench_${TAG}_filter.json 2> gpurun_out/bench_${TAG}_filter.err; cat gpurun_out/bench_${TAG}_filter.json
+timeout 900 python bench.py --stage dropin --steps 1 --warmup 1 > gpurun_out/bench_${TAG}_dropin.json 2> gpurun_out/bench_${TAG}_dropin.err; cat gpurun_out/bench_${TAG}_dropin.json
