@@ -373,6 +373,82 @@ def dropin_stage(args, real_stdout):
                                  "FinalizeReadAssignments); process wall adds reference loading, FASTQ parsing, allele selection and the writers"}}), file=real_stdout, flush=True)
 
 
+def alninfo_stage(args, real_stdout):
+    """the analyzer's edit-string pass (k_align_info through t1k_align_info_batch) over the AssignRead records of
+    config-2 read-ends, and §8d's band-DP roofline: the same items with the certified-diagonal shortcut off, band cells/s and
+    DPX operations/s (two max(a+b,c) + one three-way max per cell) against the device's measured DPX issue rate."""
+    import ctypes as C
+    import torch
+    from t1k_b200 import _lib as L
+    from t1k_b200.genotyper import SeqSet
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    n = args.pairs or 600
+    cfg = CONFIGS[2]
+    recs, ref, r1, r2 = make_workload(n, seed=100, config=2)
+    reads = sorted(set(r.tobytes() for r in r1) | set(r.tobytes() for r in r2))
+    ss = SeqSet(ref, cfg["sim"], cfg["relax"])
+    a = ss.AssignRead(reads, np.zeros(len(reads), dtype=np.int32))
+    row, ret, rec = a.fetch()
+    idx = np.repeat(np.arange(len(reads), dtype=np.uint32), np.diff(row).astype(np.int64))
+    del a
+    gops = C.c_double(0)
+    L.check(L.lib().t1k_dpx_peak(-1, C.byref(gops)))
+
+    def run(force_dp):
+        ms, wall, st = 0.0, 0.0, None
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            _, st = ss.AddOverlapAlignmentInfo(reads, idx, rec, force_dp=force_dp, with_stats=True, raw=True)
+            if it >= args.warmup:
+                ms += st["ms_kernel"]
+                wall += time.perf_counter() - t0
+        return ms / args.steps, wall / args.steps, st
+
+    ms, wall, st = run(False)
+    ms_dp, _, st_dp = run(True)
+    peak, peak_src = measured_peaks()
+    out_bytes = int((rec["seqEnd"] - rec["seqStart"] + 1 + rec["readEnd"] - rec["readStart"] + 1 + 2 + 15).astype(np.int64).sum() // 16 * 16)
+    alg = 44 * len(rec) + int((rec["seqEnd"] - rec["seqStart"] + 1 + 1).astype(np.int64).sum())     # item + the string (one byte per column + -1)
+    cells = float(st_dp["dp_cells"])
+    line = {"metric": "overlaps/sec through the analyzer's edit-string pass (AddOverlapAlignmentInfo, 150bp reads, HLA ref)", "value": len(rec) / (ms * 1e-3),
+            "unit": "overlaps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32 (affine-gap scores, DPX)", "data": "synthetic",
+            "config": {"workload": "SURVEY 8f N3: every AssignRead record (weight 0) of %d unique read-ends of configs[1] (%d overlaps)" % (len(reads), len(rec)),
+                       "certified_diagonal": int(st["n_diagonal"]), "band_dp": int(st["n_dp"]), "value_basis": "CUDA-event time of k_align_info, items resident in HBM"},
+            "e2e": {"value": len(rec) / wall, "unit": "overlaps/s", "h2d_bytes_per_step": int(44 * len(rec) + sum(len(r) for r in reads)), "d2h_bytes_per_step": out_bytes},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"kernel": "k_align_info", "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg),
+                         "note": "bytes = 44 B per item + one byte per alignment column; the allele / read windows are L2-resident"},
+            "dp_roofline": {"kernel": "k_align_info with the band DP forced for every item (dp_align_eq / dp_align + traceback)", "bound": "dpx",
+                            "band_cells_per_s": cells / (ms_dp * 1e-3), "achieved": 3 * cells / (ms_dp * 1e-3) / 1e9, "peak": gops.value, "unit": "G DPX ops/s",
+                            "frac": 3 * cells / (ms_dp * 1e-3) / 1e9 / gops.value if gops.value else None, "ms": ms_dp, "band_dps": int(st_dp["n_dp"]),
+                            "peak_source": "t1k_dpx_peak: 8 independent VIADDMNMX chains per thread, 8 blocks of 256 threads per SM, CUDA events",
+                            "note": "3 DPX operations per band cell (e, f: max(a+b,c); m: three-way max); a cell also costs ~12 integer / logic instructions "
+                                    "(direction nibble, base compare, band bookkeeping), so the DPX pipe cannot be the binding limit"}}
+    if not args.no_cpu_baseline:
+        import oracle_py as O        # checker only: the CPU restatement of GlobalAlignment as the 1-core baseline
+        rc = np.zeros(256, dtype=np.uint8)
+        for x, y in zip(b"ACGTN", b"TGCAN"):
+            rc[x] = y
+        m = min(len(rec), 20000)
+        pairs = []
+        for k in range(m):
+            rd = np.frombuffer(reads[int(idx[k])], dtype=np.uint8)
+            if rec["strand"][k] == -1:
+                rd = rc[rd[::-1]]
+            pairs.append((bytes(ref.seqs[int(rec["seqIdx"][k])][int(rec["seqStart"][k]):int(rec["seqEnd"][k]) + 1]),
+                          rd[int(rec["readStart"][k]):int(rec["readEnd"][k]) + 1].tobytes()))
+        t0 = time.perf_counter()
+        for t, q in pairs:
+            O.global_alignment(t, q)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": m / dt, "unit": "overlaps/s", "cores": 1, "kind": "port",
+                                "sample": "the first %d items through the oracle's GlobalAlignment (full three-matrix DP as AlignAlgo.hpp:215-421), one core" % m}
+    print(json.dumps(line), file=real_stdout, flush=True)
+
+
 def _claim_stdout():
     """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON line on stdout.
     Everything else is sent to stderr; the returned file object is the real stdout for the JSON line."""
@@ -402,14 +478,19 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=0, help="fragments of the CPU reference sample (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the multi-GPU check against a one-GPU run of the union")
-    ap.add_argument("--stage", default="genotype", choices=["genotype", "filter", "dropin"],
-                    help="filter: SURVEY 8f N1, the extractor's candidate filter; dropin: the drop-in genotyper binary on FASTQ files")
+    ap.add_argument("--stage", default="genotype", choices=["genotype", "filter", "dropin", "alninfo"],
+                    help="filter: SURVEY 8f N1, the extractor's candidate filter; dropin: the drop-in genotyper binary on FASTQ files; "
+                         "alninfo: SURVEY 8f N3, the analyzer's edit strings + the band-DP / DPX roofline")
     args = ap.parse_args()
     if args.stage == "filter":
         filter_stage(args, real_stdout)
         return
     if args.stage == "dropin":
         dropin_stage(args, real_stdout)
+        return
+    if args.stage == "alninfo":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        alninfo_stage(args, real_stdout)
         return
     cfg = CONFIGS[args.config]
     if not args.pairs:

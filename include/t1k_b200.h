@@ -215,6 +215,28 @@ void t1k_filter_destroy(T1KFilter *f);
 int t1k_filter_batch(T1KFilter *f, const char *bases, const uint64_t *off, const uint32_t *len, uint32_t n_reads,
                      uint8_t *good, T1KFilterStats *stats);
 
+/* ---- the analyzer, second caller of the boundary (Analyzer.cpp:467-669).  It calls AssignRead with weight 0
+ * (t1k_assign_batch above), pairs on the host over the fetched records, and after the EM asks for the edit string of every
+ * overlap it kept: SeqSet::AddFragmentAlignmentInfo -> AddOverlapAlignmentInfo (SeqSet.hpp:2757-2778, 2657-2680) =
+ * AlignAlgo::GlobalAlignment(allele[seqStart..seqEnd], strand-adjusted read[readStart..readEnd]) (AlignAlgo.hpp:215-421).
+ * One call for a batch of (read, overlap) items: read_idx[i] indexes the reads (bases/off/len as in t1k_assign_batch),
+ * ov[i] is a record of t1k_assignment_fetch (coordinates on the record's strand).  *align is library-allocated (t1k_free);
+ * item i's string starts at *align + align_ptr[i] and ends with -1 exactly as `_overlap::align` does (0 EDIT_MATCH,
+ * 1 EDIT_MISMATCH, 2 EDIT_INSERT, 3 EDIT_DELETE, AlignAlgo.hpp:7-10); align_ptr[i] = UINT64_MAX for seqIdx == -1 (the
+ * reference leaves `align` unset, SeqSet.hpp:2659-2660).  flags bit 0: run the band DP for every item (no certified-diagonal
+ * shortcut; results are identical, used for A/B checks and the DP roofline).  stats may be NULL. */
+typedef struct {
+  uint64_t n_diagonal, n_dp, dp_cells;   /* items written from the mismatch plane / by the band DP, band cells of the latter */
+  float ms_kernel;                       /* device time of k_align_info (CUDA events) */
+} T1KAlignInfoStats;
+int t1k_align_info_batch(T1KRef *ref, const char *bases, const uint64_t *off, const uint32_t *len, uint32_t n_reads,
+                         const uint32_t *read_idx, const T1KOverlap *ov, uint32_t n_items, int32_t flags,
+                         uint64_t *align_ptr /* [n_items], caller-allocated */, int8_t **align, uint64_t *align_bytes,
+                         T1KAlignInfoStats *stats);
+/* Measured DPX issue rate of the device (G max(a+b,c) operations per second): the ceiling the band DP's cell rate is
+ * reported against ("Banded DP").  No reference counterpart. */
+int t1k_dpx_peak(int32_t device, double *gops);
+
 /* ---- multi-GPU plumbing.  The launcher (torchrun + torch.distributed, MPI, a shared file ...) moves the 128-byte
  * unique id from rank 0 to the other ranks; everything on the data path is NCCL over NVLink. */
 #define T1K_UNIQUE_ID_BYTES 128

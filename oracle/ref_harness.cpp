@@ -7,6 +7,8 @@
 //
 //   align     AlignAlgo::GlobalAlignment            (/root/reference/AlignAlgo.hpp:215-421)
 //   assign    SeqSet::AssignRead                    (/root/reference/SeqSet.hpp:2119-2303)
+//   alninfo   AssignRead with weight 0 (the analyzer's call, Analyzer.cpp:142,476) followed by
+//             SeqSet::AddOverlapAlignmentInfo          (/root/reference/SeqSet.hpp:2657-2680) on every record
 //   genotype  the Genotyper.cpp:450-646 flow        (AssignRead -> ReadAssignmentToFragmentAssignment
 //             -> SetReadAssignments -> CoalesceReadAssignments -> FinalizeReadAssignments
 //             -> QuantifyAlleleEquivalentClass), dumping every boundary the C ABI exposes.
@@ -146,6 +148,40 @@ static int mode_assign(int argc, char **argv)
 	return 0;
 }
 
+static int mode_alninfo(int argc, char **argv)
+{
+	Args a = parse(argc, argv);
+	Genotyper g(11);
+	g.InitRefSet((char *)a.ref);
+	SeqSet &refSet = g.refSet;
+	refSet.SetRefSeqSimilarity(a.sim);
+	refSet.SetRelaxIntronAlign(a.relax);
+	std::vector<std::string> seqs; std::vector<int> w;
+	load_lines(a.reads1, seqs, w);
+	FILE *fp = a.out ? fopen(a.out, "w") : stdout;
+	fprintf(fp, "A %d\n", refSet.Size());
+	for (size_t i = 0; i < seqs.size(); ++i)
+	{
+		std::vector<struct _overlap> out;
+		int ret = refSet.AssignRead((char *)seqs[i].c_str(), -1, 0, out);
+		fprintf(fp, "R %d %d %d\n", (int)i, ret, (int)out.size());
+		for (size_t j = 0; j < out.size(); ++j)
+		{
+			print_overlap(fp, out[j]);
+			refSet.AddOverlapAlignmentInfo((char *)seqs[i].c_str(), out[j]);
+			fputs("L ", fp);
+			int k;
+			for (k = 0; out[j].align[k] != -1; ++k)
+				fputc('0' + out[j].align[k], fp);
+			if (k == 0) fputc('-', fp);
+			fputc('\n', fp);
+			delete[] out[j].align;
+		}
+	}
+	if (a.out) fclose(fp);
+	return 0;
+}
+
 struct Rd { std::string seq; int mate, idx, info; bool hasN; };
 static bool rd_lt(const Rd &a, const Rd &b) { return strcmp(a.seq.c_str(), b.seq.c_str()) < 0; }
 
@@ -258,6 +294,7 @@ int main(int argc, char **argv)
 	std::string m(argv[1]);
 	if (m == "align") return mode_align(argc, argv);
 	if (m == "assign") return mode_assign(argc, argv);
+	if (m == "alninfo") return mode_alninfo(argc, argv);
 	if (m == "genotype") return mode_genotype(argc, argv);
 	die("unknown mode");
 	return 2;

@@ -27,7 +27,7 @@ EXPORTS = ["t1k_last_error", "t1k_device_count", "t1k_ref_create", "t1k_ref_dest
            "t1k_em_run", "t1k_genotype", "t1k_comm_unique_id", "t1k_comm_create", "t1k_comm_destroy",
            "t1k_coverage_allreduce", "t1k_groups_create", "t1k_groups_destroy", "t1k_groups_add_fragments",
            "t1k_groups_serialize", "t1k_groups_merge", "t1k_groups_fetch", "t1k_em_partition",
-           "t1k_filter_create", "t1k_filter_destroy", "t1k_filter_batch"]
+           "t1k_filter_create", "t1k_filter_destroy", "t1k_filter_batch", "t1k_align_info_batch", "t1k_dpx_peak"]
 
 UNIQUE_ID_BYTES = 128
 
@@ -79,6 +79,10 @@ class FilterDesc(C.Structure):
 class FilterStats(C.Structure):
     _fields_ = [("windows", C.c_uint64), ("entries", C.c_uint64), ("chained", C.c_uint64), ("ms_kernel", C.c_float),
                 ("kmer_length", C.c_int32)]
+
+
+class AlignInfoStats(C.Structure):
+    _fields_ = [("n_diagonal", C.c_uint64), ("n_dp", C.c_uint64), ("dp_cells", C.c_uint64), ("ms_kernel", C.c_float)]
 
 
 class AssignStats(C.Structure):
@@ -141,6 +145,9 @@ def lib():
         L.t1k_filter_destroy.argtypes = [C.c_void_p]
         L.t1k_filter_destroy.restype = None
         L.t1k_filter_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(FilterStats)]
+        L.t1k_align_info_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                           C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(AlignInfoStats)]
+        L.t1k_dpx_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 

@@ -20,6 +20,7 @@
 #include "t1k_model.hpp"
 #include "t1k_pair.cuh"
 #include "t1k_filter.cuh"
+#include "t1k_alninfo.cuh"
 
 using namespace t1k;
 
@@ -1420,6 +1421,122 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     g->G.assignedFragments = groups.assignedFragments;
     *prm->groups_out = g;
   }
+  return T1K_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// edit strings for the analyzer (SeqSet::AddOverlapAlignmentInfo)
+static_assert(sizeof(OvIn) == sizeof(T1KOverlap), "OvIn mirrors T1KOverlap");
+
+extern "C" {
+
+int t1k_align_info_batch(T1KRef *ref, const char *bases, const uint64_t *off, const uint32_t *len, uint32_t n_reads, const uint32_t *read_idx,
+                         const T1KOverlap *ov, uint32_t n_items, int32_t flags, uint64_t *align_ptr, int8_t **align, uint64_t *align_bytes,
+                         T1KAlignInfoStats *stats) {
+  if (!ref || !align || !align_bytes || (n_items > 0 && (!read_idx || !ov || !align_ptr)) || (n_reads > 0 && (!bases || !off || !len)))
+    return fail(T1K_ERR_ARG, "t1k_align_info_batch: bad argument");
+  *align = nullptr; *align_bytes = 0;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  CK(cudaSetDevice(ref->device));
+  cudaStream_t st = ref->stream;
+  size_t total = 0; int maxLen = KMER;
+  for (uint32_t i = 0; i < n_reads; ++i) {
+    if (len[i] > T1K_MAX_READ_LEN) return fail(T1K_ERR_ARG, "read longer than T1K_MAX_READ_LEN");
+    total = std::max(total, (size_t)(off[i] + len[i]));
+    maxLen = std::max(maxLen, (int)len[i]);
+  }
+  // output slots: 16-byte aligned, lent + lenp + 2 bytes (every op consumes a base of at least one side; + the -1)
+  std::vector<u64> slot(n_items);
+  u64 bytes = 0;
+  for (uint32_t i = 0; i < n_items; ++i) {
+    const T1KOverlap &o = ov[i];
+    if (o.seqIdx == -1) { slot[i] = ~0ull; align_ptr[i] = ~0ull; continue; }
+    if (o.seqIdx < 0 || o.seqIdx >= ref->nAlleles || read_idx[i] >= n_reads || (o.strand != 1 && o.strand != -1) || o.seqStart < 0 ||
+        o.seqEnd < o.seqStart - 1 || o.seqEnd >= ref->len[o.seqIdx] || o.readStart < 0 || o.readEnd < o.readStart - 1 ||
+        o.readEnd >= (int32_t)len[read_idx[i]])
+      return fail(T1K_ERR_ARG, "t1k_align_info_batch: overlap coordinates outside the allele / read");
+    slot[i] = bytes; align_ptr[i] = bytes;
+    bytes += ((u64)(o.seqEnd - o.seqStart + 1) + (u64)(o.readEnd - o.readStart + 1) + 2 + 15) & ~(u64)15;
+  }
+  PhaseTimer pt;
+  stale("t1k_align_info_batch");
+  if (int rc = setup_assign_launch(ref, maxLen)) return rc;
+  int8_t *host = (int8_t *)malloc(std::max<u64>(bytes, 16));
+  if (!host) return fail(T1K_ERR_ARG, "t1k_align_info_batch: out of host memory");
+  struct HostGuard { int8_t *p; ~HostGuard() { free(p); } } hg{host};
+  if (n_items == 0 || bytes == 0) { hg.p = nullptr; *align = host; return T1K_OK; }
+  DevMem dBases, dOff, dLen, planes, len16, dOv, dIdx, dSlot, dOut;
+  const int rwords = read_words(ref->scrLen);
+  CK(dBases.alloc(total)); CK(dOff.alloc((size_t)n_reads * 8)); CK(dLen.alloc((size_t)n_reads * 4));
+  CK(planes.alloc((size_t)n_reads * 4 * rwords * 8)); CK(len16.alloc((size_t)n_reads * 2));
+  CK(dOv.alloc((size_t)n_items * sizeof(OvIn))); CK(dIdx.alloc((size_t)n_items * 4)); CK(dSlot.alloc((size_t)n_items * 8)); CK(dOut.alloc(bytes));
+  CK(cudaMemcpyAsync(dBases.p, bases, total, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dOff.p, off, (size_t)n_reads * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dLen.p, len, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dOv.p, ov, (size_t)n_items * sizeof(OvIn), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dIdx.p, read_idx, (size_t)n_items * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dSlot.p, slot.data(), (size_t)n_items * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(ref->errFlag.p, 0, sizeof(int), st));
+  CK(cudaMemsetAsync(ref->stats.p, 0, 4 * sizeof(unsigned long long), st));
+  k_pack_reads<<<(n_reads + 127) / 128, 128, 0, st>>>(dBases.as<char>(), dOff.as<u64>(), dLen.as<u32>(), n_reads, rwords, planes.as<u64>(), len16.as<u16>(),
+                                                        ref->errFlag.as<int>());
+  CK(cudaGetLastError());
+  AlnInfoParams P;
+  P.R = ref->R; P.planes = planes.as<u64>(); P.rwords = rwords; P.maxLen = ref->scrLen; P.len = len16.as<u16>();
+  P.ov = dOv.as<OvIn>(); P.readIdx = dIdx.as<u32>(); P.nItems = n_items; P.slot = dSlot.as<u64>(); P.out = dOut.as<u8>();
+  P.laneScratch = ref->laneScratch.as<u8>(); P.err = ref->errFlag.as<int>(); P.stats = ref->stats.as<unsigned long long>();
+  P.noDiag = (flags & 1) ? 1 : 0;
+  cudaEvent_t ev0, ev1;
+  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+  struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
+  CK(cudaEventRecord(ev0, st));
+  const int blocks = (int)std::min<size_t>(ref->gridBlocks, ((size_t)n_items + WARPS_PER_BLOCK * 32 - 1) / (WARPS_PER_BLOCK * 32));
+  k_align_info<<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(P);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ev1, st));
+  int err = 0; unsigned long long hs[4] = {0, 0, 0, 0};
+  CK(cudaMemcpyAsync(&err, ref->errFlag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hs, ref->stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(host, dOut.p, bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  pt.lap("align info: kernel + D2H");
+  if (err & (ERR_READ_LEN | ERR_READ_CHAR)) return fail(T1K_ERR_ARG, "read contains a character outside ACGTN or is too long");
+  if (err) return fail(T1K_ERR_UNSUPPORTED, "t1k_align_info_batch:" + decode_err(err));
+  if (stats) {
+    stats->n_diagonal = hs[0]; stats->n_dp = hs[1]; stats->dp_cells = hs[2];
+    CK(cudaEventElapsedTime(&stats->ms_kernel, ev0, ev1));
+  }
+  hg.p = nullptr;
+  *align = host; *align_bytes = bytes;
+  return T1K_OK;
+}
+
+int t1k_dpx_peak(int32_t device, double *gops) {
+  if (!gops) return fail(T1K_ERR_ARG, "t1k_dpx_peak: bad argument");
+  int dev = 0;
+  if (int rc = pick_device(device, &dev)) return rc;
+  CK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  DevMem sink;
+  CK(sink.alloc(4));
+  cudaEvent_t ev0, ev1;
+  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+  struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  double best = 0;
+  for (int rep = 0; rep < 4; ++rep) {          // first round warms up
+    CK(cudaEventRecord(ev0, 0));
+    k_dpx_peak<<<blocks, threads>>>(iters, 12345 + rep, sink.as<int>());
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ev1, 0));
+    CK(cudaEventSynchronize(ev1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    if (rep > 0 && ms > 0) best = std::max(best, (double)blocks * threads * (double)iters * 8.0 / (ms * 1e-3) / 1e9);
+  }
+  *gops = best;
   return T1K_OK;
 }
 

@@ -211,6 +211,22 @@ T1K_HD int ctz64(u64 x) {
 T1K_HD int imin(int a, int b) { return a < b ? a : b; }
 T1K_HD int imax(int a, int b) { return a > b ? a : b; }
 T1K_HD int iabs(int a) { return a < 0 ? -a : a; }
+// DPX (sm_90+): max(a + b, c) and the three-way max as one instruction each (VIADDMNMX / VIMNMX3) — the two shapes the
+// affine-gap recurrences of GlobalAlignment consist of.  Plain integer arithmetic on the host (same values).
+T1K_HD int addmax(int a, int b, int c) {
+#ifdef __CUDA_ARCH__
+  return __viaddmax_s32(a, b, c);
+#else
+  const int s = a + b; return s > c ? s : c;
+#endif
+}
+T1K_HD int max3(int a, int b, int c) {
+#ifdef __CUDA_ARCH__
+  return __vimax3_s32(a, b, c);
+#else
+  const int m = a > b ? a : b; return m > c ? m : c;
+#endif
+}
 
 constexpr int COV_STRIDE = 32;
 T1K_HD void cov_add(int32_t *p, int v) {
@@ -498,16 +514,13 @@ T1K_HDN T1K_NOINLINE inline int dp_align_eq(const AlleleView &T, int tpos, const
       else if (j == 0) { mv = -4 - 4 * i; ev = -4 - i; fv = -4 - 4 * i; }
       else {
         const int mUp = mP[jj + 1], eUp = eP[jj + 1], mDiag = mP[jj];
-        const int e1 = eUp - 1, e2 = mUp - 5;
-        ev = e1 > e2 ? e1 : e2;
-        const int f1 = fPrev - 1, f2 = mLeft - 5;
-        fv = f1 > f2 ? f1 : f2;
+        const int e2 = mUp - 5, f2 = mLeft - 5;
+        ev = addmax(eUp, -1, e2);
+        fv = addmax(fPrev, -1, f2);
         const int sh = (j - start) * 2;
         const bool eq = pn || ((tn >> sh) & 3) || (int)((ts >> sh) & 3) == pb;
         const int dv = mDiag + (eq ? 2 : -2);
-        mv = dv;
-        if (ev > mv) mv = ev;
-        if (fv > mv) mv = fv;
+        mv = max3(dv, ev, fv);
         const u64 bits = (u64)((dv == mv ? 1 : 0) | (fv >= ev ? 2 : 0) | (e2 == ev ? 4 : 0) | (f2 == fv ? 8 : 0));
         bitsRow |= bits << (4 * jj);
       }
@@ -606,17 +619,14 @@ T1K_HDN T1K_NOINLINE inline int dp_align(const AlleleView &T, int tpos, int lent
       else {
         // previous row window starts one column earlier: column j is at jj+1, column j-1 at jj
         int mUp = mP[jj + 1], eUp = eP[jj + 1], mDiag = mP[jj];
-        int e1 = eUp - 1, e2 = mUp - 5;
-        ev = e1 > e2 ? e1 : e2;
-        int f1 = fPrev - 1, f2 = mLeft - 5;
-        fv = f1 > f2 ? f1 : f2;
+        const int e2 = mUp - 5, f2 = mLeft - 5;
+        ev = addmax(eUp, -1, e2);
+        fv = addmax(fPrev, -1, f2);
         const int q = j - start, sh = (q & 31) * 2;
         const int tbase = (int)(((q < 32 ? ts0 : ts1) >> sh) & 3), tnn = (int)(((q < 32 ? tn0 : tn1) >> sh) & 3);
         bool eq = pn || tnn || tbase == pb;
         int dv = mDiag + (eq ? 2 : -2);
-        mv = dv;
-        if (ev > mv) mv = ev;
-        if (fv > mv) mv = fv;
+        mv = max3(dv, ev, fv);
         bits = (u8)((dv == mv ? 1 : 0) | (fv >= ev ? 2 : 0) | (e2 == ev ? 4 : 0) | (f2 == fv ? 8 : 0));
       }
       mC[jj] = mv; eC[jj] = ev;
@@ -700,6 +710,36 @@ T1K_HD int align_matches(const AlleleView &T, int tpos, int lent, const ReadView
   T1K_COUNT(4, 1);
   const int m = align_matches_hot(T, tpos, lent, Q, ppos, lenp);
   return m >= 0 ? m : align_matches_cold(T, tpos, lent, Q, ppos, lenp, S, err);
+}
+
+// SeqSet::AddOverlapAlignmentInfo (SeqSet.hpp:2657-2680): the edit string of GlobalAlignment(allele[tpos, tpos + lent),
+// read strand[ppos, ppos + lenp)) in S.ops() (0 M, 1 X, 2 I, 3 D), returns its length (< 0: error).  An equal-length pair whose
+// diagonal is certified (diag_certified: the reference's traceback provably stays on the diagonal) is written straight from
+// the mismatch plane, eight columns per store; everything else runs the band DP.  noDiag: always the DP (A/B switch).
+T1K_HDN T1K_NOINLINE inline int align_info(const AlleleView &T, int tpos, int lent, const ReadView &Q, int ppos, int lenp, const LaneScratch &S,
+                                           int &err, bool noDiag, bool &ranDp) {
+  ranDp = false;
+  if (lent == lenp && lent > 1 && !noDiag && lent + 16 <= S.opsCap) {
+    int mm;
+    if (diag_certified(T, tpos, Q, ppos, lent, mm)) {
+      u64 *w = (u64 *)S.ops();
+      T1K_NOUNROLL
+      for (int k = 0; k < lent; k += 32) {
+        const u64 d = mm_chunk(T, tpos + k, Q, ppos + k, lent - k);
+        T1K_NOUNROLL
+        for (int q = 0; q < 4 && k + 8 * q < lent; ++q) {
+          const u32 x = (u32)(d >> (16 * q)) & 0xFFFFu;
+          u64 v = 0;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v |= (u64)((x >> (2 * c)) & 1u) << (8 * c);
+          w[(k >> 3) + q] = v;
+        }
+      }
+      return lent;
+    }
+  }
+  ranDp = lent > 0 && lenp > 0 && !(lent == 1 && lenp == 1);
+  return dp_align(T, tpos, lent, Q, ppos, lenp, S, err);
 }
 
 // any N inside [s, e] of an N plane that starts at the allele's first word

@@ -124,6 +124,38 @@ class SeqSet:
             L.lib().t1k_free(en)
         return (row, ent, fa) if with_assigned else (row, ent)
 
+    def AddOverlapAlignmentInfo(self, reads, read_idx, overlaps, force_dp=False, with_stats=False, raw=False):
+        """SeqSet::AddOverlapAlignmentInfo (SeqSet.hpp:2657-2680) for a batch of (read, overlap) items: overlaps are records of
+        Assignment.fetch() (OVERLAP_DT), read_idx[i] the read each belongs to -> list of int8 edit strings (0 M, 1 X, 2 I, 3 D;
+        None where seqIdx == -1).  force_dp: the band DP for every item (A/B switch).  raw: (blob, align_ptr) instead of the list."""
+        bases, off, lens = _reads_to_batch(reads)
+        ov = np.ascontiguousarray(overlaps, dtype=L.OVERLAP_DT)
+        idx = np.ascontiguousarray(read_idx, dtype=np.uint32)
+        n = len(ov)
+        aptr = np.zeros(n, dtype=np.uint64)
+        blob, nbytes, st = C.c_void_p(), C.c_uint64(0), L.AlignInfoStats()
+        L.check(L.lib().t1k_align_info_batch(self.h, L.ptr(bases), L.ptr(off), L.ptr(lens), len(lens), L.ptr(idx), L.ptr(ov), n,
+                                             1 if force_dp else 0, L.ptr(aptr), C.byref(blob), C.byref(nbytes), C.byref(st)))
+        try:
+            buf = np.ctypeslib.as_array(C.cast(blob, C.POINTER(C.c_int8)), shape=(max(1, nbytes.value),)).copy()
+        finally:
+            L.lib().t1k_free(blob)
+        if raw:
+            out = (buf, aptr)
+            return (out, {k: getattr(st, k) for k, _ in st._fields_}) if with_stats else out
+        out = []
+        for i in range(n):
+            if aptr[i] == np.uint64(0xFFFFFFFFFFFFFFFF):
+                out.append(None)
+                continue
+            a = int(aptr[i])
+            cap = int(ov["seqEnd"][i] - ov["seqStart"][i] + 1 + ov["readEnd"][i] - ov["readStart"][i] + 1) + 2
+            s = buf[a:a + cap]
+            out.append(s[:int(np.argmax(s == -1))])
+        if with_stats:
+            return out, {k: getattr(st, k) for k, _ in st._fields_}
+        return out
+
     def GetBaseCoverage(self):
         """posWeight[].count[consensus base] of every allele, concatenated (Q11)."""
         out = np.zeros(int(self.offset[-1]), dtype=np.int32)

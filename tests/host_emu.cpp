@@ -304,6 +304,25 @@ int32_t emu_assign(Emu *E, const char *read, int32_t weight, EmuOverlap *out, in
   return (int)order.size();
 }
 
+// SeqSet::AddOverlapAlignmentInfo through the product's lane code (align_info): edit string of one record of emu_assign.
+// Returns the number of ops (< 0: error); *ranDp = 1 when the band DP ran (0: certified diagonal).
+int32_t emu_align_info(Emu *E, const char *read, const EmuOverlap *o, int32_t noDiag, int8_t *opsOut, int32_t *ranDpOut) {
+  int len = (int)strlen(read);
+  if (len > MAX_READ_LEN || o->seqIdx < 0) return -2;
+  u64 planes[4][MAX_RWORDS];
+  if (!pack_read(read, len, planes[0], planes[1], planes[2], planes[3], MAX_RWORDS)) return -2;
+  const int pass = o->strand == 1 ? 0 : 1;
+  ReadView Q; Q.seq2 = planes[pass * 2]; Q.n2 = planes[pass * 2 + 1]; Q.len = len; Q.anyN = strchr(read, 'N') != NULL;
+  const LaneScratch S = lane_scratch(E->scratch.data(), MAX_READ_LEN);
+  const AlleleView T = allele_view(E->R, o->seqIdx, Q);
+  int err = 0; bool ranDp = false;
+  const int n = align_info(T, o->seqStart, o->seqEnd - o->seqStart + 1, Q, o->readStart, o->readEnd - o->readStart + 1, S, err, noDiag != 0, ranDp);
+  *ranDpOut = ranDp ? 1 : 0;
+  if (err || n < 0) return -1;
+  for (int i = 0; i < n; ++i) opsOut[i] = (int8_t)S.ops()[i];
+  return n;
+}
+
 // coverage of one allele = prefix(covDiff) + covPoint
 void emu_coverage(Emu *E, int32_t allele, int32_t *out) {
   size_t cb = (size_t)E->P.covOff[allele];
