@@ -183,6 +183,13 @@ typedef struct {
                                                                of Genotyper::SetAlleleAbundance, Genotyper.hpp:957) */
   int32_t *ec_allele_ptr, *ec_alleles;                      /* optional, caller-allocated [n_alleles+1] / [n_alleles]: members of every EC in the
                                                                order of Genotyper::equivalentClassToAlleles (Genotyper.hpp:1072-1139) */
+  /* SURVEY.md §8f N4 — Genotyper::RemoveLowLikelihoodAlleleInEquivalentClass (Genotyper.hpp:1371-1460, called at Genotyper.cpp:647
+   * right after the EM).  Optional, caller-allocated: allele_kept[n_alleles] = 1 when the allele stays in its equivalence
+   * class (likelihood pow(covered range / length, ecAbundance) within 0.05 of the class's best), 0 when it is removed or has no
+   * class; allele_span[2 * n_alleles] = the covered range the likelihood is computed from (min start at [a], INT32_MAX without
+   * entries; max end at [n_alleles + a], -1 without).  Read-sharded runs reduce the ranges over the ranks (one int32 all-reduce). */
+  uint8_t *allele_kept;
+  int32_t *allele_span;
 } T1KGenotypeResult;
 
 int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t stride, uint32_t n_frag,
@@ -258,6 +265,11 @@ int t1k_groups_merge(T1KGroups *g, const void *blob, uint64_t bytes);
 /* n_groups / total entries / assigned fragments; then ptr[n_groups+1] and entries (caller-allocated, may be NULL) */
 int t1k_groups_fetch(const T1KGroups *g, int32_t *n_groups, uint64_t *n_entries, uint64_t *assigned_fragments,
                      int64_t *ptr, T1KReadAssignment *entries);
+/* Genotyper::RemoveLowLikelihoodAlleleInEquivalentClass (Genotyper.hpp:1371-1460) over a group table: ec_allele_ptr / ec_alleles
+ * = Genotyper::equivalentClassToAlleles, allele_len = SeqSet::GetSeqConsensusLen, ec_abundance = alleleInfo[].ecAbundance
+ * (T1KGenotypeResult.ec_abundance).  allele_kept[n_alleles], allele_span[2 * n_alleles] (may be NULL) as in T1KGenotypeResult. */
+int t1k_groups_ec_filter(const T1KGroups *g, int32_t n_alleles, const int32_t *allele_len, const double *ec_abundance,
+                         const int32_t *ec_allele_ptr, const int32_t *ec_alleles, int32_t n_ec, uint8_t *allele_kept, int32_t *allele_span);
 /* contiguous row ranges of the EM problem balanced by non-zeros: bounds[world+1] */
 int t1k_em_partition(const int64_t *row_ptr, int32_t n_groups, int32_t world, int32_t *bounds);
 

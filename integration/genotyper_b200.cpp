@@ -202,6 +202,7 @@ int main(int argc, char *argv[]) {
   int emIterCntLib = 0;
   std::vector<double> libRc;
   std::vector<int32_t> libEc, libEcPtr, libEcAlleles, libMissing;
+  std::vector<uint8_t> libKept;
   int libEcCnt = 0;
   const bool pipelined = !outputReadAssignment && getenv("T1K_DROPIN_SYNC") == NULL;
   const double tHot0 = (double)clock() / CLOCKS_PER_SEC;
@@ -238,6 +239,7 @@ int main(int argc, char *argv[]) {
     res.abundance = abundance.data(); res.ec_abundance = ecAbundance.data(); res.equivalent_class = libEc.data();
     res.missing_coverage = libMissing.data(); res.fragment_assigned = fragAssigned.data(); res.ec_read_count = libRc.data();
     res.ec_allele_ptr = libEcPtr.data(); res.ec_alleles = libEcAlleles.data();
+    libKept.assign(alleleCnt > 0 ? alleleCnt : 1, 0); res.allele_kept = libKept.data();
     T1K_CALL(t1k_genotype(ref, buf1.data(), hasMate ? buf2.data() : NULL, stride, (uint32_t)readCnt, &prm, &res));
     int32_t nG = 0; uint64_t nE = 0, nAssigned = 0;
     T1K_CALL(t1k_groups_fetch(grp, &nG, &nE, &nAssigned, NULL, NULL));
@@ -433,7 +435,18 @@ int main(int argc, char *argv[]) {
   t1k_ref_destroy(ref);
 
   // ---- downstream of the hot path: the reference's own selection and writers (Genotyper.cpp:647-718)
-  genotyper.RemoveLowLikelihoodAlleleInEquivalentClass();
+  // RemoveLowLikelihoodAlleleInEquivalentClass (Genotyper.hpp:1371-1460): the pipelined path already has the answer from the
+  // library (allele_kept of t1k_genotype, computed over the same read groups, classes and ecAbundance); T1K_DROPIN_REF_FINALIZE=1
+  // and the synchronous path run the reference's own code.
+  if (sameEc && !fpAbundance && !libKept.empty() && getenv("T1K_DROPIN_REF_FINALIZE") == NULL) {
+    for (size_t e = 0; e < genotyper.equivalentClassToAlleles.size(); ++e) {
+      std::vector<int> &m = genotyper.equivalentClassToAlleles[e];
+      std::vector<int> keptAlleles;
+      for (size_t j = 0; j < m.size(); ++j) if (libKept[m[j]]) keptAlleles.push_back(m[j]);
+      m = keptAlleles;
+    }
+  } else
+    genotyper.RemoveLowLikelihoodAlleleInEquivalentClass();
   genotyper.SelectAllelesForGenes();
   const int geneCnt = genotyper.GetGeneCnt();
   char *bufferAllele[3];

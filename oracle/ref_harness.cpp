@@ -62,10 +62,10 @@ static int mode_align(int argc, char **argv)
 struct Args
 {
 	const char *ref, *reads1, *reads2, *out;
-	double sim; bool relax; int maxAssign; double minAlpha; bool hasMinAlpha; int dumpCov;
+	double sim; bool relax; int maxAssign; double minAlpha; bool hasMinAlpha; int dumpCov; int ecFilter;
 	double filterFrac;
 	Args(): ref(NULL), reads1(NULL), reads2(NULL), out(NULL), sim(0.8), relax(false), maxAssign(2000),
-		minAlpha(0), hasMinAlpha(false), dumpCov(0), filterFrac(0.15) {}
+		minAlpha(0), hasMinAlpha(false), dumpCov(0), ecFilter(0), filterFrac(0.15) {}
 };
 
 static Args parse(int argc, char **argv)
@@ -84,6 +84,7 @@ static Args parse(int argc, char **argv)
 		else if (s == "--frac") a.filterFrac = atof(argv[++i]);
 		else if (s == "--squaremMinAlpha") { a.minAlpha = atof(argv[++i]); a.hasMinAlpha = true; }
 		else if (s == "--cov") a.dumpCov = 1;
+		else if (s == "--ecfilter") a.ecFilter = 1;
 		else die("unknown argument");
 	}
 	if (!a.ref) die("need -f");
@@ -283,6 +284,16 @@ static int mode_genotype(int argc, char **argv)
 	for (int i = 0; i < g.alleleCnt; ++i)
 		fprintf(fp, "q %d %d %a %a %d %d\n", i, g.alleleInfo[i].equivalentClass, g.alleleInfo[i].abundance,
 			g.alleleInfo[i].ecAbundance, refSet.GetSeqEffectiveLen(i), refSet.GetSeqWeight(i));
+	if (a.ecFilter)
+	{
+		// Genotyper.cpp:647: what stays in the classes after the likelihood filter (Genotyper.hpp:1371-1460)
+		g.RemoveLowLikelihoodAlleleInEquivalentClass();
+		fprintf(fp, "K");
+		for (int i = 0; i < ecCnt; ++i)
+			for (size_t j = 0; j < g.equivalentClassToAlleles[i].size(); ++j)
+				fprintf(fp, " %d", g.equivalentClassToAlleles[i][j]);
+		fprintf(fp, "\n");
+	}
 	if (a.dumpCov) dump_cov(fp, refSet);
 	if (a.out) fclose(fp);
 	return 0;

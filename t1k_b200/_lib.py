@@ -27,7 +27,7 @@ EXPORTS = ["t1k_last_error", "t1k_device_count", "t1k_ref_create", "t1k_ref_dest
            "t1k_em_run", "t1k_genotype", "t1k_comm_unique_id", "t1k_comm_create", "t1k_comm_destroy",
            "t1k_coverage_allreduce", "t1k_groups_create", "t1k_groups_destroy", "t1k_groups_add_fragments",
            "t1k_groups_serialize", "t1k_groups_merge", "t1k_groups_fetch", "t1k_em_partition",
-           "t1k_filter_create", "t1k_filter_destroy", "t1k_filter_batch", "t1k_align_info_batch", "t1k_dpx_peak"]
+           "t1k_filter_create", "t1k_filter_destroy", "t1k_filter_batch", "t1k_align_info_batch", "t1k_dpx_peak", "t1k_groups_ec_filter"]
 
 UNIQUE_ID_BYTES = 128
 
@@ -68,7 +68,7 @@ class GenotypeResult(C.Structure):
                 ("n_postings", C.c_uint64), ("n_candidates", C.c_uint64), ("n_launches", C.c_uint64),
                 ("ms_prep_wait", C.c_float), ("ms_exchange", C.c_float), ("n_pair_records", C.c_uint64), ("em_nnz", C.c_uint64),
                 ("em_updates", C.c_int32), ("ec_read_count", C.c_void_p),
-                ("ec_allele_ptr", C.c_void_p), ("ec_alleles", C.c_void_p)]
+                ("ec_allele_ptr", C.c_void_p), ("ec_alleles", C.c_void_p), ("allele_kept", C.c_void_p), ("allele_span", C.c_void_p)]
 
 
 class FilterDesc(C.Structure):
@@ -140,6 +140,7 @@ def lib():
         L.t1k_groups_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.t1k_groups_fetch.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                        C.c_void_p, C.c_void_p]
+        L.t1k_groups_ec_filter.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.t1k_em_partition.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.t1k_filter_create.argtypes = [C.POINTER(FilterDesc), C.POINTER(C.c_void_p)]
         L.t1k_filter_destroy.argtypes = [C.c_void_p]

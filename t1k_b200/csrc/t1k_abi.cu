@@ -1092,6 +1092,21 @@ int t1k_groups_fetch(const T1KGroups *g, int32_t *n_groups, uint64_t *n_entries,
   return T1K_OK;
 }
 
+int t1k_groups_ec_filter(const T1KGroups *g, int32_t n_alleles, const int32_t *allele_len, const double *ec_abundance, const int32_t *ec_allele_ptr,
+                         const int32_t *ec_alleles, int32_t n_ec, uint8_t *allele_kept, int32_t *allele_span) {
+  if (!g || n_alleles < 0 || n_ec < 0 || !allele_len || !ec_abundance || !ec_allele_ptr || !ec_alleles || !allele_kept)
+    return fail(T1K_ERR_ARG, "t1k_groups_ec_filter: bad argument");
+  for (size_t k = 0; k < g->G.ent.size(); ++k)
+    if (g->G.ent[k].alleleIdx < 0 || g->G.ent[k].alleleIdx >= n_alleles) return fail(T1K_ERR_ARG, "t1k_groups_ec_filter: allele index out of range");
+  for (int32_t k = 0; k < ec_allele_ptr[n_ec]; ++k)
+    if (ec_alleles[k] < 0 || ec_alleles[k] >= n_alleles) return fail(T1K_ERR_ARG, "t1k_groups_ec_filter: class member out of range");
+  std::vector<int32_t> spans;
+  allele_spans(g->G, n_alleles, std::max(1u, std::min(16u, std::thread::hardware_concurrency())), spans);
+  ec_likelihood_filter(ec_allele_ptr, ec_alleles, n_ec, n_alleles, allele_len, ec_abundance, spans.data(), allele_kept);
+  if (allele_span) memcpy(allele_span, spans.data(), spans.size() * 4);
+  return T1K_OK;
+}
+
 int t1k_em_partition(const int64_t *row_ptr, int32_t n_groups, int32_t world, int32_t *bounds) {
   if (!row_ptr || !bounds || n_groups < 0 || world < 1) return fail(T1K_ERR_ARG, "t1k_em_partition: bad argument");
   partition_rows(row_ptr, n_groups, world, bounds);
@@ -1288,8 +1303,10 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   uint64_t nAssignAll = res->n_assignments;
   CompactGroups compactGroups;
   bool useCompact = false;
+  std::vector<int32_t> spans;       // N4: covered range of every allele over the coalesced groups
   if (comm) {
     double tx = now_ms();
+    PhaseTimer px;
     const int W = comm->world, T = shards.threads();
     // status + sizes: {status, assignments, fragments, bytes for rank 0 .. W-1}
     ShardPlan plan;
@@ -1306,7 +1323,9 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
         if (localRc) { g_err = localErr; return localRc; }
         return fail(T1K_ERR_NCCL, "rank " + std::to_string(r) + " of the read-sharded run failed before the exchange");
       }
+    px.lap("exchange: plan + status");
     if (int rc = t1k_coverage_allreduce(ref, comm)) return rc;
+    px.lap("exchange: coverage all-reduce");
     std::vector<int64_t> fragBase((size_t)W, 0);
     std::vector<uint64_t> bytesFrom((size_t)W, 0);
     nAssignAll = 0;
@@ -1318,14 +1337,18 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     }
     CK(ref->pinSend.grow(std::max<size_t>(plan.total, 16), 0));
     serialize_partitions(shards, plan, ref->pinSend.as<uint8_t>(), T);
+    px.lap("exchange: serialize partitions");
     std::vector<size_t> recvOff;
     if (int rc = alltoall_blobs(ref, comm, ref->pinSend.as<uint8_t>(), plan.bytes, bytesFrom, ref->pinRecv, recvOff)) return rc;
+    px.lap("exchange: all-to-all");
     std::vector<GroupBlobView> tables((size_t)W);
     int mergeRc = 0;
     for (int r = 0; r < W && !mergeRc; ++r)
       if (!tables[r].parse(ref->pinRecv.as<uint8_t>() + recvOff[r], bytesFrom[r])) mergeRc = 1;
     ReadGroups mine, merged;
     if (!mergeRc && !merge_tables_partition(tables, fragBase, comm->rank, W, T, mine)) mergeRc = 1;
+    px.lap("exchange: merge my partitions");
+    if (!mergeRc && (res->allele_kept || res->allele_span)) allele_spans(mine, nA, T, spans);     // N4: this rank's share of the covered ranges
     // second exchange: status + the merged partitions.  The global tail (equivalence classes, EM inputs) reads only the allele ids
     // and the count of every group, so the partitions travel in compact form (4 bytes per entry instead of 24) unless the caller
     // wants the whole table back (groups_out).
@@ -1333,6 +1356,7 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     const size_t partBytes = mergeRc ? 0 : (compact ? compact_group_bytes(mine) : serialized_group_bytes(mine));
     CK(ref->pinSend.grow(std::max<size_t>(partBytes, 16), 0));         // (the first exchange's send buffer is no longer needed)
     if (!mergeRc) { if (compact) serialize_compact(mine, ref->pinSend.as<uint8_t>(), T); else serialize_groups(mine, ref->pinSend.as<uint8_t>()); }
+    px.lap("exchange: serialize merged");
     const uint64_t st2 = (uint64_t)mergeRc;
     std::vector<uint64_t> allSt;
     if (int rc = allgather_u64(ref, comm, &st2, 1, allSt)) return rc;
@@ -1340,6 +1364,7 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     uint64_t stride2 = 0;
     std::vector<uint64_t> sizes2;
     if (int rc = allgather_blobs(ref, comm, ref->pinSend.as<uint8_t>(), partBytes, ref->pinRecv2, stride2, sizes2)) return rc;
+    px.lap("exchange: all-gather merged");
     if (compact) {
       std::vector<const uint8_t *> blobs((size_t)W);
       for (int r = 0; r < W; ++r) blobs[r] = ref->pinRecv2.as<uint8_t>() + (size_t)r * stride2;
@@ -1356,8 +1381,23 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
       groups.first.swap(merged.first); groups.hashes.swap(merged.hashes);
       groups.assignedFragments = merged.assignedFragments;
     }
+    px.lap("exchange: assemble");
+    if (res->allele_kept || res->allele_span) {
+      // min / max over the ranks as ONE max all-reduce of {-minStart, maxEnd}
+      if (spans.size() != (size_t)2 * nA) return fail(T1K_ERR_NCCL, "covered ranges missing on this rank");
+      for (int32_t a = 0; a < nA; ++a) spans[a] = spans[a] == INT32_MAX ? INT32_MIN : -spans[a];
+      DevMem dSp;
+      CK(dSp.alloc(spans.size() * 4));
+      CK(cudaMemcpyAsync(dSp.p, spans.data(), spans.size() * 4, cudaMemcpyHostToDevice, ref->stream));
+      NK(nccl().AllReduce(dSp.p, dSp.p, spans.size(), NCCL_INT32, NCCL_MAX, comm->comm, ref->stream));
+      CK(cudaMemcpyAsync(spans.data(), dSp.p, spans.size() * 4, cudaMemcpyDeviceToHost, ref->stream));
+      CK(cudaStreamSynchronize(ref->stream));
+      for (int32_t a = 0; a < nA; ++a) spans[a] = spans[a] == INT32_MIN ? INT32_MAX : -spans[a];
+    }
     res->ms_exchange = (float)(now_ms() - tx);
     res->ms_coalesce += res->ms_exchange;
+  } else if (res->allele_kept || res->allele_span) {
+    allele_spans(groups, nA, shards.threads(), spans);
   }
   res->assigned_fragments = (int32_t)groups.assignedFragments;
   // Genotyper::GetAverageReadAssignmentCnt (Genotyper.hpp:941-955) averages over the coalesced read groups
@@ -1415,6 +1455,12 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     if (res->ec_read_count) memcpy(res->ec_read_count, rc.data(), (size_t)EC.size() * 8);
   }
   res->ms_em = (float)(now_ms() - te);
+  // ---- RemoveLowLikelihoodAlleleInEquivalentClass (Genotyper.cpp:647)
+  if (res->allele_span) memcpy(res->allele_span, spans.data(), spans.size() * 4);
+  if (res->allele_kept) {
+    if (!res->ec_abundance) return fail(T1K_ERR_ARG, "t1k_genotype: allele_kept needs ec_abundance");
+    ec_likelihood_filter(EC.ecPtr.data(), EC.ecAlleles.data(), EC.size(), nA, ref->len.data(), res->ec_abundance, spans.data(), res->allele_kept);
+  }
   if (prm->groups_out) {
     T1KGroups *g = new T1KGroups;
     g->G.ptr.swap(groups.ptr); g->G.ent.swap(groups.ent); g->G.first.swap(groups.first); g->G.hashes.swap(groups.hashes);

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <memory>
 #include <thread>
 #include <unordered_map>
@@ -772,6 +773,60 @@ inline void set_allele_abundance(const double *rc, const int32_t *ecLen, const i
     const int32_t size = ecPtr[e + 1] - ecPtr[e];
     const double abund = rc[e] / ecLen[e] * 1000.0;
     for (int32_t k = ecPtr[e]; k < ecPtr[e + 1]; ++k) { abundance[ecAlleles[k]] = abund / size; ecAbundance[ecAlleles[k]] = abund; }
+  }
+}
+
+// ---- Genotyper::RemoveLowLikelihoodAlleleInEquivalentClass (Genotyper.hpp:1371-1460; Genotyper.cpp:647), SURVEY.md §8f N4.
+// Step 1 (:1395-1416): the covered range of every allele = min start / max end over its entries in the coalesced read groups.
+// The reference walks the groups of the class representative and picks the entries of the class members; members of one
+// class sit in exactly the same groups, so this is the per-allele min / max over all groups.  Threads own contiguous group
+// ranges; min / max commute, so the result does not depend on the thread count.  spans[a] = minStart (INT32_MAX: no entry),
+// spans[nAlleles + a] = maxEnd (-1: no entry).
+inline void allele_spans(const ReadGroups &G, int32_t nAlleles, int threads, std::vector<int32_t> &spans) {
+  const int32_t n = G.size();
+  if (threads < 1 || G.ent.size() < par_min_entries()) threads = 1;
+  const std::vector<int32_t> b = balanced_ranges(G.ptr.data(), n, threads);
+  std::vector<std::vector<int32_t> > part((size_t)threads);
+  run_threads(threads, [&](int t) {
+    std::vector<int32_t> &sp = part[t];
+    sp.assign((size_t)2 * nAlleles, -1);
+    std::fill(sp.begin(), sp.begin() + nAlleles, INT32_MAX);
+    for (int64_t k = G.ptr[b[t]]; k < G.ptr[b[t + 1]]; ++k) {
+      const HostEntry &e = G.ent[k];
+      if (e.start < sp[e.alleleIdx]) sp[e.alleleIdx] = e.start;
+      if (e.end > sp[nAlleles + e.alleleIdx]) sp[nAlleles + e.alleleIdx] = e.end;
+    }
+  });
+  spans.swap(part[0]);
+  for (int t = 1; t < threads; ++t)
+    for (int32_t a = 0; a < nAlleles; ++a) {
+      spans[a] = std::min(spans[a], part[t][a]);
+      spans[nAlleles + a] = std::max(spans[nAlleles + a], part[t][nAlleles + a]);
+    }
+}
+// Step 2 (:1418-1457): likelihood pow(effectiveLen / len, ecAbundance) per member, keep the members within 0.05 of the best
+// (or equal to it).  kept[a] = 1 when allele a stays in its class (0 also for alleles without a class).
+inline void ec_likelihood_filter(const int32_t *ecPtr, const int32_t *ecAlleles, int32_t nEc, int32_t nAlleles, const int32_t *alleleLen,
+                                 const double *ecAbundance, const int32_t *spans, uint8_t *kept) {
+  memset(kept, 0, (size_t)nAlleles);
+  std::vector<double> ll;
+  for (int32_t e = 0; e < nEc; ++e) {
+    const int32_t size = ecPtr[e + 1] - ecPtr[e];
+    ll.assign((size_t)size, 0.0);
+    double maxLikelihood = -1;
+    for (int32_t j = 0; j < size; ++j) {
+      const int32_t a = ecAlleles[ecPtr[e] + j];
+      const int32_t len = alleleLen[a];
+      const int32_t minStart = std::min(len, spans[a]), maxEnd = std::max(-1, spans[nAlleles + a]);
+      int32_t effectiveLen = maxEnd - minStart + 1;
+      if (effectiveLen > len) effectiveLen = len;
+      const double v = pow(double(effectiveLen) / len, ecAbundance[a]);
+      if (v > maxLikelihood) maxLikelihood = v;
+      ll[j] = v;
+    }
+    const double cutoff = 0.05;
+    for (int32_t j = 0; j < size; ++j)
+      if (ll[j] / maxLikelihood >= cutoff || ll[j] == maxLikelihood) kept[ecAlleles[ecPtr[e] + j]] = 1;
   }
 }
 

@@ -97,6 +97,18 @@ class ReadGroups:
         buf = np.frombuffer(blob, dtype=np.uint8)
         L.check(L.lib().t1k_groups_merge(self.h, L.ptr(buf), len(buf)))
 
+    def ec_filter(self, allele_len, ec_abundance, ec_allele_ptr, ec_alleles):
+        """Genotyper::RemoveLowLikelihoodAlleleInEquivalentClass (Genotyper.hpp:1371-1460) over this table ->
+        (allele_kept uint8[n_alleles], allele_span int32[2 * n_alleles])"""
+        ln = np.ascontiguousarray(allele_len, dtype=np.int32)
+        ab = np.ascontiguousarray(ec_abundance, dtype=np.float64)
+        ep = np.ascontiguousarray(ec_allele_ptr, dtype=np.int32)
+        ea = np.ascontiguousarray(ec_alleles, dtype=np.int32)
+        kept = np.zeros(len(ln), dtype=np.uint8)
+        span = np.zeros(2 * len(ln), dtype=np.int32)
+        L.check(L.lib().t1k_groups_ec_filter(self.h, len(ln), L.ptr(ln), L.ptr(ab), L.ptr(ep), L.ptr(ea), len(ep) - 1, L.ptr(kept), L.ptr(span)))
+        return kept, span
+
     def fetch(self):
         """-> (ptr[n_groups+1], entries, assigned_fragments)"""
         ng, ne, na = C.c_int32(0), C.c_uint64(0), C.c_uint64(0)

@@ -229,11 +229,14 @@ class Genotyper:
                                comm.h if comm is not None else None, None)
         out = dict(abundance=np.zeros(ref.n), ec_abundance=np.zeros(ref.n),
                    equivalent_class=np.zeros(ref.n, dtype=np.int32), missing_coverage=np.zeros(ref.n, dtype=np.int32),
-                   fragment_assigned=np.zeros(n, dtype=np.uint8))
+                   fragment_assigned=np.zeros(n, dtype=np.uint8),
+                   # Genotyper::RemoveLowLikelihoodAlleleInEquivalentClass (Genotyper.cpp:647): members that stay in their class
+                   allele_kept=np.zeros(ref.n, dtype=np.uint8), allele_span=np.zeros(2 * ref.n, dtype=np.int32))
         res = L.GenotypeResult()
         res.abundance, res.ec_abundance = L.ptr(out["abundance"]), L.ptr(out["ec_abundance"])
         res.equivalent_class, res.missing_coverage = L.ptr(out["equivalent_class"]), L.ptr(out["missing_coverage"])
         res.fragment_assigned = L.ptr(out["fragment_assigned"])
+        res.allele_kept, res.allele_span = L.ptr(out["allele_kept"]), L.ptr(out["allele_span"])
         L.check(L.lib().t1k_genotype(self.refSet.h, L.ptr(r1), L.ptr(r2), stride, n, C.byref(prm), C.byref(res)))
         for k, _ in res._fields_:
             v = getattr(res, k)

@@ -233,6 +233,8 @@ def parse_harness(path):
                 out["q"].append((int(t[2]), float.fromhex(t[3]), float.fromhex(t[4]), int(t[5]), int(t[6])))
             elif k == "C":
                 out["cov"][int(t[1])] = np.asarray(t[3:], dtype=np.int32)
+            elif k == "K":
+                out["kept"] = [int(x) for x in t[1:]]
             else:
                 cur["ov"].append(tuple(int(x) for x in t[:10]) + (float.fromhex(t[10]),))
     return out
