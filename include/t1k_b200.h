@@ -72,6 +72,18 @@ int t1k_ref_n_alleles(const T1KRef *ref);
 int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const uint32_t *len,
                      const int32_t *weight, uint32_t n_reads, T1KAssignment **out);
 void t1k_assignment_destroy(T1KAssignment *a);
+/* Asynchronous variant ("async variant with stream / double-buffered pinned staging").  Returns at once; the batch
+ * is aligned on the reference's stream by a worker of the library while the caller de-duplicates and stages the next batch —
+ * what the pthread fan-out of Genotyper.cpp:481-507 gives the reference.  Jobs of one T1KRef run in submission order (coverage
+ * and results are those of the same sequence of synchronous calls).  The input arrays must stay valid and unchanged until
+ * t1k_assign_wait returns; t1k_pinned_alloc gives page-locked staging buffers so that the upload is a true DMA.
+ * t1k_assign_wait blocks until the job is done, hands out its result and status (error text in t1k_last_error) and frees the job. */
+typedef struct T1KAssignJob T1KAssignJob;
+int t1k_assign_batch_async(T1KRef *ref, const char *bases, const uint64_t *off, const uint32_t *len, const int32_t *weight,
+                           uint32_t n_reads, T1KAssignJob **job);
+int t1k_assign_wait(T1KAssignJob *job, T1KAssignment **out);
+int t1k_pinned_alloc(uint64_t bytes, void **p);
+void t1k_pinned_free(void *p);
 /* Host copy, per read in the reference's output order (`assign` of SeqSet.hpp:2300):
  * row_ptr[n_reads+1] (caller-allocated), ret[n_reads] = AssignRead's return value (count or -1),
  * records: call once with records==NULL to get *total, then with a buffer of *total entries. */

@@ -27,7 +27,8 @@ EXPORTS = ["t1k_last_error", "t1k_device_count", "t1k_ref_create", "t1k_ref_dest
            "t1k_em_run", "t1k_genotype", "t1k_comm_unique_id", "t1k_comm_create", "t1k_comm_destroy",
            "t1k_coverage_allreduce", "t1k_groups_create", "t1k_groups_destroy", "t1k_groups_add_fragments",
            "t1k_groups_serialize", "t1k_groups_merge", "t1k_groups_fetch", "t1k_em_partition",
-           "t1k_filter_create", "t1k_filter_destroy", "t1k_filter_batch", "t1k_align_info_batch", "t1k_dpx_peak", "t1k_groups_ec_filter"]
+           "t1k_filter_create", "t1k_filter_destroy", "t1k_filter_batch", "t1k_align_info_batch", "t1k_dpx_peak", "t1k_groups_ec_filter",
+           "t1k_assign_batch_async", "t1k_assign_wait", "t1k_pinned_alloc", "t1k_pinned_free"]
 
 UNIQUE_ID_BYTES = 128
 
@@ -113,6 +114,11 @@ def lib():
         L.t1k_ref_n_alleles.argtypes = [C.c_void_p]
         L.t1k_assign_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                        C.POINTER(C.c_void_p)]
+        L.t1k_assign_batch_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.t1k_assign_wait.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.t1k_pinned_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
+        L.t1k_pinned_free.argtypes = [C.c_void_p]
+        L.t1k_pinned_free.restype = None
         L.t1k_assignment_destroy.argtypes = [C.c_void_p]
         L.t1k_assignment_destroy.restype = None
         L.t1k_assignment_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include <chrono>
+#include <condition_variable>
 #include <mutex>
 #include <numeric>
 #include <string>
@@ -217,6 +218,8 @@ struct T1KRef {
   bool covDirty = true;
   PinnedMem pinEntries[2];   // D2H staging of pairing rows (double-buffered by t1k_genotype's chunk pipeline)
   PinnedMem pinSend, pinRecv, pinRecv2; // read-group tables on their way to / from the peers
+  // t1k_assign_batch_async: jobs of one reference run in submission order
+  std::mutex qMu; std::condition_variable qCv; uint64_t qNext = 0, qServing = 0;
   ~T1KRef() { if (stream) cudaStreamDestroy(stream); }
 };
 
@@ -543,6 +546,50 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   *out = a;
   return T1K_OK;
 }
+
+struct T1KAssignJob {
+  std::thread worker;
+  int rc = T1K_OK;
+  std::string err;
+  T1KAssignment *result = nullptr;
+};
+
+int t1k_assign_batch_async(T1KRef *ref, const char *bases, const uint64_t *off, const uint32_t *len, const int32_t *weight, uint32_t n,
+                           T1KAssignJob **job) {
+  if (!ref || !job || (n > 0 && (!bases || !off || !len || !weight))) return fail(T1K_ERR_ARG, "t1k_assign_batch_async: bad argument");
+  T1KAssignJob *j = new T1KAssignJob;
+  uint64_t ticket;
+  { std::lock_guard<std::mutex> lk(ref->qMu); ticket = ref->qNext++; }
+  j->worker = std::thread([=]() {
+    { std::unique_lock<std::mutex> lk(ref->qMu); ref->qCv.wait(lk, [&] { return ref->qServing == ticket; }); }
+    j->rc = t1k_assign_batch(ref, bases, off, len, weight, n, &j->result);
+    if (j->rc) j->err = g_err;
+    { std::lock_guard<std::mutex> lk(ref->qMu); ++ref->qServing; }
+    ref->qCv.notify_all();
+  });
+  *job = j;
+  return T1K_OK;
+}
+
+int t1k_assign_wait(T1KAssignJob *job, T1KAssignment **out) {
+  if (!job || !out) return fail(T1K_ERR_ARG, "t1k_assign_wait: bad argument");
+  if (job->worker.joinable()) job->worker.join();
+  const int rc = job->rc;
+  *out = job->result;
+  if (rc) g_err = job->err;
+  delete job;
+  return rc;
+}
+
+int t1k_pinned_alloc(uint64_t bytes, void **p) {
+  if (!p) return fail(T1K_ERR_ARG, "t1k_pinned_alloc: bad argument");
+  *p = nullptr;
+  int dev = 0;
+  if (int rc = pick_device(-1, &dev)) return rc;
+  CK(cudaMallocHost(p, std::max<uint64_t>(bytes, 16)));
+  return T1K_OK;
+}
+void t1k_pinned_free(void *p) { if (p) cudaFreeHost(p); }
 
 int t1k_assignment_stats(const T1KAssignment *a, T1KAssignStats *out) {
   if (!a || !out) return fail(T1K_ERR_ARG, "t1k_assignment_stats: bad argument");

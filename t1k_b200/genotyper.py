@@ -70,6 +70,30 @@ class Assignment:
         return {k: getattr(s, k) for k, _ in s._fields_}
 
 
+class AssignJob:
+    """A batch in flight (t1k_assign_batch_async); the input arrays are kept alive until wait()."""
+
+    def __init__(self, handle, n, owner, keep):
+        self.h, self.n, self._owner, self._keep = handle, n, owner, keep
+
+    def wait(self) -> Assignment:
+        h = C.c_void_p()
+        job, self.h = self.h, None
+        try:
+            L.check(L.lib().t1k_assign_wait(job, C.byref(h)))
+        finally:
+            self._keep = None
+        return Assignment(h, self.n, self._owner)
+
+    def __del__(self):
+        if getattr(self, "h", None):       # never waited for: join and drop the result
+            h = C.c_void_p()
+            L.lib().t1k_assign_wait(self.h, C.byref(h))
+            if h:
+                L.lib().t1k_assignment_destroy(h)
+            self.h = None
+
+
 class SeqSet:
     """Allele reference + k-mer index + base coverage on one GPU (SeqSet.hpp)."""
 
@@ -101,6 +125,15 @@ class SeqSet:
         h = C.c_void_p()
         L.check(L.lib().t1k_assign_batch(self.h, L.ptr(bases), L.ptr(off), L.ptr(lens), L.ptr(w), n, C.byref(h)))
         return Assignment(h, n, self)
+
+    def AssignReadAsync(self, reads, weights=None):
+        """t1k_assign_batch_async: returns a job at once; job.wait() -> Assignment.  Jobs of one SeqSet run in submission order."""
+        bases, off, lens = _reads_to_batch(reads)
+        n = len(lens)
+        w = np.ones(n, dtype=np.int32) if weights is None else np.ascontiguousarray(weights, dtype=np.int32)
+        j = C.c_void_p()
+        L.check(L.lib().t1k_assign_batch_async(self.h, L.ptr(bases), L.ptr(off), L.ptr(lens), L.ptr(w), n, C.byref(j)))
+        return AssignJob(j, n, self, (bases, off, lens, w))
 
     def ReadAssignmentToFragmentAssignment(self, assignment: Assignment, end1, end2=None, has_n=None, max_assign=2000,
                                            with_assigned=False):

@@ -387,3 +387,31 @@ def test_hla_scale_properties():
     row, ent = ss.ReadAssignmentToFragmentAssignment(a, e1, e2, None, 2000)
     assert (np.diff(row) > 0).all()
     assert (ent["weight"] == 1.0).all() and (ent["qual"] == 1.0).all()
+
+
+def test_async_assign_batches_equal_the_synchronous_calls():
+    """t1k_assign_batch_async / t1k_assign_wait (the async variant): two batches in flight give the records, return
+    values and accumulated coverage of the same two synchronous calls; a failing batch reports its error at wait()."""
+    factory, sim, relax, kw = WORKLOADS[sorted(WORKLOADS)[0]]
+    recs = factory()
+    ref = RefSet(recs)
+    kept, _ = O.collapse_reference(recs)
+    r1, r2 = W.reads_for(kept, 300, seed=91, **kw)
+    uniq, w, _, _ = uniq_batch(r1, r2)
+    half = len(uniq) // 2
+    ss = SeqSet(ref, sim, relax)
+    a0, a1 = ss.AssignRead(uniq[:half], w[:half]), ss.AssignRead(uniq[half:], w[half:])
+    want = [a0.fetch(), a1.fetch()]
+    cov = ss.GetBaseCoverage()
+    ss2 = SeqSet(ref, sim, relax)
+    j0 = ss2.AssignReadAsync(uniq[:half], w[:half])
+    j1 = ss2.AssignReadAsync(uniq[half:], w[half:])          # queued behind j0 while the host is free
+    got = [j0.wait().fetch(), j1.wait().fetch()]
+    for g, x in zip(got, want):
+        assert np.array_equal(g[0], x[0]) and np.array_equal(g[1], x[1]) and np.array_equal(g[2], x[2])
+    assert np.array_equal(ss2.GetBaseCoverage(), cov)
+    bad = ss2.AssignReadAsync([b"ACGTACGTACGTXACGTACGTACGT"], np.ones(1, dtype=np.int32))
+    with pytest.raises(T1KError):
+        bad.wait()
+    ok = ss2.AssignReadAsync(uniq[:4], w[:4]).wait().fetch()        # the queue keeps working after a failed job
+    assert np.array_equal(ok[2], want[0][2][:len(ok[2])])
