@@ -230,7 +230,7 @@ struct T1KAssignment {
   DevMem store, storeCtr, readOff, readCnt, readRet, readTop, dMaxCnt;
   u64 storeCap = 0, storeUsed = 0;
   u32 maxCnt = 0;
-  unsigned long long stats[4] = {0, 0, 0, 0};
+  unsigned long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float msKernel = 0;
   u32 launches = 0;
 };
@@ -367,7 +367,7 @@ int setup_assign_launch(T1KRef *r, int maxLen) {
   CK(r->qCtr.alloc(4 * sizeof(unsigned int)));
   CK(r->workCtr.alloc(sizeof(unsigned int)));
   CK(r->errFlag.alloc(sizeof(int)));
-  CK(r->stats.alloc(4 * sizeof(unsigned long long)));
+  CK(r->stats.alloc(8 * sizeof(unsigned long long)));
   return T1K_OK;
 }
 
@@ -417,7 +417,7 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   CK(cudaMemcpyAsync(dLen.p, len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dW.p, weight, (size_t)n * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(ref->errFlag.p, 0, sizeof(int), st));
-  CK(cudaMemsetAsync(ref->stats.p, 0, 4 * sizeof(unsigned long long), st));
+  CK(cudaMemsetAsync(ref->stats.p, 0, 8 * sizeof(unsigned long long), st));
   CK(cudaMemsetAsync(a->storeCtr.p, 0, 8, st));
   k_pack_reads<<<(n + 127) / 128, 128, 0, st>>>(dBases.as<char>(), dOff.as<u64>(), dLen.as<u32>(), n, rwords, planes.as<u64>(), len16.as<u16>(),
                                                   ref->errFlag.as<int>());
@@ -450,6 +450,10 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   P.queueMargin = (u32)std::min<size_t>(ref->dqCap / 2, ref->scratchWarps * 2048);
   P.workBegin = 0; P.workEnd = 0;
   { const char *env = getenv("T1K_NO_FAST"); P.noFast = (env && atoi(env) != 0) ? 1 : 0; }
+  { const char *env = getenv("T1K_NO_SHARE"); P.noShare = (env && atoi(env) != 0) ? 1 : 0; }
+  // the leader list of k_defer_group lives in the AlignItem queue's storage (k_passes fills that queue after k_defer_copy is done)
+  const bool canGroup = !P.noShare && (size_t)ref->aqCap * sizeof(AlignItem) >= (size_t)ref->dqCap * sizeof(u32) && ref->dqCap > 0;
+  P.lead = canGroup ? (u32 *)ref->aq.p : nullptr; P.leadCtr = ref->qCtr.as<unsigned int>() + 3;
   P.workCtr = ref->workCtr.as<unsigned int>();
   P.hitBuf = ref->hitBuf.as<u32>(); P.hitCap = ref->hitCap; P.seedCap = ref->seedCap;
   DevMem workList;
@@ -484,8 +488,10 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
         default: k_seed<2><<<ref->gridBlocks, WARPS_PER_BLOCK * 32, smem, st>>>(P); break;
       }
       CK(cudaGetLastError());
+      if (P.lead) { k_defer_group<<<ref->nSM * 9, WARPS_PER_BLOCK * 32, 0, st>>>(P); CK(cudaGetLastError()); }     // (no per-lane scratch: full occupancy)
       k_deferred<<<ref->gridBlocks, WARPS_PER_BLOCK * 32, 0, st>>>(P);
       CK(cudaGetLastError());
+      if (P.lead) { k_defer_copy<<<ref->nSM * 8, 256, 0, st>>>(P); CK(cudaGetLastError()); a->launches += 2; }
       unsigned int taken = 0;
       CK(cudaMemcpyAsync(&taken, ref->workCtr.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
@@ -541,6 +547,7 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   a->storeUsed = used;
   CK(cudaMemcpy(&a->maxCnt, a->dMaxCnt.p, 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(a->stats, ref->stats.p, sizeof(a->stats), cudaMemcpyDeviceToHost));
+  if (pt.on) fprintf(stderr, "[t1k timing]   assign: deferred items %llu, distinct within their warp %llu; align items %llu, distinct %llu\n", a->stats[4], a->stats[5], a->stats[6], a->stats[7]);
   pt.lap("  assign: tail");
   guard.a = nullptr;
   *out = a;
@@ -1572,7 +1579,7 @@ int t1k_align_info_batch(T1KRef *ref, const char *bases, const uint64_t *off, co
   CK(cudaMemcpyAsync(dIdx.p, read_idx, (size_t)n_items * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dSlot.p, slot.data(), (size_t)n_items * 8, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(ref->errFlag.p, 0, sizeof(int), st));
-  CK(cudaMemsetAsync(ref->stats.p, 0, 4 * sizeof(unsigned long long), st));
+  CK(cudaMemsetAsync(ref->stats.p, 0, 8 * sizeof(unsigned long long), st));
   k_pack_reads<<<(n_reads + 127) / 128, 128, 0, st>>>(dBases.as<char>(), dOff.as<u64>(), dLen.as<u32>(), n_reads, rwords, planes.as<u64>(), len16.as<u16>(),
                                                         ref->errFlag.as<int>());
   CK(cudaGetLastError());

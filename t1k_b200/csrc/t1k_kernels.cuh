@@ -75,6 +75,7 @@ struct AssignParams {
   ReadState *state;        // [reads of the batch]
   u32 *stabBuf;            // [reads][2 strands][256]: seed tables of the strands that deferred something (k_deferred reads them)
   DeferItem *dq; unsigned int *dqCtr; u32 dqCap;
+  u32 *lead; unsigned int *leadCtr;                     // queue indices of the distinct deferred items (NULL: no grouping); aliases aq, which is idle then
   AlignItem *aq; unsigned int *aqCtr; u32 aqCap;
   AlignItem *dpq; unsigned int *dpqCtr; u32 dpqCap;     // AlignItems whose alignment needs the band DP (k_align -> k_align_dp)
   u8 *laneScratch;         // per lane scr_bytes(Q.maxLen)
@@ -84,6 +85,7 @@ struct AssignParams {
   int hitCap;              // hits per allele the hit-list path holds
   int seedCap;             // seeds per strand the shared-memory tables hold (>= longest read - k + 1, multiple of 32, >= 64)
   int noFast;              // 1: every allele goes through the hit-list path (A/B switch, T1K_NO_FAST)
+  int noShare;             // 1: k_deferred / k_align evaluate every item on its own (A/B switch, T1K_NO_SHARE)
   u32 queueMargin;         // k_seed takes no new read-end once the DeferItem queue is this close to full
 };
 
@@ -556,14 +558,89 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) k_seed(AssignParam
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_deferred: thread per DeferItem
+// The deferred alleles in three steps.  The items that are queued together are mostly consecutive alleles of ONE read-end (a
+// tile's deferred lanes are queued in lane order), and the alleles of a gene are nearly identical: inside the window the read
+// covers, most of them hold the very same bases (KIR-DNA-like set: 5.4 items per distinct one within a warp).  Everything
+// diag_fast + extend_cand read of an allele lies inside that window (plus its length), so items whose (read-end, strand,
+// diagonal, hit counts, allele length, window bases[, exon mask]) are EQUAL — compared word for word, the hash only forms the
+// groups — get the same candidate up to seqIdx.  Identical lanes of a warp cost what one lane costs, so the saving comes from
+// COMPACTING the distinct items:
+//   k_defer_group  warp per 32 consecutive items: groups equal items, the lowest lane of a group becomes its leader; leaders
+//                  are appended to a dense list, a member keeps the queue index of its leader (n) and is flagged (pass bit 31)
+//   k_deferred     thread per leader: the full evaluation, candidate into its slot; status and strand key left in the item
+//   k_defer_copy   thread per member: the leader's candidate with its own seqIdx
+// T1K_NO_SHARE=1 (P.noShare): k_deferred alone over every item (A/B switch).
+__device__ __forceinline__ u64 mix64(u64 h, u64 v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); return h * 0xff51afd7ed558ccdull; }
+constexpr u32 DEFER_MEMBER = 0x80000000u;
+
+__global__ void __launch_bounds__(128) k_defer_group(AssignParams P) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nThreads = (size_t)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const u32 nItems = min(*P.dqCtr, P.dqCap);
+  const RefView &R = P.R;
+  for (size_t i0 = tid - lane; i0 < nItems; i0 += nThreads) {        // warp-uniform: 32 consecutive items per round
+    const size_t i = i0 + lane;
+    DeferItem it;
+    bool valid = i < nItems;
+    if (valid) { it = P.dq[i]; valid = it.read != 0xffffffffu; }
+    if (!valid) { it.read = 0xffffffffu; it.seqIdx = 0; it.d0 = 0; it.n = it.onDiag = it.far = it.at = it.pass = 0; }
+    // ---- signature of what the evaluation reads
+    u64 w[5] = {0, 0, 0, 0, 0}, x[5] = {0, 0, 0, 0, 0};
+    int clen = 0;
+    bool shareable = false;
+    u64 h = ~(u64)lane;
+    if (valid) {
+      const uint4 mt = *reinterpret_cast<const uint4 *>(R.meta + it.seqIdx);
+      const u64 w0 = (u64)mt.x | ((u64)mt.y << 32);
+      clen = (int)mt.z;
+      const int len = P.Q.len[it.read];
+      const int pLo = it.d0 < 0 ? -it.d0 : 0, pHi = imin(len, clen - it.d0), Wn = pHi - pLo;
+      if (Wn >= KMER && Wn <= 160) {
+        shareable = true;
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+          if (32 * j < Wn) {
+            w[j] = fetch32(R.seq2 + w0, pLo + it.d0 + 32 * j) & lowmask2(Wn - 32 * j);
+            if (R.relax) x[j] = fetch32(R.ex2 + w0, pLo + it.d0 + 32 * j) & lowmask2(Wn - 32 * j);
+          }
+        h = mix64(mix64((u64)it.read << 1 | it.pass, (u64)(u32)it.d0 | ((u64)it.n << 32)), (u64)it.onDiag | ((u64)it.far << 20) | ((u64)(u32)clen << 40));
+#pragma unroll
+        for (int j = 0; j < 5; ++j) h = mix64(h, w[j] ^ (x[j] * 0x9e3779b97f4a7c15ull));
+        h &= ~(1ull << 63);              // (never equal to an unshareable lane's ~lane)
+      }
+    }
+    const unsigned grp = __match_any_sync(FULL, h);
+    int leader = __ffs(grp) - 1;
+    {
+      // word-for-word check against the group's lowest lane; a lane that differs (hash collision) evaluates for itself
+      bool same = shareable;
+      same &= __shfl_sync(FULL, it.read, leader) == it.read && __shfl_sync(FULL, it.pass, leader) == it.pass && __shfl_sync(FULL, it.d0, leader) == it.d0;
+      same &= __shfl_sync(FULL, it.n, leader) == it.n && __shfl_sync(FULL, it.onDiag, leader) == it.onDiag && __shfl_sync(FULL, it.far, leader) == it.far;
+      same &= __shfl_sync(FULL, clen, leader) == clen;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) { same &= __shfl_sync(FULL, w[j], leader) == w[j]; same &= __shfl_sync(FULL, x[j], leader) == x[j]; }
+      if (!same) leader = lane;
+    }
+    const bool isLeader = valid && leader == lane;
+    const unsigned bal = __ballot_sync(FULL, isLeader);
+    unsigned int base = 0;
+    if (lane == 0 && bal) base = atomicAdd(P.leadCtr, (unsigned int)__popc(bal));
+    base = __shfl_sync(FULL, base, 0);
+    if (isLeader) P.lead[base + __popc(bal & ((1u << lane) - 1))] = (u32)i;
+    else if (valid) { P.dq[i].n = (u32)(i0 + leader); P.dq[i].pass = it.pass | DEFER_MEMBER; }
+  }
+  if (tid == 0) atomicAdd(P.O.stats + 4, (unsigned long long)nItems);
+}
+
+// thread per leader (P.lead != NULL) or per item
 __global__ void __launch_bounds__(128) k_deferred(AssignParams P) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nThreads = (size_t)gridDim.x * blockDim.x;
-  const u32 nItems = min(*P.dqCtr, P.dqCap);
+  const u32 nWork = P.lead ? *P.leadCtr : min(*P.dqCtr, P.dqCap);
   const LaneScratch S = lane_scratch(P.laneScratch + tid * scr_bytes(P.Q.maxLen), P.Q.maxLen);
   const RefView &R = P.R;
   int err = 0;
-  for (size_t i = tid; i < nItems; i += nThreads) {
+  for (size_t k = tid; k < nWork; k += nThreads) {
+    const size_t i = P.lead ? P.lead[k] : k;
     const DeferItem it = P.dq[i];
     if (it.read == 0xffffffffu) continue;
     const int strand01 = it.pass == 0 ? 1 : 0;
@@ -577,17 +654,48 @@ __global__ void __launch_bounds__(128) k_deferred(AssignParams P) {
     const int df = diag_fast(R, Q, strand01, (int)it.seqIdx, (int)it.n, it.d0, (int)it.onDiag, (int)it.far,
                              P.stabBuf + ((size_t)it.read * 2 + it.pass) * 256, false, c, em, laneKey, lcMemo, S, err);
     if (df == DF_DECLINED) err |= ERR_SCRATCH;        // (cannot happen: the hit-count certificate passed in hot mode)
-    if (df == DF_DONE && em) {
+    const bool done = df == DF_DONE && em;
+    if (done) {
       if (!(c.flags & CF_PRE)) { extend_cand<false>(R, Q, c, S, err); c.flags |= CF_PRE; }     // a long or dirty overhang
       *slot = c;
       if (!(c.flags & CF_SEP)) {
-        const u64 k = ord_word(cand_key_pre(c), (int)it.at);
-        atomicMin((unsigned long long *)((c.flags & CF_RET) ? &st->rOrd[it.pass] : &st->fOrd[it.pass]), (unsigned long long)k);
+        const u64 kk = ord_word(cand_key_pre(c), (int)it.at);
+        atomicMin((unsigned long long *)((c.flags & CF_RET) ? &st->rOrd[it.pass] : &st->fOrd[it.pass]), (unsigned long long)kk);
       }
     } else *slot = void_cand(it.seqIdx, strand01);
     if (laneKey) atomicMax((unsigned long long *)&st->bestKey, (unsigned long long)laneKey);
+    if (P.lead) {                                     // what the members of this leader's group need besides the candidate
+      DeferItem *o = P.dq + i;
+      o->n = done ? 1u : 0u; o->onDiag = (u32)laneKey; o->far = (u32)(laneKey >> 32);
+    }
   }
   if (err) atomicOr(P.O.err, err);
+  if (tid == 0) atomicAdd(P.O.stats + 5, (unsigned long long)nWork);
+}
+
+__global__ void __launch_bounds__(256) k_defer_copy(AssignParams P) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nThreads = (size_t)gridDim.x * blockDim.x;
+  const u32 nItems = min(*P.dqCtr, P.dqCap);
+  for (size_t i = tid; i < nItems; i += nThreads) {
+    const DeferItem it = P.dq[i];
+    if (it.read == 0xffffffffu || !(it.pass & DEFER_MEMBER)) continue;
+    const u32 pass = it.pass & ~DEFER_MEMBER;
+    const DeferItem L = P.dq[it.n];                   // same read-end, strand and diagonal
+    ReadState *st = P.state + it.read;
+    const Cand *cands = P.candPool + st->candOff;
+    Cand *slot = P.candPool + st->candOff + it.at;
+    if (L.n) {
+      Cand c = cands[L.at];
+      c.seqIdx = (int32_t)it.seqIdx;
+      *slot = c;
+      if (!(c.flags & CF_SEP)) {
+        const u64 kk = ord_word(cand_key_pre(c), (int)it.at);
+        atomicMin((unsigned long long *)((c.flags & CF_RET) ? &st->rOrd[pass] : &st->fOrd[pass]), (unsigned long long)kk);
+      }
+    } else *slot = void_cand(it.seqIdx, pass == 0 ? 1 : 0);
+    const u64 keyL = (u64)L.onDiag | ((u64)L.far << 32);
+    if (keyL) atomicMax((unsigned long long *)&st->bestKey, (unsigned long long)((keyL & ~(0xFFFFFFull << 1)) | ((u64)(0xFFFFFFu - it.seqIdx) << 1)));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------

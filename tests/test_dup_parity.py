@@ -12,7 +12,6 @@ import pytest
 import dup_workloads as D
 import oracle_py as O
 from t1k_b200.refset import RefSet
-from test_host_logic import emu  # noqa: F401  (fixture)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = {name: (recs, reads, sim, relax) for name, recs, reads, sim, relax in D.cases()}
@@ -64,7 +63,7 @@ def test_oracle_matches_reference_on_duplications(name):
 
 @pytest.mark.parametrize("fast", [1, 0])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_lane_code_matches_reference_on_duplications(emu, name, fast):  # noqa: F811
+def test_lane_code_matches_reference_on_duplications(emu, name, fast):
     recs, reads, sim, relax = CASES[name]
     g = _golden(name)
     out, cov = _emu_run(emu, recs, reads, sim, relax, int(g["weight"]), fast)
@@ -75,7 +74,7 @@ def test_lane_code_matches_reference_on_duplications(emu, name, fast):  # noqa: 
 
 
 @pytest.mark.skipif(not os.path.exists(O.REF_HARNESS), reason="reference harness not built")
-def test_lane_code_fuzz_against_reference_harness(emu):  # noqa: F811
+def test_lane_code_fuzz_against_reference_harness(emu):
     """Seeded fuzz of the emulation against the live reference: duplication lengths, tandem units, thresholds."""
     import sys
     sys.path.insert(0, os.path.join(HERE, "golden"))
@@ -142,7 +141,7 @@ def test_oracle_matches_reference_on_long_reads(name):
 
 
 @pytest.mark.parametrize("name", sorted(LONG))
-def test_lane_code_matches_reference_on_long_reads(emu, name):  # noqa: F811
+def test_lane_code_matches_reference_on_long_reads(emu, name):
     recs, reads, sim, relax = LONG[name]
     g = _golden_long(name)
     out, cov = _emu_run(emu, recs, reads, sim, relax, int(g["weight"]))

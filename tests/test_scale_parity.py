@@ -10,7 +10,6 @@ import pytest
 
 import bench
 import oracle_py as O
-from test_host_logic import emu  # noqa: F401  (fixture)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -27,7 +26,7 @@ def _load(config):
 
 
 @pytest.mark.parametrize("config", [3, 4])
-def test_oracle_and_lane_code_match_the_reference_at_config_scale(emu, config):  # noqa: F811
+def test_oracle_and_lane_code_match_the_reference_at_config_scale(emu, config):
     g = _load(config)
     cfg = bench.CONFIGS[config]
     recs, ref = bench.make_reference(config)
@@ -54,9 +53,13 @@ def test_oracle_and_lane_code_match_the_reference_at_config_scale(emu, config): 
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("no_share", ["0", "1"])
 @pytest.mark.parametrize("config", [3, 4])
-def test_device_matches_the_reference_at_config_scale(config):
+def test_device_matches_the_reference_at_config_scale(config, no_share, monkeypatch):
+    """no_share = 1: every deferred allele / full-read alignment evaluated on its own instead of once per group of alleles with
+    identical window content (T1K_NO_SHARE, the A/B switch of the sharing in k_deferred / k_align)"""
     from t1k_b200.genotyper import Genotyper
+    monkeypatch.setenv("T1K_NO_SHARE", no_share)
     g = _load(config)
     cfg = bench.CONFIGS[config]
     recs, ref = bench.make_reference(config)
