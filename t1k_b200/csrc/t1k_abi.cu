@@ -22,6 +22,7 @@
 #include "t1k_pair.cuh"
 #include "t1k_filter.cuh"
 #include "t1k_alninfo.cuh"
+#include "t1k_ingest.cuh"
 
 using namespace t1k;
 
@@ -29,6 +30,9 @@ namespace {
 
 thread_local std::string g_err;
 thread_local bool g_emTrusted = false;
+// columns of the EM's matrix handed over by t1k_genotype (see EquivalenceClasses::inPtr): column e = rows[beg[e] .. end[e])
+struct EmColumns { const int64_t *beg, *end; const int32_t *rows; size_t nRows; };
+thread_local const EmColumns *g_emCols = nullptr;
 
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
@@ -205,6 +209,8 @@ struct T1KRef {
   DevMem seq2, n2, ex2, dWordOff, dLen, dHasN, dMeta, dSimThr, kinfo, entries, covDiff, covPoint, covFinal, dCovOff;
   RefView R;
   cudaStream_t stream = nullptr;
+  cudaStream_t copyStream = nullptr;   // D2H of a chunk's fragment rows while the next chunk's kernels run (t1k_genotype)
+  cudaStream_t prepStream = nullptr;   // H2D of the next chunk's raw reads (device-side ingest)
   // launch state of the AssignRead kernels (k_seed / k_deferred / k_passes / k_align), sized on first use
   DevMem candPool, laneScratch, hitBuf, workCtr, errFlag, stats, dq, aq, qCtr;
   u32 candCap = 0, dqCap = 0, aqCap = 0;
@@ -220,7 +226,7 @@ struct T1KRef {
   PinnedMem pinSend, pinRecv, pinRecv2; // read-group tables on their way to / from the peers
   // t1k_assign_batch_async: jobs of one reference run in submission order
   std::mutex qMu; std::condition_variable qCv; uint64_t qNext = 0, qServing = 0;
-  ~T1KRef() { if (stream) cudaStreamDestroy(stream); }
+  ~T1KRef() { if (stream) cudaStreamDestroy(stream); if (copyStream) cudaStreamDestroy(copyStream); if (prepStream) cudaStreamDestroy(prepStream); }
 };
 
 struct T1KAssignment {
@@ -293,6 +299,8 @@ int t1k_ref_create(const T1KRefDesc *d, T1KRef **out) {
   if (e == cudaSuccess) e = cudaMemset(r->covDiff.p, 0, covBytes);
   if (e == cudaSuccess) e = cudaMemset(r->covPoint.p, 0, covBytes);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->copyStream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->prepStream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete r; return fail(T1K_ERR_CUDA, std::string("t1k_ref_create: ") + cudaGetErrorString(e)); }
   RefView &R = r->R;
   R.seq2 = r->seq2.as<u64>(); R.n2 = r->n2.as<u64>(); R.ex2 = r->ex2.as<u64>();
@@ -383,58 +391,38 @@ std::string decode_err(int err) {
 
 }  // namespace
 
-extern "C" {
+namespace {
+// Packed read-ends resident on the device: planes / lengths as k_pack_reads (or the ingest kernels) leave them for
+// read_words(ref->scrLen) words per plane, weight = number of duplicates.
+struct DevReads { const u64 *planes; const u16 *len16; const int32_t *w; u32 n; };
 
-int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const uint32_t *len, const int32_t *weight,
-                     uint32_t n, T1KAssignment **out) {
-  if (!ref || !out || (n > 0 && (!bases || !off || !len || !weight))) return fail(T1K_ERR_ARG, "t1k_assign_batch: bad argument");
-  *out = nullptr;
-  CK(cudaSetDevice(ref->device));
+// SeqSet::AssignRead for the batch.  The caller has run setup_assign_launch, reset ref->errFlag / ref->stats and queued the packing
+// kernels on ref->stream (their error flags are picked up after the first round).
+int assign_core(T1KRef *ref, const DevReads &D, T1KAssignment **out) {
+  const u32 n = D.n;
   cudaStream_t st = ref->stream;
-  size_t total = 0; int maxLen = KMER;
-  for (uint32_t i = 0; i < n; ++i) {
-    if (len[i] > T1K_MAX_READ_LEN) return fail(T1K_ERR_ARG, "read longer than T1K_MAX_READ_LEN");
-    total = std::max(total, (size_t)(off[i] + len[i]));
-    maxLen = std::max(maxLen, (int)len[i]);
-  }
   PhaseTimer pt;
-  stale("t1k_assign_batch");
-  if (int rc = setup_assign_launch(ref, maxLen)) return rc;
-  pt.lap("  assign: launch setup");
   T1KAssignment *a = new T1KAssignment;
   struct Guard { T1KAssignment *a; ~Guard() { delete a; } } guard{a};
   a->ref = ref; a->device = ref->device; a->nReads = n;
-  DevMem dBases, dOff, dLen, dW, planes, len16;
-  CK(dBases.alloc(total)); CK(dOff.alloc((size_t)n * 8)); CK(dLen.alloc((size_t)n * 4)); CK(dW.alloc((size_t)n * 4));
   const int rwords = read_words(ref->scrLen);
-  CK(planes.alloc((size_t)n * 4 * rwords * 8)); CK(len16.alloc((size_t)n * 2));
   CK(a->readOff.alloc((size_t)n * 8)); CK(a->readCnt.alloc((size_t)n * 4)); CK(a->readRet.alloc((size_t)n * 4)); CK(a->readTop.alloc((size_t)n * 4));
   CK(a->storeCtr.alloc(8)); CK(a->dMaxCnt.alloc(4));
   CK(cudaMemsetAsync(a->dMaxCnt.p, 0, 4, st));
   if (n == 0) { guard.a = nullptr; *out = a; return T1K_OK; }
-  CK(cudaMemcpyAsync(dBases.p, bases, total, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(dOff.p, off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(dLen.p, len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(dW.p, weight, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(ref->errFlag.p, 0, sizeof(int), st));
-  CK(cudaMemsetAsync(ref->stats.p, 0, 8 * sizeof(unsigned long long), st));
   CK(cudaMemsetAsync(a->storeCtr.p, 0, 8, st));
-  k_pack_reads<<<(n + 127) / 128, 128, 0, st>>>(dBases.as<char>(), dOff.as<u64>(), dLen.as<u32>(), n, rwords, planes.as<u64>(), len16.as<u16>(),
-                                                  ref->errFlag.as<int>());
-  CK(cudaGetLastError());
   // record store: sized from free memory, grown (and only the deferred read-ends re-run) if it fills up
   size_t freeB = ref->memBudget;
   u64 cap = std::max<u64>((u64)n * 6144, 1u << 20);
   const u64 capMax = (u64)(freeB * 0.70) / sizeof(Rec);
   if (cap > capMax) cap = capMax;
   if (const char *envCap = getenv("T1K_STORE_RECORDS")) cap = std::max<u64>(1024, strtoull(envCap, nullptr, 10));
-  pt.lap("  assign: input alloc + pack");
   CK(a->store.alloc(cap * sizeof(Rec)));
   a->storeCap = cap;
   pt.lap("  assign: store alloc");
   AssignParams P;
   P.R = ref->R;
-  P.Q.planes = planes.as<u64>(); P.Q.rwords = rwords; P.Q.maxLen = ref->scrLen; P.Q.len = len16.as<u16>(); P.Q.weight = dW.as<int32_t>(); P.Q.workList = nullptr; P.Q.nWork = n;
+  P.Q.planes = D.planes; P.Q.rwords = rwords; P.Q.maxLen = ref->scrLen; P.Q.len = D.len16; P.Q.weight = D.w; P.Q.workList = nullptr; P.Q.nWork = n;
   P.O.store = a->store.as<Rec>(); P.O.storeCtr = a->storeCtr.as<unsigned long long>(); P.O.storeCap = cap;
   P.O.readOff = a->readOff.as<u64>(); P.O.readCnt = a->readCnt.as<u32>(); P.O.readRet = a->readRet.as<int32_t>(); P.O.readTop = a->readTop.as<u32>();
   P.O.maxCnt = a->dMaxCnt.as<u32>();
@@ -552,6 +540,47 @@ int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const 
   guard.a = nullptr;
   *out = a;
   return T1K_OK;
+}
+
+
+}  // namespace
+
+extern "C" {
+
+int t1k_assign_batch(T1KRef *ref, const char *bases, const uint64_t *off, const uint32_t *len, const int32_t *weight,
+                     uint32_t n, T1KAssignment **out) {
+  if (!ref || !out || (n > 0 && (!bases || !off || !len || !weight))) return fail(T1K_ERR_ARG, "t1k_assign_batch: bad argument");
+  *out = nullptr;
+  CK(cudaSetDevice(ref->device));
+  cudaStream_t st = ref->stream;
+  size_t total = 0; int maxLen = KMER;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (len[i] > T1K_MAX_READ_LEN) return fail(T1K_ERR_ARG, "read longer than T1K_MAX_READ_LEN");
+    total = std::max(total, (size_t)(off[i] + len[i]));
+    maxLen = std::max(maxLen, (int)len[i]);
+  }
+  PhaseTimer pt;
+  stale("t1k_assign_batch");
+  if (int rc = setup_assign_launch(ref, maxLen)) return rc;
+  pt.lap("  assign: launch setup");
+  DevMem dBases, dOff, dLen, dW, planes, len16;
+  CK(dBases.alloc(total)); CK(dOff.alloc((size_t)n * 8)); CK(dLen.alloc((size_t)n * 4)); CK(dW.alloc((size_t)n * 4));
+  const int rwords = read_words(ref->scrLen);
+  CK(planes.alloc((size_t)n * 4 * rwords * 8)); CK(len16.alloc((size_t)n * 2));
+  CK(cudaMemsetAsync(ref->errFlag.p, 0, sizeof(int), st));
+  CK(cudaMemsetAsync(ref->stats.p, 0, 8 * sizeof(unsigned long long), st));
+  if (n) {
+    CK(cudaMemcpyAsync(dBases.p, bases, total, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dOff.p, off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dLen.p, len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dW.p, weight, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    k_pack_reads<<<(n + 127) / 128, 128, 0, st>>>(dBases.as<char>(), dOff.as<u64>(), dLen.as<u32>(), n, rwords, planes.as<u64>(), len16.as<u16>(),
+                                                    ref->errFlag.as<int>());
+    CK(cudaGetLastError());
+  }
+  pt.lap("  assign: input alloc + pack");
+  const DevReads D = {planes.as<u64>(), len16.as<u16>(), dW.as<int32_t>(), n};
+  return assign_core(ref, D, out);
 }
 
 struct T1KAssignJob {
@@ -763,34 +792,67 @@ struct PairHost {
   float msKernel = 0;
   u32 launches = 1;
   uint64_t nPairRecords = 0;          // records of both mates' lists summed over the fragments (k_pair's algorithmic reads)
+  // asynchronous hand-over (t1k_genotype): the D2H copies run on the copy stream while the next chunk's kernels run; the
+  // consumer calls finish() before it reads the rows.  keep[] holds the device buffers the copies read from.
+  DevMem keep[4];
+  cudaEvent_t copied = nullptr;
+  bool pending = false;
+  int device = 0;
+  ~PairHost() { if (copied) cudaEventDestroy(copied); }
+  void unpack_flags() {
+    for (size_t i = 0; i < rowCnt.size(); ++i) { assigned[i] = (u8)(rowCnt[i] >> 31); rowCnt[i] &= 0x7fffffffu; }
+  }
+  cudaError_t finish() {
+    if (!pending) return cudaSuccess;
+    pending = false;
+    cudaSetDevice(device);
+    const cudaError_t e = cudaEventSynchronize(copied);
+    if (e == cudaSuccess) unpack_flags();
+    return e;
+  }
 };
 
+// devIn: end1 / end2 / hasN are DEVICE arrays the ingest kernels left (valid by construction); else host arrays
 int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const uint32_t *end2, const uint8_t *hasN, uint32_t nFrag,
-                   int maxAssign, bool wantOrder, PairHost &H, bool wantHash = false) {
+                   int maxAssign, bool wantOrder, PairHost &H, bool wantHash = false, bool async = false, bool devIn = false) {
   cudaStream_t st = ref->stream;
+  if (H.pending) { if (H.finish() != cudaSuccess) return fail(T1K_ERR_CUDA, "D2H of the previous chunk's fragment rows failed"); }
+  for (int k = 0; k < 4; ++k) H.keep[k].release();
   H.rowOff.assign(nFrag, 0); H.rowCnt.assign(nFrag, 0);
   H.rowHash.assign(wantHash ? 2 * (size_t)nFrag : 0, 0);
   H.assigned.assign(nFrag, 0);
   H.nEntries = 0; H.ordKey.clear(); H.ordIdx.clear(); H.nPairRecords = 0; H.msKernel = 0; H.launches = 0;
   if (nFrag == 0) return T1K_OK;
-  {
-    std::vector<u32> cnt(a->nReads);
-    if (a->nReads) CK(cudaMemcpyAsync(cnt.data(), a->readCnt.p, (size_t)a->nReads * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    for (uint32_t i = 0; i < nFrag; ++i) {
-      if (end1[i] < a->nReads) H.nPairRecords += cnt[end1[i]];
-      if (end2 && end2[i] < a->nReads) H.nPairRecords += cnt[end2[i]];
-    }
-  }
-  for (uint32_t i = 0; i < nFrag; ++i)
-    if (end1[i] >= a->nReads || (end2 && end2[i] >= a->nReads)) return fail(T1K_ERR_ARG, "t1k_pair_batch: read-end index out of range");
   DevMem dE1, dE2, dN, dRowOff, dRowCnt, dOut, dKey, dIdx, dCtr, dOutCtr, dB0, dStage, dStageKey, dStageIdx, dHash;
-  if (wantHash) CK(dHash.alloc((size_t)nFrag * 16));
-  CK(dE1.alloc((size_t)nFrag * 4));
-  CK(cudaMemcpyAsync(dE1.p, end1, (size_t)nFrag * 4, cudaMemcpyHostToDevice, st));
-  if (end2) { CK(dE2.alloc((size_t)nFrag * 4)); CK(cudaMemcpyAsync(dE2.p, end2, (size_t)nFrag * 4, cudaMemcpyHostToDevice, st)); }
-  if (hasN) { CK(dN.alloc(nFrag)); CK(cudaMemcpyAsync(dN.p, hasN, nFrag, cudaMemcpyHostToDevice, st)); }
   CK(dCtr.alloc(4)); CK(dOutCtr.alloc(8));
+  const u32 *pE1 = end1, *pE2 = end2; const u8 *pN = hasN;
+  if (devIn) {
+    CK(cudaMemsetAsync(dOutCtr.p, 0, 8, st));
+    k_pair_records<<<(nFrag + 255) / 256, 256, 0, st>>>(end1, end2, nFrag, a->readCnt.as<u32>(), dOutCtr.as<unsigned long long>());
+    CK(cudaGetLastError());
+    unsigned long long np = 0;
+    CK(cudaMemcpyAsync(&np, dOutCtr.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    H.nPairRecords = np;
+  } else {
+    {
+      std::vector<u32> cnt(a->nReads);
+      if (a->nReads) CK(cudaMemcpyAsync(cnt.data(), a->readCnt.p, (size_t)a->nReads * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      for (uint32_t i = 0; i < nFrag; ++i) {
+        if (end1[i] < a->nReads) H.nPairRecords += cnt[end1[i]];
+        if (end2 && end2[i] < a->nReads) H.nPairRecords += cnt[end2[i]];
+      }
+    }
+    for (uint32_t i = 0; i < nFrag; ++i)
+      if (end1[i] >= a->nReads || (end2 && end2[i] >= a->nReads)) return fail(T1K_ERR_ARG, "t1k_pair_batch: read-end index out of range");
+    CK(dE1.alloc((size_t)nFrag * 4));
+    CK(cudaMemcpyAsync(dE1.p, end1, (size_t)nFrag * 4, cudaMemcpyHostToDevice, st));
+    if (end2) { CK(dE2.alloc((size_t)nFrag * 4)); CK(cudaMemcpyAsync(dE2.p, end2, (size_t)nFrag * 4, cudaMemcpyHostToDevice, st)); }
+    if (hasN) { CK(dN.alloc(nFrag)); CK(cudaMemcpyAsync(dN.p, hasN, nFrag, cudaMemcpyHostToDevice, st)); }
+    pE1 = dE1.as<u32>(); pE2 = end2 ? dE2.as<u32>() : nullptr; pN = hasN ? dN.as<u8>() : nullptr;
+  }
+  if (wantHash) CK(dHash.alloc((size_t)nFrag * 16));
   CK(dRowOff.alloc((size_t)nFrag * 8)); CK(dRowCnt.alloc((size_t)nFrag * 4));
   cudaEvent_t ev0, ev1;
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
@@ -812,7 +874,7 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
     CK(cudaMemsetAsync(dOutCtr.p, 0, 8, st));
     PairParams P;
     P.R = ref->R; P.store = a->store.as<Rec>(); P.readOff = a->readOff.as<u64>(); P.readCnt = a->readCnt.as<u32>(); P.readTop = a->readTop.as<u32>();
-    P.end1 = dE1.as<u32>(); P.end2 = end2 ? dE2.as<u32>() : nullptr; P.hasN = hasN ? dN.as<u8>() : nullptr;
+    P.end1 = pE1; P.end2 = pE2; P.hasN = pN;
     P.fragBase = 0; P.nFrag = nFrag; P.maxAssign = maxAssign;
     P.out = dOut.as<PairEntry>(); P.outCap = cap; P.outCtr = dOutCtr.as<unsigned long long>(); P.rowOff = dRowOff.as<u64>();
     P.ordKey = wantOrder ? dKey.as<u64>() : nullptr; P.ordIdx = wantOrder ? dIdx.as<u32>() : nullptr;
@@ -842,6 +904,21 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
     if (attempt >= 2 || used * perEntry > (u64)(freeB * 0.9)) return fail(T1K_ERR_UNSUPPORTED, "fragment rows do not fit in device memory; use smaller batches");
     cap = used;
   }
+  H.nEntries = used;
+  if (async && !wantOrder) {
+    // the kernel is done (its counter has been read): the rows travel on the copy stream and the caller goes on
+    cudaStream_t cs = ref->copyStream;
+    if (used > 0) CK(H.pin->grow(used * sizeof(HostEntry), 0));
+    CK(cudaMemcpyAsync(H.rowOff.data(), dRowOff.p, (size_t)nFrag * 8, cudaMemcpyDeviceToHost, cs));
+    CK(cudaMemcpyAsync(H.rowCnt.data(), dRowCnt.p, (size_t)nFrag * 4, cudaMemcpyDeviceToHost, cs));
+    if (wantHash) CK(cudaMemcpyAsync(H.rowHash.data(), dHash.p, (size_t)nFrag * 16, cudaMemcpyDeviceToHost, cs));
+    if (used > 0) CK(cudaMemcpyAsync(H.entries(), dOut.p, used * sizeof(PairEntry), cudaMemcpyDeviceToHost, cs));
+    if (!H.copied) CK(cudaEventCreateWithFlags(&H.copied, cudaEventDisableTiming));
+    CK(cudaEventRecord(H.copied, cs));
+    H.keep[0].swap(dRowOff); H.keep[1].swap(dRowCnt); H.keep[2].swap(dHash); H.keep[3].swap(dOut);
+    H.pending = true; H.device = ref->device;
+    return T1K_OK;
+  }
   CK(cudaMemcpyAsync(H.rowOff.data(), dRowOff.p, (size_t)nFrag * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(H.rowCnt.data(), dRowCnt.p, (size_t)nFrag * 4, cudaMemcpyDeviceToHost, st));
   if (wantHash) CK(cudaMemcpyAsync(H.rowHash.data(), dHash.p, (size_t)nFrag * 16, cudaMemcpyDeviceToHost, st));
@@ -856,11 +933,7 @@ int pair_fragments(T1KRef *ref, T1KAssignment *a, const uint32_t *end1, const ui
   }
   CK(cudaStreamSynchronize(st));
   pt.lap("  pair: D2H");
-  H.nEntries = used;
-  for (u32 i = 0; i < nFrag; ++i) {
-    H.assigned[i] = (u8)(H.rowCnt[i] >> 31);
-    H.rowCnt[i] &= 0x7fffffffu;
-  }
+  H.unpack_flags();
   return T1K_OK;
 }
 
@@ -928,7 +1001,8 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   // CSC of the local rows with ascending group order inside every column => fixed summation order
   std::vector<int64_t> colPtr;
   std::vector<int32_t> rowIdx;
-  {
+  const EmColumns *cols = (!comm && g_emTrusted) ? g_emCols : nullptr;
+  if (!cols) {
     int hostThreads = (int)std::thread::hardware_concurrency() / (comm ? comm->world : 1);
     if (const char *env = getenv("T1K_HOST_THREADS")) hostThreads = atoi(env);
     const int32_t *colp = p->col;
@@ -939,18 +1013,26 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   cudaStream_t st;
   CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   struct StGuard { cudaStream_t s; ~StGuard() { cudaStreamDestroy(s); } } sg{st};
-  DevMem dRowPtr, dCol, dColPtr, dRowIdx, dCount, dLen, dPsum, dRc, dX0, dX1, dX2, dX3, dDiff, dTmpA, dTmpB;
+  DevMem dRowPtr, dCol, dColPtr, dColEnd, dRowIdx, dCount, dLen, dPsum, dRc, dX0, dX1, dX2, dX3, dDiff, dTmpA, dTmpB;
   // reference-order sums only where they can give the reference's bits: one GPU; a row-sharded run adds the per-rank sums in
   // another order anyway (documented tolerance 1e-5), so it takes the tree reductions
   const bool fast = p->fast_sums != 0 || comm != nullptr;
   CK(dTmpA.alloc((size_t)E * 8)); CK(dTmpB.alloc((size_t)E * 8));
-  CK(dRowPtr.alloc(((size_t)Gl + 1) * 8)); CK(dCol.alloc((size_t)nnzL * 4)); CK(dColPtr.alloc(((size_t)E + 1) * 8)); CK(dRowIdx.alloc((size_t)nnzL * 4));
+  CK(dRowPtr.alloc(((size_t)Gl + 1) * 8)); CK(dCol.alloc((size_t)nnzL * 4)); CK(dColPtr.alloc(((size_t)E + 1) * 8)); CK(dRowIdx.alloc((cols ? cols->nRows : (size_t)nnzL) * 4));
+  if (cols) CK(dColEnd.alloc((size_t)E * 8));
   CK(dCount.alloc((size_t)G * 8)); CK(dLen.alloc((size_t)E * 4)); CK(dPsum.alloc((size_t)G * 8)); CK(dRc.alloc((size_t)E * 8));
   CK(dX0.alloc((size_t)E * 8)); CK(dX1.alloc((size_t)E * 8)); CK(dX2.alloc((size_t)E * 8)); CK(dX3.alloc((size_t)E * 8)); CK(dDiff.alloc(8));
   CK(cudaMemcpyAsync(dRowPtr.p, rowPtrL.data(), ((size_t)Gl + 1) * 8, cudaMemcpyHostToDevice, st));
   if (nnzL) CK(cudaMemcpyAsync(dCol.p, p->col + k0, (size_t)nnzL * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(dColPtr.p, colPtr.data(), ((size_t)E + 1) * 8, cudaMemcpyHostToDevice, st));
-  if (nnzL) CK(cudaMemcpyAsync(dRowIdx.p, rowIdx.data(), (size_t)nnzL * 4, cudaMemcpyHostToDevice, st));
+  if (cols) {
+    CK(cudaMemcpyAsync(dColPtr.p, cols->beg, (size_t)E * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dColEnd.p, cols->end, (size_t)E * 8, cudaMemcpyHostToDevice, st));
+    if (cols->nRows) CK(cudaMemcpyAsync(dRowIdx.p, cols->rows, cols->nRows * 4, cudaMemcpyHostToDevice, st));
+  } else {
+    CK(cudaMemcpyAsync(dColPtr.p, colPtr.data(), ((size_t)E + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (nnzL) CK(cudaMemcpyAsync(dRowIdx.p, rowIdx.data(), (size_t)nnzL * 4, cudaMemcpyHostToDevice, st));
+  }
+  const int64_t *dBeg = dColPtr.as<int64_t>(), *dEnd = cols ? dColEnd.as<int64_t>() : dColPtr.as<int64_t>() + 1;
   if (G) CK(cudaMemcpyAsync(dCount.p, p->count, (size_t)G * 8, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dLen.p, p->ec_len, (size_t)E * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dX0.p, p->x0, (size_t)E * 8, cudaMemcpyHostToDevice, st));
@@ -966,10 +1048,10 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
     double *psumL = dPsum.as<double>() + g0;    // psum / count stay indexed by the global group id
     if (fast) {
       if (Gl) k_em_rowsum<<<gRow, 256, 0, st>>>(Gl, dRowPtr.as<int64_t>(), dCol.as<int32_t>(), xin, psumL);
-      k_em_colsum<<<gCol, 256, 0, st>>>(E, dColPtr.as<int64_t>(), dRowIdx.as<int32_t>(), dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
+      k_em_colsum<<<gCol, 256, 0, st>>>(E, dBeg, dEnd, dRowIdx.as<int32_t>(), dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
     } else {
       if (Gl) k_em_rowsum_seq<<<(Gl + 127) / 128, 128, 0, st>>>(Gl, dRowPtr.as<int64_t>(), dCol.as<int32_t>(), xin, psumL);
-      k_em_colsum_seq<<<(unsigned)(((size_t)E * 32 + 255) / 256), 256, 0, st>>>(E, dColPtr.as<int64_t>(), dRowIdx.as<int32_t>(), dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
+      k_em_colsum_seq<<<(unsigned)(((size_t)E * 32 + 255) / 256), 256, 0, st>>>(E, dBeg, dEnd, dRowIdx.as<int32_t>(), dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
     }
     CK(cudaGetLastError());
     // the one exchange of the EM: per-EC expected read counts summed over the row shards (NVLink all-reduce)
@@ -1266,6 +1348,74 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     unique_read_ends(reads1, reads2, stride, f0, m, T1K_MAX_READ_LEN, prepThreads, C);
     C.ms = now_ms() - t;
   };
+  // Device-side ingest (t1k_ingest.cuh): the prepare stage shrinks to one H2D copy of the chunk's raw reads, packing
+  // and de-duplication run on the device in front of the AssignRead kernels.  Reads up to 255 bases (one plane geometry
+  // whatever the reads' actual lengths); longer strides and T1K_HOST_DEDUP=1 take the host de-duplication above.
+  const bool devIngest = stride <= 255 && getenv("T1K_HOST_DEDUP") == nullptr;
+  struct DevChunk {
+    DevMem raw1, raw2;
+    u32 f0 = 0, m = 0; double ms = 0; int rc = 0; std::string err;
+  } dchunk[2];
+  auto do_prep_dev = [&](DevChunk &C, u32 f0, u32 m) {
+    const double t = now_ms();
+    C.f0 = f0; C.m = m; C.rc = 0;
+    cudaError_t e = cudaSetDevice(ref->device);
+    if (e == cudaSuccess) e = C.raw1.alloc((size_t)m * stride);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(C.raw1.p, reads1 + (size_t)f0 * stride, (size_t)m * stride, cudaMemcpyHostToDevice, ref->prepStream);
+    if (e == cudaSuccess && reads2) e = C.raw2.alloc((size_t)m * stride);
+    if (e == cudaSuccess && reads2) e = cudaMemcpyAsync(C.raw2.p, reads2 + (size_t)f0 * stride, (size_t)m * stride, cudaMemcpyHostToDevice, ref->prepStream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ref->prepStream);
+    if (e != cudaSuccess) { C.rc = T1K_ERR_CUDA; C.err = std::string("H2D of the chunk's reads: ") + cudaGetErrorString(e); }
+    C.ms = now_ms() - t;
+  };
+  // packing + de-duplication of one chunk on ref->stream -> compact batch (DevReads) + per-fragment (end1, end2, hasN) on the device
+  struct DevBatch { DevMem planesAll, lenAll, endHasN, hash, table, repOf, cnt, uid, blockSum, planes, len16, w, e1, e2, fragHasN, nUnique; u32 nU = 0; int maxLen = 0; float ms = 0; };
+  auto ingest_chunk = [&](DevChunk &C, DevBatch &B) -> int {
+    cudaStream_t st = ref->stream;
+    const int mates = reads2 ? 2 : 1;
+    const u32 nEnds = C.m * (u32)mates;
+    if (int rc = setup_assign_launch(ref, KMER)) return rc;          // (geometry for reads up to 255 bases; refined below)
+    const int RW = read_words(255);
+    u32 tab = 1024; while (tab < 2 * nEnds) tab <<= 1;
+    CK(B.planesAll.alloc((size_t)nEnds * 4 * RW * 8)); CK(B.lenAll.alloc((size_t)nEnds * 2)); CK(B.endHasN.alloc(nEnds)); CK(B.hash.alloc((size_t)nEnds * 8));
+    CK(B.table.alloc((size_t)tab * 4)); CK(B.repOf.alloc((size_t)nEnds * 4)); CK(B.cnt.alloc((size_t)nEnds * 4)); CK(B.uid.alloc((size_t)nEnds * 4));
+    const u32 nBlocks = (nEnds + 1023) / 1024;
+    CK(B.blockSum.alloc((size_t)std::max(1u, nBlocks) * 4));
+    CK(B.planes.alloc((size_t)nEnds * 4 * RW * 8)); CK(B.len16.alloc((size_t)nEnds * 2)); CK(B.w.alloc((size_t)nEnds * 4));
+    CK(B.e1.alloc((size_t)C.m * 4)); CK(B.e2.alloc((size_t)C.m * 4)); CK(B.fragHasN.alloc(C.m)); CK(B.nUnique.alloc(8));
+    CK(cudaMemsetAsync(B.table.p, 0xff, (size_t)tab * 4, st));
+    CK(cudaMemsetAsync(B.nUnique.p, 0, 8, st));
+    CK(cudaMemsetAsync(ref->errFlag.p, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(ref->stats.p, 0, 8 * sizeof(unsigned long long), st));
+    IngestParams P;
+    P.raw1 = C.raw1.as<char>(); P.raw2 = reads2 ? C.raw2.as<char>() : nullptr; P.stride = stride; P.m = C.m; P.nEnds = nEnds; P.mates = mates; P.RW = RW;
+    P.planesAll = B.planesAll.as<u64>(); P.lenAll = B.lenAll.as<u16>(); P.endHasN = B.endHasN.as<u8>(); P.hash = B.hash.as<u64>();
+    P.table = B.table.as<u32>(); P.tabMask = tab - 1; P.repOf = B.repOf.as<u32>(); P.cnt = B.cnt.as<u32>(); P.uid = B.uid.as<u32>(); P.blockSum = B.blockSum.as<u32>();
+    P.planes = B.planes.as<u64>(); P.len16 = B.len16.as<u16>(); P.w = B.w.as<int32_t>();
+    P.e1 = B.e1.as<u32>(); P.e2 = B.e2.as<u32>(); P.fragHasN = B.fragHasN.as<u8>(); P.nUnique = B.nUnique.as<u32>(); P.err = ref->errFlag.as<int>();
+    cudaEvent_t ev0, ev1;
+    CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+    struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
+    CK(cudaEventRecord(ev0, st));
+    if (nEnds) {
+      const unsigned g = (nEnds + 255) / 256;
+      k_ingest_pack<<<g, 256, 0, st>>>(P);
+      k_dedup_insert<<<g, 256, 0, st>>>(P);
+      k_dedup_resolve<<<g, 256, 0, st>>>(P);
+      k_scan_block<<<nBlocks, 1024, 0, st>>>(P);
+      k_scan_sums<<<1, 1024, 0, st>>>(P, nBlocks);
+      k_dedup_emit<<<g, 256, 0, st>>>(P);
+      k_dedup_map<<<(C.m + 255) / 256, 256, 0, st>>>(P);
+      CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ev1, st));
+    u32 h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, B.nUnique.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&B.ms, ev0, ev1));
+    B.nU = h[0]; B.maxLen = (int)h[1];
+    return setup_assign_launch(ref, std::max<int>(KMER, B.maxLen));
+  };
   CK(cudaMemsetAsync(ref->covDiff.p, 0, ref->covEntries * 4, ref->stream));
   CK(cudaMemsetAsync(ref->covPoint.p, 0, ref->covEntries * 4, ref->stream));
   ref->covDirty = true;
@@ -1281,7 +1431,9 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   PairHost pairOut[2];
   pairOut[0].pin = &ref->pinEntries[0]; pairOut[1].pin = &ref->pinEntries[1];
   double msCoalesce = 0;
-  auto do_coalesce = [&](const PairHost &H, u32 f0, u32 m) {
+  int coalRc = 0;
+  auto do_coalesce = [&](PairHost &H, u32 f0, u32 m) {
+    if (H.finish() != cudaSuccess) { coalRc = 1; return; }       // the rows of this chunk arrive on the copy stream
     const double t = now_ms();
     shards.add_chunk(H.entries(), H.rowOff.data(), H.rowCnt.data(), H.rowHash.data(), m, (int64_t)f0);
     if (res->fragment_assigned) memcpy(res->fragment_assigned + f0, H.assigned.data(), m);
@@ -1307,16 +1459,35 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   // the rank-local stage (no collective inside): returns this rank's status instead of leaving early, so that in a
   // read-sharded run every rank reaches the status exchange below
   auto local_stage = [&]() -> int {
-  { const double t = now_ms(); if (nChunks) do_prep(prep[0], chunks[0].first, chunks[0].second); msPrepWait += now_ms() - t; }
+  {
+    const double t = now_ms();
+    if (nChunks) { if (devIngest) do_prep_dev(dchunk[0], chunks[0].first, chunks[0].second); else do_prep(prep[0], chunks[0].first, chunks[0].second); }
+    msPrepWait += now_ms() - t;
+  }
   for (u32 c = 0; c < nChunks; ++c) {
     Prep &C = prep[c & 1];
+    DevChunk &DC = dchunk[c & 1];
+    DevBatch DB;
+    if (devIngest) { C.f0 = DC.f0; C.m = DC.m; C.ms = DC.ms; }
     res->ms_dedup += (float)C.ms;
-    if (c + 1 < nChunks) prepThread = std::thread(do_prep, std::ref(prep[(c + 1) & 1]), chunks[c + 1].first, chunks[c + 1].second);
-    if (C.tooLong) return fail(T1K_ERR_ARG, "read longer than T1K_MAX_READ_LEN");
-    res->n_unique_ends += C.rep.size();
+    if (c + 1 < nChunks) {
+      if (devIngest) prepThread = std::thread(do_prep_dev, std::ref(dchunk[(c + 1) & 1]), chunks[c + 1].first, chunks[c + 1].second);
+      else prepThread = std::thread(do_prep, std::ref(prep[(c + 1) & 1]), chunks[c + 1].first, chunks[c + 1].second);
+    }
     double ta = now_ms();
     T1KAssignment *a = nullptr;
-    if (int rc = t1k_assign_batch(ref, C.bases.data(), C.off.data(), C.len.data(), C.w.data(), (uint32_t)C.rep.size(), &a)) return rc;
+    if (devIngest) {
+      if (DC.rc) { g_err = DC.err; return DC.rc; }
+      if (int rc = ingest_chunk(DC, DB)) return rc;
+      res->ms_dedup += DB.ms; res->n_launches += 7;
+      res->n_unique_ends += DB.nU;
+      const DevReads D = {DB.planes.as<u64>(), DB.len16.as<u16>(), DB.w.as<int32_t>(), DB.nU};
+      if (int rc = assign_core(ref, D, &a)) return rc;
+    } else {
+      if (C.tooLong) return fail(T1K_ERR_ARG, "read longer than T1K_MAX_READ_LEN");
+      res->n_unique_ends += C.rep.size();
+      if (int rc = t1k_assign_batch(ref, C.bases.data(), C.off.data(), C.len.data(), C.w.data(), (uint32_t)C.rep.size(), &a)) return rc;
+    }
     struct AG { T1KAssignment *a; ~AG() { t1k_assignment_destroy(a); } } ag{a};
     res->ms_align += (float)(now_ms() - ta);
     res->n_overlaps += a->storeUsed;
@@ -1324,16 +1495,22 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     res->n_launches += 2 + a->launches;
     double tp = now_ms();
     PairHost &H = pairOut[c & 1];     // last read by the coalescing of chunk c-2, which has been joined
-    if (int rc = pair_fragments(ref, a, C.e1.data(), reads2 ? C.e2.data() : nullptr, C.hasN.data(), C.m, prm->max_assign, false, H, true)) return rc;
+    if (devIngest) {
+      if (int rc = pair_fragments(ref, a, DB.e1.as<u32>(), reads2 ? DB.e2.as<u32>() : nullptr, DB.fragHasN.as<u8>(), C.m, prm->max_assign, false, H, true,
+                                  getenv("T1K_SYNC_ROWS") == nullptr, true)) return rc;
+    } else if (int rc = pair_fragments(ref, a, C.e1.data(), reads2 ? C.e2.data() : nullptr, C.hasN.data(), C.m, prm->max_assign, false, H, true,
+                                       getenv("T1K_SYNC_ROWS") == nullptr)) return rc;
     res->ms_pair += (float)(now_ms() - tp);
     res->ms_pair_kernel += H.msKernel; res->n_launches += H.launches;
     res->n_assignments += H.nEntries;
     nPairRecords += H.nPairRecords;
     if (coalThread.joinable()) coalThread.join();
-    coalThread = std::thread(do_coalesce, std::cref(H), C.f0, C.m);
+    if (coalRc) return fail(T1K_ERR_CUDA, "D2H of a chunk's fragment rows failed");
+    coalThread = std::thread(do_coalesce, std::ref(H), C.f0, C.m);
     { const double t = now_ms(); if (prepThread.joinable()) prepThread.join(); msPrepWait += now_ms() - t; }
   }
   if (coalThread.joinable()) coalThread.join();
+  if (coalRc) return fail(T1K_ERR_CUDA, "D2H of a chunk's fragment rows failed");
   return T1K_OK;
   };
   int localRc = local_stage();
@@ -1489,6 +1666,10 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     ep.row_ptr = in.rowPtr.data(); ep.col = in.col.data(); ep.count = in.count.data(); ep.ec_len = in.ecLen.data(); ep.x0 = in.x0.data();
     ep.min_squarem_alpha = prm->min_squarem_alpha; ep.filter_frac = prm->filter_frac; ep.fast_sums = prm->em_fast_sums;
     ep.comm = comm;
+    // the columns of the matrix are the group lists of the class representatives: handed over as they lie in EC
+    std::vector<int64_t> colBeg((size_t)EC.size()), colEnd((size_t)EC.size());
+    for (int32_t e = 0; e < EC.size(); ++e) { const int32_t rep = EC.ecAlleles[EC.ecPtr[e]]; colBeg[e] = EC.inPtr[rep]; colEnd[e] = EC.inPtr[rep + 1]; }
+    const EmColumns emCols = {colBeg.data(), colEnd.data(), EC.in.data(), EC.in.size()};
     if (prm->allele_major && prm->allele_gene) {
       ep.n_alleles = nA; ep.n_major = prm->n_major; ep.n_gene = prm->n_gene;
       ep.ec_allele_ptr = EC.ecPtr.data(); ep.ec_alleles = EC.ecAlleles.data();
@@ -1496,9 +1677,9 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     }
     std::vector<double> x(EC.size()), rc(EC.size());
     T1KEmResult er; er.x = x.data(); er.ec_read_count = rc.data(); er.iterations = 0;
-    g_emTrusted = true;
+    g_emTrusted = true; g_emCols = &emCols;
     const int rcode = t1k_em_run(&ep, &er, ref->device);
-    g_emTrusted = false;
+    g_emTrusted = false; g_emCols = nullptr;
     if (rcode) return rcode;
     pt.lap("t1k_em_run");
     res->em_iterations = er.iterations;

@@ -44,13 +44,13 @@ __global__ void k_em_rowsum(int nGroups, const int64_t *__restrict__ rowPtr, con
   if (lane == 0) psum[g] = s == 0 ? 1.0 : s;      // Genotyper.hpp:393-394
 }
 
-__global__ void k_em_colsum(int nEc, const int64_t *__restrict__ colPtr, const int32_t *__restrict__ rowIdx,
+__global__ void k_em_colsum(int nEc, const int64_t *__restrict__ colBeg, const int64_t *__restrict__ colEnd, const int32_t *__restrict__ rowIdx,
                             const double *__restrict__ count, const double *__restrict__ psum,
                             const double *__restrict__ x, double *__restrict__ rc) {
   const int e = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (e >= nEc) return;
-  const int64_t b = colPtr[e], en = colPtr[e + 1];
+  const int64_t b = colBeg[e], en = colEnd[e];
   const double xe = x[e];
   double s = 0;
   for (int64_t k = b + lane; k < en; k += 32) { const int g = rowIdx[k]; s += count[g] * (xe / psum[g]); }
@@ -112,15 +112,15 @@ __global__ void k_em_rowsum_seq(int nGroups, const int64_t *__restrict__ rowPtr,
 // divisions in parallel), then every lane adds them in ascending group order through shuffles — the same roundings in
 // the same order as the reference's serial loop (Genotyper.hpp:391-404), without one thread issuing 60 instructions per
 // entry of a 50 k-entry column.
-__global__ void k_em_colsum_seq(int nEc, const int64_t *__restrict__ colPtr, const int32_t *__restrict__ rowIdx,
+__global__ void k_em_colsum_seq(int nEc, const int64_t *__restrict__ colBeg, const int64_t *__restrict__ colEnd, const int32_t *__restrict__ rowIdx,
                                 const double *__restrict__ count, const double *__restrict__ psum,
                                 const double *__restrict__ x, double *__restrict__ rc) {
   const int e = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (e >= nEc) return;
   const double xe = x[e];
   double s = 0;
-  const int64_t k1 = colPtr[e + 1];
-  for (int64_t b = colPtr[e]; b < k1; b += 32) {
+  const int64_t k1 = colEnd[e];
+  for (int64_t b = colBeg[e]; b < k1; b += 32) {
     const int64_t k = b + lane;
     double t = 0;
     if (k < k1) { const int g = rowIdx[k]; t = __dmul_rn(count[g], __ddiv_rn(xe, psum[g])); }

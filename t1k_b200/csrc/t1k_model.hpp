@@ -665,13 +665,13 @@ inline void unique_read_ends(const char *reads1, const char *reads2, uint32_t st
 
 struct EquivalenceClasses {
   std::vector<int32_t> ecPtr{0}, ecAlleles, alleleEc;
+  std::vector<int64_t> inPtr;          // readsInAllele: the groups of every allele, ascending (kept: the members of a class sit in exactly
+  std::vector<int32_t> in;             // the same groups, so column e of the EM's matrix IS the group list of the class's first member)
 
   void build(const ReadGroups &G, int32_t nAlleles, int threads = 1) { build(view_of(G), nAlleles, threads); }
   void build(const GroupsView &G, int32_t nAlleles, int threads = 1) {
     const int32_t readCnt = G.n;
     // readsInAllele (Genotyper.hpp:912-939): the groups of every allele, ascending
-    std::vector<int64_t> inPtr;
-    std::vector<int32_t> in;
     transpose_csr(G.ptr, readCnt, [&G](int64_t k) { return G.allele_at(k); }, nAlleles, threads, inPtr, in);
     struct FP { int32_t a, b; };
     std::vector<FP> fp(nAlleles);
@@ -715,6 +715,7 @@ struct EquivalenceClasses {
     }
   }
   int32_t size() const { return (int32_t)ecPtr.size() - 1; }
+
 };
 
 // EM inputs as QuantifyAlleleEquivalentClass assembles them (Genotyper.hpp:1155-1232)
