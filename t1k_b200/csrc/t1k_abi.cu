@@ -23,6 +23,7 @@
 #include "t1k_filter.cuh"
 #include "t1k_alninfo.cuh"
 #include "t1k_ingest.cuh"
+#include "t1k_tail.cuh"
 
 using namespace t1k;
 
@@ -33,6 +34,9 @@ thread_local bool g_emTrusted = false;
 // columns of the EM's matrix handed over by t1k_genotype (see EquivalenceClasses::inPtr): column e = rows[beg[e] .. end[e])
 struct EmColumns { const int64_t *beg, *end; const int32_t *rows; size_t nRows; };
 thread_local const EmColumns *g_emCols = nullptr;
+// the whole matrix already on the device (t1k_tail.cuh): CSR with global offsets (rowPtr[G+1], col), CSC of the rows [g0, g1)
+struct EmDevice { const int64_t *rowPtr; const int32_t *col; const int64_t *colBeg, *colEnd; const int32_t *rowIdx; int g0, g1; };
+thread_local const EmDevice *g_emDev = nullptr;
 
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
@@ -983,6 +987,7 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   const int G = p->n_groups, E = p->n_ec;
   const int64_t nnz = p->row_ptr[G];
   PhaseTimer pt;
+  const EmDevice *emd = g_emTrusted ? g_emDev : nullptr;
   if (!g_emTrusted)        // (t1k_genotype builds the matrix itself)
     for (int64_t k = 0; k < nnz; ++k) if (p->col[k] < 0 || p->col[k] >= E) return fail(T1K_ERR_ARG, "t1k_em_run: column index out of range");
   // read-sharded E-step: this rank's contiguous row range [g0, g1)
@@ -993,16 +998,17 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
     std::vector<int32_t> bounds((size_t)comm->world + 1);
     partition_rows(p->row_ptr, G, comm->world, bounds.data());
     g0 = bounds[comm->rank]; g1 = bounds[comm->rank + 1];
+    if (emd && (emd->g0 != g0 || emd->g1 != g1)) return fail(T1K_ERR_ARG, "t1k_em_run: device matrix built for another row range");
   }
   const int Gl = g1 - g0;
   const int64_t k0 = p->row_ptr[g0], nnzL = p->row_ptr[g1] - k0;
-  std::vector<int64_t> rowPtrL((size_t)Gl + 1);
-  for (int g = 0; g <= Gl; ++g) rowPtrL[g] = p->row_ptr[g0 + g] - k0;
+  std::vector<int64_t> rowPtrL((size_t)(emd ? 0 : Gl + 1));
+  if (!emd) for (int g = 0; g <= Gl; ++g) rowPtrL[g] = p->row_ptr[g0 + g] - k0;
   // CSC of the local rows with ascending group order inside every column => fixed summation order
   std::vector<int64_t> colPtr;
   std::vector<int32_t> rowIdx;
-  const EmColumns *cols = (!comm && g_emTrusted) ? g_emCols : nullptr;
-  if (!cols) {
+  const EmColumns *cols = (!comm && g_emTrusted && !emd) ? g_emCols : nullptr;
+  if (!cols && !emd) {
     int hostThreads = (int)std::thread::hardware_concurrency() / (comm ? comm->world : 1);
     if (const char *env = getenv("T1K_HOST_THREADS")) hostThreads = atoi(env);
     const int32_t *colp = p->col;
@@ -1018,13 +1024,14 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   // another order anyway (documented tolerance 1e-5), so it takes the tree reductions
   const bool fast = p->fast_sums != 0 || comm != nullptr;
   CK(dTmpA.alloc((size_t)E * 8)); CK(dTmpB.alloc((size_t)E * 8));
-  CK(dRowPtr.alloc(((size_t)Gl + 1) * 8)); CK(dCol.alloc((size_t)nnzL * 4)); CK(dColPtr.alloc(((size_t)E + 1) * 8)); CK(dRowIdx.alloc((cols ? cols->nRows : (size_t)nnzL) * 4));
+  if (!emd) { CK(dRowPtr.alloc(((size_t)Gl + 1) * 8)); CK(dCol.alloc((size_t)nnzL * 4)); CK(dColPtr.alloc(((size_t)E + 1) * 8)); CK(dRowIdx.alloc((cols ? cols->nRows : (size_t)nnzL) * 4)); }
   if (cols) CK(dColEnd.alloc((size_t)E * 8));
   CK(dCount.alloc((size_t)G * 8)); CK(dLen.alloc((size_t)E * 4)); CK(dPsum.alloc((size_t)G * 8)); CK(dRc.alloc((size_t)E * 8));
   CK(dX0.alloc((size_t)E * 8)); CK(dX1.alloc((size_t)E * 8)); CK(dX2.alloc((size_t)E * 8)); CK(dX3.alloc((size_t)E * 8)); CK(dDiff.alloc(8));
-  CK(cudaMemcpyAsync(dRowPtr.p, rowPtrL.data(), ((size_t)Gl + 1) * 8, cudaMemcpyHostToDevice, st));
-  if (nnzL) CK(cudaMemcpyAsync(dCol.p, p->col + k0, (size_t)nnzL * 4, cudaMemcpyHostToDevice, st));
-  if (cols) {
+  if (!emd) CK(cudaMemcpyAsync(dRowPtr.p, rowPtrL.data(), ((size_t)Gl + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (!emd && nnzL) CK(cudaMemcpyAsync(dCol.p, p->col + k0, (size_t)nnzL * 4, cudaMemcpyHostToDevice, st));
+  if (emd) {
+  } else if (cols) {
     CK(cudaMemcpyAsync(dColPtr.p, cols->beg, (size_t)E * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dColEnd.p, cols->end, (size_t)E * 8, cudaMemcpyHostToDevice, st));
     if (cols->nRows) CK(cudaMemcpyAsync(dRowIdx.p, cols->rows, cols->nRows * 4, cudaMemcpyHostToDevice, st));
@@ -1032,7 +1039,10 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
     CK(cudaMemcpyAsync(dColPtr.p, colPtr.data(), ((size_t)E + 1) * 8, cudaMemcpyHostToDevice, st));
     if (nnzL) CK(cudaMemcpyAsync(dRowIdx.p, rowIdx.data(), (size_t)nnzL * 4, cudaMemcpyHostToDevice, st));
   }
-  const int64_t *dBeg = dColPtr.as<int64_t>(), *dEnd = cols ? dColEnd.as<int64_t>() : dColPtr.as<int64_t>() + 1;
+  const int64_t *dBeg = emd ? emd->colBeg : dColPtr.as<int64_t>(), *dEnd = emd ? emd->colEnd : cols ? dColEnd.as<int64_t>() : dColPtr.as<int64_t>() + 1;
+  const int64_t *dRowPtrP = emd ? emd->rowPtr + g0 : dRowPtr.as<int64_t>();      // (global offsets into the whole col array)
+  const int32_t *dColP = emd ? emd->col : dCol.as<int32_t>();
+  const int32_t *dRowIdxP = emd ? emd->rowIdx : dRowIdx.as<int32_t>();
   if (G) CK(cudaMemcpyAsync(dCount.p, p->count, (size_t)G * 8, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dLen.p, p->ec_len, (size_t)E * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dX0.p, p->x0, (size_t)E * 8, cudaMemcpyHostToDevice, st));
@@ -1047,11 +1057,11 @@ int t1k_em_run(const T1KEmProblem *p, T1KEmResult *r, int32_t device) {
   auto em_update = [&](const double *xin, double *xout) -> int {   // Genotyper::EMupdate
     double *psumL = dPsum.as<double>() + g0;    // psum / count stay indexed by the global group id
     if (fast) {
-      if (Gl) k_em_rowsum<<<gRow, 256, 0, st>>>(Gl, dRowPtr.as<int64_t>(), dCol.as<int32_t>(), xin, psumL);
-      k_em_colsum<<<gCol, 256, 0, st>>>(E, dBeg, dEnd, dRowIdx.as<int32_t>(), dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
+      if (Gl) k_em_rowsum<<<gRow, 256, 0, st>>>(Gl, dRowPtrP, dColP, xin, psumL);
+      k_em_colsum<<<gCol, 256, 0, st>>>(E, dBeg, dEnd, dRowIdxP, dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
     } else {
-      if (Gl) k_em_rowsum_seq<<<(Gl + 127) / 128, 128, 0, st>>>(Gl, dRowPtr.as<int64_t>(), dCol.as<int32_t>(), xin, psumL);
-      k_em_colsum_seq<<<(unsigned)(((size_t)E * 32 + 255) / 256), 256, 0, st>>>(E, dBeg, dEnd, dRowIdx.as<int32_t>(), dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
+      if (Gl) k_em_rowsum_seq<<<(Gl + 127) / 128, 128, 0, st>>>(Gl, dRowPtrP, dColP, xin, psumL);
+      k_em_colsum_seq<<<(unsigned)(((size_t)E * 32 + 255) / 256), 256, 0, st>>>(E, dBeg, dEnd, dRowIdxP, dCount.as<double>(), dPsum.as<double>(), xin, dRc.as<double>());
     }
     CK(cudaGetLastError());
     // the one exchange of the EM: per-EC expected read counts summed over the row shards (NVLink all-reduce)
@@ -1319,6 +1329,152 @@ int alltoall_blobs(T1KRef *ref, T1KComm *comm, const uint8_t *send, const std::v
   CK(recv.grow(std::max<size_t>(totRecv, 16), 0));
   if (totRecv) CK(cudaMemcpyAsync(recv.p, dRecv.p, totRecv, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return T1K_OK;
+}
+
+}  // namespace
+
+namespace {
+
+// ---- the global tail on the device (t1k_tail.cuh)
+struct TailDevice {
+  DevMem gPtr, gAllele, bits, fp, rowHash, listLen, alleleEc, isRep, ecRep, rowLen, rowPtr, col, colLen, colBeg, rowIdx, pairs, differ;
+  TailParams P;
+  std::vector<int64_t> hRowPtr;      // the EM's CSR row pointer (host copy: row partition, nnz)
+};
+
+// Equivalence classes of the alleles from the bit matrix.  *ok = false: a (fingerprint, hash, length) bucket held alleles with
+// different lists (a 64-bit hash collision) — nothing is lost, the caller takes the host path.
+int device_tail_classes(T1KRef *ref, const GroupsView &G, int32_t nA, int threads, TailDevice &T, EquivalenceClasses &EC, bool *ok) {
+  *ok = false;
+  cudaStream_t st = ref->stream;
+  const int32_t n = G.n;
+  const int64_t nE = G.entries();
+  // allele ids of the entries: the compact form has them as they are; a full table is read once
+  std::vector<int32_t> ids;
+  const int32_t *hAllele = G.allele;
+  if (!hAllele) {
+    ids.resize((size_t)std::max<int64_t>(nE, 1));
+    if (threads < 1 || (size_t)nE < par_min_entries()) threads = 1;
+    const HostEntry *ent = G.ent;
+    run_threads(threads, [&](int t) { for (int64_t k = nE * t / threads; k < nE * (t + 1) / threads; ++k) ids[k] = ent[k].alleleIdx; });
+    hAllele = ids.data();
+  }
+  const int32_t W = (n + 63) / 64;
+  CK(T.gPtr.alloc(((size_t)n + 1) * 8)); CK(T.gAllele.alloc((size_t)std::max<int64_t>(nE, 1) * 4));
+  CK(T.bits.alloc((size_t)nA * std::max(W, 1) * 8));
+  CK(T.fp.alloc((size_t)nA * 4)); CK(T.rowHash.alloc((size_t)nA * 8)); CK(T.listLen.alloc((size_t)nA * 4)); CK(T.differ.alloc(4));
+  CK(cudaMemcpyAsync(T.gPtr.p, G.ptr, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (nE) CK(cudaMemcpyAsync(T.gAllele.p, hAllele, (size_t)nE * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(T.bits.p, 0, (size_t)nA * std::max(W, 1) * 8, st));
+  CK(cudaMemsetAsync(T.differ.p, 0, 4, st));
+  TailParams &P = T.P;
+  memset(&P, 0, sizeof(P));
+  P.nGroups = n; P.nAlleles = nA; P.gPtr = T.gPtr.as<int64_t>(); P.gAllele = T.gAllele.as<int32_t>();
+  P.bits = T.bits.as<u64>(); P.wordsPerRow = std::max(W, 1);
+  P.fp = T.fp.as<int32_t>(); P.rowHash = T.rowHash.as<u64>(); P.listLen = T.listLen.as<int32_t>();
+  k_tail_bits<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(P);
+  k_tail_fp<<<(nA + 127) / 128, 128, 0, st>>>(P);
+  CK(cudaGetLastError());
+  std::vector<int32_t> fp(nA), len(nA);
+  std::vector<u64> hs(nA);
+  CK(cudaMemcpyAsync(fp.data(), T.fp.p, (size_t)nA * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(len.data(), T.listLen.p, (size_t)nA * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hs.data(), T.rowHash.p, (size_t)nA * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  // the reference's order (Genotyper.hpp:1094-1101): fingerprint descending, allele ascending; alleles without reads last
+  std::vector<int32_t> order(nA);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return fp[x] != fp[y] ? fp[y] < fp[x] : x < y; });
+  // candidates for one class: same fingerprint, row hash and list length.  Inside a fingerprint run the buckets keep the order
+  // of their first members, which is the order the reference creates the classes in.
+  EC.alleleEc.assign(nA, -1);
+  std::vector<std::vector<int32_t> > ecs;
+  std::vector<int32_t> pairs;
+  for (int32_t i = 0; i < nA;) {
+    if (fp[order[i]] == -1) break;
+    int32_t j = i;
+    while (j < nA && fp[order[j]] == fp[order[i]]) ++j;
+    const size_t firstClass = ecs.size();
+    for (int32_t k = i; k < j; ++k) {
+      const int32_t a = order[k];
+      size_t c = firstClass;
+      for (; c < ecs.size(); ++c) { const int32_t r = ecs[c][0]; if (hs[r] == hs[a] && len[r] == len[a]) break; }
+      if (c == ecs.size()) ecs.push_back(std::vector<int32_t>(1, a));
+      else { pairs.push_back(ecs[c][0]); pairs.push_back(a); ecs[c].push_back(a); }
+      EC.alleleEc[a] = (int32_t)c;
+    }
+    i = j;
+  }
+  if (!pairs.empty()) {
+    const int nPairs = (int)(pairs.size() / 2);
+    CK(T.pairs.alloc(pairs.size() * 4));
+    CK(cudaMemcpyAsync(T.pairs.p, pairs.data(), pairs.size() * 4, cudaMemcpyHostToDevice, st));
+    k_tail_cmp<<<(unsigned)(((size_t)nPairs * 32 + 255) / 256), 256, 0, st>>>(P, T.pairs.as<int32_t>(), nPairs, T.differ.as<int>());
+    CK(cudaGetLastError());
+    int differ = 0;
+    CK(cudaMemcpyAsync(&differ, T.differ.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (differ) { EC.alleleEc.clear(); return T1K_OK; }
+  }
+  EC.ecPtr.assign(1, 0); EC.ecAlleles.clear();
+  for (size_t e = 0; e < ecs.size(); ++e) {
+    EC.ecAlleles.insert(EC.ecAlleles.end(), ecs[e].begin(), ecs[e].end());
+    EC.ecPtr.push_back((int32_t)EC.ecAlleles.size());
+  }
+  *ok = true;
+  return T1K_OK;
+}
+
+// The EM's matrix from the bit matrix and the classes: CSR of all rows (first-appearance order inside a row), CSC of the rows
+// [g0, g1) this rank's E-step covers (the partition needs the row pointer, so the CSR comes first).
+int device_tail_matrix(T1KRef *ref, TailDevice &T, const EquivalenceClasses &EC, int32_t nA, T1KComm *comm, EmDevice &out) {
+  cudaStream_t st = ref->stream;
+  TailParams &P = T.P;
+  const int32_t n = P.nGroups, E = EC.size();
+  std::vector<u8> isRep(nA, 0);
+  std::vector<int32_t> ecRep(std::max(E, 1));
+  for (int32_t e = 0; e < E; ++e) { ecRep[e] = EC.ecAlleles[EC.ecPtr[e]]; isRep[ecRep[e]] = 1; }
+  CK(T.alleleEc.alloc((size_t)nA * 4)); CK(T.isRep.alloc(nA)); CK(T.ecRep.alloc((size_t)std::max(E, 1) * 4));
+  CK(T.rowLen.alloc((size_t)std::max(n, 1) * 8)); CK(T.rowPtr.alloc(((size_t)n + 1) * 8));
+  CK(T.colLen.alloc((size_t)std::max(E, 1) * 8)); CK(T.colBeg.alloc(((size_t)E + 1) * 8));
+  CK(cudaMemcpyAsync(T.alleleEc.p, EC.alleleEc.data(), (size_t)nA * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(T.isRep.p, isRep.data(), nA, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(T.ecRep.p, ecRep.data(), (size_t)std::max(E, 1) * 4, cudaMemcpyHostToDevice, st));
+  P.nEc = E; P.alleleEc = T.alleleEc.as<int32_t>(); P.isRep = T.isRep.as<u8>(); P.ecRep = T.ecRep.as<int32_t>();
+  P.rowLen = T.rowLen.as<int64_t>(); P.rowPtr = T.rowPtr.as<int64_t>(); P.colLen = T.colLen.as<int64_t>(); P.colBeg = T.colBeg.as<int64_t>();
+  const unsigned gGroups = (unsigned)(((size_t)n * 32 + 255) / 256), gEc = (unsigned)(((size_t)E * 32 + 255) / 256);
+  k_tail_rowlen<<<gGroups, 256, 0, st>>>(P);
+  k_scan_i64<<<1, 1024, 0, st>>>(P.rowLen, n, P.rowPtr);
+  CK(cudaGetLastError());
+  T.hRowPtr.resize((size_t)n + 1);
+  CK(cudaMemcpyAsync(T.hRowPtr.data(), T.rowPtr.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int64_t nnz = T.hRowPtr[n];
+  CK(T.col.alloc((size_t)std::max<int64_t>(nnz, 1) * 4));
+  P.col = T.col.as<int32_t>();
+  k_tail_rowfill<<<gGroups, 256, 0, st>>>(P);
+  int g0 = 0, g1 = n;
+  if (comm) {
+    std::vector<int32_t> bounds((size_t)comm->world + 1);
+    partition_rows(T.hRowPtr.data(), n, comm->world, bounds.data());
+    g0 = bounds[comm->rank]; g1 = bounds[comm->rank + 1];
+  }
+  P.g0 = g0; P.g1 = g1;
+  k_tail_collen<<<gEc, 256, 0, st>>>(P);
+  k_scan_i64<<<1, 1024, 0, st>>>(P.colLen, E, P.colBeg);
+  CK(cudaGetLastError());
+  int64_t nnzL = 0;
+  CK(cudaMemcpyAsync(&nnzL, T.colBeg.as<int64_t>() + E, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(T.rowIdx.alloc((size_t)std::max<int64_t>(nnzL, 1) * 4));
+  P.rowIdx = T.rowIdx.as<int32_t>();
+  k_tail_colfill<<<gEc, 256, 0, st>>>(P);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  out.rowPtr = T.rowPtr.as<int64_t>(); out.col = T.col.as<int32_t>();
+  out.colBeg = T.colBeg.as<int64_t>(); out.colEnd = T.colBeg.as<int64_t>() + 1; out.rowIdx = T.rowIdx.as<int32_t>();
+  out.g0 = g0; out.g1 = g1;
   return T1K_OK;
 }
 
@@ -1639,8 +1795,13 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   double tc = now_ms();
   PhaseTimer pt;
   EquivalenceClasses EC;
-  EC.build(GV, nA, shards.threads());
-  pt.lap("equivalence classes");
+  TailDevice tail;
+  bool tailOnDevice = false;
+  if (getenv("T1K_HOST_TAIL") == nullptr && GV.n > 0) {
+    if (int rc = device_tail_classes(ref, GV, nA, shards.threads(), tail, EC, &tailOnDevice)) return rc;
+  }
+  if (!tailOnDevice) { EC = EquivalenceClasses(); EC.build(GV, nA, shards.threads()); }
+  pt.lap(tailOnDevice ? "equivalence classes (device)" : "equivalence classes");
   res->n_groups = GV.n; res->n_ec = EC.size(); res->n_alleles = nA;
   if (res->missing_coverage) { if (int rc = t1k_missing_coverage(ref, res->missing_coverage)) return rc; }
   pt.lap("missing coverage");
@@ -1657,19 +1818,25 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   if (res->ec_abundance) memset(res->ec_abundance, 0, (size_t)nA * 8);
   if (EC.size() > 0) {
     EmInputs in;
-    in.build(GV, EC, prm->effective_len, prm->seq_weight, shards.threads());
-    pt.lap("EM inputs");
-    if (pt.on) fprintf(stderr, "[t1k timing] groups %d entries %lld ECs %d nnz %zu\n", GV.n, (long long)GV.entries(), EC.size(), in.col.size());
+    EmDevice emDev;
+    if (tailOnDevice) {
+      if (int rc = device_tail_matrix(ref, tail, EC, nA, comm, emDev)) return rc;
+      in.build_vectors(GV, EC, prm->effective_len, prm->seq_weight, shards.threads());
+      in.rowPtr.swap(tail.hRowPtr);
+    } else in.build(GV, EC, prm->effective_len, prm->seq_weight, shards.threads());
+    pt.lap(tailOnDevice ? "EM inputs (device)" : "EM inputs");
+    if (pt.on) fprintf(stderr, "[t1k timing] groups %d entries %lld ECs %d nnz %lld\n", GV.n, (long long)GV.entries(), EC.size(), (long long)in.rowPtr[GV.n]);
     T1KEmProblem ep;
     memset(&ep, 0, sizeof(ep));
     ep.n_groups = GV.n; ep.n_ec = EC.size();
-    ep.row_ptr = in.rowPtr.data(); ep.col = in.col.data(); ep.count = in.count.data(); ep.ec_len = in.ecLen.data(); ep.x0 = in.x0.data();
+    ep.row_ptr = in.rowPtr.data(); ep.col = tailOnDevice ? nullptr : in.col.data(); ep.count = in.count.data(); ep.ec_len = in.ecLen.data(); ep.x0 = in.x0.data();
     ep.min_squarem_alpha = prm->min_squarem_alpha; ep.filter_frac = prm->filter_frac; ep.fast_sums = prm->em_fast_sums;
     ep.comm = comm;
     // the columns of the matrix are the group lists of the class representatives: handed over as they lie in EC
     std::vector<int64_t> colBeg((size_t)EC.size()), colEnd((size_t)EC.size());
     for (int32_t e = 0; e < EC.size(); ++e) { const int32_t rep = EC.ecAlleles[EC.ecPtr[e]]; colBeg[e] = EC.inPtr[rep]; colEnd[e] = EC.inPtr[rep + 1]; }
     const EmColumns emCols = {colBeg.data(), colEnd.data(), EC.in.data(), EC.in.size()};
+    if (tailOnDevice) { colBeg.clear(); colEnd.clear(); }
     if (prm->allele_major && prm->allele_gene) {
       ep.n_alleles = nA; ep.n_major = prm->n_major; ep.n_gene = prm->n_gene;
       ep.ec_allele_ptr = EC.ecPtr.data(); ep.ec_alleles = EC.ecAlleles.data();
@@ -1677,14 +1844,14 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     }
     std::vector<double> x(EC.size()), rc(EC.size());
     T1KEmResult er; er.x = x.data(); er.ec_read_count = rc.data(); er.iterations = 0;
-    g_emTrusted = true; g_emCols = &emCols;
+    g_emTrusted = true; g_emCols = tailOnDevice ? nullptr : &emCols; g_emDev = tailOnDevice ? &emDev : nullptr;
     const int rcode = t1k_em_run(&ep, &er, ref->device);
-    g_emTrusted = false; g_emCols = nullptr;
+    g_emTrusted = false; g_emCols = nullptr; g_emDev = nullptr;
     if (rcode) return rcode;
     pt.lap("t1k_em_run");
     res->em_iterations = er.iterations;
     res->ms_em_kernel = er.ms_kernel; res->n_launches += er.n_launches;
-    res->em_nnz = (uint64_t)in.col.size(); res->em_updates = 3 * er.iterations;
+    res->em_nnz = (uint64_t)in.rowPtr[GV.n]; res->em_updates = 3 * er.iterations;
     if (res->abundance && res->ec_abundance)
       set_allele_abundance(rc.data(), in.ecLen.data(), EC.ecPtr.data(), EC.ecAlleles.data(), EC.size(), nA, res->abundance, res->ec_abundance);
     if (res->ec_read_count) memcpy(res->ec_read_count, rc.data(), (size_t)EC.size() * 8);

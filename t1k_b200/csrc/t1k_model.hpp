@@ -753,6 +753,11 @@ struct EmInputs {
     run_threads(threads, [&](int t) {
       if (!cols[t].empty()) memcpy(col.data() + rowPtr[b[t]], cols[t].data(), cols[t].size() * sizeof(int32_t));
     });
+    build_ec_vectors(EC, effectiveLen, seqWeight);
+  }
+  // ecInfo[].length and the initial abundances (Genotyper.hpp:1191-1232)
+  void build_ec_vectors(const EquivalenceClasses &EC, const int32_t *effectiveLen, const int32_t *seqWeight) {
+    const int32_t E = EC.size();
     ecLen.resize(E); x0.resize(E);
     for (int32_t e = 0; e < E; ++e) {
       int32_t len = effectiveLen[EC.ecAlleles[EC.ecPtr[e]]];
@@ -763,6 +768,15 @@ struct EmInputs {
       }
       ecLen[e] = len; x0[e] = w;
     }
+  }
+  // everything but the matrix (which the device tail builds where the EM reads it): group counts and the class vectors
+  void build_vectors(const GroupsView &G, const EquivalenceClasses &EC, const int32_t *effectiveLen, const int32_t *seqWeight, int threads = 1) {
+    const int32_t n = G.n;
+    count.resize(n);
+    if (threads < 1 || (size_t)G.entries() < par_min_entries()) threads = 1;
+    const std::vector<int32_t> b = balanced_ranges(G.ptr, n, threads);
+    run_threads(threads, [&](int t) { for (int32_t g = b[t]; g < b[t + 1]; ++g) count[g] = G.count_of(g); });
+    build_ec_vectors(EC, effectiveLen, seqWeight);
   }
 };
 
