@@ -228,6 +228,7 @@ struct T1KRef {
   bool covDirty = true;
   PinnedMem pinEntries[2];   // D2H staging of pairing rows (double-buffered by t1k_genotype's chunk pipeline)
   PinnedMem pinSend, pinRecv, pinRecv2; // read-group tables on their way to / from the peers
+  PinnedMem pinIds;                     // allele ids of the group entries on their way to the device tail
   // t1k_assign_batch_async: jobs of one reference run in submission order
   std::mutex qMu; std::condition_variable qCv; uint64_t qNext = 0, qServing = 0;
   ~T1KRef() { if (stream) cudaStreamDestroy(stream); if (copyStream) cudaStreamDestroy(copyStream); if (prepStream) cudaStreamDestroy(prepStream); }
@@ -1351,15 +1352,17 @@ int device_tail_classes(T1KRef *ref, const GroupsView &G, int32_t nA, int thread
   const int32_t n = G.n;
   const int64_t nE = G.entries();
   // allele ids of the entries: the compact form has them as they are; a full table is read once
-  std::vector<int32_t> ids;
+  PhaseTimer pt;
   const int32_t *hAllele = G.allele;
   if (!hAllele) {
-    ids.resize((size_t)std::max<int64_t>(nE, 1));
+    CK(ref->pinIds.ensure((size_t)std::max<int64_t>(nE, 1) * 4));      // (pinned: the upload is a DMA at link speed)
+    int32_t *ids = ref->pinIds.as<int32_t>();
     if (threads < 1 || (size_t)nE < par_min_entries()) threads = 1;
     const HostEntry *ent = G.ent;
     run_threads(threads, [&](int t) { for (int64_t k = nE * t / threads; k < nE * (t + 1) / threads; ++k) ids[k] = ent[k].alleleIdx; });
-    hAllele = ids.data();
+    hAllele = ids;
   }
+  pt.lap("  tail: allele ids");
   const int32_t W = (n + 63) / 64;
   CK(T.gPtr.alloc(((size_t)n + 1) * 8)); CK(T.gAllele.alloc((size_t)std::max<int64_t>(nE, 1) * 4));
   CK(T.bits.alloc((size_t)nA * std::max(W, 1) * 8));
@@ -1382,6 +1385,7 @@ int device_tail_classes(T1KRef *ref, const GroupsView &G, int32_t nA, int thread
   CK(cudaMemcpyAsync(len.data(), T.listLen.p, (size_t)nA * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(hs.data(), T.rowHash.p, (size_t)nA * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  pt.lap("  tail: upload + bit matrix + fingerprints");
   // the reference's order (Genotyper.hpp:1094-1101): fingerprint descending, allele ascending; alleles without reads last
   std::vector<int32_t> order(nA);
   std::iota(order.begin(), order.end(), 0);
@@ -1406,6 +1410,7 @@ int device_tail_classes(T1KRef *ref, const GroupsView &G, int32_t nA, int thread
     }
     i = j;
   }
+  pt.lap("  tail: class buckets (host)");
   if (!pairs.empty()) {
     const int nPairs = (int)(pairs.size() / 2);
     CK(T.pairs.alloc(pairs.size() * 4));
@@ -1833,10 +1838,12 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     ep.min_squarem_alpha = prm->min_squarem_alpha; ep.filter_frac = prm->filter_frac; ep.fast_sums = prm->em_fast_sums;
     ep.comm = comm;
     // the columns of the matrix are the group lists of the class representatives: handed over as they lie in EC
-    std::vector<int64_t> colBeg((size_t)EC.size()), colEnd((size_t)EC.size());
-    for (int32_t e = 0; e < EC.size(); ++e) { const int32_t rep = EC.ecAlleles[EC.ecPtr[e]]; colBeg[e] = EC.inPtr[rep]; colEnd[e] = EC.inPtr[rep + 1]; }
+    std::vector<int64_t> colBeg, colEnd;
+    if (!tailOnDevice) {
+      colBeg.resize((size_t)EC.size()); colEnd.resize((size_t)EC.size());
+      for (int32_t e = 0; e < EC.size(); ++e) { const int32_t rep = EC.ecAlleles[EC.ecPtr[e]]; colBeg[e] = EC.inPtr[rep]; colEnd[e] = EC.inPtr[rep + 1]; }
+    }
     const EmColumns emCols = {colBeg.data(), colEnd.data(), EC.in.data(), EC.in.size()};
-    if (tailOnDevice) { colBeg.clear(); colEnd.clear(); }
     if (prm->allele_major && prm->allele_gene) {
       ep.n_alleles = nA; ep.n_major = prm->n_major; ep.n_gene = prm->n_gene;
       ep.ec_allele_ptr = EC.ecPtr.data(); ep.ec_alleles = EC.ecAlleles.data();
