@@ -135,11 +135,25 @@ __global__ void k_em_colsum_seq(int nEc, const int64_t *__restrict__ colBeg, con
   if (lane == 0) rc[e] = s;
 }
 
-// tmp[e] = f(e) elementwise, then one thread adds tmp[0..n) in index order
+// tmp[e] = f(e) elementwise, then tmp[0..n) added in index order.  Called by a whole warp: the lanes load 32 consecutive terms
+// at once (the next 32 are already in flight) and every lane runs the same chain of separately rounded adds over them through
+// shuffles — the reference's order and roundings, without one thread waiting for 26 k dependent global loads.
 __device__ __forceinline__ double seq_sum(const double *tmp, int n) {
+  const int lane = threadIdx.x & 31;
   double s = 0;
-#pragma unroll 8
-  for (int e = 0; e < n; ++e) s = __dadd_rn(s, tmp[e]);
+  double t = lane < n ? tmp[lane] : 0.0;
+  for (int b = 0; b < n; b += 32) {
+    const int nb = b + 32 + lane;
+    const double tn = nb < n ? tmp[nb] : 0.0;
+    const int m = n - b < 32 ? n - b : 32;
+    if (m == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) s = __dadd_rn(s, __shfl_sync(0xffffffffu, t, j));
+    } else {
+      for (int j = 0; j < m; ++j) s = __dadd_rn(s, __shfl_sync(0xffffffffu, t, j));
+    }
+    t = tn;
+  }
   return s;
 }
 
@@ -148,7 +162,7 @@ __global__ void __launch_bounds__(1024) k_em_mstep_seq(int nEc, const double *__
   __shared__ double norm;
   for (int e = threadIdx.x; e < nEc; e += blockDim.x) tmp[e] = __ddiv_rn(rc[e], (double)len[e]);
   __syncthreads();
-  if (threadIdx.x == 0) norm = seq_sum(tmp, nEc);
+  if (threadIdx.x < 32) { const double v = seq_sum(tmp, nEc); if (threadIdx.x == 0) norm = v; }
   __syncthreads();
   const double nrm = norm;
   for (int e = threadIdx.x; e < nEc; e += blockDim.x) xNext[e] = __ddiv_rn(tmp[e], nrm);
@@ -164,17 +178,12 @@ __global__ void __launch_bounds__(1024) k_em_squarem_seq(int nEc, const double *
     tmpR[e] = __dmul_rn(r, r); tmpV[e] = __dmul_rn(v, v);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const double sr = seq_sum(tmpR, nEc);
-    sAlpha = sr;
-  }
-  if (threadIdx.x == 32) {
-    const double sv = seq_sum(tmpV, nEc);
-    tmpV[0] = sv;              // tmpV is dead after this sum
-  }
+  __shared__ double sSv;
+  if (threadIdx.x < 32) { const double sr = seq_sum(tmpR, nEc); if (threadIdx.x == 0) sAlpha = sr; }
+  else if (threadIdx.x < 64) { const double sv = seq_sum(tmpV, nEc); if (threadIdx.x == 32) sSv = sv; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const double sr = sAlpha, sv = tmpV[0];
+    const double sr = sAlpha, sv = sSv;
     double alpha = sv == 0 ? -1.0 : __ddiv_rn(-sqrt(sr), sqrt(sv));
     if (minAlpha < 0 && alpha < minAlpha) alpha = minAlpha;
     sAlpha = alpha;
@@ -193,7 +202,7 @@ __global__ void __launch_bounds__(1024) k_em_advance_seq(int nEc, double *__rest
                                                           double *__restrict__ tmp, double *__restrict__ diffOut) {
   for (int e = threadIdx.x; e < nEc; e += blockDim.x) { tmp[e] = fabs(__dsub_rn(x1[e], x0[e])); x0[e] = x1[e]; }
   __syncthreads();
-  if (threadIdx.x == 0) *diffOut = seq_sum(tmp, nEc);
+  if (threadIdx.x < 32) { const double v = seq_sum(tmp, nEc); if (threadIdx.x == 0) *diffOut = v; }
 }
 
 }  // namespace t1k
