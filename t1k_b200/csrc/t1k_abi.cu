@@ -1292,6 +1292,46 @@ int allgather_blobs(T1KRef *ref, T1KComm *comm, const uint8_t *mine, uint64_t my
   return T1K_OK;
 }
 
+// The same all-gather for COMPACT partitions that the device tail consumes where they land: the blobs stay in `dBuf`
+// (blob r at r * stride); only their heads ([nG, nE], ptr, first, count) are copied to pinned memory `recv` (head r at
+// headOff[r], headBytes[r] bytes).
+int allgather_blobs_dev(T1KRef *ref, T1KComm *comm, const uint8_t *mine, uint64_t myBytes, DevMem &dBuf, PinnedMem &recv, uint64_t &stride,
+                        std::vector<uint64_t> &sizes, std::vector<uint64_t> &headOff, std::vector<uint64_t> &headBytes) {
+  cudaStream_t st = ref->stream;
+  const int W = comm->world;
+  DevMem dSizes;
+  CK(dSizes.alloc((size_t)W * 8));
+  CK(cudaMemcpyAsync(dSizes.as<uint64_t>() + comm->rank, &myBytes, 8, cudaMemcpyHostToDevice, st));
+  NK(nccl().AllGather(dSizes.as<uint64_t>() + comm->rank, dSizes.p, 1, NCCL_UINT64, comm->comm, st));
+  sizes.assign(W, 0);
+  CK(cudaMemcpyAsync(sizes.data(), dSizes.p, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  uint64_t mx = 16;
+  for (int r = 0; r < W; ++r) mx = std::max(mx, sizes[r]);
+  mx = (mx + 15) & ~15ull;
+  stride = mx;
+  CK(dBuf.alloc((size_t)W * mx));
+  uint8_t *slot = dBuf.as<uint8_t>() + (size_t)comm->rank * mx;
+  if (myBytes) CK(cudaMemcpyAsync(slot, mine, myBytes, cudaMemcpyHostToDevice, st));
+  NK(nccl().AllGather(slot, dBuf.p, mx, NCCL_UINT8, comm->comm, st));
+  std::vector<uint64_t> hdr((size_t)W * 2, 0);
+  for (int r = 0; r < W; ++r)
+    if (sizes[r] >= 16) CK(cudaMemcpyAsync(&hdr[(size_t)r * 2], dBuf.as<uint8_t>() + (size_t)r * mx, 16, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  headOff.assign(W, 0); headBytes.assign(W, 0);
+  uint64_t tot = 0;
+  for (int r = 0; r < W; ++r) {
+    const uint64_t want = 16 + (hdr[(size_t)r * 2] + 1) * 8 + hdr[(size_t)r * 2] * 16;
+    headBytes[r] = std::min<uint64_t>(want, sizes[r]);
+    headOff[r] = tot; tot += (headBytes[r] + 15) & ~15ull;
+  }
+  CK(recv.grow(std::max<size_t>(tot, 16), 0));
+  for (int r = 0; r < W; ++r)
+    if (headBytes[r]) CK(cudaMemcpyAsync(recv.as<uint8_t>() + headOff[r], dBuf.as<uint8_t>() + (size_t)r * mx, headBytes[r], cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return T1K_OK;
+}
+
 // every rank contributes `n` words; all[r * n + i] = word i of rank r
 int allgather_u64(T1KRef *ref, T1KComm *comm, const uint64_t *mine, int n, std::vector<uint64_t> &all) {
   cudaStream_t st = ref->stream;
@@ -1354,7 +1394,7 @@ int device_tail_classes(T1KRef *ref, const GroupsView &G, int32_t nA, int thread
   // allele ids of the entries: the compact form has them as they are; a full table is read once
   PhaseTimer pt;
   const int32_t *hAllele = G.allele;
-  if (!hAllele) {
+  if (!hAllele && !G.dAllele) {
     CK(ref->pinIds.ensure((size_t)std::max<int64_t>(nE, 1) * 4));      // (pinned: the upload is a DMA at link speed)
     int32_t *ids = ref->pinIds.as<int32_t>();
     if (threads < 1 || (size_t)nE < par_min_entries()) threads = 1;
@@ -1364,16 +1404,17 @@ int device_tail_classes(T1KRef *ref, const GroupsView &G, int32_t nA, int thread
   }
   pt.lap("  tail: allele ids");
   const int32_t W = (n + 63) / 64;
-  CK(T.gPtr.alloc(((size_t)n + 1) * 8)); CK(T.gAllele.alloc((size_t)std::max<int64_t>(nE, 1) * 4));
+  CK(T.gPtr.alloc(((size_t)n + 1) * 8));
+  if (!G.dAllele) CK(T.gAllele.alloc((size_t)std::max<int64_t>(nE, 1) * 4));
   CK(T.bits.alloc((size_t)nA * std::max(W, 1) * 8));
   CK(T.fp.alloc((size_t)nA * 4)); CK(T.rowHash.alloc((size_t)nA * 8)); CK(T.listLen.alloc((size_t)nA * 4)); CK(T.differ.alloc(4));
   CK(cudaMemcpyAsync(T.gPtr.p, G.ptr, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
-  if (nE) CK(cudaMemcpyAsync(T.gAllele.p, hAllele, (size_t)nE * 4, cudaMemcpyHostToDevice, st));
+  if (nE && !G.dAllele) CK(cudaMemcpyAsync(T.gAllele.p, hAllele, (size_t)nE * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(T.bits.p, 0, (size_t)nA * std::max(W, 1) * 8, st));
   CK(cudaMemsetAsync(T.differ.p, 0, 4, st));
   TailParams &P = T.P;
   memset(&P, 0, sizeof(P));
-  P.nGroups = n; P.nAlleles = nA; P.gPtr = T.gPtr.as<int64_t>(); P.gAllele = T.gAllele.as<int32_t>();
+  P.nGroups = n; P.nAlleles = nA; P.gPtr = T.gPtr.as<int64_t>(); P.gAllele = G.dAllele ? G.dAllele : T.gAllele.as<int32_t>();
   P.bits = T.bits.as<u64>(); P.wordsPerRow = std::max(W, 1);
   P.fp = T.fp.as<int32_t>(); P.rowHash = T.rowHash.as<u64>(); P.listLen = T.listLen.as<int32_t>();
   k_tail_bits<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(P);
@@ -1694,7 +1735,8 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   // partitions are all-gathered and interleaved by the fragment that created each group = the single-process order.
   uint64_t nAssignAll = res->n_assignments;
   CompactGroups compactGroups;
-  bool useCompact = false;
+  bool useCompact = false, compactOnDevice = false;
+  DevMem dBlobs, dGPtr, dGAllele;     // read-sharded run: merged partitions / assembled (ptr, allele ids) resident on the device
   std::vector<int32_t> spans;       // N4: covered range of every allele over the coalesced groups
   if (comm) {
     double tx = now_ms();
@@ -1755,9 +1797,34 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     for (int r = 0; r < W; ++r) if (allSt[r]) return fail(T1K_ERR_NCCL, "malformed read-group table on rank " + std::to_string(r));
     uint64_t stride2 = 0;
     std::vector<uint64_t> sizes2;
+    const bool devAssemble = compact && getenv("T1K_HOST_TAIL") == nullptr;
+    if (devAssemble) {
+      // the merged partitions stay in HBM: the host sees their heads, the allele runs are gathered into the global order on the device
+      std::vector<uint64_t> headOff, headBytes, blobBase((size_t)W);
+      if (int rc = allgather_blobs_dev(ref, comm, ref->pinSend.as<uint8_t>(), partBytes, dBlobs, ref->pinRecv2, stride2, sizes2, headOff, headBytes)) return rc;
+      px.lap("exchange: all-gather merged");
+      std::vector<const uint8_t *> heads((size_t)W);
+      for (int r = 0; r < W; ++r) { heads[r] = ref->pinRecv2.as<uint8_t>() + headOff[r]; blobBase[r] = (uint64_t)r * stride2; }
+      std::vector<int64_t> srcOff;
+      if (!assemble_compact_heads(heads, headBytes, sizes2, blobBase, compactGroups, srcOff)) return fail(T1K_ERR_NCCL, "malformed merged partition from a peer");
+      const int32_t nG = (int32_t)compactGroups.ptr.size() - 1;
+      const int64_t nE = compactGroups.ptr[nG];
+      DevMem dSrc;
+      CK(dSrc.alloc((size_t)std::max(nG, 1) * 8)); CK(dGPtr.alloc(((size_t)nG + 1) * 8)); CK(dGAllele.alloc((size_t)std::max<int64_t>(nE, 1) * 4));
+      CK(cudaMemcpyAsync(dSrc.p, srcOff.data(), (size_t)nG * 8, cudaMemcpyHostToDevice, ref->stream));
+      CK(cudaMemcpyAsync(dGPtr.p, compactGroups.ptr.data(), ((size_t)nG + 1) * 8, cudaMemcpyHostToDevice, ref->stream));
+      if (nG) k_tail_gather<<<(unsigned)(((size_t)nG * 32 + 255) / 256), 256, 0, ref->stream>>>(dBlobs.as<uint8_t>(), dSrc.as<int64_t>(), dGPtr.as<int64_t>(), nG, dGAllele.as<int32_t>());
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(ref->stream));
+      dBlobs.release();
+      useCompact = true; compactOnDevice = true;
+      groups.assignedFragments = assignedAll;
+    } else {
     if (int rc = allgather_blobs(ref, comm, ref->pinSend.as<uint8_t>(), partBytes, ref->pinRecv2, stride2, sizes2)) return rc;
     px.lap("exchange: all-gather merged");
-    if (compact) {
+    }
+    if (devAssemble) {
+    } else if (compact) {
       std::vector<const uint8_t *> blobs((size_t)W);
       for (int r = 0; r < W; ++r) blobs[r] = ref->pinRecv2.as<uint8_t>() + (size_t)r * stride2;
       if (!assemble_compact(blobs, sizes2, T, compactGroups)) return fail(T1K_ERR_NCCL, "malformed merged partition from a peer");
@@ -1793,7 +1860,8 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   }
   res->assigned_fragments = (int32_t)groups.assignedFragments;
   // Genotyper::GetAverageReadAssignmentCnt (Genotyper.hpp:941-955) averages over the coalesced read groups
-  const GroupsView GV = useCompact ? compactGroups.view() : view_of(groups);
+  GroupsView GV = useCompact ? compactGroups.view() : view_of(groups);
+  if (compactOnDevice) { GV.allele = nullptr; GV.dAllele = dGAllele.as<int32_t>(); }
   res->avg_alleles_per_read = GV.n ? (double)GV.entries() / (double)GV.n : 0.0;
   res->n_assignments = nAssignAll;
   // ---- FinalizeReadAssignments: equivalence classes + missing coverage
@@ -1805,7 +1873,14 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
   if (getenv("T1K_HOST_TAIL") == nullptr && GV.n > 0) {
     if (int rc = device_tail_classes(ref, GV, nA, shards.threads(), tail, EC, &tailOnDevice)) return rc;
   }
-  if (!tailOnDevice) { EC = EquivalenceClasses(); EC.build(GV, nA, shards.threads()); }
+  if (!tailOnDevice) {
+    if (compactOnDevice) {           // the host path needs the allele ids after all
+      compactGroups.allele.resize((size_t)std::max<int64_t>(GV.entries(), 1));
+      CK(cudaMemcpy(compactGroups.allele.data(), dGAllele.p, (size_t)GV.entries() * 4, cudaMemcpyDeviceToHost));
+      GV.allele = compactGroups.allele.data(); GV.dAllele = nullptr;
+    }
+    EC = EquivalenceClasses(); EC.build(GV, nA, shards.threads());
+  }
   pt.lap(tailOnDevice ? "equivalence classes (device)" : "equivalence classes");
   res->n_groups = GV.n; res->n_ec = EC.size(); res->n_alleles = nA;
   if (res->missing_coverage) { if (int rc = t1k_missing_coverage(ref, res->missing_coverage)) return rc; }

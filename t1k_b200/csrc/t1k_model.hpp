@@ -98,6 +98,8 @@ struct GroupsView {
   const HostEntry *ent = nullptr;      // full table ...
   const int32_t *allele = nullptr;     // ... or compact: allele ids
   const double *count = nullptr;       //                  and counts
+  const int32_t *dAllele = nullptr;    // ... or compact with the allele ids resident on the DEVICE (allele == NULL then; host code
+                                       // that needs the ids falls back to fetching them)
   int64_t entries() const { return n > 0 ? ptr[n] : 0; }
   int32_t allele_at(int64_t k) const { return ent ? ent[k].alleleIdx : allele[k]; }
   double count_of(int32_t g) const {
@@ -573,6 +575,41 @@ inline bool assemble_compact(const std::vector<const uint8_t *> &blobs, const st
       if (e > b) memcpy(out.allele.data() + out.ptr[k], v.al + b, (size_t)(e - b) * 4);
     }
   });
+  return true;
+}
+
+// The same for partitions that stay on the device: heads[r] = the start of rank r's compact blob up to (not including) its
+// allele ids ([nG, nE], ptr, first, count — all the host needs), blobBase[r] = the blob's byte offset in the device buffer.
+// out.ptr / out.count as assemble_compact gives them, out.allele stays empty; srcOff[k] = byte offset of group k's allele run.
+inline bool assemble_compact_heads(const std::vector<const uint8_t *> &heads, const std::vector<uint64_t> &headBytes, const std::vector<uint64_t> &blobBytes,
+                                   const std::vector<uint64_t> &blobBase, CompactGroups &out, std::vector<int64_t> &srcOff) {
+  struct Ref { int64_t first; uint32_t r; uint32_t g; };
+  struct View { uint64_t nG, nE; const int64_t *ptr, *first; const double *cnt; uint64_t alOff; };
+  std::vector<View> V(heads.size());
+  std::vector<Ref> order;
+  for (size_t r = 0; r < heads.size(); ++r) {
+    if (headBytes[r] < 16) return false;
+    uint64_t hdr[2]; memcpy(hdr, heads[r], 16);
+    View &v = V[r];
+    v.nG = hdr[0]; v.nE = hdr[1];
+    v.alOff = 16 + (v.nG + 1) * 8 + v.nG * 16;
+    if (headBytes[r] < v.alOff || blobBytes[r] < v.alOff + v.nE * 4) return false;
+    v.ptr = (const int64_t *)(heads[r] + 16); v.first = v.ptr + v.nG + 1; v.cnt = (const double *)(v.first + v.nG);
+    for (uint64_t g = 0; g < v.nG; ++g) {
+      if (v.ptr[g] < 0 || v.ptr[g + 1] < v.ptr[g] || (uint64_t)v.ptr[g + 1] > v.nE) return false;
+      order.push_back(Ref{v.first[g], (uint32_t)r, (uint32_t)g});
+    }
+  }
+  std::sort(order.begin(), order.end(), [](const Ref &a, const Ref &b) { return a.first < b.first; });
+  const size_t nG = order.size();
+  out.ptr.assign(nG + 1, 0); out.count.resize(nG); out.allele.clear();
+  srcOff.resize(nG);
+  for (size_t k = 0; k < nG; ++k) {
+    const View &v = V[order[k].r];
+    out.ptr[k + 1] = out.ptr[k] + (v.ptr[order[k].g + 1] - v.ptr[order[k].g]);
+    out.count[k] = v.cnt[order[k].g];
+    srcOff[k] = (int64_t)(blobBase[order[k].r] + v.alOff + (uint64_t)v.ptr[order[k].g] * 4);
+  }
   return true;
 }
 

@@ -138,6 +138,16 @@ __global__ void k_tail_colfill(TailParams P) {
   }
 }
 
+// allele runs of the merged partitions (as the all-gather left them in HBM) into the global first-appearance order:
+// group k's run starts at byte srcOff[k] of `blobs` and goes to dst[dstPtr[k] .. dstPtr[k + 1])
+__global__ void k_tail_gather(const uint8_t *blobs, const int64_t *srcOff, const int64_t *dstPtr, int nGroups, int32_t *dst) {
+  const int g = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (g >= nGroups) return;
+  const int32_t *src = reinterpret_cast<const int32_t *>(blobs + srcOff[g]);
+  const int64_t b = dstPtr[g], n = dstPtr[g + 1] - b;
+  for (int64_t k = lane; k < n; k += 32) dst[b + k] = src[k];
+}
+
 // out[0..n] = exclusive scan of len[0..n) (one block)
 __global__ void __launch_bounds__(1024) k_scan_i64(const int64_t *len, int n, int64_t *out) {
   __shared__ int64_t warpSum[32];
