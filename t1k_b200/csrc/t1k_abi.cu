@@ -1882,6 +1882,7 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
     EC = EquivalenceClasses(); EC.build(GV, nA, shards.threads());
   }
   pt.lap(tailOnDevice ? "equivalence classes (device)" : "equivalence classes");
+  if (tailOnDevice) res->n_launches += 3;
   res->n_groups = GV.n; res->n_ec = EC.size(); res->n_alleles = nA;
   if (res->missing_coverage) { if (int rc = t1k_missing_coverage(ref, res->missing_coverage)) return rc; }
   pt.lap("missing coverage");
@@ -1903,6 +1904,7 @@ int t1k_genotype(T1KRef *ref, const char *reads1, const char *reads2, uint32_t s
       if (int rc = device_tail_matrix(ref, tail, EC, nA, comm, emDev)) return rc;
       in.build_vectors(GV, EC, prm->effective_len, prm->seq_weight, shards.threads());
       in.rowPtr.swap(tail.hRowPtr);
+      res->n_launches += 6;
     } else in.build(GV, EC, prm->effective_len, prm->seq_weight, shards.threads());
     pt.lap(tailOnDevice ? "EM inputs (device)" : "EM inputs");
     if (pt.on) fprintf(stderr, "[t1k timing] groups %d entries %lld ECs %d nnz %lld\n", GV.n, (long long)GV.entries(), EC.size(), (long long)in.rowPtr[GV.n]);

@@ -456,7 +456,7 @@ inline void transpose_csr(const int64_t *rowPtr, int32_t nRows, ColOf colOf, int
   (void)k0;
 }
 
-// ---- The same merge with the work divided over the ranks (opt-in, T1K_MERGE_PARTITIONED): rank r merges only the hash
+// ---- The same merge with the work divided over the ranks (the default of a read-sharded run): rank r merges only the hash
 // partitions it owns (partition space = world x T; thread t of rank r takes partition r*T + t) from every rank's table,
 // the ranks exchange their merged partitions, and assemble_partitions() interleaves them by the creating fragment.
 // Every group is still merged by exactly one thread in rank order, so the result equals merge_tables_parallel's; the

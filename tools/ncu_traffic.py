@@ -9,7 +9,7 @@ import json
 import os
 import sys
 
-GROUPS = {"k_assign": ("k_seed", "k_deferred", "k_passes", "k_align"), "k_pair": ("k_pair",), "k_em": ("k_em_",)}
+GROUPS = {"k_assign": ("k_seed", "k_deferred", "k_defer_", "k_passes", "k_align"), "k_pair": ("k_pair",), "k_em": ("k_em_",)}
 
 
 def main():
