@@ -234,6 +234,18 @@ void t1k_filter_destroy(T1KFilter *f);
 int t1k_filter_batch(T1KFilter *f, const char *bases, const uint64_t *off, const uint32_t *len, uint32_t n_reads,
                      uint8_t *good, T1KFilterStats *stats);
 
+/* ---- reads into memory as Genotyper.cpp:363-454 gets them from ReadFiles / kseq (ReadFiles.hpp:155-204):
+ * FASTA or FASTQ, plain or gzip; path2 == NULL for single-end.  Sequences only, exactly as they stand in the files (kseq's record
+ * grammar, see csrc/t1k_reads.hpp), laid out as the fixed-stride NUL-padded buffers t1k_genotype takes (stride = longest read + 1;
+ * page-locked when a CUDA device is present so that the chunk uploads are DMAs).  Host-side; needs no device. */
+typedef struct {
+  char *reads1, *reads2;       /* [n_frag * stride]; reads2 NULL for single-end */
+  uint32_t stride, n_frag, max_len;
+  int32_t pinned;              /* internal: how the buffers were allocated */
+} T1KReads;
+int t1k_reads_load(const char *path1, const char *path2, T1KReads *out);
+void t1k_reads_free(T1KReads *r);
+
 /* ---- the analyzer, second caller of the boundary (Analyzer.cpp:467-669).  It calls AssignRead with weight 0
  * (t1k_assign_batch above), pairs on the host over the fetched records, and after the EM asks for the edit string of every
  * overlap it kept: SeqSet::AddFragmentAlignmentInfo -> AddOverlapAlignmentInfo (SeqSet.hpp:2757-2778, 2657-2680) =

@@ -9,6 +9,7 @@
 //   assign    SeqSet::AssignRead                    (/root/reference/SeqSet.hpp:2119-2303)
 //   alninfo   AssignRead with weight 0 (the analyzer's call, Analyzer.cpp:142,476) followed by
 //             SeqSet::AddOverlapAlignmentInfo          (/root/reference/SeqSet.hpp:2657-2680) on every record
+//   reads     ReadFiles::AddReadFile / Next (the kseq reader of /root/reference/ReadFiles.hpp:86-204): one sequence per line
 //   genotype  the Genotyper.cpp:450-646 flow        (AssignRead -> ReadAssignmentToFragmentAssignment
 //             -> SetReadAssignments -> CoalesceReadAssignments -> FinalizeReadAssignments
 //             -> QuantifyAlleleEquivalentClass), dumping every boundary the C ABI exposes.
@@ -183,6 +184,16 @@ static int mode_alninfo(int argc, char **argv)
 	return 0;
 }
 
+static int mode_reads(int argc, char **argv)
+{
+	if (argc < 3) die("reads: need a file");
+	ReadFiles reads;
+	reads.AddReadFile(argv[2], false);
+	while (reads.Next())
+		printf("%s\n", reads.seq);
+	return 0;
+}
+
 struct Rd { std::string seq; int mate, idx, info; bool hasN; };
 static bool rd_lt(const Rd &a, const Rd &b) { return strcmp(a.seq.c_str(), b.seq.c_str()) < 0; }
 
@@ -306,6 +317,7 @@ int main(int argc, char **argv)
 	if (m == "align") return mode_align(argc, argv);
 	if (m == "assign") return mode_assign(argc, argv);
 	if (m == "alninfo") return mode_alninfo(argc, argv);
+	if (m == "reads") return mode_reads(argc, argv);
 	if (m == "genotype") return mode_genotype(argc, argv);
 	die("unknown mode");
 	return 2;

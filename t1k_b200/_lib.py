@@ -28,7 +28,7 @@ EXPORTS = ["t1k_last_error", "t1k_device_count", "t1k_ref_create", "t1k_ref_dest
            "t1k_coverage_allreduce", "t1k_groups_create", "t1k_groups_destroy", "t1k_groups_add_fragments",
            "t1k_groups_serialize", "t1k_groups_merge", "t1k_groups_fetch", "t1k_em_partition",
            "t1k_filter_create", "t1k_filter_destroy", "t1k_filter_batch", "t1k_align_info_batch", "t1k_dpx_peak", "t1k_groups_ec_filter",
-           "t1k_assign_batch_async", "t1k_assign_wait", "t1k_pinned_alloc", "t1k_pinned_free"]
+           "t1k_assign_batch_async", "t1k_assign_wait", "t1k_pinned_alloc", "t1k_pinned_free", "t1k_reads_load", "t1k_reads_free"]
 
 UNIQUE_ID_BYTES = 128
 
@@ -84,6 +84,11 @@ class FilterStats(C.Structure):
 
 class AlignInfoStats(C.Structure):
     _fields_ = [("n_diagonal", C.c_uint64), ("n_dp", C.c_uint64), ("dp_cells", C.c_uint64), ("ms_kernel", C.c_float)]
+
+
+class Reads(C.Structure):
+    _fields_ = [("reads1", C.c_void_p), ("reads2", C.c_void_p), ("stride", C.c_uint32), ("n_frag", C.c_uint32), ("max_len", C.c_uint32),
+                ("pinned", C.c_int32)]
 
 
 class AssignStats(C.Structure):
@@ -155,6 +160,9 @@ def lib():
         L.t1k_align_info_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                            C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(AlignInfoStats)]
         L.t1k_dpx_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
+        L.t1k_reads_load.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Reads)]
+        L.t1k_reads_free.argtypes = [C.POINTER(Reads)]
+        L.t1k_reads_free.restype = None
         _lib = L
     return _lib
 

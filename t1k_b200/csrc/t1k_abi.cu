@@ -20,6 +20,7 @@
 #include "t1k_kernels.cuh"
 #include "t1k_model.hpp"
 #include "t1k_pair.cuh"
+#include "t1k_reads.hpp"
 #include "t1k_filter.cuh"
 #include "t1k_alninfo.cuh"
 #include "t1k_ingest.cuh"
@@ -1186,6 +1187,45 @@ int t1k_coverage_allreduce(T1KRef *ref, T1KComm *comm) {
   CK(cudaStreamSynchronize(ref->stream));
   ref->covDirty = true;
   return T1K_OK;
+}
+
+int t1k_reads_load(const char *path1, const char *path2, T1KReads *out) {
+  if (!path1 || !out) return fail(T1K_ERR_ARG, "t1k_reads_load: bad argument");
+  memset(out, 0, sizeof(*out));
+  LoadedReads R;
+  std::string err;
+  if (load_reads(path1, path2, T1K_MAX_READ_LEN, R, err)) return fail(T1K_ERR_ARG, "t1k_reads_load: " + err);
+  const uint32_t n = (uint32_t)(R.off[0].size() - 1), stride = R.maxLen + 1;
+  const int mates = path2 ? 2 : 1;
+  int nDev = 0;
+  const bool pin = cudaGetDeviceCount(&nDev) == cudaSuccess && nDev > 0;
+  if (!pin) cudaGetLastError();
+  char *buf[2] = {nullptr, nullptr};
+  const size_t bytes = std::max<size_t>((size_t)n * stride, 16);
+  for (int m = 0; m < mates; ++m) {
+    if (pin) { if (cudaMallocHost((void **)&buf[m], bytes) != cudaSuccess) { cudaGetLastError(); buf[m] = nullptr; } }
+    else buf[m] = (char *)malloc(bytes);
+    if (!buf[m]) { for (int k = 0; k < m; ++k) { if (pin) cudaFreeHost(buf[k]); else free(buf[k]); } return fail(T1K_ERR_ARG, "t1k_reads_load: out of host memory"); }
+  }
+  const int T = n < 4096 ? 1 : (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+  run_threads(T, [&](int t) {
+    for (int m = 0; m < mates; ++m)
+      for (size_t i = (size_t)n * t / T; i < (size_t)n * (t + 1) / T; ++i) {
+        const size_t len = (size_t)(R.off[m][i + 1] - R.off[m][i]);
+        char *dst = buf[m] + i * stride;
+        memcpy(dst, R.bases[m].data() + R.off[m][i], len);
+        memset(dst + len, 0, stride - len);
+      }
+  });
+  out->reads1 = buf[0]; out->reads2 = buf[1]; out->stride = stride; out->n_frag = n; out->max_len = R.maxLen; out->pinned = pin ? 1 : 0;
+  return T1K_OK;
+}
+
+void t1k_reads_free(T1KReads *r) {
+  if (!r) return;
+  if (r->pinned) { if (r->reads1) cudaFreeHost(r->reads1); if (r->reads2) cudaFreeHost(r->reads2); }
+  else { free(r->reads1); free(r->reads2); }
+  r->reads1 = r->reads2 = nullptr; r->n_frag = 0;
 }
 
 int t1k_groups_create(T1KGroups **out) {
