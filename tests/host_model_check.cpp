@@ -228,6 +228,54 @@ extern "C" int host_model_check(int seed, int nFrag, int nAlleles, int nSets) {
         if (!assemble_partitions(pv2, T, asm2)) return 21;
         asm2.assignedFragments = full.assignedFragments;
         if (!same_groups(asm2, full)) return 22;
+        // compact form of the second exchange: the host assembly, and the heads-only assembly of the device path (the allele
+        // runs gathered from the blobs by their byte offsets, as k_tail_gather does) give the full table's ids / counts
+        {
+          std::vector<ReadGroups> mine(W);
+          std::vector<std::vector<uint8_t> > cb(W);
+          std::vector<const uint8_t *> blobs(W), heads(W);
+          std::vector<uint64_t> bytes(W), headBytes(W), base(W);
+          std::vector<uint8_t> all;
+          for (int r = 0; r < W; ++r) {
+            std::vector<GroupBlobView> in(W);
+            for (int q = 0; q < W; ++q) {
+              size_t at = 0;
+              for (int z = 0; z < r; ++z) at += plans[q].bytes[z];
+              if (!in[q].parse(sendBuf[q].data() + at, plans[q].bytes[r])) return 30;
+            }
+            if (!merge_tables_partition(in, fb3, r, W, T, mine[r])) return 31;
+            cb[r].assign(compact_group_bytes(mine[r]), 0);
+            serialize_compact(mine[r], cb[r].data(), T);
+            base[r] = all.size();
+            all.insert(all.end(), cb[r].begin(), cb[r].end());
+            bytes[r] = cb[r].size();
+            headBytes[r] = 16 + ((uint64_t)mine[r].size() + 1) * 8 + (uint64_t)mine[r].size() * 16;
+          }
+          for (int r = 0; r < W; ++r) { blobs[r] = cb[r].data(); heads[r] = all.data() + base[r]; }
+          CompactGroups c1, c2;
+          std::vector<int64_t> srcOff;
+          if (!assemble_compact(blobs, bytes, T, c1)) return 32;
+          if (!assemble_compact_heads(heads, headBytes, bytes, base, c2, srcOff)) return 33;
+          if (!same_vec(c1.ptr, full.ptr) || !same_vec(c2.ptr, full.ptr) || !same_vec(c1.count, c2.count)) return 34;
+          const GroupsView fv = view_of(full);
+          for (int32_t g = 0; g < full.size(); ++g) {
+            if (c1.count[g] != fv.count_of(g)) return 35;
+            for (int64_t k = full.ptr[g]; k < full.ptr[g + 1]; ++k) {
+              int32_t fromBlob;
+              memcpy(&fromBlob, all.data() + srcOff[g] + (size_t)(k - full.ptr[g]) * 4, 4);
+              if (c1.allele[k] != full.ent[k].alleleIdx || fromBlob != full.ent[k].alleleIdx) return 36;
+            }
+          }
+        }
+        // covered ranges of the alleles (N4): threaded == serial
+        {
+          int32_t nA = 0;
+          for (size_t k = 0; k < full.ent.size(); ++k) nA = std::max(nA, full.ent[k].alleleIdx + 1);
+          std::vector<int32_t> s1, sT;
+          allele_spans(full, nA, 1, s1);
+          allele_spans(full, nA, T + 2, sT);
+          if (!same_vec(s1, sT)) return 37;
+        }
       }
     }
     // the merged table has the single-process groups in the single-process order (float32 sums may differ in the last

@@ -415,3 +415,25 @@ def test_async_assign_batches_equal_the_synchronous_calls():
         bad.wait()
     ok = ss2.AssignReadAsync(uniq[:4], w[:4]).wait().fetch()        # the queue keeps working after a failed job
     assert np.array_equal(ok[2], want[0][2][:len(ok[2])])
+
+
+@pytest.mark.parametrize("switch", ["T1K_HOST_DEDUP", "T1K_HOST_TAIL", "T1K_SYNC_ROWS", "T1K_EM_NO_GRAPH"])
+def test_device_stages_equal_their_host_counterparts(workload, switch, monkeypatch):
+    """The stages that moved to the device this round keep an A/B switch back to the host code: read-end de-duplication
+    (ingest kernels vs unique_read_ends), the global tail (bit-matrix equivalence classes + EM matrix vs EquivalenceClasses /
+    EmInputs), the copy-stream hand-over of the fragment rows, the CUDA graph of the SQUAREM iteration.  Every output of the whole
+    flow must be identical either way (the EM runs in reference order, so abundances too)."""
+    wl = workload
+    res = []
+    for on in (False, True):
+        if on:
+            monkeypatch.setenv(switch, "1")
+        else:
+            monkeypatch.delenv(switch, raising=False)
+        monkeypatch.setenv("T1K_CHUNK_FRAGMENTS", "150")          # several chunks: the pipeline stages hand over more than once
+        res.append(Genotyper(wl["ref"], wl["sim"], wl["relax"]).Genotype(wl["r1"], wl["r2"]))
+    a, b = res
+    for k in ("equivalent_class", "missing_coverage", "fragment_assigned", "abundance", "ec_abundance", "allele_kept", "allele_span"):
+        assert np.array_equal(a[k], b[k]), (switch, k)
+    for k in ("em_iterations", "n_groups", "n_ec", "assigned_fragments", "n_unique_ends", "n_overlaps", "n_assignments", "em_nnz"):
+        assert a[k] == b[k], (switch, k)
