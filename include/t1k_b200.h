@@ -92,7 +92,7 @@ int t1k_assignment_fetch(T1KAssignment *a, uint64_t *row_ptr, int32_t *ret, T1KO
 /* Work counters of one t1k_assign_batch call, for roofline accounting (no reference counterpart). */
 typedef struct {
   uint64_t postings, candidates, tiles, records;   /* postings read, seed overlaps chained, allele tiles, records kept */
-  float ms_kernel;                                 /* device time of k_assign (CUDA events) */
+  float ms_kernel;                                 /* device time of the AssignRead kernels (CUDA events) */
   int32_t grid_blocks, hit_cap, n_sm;              /* launch geometry */
 } T1KAssignStats;
 int t1k_assignment_stats(const T1KAssignment *a, T1KAssignStats *out);
@@ -183,7 +183,7 @@ typedef struct {
   uint64_t n_unique_ends, n_overlaps, n_assignments;
   double avg_alleles_per_read;        /* Genotyper::GetAverageReadAssignmentCnt: over read groups */
   float ms_dedup, ms_align, ms_pair, ms_coalesce, ms_em;   /* wall time of the phases of this call (host clock) */
-  float ms_align_kernel, ms_pair_kernel, ms_em_kernel;      /* device time (CUDA events) inside k_assign / k_pair / the EM kernels */
+  float ms_align_kernel, ms_pair_kernel, ms_em_kernel;      /* device time (CUDA events) inside the AssignRead kernels / k_pair / the EM kernels */
   uint64_t n_postings, n_candidates;                        /* k-mer postings read and seed overlaps chained (roofline accounting) */
   uint64_t n_launches;                                      /* kernels launched by this call */
   float ms_prep_wait;                                       /* part of ms_dedup the device stage had to wait for (not overlapped) */

@@ -1,6 +1,8 @@
-// sm_100a kernels of the alignment path: read packing, the persistent warp-per-read-end assignment kernel
-// (seed selection -> allele-tile gather -> lane-per-allele chaining/rescoring -> extension -> full-read
-// alignment + coverage -> ordered compaction into the HBM-resident overlap store) and coverage finalisation.
+// sm_100a kernels of the alignment path: read packing and SeqSet::AssignRead as rounds of kernels over a slice of the batch —
+// k_seed (persistent, warp per read-end: seed selection, sweep over the allele tiles of the index, lane-per-allele mismatch-mask
+// evaluation, candidates into the warp's arena), k_defer_group / k_deferred / k_defer_copy (alleles that need real gap or
+// overhang alignments, distinct ones compacted), k_passes (the ordered scan, inclusion, > 1000 cut, records into the
+// HBM-resident overlap store), k_align / k_align_dp (full-read alignments: certificates, band DP, coverage).
 #pragma once
 #include <cuda_runtime.h>
 

@@ -1,6 +1,6 @@
 // Fragment pairing on the device: SeqSet::ReadAssignmentToFragmentAssignment (SeqSet.hpp:2310-2655) followed by
 // Genotyper::SetReadAssignments (Genotyper.hpp:778-832) and Genotyper::ReadAssignmentWeight (Genotyper.hpp:205-230),
-// one warp per fragment, reading the HBM-resident per-read-end record lists that k_assign left behind.
+// one warp per fragment, reading the HBM-resident per-read-end record lists that the AssignRead kernels (k_passes) left behind.
 //
 // The record lists are stored in allele order (ties in candidate order); `key` + the record's position give the
 // reference's list order (the order AssignRead returned them in).  Nothing is materialised per (fragment, allele):
@@ -22,7 +22,7 @@ struct PairParams {
   const Rec *store;
   const u64 *readOff;
   const u32 *readCnt;
-  const u32 *readTop;       // per read-end: max matchCnt << 16 | (65535 - denominator) over its records (k_assign)
+  const u32 *readTop;       // per read-end: max matchCnt << 16 | (65535 - denominator) over its records (k_passes)
   const u32 *end1, *end2;   // end2 == NULL: single-end data
   const u8 *hasN;
   u32 fragBase, nFrag;      // fragments [fragBase, fragBase + nFrag) of the caller's arrays
